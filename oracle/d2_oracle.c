@@ -1,0 +1,490 @@
+/*
+ * d2_oracle.c -- CPU restatement (plain C) of the dashing2 sketch / cmp hot paths.
+ *
+ * TEST INFRASTRUCTURE ONLY -- see d2_oracle.h.  Citations are file:line under /root/reference.
+ * Written from the reference's *behaviour*; no reference code is included or linked.
+ *
+ * Third-party arithmetic this depends on (same as the reference): glibc libm log/logl of the host,
+ * and the constant D2O_OPH_SEED = first output of libstdc++ std::mt19937_64(0x321b919a61cb41f7).
+ */
+#include "d2_oracle.h"
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+/* ------------------------------------------------------------------------------------------ */
+/* hashes                                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Thomas Wang 64-bit mix. hash.h:42-62 */
+uint64_t d2o_wang64(uint64_t key) {
+    key = (~key) + (key << 21);
+    key ^= key >> 24;
+    key = (key + (key << 3)) + (key << 8);
+    key ^= key >> 14;
+    key = (key + (key << 2)) + (key << 4);
+    key ^= key >> 28;
+    key += key << 31;
+    return key;
+}
+
+static uint64_t modinv64(uint64_t a) { /* a odd; Newton iteration mod 2^64 */
+    uint64_t x = a;
+    for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x;
+}
+
+/* Inverse of the bijection above (any correct inverse is *the* inverse). Used by oph.h:81-83. */
+uint64_t d2o_wang64_inv(uint64_t h) {
+    h *= modinv64((1ULL << 31) + 1);
+    h ^= h >> 28; h ^= h >> 56;
+    h *= modinv64(21);
+    h ^= (h >> 14) ^ (h >> 28) ^ (h >> 42) ^ (h >> 56);
+    h *= modinv64(265);
+    h ^= (h >> 24) ^ (h >> 48);
+    /* forward: key = key*(2^21 - 1) - 1 */
+    h = (h + 1) * modinv64((1ULL << 21) - 1);
+    return h;
+}
+
+/* FRev64 = XOR c1, MUL (c2|1), ROTL 31, XOR c3. encoder.h:47; hash.h:688-709,764-826 */
+uint64_t d2o_frev64(uint64_t x) {
+    x ^= 0x533f8c2151b20f97ULL;
+    x *= (0x9a98567ed20c127dULL | 1);
+    x = (x << 31) ^ (x >> 33);
+    return x ^ 0x691a9d706391077aULL;
+}
+
+/* CEHasher = XOR c1, MUL (c2|1), XOR c3. hash.h:858 */
+uint64_t d2o_cehash(uint64_t x) {
+    x ^= 0x533f8c2151b20f97ULL;
+    x *= (0x9a98567ed20c127dULL | 1);
+    return x ^ 0x691a9d706391077aULL;
+}
+
+/* wy.h:45-59 */
+static inline uint64_t wymum(uint64_t x, uint64_t y) {
+    u128 l = (u128)x * y;
+    return (uint64_t)l ^ (uint64_t)(l >> 64);
+}
+uint64_t d2o_wyhash64(uint64_t *state) {
+    *state += 0x60bee2bee120fc15ULL;
+    return wymum(*state ^ 0xe7037ed1a0b428dbULL, *state);
+}
+
+/* kmerutil.h:83-90 : reverse the 2-bit groups, complement, right-align. */
+uint64_t d2o_revcomp(uint64_t x, int k) {
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    x = (x >> 32) | (x << 32);
+    return (~x) >> (64 - 2 * k);
+}
+
+static inline uint64_t canonical(uint64_t x, int k) { /* kmerutil.h:137-140 */
+    uint64_t rc = d2o_revcomp(x, k);
+    return x < rc ? x : rc;
+}
+
+/* src/enums.cpp:133-140 */
+uint64_t d2o_xormask_for_seed(uint64_t seed) { return seed ? d2o_wang64(seed) : 0; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* k-mer / minimizer stream                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* alphabet.h:128 DNA4 ("A,C,G,T", case-insensitive): A0 C1 G2 T3, everything else invalid.
+ * (The "U:T" alias is a no-op in the reference's table builder, alphabet.h:50-54.) */
+static inline int dna_code(unsigned char c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return -1;
+    }
+}
+
+uint64_t d2o_kmer_positions(uint64_t len, int k) { return len >= (uint64_t)k ? len - k + 1 : 0; }
+
+typedef struct { uint64_t score, el; } elscore_t;
+static inline int es_less(elscore_t a, elscore_t b) { /* qmap.h:23-25 */
+    return a.score < b.score || (a.score == b.score && a.el < b.el);
+}
+
+/* Sliding window minimum by (score, el): equivalent to QueueMap::next_value (qmap.h:79-87), which
+ * keeps the last wsz entries in a deque and reads the smallest key of an ordered multiset.
+ * Implemented as a ring buffer + linear rescan only when the minimum leaves (oracle: clarity first). */
+typedef struct {
+    elscore_t *ring; uint32_t wsz, n, head; /* n entries, oldest at head */
+} window_t;
+
+static void win_init(window_t *w, uint32_t wsz) {
+    w->ring = (elscore_t *)malloc(sizeof(elscore_t) * wsz); w->wsz = wsz; w->n = 0; w->head = 0;
+}
+static void win_reset(window_t *w) { w->n = 0; w->head = 0; }
+static elscore_t win_min(const window_t *w) {
+    elscore_t best = w->ring[w->head];
+    for (uint32_t i = 1; i < w->n; ++i) {
+        elscore_t e = w->ring[(w->head + i) % w->wsz];
+        if (es_less(e, best)) best = e;
+    }
+    return best;
+}
+/* returns 1 and sets *out when the window is full after the push */
+static int win_push(window_t *w, uint64_t el, uint64_t score, uint64_t *out) {
+    if (w->n == w->wsz) { w->head = (w->head + 1) % w->wsz; --w->n; } /* pop_front once size > wsz */
+    w->ring[(w->head + w->n) % w->wsz] = (elscore_t){score, el};
+    ++w->n;
+    if (w->n == w->wsz) { *out = win_min(w).el; return 1; }
+    return 0;
+}
+
+#define EMIT(v) do { if (nout < cap) out[nout] = d2o_wang64((v) ^ xormask); ++nout; } while (0)
+
+uint64_t d2o_hash_stream(const char *seq, uint64_t len, int k, int w, int canon, uint64_t xormask,
+                         uint64_t *out, uint64_t cap) {
+    uint64_t nout = 0;
+    const uint64_t mask = k < 32 ? ((1ULL << (2 * k)) - 1) : ~0ULL; /* rhtraits.h:52-55 */
+    const int windowed = w > k;   /* spacer.h:57 w_ = max(c_, w); unwindowed() iff w_ == k_ */
+    if (!windowed) {
+        /* encoder.h:241-272 (+ canonicalising wrapper :219-232): rolling encode, any invalid base
+         * restarts the run, so k-mers containing it are skipped. */
+        uint64_t kmer = 0; int filled = 0;
+        for (uint64_t pos = 0; pos < len; ++pos) {
+            int c = dna_code((unsigned char)seq[pos]);
+            if (c < 0) { kmer = 0; filled = 0; continue; }
+            kmer = ((kmer << 2) | (uint64_t)c) & mask;
+            if (filled < k) ++filled; /* note: reference masks only once filled==k; same value */
+            if (filled == k) {
+                uint64_t v = canon ? canonical(kmer, k) : kmer;
+                EMIT(v);
+            }
+        }
+        return nout;
+    }
+    window_t win; win_init(&win, (uint32_t)(w - k + 1)); /* encoder.h:141 qmap_(w - c + 1) */
+    if (canon) {
+        /* encoder.h:212-217,622-628,547-592: every position is (re)encoded; a k-mer holding an
+         * invalid base encodes as all-ones and canonicalises to min(~0, revcomp(~0)) = 0, so it
+         * ENTERS the window as k-mer 0. One emission per full window. */
+        if (len >= (uint64_t)k) {
+            for (uint64_t pos = 0; pos + k <= len; ++pos) {
+                uint64_t kmer = 0; int bad = 0;
+                for (int i = 0; i < k; ++i) {
+                    int c = dna_code((unsigned char)seq[pos + i]);
+                    if (c < 0) { bad = 1; break; }
+                    kmer = (kmer << 2) | (uint64_t)c;
+                }
+                if (bad) kmer = ~0ULL;
+                kmer = canonical(kmer, k);
+                uint64_t m;
+                if (win_push(&win, kmer, d2o_frev64(kmer), &m) && m != ~0ULL) EMIT(m);
+            }
+        }
+    } else {
+        /* encoder.h:274-306: rolling encode; an invalid base (or an accumulator that becomes
+         * all-ones) restarts the k-mer run but NOT the window; trailing partial window flushes once. */
+        uint64_t kmer = 0; int filled = 0; uint64_t pos = 0;
+        while (pos < len) {
+            int restart = 0;
+            while (filled < k && pos < len) {
+                int c = dna_code((unsigned char)seq[pos++]);
+                kmer <<= 2;
+                kmer |= (uint64_t)(int64_t)c; /* -1 sign-extends to all ones */
+                if (kmer == ~0ULL) { restart = 1; break; }
+                ++filled;
+            }
+            if (restart) { kmer = 0; filled = 0; continue; }
+            if (filled == k) {
+                kmer &= mask;
+                uint64_t m;
+                if (win_push(&win, kmer, d2o_frev64(kmer), &m) && m != ~0ULL) EMIT(m);
+                --filled;
+            }
+        }
+        if (win.n > 0 && win.n < win.wsz) EMIT(win_min(&win).el); /* encoder.h:304-305 */
+    }
+    (void)win_reset;
+    free(win.ring);
+    return nout;
+}
+#undef EMIT
+
+/* ------------------------------------------------------------------------------------------ */
+/* One-permutation MinHash (LazyOnePermSetSketch<uint64_t>)                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+uint32_t d2o_opmh_m(uint32_t sketchsize) { return sketchsize + (sketchsize & 1u); } /* oph.h:145 */
+
+void d2o_opmh_reset(uint64_t *regs, double *counts, uint32_t m) {
+    for (uint32_t i = 0; i < m; ++i) { regs[i] = ~0ULL; if (counts) counts[i] = 0.; }
+}
+
+/* DHasher(x) = Wang(x ^ seed_ ^ 0x533f8c2151b20f97). oph.h:44-53,55-71 */
+static inline uint64_t dhash(uint64_t x) { return d2o_wang64(x ^ D2O_OPH_SEED ^ 0x533f8c2151b20f97ULL); }
+static inline uint64_t dhash_inv(uint64_t h) { return d2o_wang64_inv(h) ^ 0x533f8c2151b20f97ULL ^ D2O_OPH_SEED; }
+
+void d2o_opmh_update(uint64_t *regs, double *counts, uint32_t m, const uint64_t *hv, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t id = dhash(hv[i]);
+        const uint32_t idx = (uint32_t)id % m; /* Schismatic<uint32_t>::mod truncates; div.h:256-262 */
+        if (regs[idx] > id) { regs[idx] = id; if (counts) counts[idx] = 1.; }
+        else if (counts) counts[idx] += (regs[idx] == id);
+    }
+}
+
+/* oph.h:188-205: a candidate is promoted once seen mincount times; per-bucket candidate multiset. */
+typedef struct { uint64_t id; uint32_t cnt; } pot_t;
+typedef struct { pot_t *v; uint32_t n, cap; } potvec_t;
+void d2o_opmh_update_mincount(uint64_t *regs, double *counts, uint32_t m, const uint64_t *hv,
+                              uint64_t n, double mincount) {
+    potvec_t *pots = (potvec_t *)calloc(m, sizeof(potvec_t));
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t id = dhash(hv[i]);
+        const uint32_t idx = (uint32_t)id % m;
+        if (regs[idx] > id) {
+            potvec_t *p = &pots[idx];
+            uint32_t j = 0;
+            for (; j < p->n; ++j) if (p->v[j].id == id) break;
+            if (j == p->n) {
+                if (p->n == p->cap) { p->cap = p->cap ? p->cap * 2 : 4; p->v = (pot_t *)realloc(p->v, p->cap * sizeof(pot_t)); }
+                p->v[p->n++] = (pot_t){id, 1};
+            } else ++p->v[j].cnt;
+            if (p->v[j].cnt >= mincount) {
+                regs[idx] = id; if (counts) counts[idx] = p->v[j].cnt;
+                uint32_t o = 0;
+                for (uint32_t t = 0; t < p->n; ++t) if (p->v[t].id < id) p->v[o++] = p->v[t];
+                p->n = o;
+            }
+        } else if (counts) counts[idx] += (regs[idx] == id);
+    }
+    for (uint32_t i = 0; i < m; ++i) free(pots[i].v);
+    free(pots);
+}
+
+double d2o_opmh_card(const uint64_t *regs, uint32_t m) {
+    long double sum = 0.L;
+    for (uint32_t i = 0; i < m; ++i) sum = sum + (long double)regs[i] * 0x1p-64L;
+    if (!sum) return INFINITY;
+    return (double)((long double)m * ((long double)m / sum));
+}
+
+void d2o_opmh_sigs(const uint64_t *regs, uint32_t m, double *out) {
+    uint64_t nempty = 0;
+    for (uint32_t i = 0; i < m; ++i) nempty += regs[i] == ~0ULL;
+    const double muld = -1.0 / (double)((uint64_t)m - nempty);
+    const long double mul = muld;
+    for (uint32_t i = 0; i < m; ++i) {
+        const uint64_t x = regs[i];
+        if (x == ~0ULL || x == 0) { out[i] = 0.; continue; }
+        const uint64_t rem = ~0ULL - x + 1;
+        out[i] = (double)(mul * logl(0x1p-64L * (long double)rem));
+    }
+}
+
+void d2o_opmh_ids(const uint64_t *regs, uint32_t m, uint64_t *out) {
+    for (uint32_t i = 0; i < m; ++i) out[i] = dhash_inv(regs[i]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Full continuous SetSketch  (CSetSketch<double>)                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+void d2o_css_reset(double *regs, uint32_t m) {
+    for (uint64_t i = 0; i < 2ULL * m - 1; ++i) regs[i] = DBL_MAX; /* setsketch.h:139-142 */
+}
+
+/* max-tree update, setsketch.h:151-166 */
+static int mvt_update(double *d, uint32_t m, uint64_t index, double x) {
+    const uint64_t sz = 2ULL * m - 1;
+    if (!(x < d[index])) return 0;
+    for (;;) {
+        d[index] = x;
+        if ((index = m + (index >> 1)) >= sz) break;
+        const uint64_t lhi = (index - m) << 1, rhi = lhi + 1;
+        x = d[lhi] > d[rhi] ? d[lhi] : d[rhi];
+        if (x >= d[index]) break;
+    }
+    return 1;
+}
+
+/* flog.h:14-20 */
+static inline double flog_d(double x) {
+    uint64_t yi; memcpy(&yi, &x, 8);
+    return fma((double)yi, 1.539095918623324e-16, -709.0895657128241);
+}
+
+/* Lazy Fisher-Yates (fy.h:14-66) with the WyRand<uint32_t,2> stream (wy.h:96-145). */
+typedef struct {
+    uint32_t *g, *v; uint32_t n, i, c;
+    uint64_t state; uint64_t buf[2]; unsigned off;
+} lazyshuf_t;
+static uint32_t ls_rng32(lazyshuf_t *s) {
+    if (s->off + 4 > 16) { s->buf[0] = d2o_wyhash64(&s->state); s->buf[1] = d2o_wyhash64(&s->state); s->off = 0; }
+    uint32_t r; memcpy(&r, (const unsigned char *)s->buf + s->off, 4); s->off += 4;
+    return r;
+}
+static uint32_t ls_step(lazyshuf_t *s) {
+    const uint32_t samp = ls_rng32(s) % (s->n - s->i);
+    const uint32_t j = s->i + samp;
+    const uint32_t k = s->v[j] == s->c ? s->g[j] : j;
+    s->g[j] = s->v[s->i] == s->c ? s->g[s->i] : s->i;
+    s->v[j] = s->c;
+    if (++s->i == s->n) s->i = 0;
+    return k;
+}
+
+void d2o_css_update(double *regs, uint32_t m, const uint64_t *hv, uint64_t n, uint64_t *ids) {
+    lazyshuf_t ls; ls.n = m; ls.c = 0;
+    ls.g = (uint32_t *)calloc(m, 4); ls.v = (uint32_t *)calloc(m, 4);
+    const double INVMUL64 = 0x1p-64;
+    for (uint64_t e = 0; e < n; ++e) {
+        const uint64_t id = hv[e];
+        double carry = 0.;
+        uint64_t hid = id;
+        uint64_t rv = d2o_cehash(id ^ 0xb2069fc679a8da0bULL);
+        double mv = regs[2ULL * m - 2];
+        double tv = (double)rv * INVMUL64;
+        const double bv0 = -1. / m;
+        if (bv0 * flog_d(tv) * .7 > mv) continue;
+        double ev = bv0 * log(tv);
+        if (ev > mv) continue;
+        ls.i = 0; ++ls.c; ls.state = rv; ls.off = 16; /* reset(); seed(rv) */
+        uint64_t bi = 1;
+        for (;;) {
+            const uint32_t idx = ls_step(&ls);
+            if (mvt_update(regs, m, idx, ev)) { if (ids) ids[idx] = id; mv = regs[2ULL * m - 2]; }
+            if (bi == m) break;
+            rv = d2o_wyhash64(&hid);
+            const double bv = -(1. / (double)(m - bi)); ++bi; /* getbeta, setsketch.h:300-302 */
+            const double nv = (double)rv * INVMUL64;
+            if (bv * flog_d(nv) * .7 + ev > mv) break;
+            /* kahan.h:8-13 */
+            double inc = fma(bv, log(nv), -carry); /* GCC contracts `bv*log(nv) - carry` at -O3 -mfma */
+            const double tmp = ev + inc;
+            carry = (tmp - ev) - inc;
+            ev = tmp;
+            if (ev > mv) break;
+        }
+    }
+    free(ls.g); free(ls.v);
+}
+
+double d2o_css_card(const double *regs, uint32_t m) {
+    double s = 0.;
+    for (uint32_t i = 0; i < m; ++i) s += regs[i];
+    return m / s;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* densify                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+uint64_t d2o_densify(double *sig, uint64_t *kmers, uint64_t S) {
+    uint64_t nz = 0;
+    for (uint64_t i = 0; i < S; ++i) nz += sig[i] == 0.;
+    if (nz == S) return S;
+    double *tmp = (double *)malloc(S * sizeof(double));
+    memcpy(tmp, sig, S * sizeof(double));
+    uint64_t ne = 0;
+    for (uint64_t i = 0; i < S; ++i) {
+        if (sig[i] != 0.) continue;
+        ++ne;
+        uint64_t rng = i + 0x5bf2b8bdf07c06cULL, j;
+        do { j = d2o_wyhash64(&rng) % S; } while (sig[j] == 0.);
+        tmp[i] = sig[j];
+        if (kmers) kmers[i] = kmers[j];
+    }
+    memcpy(sig, tmp, S * sizeof(double));
+    free(tmp);
+    return ne;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* compare                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+void d2o_count_gtlt(const double *a, const double *b, uint64_t n, uint64_t *gt, uint64_t *lt) {
+    uint64_t g = 0, l = 0;
+    for (uint64_t i = 0; i < n; ++i) { g += a[i] > b[i]; l += b[i] > a[i]; }
+    *gt = g; *lt = l;
+}
+
+uint64_t d2o_count_eq(const uint64_t *a, const uint64_t *b, uint64_t n) {
+    uint64_t e = 0;
+    for (uint64_t i = 0; i < n; ++i) e += a[i] == b[i];
+    return e;
+}
+
+static inline long double ldmax(long double a, long double b) { return a < b ? b : a; } /* std::max */
+static inline long double ldmin(long double a, long double b) { return b < a ? b : a; } /* std::min */
+
+float d2o_finalize(uint64_t c0, uint64_t c1, uint64_t S, double lhc, double rhc, int measure, int k,
+                   int cmp_kind) {
+    long double ret;
+    const long double lhcard = lhc, rhcard = rhc;
+    const long double invdenom = 1.L / S;
+    const double poisson_mult = -1. / (k > 1 ? k : 1);
+    if (cmp_kind == 0) { /* cmp_core.cpp:458-494 */
+        const long double alpha = c0 * invdenom, beta = c1 * invdenom;
+        long double eq = (1. - alpha - beta);
+        const long double ucard = ldmax((lhcard + rhcard) / (2.L - alpha - beta), 0.L);
+        if (eq <= 0.) return measure != D2O_POISSON_LLR ? 0.f : (float)DBL_MAX;
+        if (eq <= 1e-15L) eq = 0;
+        const float isz = (float)(ucard * eq), sim = (float)eq;
+        switch (measure) {
+            case D2O_SIMILARITY: ret = sim; break;
+            case D2O_INTERSECTION: ret = isz; break;
+            case D2O_CONTAINMENT: ret = isz / rhcard; break;
+            case D2O_SYMMETRIC_CONTAINMENT: ret = isz / ldmin(lhcard, rhcard); break;
+            case D2O_POISSON_LLR:
+                ret = sim ? (double)(log(2. * sim / (1. + sim)) * poisson_mult) : (double)INFINITY; break;
+            case D2O_UNION_SIZE: ret = lhcard + rhcard - isz; break;
+            default: ret = -1.f;
+        }
+    } else { /* cmp_core.cpp:495-517 */
+        ret = invdenom * c0;
+        if (measure == D2O_INTERSECTION) ret *= ldmax((lhcard + rhcard) / (1.L + ret), 0.L);
+        else if (measure == D2O_SYMMETRIC_CONTAINMENT) ret *= ldmax((lhcard + rhcard) / (1.L + ret), 0.L) / ldmin(lhcard, rhcard);
+        else if (measure == D2O_CONTAINMENT) ret *= ldmax((lhcard + rhcard) / (1.L + ret), 0.L) / lhcard;
+        else if (measure == D2O_POISSON_LLR) ret = ret ? (double)(logl(2. * ret / (1. + ret)) * poisson_mult) : (double)INFINITY;
+        else if (measure == D2O_UNION_SIZE) {
+            const long double isz = ret * ldmax((lhcard + rhcard) / (1.L + ret), 0.L);
+            ret = lhcard + rhcard - isz;
+        }
+    }
+    if (isnan(ret) || isinf(ret)) ret = LDBL_MAX; /* cmp_core.cpp:573 */
+    return (float)ret;
+}
+
+float d2o_compare(const double *a, const double *b, uint64_t S, double lhc, double rhc, int measure,
+                  int k, int cmp_kind) {
+    uint64_t c0 = 0, c1 = 0;
+    if (cmp_kind == 0) d2o_count_gtlt(a, b, S, &c0, &c1);
+    else c0 = d2o_count_eq((const uint64_t *)a, (const uint64_t *)b, S);
+    return d2o_finalize(c0, c1, S, lhc, rhc, measure, k, cmp_kind);
+}
+
+void d2o_allpairs_symmetric(const double *regs, const double *cards, uint64_t n, uint64_t S,
+                            int measure, int k, int cmp_kind, float *out) {
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint64_t j = i + 1; j < n; ++j)
+            *out++ = d2o_compare(regs + i * S, regs + j * S, S, cards[i], cards[j], measure, k, cmp_kind);
+}
+void d2o_allpairs_asymmetric(const double *regs, const double *cards, uint64_t n, uint64_t S,
+                             int measure, int k, int cmp_kind, float *out) {
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint64_t j = 0; j < n; ++j)
+            *out++ = d2o_compare(regs + i * S, regs + j * S, S, cards[i], cards[j], measure, k, cmp_kind);
+}
+void d2o_panel(const double *regs, const double *cards, uint64_t nf, uint64_t nq, uint64_t S,
+               int measure, int k, int cmp_kind, float *out) {
+    for (uint64_t i = 0; i < nf; ++i)
+        for (uint64_t j = 0; j < nq; ++j)
+            *out++ = d2o_compare(regs + i * S, regs + (nf + j) * S, S, cards[i], cards[nf + j], measure, k, cmp_kind);
+}

@@ -1,0 +1,162 @@
+"""ctypes binding to oracle/libd2oracle.so (the CPU restatement; TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = os.path.join(ROOT, "oracle", "libd2oracle.so")
+
+u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+MEASURES = {"similarity": 0, "containment": 1, "symmetric_containment": 2, "poisson_llr": 3,
+            "intersection": 4, "union_size": 5}
+
+
+def build():
+    src = [os.path.join(ROOT, "oracle", f) for f in ("d2_oracle.c", "d2_oracle.h")]
+    if (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
+        subprocess.check_call(["make", "-s", "-f", "oracle/Makefile", "oracle/libd2oracle.so"], cwd=ROOT)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB)
+    L.d2o_wang64.restype = C.c_uint64; L.d2o_wang64.argtypes = [C.c_uint64]
+    L.d2o_wang64_inv.restype = C.c_uint64; L.d2o_wang64_inv.argtypes = [C.c_uint64]
+    L.d2o_revcomp.restype = C.c_uint64; L.d2o_revcomp.argtypes = [C.c_uint64, C.c_int]
+    L.d2o_xormask_for_seed.restype = C.c_uint64; L.d2o_xormask_for_seed.argtypes = [C.c_uint64]
+    L.d2o_hash_stream.restype = C.c_uint64
+    L.d2o_hash_stream.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, C.c_uint64]
+    L.d2o_opmh_m.restype = C.c_uint32; L.d2o_opmh_m.argtypes = [C.c_uint32]
+    L.d2o_opmh_reset.argtypes = [u64p, f64p, C.c_uint32]
+    L.d2o_opmh_update.argtypes = [u64p, f64p, C.c_uint32, u64p, C.c_uint64]
+    L.d2o_opmh_update_mincount.argtypes = [u64p, f64p, C.c_uint32, u64p, C.c_uint64, C.c_double]
+    L.d2o_opmh_card.restype = C.c_double; L.d2o_opmh_card.argtypes = [u64p, C.c_uint32]
+    L.d2o_opmh_sigs.argtypes = [u64p, C.c_uint32, f64p]
+    L.d2o_opmh_ids.argtypes = [u64p, C.c_uint32, u64p]
+    L.d2o_css_reset.argtypes = [f64p, C.c_uint32]
+    L.d2o_css_update.argtypes = [f64p, C.c_uint32, u64p, C.c_uint64, C.c_void_p]
+    L.d2o_css_card.restype = C.c_double; L.d2o_css_card.argtypes = [f64p, C.c_uint32]
+    L.d2o_densify.restype = C.c_uint64; L.d2o_densify.argtypes = [f64p, C.c_void_p, C.c_uint64]
+    L.d2o_finalize.restype = C.c_float
+    L.d2o_finalize.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
+    for nm in ("d2o_allpairs_symmetric", "d2o_allpairs_asymmetric"):
+        getattr(L, nm).argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
+    L.d2o_panel.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
+    _lib = L
+    return L
+
+
+# ---------------------------------------------------------------------------------------------
+# FASTA/FASTQ record reader with kseq semantics (bonsai/klib/kseq.h:178): '>' or '@' starts a
+# record, the name line is dropped, sequence lines are concatenated without line terminators,
+# FASTQ '+' line and qualities are skipped.
+# ---------------------------------------------------------------------------------------------
+def read_fastx(path: str):
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rb") as f:
+        data = f.read()
+    recs = []
+    lines = data.split(b"\n")
+    i, n = 0, len(lines)
+    while i < n:
+        ln = lines[i]
+        if not ln or ln[:1] not in (b">", b"@"):
+            i += 1
+            continue
+        fastq = ln[:1] == b"@"
+        i += 1
+        seq = []
+        while i < n and lines[i][:1] not in (b">", b"+", b"@"):
+            seq.append(lines[i].rstrip(b"\r"))
+            i += 1
+        s = b"".join(seq)
+        if fastq and i < n and lines[i][:1] == b"+":
+            i += 1
+            got = 0
+            while i < n and got < len(s):
+                got += len(lines[i].rstrip(b"\r"))
+                i += 1
+        recs.append(s)
+    return recs
+
+
+def hash_stream(seq: bytes, k: int, w: int = -1, canon: bool = True, seed: int = 0) -> np.ndarray:
+    L = lib()
+    out = np.empty(len(seq) + 2, dtype=np.uint64)
+    n = L.d2o_hash_stream(seq, len(seq), k, w, int(canon), L.d2o_xormask_for_seed(seed), out, len(out))
+    return out[:n].copy()
+
+
+def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool = True, seed: int = 0,
+                count_threshold: float = 0.0):
+    """Oracle equivalent of one iteration of the per-file loop (src/fastxsketch.cpp:303-624).
+
+    Returns dict(card=..., sig=f64[S], regs_u64=..., ids=...)."""
+    L = lib()
+    streams = [hash_stream(r, k, w, canon, seed) for r in read_fastx(path)]
+    hv = np.concatenate(streams) if streams else np.empty(0, dtype=np.uint64)
+    if mode == "opmh":
+        m = L.d2o_opmh_m(S)
+        regs = np.empty(m, dtype=np.uint64); counts = np.empty(m, dtype=np.float64)
+        L.d2o_opmh_reset(regs, counts, m)
+        if count_threshold > 1:
+            L.d2o_opmh_update_mincount(regs, counts, m, hv, len(hv), float(count_threshold))
+        else:
+            L.d2o_opmh_update(regs, counts, m, hv, len(hv))
+        sig = np.empty(m, dtype=np.float64)
+        L.d2o_opmh_sigs(regs, m, sig)
+        ids = np.empty(m, dtype=np.uint64)
+        L.d2o_opmh_ids(regs, m, ids)
+        return dict(card=L.d2o_opmh_card(regs, m), sig=sig[:S], regs_u64=regs, ids=ids[:S],
+                    counts=counts[:S], n_hashed=len(hv))
+    if mode == "fss":
+        regs = np.empty(2 * S - 1, dtype=np.float64)
+        L.d2o_css_reset(regs, S)
+        ids = np.zeros(S, dtype=np.uint64)
+        L.d2o_css_update(regs, S, hv, len(hv), ids.ctypes.data)
+        return dict(card=L.d2o_css_card(regs, S), sig=regs[:S].copy(), ids=ids, n_hashed=len(hv))
+    raise ValueError(mode)
+
+
+def densify(sig: np.ndarray) -> np.ndarray:
+    out = np.ascontiguousarray(sig, dtype=np.float64).copy()
+    lib().d2o_densify(out, None, len(out))
+    return out
+
+
+def allpairs(regs: np.ndarray, cards: np.ndarray, kind: str = "symmetric", measure: str = "similarity",
+             k: int = 31, cmp_kind: int = 0, nq: int = 0) -> np.ndarray:
+    L = lib()
+    regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
+    n, S = regs.shape
+    me = MEASURES[measure]
+    if kind == "symmetric":
+        out = np.empty(n * (n - 1) // 2, dtype=np.float32)
+        L.d2o_allpairs_symmetric(regs, cards, n, S, me, k, cmp_kind, out)
+    elif kind == "asymmetric":
+        out = np.empty(n * n, dtype=np.float32)
+        L.d2o_allpairs_asymmetric(regs, cards, n, S, me, k, cmp_kind, out)
+    elif kind == "panel":
+        nf = n - nq
+        out = np.empty(nf * nq, dtype=np.float32)
+        L.d2o_panel(regs, cards, nf, nq, S, me, k, cmp_kind, out)
+    else:
+        raise ValueError(kind)
+    return out

@@ -1,0 +1,102 @@
+"""Pins the oracle (oracle/d2_oracle.c) against outputs of the unmodified reference binary
+(tests/golden/expected, produced by tests/golden/make_golden.py) and the two known answers the
+reference's own tests hold for this path (bonsai/test/encoding.cpp:84,122)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import expected
+
+SKETCH = {
+    "opmh_k31_S1024": dict(mode="opmh", S=1024, k=31),
+    "opmh_k31_w51_S512": dict(mode="opmh", S=512, k=31, w=51),
+    "opmh_k21_S256_nocanon": dict(mode="opmh", S=256, k=21, canon=False),
+    "opmh_k21_w30_S256_nocanon": dict(mode="opmh", S=256, k=21, w=30, canon=False),
+    "opmh_k31_S256_seed17": dict(mode="opmh", S=256, k=31, seed=17),
+    "opmh_k15_S64": dict(mode="opmh", S=64, k=15),
+    "opmh_k31_S1000": dict(mode="opmh", S=1000, k=31),
+    "fss_k31_S256": dict(mode="fss", S=256, k=31),
+    "fss_k31_w51_S1024": dict(mode="fss", S=1024, k=31, w=51),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SKETCH))
+def test_sketch_registers_bit_exact(case, golden_inputs):
+    names, paths = golden_inputs
+    z = np.load(expected(case + ".npz"))
+    for i, p in enumerate(paths):
+        o = O.sketch_file(p, **SKETCH[case])
+        assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)), (case, names[i])
+        if SKETCH[case]["mode"] == "opmh":
+            assert o["card"] == z["cards"][i], (case, names[i])
+        else:  # reference sums registers under `omp simd` (order is compiler-chosen): 1e-12 relative
+            assert o["card"] == pytest.approx(z["cards"][i], rel=1e-12)
+
+
+def test_save_kmers_ids(golden_inputs):
+    names, paths = golden_inputs
+    z = np.load(expected("opmh_k31_S256_savekmers.npz"))
+    for i, p in enumerate(paths):
+        o = O.sketch_file(p, mode="opmh", S=256, k=31)
+        assert np.array_equal(o["ids"], z["ids"][i])
+
+
+def test_densify_matches_reference(golden_inputs):
+    names, paths = golden_inputs
+    raw = np.load(expected("opmh_k15_S64.npz"))        # sketch only: not densified
+    den = np.load(expected("opmh_k15_S64_densified.npz"))  # sketch --cmpout: densified in place
+    changed = 0
+    for i in range(len(paths)):
+        got = O.densify(raw["sigs"][i])
+        assert np.array_equal(got, den["sigs"][i])
+        changed += int((raw["sigs"][i] != den["sigs"][i]).sum())
+    assert changed > 0  # the fixture really exercises densification
+    got = O.allpairs(den["sigs"], den["cards"], "symmetric", "similarity", k=15)
+    assert np.array_equal(got.view(np.uint32), den["mat"].view(np.uint32))
+
+
+CMP = {"sim_sym": ("symmetric", "similarity"), "sim_asym": ("asymmetric", "similarity"),
+       "containment_sym": ("symmetric", "containment"), "symcontainment_sym": ("symmetric", "symmetric_containment"),
+       "mash_sym": ("symmetric", "poisson_llr"), "isz_sym": ("symmetric", "intersection"),
+       "usz_sym": ("symmetric", "union_size")}
+
+
+@pytest.mark.parametrize("kind", sorted(CMP))
+def test_compare_opmh_matrix(kind):
+    z = np.load(expected("opmh_k31_S1024.npz"))
+    sigs = np.stack([O.densify(s) for s in z["sigs"]])
+    got = O.allpairs(sigs, z["cards"], CMP[kind][0], CMP[kind][1], k=31)
+    exp = np.load(expected(f"cmp_opmh_k31_S1024_{kind}.npy"))
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+@pytest.mark.parametrize("suffix,cmp_kind", [(".ss", 0), (".bmh", 1)])
+@pytest.mark.parametrize("kind", sorted(CMP))
+def test_compare_presketched(kind, suffix, cmp_kind):
+    f = expected(f"cmp_sk48{suffix}_{kind}.npy")
+    if not os.path.exists(f):
+        pytest.skip("no golden for this combination")
+    z = np.load(os.path.join(os.path.dirname(expected("x")), "..", "inputs", "sk48x256.npz"))
+    # `cmp --presketched` without -k: k defaults to 32 (src/sketch_main.cpp:70 nregperitem)
+    got = O.allpairs(z["regs"], z["cards"], CMP[kind][0], CMP[kind][1], k=32, cmp_kind=cmp_kind)
+    exp = np.load(f)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+def test_known_answers_from_reference_tests():
+    """bonsai/test/encoding.cpp:84 -- windowed minimizer count == len - w + 1 (canonical path);
+    :122 pins 5356 distinct phiX 31-mers, whose fixture (phix.fa) is not redistributable here, so we
+    check the structural identity it relies on: #k-mers emitted == len - k + 1 on ACGT-only input."""
+    rng = np.random.default_rng(3)
+    seq = b"ACGT"[0:0] + bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 5386)])
+    assert len(O.hash_stream(seq, 31)) == 5386 - 31 + 1
+    for w in (40, 51, 100):
+        assert len(O.hash_stream(seq, 31, w)) == 5386 - w + 1
+
+
+def test_wang_inverse_roundtrip():
+    L = O.lib()
+    for x in (0, 1, 133348, 0xdeadbeefcafebabe, 2**64 - 1):
+        assert L.d2o_wang64_inv(L.d2o_wang64(x)) == x
