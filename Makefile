@@ -1,0 +1,16 @@
+# Builds libd2gpu.so (CUDA kernels + C ABI, sm_100a only) in-tree under dashing2_b200/.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX_HOST ?= /usr/bin/g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -ccbin $(CXX_HOST) --fmad=false -Xptxas -v
+CSRC := dashing2_b200/csrc
+HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/d2gpu.h
+
+all: dashing2_b200/libd2gpu.so
+
+dashing2_b200/libd2gpu.so: $(CSRC)/d2gpu_api.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/d2gpu_api.cu -lcudart_static -lpthread -ldl -lrt 2> dashing2_b200/ptxas.log || (cat dashing2_b200/ptxas.log; exit 1)
+
+clean:
+	rm -f dashing2_b200/libd2gpu.so dashing2_b200/ptxas.log
+.PHONY: all clean

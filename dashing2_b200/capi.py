@@ -1,0 +1,210 @@
+"""ctypes binding of libd2gpu.so (include/d2gpu.h) -- the only way Python reaches the product.
+
+The library is built in-tree (``make`` / ``__graft_entry__.build()``) as dashing2_b200/libd2gpu.so.
+There is no CPU fallback anywhere in this module: if the shared library is missing ``load()`` raises,
+and without a CUDA device ``Context()`` raises (D2G_ENODEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libd2gpu.so")
+
+MODE = {"opmh": 0, "fss": 1, "bmh": 2, "pmh": 3}
+MEASURE = {"similarity": 0, "containment": 1, "symmetric_containment": 2, "poisson_llr": 3,
+           "intersection": 4, "union_size": 5}
+SHAPE = {"symmetric": 0, "asymmetric": 1, "panel": 2}
+
+
+class SketchParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("canon", C.c_int32), ("mode", C.c_int32),
+                ("xormask", C.c_uint64), ("sketchsize", C.c_uint32), ("count_threshold", C.c_uint32),
+                ("countsketch_size", C.c_uint64)]
+
+
+class CmpParams(C.Structure):
+    _fields_ = [("sketchsize", C.c_uint32), ("cmp_kind", C.c_int32), ("measure", C.c_int32), ("k", C.c_int32),
+                ("shape", C.c_int32), ("n", C.c_uint64), ("nq", C.c_uint64)]
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c_uint64, C.c_uint64)
+
+# every symbol include/d2gpu.h declares
+EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stream", "d2g_sync", "d2g_launch_count",
+           "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
+           "d2g_densify", "d2g_densify_dev", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
+           "d2g_cmp_stream", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_free"]
+
+_lib = None
+
+
+class D2GError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise D2GError(f"{LIB_PATH} not built: run `make` (or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+    L.d2g_init.argtypes = [C.POINTER(vp), C.c_int]; L.d2g_init.restype = C.c_int
+    L.d2g_destroy.argtypes = [vp]; L.d2g_destroy.restype = None
+    L.d2g_last_error.restype = C.c_char_p
+    L.d2g_version.restype = C.c_char_p
+    L.d2g_stream.argtypes = [vp]; L.d2g_stream.restype = vp
+    L.d2g_sync.argtypes = [vp]; L.d2g_sync.restype = C.c_int
+    L.d2g_launch_count.argtypes = [vp]; L.d2g_launch_count.restype = u64
+    L.d2g_opmh_m.argtypes = [u32]; L.d2g_opmh_m.restype = u32
+    L.d2g_count_kmers.argtypes = [vp, u64, i32]; L.d2g_count_kmers.restype = u64
+    L.d2g_sketch_batch.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, vp, vp, vp, vp, C.POINTER(u64)]
+    L.d2g_sketch_batch.restype = C.c_int
+    L.d2g_opmh_finalize.argtypes = [vp, u32, u32, vp, vp]; L.d2g_opmh_finalize.restype = C.c_int
+    L.d2g_sketch_batch_dev.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, u64, vp, vp, vp, vp]
+    L.d2g_sketch_batch_dev.restype = C.c_int
+    L.d2g_densify.argtypes = [vp, vp, vp, u64, u32]; L.d2g_densify.restype = C.c_int
+    L.d2g_densify_dev.argtypes = [vp, vp, vp, u64, u32]; L.d2g_densify_dev.restype = C.c_int
+    L.d2g_cmp_output_size.argtypes = [C.POINTER(CmpParams)]; L.d2g_cmp_output_size.restype = u64
+    L.d2g_cmp_rows_size.argtypes = [C.POINTER(CmpParams), u64, u64, C.POINTER(u64)]; L.d2g_cmp_rows_size.restype = C.c_int
+    L.d2g_cmp_matrix.argtypes = [vp, C.POINTER(CmpParams), vp, vp, vp]; L.d2g_cmp_matrix.restype = C.c_int
+    L.d2g_cmp_stream.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, SINK_FN, vp]; L.d2g_cmp_stream.restype = C.c_int
+    L.d2g_cmp_rows_dev.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, vp]; L.d2g_cmp_rows_dev.restype = C.c_int
+    L.d2g_cmp_counts.argtypes = [vp, u32, i32, vp, u64, vp, u64, vp, vp]; L.d2g_cmp_counts.restype = C.c_int
+    L.d2g_free.argtypes = [vp]; L.d2g_free.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise D2GError(f"libd2gpu error {rc}: {load().d2g_last_error().decode(errors='replace')}")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def xormask_for_seed(seed: int) -> int:
+    """maskfn XOR mask (src/enums.cpp:133-140): 0 for seed 0, else Wang(seed)."""
+    if seed == 0:
+        return 0
+    M = (1 << 64) - 1
+    key = seed & M
+    key = (~key + (key << 21)) & M
+    key ^= key >> 24
+    key = (key + (key << 3) + (key << 8)) & M
+    key ^= key >> 14
+    key = (key + (key << 2) + (key << 4)) & M
+    key ^= key >> 28
+    key = (key + (key << 31)) & M
+    return key
+
+
+class Context:
+    """One libd2gpu context (device + stream + scratch)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        _check(self.L.d2g_init(C.byref(h), device))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.d2g_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def stream(self) -> int:
+        return self.L.d2g_stream(self.h) or 0
+
+    def sync(self):
+        _check(self.L.d2g_sync(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.L.d2g_launch_count(self.h))
+
+    # ---- sketch ----
+    @staticmethod
+    def params(mode="opmh", S=1024, k=31, w=-1, canon=True, seed=0, count_threshold=0):
+        return SketchParams(k, w, int(canon), MODE[mode], xormask_for_seed(seed), S, int(count_threshold), 0)
+
+    def sketch_batch(self, seq: np.ndarray, rec_off: np.ndarray, rec_entity: np.ndarray, n_entities: int,
+                     p: SketchParams, want_ids=False, want_regs=True):
+        """Host buffers in, host arrays out (d2g_sketch_batch)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        rec_entity = np.ascontiguousarray(rec_entity, dtype=np.uint32)
+        n_rec = len(rec_entity)
+        S = p.sketchsize
+        m = self.L.d2g_opmh_m(S)
+        regs = np.empty((n_entities, m), dtype=np.uint64) if (p.mode == 0 and want_regs) else None
+        sig = np.empty((n_entities, S), dtype=np.float64)
+        card = np.empty(n_entities, dtype=np.float64)
+        ids = np.empty((n_entities, S), dtype=np.uint64) if want_ids else None
+        nk = C.c_uint64(0)
+        _check(self.L.d2g_sketch_batch(self.h, C.byref(p), _ptr(seq), _ptr(rec_off), _ptr(rec_entity), n_rec, n_entities,
+                                       _ptr(regs), _ptr(sig), _ptr(card), _ptr(ids), C.byref(nk)))
+        return dict(regs_u64=regs, sig=sig, card=card, ids=ids, n_kmers=int(nk.value))
+
+    def sketch_batch_dev(self, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
+                         regs_u64_d=0, sig_d=0, card_d=0, ids_d=0):
+        """Device pointers (ints) in/out; asynchronous on self.stream (d2g_sketch_batch_dev)."""
+        _check(self.L.d2g_sketch_batch_dev(self.h, C.byref(p), seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
+                                           regs_u64_d or None, sig_d or None, card_d or None, ids_d or None))
+
+    def opmh_finalize(self, regs_u64: np.ndarray, S: int):
+        regs_u64 = np.ascontiguousarray(regs_u64, dtype=np.uint64)
+        n = regs_u64.shape[0]
+        sig = np.empty((n, S), dtype=np.float64); card = np.empty(n, dtype=np.float64)
+        _check(self.L.d2g_opmh_finalize(_ptr(regs_u64), n, S, _ptr(sig), _ptr(card)))
+        return sig, card
+
+    # ---- compare ----
+    @staticmethod
+    def cmp_params(S, n, shape="symmetric", measure="similarity", k=31, cmp_kind=0, nq=0):
+        return CmpParams(S, cmp_kind, MEASURE[measure], k, SHAPE[shape], n, nq)
+
+    def densify(self, sig: np.ndarray, kmers: np.ndarray | None = None):
+        sig = np.ascontiguousarray(sig, dtype=np.float64).copy()
+        n, S = sig.shape
+        _check(self.L.d2g_densify(self.h, _ptr(sig), _ptr(kmers), n, S))
+        return sig
+
+    def cmp_matrix(self, regs: np.ndarray, cards: np.ndarray, p: CmpParams) -> np.ndarray:
+        regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
+        out = np.empty(int(self.L.d2g_cmp_output_size(C.byref(p))), dtype=np.float32)
+        _check(self.L.d2g_cmp_matrix(self.h, C.byref(p), _ptr(regs), _ptr(cards), _ptr(out)))
+        return out
+
+    def cmp_stream(self, regs, cards, p: CmpParams, row_begin, row_end, callback):
+        regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
+
+        def _sink(user, block, first_row, n_rows, n_vals):
+            arr = np.ctypeslib.as_array(block, shape=(int(n_vals),))
+            return int(callback(arr, int(first_row), int(n_rows)) or 0)
+        fn = SINK_FN(_sink)
+        _check(self.L.d2g_cmp_stream(self.h, C.byref(p), _ptr(regs), _ptr(cards), row_begin, row_end, fn, None))
+
+    def cmp_rows_dev(self, p: CmpParams, regs_d, cards_d, row_begin, row_end, out_d):
+        _check(self.L.d2g_cmp_rows_dev(self.h, C.byref(p), regs_d, cards_d, row_begin, row_end, out_d))
+
+    def cmp_rows_size(self, p: CmpParams, row_begin, row_end) -> int:
+        nv = C.c_uint64(0)
+        _check(self.L.d2g_cmp_rows_size(C.byref(p), row_begin, row_end, C.byref(nv)))
+        return int(nv.value)
+
+    def cmp_counts(self, rows: np.ndarray, cols: np.ndarray, cmp_kind=0):
+        rows = np.ascontiguousarray(rows, dtype=np.float64); cols = np.ascontiguousarray(cols, dtype=np.float64)
+        nr, S = rows.shape; nc = cols.shape[0]
+        c0 = np.empty((nr, nc), dtype=np.uint32); c1 = np.zeros((nr, nc), dtype=np.uint32)
+        _check(self.L.d2g_cmp_counts(self.h, S, cmp_kind, _ptr(rows), nr, _ptr(cols), nc, _ptr(c0), _ptr(c1)))
+        return c0, c1

@@ -1,0 +1,589 @@
+// d2gpu_api.cu -- implementation of the C ABI declared in include/d2gpu.h.
+//
+// Host-side runtime around the kernels: context (device, stream, grow-only scratch), launch
+// geometry, host<->device staging, and the parts of the reference's finalisation that are x87
+// long-double arithmetic on the host in the reference too (one-permutation signature transform,
+// /root/reference/src/oph.h:240-263).  There is deliberately no CPU implementation of the hot paths
+// here: without a device every entry point fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/d2gpu.h"
+#include "cmp_kernels.cuh"
+#include "sketch_kernels.cuh"
+#include "fss_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(D2G_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return D2G_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(D2G_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want; return D2G_OK;
+    }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return D2G_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e != cudaSuccess) { p = nullptr; return fail(D2G_ENOMEM, "cudaMallocHost(%zu) failed: %s", n, cudaGetErrorString(e)); }
+        cap = n; return D2G_OK;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+} // namespace
+
+struct d2g_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::atomic<uint64_t> launches{0};
+    DevBuf seq, recoff, recent, regs, sig, card, ids, aux, aux2;   // sketch scratch
+    DevBuf cregs, ccards, cout, clut, ctmp, cktmp;                 // compare scratch
+    PinBuf pin[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    uint32_t lut_S = 0; int lut_k = -1;
+};
+
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *d2g_last_error(void) { return g_err.c_str(); }
+const char *d2g_version(void) { return "d2gpu 0.1 (sm_100a)"; }
+
+int d2g_init(d2g_ctx **out, int device) {
+    if (!out) return fail(D2G_EINVAL, "null ctx pointer");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(D2G_ENODEVICE, "no CUDA device available (%s); libd2gpu has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(D2G_EINVAL, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    d2g_ctx *c = new d2g_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming));
+    *out = c;
+    return D2G_OK;
+}
+
+void d2g_destroy(d2g_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+    if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+void *d2g_stream(d2g_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int d2g_sync(d2g_ctx *c) { if (!c) return fail(D2G_EINVAL, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return D2G_OK; }
+uint64_t d2g_launch_count(const d2g_ctx *c) { return c ? c->launches.load() : 0; }
+void d2g_free(void *p) { free(p); }
+
+uint32_t d2g_opmh_m(uint32_t S) { return S + (S & 1u); }
+
+uint64_t d2g_count_kmers(const uint64_t *rec_off, uint64_t n_rec, int32_t k) {
+    uint64_t t = 0;
+    for (uint64_t r = 0; r < n_rec; ++r) { const uint64_t l = rec_off[r + 1] - rec_off[r]; if (l >= (uint64_t)k) t += l - k + 1; }
+    return t;
+}
+
+} // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// sketch path
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void fill_u64_kernel(uint64_t *p, uint64_t n, uint64_t v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void opmh_ids_kernel(const uint64_t *regs, uint64_t *ids, uint64_t n_ent, uint32_t m, uint32_t S) {
+    const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= n_ent * S) return;
+    const uint64_t g = e / S, i = e % S;
+    ids[e] = d2g::dhash_inv(regs[g * m + i]);   // src/oph.h:264-271
+}
+
+int check_sketch_params(const d2g_sketch_params *p) {
+    if (!p) return fail(D2G_EINVAL, "null params");
+    if (p->k < 1 || p->k > 32) return fail(D2G_EUNSUPPORTED, "k=%d: only 1..32 (exact 2-bit encoding) is implemented; k>32 rolling hash is out of scope", p->k);
+    if (p->sketchsize == 0) return fail(D2G_EINVAL, "sketchsize must be > 0");
+    if (p->w > p->k) {
+        if (p->w > d2g::SK_MAX_W) return fail(D2G_EUNSUPPORTED, "window %d > %d not supported", p->w, d2g::SK_MAX_W);
+        if (!p->canon) return fail(D2G_EUNSUPPORTED, "windowed minimizers without canonicalisation (-C -w) are not implemented on the GPU");
+    }
+    if (p->mode != D2G_MODE_OPMH && p->mode != D2G_MODE_FULL_SETSKETCH)
+        return fail(D2G_EUNSUPPORTED, "sketch mode %d not implemented yet (OPMH and Full SetSketch are)", p->mode);
+    if (p->count_threshold > 1) return fail(D2G_EUNSUPPORTED, "--count-threshold > 1 not implemented on the GPU");
+    if (p->countsketch_size) return fail(D2G_EUNSUPPORTED, "--countsketch-size not implemented on the GPU");
+    return D2G_OK;
+}
+
+uint64_t pick_span(const d2g_ctx *c, uint64_t total_len, uint32_t m) {
+    // enough CTAs for ~8 waves, but spans long enough that the per-CTA register flush (m atomics) is noise
+    const uint64_t min_span = std::max<uint64_t>(16ULL * d2g::SK_TILE, 16ULL * m);
+    uint64_t span = total_len / ((uint64_t)c->sm_count * 32) + 1;
+    span = std::max(span, min_span);
+    span = (span + d2g::SK_TILE - 1) / d2g::SK_TILE * d2g::SK_TILE;
+    return span;
+}
+
+d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
+                                 const uint32_t *rec_ent_d, uint64_t n_rec, uint64_t total_len, uint32_t m) {
+    d2g::SketchArgs a;
+    a.seq = reinterpret_cast<const uint8_t *>(seq_d); a.rec_off = rec_off_d; a.rec_entity = rec_ent_d;
+    a.n_rec = n_rec; a.total_len = total_len; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
+    a.m = m; a.tile_stride = 1;
+    a.span = pick_span(c, total_len, m);
+    return a;
+}
+
+template <class Consumer>
+int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer::Params &cp, bool windowed) {
+    const size_t smem = d2g::sketch_smem_bytes<Consumer>(a.m, windowed);
+    if (smem > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sketch with %u registers needs %zu bytes of shared memory per CTA (max 200 KiB)", a.m, smem);
+    const uint64_t grid = (a.total_len + a.span - 1) / a.span;
+    if (windowed) {
+        CU(cudaFuncSetAttribute(d2g::sketch_kernel<true, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        d2g::sketch_kernel<true, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+    } else {
+        CU(cudaFuncSetAttribute(d2g::sketch_kernel<false, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        d2g::sketch_kernel<false, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return D2G_OK;
+}
+
+// regs_d: [n_ent][m] u64 for OPMH.  Launches the OPMH sketch kernels on the ctx stream.
+int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
+                const uint32_t *rec_ent_d, uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d) {
+    const uint32_t m = d2g_opmh_m(p->sketchsize);
+    const uint64_t nreg = (uint64_t)n_ent * m;
+    fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, c->stream>>>(regs_d, nreg, ~0ULL);
+    c->launches++;
+    if (total_len == 0 || n_rec == 0) return D2G_OK;
+    const bool windowed = p->w > p->k;
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m);
+    d2g::OpmhConsumer::Params cp{regs_d, d2g::make_fastmod32(m), m};
+    return launch_sketch<d2g::OpmhConsumer>(c, a, cp, windowed);
+}
+
+// Full SetSketch (see fss_kernels.cuh): boot -> threshold -> main -> long walks -> finalize.
+// sig_d [n_ent][S] / card_d [n_ent] may be null.  Synchronises the stream to check the long-walk queue.
+int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+               uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d) {
+    if (ids_d) return fail(D2G_EUNSUPPORTED, "--save-kmers ids for Full SetSketch are not implemented on the GPU yet");
+    const uint32_t m = p->sketchsize;
+    const uint64_t nreg = (uint64_t)n_ent * m;
+    const uint64_t ovf_cap = 1ULL << 20;
+    // aux layout: maxrv[nreg] | keys[nreg] | T[n_ent] | rvmin[n_ent] | ovf_count[1] (+pad) | ovf[2*ovf_cap]
+    const size_t aux_bytes = (nreg * 2 + (uint64_t)n_ent * 2 + 2 + 2 * ovf_cap) * 8;
+    if (int rc = c->aux.reserve(aux_bytes)) return rc;
+    uint64_t *maxrv = c->aux.as<uint64_t>(), *keys = maxrv + nreg;
+    double *T = reinterpret_cast<double *>(keys + nreg);
+    uint64_t *rvmin = reinterpret_cast<uint64_t *>(T + n_ent);
+    unsigned long long *ovf_count = reinterpret_cast<unsigned long long *>(rvmin + n_ent);
+    uint64_t *ovf = reinterpret_cast<uint64_t *>(ovf_count + 2);
+    CU(cudaMemsetAsync(maxrv, 0, nreg * 8, c->stream));
+    CU(cudaMemsetAsync(ovf_count, 0, 16, c->stream));
+    fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, c->stream>>>(keys, nreg, d2g::FSS_KEY_EMPTY);
+    c->launches++;
+    const bool windowed = p->w > p->k;
+    if (total_len && n_rec) {
+        d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m);
+        // boot on a 1/8 sample of the tiles when entities are large enough for the sample to hit every register
+        const double per_ent = (double)total_len / std::max(1u, n_ent);
+        a.tile_stride = (per_ent / 8. >= 24. * m * std::log((double)m + 2.)) ? 8 : 1;
+        d2g::FssBootConsumer::Params bp{maxrv, d2g::make_fastmod32(m), m};
+        if (int rc = launch_sketch<d2g::FssBootConsumer>(c, a, bp, windowed)) return rc;
+        d2g::fss_threshold_kernel<<<n_ent, 256, 0, c->stream>>>(maxrv, m, T, rvmin);
+        c->launches++;
+        a.tile_stride = 1;
+        d2g::FssMainConsumer::Params mp{keys, T, rvmin, ovf, ovf_count, ovf_cap, m};
+        if (int rc = launch_sketch<d2g::FssMainConsumer>(c, a, mp, windowed)) return rc;
+        // long walks (normally none): dense permutation state per thread slot
+        uint64_t nslots = std::min<uint64_t>(4096, (256ULL << 20) / ((uint64_t)m * 8));
+        nslots = std::max<uint64_t>(32, nslots / 32 * 32);
+        if (int rc = c->aux2.reserve(nslots * 2ULL * m * 4)) return rc;
+        CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, c->stream));
+        d2g::fss_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, c->stream>>>(ovf, ovf_count, ovf_cap, m, T, keys, c->aux2.as<uint32_t>());
+        c->launches++;
+    }
+    const uint64_t nthreads = std::max<uint64_t>(nreg, n_ent);
+    d2g::fss_finalize_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, c->stream>>>(keys, n_ent, m, sig_d, card_d);
+    c->launches++;
+    unsigned long long h_ovf = 0;
+    CU(cudaMemcpyAsync(&h_ovf, ovf_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    if (h_ovf > ovf_cap) return fail(D2G_EUNSUPPORTED, "Full SetSketch: %llu elements needed a long register walk (queue holds %llu); "
+                                     "inputs this small relative to the sketch size are not supported in one batch", h_ovf, (unsigned long long)ovf_cap);
+    return D2G_OK;
+}
+
+// Host finalisation of one-permutation registers: x87 long double, as the reference does on the host
+// (src/oph.h:240-263).  Threads over entities.
+void opmh_finalize_host(const uint64_t *regs, uint32_t n_ent, uint32_t m, uint32_t S, double *sig, double *card) {
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t g = lo; g < hi; ++g) {
+            const uint64_t *r = regs + (uint64_t)g * m;
+            if (card) {
+                long double sum = 0.L;
+                for (uint32_t i = 0; i < m; ++i) sum = sum + (long double)r[i] * 0x1p-64L;
+                card[g] = sum ? (double)((long double)m * ((long double)m / sum)) : (double)INFINITY;
+            }
+            if (sig) {
+                uint64_t nempty = 0;
+                for (uint32_t i = 0; i < m; ++i) nempty += r[i] == ~0ULL;
+                const long double mul = -1.0 / (double)((uint64_t)m - nempty);
+                double *o = sig + (uint64_t)g * S;
+                for (uint32_t i = 0; i < S; ++i) {
+                    const uint64_t x = r[i];
+                    o[i] = (x == ~0ULL || x == 0) ? 0. : (double)(mul * logl(0x1p-64L * (long double)(~0ULL - x + 1)));
+                }
+            }
+        }
+    };
+    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 64u));
+    nt = std::min<unsigned>(nt, std::max(1u, n_ent / 4));
+    if (nt <= 1) { work(0, n_ent); return; }
+    std::vector<std::thread> th;
+    const uint32_t per = (n_ent + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) { const uint32_t lo = t * per, hi = std::min(n_ent, lo + per); if (lo < hi) th.emplace_back(work, lo, hi); }
+    for (auto &t : th) t.join();
+}
+
+} // namespace
+
+extern "C" int d2g_opmh_finalize(const uint64_t *regs_u64, uint32_t n_entities, uint32_t sketchsize, double *sig_out, double *card_out) {
+    if (!regs_u64) return fail(D2G_EINVAL, "null registers");
+    opmh_finalize_host(regs_u64, n_entities, d2g_opmh_m(sketchsize), sketchsize, sig_out, card_out);
+    return D2G_OK;
+}
+
+extern "C" int d2g_sketch_batch_dev(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
+                                    const uint32_t *rec_entity_d, uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
+                                    uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    CU(cudaSetDevice(c->device));
+    if (p->mode == D2G_MODE_OPMH) {
+        if (sig_out_d || card_out_d)
+            return fail(D2G_EINVAL, "OPMH signatures/cardinalities are x87 long-double transforms of the u64 minima (src/oph.h:240-263): "
+                                    "take regs_u64_out_d and call d2g_opmh_finalize on the host");
+        if (!regs_u64_out_d) return fail(D2G_EINVAL, "regs_u64_out_d required for OPMH");
+        if (int rc = launch_opmh(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, regs_u64_out_d)) return rc;
+        if (ids_out_d) {
+            const uint64_t n = (uint64_t)n_entities * p->sketchsize;
+            opmh_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(regs_u64_out_d, ids_out_d, n_entities, d2g_opmh_m(p->sketchsize), p->sketchsize);
+            c->launches++;
+        }
+        return D2G_OK;
+    }
+    return launch_fss(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, sig_out_d, card_out_d, ids_out_d);
+}
+
+extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const char *seq, const uint64_t *rec_off,
+                                const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities, uint64_t *regs_u64_out,
+                                double *sig_out, double *card_out, uint64_t *ids_out, uint64_t *n_kmers_hashed) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    if (n_rec && (!rec_off || !rec_entity)) return fail(D2G_EINVAL, "null record tables");
+    CU(cudaSetDevice(c->device));
+    const uint64_t total_len = n_rec ? rec_off[n_rec] : 0;
+    if (total_len && !seq) return fail(D2G_EINVAL, "null sequence buffer");
+    for (uint64_t r = 0; r < n_rec; ++r) {
+        if (rec_off[r + 1] < rec_off[r]) return fail(D2G_EINVAL, "rec_off not monotone at %llu", (unsigned long long)r);
+        if (rec_entity[r] >= n_entities) return fail(D2G_EINVAL, "rec_entity[%llu]=%u >= n_entities", (unsigned long long)r, rec_entity[r]);
+        if (r && rec_entity[r] < rec_entity[r - 1]) return fail(D2G_EINVAL, "rec_entity must be non-decreasing");
+    }
+    if (n_kmers_hashed) *n_kmers_hashed = d2g_count_kmers(rec_off, n_rec, p->k);
+    const uint32_t S = p->sketchsize, m = d2g_opmh_m(S);
+    if (int rc = c->seq.reserve(total_len + 64)) return rc;
+    if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
+    if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
+    if (total_len) CU(cudaMemcpyAsync(c->seq.p, seq, total_len, cudaMemcpyHostToDevice, c->stream));
+    if (n_rec) {
+        CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (p->mode == D2G_MODE_OPMH) {
+        if (int rc = c->regs.reserve((uint64_t)n_entities * m * 8)) return rc;
+        if (int rc = launch_opmh(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len, c->regs.as<uint64_t>())) return rc;
+        std::vector<uint64_t> tmp;
+        uint64_t *hregs = regs_u64_out;
+        if (!hregs) { tmp.resize((uint64_t)n_entities * m); hregs = tmp.data(); }
+        if (ids_out) {
+            if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) return rc;
+            const uint64_t n = (uint64_t)n_entities * S;
+            opmh_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->regs.as<uint64_t>(), c->ids.as<uint64_t>(), n_entities, m, S);
+            c->launches++;
+            CU(cudaMemcpyAsync(ids_out, c->ids.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaMemcpyAsync(hregs, c->regs.p, (uint64_t)n_entities * m * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (sig_out || card_out) opmh_finalize_host(hregs, n_entities, m, S, sig_out, card_out);
+        return D2G_OK;
+    }
+    // Full SetSketch: registers are doubles produced on the device
+    if (int rc = c->sig.reserve((uint64_t)n_entities * S * 8)) return rc;
+    if (int rc = c->card.reserve((uint64_t)n_entities * 8)) return rc;
+    if (ids_out) if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) return rc;
+    if (int rc = launch_fss(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len,
+                            c->sig.as<double>(), c->card.as<double>(), ids_out ? c->ids.as<uint64_t>() : nullptr)) return rc;
+    if (sig_out) CU(cudaMemcpyAsync(sig_out, c->sig.p, (uint64_t)n_entities * S * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (card_out) CU(cudaMemcpyAsync(card_out, c->card.p, (uint64_t)n_entities * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (ids_out) CU(cudaMemcpyAsync(ids_out, c->ids.p, (uint64_t)n_entities * S * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    (void)regs_u64_out;
+    return D2G_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// compare path
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+int check_cmp_params(const d2g_cmp_params *p) {
+    if (!p) return fail(D2G_EINVAL, "null params");
+    if (p->sketchsize == 0) return fail(D2G_EINVAL, "sketchsize must be > 0");
+    if (p->cmp_kind != D2G_CMP_GTLT && p->cmp_kind != D2G_CMP_EQ) return fail(D2G_EINVAL, "bad cmp_kind %d", p->cmp_kind);
+    if (p->measure < 0 || p->measure > D2G_UNION_SIZE) return fail(D2G_EINVAL, "bad measure %d", p->measure);
+    if (p->shape < 0 || p->shape > D2G_PANEL) return fail(D2G_EINVAL, "bad shape %d", p->shape);
+    if (p->shape == D2G_PANEL && p->nq > p->n) return fail(D2G_EINVAL, "nq > n");
+    return D2G_OK;
+}
+uint64_t n_rows(const d2g_cmp_params *p) { return p->shape == D2G_PANEL ? p->n - p->nq : p->n; }
+uint64_t n_cols(const d2g_cmp_params *p) { return p->shape == D2G_PANEL ? p->nq : p->n; }
+uint64_t rows_size(const d2g_cmp_params *p, uint64_t r0, uint64_t r1) {
+    if (p->shape == D2G_SYMMETRIC) {
+        auto tri = [&](uint64_t i) { return i * p->n - i * (i + 1) / 2; };
+        return tri(r1) - tri(r0);
+    }
+    return (r1 - r0) * n_cols(p);
+}
+
+int make_consts(d2g_ctx *c, const d2g_cmp_params *p, d2g::CmpConsts *k) {
+    const uint32_t S = p->sketchsize;
+    k->invdenom = xf::from_long_double(1.L / S);
+    k->eps = xf::from_long_double(1e-15L);
+    k->poisson_mult = -1. / std::max(1, p->k);
+    k->S = S; k->measure = p->measure; k->cmp_kind = p->cmp_kind;
+    k->fast_sim = (p->measure == D2G_SIMILARITY && p->cmp_kind == D2G_CMP_GTLT && (S & (S - 1)) == 0) ? 1 : 0;
+    k->eq_llr_lut = nullptr;
+    if (p->cmp_kind == D2G_CMP_EQ && p->measure == D2G_POISSON_LLR) {
+        if (c->lut_S != S || c->lut_k != p->k) {
+            // equality branch of the Mash distance is long-double logl on the host in the reference
+            // (cmp_core.cpp:361,509); it only depends on the integer count, so tabulate it here.
+            std::vector<float> lut(S + 1);
+            const long double invdenom = 1.L / S;
+            for (uint32_t e = 0; e <= S; ++e) {
+                long double ret = invdenom * e;
+                ret = ret ? (long double)(double)(logl(2. * ret / (1. + ret)) * k->poisson_mult) : (long double)INFINITY;
+                if (isnan(ret) || isinf(ret)) ret = __LDBL_MAX__;
+                lut[e] = (float)ret;
+            }
+            if (int rc = c->clut.reserve((S + 1) * 4)) return rc;
+            CU(cudaMemcpyAsync(c->clut.p, lut.data(), (S + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            c->lut_S = S; c->lut_k = p->k;
+        }
+        k->eq_llr_lut = c->clut.as<float>();
+    }
+    return D2G_OK;
+}
+
+int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, const double *regs_d, const double *cards_d,
+               uint64_t r0, uint64_t r1, float *out_d, uint32_t *c0_d, uint32_t *c1_d) {
+    if (r1 <= r0) return D2G_OK;
+    d2g::CmpArgs a;
+    a.regs = regs_d; a.cards = cards_d; a.n = p->n; a.row0 = r0; a.row1 = r1;
+    a.col_base = p->shape == D2G_PANEL ? p->n - p->nq : 0;
+    a.ncols = n_cols(p); a.shape = p->shape; a.out = out_d; a.c0_out = c0_d; a.c1_out = c1_d; a.c = k;
+    if (a.ncols == 0) return D2G_OK;
+    const uint64_t tiles_i = (r1 - r0 + d2g::CMP_T - 1) / d2g::CMP_T;
+    a.tiles_j = (a.ncols + d2g::CMP_T - 1) / d2g::CMP_T;
+    const uint64_t grid = tiles_i * a.tiles_j;
+    if (grid > 0x7fffffffULL) return fail(D2G_EINVAL, "row block too large for one launch");
+    if (p->cmp_kind == D2G_CMP_GTLT) d2g::cmp_tile_kernel<0><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
+    else d2g::cmp_tile_kernel<1><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return D2G_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+uint64_t d2g_cmp_output_size(const d2g_cmp_params *p) { return p ? rows_size(p, 0, n_rows(p)) : 0; }
+
+int d2g_cmp_rows_size(const d2g_cmp_params *p, uint64_t r0, uint64_t r1, uint64_t *n_vals) {
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    if (n_vals) *n_vals = rows_size(p, r0, r1);
+    return D2G_OK;
+}
+
+int d2g_densify_dev(d2g_ctx *c, double *sig_d, uint64_t *kmers_d, uint64_t n, uint32_t S) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (!n || !S) return D2G_OK;
+    CU(cudaSetDevice(c->device));
+    const uint64_t tot = n * S;
+    if (int rc = c->ctmp.reserve(tot * 8)) return rc;
+    if (kmers_d) if (int rc = c->cktmp.reserve(tot * 8)) return rc;
+    d2g::densify_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(sig_d, kmers_d, n, S, c->ctmp.as<double>(), c->cktmp.as<uint64_t>());
+    c->launches++;
+    CU(cudaMemcpyAsync(sig_d, c->ctmp.p, tot * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (kmers_d) CU(cudaMemcpyAsync(kmers_d, c->cktmp.p, tot * 8, cudaMemcpyDeviceToDevice, c->stream));
+    return D2G_OK;
+}
+
+int d2g_densify(d2g_ctx *c, double *sig, uint64_t *kmers, uint64_t n, uint32_t S) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (!n || !S) return D2G_OK;
+    CU(cudaSetDevice(c->device));
+    const uint64_t tot = n * S;
+    if (int rc = c->cregs.reserve(tot * 8)) return rc;
+    CU(cudaMemcpyAsync(c->cregs.p, sig, tot * 8, cudaMemcpyHostToDevice, c->stream));
+    if (kmers) { if (int rc = c->ids.reserve(tot * 8)) return rc; CU(cudaMemcpyAsync(c->ids.p, kmers, tot * 8, cudaMemcpyHostToDevice, c->stream)); }
+    if (int rc = d2g_densify_dev(c, c->cregs.as<double>(), kmers ? c->ids.as<uint64_t>() : nullptr, n, S)) return rc;
+    CU(cudaMemcpyAsync(sig, c->cregs.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (kmers) CU(cudaMemcpyAsync(kmers, c->ids.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return D2G_OK;
+}
+
+int d2g_cmp_rows_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *regs_d, const double *cards_d,
+                     uint64_t r0, uint64_t r1, float *out_d) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    CU(cudaSetDevice(c->device));
+    d2g::CmpConsts k;
+    if (int rc = make_consts(c, p, &k)) return rc;
+    return launch_cmp(c, p, k, regs_d, cards_d, r0, r1, out_d, nullptr, nullptr);
+}
+
+int d2g_cmp_stream(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards,
+                   uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    if (!sink) return fail(D2G_EINVAL, "null sink");
+    if (r0 == r1 || p->n == 0) return D2G_OK;
+    CU(cudaSetDevice(c->device));
+    const uint32_t S = p->sketchsize;
+    if (int rc = c->cregs.reserve(p->n * S * 8)) return rc;
+    if (int rc = c->ccards.reserve(p->n * 8)) return rc;
+    CU(cudaMemcpyAsync(c->cregs.p, regs, p->n * S * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ccards.p, cards, p->n * 8, cudaMemcpyHostToDevice, c->stream));
+    d2g::CmpConsts k;
+    if (int rc = make_consts(c, p, &k)) return rc;
+    // row blocks of <= ~64M values, double-buffered: block b+1 computes while block b drains to the sink
+    const uint64_t max_vals = 64ULL << 20;
+    const uint64_t ncol = n_cols(p);
+    uint64_t rows_per = std::max<uint64_t>(d2g::CMP_T, max_vals / std::max<uint64_t>(1, ncol) / d2g::CMP_T * d2g::CMP_T);
+    uint64_t cap_vals = 0;
+    for (uint64_t b = r0; b < r1; b += rows_per) cap_vals = std::max(cap_vals, rows_size(p, b, std::min(r1, b + rows_per)));
+    if (int rc = c->cout.reserve(2 * cap_vals * 4)) return rc;
+    if (int rc = c->pin[0].reserve(cap_vals * 4)) return rc;
+    if (int rc = c->pin[1].reserve(cap_vals * 4)) return rc;
+    struct Pending { uint64_t b0, b1, nv; int slot; bool live; } pend{0, 0, 0, 0, false};
+    int slot = 0;
+    for (uint64_t b = r0; b < r1; b += rows_per) {
+        const uint64_t e = std::min(r1, b + rows_per), nv = rows_size(p, b, e);
+        float *out_d = c->cout.as<float>() + (uint64_t)slot * cap_vals;
+        if (int rc = launch_cmp(c, p, k, c->cregs.as<double>(), c->ccards.as<double>(), b, e, out_d, nullptr, nullptr)) return rc;
+        CU(cudaMemcpyAsync(c->pin[slot].p, out_d, nv * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->ev[slot], c->stream));
+        if (pend.live) {
+            CU(cudaEventSynchronize(c->ev[pend.slot]));
+            if (sink(user, (const float *)c->pin[pend.slot].p, pend.b0, pend.b1 - pend.b0, pend.nv)) return fail(D2G_EIO, "sink aborted");
+        }
+        pend = {b, e, nv, slot, true};
+        slot ^= 1;
+    }
+    if (pend.live) {
+        CU(cudaEventSynchronize(c->ev[pend.slot]));
+        if (sink(user, (const float *)c->pin[pend.slot].p, pend.b0, pend.b1 - pend.b0, pend.nv)) return fail(D2G_EIO, "sink aborted");
+    }
+    return D2G_OK;
+}
+
+static int copy_sink(void *user, const float *block, uint64_t, uint64_t, uint64_t n_vals) {
+    float **dst = (float **)user;
+    memcpy(*dst, block, n_vals * 4);
+    *dst += n_vals;
+    return 0;
+}
+
+int d2g_cmp_matrix(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards, float *out) {
+    if (int rc = check_cmp_params(p)) return rc;
+    float *cursor = out;
+    return d2g_cmp_stream(c, p, regs, cards, 0, n_rows(p), copy_sink, &cursor);
+}
+
+int d2g_cmp_counts(d2g_ctx *c, uint32_t S, int32_t cmp_kind, const double *rows, uint64_t nr, const double *cols, uint64_t nc,
+                   uint32_t *c0_out, uint32_t *c1_out) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (!nr || !nc) return D2G_OK;
+    CU(cudaSetDevice(c->device));
+    d2g_cmp_params p{};
+    p.sketchsize = S; p.cmp_kind = cmp_kind; p.measure = D2G_SIMILARITY; p.k = 31; p.shape = D2G_PANEL; p.n = nr + nc; p.nq = nc;
+    if (int rc = check_cmp_params(&p)) return rc;
+    if (int rc = c->cregs.reserve(p.n * S * 8)) return rc;
+    CU(cudaMemcpyAsync(c->cregs.p, rows, nr * S * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->cregs.as<double>() + nr * S, cols, nc * S * 8, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = c->cout.reserve(2 * nr * nc * 4)) return rc;
+    uint32_t *c0_d = c->cout.as<uint32_t>(), *c1_d = c0_d + nr * nc;
+    d2g::CmpConsts k;
+    if (int rc = make_consts(c, &p, &k)) return rc;
+    if (int rc = launch_cmp(c, &p, k, c->cregs.as<double>(), nullptr, 0, nr, nullptr, c0_d, cmp_kind == D2G_CMP_GTLT ? c1_d : nullptr)) return rc;
+    if (c0_out) CU(cudaMemcpyAsync(c0_out, c0_d, nr * nc * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (c1_out && cmp_kind == D2G_CMP_GTLT) CU(cudaMemcpyAsync(c1_out, c1_d, nr * nc * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return D2G_OK;
+}
+
+} // extern "C"

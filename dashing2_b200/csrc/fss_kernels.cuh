@@ -1,0 +1,251 @@
+// fss_kernels.cuh -- K3: Full (continuous) SetSketch register construction on the device.
+//
+// Reference: CSetSketch<double>::update, /root/reference/src/setsketch.h:369-423 (max-tree mvt_t
+// :123-167, lazy Fisher-Yates bonsai/hll/include/sketch/fy.h:14-66, WyRand<uint32_t,2> aesctr/wy.h,
+// flog.h, kahan.h).  Per element id the reference generates an increasing sequence
+//     ev_0 = -log(CEHasher(id ^ C) * 2^-64) / m,   ev_t = ev_{t-1} (+Kahan) -log(wy_t(id) * 2^-64) / (m - t)
+// and applies reg[pi_t] = min(reg[pi_t], ev_t) along a per-element random permutation pi until ev_t
+// exceeds the current maximum register.  The early exit (and its 0.7*flog pre-test) only skips updates
+// that could not lower any register, so the final registers are the element-wise minimum over all
+// elements of all (pi_t, ev_t) -- independent of element order.  That is what is computed here:
+//
+//   boot   : over a sample of the stream, the t=0 contribution alone (register pi_0 receives ev_0; the
+//            largest CEHasher value per register gives the smallest ev_0) -> a per-entity upper bound T
+//            of the final maximum register;
+//   main   : every element whose ev_0 <= T walks its sequence while ev_t <= T, atomicMin into registers
+//            held in shared memory (order-preserving u64 keys of the doubles).  Elements are first
+//            compacted into a shared-memory queue so the walk runs on dense warps;
+//   long   : walks longer than FSS_SPARSE steps (only when T is loose: tiny inputs) are replayed by a
+//            second kernel with a dense permutation state in HBM scratch.
+// log() is ref_log (devlog.cuh), bit-identical to the host libm; the Kahan increment is the fused
+// fma(b, log, -carry) that the reference binary executes (GCC contracts `b*log(v) - carry`).
+#pragma once
+#include "common.cuh"
+#include "devlog.cuh"
+#include "sketch_kernels.cuh"
+
+namespace d2g {
+
+constexpr uint64_t FSS_XOR = 0xb2069fc679a8da0bULL;   // setsketch.h:376
+constexpr int FSS_SPARSE = 24;                         // walk steps kept in the per-thread sparse permutation
+
+__host__ __device__ __forceinline__ uint64_t dkey(double d) {   // order-preserving u64 key of a double
+    uint64_t b;
+#if defined(__CUDA_ARCH__)
+    b = (uint64_t)__double_as_longlong(d);
+#else
+    memcpy(&b, &d, 8);
+#endif
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ double dunkey(uint64_t k) {
+    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d; memcpy(&d, &b, 8); return d;
+#endif
+}
+constexpr uint64_t FSS_KEY_EMPTY = 0x7fefffffffffffffULL | 0x8000000000000000ULL; // dkey(DBL_MAX), setsketch.h:130
+
+// flog.h:14-20
+__device__ __forceinline__ double flog_d(double x) {
+    return __fma_rn((double)(unsigned long long)__double_as_longlong(x), 1.539095918623324e-16, -709.0895657128241);
+}
+
+// ---- boot: t = 0 contributions only --------------------------------------------------------------
+struct FssBootConsumer {
+    struct Params { uint64_t *maxrv; FastMod32 fm; uint32_t m; };   // maxrv [n_entities][m], zero-initialised
+    static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8; }
+    uint64_t *s; Params p;
+    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp) {
+        p = pp; s = reinterpret_cast<uint64_t *>(smem);
+        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) s[i] = 0;
+    }
+    __device__ __forceinline__ void begin_entity(uint32_t) {}
+    __device__ __forceinline__ void consume(uint64_t hv) {
+        const uint64_t rv = cehash(hv ^ FSS_XOR);
+        uint64_t st = rv;
+        const uint32_t idx = fastmod32((uint32_t)wyhash64(st), p.fm);   // first draw of the permutation, fy.h:36-37
+        if (rv > s[idx]) atomicMax(reinterpret_cast<unsigned long long *>(s + idx), (unsigned long long)rv);
+    }
+    __device__ __forceinline__ void end_tile(uint32_t) {}
+    __device__ __forceinline__ void flush(uint32_t ent) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) {
+            const uint64_t v = s[i];
+            if (v) { atomicMax(reinterpret_cast<unsigned long long *>(p.maxrv + (uint64_t)ent * p.m + i), (unsigned long long)v); s[i] = 0; }
+        }
+        __syncthreads();
+    }
+};
+
+// one CTA per entity: T = max_i ev_0(maxrv_i) (DBL_MAX when some register was never hit) and the integer
+// pre-filter rvmin (every rv < rvmin certainly has ev_0 > T)
+__global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *T, uint64_t *rvmin) {
+    __shared__ double red[256];
+    const uint32_t ent = blockIdx.x;
+    const double bv0 = -1. / m;
+    double mx = 0.;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const uint64_t rv = maxrv[(uint64_t)ent * m + i];
+        const double ev = rv ? __dmul_rn(bv0, ref_log(__dmul_rn(__ull2double_rn(rv), 0x1p-64))) : 1.7976931348623157e308;
+        mx = fmax(mx, ev);
+    }
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    if (threadIdx.x == 0) {
+        const double t = red[0];
+        T[ent] = t;
+        uint64_t rm = 0;
+        if (t < 1e300) {
+            const double tv = exp(-t * (double)m) * (1. - 1e-6);   // any slightly-low estimate is safe
+            const double scaled = tv * 18446744073709551616.0;
+            rm = scaled >= 18446744073709549568.0 ? 0xFFFFFFFFFFFFF800ULL : (scaled <= 0. ? 0 : (uint64_t)scaled);
+        }
+        rvmin[ent] = rm;
+    }
+}
+
+// ---- the per-element walk ------------------------------------------------------------------------
+struct WalkRng {   // WyRand<uint32_t, 2>: two 64-bit draws per refill, served as four little-endian u32
+    uint64_t state, b0, b1; int off;
+    __device__ __forceinline__ void seed(uint64_t s) { state = s; off = 4; }
+    __device__ __forceinline__ uint32_t next() {
+        if (off == 4) { b0 = wyhash64(state); b1 = wyhash64(state); off = 0; }
+        const uint64_t w = (off & 2) ? b1 : b0;
+        const uint32_t r = (off & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
+        ++off;
+        return r;
+    }
+};
+
+// Replays the sequence of one element against registers `keys` (shared or global) with threshold T.
+// PermState provides step(i, samp) -> register index (lazy Fisher-Yates) and may report overflow.
+template <class PermState>
+__device__ __forceinline__ bool fss_walk(uint64_t x, uint32_t m, double T, uint64_t *keys, PermState &ps) {
+    uint64_t hid = x;
+    uint64_t rv = cehash(x ^ FSS_XOR);
+    const double tv = __dmul_rn(__ull2double_rn(rv), 0x1p-64);
+    const double bv0 = -1. / m;
+    double ev = __dmul_rn(bv0, ref_log(tv));
+    if (ev > T) return true;
+    WalkRng rng; rng.seed(rv);
+    double carry = 0.;
+    uint32_t bi = 1;
+    for (uint32_t i = 0;; ++i) {
+        const uint32_t samp = rng.next() % (m - i);
+        uint32_t idx;
+        if (!ps.step(i, samp, idx)) return false;                       // sparse state exhausted
+        const uint64_t kk = dkey(ev);
+        if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
+        if (bi == m) return true;
+        rv = wyhash64(hid);
+        const double bv = -(1. / (double)(m - bi)); ++bi;               // getbeta, setsketch.h:300-302
+        const double nv = __dmul_rn(__ull2double_rn(rv), 0x1p-64);
+        if (__fma_rn(__dmul_rn(bv, flog_d(nv)), .7, ev) > T) return true; // conservative pre-test, setsketch.h:418
+        const double inc = __fma_rn(bv, ref_log(nv), -carry);           // kahan.h:8-13 (contracted by the reference build)
+        const double tmp = __dadd_rn(ev, inc);
+        carry = __dadd_rn(__dadd_rn(tmp, -ev), -inc);
+        ev = tmp;
+        if (ev > T) return true;
+    }
+}
+
+struct SparsePerm {   // lazy Fisher-Yates over a handful of touched slots (fy.h:35-47)
+    uint32_t key[FSS_SPARSE], val[FSS_SPARSE]; int n = 0;
+    __device__ __forceinline__ uint32_t get(uint32_t j) const { for (int q = 0; q < n; ++q) if (key[q] == j) return val[q]; return j; }
+    __device__ __forceinline__ bool step(uint32_t i, uint32_t samp, uint32_t &out) {
+        const uint32_t j = i + samp;
+        out = get(j);
+        const uint32_t gi = get(i);
+        for (int q = 0; q < n; ++q) if (key[q] == j) { val[q] = gi; return true; }
+        if (n == FSS_SPARSE) return false;
+        key[n] = j; val[n] = gi; ++n;
+        return true;
+    }
+};
+
+struct DensePerm {    // the reference's layout: g/v arrays with a generation counter
+    uint32_t *g, *v; uint32_t c;
+    __device__ __forceinline__ bool step(uint32_t i, uint32_t samp, uint32_t &out) {
+        const uint32_t j = i + samp;
+        out = v[j] == c ? g[j] : j;
+        g[j] = v[i] == c ? g[i] : i;
+        v[j] = c;
+        return true;
+    }
+};
+
+struct FssMainConsumer {
+    struct Params {
+        uint64_t *keys;            // [n_entities][m], initialised to FSS_KEY_EMPTY
+        const double *T; const uint64_t *rvmin;
+        uint64_t *ovf; unsigned long long *ovf_count; uint64_t ovf_cap;   // (x, entity) pairs for the long-walk kernel
+        uint32_t m;
+    };
+    static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8 + (size_t)SK_TILE * 8 + 16; }
+    uint64_t *skeys, *queue; int *qn; Params p; double T; uint64_t rvmin;
+    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp) {
+        p = pp; skeys = reinterpret_cast<uint64_t *>(smem); queue = skeys + p.m; qn = reinterpret_cast<int *>(queue + SK_TILE);
+        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) skeys[i] = FSS_KEY_EMPTY;
+        if (threadIdx.x == 0) *qn = 0;
+        T = 1.7976931348623157e308; rvmin = 0;
+    }
+    __device__ __forceinline__ void begin_entity(uint32_t ent) { T = p.T[ent]; rvmin = p.rvmin[ent]; }
+    __device__ __forceinline__ void consume(uint64_t hv) {
+        if (cehash(hv ^ FSS_XOR) < rvmin) return;
+        queue[atomicAdd(qn, 1)] = hv;
+    }
+    __device__ __forceinline__ void end_tile(uint32_t ent) {
+        __syncthreads();
+        const int n = *qn;
+        for (int q = threadIdx.x; q < n; q += SK_THREADS) {
+            const uint64_t x = queue[q];
+            SparsePerm sp;
+            if (!fss_walk(x, p.m, T, skeys, sp)) {
+                const unsigned long long slot = atomicAdd(p.ovf_count, 1ULL);
+                if (slot < p.ovf_cap) { p.ovf[2 * slot] = x; p.ovf[2 * slot + 1] = ent; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *qn = 0;
+    }
+    __device__ __forceinline__ void flush(uint32_t ent) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) {
+            const uint64_t v = skeys[i];
+            if (v != FSS_KEY_EMPTY) { atomicMin(reinterpret_cast<unsigned long long *>(p.keys + (uint64_t)ent * p.m + i), (unsigned long long)v); skeys[i] = FSS_KEY_EMPTY; }
+        }
+        __syncthreads();
+    }
+};
+
+// long walks: one thread per queued element, dense permutation state in HBM scratch (slot-private)
+__global__ void fss_longwalk_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,
+                                    const double *T, uint64_t *keys, uint32_t *scratch) {
+    const uint64_t slot = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t nslots = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n = min((uint64_t)*ovf_count, ovf_cap);
+    DensePerm dp; dp.g = scratch + slot * 2ULL * m; dp.v = dp.g + m; dp.c = 0;   // scratch zero-initialised; generations start at 1
+    for (uint64_t e = slot; e < n; e += nslots) {
+        const uint64_t x = ovf[2 * e]; const uint32_t ent = (uint32_t)ovf[2 * e + 1];
+        ++dp.c;
+        fss_walk(x, m, T[ent], keys + (uint64_t)ent * m, dp);
+    }
+}
+
+// keys -> doubles (first S registers) and cardinality m / sum(reg) (setsketch.h:553-561; the reference
+// sums under `omp simd`, i.e. in compiler-chosen order: sequential here, agreement ~1e-15 relative)
+__global__ void fss_finalize_kernel(const uint64_t *keys, uint32_t n_ent, uint32_t m, double *sig, double *card) {
+    const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (sig && e < (uint64_t)n_ent * m) sig[e] = dunkey(keys[e]);
+    if (card && e < n_ent) {
+        double s = 0.;
+        for (uint32_t i = 0; i < m; ++i) s = __dadd_rn(s, dunkey(keys[e * m + i]));
+        card[e] = (double)m / s;
+    }
+}
+
+} // namespace d2g

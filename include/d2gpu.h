@@ -1,0 +1,152 @@
+/*
+ * d2gpu.h -- C ABI of libd2gpu.so: the B200 (sm_100a) implementation of dashing2's two hot paths.
+ *
+ * The reference (dnbaker/dashing2 @ 3906ebde, paths relative to /root/reference) has no FFI; its
+ * seam for these paths is a handful of C++ functions.  Each entry point below names the reference
+ * function(s) it replaces.  Conventions: plain pointers + sizes, no C++/torch types; every call
+ * returns 0 on success or a negative D2G_E* code, with a message in d2g_last_error() (thread local);
+ * no exception crosses this boundary.  A d2g_ctx owns one CUDA device + stream + scratch memory and
+ * is thread-compatible (one thread at a time per ctx).  There is NO CPU fallback: without a CUDA
+ * device d2g_init fails with D2G_ENODEVICE.
+ *
+ * Pointer naming: plain = host memory; *_d = device memory on the ctx's device.
+ */
+#ifndef D2GPU_H
+#define D2GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2G_OK 0
+#define D2G_EINVAL (-1)      /* bad argument / unsupported parameter combination */
+#define D2G_ENODEVICE (-2)   /* no usable CUDA device */
+#define D2G_ECUDA (-3)       /* CUDA runtime error (see d2g_last_error) */
+#define D2G_ENOMEM (-4)
+#define D2G_EIO (-5)
+#define D2G_EUNSUPPORTED (-6)/* a reference mode this library does not implement on the GPU */
+
+typedef struct d2g_ctx d2g_ctx;
+
+int d2g_init(d2g_ctx **ctx, int device);
+void d2g_destroy(d2g_ctx *ctx);
+const char *d2g_last_error(void);
+const char *d2g_version(void);
+/* The CUDA stream (cudaStream_t) every call on this ctx is enqueued on; for event timing. */
+void *d2g_stream(d2g_ctx *ctx);
+int d2g_sync(d2g_ctx *ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+uint64_t d2g_launch_count(const d2g_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sketch path.  Replaces the per-file body of fastx2sketch (src/fastxsketch.cpp:303-624): k-mer
+ * encode (bonsai encoder.h:241-272), canonicalise (kmerutil.h:137), windowed minimizer
+ * (encoder.h:212-217, qmap.h:79-87), maskfn (src/enums.h:136-140) and the sketch update
+ * (src/oph.h:176-211 / src/setsketch.h:369-423 / bmh.h:269-316 / bmh.h:662-700).
+ * ---------------------------------------------------------------------------------------------- */
+enum { D2G_MODE_OPMH = 0, D2G_MODE_FULL_SETSKETCH = 1, D2G_MODE_BAGMINHASH = 2, D2G_MODE_PROBMINHASH = 3 };
+
+typedef struct {
+    int32_t k;                 /* 1..32 (2-bit exact encoding; k > 32 rolling hash is out of scope) */
+    int32_t w;                 /* window; w <= k means unwindowed */
+    int32_t canon;             /* reference default 1 (src/sketch_main.cpp:28) */
+    int32_t mode;              /* D2G_MODE_* */
+    uint64_t xormask;          /* maskfn XOR mask: 0 for --seed 0, else Wang(seed) (src/enums.cpp:133) */
+    uint32_t sketchsize;       /* S */
+    uint32_t count_threshold;  /* --count-threshold; 0/1 = off */
+    uint64_t countsketch_size; /* --countsketch-size; 0 = exact counting */
+} d2g_sketch_params;
+
+/* Number of registers per entity the OPMH sketch keeps (S rounded up to even, src/oph.h:145). */
+uint32_t d2g_opmh_m(uint32_t sketchsize);
+/* The metric unit: k-mer positions fed to the sketch = sum over records of max(0, len-k+1). */
+uint64_t d2g_count_kmers(const uint64_t *rec_off, uint64_t n_rec, int32_t k);
+
+/*
+ * One batch of records belonging to n_entities sketches (entity = input file, or record under
+ * --parse-by-seq).  seq = concatenated record bytes with line terminators already removed
+ * (kseq semantics, bonsai/klib/kseq.h:178); rec_off[n_rec+1] byte offsets; rec_entity[n_rec] the
+ * sketch each record feeds (non-decreasing).  Outputs are caller-allocated and may be NULL when
+ * not wanted:
+ *   regs_u64_out [n_entities][m]  OPMH raw 64-bit bucket minima (m = d2g_opmh_m(S)), ~0 = empty
+ *   sig_out      [n_entities][S]  f64 registers exactly as the reference stores them in
+ *                                 SketchingResult::signatures_ (src/fastxsketch.h:47)
+ *   card_out     [n_entities]     cardinality estimate (oph.h:240-247 / setsketch.h:553-561 / total weight)
+ *   ids_out      [n_entities][S]  --save-kmers ids (oph.h:264-271), OPMH/FSS only
+ * All pointers are HOST memory; the call copies in, runs the kernels, copies out and synchronises.
+ */
+int d2g_sketch_batch(d2g_ctx *ctx, const d2g_sketch_params *p,
+                     const char *seq, const uint64_t *rec_off, const uint32_t *rec_entity,
+                     uint64_t n_rec, uint32_t n_entities,
+                     uint64_t *regs_u64_out, double *sig_out, double *card_out, uint64_t *ids_out,
+                     uint64_t *n_kmers_hashed);
+
+/* Host-side transform of OPMH bucket minima (host memory) into the reference's f64 signatures and
+ * cardinality: sig = -1/(m-nempty) * logl(2^-64 * (2^64 - reg)), card = m*m / sum(reg * 2^-64), both in
+ * x87 long double exactly as src/oph.h:240-263 does on the host. regs_u64 [n][d2g_opmh_m(S)]. */
+int d2g_opmh_finalize(const uint64_t *regs_u64, uint32_t n_entities, uint32_t sketchsize, double *sig_out, double *card_out);
+
+/* Same computation with inputs and outputs resident in device memory (asynchronous on
+ * d2g_stream(ctx); no host copies).  seq_d must be readable for total_len rounded up to 16 bytes. */
+int d2g_sketch_batch_dev(d2g_ctx *ctx, const d2g_sketch_params *p,
+                         const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_entity_d,
+                         uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
+                         uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Compare path.  Replaces compare() (src/cmp_core.cpp:349-575), densify (:577-613) and the
+ * row/column orderings of emit_rectangular (src/emitrect.cpp:198-326).
+ * ---------------------------------------------------------------------------------------------- */
+enum { D2G_SIMILARITY = 0, D2G_CONTAINMENT = 1, D2G_SYMMETRIC_CONTAINMENT = 2, D2G_POISSON_LLR = 3,
+       D2G_INTERSECTION = 4, D2G_UNION_SIZE = 5 };
+enum { D2G_CMP_GTLT = 0,   /* SetSketch / OPMH registers: count a>b and a<b (cmp_core.cpp:458-494) */
+       D2G_CMP_EQ = 1 };   /* BagMinHash / ProbMinHash / b-bit: count bitwise-equal (cmp_core.cpp:495-517) */
+enum { D2G_SYMMETRIC = 0,  /* condensed upper triangle, rows i<j (emitrect.cpp:290-323) */
+       D2G_ASYMMETRIC = 1, /* full n x n (emitrect.cpp:249-268) */
+       D2G_PANEL = 2 };    /* rows = first n-nq sketches (-F), cols = last nq (-Q) (emitrect.cpp:229-246) */
+
+typedef struct {
+    uint32_t sketchsize;   /* S registers of 8 bytes per sketch */
+    int32_t cmp_kind;      /* D2G_CMP_* */
+    int32_t measure;       /* D2G_* measure */
+    int32_t k;             /* k-mer length, only used by D2G_POISSON_LLR */
+    int32_t shape;         /* D2G_SYMMETRIC / D2G_ASYMMETRIC / D2G_PANEL */
+    uint64_t n;            /* total sketches */
+    uint64_t nq;           /* PANEL: number of query (column) sketches */
+} d2g_cmp_params;
+
+/* In-place densification of OPMH signatures (empty == 0.0), src/cmp_core.cpp:577-613. */
+int d2g_densify(d2g_ctx *ctx, double *sig, uint64_t *kmers /*nullable*/, uint64_t n, uint32_t sketchsize);
+int d2g_densify_dev(d2g_ctx *ctx, double *sig_d, uint64_t *kmers_d, uint64_t n, uint32_t sketchsize);
+
+/* Number of float32 values the full output holds for these parameters. */
+uint64_t d2g_cmp_output_size(const d2g_cmp_params *p);
+/* Rows [row_begin,row_end) of the output, as emit_rectangular would produce them; returns the number
+ * of float32 values in that row range through *n_vals. */
+int d2g_cmp_rows_size(const d2g_cmp_params *p, uint64_t row_begin, uint64_t row_end, uint64_t *n_vals);
+
+/* Whole matrix, host in / host out (regs f64[n][S], cards f64[n], out f32[d2g_cmp_output_size]). */
+int d2g_cmp_matrix(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards, float *out);
+/* Row range with a sink: results are delivered in row order in blocks (host memory valid only during
+ * the callback), so a front-end can stream them to the reference's output format. sink returns 0 to continue. */
+typedef int (*d2g_sink_fn)(void *user, const float *block, uint64_t first_row, uint64_t n_rows, uint64_t n_vals);
+int d2g_cmp_stream(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards,
+                   uint64_t row_begin, uint64_t row_end, d2g_sink_fn sink, void *user);
+/* Device-resident variant: regs_d/cards_d/out_d on the device; computes rows [row_begin,row_end) into
+ * out_d (packed, starting at offset 0); asynchronous on the ctx stream. */
+int d2g_cmp_rows_dev(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs_d, const double *cards_d,
+                     uint64_t row_begin, uint64_t row_end, float *out_d);
+/* Raw integer counts for one tile (rows x cols), for callers that finalise themselves:
+ * c0 = #(row > col) (or #equal for D2G_CMP_EQ), c1 = #(row < col). Host pointers. */
+int d2g_cmp_counts(d2g_ctx *ctx, uint32_t sketchsize, int32_t cmp_kind,
+                   const double *rows, uint64_t n_rows, const double *cols, uint64_t n_cols,
+                   uint32_t *c0_out, uint32_t *c1_out);
+
+void d2g_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

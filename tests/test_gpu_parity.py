@@ -1,0 +1,209 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libd2gpu.so) against the committed golden
+vectors of the reference binary and against the oracle on seeded inputs.  Bit-exact for integer
+registers, signatures and float32 matrices; 1e-12 relative only for the Full SetSketch cardinality
+(the reference sums registers in compiler-chosen SIMD order)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import expected, GOLD
+from gpu_util import ctx, pack_batch, pack_files
+
+pytestmark = pytest.mark.gpu
+
+SKETCH = {
+    "opmh_k31_S1024": dict(mode="opmh", S=1024, k=31),
+    "opmh_k31_w51_S512": dict(mode="opmh", S=512, k=31, w=51),
+    "opmh_k21_S256_nocanon": dict(mode="opmh", S=256, k=21, canon=False),
+    "opmh_k31_S256_seed17": dict(mode="opmh", S=256, k=31, seed=17),
+    "opmh_k15_S64": dict(mode="opmh", S=64, k=15),
+    "opmh_k31_S1000": dict(mode="opmh", S=1000, k=31),
+    "fss_k31_S256": dict(mode="fss", S=256, k=31),
+    "fss_k31_w51_S1024": dict(mode="fss", S=1024, k=31, w=51),
+}
+
+
+def u64(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+@pytest.mark.parametrize("case", sorted(SKETCH))
+def test_sketch_matches_reference_golden(case, golden_inputs):
+    names, paths = golden_inputs
+    z = np.load(expected(case + ".npz"))
+    c = ctx()
+    seq, off, ent = pack_files(paths)
+    r = c.sketch_batch(seq, off, ent, len(paths), c.params(**SKETCH[case]))
+    for i, nm in enumerate(names):
+        assert np.array_equal(u64(r["sig"][i]), u64(z["sigs"][i])), (case, nm)
+    if SKETCH[case]["mode"] == "opmh":
+        assert np.array_equal(u64(r["card"]), u64(z["cards"]))
+    else:
+        np.testing.assert_allclose(r["card"], z["cards"], rtol=1e-12)
+    assert r["n_kmers"] == sum(max(0, len(rec) - SKETCH[case]["k"] + 1) for p in paths for rec in O.read_fastx(p))
+
+
+def test_unsupported_modes_fail_loudly(golden_inputs):
+    from dashing2_b200.capi import D2GError
+    names, paths = golden_inputs
+    c = ctx()
+    seq, off, ent = pack_files(paths[:1])
+    with pytest.raises(D2GError):
+        c.sketch_batch(seq, off, ent, 1, c.params(mode="opmh", S=64, k=21, w=30, canon=False))
+    with pytest.raises(D2GError):
+        c.sketch_batch(seq, off, ent, 1, c.params(mode="opmh", S=64, k=40))
+
+
+def test_save_kmers_ids(golden_inputs):
+    names, paths = golden_inputs
+    z = np.load(expected("opmh_k31_S256_savekmers.npz"))
+    c = ctx()
+    seq, off, ent = pack_files(paths)
+    r = c.sketch_batch(seq, off, ent, len(paths), c.params(mode="opmh", S=256, k=31), want_ids=True)
+    assert np.array_equal(r["ids"], z["ids"])
+
+
+@pytest.mark.parametrize("mode,S,k,w", [("opmh", 1024, 31, -1), ("opmh", 4096, 31, 51), ("opmh", 333, 17, 40),
+                                         ("fss", 512, 31, -1), ("fss", 2048, 31, 51), ("opmh", 8192, 32, -1)])
+def test_sketch_matches_oracle_seeded(mode, S, k, w, tmp_path):
+    """Seeded inputs larger than the goldens (multi-tile, multi-CTA, several entities per CTA span)."""
+    from dashing2_b200 import synth
+    rng = np.random.default_rng(1234 + S)
+    files = []
+    for g, s in synth.family_genomes(5, 150_000, seed=77 + S):
+        b = bytearray(s.tobytes())
+        for p in rng.integers(0, len(b), 12):       # sprinkle invalid bases / lowercase
+            b[p] = ord("N")
+        for p in rng.integers(0, len(b), 200):
+            b[p] = b[p] | 0x20
+        cut = sorted(rng.integers(1, len(b) - 1, 3))  # multi-record entity, one tiny record
+        recs = [bytes(b[:cut[0]]), bytes(b[cut[0]:cut[1]]), b"ACGT", bytes(b[cut[1]:cut[2]]), b"", bytes(b[cut[2]:])]
+        files.append(recs)
+    files.append([b"ACGTAC"])          # entity with no k-mer at all
+    files.append([])                    # entity with no record
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    r = c.sketch_batch(seq, off, ent, len(files), c.params(mode=mode, S=S, k=k, w=w))
+    L = O.lib()
+    for e, recs in enumerate(files):
+        hv = [O.hash_stream(x, k, w) for x in recs]
+        hv = np.concatenate(hv) if hv else np.empty(0, dtype=np.uint64)
+        if mode == "opmh":
+            m = L.d2o_opmh_m(S)
+            regs = np.empty(m, dtype=np.uint64); cnt = np.empty(m, dtype=np.float64)
+            L.d2o_opmh_reset(regs, cnt, m); L.d2o_opmh_update(regs, cnt, m, hv, len(hv))
+            assert np.array_equal(r["regs_u64"][e], regs), (mode, S, e)
+            sig = np.empty(m, dtype=np.float64); L.d2o_opmh_sigs(regs, m, sig)
+            assert np.array_equal(u64(r["sig"][e]), u64(sig[:S]))
+            assert r["card"][e] == L.d2o_opmh_card(regs, m) or (np.isinf(r["card"][e]) and np.isinf(L.d2o_opmh_card(regs, m)))
+        else:
+            regs = np.empty(2 * S - 1, dtype=np.float64)
+            L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), None)
+            assert np.array_equal(u64(r["sig"][e]), u64(regs[:S])), (mode, S, e)
+            np.testing.assert_allclose(r["card"][e], L.d2o_css_card(regs, S), rtol=1e-12)
+
+
+def test_sketch_merge_property_full_size():
+    """Size-independent property at BASELINE scale (1 Mbp genomes, S=1024 / 4096): bucket minima are a
+    min-monoid, so sketch(A ++ B) == min(sketch(A), sketch(B)) register-wise, and sketching the same
+    bytes twice is idempotent."""
+    from dashing2_b200 import synth
+    c = ctx()
+    gen = [s.tobytes() for _, s in synth.family_genomes(4, 1_000_000, seed=4242)]
+    for kw in (dict(mode="opmh", S=1024, k=31), dict(mode="opmh", S=4096, k=31, w=51)):
+        p = c.params(**kw)
+        seq, off, ent = pack_batch([[gen[0]], [gen[1]], [gen[0], gen[1]], [gen[0], gen[0]]])
+        r = c.sketch_batch(seq, off, ent, 4, p)["regs_u64"]
+        assert np.array_equal(r[2], np.minimum(r[0], r[1]))
+        assert np.array_equal(r[3], r[0])
+
+
+def test_densify_matches_reference_golden():
+    raw = np.load(expected("opmh_k15_S64.npz")); den = np.load(expected("opmh_k15_S64_densified.npz"))
+    c = ctx()
+    got = c.densify(raw["sigs"])
+    assert np.array_equal(u64(got), u64(den["sigs"]))
+    p = c.cmp_params(64, len(got), "symmetric", "similarity", k=15)
+    assert np.array_equal(c.cmp_matrix(got, den["cards"], p).view(np.uint32), den["mat"].view(np.uint32))
+
+
+CMP = {"sim_sym": ("symmetric", "similarity"), "sim_asym": ("asymmetric", "similarity"),
+       "containment_sym": ("symmetric", "containment"), "symcontainment_sym": ("symmetric", "symmetric_containment"),
+       "mash_sym": ("symmetric", "poisson_llr"), "isz_sym": ("symmetric", "intersection"),
+       "usz_sym": ("symmetric", "union_size")}
+
+
+@pytest.mark.parametrize("kind", sorted(CMP))
+def test_compare_opmh_golden(kind):
+    z = np.load(expected("opmh_k31_S1024.npz"))
+    c = ctx()
+    sigs = c.densify(z["sigs"])
+    p = c.cmp_params(1024, len(sigs), CMP[kind][0], CMP[kind][1], k=31)
+    got = c.cmp_matrix(sigs, z["cards"], p)
+    exp = np.load(expected(f"cmp_opmh_k31_S1024_{kind}.npy"))
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+@pytest.mark.parametrize("suffix,cmp_kind", [(".ss", 0), (".bmh", 1)])
+@pytest.mark.parametrize("kind", sorted(CMP))
+def test_compare_presketched_golden(kind, suffix, cmp_kind):
+    f = expected(f"cmp_sk48{suffix}_{kind}.npy")
+    if not os.path.exists(f):
+        pytest.skip("no golden for this combination")
+    z = np.load(os.path.join(GOLD, "inputs", "sk48x256.npz"))
+    c = ctx()
+    p = c.cmp_params(256, 48, CMP[kind][0], CMP[kind][1], k=32, cmp_kind=cmp_kind)
+    got = c.cmp_matrix(z["regs"], z["cards"], p)
+    assert np.array_equal(got.view(np.uint32), np.load(f).view(np.uint32))
+
+
+@pytest.mark.parametrize("S", [1024, 1000, 4096, 77])
+@pytest.mark.parametrize("shape", ["symmetric", "asymmetric", "panel"])
+def test_compare_matches_oracle_seeded(S, shape):
+    """Ragged sizes (n not a multiple of the 64-pair tile, S not a multiple of the 32-register chunk),
+    all measures and both comparison kinds, against the oracle."""
+    from dashing2_b200 import synth
+    n, nq = 203, 71
+    regs, cards = synth.synthetic_sketches(n, S, seed=S + 5, n_families=7)
+    cards = cards * (1 + np.arange(n) % 9) / 3.0
+    regs[3] = regs[4]                     # identical pair
+    regs[10, : S // 2] = 0.0              # zeros
+    c = ctx()
+    for measure in ("similarity", "containment", "symmetric_containment", "poisson_llr", "intersection", "union_size"):
+        for cmp_kind in (0, 1):
+            p = c.cmp_params(S, n, shape, measure, k=31, cmp_kind=cmp_kind, nq=nq if shape == "panel" else 0)
+            got = c.cmp_matrix(regs, cards, p)
+            exp = O.allpairs(regs, cards, shape, measure, k=31, cmp_kind=cmp_kind, nq=nq)
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (S, shape, measure, cmp_kind)
+
+
+def test_compare_counts_and_stream_blocks():
+    from dashing2_b200 import synth
+    regs, cards = synth.synthetic_sketches(150, 512, seed=9, n_families=5)
+    c = ctx()
+    c0, c1 = c.cmp_counts(regs[:100], regs[100:])
+    a, b = regs[:100, None, :], regs[None, 100:, :]
+    assert np.array_equal(c0, (a > b).sum(-1)) and np.array_equal(c1, (a < b).sum(-1))
+    # streamed row ranges concatenate to the full matrix
+    p = c.cmp_params(512, 150, "symmetric")
+    full = c.cmp_matrix(regs, cards, p)
+    parts = []
+    for r0, r1 in ((0, 10), (10, 99), (99, 150)):
+        c.cmp_stream(regs, cards, p, r0, r1, lambda blk, fr, nr: parts.append(blk.copy()))
+    assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_compare_full_size_properties():
+    """BASELINE-scale property checks (S=4096, n=1500): the condensed symmetric matrix equals the upper
+    triangle of the asymmetric one; the asymmetric similarity matrix is symmetric with unit diagonal."""
+    from dashing2_b200 import synth
+    n, S = 1500, 4096
+    regs, cards = synth.synthetic_sketches(n, S, seed=31, n_families=40)
+    c = ctx()
+    sym = c.cmp_matrix(regs, cards, c.cmp_params(S, n, "symmetric"))
+    full = c.cmp_matrix(regs, cards, c.cmp_params(S, n, "asymmetric")).reshape(n, n)
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(sym, full[iu])
+    assert np.array_equal(full, full.T) and np.all(np.diag(full) == 1.0)
