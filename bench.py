@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- the dashing2 hot paths on B200: k-mers hashed/s (sketch) + pairwise compares/s (cmp).
+
+Workload = BASELINE.json configs[1]: 10 000 synthetic genomes x 5 Mbp, k=31 w=51, Full SetSketch
+S=4096, then all-pairs symmetric comparison of the 10 000 sketches.  One STEP is one pass of BOTH hot
+paths over the whole workload of this rank, inputs resident in HBM:
+    sketch : all genomes (50 G k-mer positions) -> f64[10000][4096] registers + cardinalities
+    cmp    : 49 995 000 pairs of those registers -> float32 condensed matrix
+`value` is the sketch throughput (k-mers hashed/s, whole job); the cmp throughput and its own roofline,
+e2e and cpu_baseline ride along under "cmp".  Weak scaling: every rank owns the same number of genomes;
+for cmp the ranks all-gather their registers (NCCL over NVLink, the path's one exchange step) and each
+computes an equal-area block of rows of the (N*10000)^2 triangle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Under torchrun (N > 1) one rank per GPU; rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, W, S = 31, 51, 4096
+METRIC = "k-mers hashed/s (sketch) + pairwise compares/s (cmp)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=10000, help="genomes per rank (config: 10000)")
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--e2e-genomes", type=int, default=256, help="genomes per host-buffer call in the e2e leg")
+    ap.add_argument("--cpu-genomes", type=int, default=16, help="genomes in the CPU-baseline sketch sample")
+    ap.add_argument("--cpu-cmp-n", type=int, default=3000, help="sketches in the CPU-baseline cmp sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU side: the reference's own OpenMP path (oracle/_ref binary) on a bounded sample of the workload
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_genomes, genome_len, cmp_n, threads, repeats=1, warm=True):
+    """Times `dashing2 sketch` and `dashing2 cmp` (unmodified reference, all host threads) on a sample of
+    the bench workload.  Returns dict(sketch_kmers_s, cmp_pairs_s, kind, cores, sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refbin
+    from dashing2_b200 import synth
+    exe = refbin.ref_binary()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    work = tempfile.mkdtemp(prefix="d2bench", dir=base)
+    try:
+        if exe is None:
+            return cpu_port_run(n_genomes, genome_len, cmp_n)
+        paths = synth.write_fasta_set(os.path.join(work, "fa"), n_genomes, genome_len, seed=2, n_families=max(1, n_genomes // 4))
+        flist = os.path.join(work, "files.txt")
+        open(flist, "w").write("\n".join(paths) + "\n")
+        sk_cmd = ["sketch", "-k", str(K), "-w", str(W), "--full-setsketch", "-S", str(S), "-p", str(threads),
+                  "-F", flist, "-o", os.path.join(work, "out.ss")]
+        regs, cards = synth.synthetic_sketches(cmp_n, S, seed=4, n_families=max(1, cmp_n // 64))
+        stk = os.path.join(work, "cmp.ss")
+        synth.write_stacked(stk, regs, cards, names=[f"s{i}" for i in range(cmp_n)])
+        cmp_cmd = ["cmp", "--presketched", "--binary-output", "--cmpout", os.path.join(work, "out.f32"), "-p", str(threads), stk]
+        if warm:  # discard one run each (thread spin-up, page cache)
+            refbin.run_ref(sk_cmd, threads=threads); refbin.run_ref(cmp_cmd, threads=threads)
+        ts, tc = [], []
+        for _ in range(repeats):
+            t0 = time.perf_counter(); refbin.run_ref(sk_cmd, threads=threads); ts.append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); refbin.run_ref(cmp_cmd, threads=threads); tc.append(time.perf_counter() - t0)
+        kmers = n_genomes * (genome_len - K + 1)
+        pairs = cmp_n * (cmp_n - 1) // 2
+        return dict(sketch_kmers_s=kmers / float(np.median(ts)), cmp_pairs_s=pairs / float(np.median(tc)),
+                    sketch_s=float(np.median(ts)), cmp_s=float(np.median(tc)), kind="reference", cores=threads,
+                    sample=f"sketch: {n_genomes} genomes x {genome_len} bp (-k31 -w51 --full-setsketch -S4096), "
+                           f"cmp: {cmp_n} sketches S=4096 all-pairs symmetric binary; dashing2 v2.1.20 {os.path.basename(exe)} "
+                           f"-p {threads}, wall clock incl. file read/write, warm")
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def cpu_port_run(n_genomes, genome_len, cmp_n):
+    """Fallback when the reference binary cannot run on this CPU: the single-threaded oracle port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from dashing2_b200 import synth
+    L = O.lib()
+    n_genomes = min(n_genomes, 2); cmp_n = min(cmp_n, 400)
+    t0 = time.perf_counter(); kmers = 0
+    for _, s in synth.family_genomes(n_genomes, genome_len, seed=2):
+        hv = O.hash_stream(s.tobytes(), K, W)
+        regs = np.empty(2 * S - 1); L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), None)
+        kmers += genome_len - K + 1
+    ts = time.perf_counter() - t0
+    regs, cards = synth.synthetic_sketches(cmp_n, S, seed=4)
+    t0 = time.perf_counter(); O.allpairs(regs, cards); tc = time.perf_counter() - t0
+    return dict(sketch_kmers_s=kmers / ts, cmp_pairs_s=cmp_n * (cmp_n - 1) / 2 / tc, sketch_s=ts, cmp_s=tc, kind="port", cores=1,
+                sample=f"oracle port, 1 thread: {n_genomes} genomes x {genome_len} bp; {cmp_n} sketches")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    vals_s, vals_c, tot = [], [], []
+    res = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = cpu_reference_run(args.cpu_genomes, args.genome_len, args.cpu_cmp_n, cores, repeats=1, warm=False)
+        if i >= args.warmup:
+            vals_s.append(res["sketch_kmers_s"]); vals_c.append(res["cmp_pairs_s"]); tot.append((res["sketch_s"] + res["cmp_s"]) * 1e3)
+    v = float(np.mean(vals_s)); vc = float(np.mean(vals_c))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "kmers/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(tot)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+            "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cmp": {"value": vc, "unit": "pairs/s", "e2e": {"value": vc, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "BASELINE configs[1]: sketch+cmp, %d synthetic genomes x %d bp per GPU, k=31 w=51, Full SetSketch S=4096, "
+                        "all-pairs symmetric" % (args.genomes, args.genome_len),
+            "genomes_per_gpu": args.genomes, "genome_len": args.genome_len, "k": K, "w": W, "sketchsize": S,
+            "sketch_mode": "--full-setsketch", "cmp": "symmetric all-pairs, similarity, f64 registers",
+            "parallelism": "files sharded over %d GPU(s), no collective; cmp rows equal-area sharded after one all-gather" % n_gpus,
+            "l2": "inputs larger than L2 (sequence buffer %.1f GB, register matrix %.0f MB per GPU)" %
+                  (args.genomes * args.genome_len / 1e9, args.genomes * S * 8 / 1e6)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []; self.proc = None; self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def make_genomes_on_device(torch, dev, n, length, seed, n_families):
+    """ASCII genomes on the device, SURVEY 8(d) recipe (family ancestor + i.i.d. substitutions at rate
+    0.001*(g%64+1)); returns uint8[n*length] (+256 B pad)."""
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    anc = torch.randint(0, 4, (n_families, length), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty(n * length + 256, dtype=torch.uint8, device=dev)
+    out[n * length:] = 0
+    for i in range(n):
+        a = anc[i % n_families]
+        rate = 0.001 * (i % 64 + 1)
+        mut = torch.rand(length, device=dev, generator=g) < rate
+        sub = torch.randint(1, 4, (length,), dtype=torch.uint8, device=dev, generator=g)
+        codes = torch.where(mut, (a + sub) & 3, a)
+        out[i * length:(i + 1) * length] = lut[codes.long()]
+    return out
+
+
+def equal_area_rows(n, parts):
+    """Row boundaries giving each part the same number of upper-triangle pairs."""
+    total = n * (n - 1) // 2
+    b = [0]
+    for r in range(1, parts):
+        target = total * r // parts
+        lo, hi = 0, n
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if mid * n - mid * (mid + 1) // 2 < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        b.append(lo)
+    b.append(n)
+    return b
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    import torch
+    import torch.distributed as dist
+    from dashing2_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libd2gpu has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = capi.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    G, Lg = args.genomes, args.genome_len
+    n_all = G * world
+    n_fam = max(1, G * 157 // 10000)
+    seq = make_genomes_on_device(torch, dev, G, Lg, seed=2 + rank, n_families=n_fam)
+    rec_off = (torch.arange(G + 1, dtype=torch.int64, device=dev) * Lg)
+    rec_ent = torch.arange(G, dtype=torch.int32, device=dev)
+    sig = torch.empty((G, S), dtype=torch.float64, device=dev)
+    card = torch.empty(G, dtype=torch.float64, device=dev)
+    all_sig = torch.empty((n_all, S), dtype=torch.float64, device=dev) if world > 1 else sig
+    all_card = torch.empty(n_all, dtype=torch.float64, device=dev) if world > 1 else card
+    bounds = equal_area_rows(n_all, world)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    p_sk = ctx.params(mode="fss", S=S, k=K, w=W)
+    p_cmp = ctx.cmp_params(S, n_all, "symmetric", "similarity", k=K)
+    my_pairs = ctx.cmp_rows_size(p_cmp, r0, r1)
+    out = torch.empty(my_pairs, dtype=torch.float32, device=dev)
+    kmers_rank = G * max(0, Lg - K + 1)
+    torch.cuda.synchronize()
+
+    def step(timed):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        evs[0].record(ext)
+        ctx.sketch_batch_dev(p_sk, seq.data_ptr(), rec_off.data_ptr(), rec_ent.data_ptr(), G, G, G * Lg,
+                             sig_d=sig.data_ptr(), card_d=card.data_ptr())
+        evs[1].record(ext)
+        if world > 1:
+            ext.synchronize()
+            dist.all_gather_into_tensor(all_sig, sig)
+            dist.all_gather_into_tensor(all_card, card)
+            torch.cuda.current_stream().synchronize()
+        evs[2].record(ext)
+        ctx.cmp_rows_dev(p_cmp, all_sig.data_ptr(), all_card.data_ptr(), r0, r1, out.data_ptr())
+        evs[3].record(ext)
+        ext.synchronize()
+        return evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    ctx.set_timing(True)
+    for c in range(3):
+        ctx.get_timing(c)
+    sampler = ClockSampler(local); sampler.start()
+    l0 = ctx.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    ts, tg, tc = [], [], []
+    for _ in range(args.steps):
+        a, b, c = step(True)
+        ts.append(a); tg.append(b); tc.append(c)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    k_main_ms, k_main_n = ctx.get_timing(0)
+    k_boot_ms, k_boot_n = ctx.get_timing(1)
+    k_cmp_ms, k_cmp_n = ctx.get_timing(2)
+    ctx.set_timing(False)
+
+    # max over ranks of the device-timed totals
+    tot = torch.tensor([sum(ts), sum(tg), sum(tc), sum(ts) + sum(tg) + sum(tc)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    sk_ms, ag_ms, cmp_ms, all_ms = (float(x) for x in tot.tolist())
+
+    # ---- e2e: the public C-ABI call with HOST buffers (pinned), H2D + kernels + D2H inside the timed region
+    Ge = min(args.e2e_genomes, G)
+    h_seq = torch.empty(Ge * Lg, dtype=torch.uint8).pin_memory()
+    h_seq.copy_(seq[:Ge * Lg])
+    h_off = (np.arange(Ge + 1, dtype=np.uint64) * np.uint64(Lg))
+    h_ent = np.arange(Ge, dtype=np.uint32)
+    h_sig = torch.empty((Ge, S), dtype=torch.float64).pin_memory()
+    h_card = torch.empty(Ge, dtype=torch.float64).pin_memory()
+    import ctypes as C
+
+    def e2e_sketch():
+        nk = C.c_uint64(0)
+        rc = ctx.L.d2g_sketch_batch(ctx.h, C.byref(p_sk), h_seq.data_ptr(), h_off.ctypes.data, h_ent.ctypes.data, Ge, Ge,
+                                    None, h_sig.data_ptr(), h_card.data_ptr(), None, C.byref(nk))
+        if rc:
+            raise RuntimeError(ctx.L.d2g_last_error().decode())
+        return nk.value
+
+    n_e2e_cmp = min(n_all, 10000)
+    h_regs = torch.empty((n_e2e_cmp, S), dtype=torch.float64).pin_memory(); h_regs.copy_(all_sig[:n_e2e_cmp])
+    h_cards = torch.empty(n_e2e_cmp, dtype=torch.float64).pin_memory(); h_cards.copy_(all_card[:n_e2e_cmp])
+    p_e2e_cmp = ctx.cmp_params(S, n_e2e_cmp, "symmetric", "similarity", k=K)
+    eb = equal_area_rows(n_e2e_cmp, world)
+    e_pairs = ctx.cmp_rows_size(p_e2e_cmp, eb[rank], eb[rank + 1])
+    h_out = torch.empty(e_pairs, dtype=torch.float32).pin_memory()
+    sink_pos = [0]
+    out_np = h_out.numpy()
+
+    def sink(blk, first_row, n_rows):
+        out_np[sink_pos[0]:sink_pos[0] + len(blk)] = blk
+        sink_pos[0] += len(blk)
+        return 0
+
+    def e2e_cmp():
+        sink_pos[0] = 0
+        ctx.cmp_stream(h_regs.numpy(), h_cards.numpy(), p_e2e_cmp, eb[rank], eb[rank + 1], sink)
+
+    e2e_sketch(); e2e_cmp()   # warm (allocations)
+    barrier(); t0 = time.perf_counter()
+    ne = max(1, min(args.steps, 3))
+    for _ in range(ne):
+        nk = e2e_sketch()
+    barrier(); t_e2e_sk = (time.perf_counter() - t0) / ne
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        e2e_cmp()
+    barrier(); t_e2e_cmp = (time.perf_counter() - t0) / ne
+    te = torch.tensor([t_e2e_sk, t_e2e_cmp], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e_sk, t_e2e_cmp = (float(x) for x in te.tolist())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    steps = args.steps
+    total_kmers = kmers_rank * world
+    total_pairs = n_all * (n_all - 1) // 2
+    sketch_rate = total_kmers * steps / (sk_ms / 1e3)
+    cmp_rate = total_pairs * steps / (cmp_ms / 1e3)
+    # roofline of the dominant kernel of each path: algorithmic bytes per launch / average launch duration
+    sk_bytes = kmers_rank * 1.0                                   # 1 B per k-mer
+    sk_ach = sk_bytes / (k_main_ms / max(1, k_main_n) / 1e3) / 1e9
+    cmp_bytes = n_all * S * 8 + 4.0 * my_pairs                    # every register read once + every result written once
+    cmp_ach = cmp_bytes / (k_cmp_ms / max(1, k_cmp_n) / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": sketch_rate, "unit": "kmers/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": all_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64+f64", "data": "synthetic", "config": workload_config(args, world),
+        "phases_ms_per_step": {"sketch": sk_ms / steps, "allgather": ag_ms / steps, "cmp": cmp_ms / steps, "wall": wall_ms / steps},
+        "roofline": {"bound": "hbm", "achieved": sk_ach, "peak": hbm_peak, "unit": "GB/s", "frac": sk_ach / hbm_peak, "traffic": None,
+                     "kernel": "sketch_kernel<windowed, FssMainConsumer>", "launch_ms": k_main_ms / max(1, k_main_n),
+                     "algorithmic_bytes_per_launch": sk_bytes, "peak_source": peak_src,
+                     "note": "1 B per k-mer position; the kernel is integer-ALU bound (~hundreds of int ops per k-mer), see DESIGN.md",
+                     "boot_kernel_ms": k_boot_ms / max(1, k_boot_n)},
+        "cmp": {"value": cmp_rate, "unit": "pairs/s", "pairs_per_step": total_pairs, "ms_per_step": cmp_ms / steps,
+                "roofline": {"bound": "hbm", "achieved": cmp_ach, "peak": hbm_peak, "unit": "GB/s", "frac": cmp_ach / hbm_peak, "traffic": None,
+                             "kernel": "cmp_tile_kernel<gtlt>", "launch_ms": k_cmp_ms / max(1, k_cmp_n),
+                             "algorithmic_bytes_per_launch": cmp_bytes,
+                             "no_reuse_bytes_per_pair": 2 * S * 8},
+                "e2e": {"value": (n_e2e_cmp * (n_e2e_cmp - 1) // 2) / t_e2e_cmp, "unit": "pairs/s",
+                        "h2d_bytes_per_step": n_e2e_cmp * S * 8 + n_e2e_cmp * 8, "d2h_bytes_per_step": e_pairs * 4,
+                        "call": "d2g_cmp_stream (host registers in, float32 rows streamed to a host sink)", "n": n_e2e_cmp}},
+        "e2e": {"value": Ge * (Lg - K + 1) * world / t_e2e_sk, "unit": "kmers/s", "h2d_bytes_per_step": Ge * Lg + (Ge + 1) * 8 + Ge * 4,
+                "d2h_bytes_per_step": Ge * S * 8 + Ge * 8, "call": "d2g_sketch_batch (pinned host sequence buffers in, host registers out)",
+                "batch": "%d genomes x %d bp per call" % (Ge, Lg)},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        cb = cpu_reference_run(args.cpu_genomes, Lg, args.cpu_cmp_n, host_cores(), repeats=1, warm=True)
+        line["cpu_baseline"] = {"value": cb["sketch_kmers_s"], "unit": "kmers/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+        line["cmp"]["cpu_baseline"] = {"value": cb["cmp_pairs_s"], "unit": "pairs/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,7 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c
 
 # every symbol include/d2gpu.h declares
 EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stream", "d2g_sync", "d2g_launch_count",
+           "d2g_set_timing", "d2g_get_timing",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_free"]
@@ -61,6 +62,8 @@ def load():
     L.d2g_stream.argtypes = [vp]; L.d2g_stream.restype = vp
     L.d2g_sync.argtypes = [vp]; L.d2g_sync.restype = C.c_int
     L.d2g_launch_count.argtypes = [vp]; L.d2g_launch_count.restype = u64
+    L.d2g_set_timing.argtypes = [vp, C.c_int]; L.d2g_set_timing.restype = C.c_int
+    L.d2g_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]; L.d2g_get_timing.restype = C.c_int
     L.d2g_opmh_m.argtypes = [u32]; L.d2g_opmh_m.restype = u32
     L.d2g_count_kmers.argtypes = [vp, u64, i32]; L.d2g_count_kmers.restype = u64
     L.d2g_sketch_batch.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, vp, vp, vp, vp, C.POINTER(u64)]
@@ -131,6 +134,15 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.L.d2g_launch_count(self.h))
+
+    def set_timing(self, on: bool):
+        _check(self.L.d2g_set_timing(self.h, int(on)))
+
+    def get_timing(self, kernel_class: int):
+        """(total ms, launches) of one kernel class since the last call; 0 sketch main, 1 sketch boot, 2 cmp."""
+        ms = C.c_double(0); n = C.c_uint64(0)
+        _check(self.L.d2g_get_timing(self.h, kernel_class, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     # ---- sketch ----
     @staticmethod

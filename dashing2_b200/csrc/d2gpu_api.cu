@@ -73,7 +73,26 @@ struct d2g_ctx {
     PinBuf pin[2];
     cudaEvent_t ev[2] = {nullptr, nullptr};
     uint32_t lut_S = 0; int lut_k = -1;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev[D2G_T_NCLASSES];
 };
+
+namespace {
+// RAII bracket: records an event pair around a kernel launch when ctx timing is on
+struct KernelTimer {
+    d2g_ctx *c; int cls; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KernelTimer(d2g_ctx *ctx, int k) : c(ctx), cls(k) {
+        if (!c->timing) return;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+    }
+    ~KernelTimer() {
+        if (!e0) return;
+        cudaEventRecord(e1, c->stream);
+        c->tev[cls].emplace_back(e0, e1);
+    }
+};
+} // namespace
 
 // -------------------------------------------------------------------------------------------------
 extern "C" {
@@ -116,6 +135,18 @@ void d2g_destroy(d2g_ctx *c) {
 void *d2g_stream(d2g_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int d2g_sync(d2g_ctx *c) { if (!c) return fail(D2G_EINVAL, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return D2G_OK; }
 uint64_t d2g_launch_count(const d2g_ctx *c) { return c ? c->launches.load() : 0; }
+int d2g_set_timing(d2g_ctx *c, int on) { if (!c) return fail(D2G_EINVAL, "null ctx"); c->timing = on != 0; return D2G_OK; }
+int d2g_get_timing(d2g_ctx *c, int cls, double *ms_total, uint64_t *n) {
+    if (!c || cls < 0 || cls >= D2G_T_NCLASSES) return fail(D2G_EINVAL, "bad timing class");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    double tot = 0.;
+    for (auto &pr : c->tev[cls]) { float ms = 0.f; cudaEventElapsedTime(&ms, pr.first, pr.second); tot += ms; cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (ms_total) *ms_total = tot;
+    if (n) *n = c->tev[cls].size();
+    c->tev[cls].clear();
+    return D2G_OK;
+}
 void d2g_free(void *p) { free(p); }
 
 uint32_t d2g_opmh_m(uint32_t S) { return S + (S & 1u); }
@@ -172,14 +203,15 @@ d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, c
     d2g::SketchArgs a;
     a.seq = reinterpret_cast<const uint8_t *>(seq_d); a.rec_off = rec_off_d; a.rec_entity = rec_ent_d;
     a.n_rec = n_rec; a.total_len = total_len; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
-    a.m = m; a.tile_stride = 1;
+    a.m = m; a.tile_stride = 1; a.score_slots = d2g::sketch_score_slots(p->k, p->w);
     a.span = pick_span(c, total_len, m);
     return a;
 }
 
 template <class Consumer>
-int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer::Params &cp, bool windowed) {
-    const size_t smem = d2g::sketch_smem_bytes<Consumer>(a.m, windowed);
+int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer::Params &cp, bool windowed, int tcls = D2G_T_SKETCH_MAIN) {
+    KernelTimer kt(c, tcls);
+    const size_t smem = d2g::sketch_smem_bytes<Consumer>(a.m, a.score_slots);
     if (smem > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sketch with %u registers needs %zu bytes of shared memory per CTA (max 200 KiB)", a.m, smem);
     const uint64_t grid = (a.total_len + a.span - 1) / a.span;
     if (windowed) {
@@ -231,15 +263,23 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const 
     const bool windowed = p->w > p->k;
     if (total_len && n_rec) {
         d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m);
-        // boot on a 1/8 sample of the tiles when entities are large enough for the sample to hit every register
+        // Boot on every stride-th tile: a cheap first bound T per entity so the first walks of the main pass are
+        // short; the main kernel keeps tightening it.  n_eff = elements fed to the sketch per entity (with
+        // minimizer windows only ~2/(window+1) of the positions emit).  Cost model per position: 1/stride for the
+        // boot pass plus the extra walkers a looser threshold admits => stride ~ sqrt(n_eff / (2 m ln m)).
         const double per_ent = (double)total_len / std::max(1u, n_ent);
-        a.tile_stride = (per_ent / 8. >= 24. * m * std::log((double)m + 2.)) ? 8 : 1;
+        const double n_eff = windowed ? per_ent * 2. / (p->w - p->k + 2) : per_ent;
+        const double mlnm = (double)m * std::log((double)m + 2.);
+        uint32_t stride = 1;
+        while (stride < 64 && (double)(stride * 2) <= std::sqrt(n_eff / (2. * mlnm)) * 4.) stride *= 2;
+        if (const char *ev = getenv("D2G_FSS_BOOT_STRIDE")) stride = (uint32_t)std::max(1, atoi(ev));   // tuning knob
+        a.tile_stride = stride;
         d2g::FssBootConsumer::Params bp{maxrv, d2g::make_fastmod32(m), m};
-        if (int rc = launch_sketch<d2g::FssBootConsumer>(c, a, bp, windowed)) return rc;
-        d2g::fss_threshold_kernel<<<n_ent, 256, 0, c->stream>>>(maxrv, m, T, rvmin);
+        if (int rc = launch_sketch<d2g::FssBootConsumer>(c, a, bp, windowed, D2G_T_SKETCH_BOOT)) return rc;
+        d2g::fss_threshold_kernel<<<n_ent, 256, 0, c->stream>>>(maxrv, m, T);
         c->launches++;
         a.tile_stride = 1;
-        d2g::FssMainConsumer::Params mp{keys, T, rvmin, ovf, ovf_count, ovf_cap, m};
+        d2g::FssMainConsumer::Params mp{keys, T, ovf, ovf_count, ovf_cap, m};
         if (int rc = launch_sketch<d2g::FssMainConsumer>(c, a, mp, windowed)) return rc;
         // long walks (normally none): dense permutation state per thread slot
         uint64_t nslots = std::min<uint64_t>(4096, (256ULL << 20) / ((uint64_t)m * 8));
@@ -256,6 +296,13 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const 
     CU(cudaMemcpyAsync(&h_ovf, ovf_count, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
+    if (getenv("D2G_DEBUG")) {
+        std::vector<double> hT(n_ent);
+        cudaMemcpy(hT.data(), T, n_ent * 8, cudaMemcpyDeviceToHost);
+        uint32_t ninf = 0; double tmax = 0, tmin = 1e308;
+        for (double t : hT) { if (t > 1e300) ++ninf; else { tmax = std::max(tmax, t); tmin = std::min(tmin, t); } }
+        fprintf(stderr, "[d2g] fss: n_ent=%u m=%u long-walk queue=%llu boot T: inf=%u min=%g max=%g\n", n_ent, m, h_ovf, ninf, tmin, tmax);
+    }
     if (h_ovf > ovf_cap) return fail(D2G_EUNSUPPORTED, "Full SetSketch: %llu elements needed a long register walk (queue holds %llu); "
                                      "inputs this small relative to the sketch size are not supported in one batch", h_ovf, (unsigned long long)ovf_cap);
     return D2G_OK;
@@ -445,6 +492,7 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     a.tiles_j = (a.ncols + d2g::CMP_T - 1) / d2g::CMP_T;
     const uint64_t grid = tiles_i * a.tiles_j;
     if (grid > 0x7fffffffULL) return fail(D2G_EINVAL, "row block too large for one launch");
+    KernelTimer kt(c, D2G_T_CMP);
     if (p->cmp_kind == D2G_CMP_GTLT) d2g::cmp_tile_kernel<0><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
     else d2g::cmp_tile_kernel<1><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
     c->launches++;

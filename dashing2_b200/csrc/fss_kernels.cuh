@@ -80,9 +80,8 @@ struct FssBootConsumer {
     }
 };
 
-// one CTA per entity: T = max_i ev_0(maxrv_i) (DBL_MAX when some register was never hit) and the integer
-// pre-filter rvmin (every rv < rvmin certainly has ev_0 > T)
-__global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *T, uint64_t *rvmin) {
+// one CTA per entity: T = max_i ev_0(maxrv_i) (DBL_MAX when some register was never hit by the sample)
+__global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *T) {
     __shared__ double red[256];
     const uint32_t ent = blockIdx.x;
     const double bv0 = -1. / m;
@@ -95,17 +94,7 @@ __global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *
     red[threadIdx.x] = mx;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) { if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
-    if (threadIdx.x == 0) {
-        const double t = red[0];
-        T[ent] = t;
-        uint64_t rm = 0;
-        if (t < 1e300) {
-            const double tv = exp(-t * (double)m) * (1. - 1e-6);   // any slightly-low estimate is safe
-            const double scaled = tv * 18446744073709551616.0;
-            rm = scaled >= 18446744073709549568.0 ? 0xFFFFFFFFFFFFF800ULL : (scaled <= 0. ? 0 : (uint64_t)scaled);
-        }
-        rvmin[ent] = rm;
-    }
+    if (threadIdx.x == 0) T[blockIdx.x] = red[0];
 }
 
 // ---- the per-element walk ------------------------------------------------------------------------
@@ -181,39 +170,110 @@ struct DensePerm {    // the reference's layout: g/v arrays with a generation co
 struct FssMainConsumer {
     struct Params {
         uint64_t *keys;            // [n_entities][m], initialised to FSS_KEY_EMPTY
-        const double *T; const uint64_t *rvmin;
+        double *T;                 // [n_entities] upper bound of the final maximum register; tightened by every CTA (atomicMin)
         uint64_t *ovf; unsigned long long *ovf_count; uint64_t ovf_cap;   // (x, entity) pairs for the long-walk kernel
         uint32_t m;
     };
-    static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8 + (size_t)SK_TILE * 8 + 16; }
-    uint64_t *skeys, *queue; int *qn; Params p; double T; uint64_t rvmin;
+    static constexpr int QCAP = SK_TILE + 512; // survivors are batched over tiles so the walk runs on full warps
+    static constexpr int DCAP = 256;          // walks that outran the sparse state wait here for a tighter threshold
+    static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8 + (size_t)(QCAP + DCAP) * 8 + 64; }
+    uint64_t *skeys, *queue, *defer, *bcast; int *qn, *dn; Params p; double T; uint64_t rvmin;
     __device__ __forceinline__ void init(unsigned char *smem, const Params &pp) {
-        p = pp; skeys = reinterpret_cast<uint64_t *>(smem); queue = skeys + p.m; qn = reinterpret_cast<int *>(queue + SK_TILE);
+        p = pp; skeys = reinterpret_cast<uint64_t *>(smem); queue = skeys + p.m; defer = queue + QCAP; bcast = defer + DCAP;
+        qn = reinterpret_cast<int *>(bcast + 4); dn = qn + 1;
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) skeys[i] = FSS_KEY_EMPTY;
-        if (threadIdx.x == 0) *qn = 0;
+        if (threadIdx.x == 0) { *qn = 0; *dn = 0; }
         T = 1.7976931348623157e308; rvmin = 0;
     }
-    __device__ __forceinline__ void begin_entity(uint32_t ent) { T = p.T[ent]; rvmin = p.rvmin[ent]; }
+    static __device__ __forceinline__ uint64_t rvmin_for(double t, uint32_t m) {   // every rv below this certainly has ev_0 > t
+        if (!(t < 1e300)) return 0;
+        const double scaled = exp(-t * (double)m) * (1. - 1e-6) * 18446744073709551616.0;
+        return scaled >= 18446744073709549568.0 ? 0xFFFFFFFFFFFFF800ULL : (scaled <= 0. ? 0 : (uint64_t)scaled);
+    }
+    __device__ __forceinline__ void begin_entity(uint32_t ent) {
+        T = *reinterpret_cast<volatile double *>(p.T + ent); rvmin = rvmin_for(T, p.m);
+    }
     __device__ __forceinline__ void consume(uint64_t hv) {
         if (cehash(hv ^ FSS_XOR) < rvmin) return;
         queue[atomicAdd(qn, 1)] = hv;
     }
+    // All threads.  Replays the queued elements against the CTA-local registers, then tightens the threshold:
+    // the final registers are element-wise <= the local ones, so the largest local register bounds the final
+    // maximum; the bound is shared with the other CTAs working on the same entity through p.T (atomicMin).
+    // Walks that outrun the sparse permutation state (threshold still loose) are retried after the tightening;
+    // only if that does not help do they go to the long-walk kernel.
+    __device__ __forceinline__ void drain(uint32_t ent, bool final) {
+        for (int round = 0;; ++round) {
+            const int n = *qn;
+            for (int q = threadIdx.x; q < n; q += SK_THREADS) {
+                const uint64_t x = queue[q];
+                SparsePerm sp;
+                if (!fss_walk(x, p.m, T, skeys, sp)) {
+                    const int slot = atomicAdd(dn, 1);
+                    if (slot < DCAP) defer[slot] = x;
+                    else {
+                        const unsigned long long g = atomicAdd(p.ovf_count, 1ULL);
+                        if (g < p.ovf_cap) { p.ovf[2 * g] = x; p.ovf[2 * g + 1] = ent; }
+                    }
+                }
+            }
+            __syncthreads();
+            uint64_t mx = 0;
+            for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) mx = max(mx, skeys[i]);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if ((threadIdx.x & 31) == 0) queue[threadIdx.x >> 5] = mx;      // queue is free now
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint64_t m2 = 0;
+                for (int w = 0; w < SK_THREADS / 32; ++w) m2 = max(m2, queue[w]);
+                double t = T;
+                if (m2 < FSS_KEY_EMPTY) {
+                    const double tl = dunkey(m2);
+                    if (tl < t && tl >= 0.) { t = tl; atomicMin(reinterpret_cast<unsigned long long *>(p.T + ent), (unsigned long long)__double_as_longlong(tl)); }
+                }
+                const double tg = *reinterpret_cast<volatile double *>(p.T + ent);
+                if (tg < t) t = tg;
+                bcast[0] = (uint64_t)__double_as_longlong(t); bcast[1] = rvmin_for(t, p.m);
+                bcast[2] = (t < T) ? 1 : 0;
+            }
+            __syncthreads();
+            const bool improved = bcast[2] != 0;
+            T = __longlong_as_double((long long)bcast[0]); rvmin = bcast[1];
+            const int nd = min(*dn, DCAP);
+            __syncthreads();
+            if (nd == 0) { if (threadIdx.x == 0) { *qn = 0; *dn = 0; } __syncthreads(); return; }
+            if (improved && (final || round == 0)) {
+                // retry the deferred walks now with the tighter threshold
+                for (int q = threadIdx.x; q < nd; q += SK_THREADS) queue[q] = defer[q];
+                if (threadIdx.x == 0) { *qn = nd; *dn = 0; }
+                __syncthreads();
+                continue;
+            }
+            if (!final && improved) {
+                // keep them for the next drain
+                for (int q = threadIdx.x; q < nd; q += SK_THREADS) queue[q] = defer[q];
+                if (threadIdx.x == 0) { *qn = nd; *dn = 0; }
+                __syncthreads();
+                return;
+            }
+            // no progress possible here: hand them to the long-walk kernel
+            for (int q = threadIdx.x; q < nd; q += SK_THREADS) {
+                const unsigned long long g = atomicAdd(p.ovf_count, 1ULL);
+                if (g < p.ovf_cap) { p.ovf[2 * g] = defer[q]; p.ovf[2 * g + 1] = ent; }
+            }
+            if (threadIdx.x == 0) { *qn = 0; *dn = 0; }
+            __syncthreads();
+            return;
+        }
+    }
     __device__ __forceinline__ void end_tile(uint32_t ent) {
         __syncthreads();
-        const int n = *qn;
-        for (int q = threadIdx.x; q < n; q += SK_THREADS) {
-            const uint64_t x = queue[q];
-            SparsePerm sp;
-            if (!fss_walk(x, p.m, T, skeys, sp)) {
-                const unsigned long long slot = atomicAdd(p.ovf_count, 1ULL);
-                if (slot < p.ovf_cap) { p.ovf[2 * slot] = x; p.ovf[2 * slot + 1] = ent; }
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) *qn = 0;
+        if (*qn > QCAP - SK_TILE) drain(ent, false);     // uniform: every thread reads the same counter after the barrier
     }
     __device__ __forceinline__ void flush(uint32_t ent) {
         __syncthreads();
+        drain(ent, true);
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) {
             const uint64_t v = skeys[i];
             if (v != FSS_KEY_EMPTY) { atomicMin(reinterpret_cast<unsigned long long *>(p.keys + (uint64_t)ent * p.m + i), (unsigned long long)v); skeys[i] = FSS_KEY_EMPTY; }

@@ -26,6 +26,10 @@ constexpr int SK_PPT = 8;                       // start positions per thread pe
 constexpr int SK_TILE = SK_THREADS * SK_PPT;    // 2048 start positions per tile
 constexpr int SK_MAX_W = 1024;                  // largest window (bases) the tile halo supports
 constexpr int SK_NWORDS = (SK_TILE + SK_MAX_W + 16 + 31) / 32 + 2;
+// Window keys live in shared memory at index q + q/8: thread t owns keys 8t..8t+7 (+ window tail), so a
+// warp's simultaneous accesses are 9 u64 apart instead of 8 -- the minimum two wavefronts instead of 16.
+__host__ __device__ constexpr int sk_pad(int q) { return q + (q >> 3); }
+constexpr int SK_SCORE_SLOTS = sk_pad(SK_TILE + SK_MAX_W) + 1;
 
 struct SketchArgs {
     const uint8_t *seq;          // concatenated record bytes (device), 16-byte aligned
@@ -38,6 +42,7 @@ struct SketchArgs {
     uint64_t xormask;
     uint32_t m;                  // registers per entity
     uint32_t tile_stride;        // process only tiles whose global index % tile_stride == 0 (sampling); 1 = all
+    uint32_t score_slots;        // shared-memory window-key slots (windowed mode): sk_pad(SK_TILE + w - k + 1) + 1
 };
 
 // ---- ASCII -> packed codes ---------------------------------------------------------------------
@@ -125,7 +130,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     uint64_t *W = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *M = reinterpret_cast<uint32_t *>(W + SK_NWORDS);
     uint64_t *score = reinterpret_cast<uint64_t *>(M + SK_NWORDS + (SK_NWORDS & 1));
-    unsigned char *csmem = reinterpret_cast<unsigned char *>(score + (WINDOWED ? (SK_TILE + SK_MAX_W) : 0));
+    unsigned char *csmem = reinterpret_cast<unsigned char *>(score + (WINDOWED ? a.score_slots : 0));
     Consumer cons;
     cons.init(csmem, cp);
 
@@ -197,7 +202,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                         // canonical windowed path: a k-mer holding an invalid base enters the window as
                         // k-mer 0 (encoder.h:568-571 + kmerutil.h:137-140)
                         const uint64_t km = tile_invalid(M, b, k) ? 0ULL : (fw < rc ? fw : rc);
-                        score[q0 + j] = frev64(km);
+                        score[sk_pad(q0 + j)] = frev64(km);
                     }
                 }
                 __syncthreads();
@@ -209,19 +214,19 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                     uint64_t prev = 0; bool have_prev = false;
                     if (wsz >= SK_PPT) {
                         uint64_t common = ~0ULL;                       // entries shared by all windows of this thread
-                        for (int q = j0 + jn - 1; q <= j0 + wsz - 1; ++q) common = min(common, score[q]);
+                        for (int q = j0 + jn - 1; q <= j0 + wsz - 1; ++q) common = min(common, score[sk_pad(q)]);
                         uint64_t left[SK_PPT];                          // suffix minima of the leading entries
                         uint64_t run = ~0ULL;
                         #pragma unroll
                         for (int j = SK_PPT - 1; j >= 0; --j) {
-                            if (j < jn - 1) run = min(run, score[j0 + j]);
+                            if (j < jn - 1) run = min(run, score[sk_pad(j0 + j)]);
                             left[j] = run;
                         }
                         run = ~0ULL;
                         #pragma unroll
                         for (int j = 0; j < SK_PPT; ++j) {
                             if (j < jn) {
-                                if (j) run = min(run, score[j0 + wsz - 1 + j]);
+                                if (j) run = min(run, score[sk_pad(j0 + wsz - 1 + j)]);
                                 const uint64_t mn = min(min(left[j], common), run);
                                 if (!have_prev || mn != prev) {
                                     const uint64_t km = frev64_inv(mn);
@@ -233,7 +238,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                     } else {
                         for (int j = 0; j < jn; ++j) {
                             uint64_t mn = ~0ULL;
-                            for (int q = 0; q < wsz; ++q) mn = min(mn, score[j0 + j + q]);
+                            for (int q = 0; q < wsz; ++q) mn = min(mn, score[sk_pad(j0 + j + q)]);
                             if (!have_prev || mn != prev) {
                                 const uint64_t km = frev64_inv(mn);
                                 if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask));
@@ -249,11 +254,11 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     if (cur_ent != 0xFFFFFFFFu) cons.flush(cur_ent);
 }
 
+inline uint32_t sketch_score_slots(int k, int w) { return w > k ? (uint32_t)sk_pad(SK_TILE + (w - k + 1)) + 2 : 0; }
 template <class Consumer>
-inline size_t sketch_smem_bytes(uint32_t m, bool windowed) {
+inline size_t sketch_smem_bytes(uint32_t m, uint32_t score_slots) {
     size_t b = (size_t)SK_NWORDS * 8 + (size_t)(SK_NWORDS + (SK_NWORDS & 1)) * 4;
-    if (windowed) b += (size_t)(SK_TILE + SK_MAX_W) * 8;
-    return b + Consumer::smem_bytes(m);
+    return b + (size_t)score_slots * 8 + Consumer::smem_bytes(m);
 }
 
 } // namespace d2g
