@@ -6,10 +6,15 @@ NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -ccbin $(CXX_HOST) 
 CSRC := dashing2_b200/csrc
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/d2gpu.h
 
-all: dashing2_b200/libd2gpu.so
+all: dashing2_b200/libd2gpu.so dashing2_b200/bin/dashing2-gpu
 
 dashing2_b200/libd2gpu.so: $(CSRC)/d2gpu_api.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/d2gpu_api.cu -lcudart_static -lpthread -ldl -lrt 2> dashing2_b200/ptxas.log || (cat dashing2_b200/ptxas.log; exit 1)
+
+# drop-in front-end for `dashing2 sketch|cmp` (host C++ only; all numerics are in libd2gpu)
+dashing2_b200/bin/dashing2-gpu: $(CSRC)/host/d2_main.cpp include/d2gpu.h dashing2_b200/libd2gpu.so
+	@mkdir -p dashing2_b200/bin
+	$(CXX_HOST) -O2 -std=c++17 -Wall -o $@ $(CSRC)/host/d2_main.cpp -Ldashing2_b200 -ld2gpu -lz -lpthread -Wl,-rpath,'$$ORIGIN/..'
 
 clean:
 	rm -f dashing2_b200/libd2gpu.so dashing2_b200/ptxas.log

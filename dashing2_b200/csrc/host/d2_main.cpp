@@ -1,0 +1,382 @@
+// d2_main.cpp -- `dashing2-gpu`: drop-in front-end for `dashing2 sketch` / `dashing2 cmp` on top of libd2gpu.
+//
+// Keeps the reference's command line (option names of /root/reference/src/options.h:63-171, short options
+// "m:p:k:w:c:f:S:F:Q:o:L:CNs2BPWh?ZJGHv" src/sketch_main.cpp:63) and its on-disk formats byte for byte:
+//   * stacked sketch file  u64 n | u64 S | f64 card[n] | f64 reg[n][S]  (+ FILE.names.txt)   src/sketch_core.cpp:129-171
+//   * per-input cache file  f64 card | f64 reg[S], named by makedest()                        src/fastxmerge.cpp:70-118
+//   * --save-kmers FILE.kmer64  u32 alphabet|canon<<8, u32 S, u32 k, u32 w, u64 seed, u64[n][S] src/fastxsketch.cpp:245-265
+//   * distance output: raw float32 (--binary-output) or the text table / PHYLIP                src/emitrect.cpp:108-403
+// Everything numeric happens in libd2gpu (CUDA); this file only parses arguments, reads FASTA/FASTQ
+// records (kseq semantics, bonsai/klib/kseq.h:178), batches them and writes files.  Modes the library
+// does not implement fail with its error message -- there is no CPU fallback.
+#include <zlib.h>
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+#include <sys/stat.h>
+
+#include "../../../include/d2gpu.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string &m) { std::fprintf(stderr, "dashing2-gpu: %s\n", m.c_str()); std::exit(1); }
+void chk(int rc) { if (rc) die(std::string("libd2gpu: ") + d2g_last_error()); }
+
+struct Opts {
+    int k = -1, w = -1, nthreads = 1;
+    uint64_t S = 1024, seed = 0;
+    bool canon = true, cache = false, save_kmers = false, presketched = false, binary = false;
+    int mode = D2G_MODE_OPMH;            // ONE_PERM default (src/sketch_main.cpp:27)
+    int measure = D2G_SIMILARITY;
+    int shape = D2G_SYMMETRIC; bool phylip = false;
+    int topk = -1;
+    std::string ffile, qfile, outfile, cmpout, outprefix;
+    std::vector<std::string> paths;
+    size_t nq = 0;
+    int verbosity = 0;
+};
+
+// ---- option parsing (only what feeds the two hot paths; unknown reference options are rejected loudly) ----
+Opts parse(int argc, char **argv, bool is_cmp) {
+    Opts o;
+    auto need = [&](int &i) -> std::string { if (i + 1 >= argc) die(std::string("option ") + argv[i] + " needs an argument"); return argv[++i]; };
+    for (int i = 0; i < argc; ++i) {
+        std::string a = argv[i];
+        std::string val; bool has_eq = false;
+        if (a.rfind("--", 0) == 0) { auto e = a.find('='); if (e != std::string::npos) { val = a.substr(e + 1); a = a.substr(0, e); has_eq = true; } }
+        auto arg = [&]() { return has_eq ? val : need(i); };
+        auto shortarg = [&](const char *s) -> bool { // -k31 or -k 31
+            if (a.size() >= 2 && a[0] == '-' && a[1] == s[1] && a[1] != '-') { if (a.size() > 2) { val = a.substr(2); has_eq = true; } return true; } return false; };
+        if (a == "--kmer-length" || shortarg("-k")) o.k = std::stoi(arg());
+        else if (a == "--window-size" || shortarg("-w")) o.w = std::stoi(arg());
+        else if (a == "--sketchsize" || shortarg("-S")) o.S = std::stoull(arg());
+        else if (a == "--sketch-size-l2" || shortarg("-L")) o.S = 1ull << std::stoi(arg());
+        else if (a == "--threads" || shortarg("-p")) o.nthreads = std::max(1, std::stoi(arg()));
+        else if (a == "--ffile" || shortarg("-F")) o.ffile = arg();
+        else if (a == "--qfile" || shortarg("-Q")) o.qfile = arg();
+        else if (a == "--outfile" || shortarg("-o")) o.outfile = arg();
+        else if (a == "--cmpout" || a == "--distout" || a == "--cmp-outfile") o.cmpout = arg();
+        else if (a == "--outprefix" || a == "--prefix") o.outprefix = arg();
+        else if (a == "--seed") o.seed = std::stoull(arg());
+        else if (a == "--topk" || a == "--top-k" || shortarg("-K")) o.topk = std::stoi(arg());
+        else if (a == "--binary-output" || a == "--emit-binary" || a == "--binary") o.binary = true;
+        else if (a == "--phylip") o.phylip = true;
+        else if (a == "--asymmetric-all-pairs" || a == "--asymmetric" || a == "--square") o.shape = D2G_ASYMMETRIC;
+        else if (a == "--full-setsketch" || a == "--full") o.mode = D2G_MODE_FULL_SETSKETCH;
+        else if (a == "--oneperm-setsketch" || a == "--oneperm" || a == "--one-perm" || a == "--oph" || a == "--doph" || a == "-Z") o.mode = D2G_MODE_OPMH;
+        else if (a == "--multiset" || a == "--bagminhash" || a == "--bmh" || a == "--BMH") o.mode = D2G_MODE_BAGMINHASH;
+        else if (a == "--prob" || a == "--probs" || a == "--pminhash" || a == "--pmh" || a == "--PMH" || a == "--probminhash" || a == "-P") o.mode = D2G_MODE_PROBMINHASH;
+        else if (a == "--no-canon" || a == "-C") o.canon = false;
+        else if (a == "--cache" || a == "--cache-sketches" || a == "-W") o.cache = true;
+        else if (a == "--save-kmers" || a == "-s") o.save_kmers = true;
+        else if (a == "--presketched") o.presketched = true;
+        else if (a == "--containment") o.measure = D2G_CONTAINMENT;
+        else if (a == "--symmetric-containment") o.measure = D2G_SYMMETRIC_CONTAINMENT;
+        else if (a == "--mash-distance" || a == "--distance" || a == "--poisson-distance") o.measure = D2G_POISSON_LLR;
+        else if (a == "--intersection" || a == "--intersection-size") o.measure = D2G_INTERSECTION;
+        else if (a == "--union-size") o.measure = D2G_UNION_SIZE;
+        else if (a == "--verbose" || a == "-v") ++o.verbosity;
+        else if (a == "-h" || a == "--help" || a == "-?") {
+            std::printf("dashing2-gpu %s: drop-in for `dashing2 sketch|cmp` (k<=32 DNA; OPMH / Full SetSketch; dense all-pairs / panel).\n"
+                        "Options follow the reference: -k -w -S -p -F -Q -o --cmpout --binary-output --phylip --asymmetric-all-pairs\n"
+                        "--full-setsketch --oneperm -C/--no-canon --seed --cache --outprefix --save-kmers --presketched\n"
+                        "--containment --symmetric-containment --mash-distance --intersection --union-size\n", d2g_version());
+            std::exit(0);
+        } else if (!a.empty() && a[0] == '-' && a.size() > 1) die("option " + a + " is not supported by the GPU front-end (see DESIGN.md section 7)");
+        else o.paths.push_back(a);
+    }
+    if (o.k < 0) o.k = 32;   // nregperitem(DNA, 64-bit), src/sketch_main.cpp:70
+    auto read_list = [](const std::string &f, std::vector<std::string> &dst) {
+        std::ifstream ifs(f); if (!ifs) die("No path found at " + f);
+        for (std::string l; std::getline(ifs, l);) dst.push_back(l);
+    };
+    if (!o.ffile.empty()) read_list(o.ffile, o.paths);
+    const size_t nref = o.paths.size();
+    if (!o.qfile.empty()) read_list(o.qfile, o.paths);
+    o.nq = o.paths.size() - nref;
+    if (o.nq) o.shape = D2G_PANEL;      // src/options.h: -Q implies PANEL
+    if (o.paths.empty()) die("No paths provided. See usage.");
+    (void)is_cmp;
+    return o;
+}
+
+// ---- names: makedest() and friends -------------------------------------------------------------
+std::string trim_folder(const std::string &s) { auto p = s.find_last_of('/'); return p == std::string::npos ? s : s.substr(p + 1); }
+const char *suffix(int mode) { return mode == D2G_MODE_OPMH ? ".opss" : mode == D2G_MODE_FULL_SETSKETCH ? ".ss" : mode == D2G_MODE_BAGMINHASH ? ".bmh" : ".pmh"; }
+std::string makedest(const Opts &o, const std::string &path) {   // src/fastxmerge.cpp:70-118
+    std::string ret = path.substr(0, path.find_first_of(' '));
+    if (!o.outprefix.empty()) ret = o.outprefix + '/' + trim_folder(path);
+    if (o.seed) ret += ".seed" + std::to_string(o.seed);
+    if (o.canon) ret += ".rc_canon";
+    ret += ".sketchsize" + std::to_string(o.S) + ".k" + std::to_string(o.k);
+    if (o.w > o.k) ret += ".w" + std::to_string(o.w);
+    const bool counted = o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH;
+    if (counted) ret += ".ExactCounting";
+    ret += '.';
+    ret += o.mode == D2G_MODE_BAGMINHASH ? "MultisetSpace" : o.mode == D2G_MODE_PROBMINHASH ? "ProbsetSpace" : "SetSpace";
+    return ret + ".DNA" + suffix(o.mode);
+}
+
+// ---- FASTA/FASTQ records, kseq semantics ---------------------------------------------------------
+struct FileRecords { std::string seq; std::vector<uint64_t> ends; };
+void read_fastx(const std::string &path, FileRecords &out) {
+    gzFile fp = gzopen(path.c_str(), "rb");
+    if (!fp) die("Could not open file at " + path + ". Abort!");
+    gzbuffer(fp, 1 << 18);
+    std::string data; std::vector<char> buf(1 << 20);
+    for (int n; (n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0;) data.append(buf.data(), n);
+    gzclose(fp);
+    const char *p = data.data(), *e = p + data.size();
+    auto next_line = [&](const char *&b, const char *&le) { le = (const char *)memchr(b, '\n', e - b); if (!le) le = e; };
+    while (p < e) {
+        // skip to the next header
+        while (p < e && *p != '>' && *p != '@') { const char *le; next_line(p, le); p = le < e ? le + 1 : e; }
+        if (p >= e) break;
+        const bool fastq = *p == '@';
+        const char *le; next_line(p, le); p = le < e ? le + 1 : e;          // header line
+        const size_t start = out.seq.size();
+        while (p < e && *p != '>' && *p != '+' && *p != '@') {
+            next_line(p, le);
+            const char *t = le; while (t > p && (t[-1] == '\r')) --t;
+            out.seq.append(p, t - p);
+            p = le < e ? le + 1 : e;
+        }
+        const size_t len = out.seq.size() - start;
+        if (fastq && p < e && *p == '+') {
+            next_line(p, le); p = le < e ? le + 1 : e;
+            size_t got = 0;
+            while (p < e && got < len) { next_line(p, le); const char *t = le; while (t > p && t[-1] == '\r') --t; got += t - p; p = le < e ? le + 1 : e; }
+        }
+        out.ends.push_back(out.seq.size());
+    }
+}
+
+// ---- float -> text exactly as fmt's "{}" (shortest round trip; exponent form iff exp10 < -4 or >= 16) ----
+void fmt_float(float v, std::string &out) {
+    if (std::isnan(v)) { out += "nan"; return; }
+    if (std::isinf(v)) { out += v < 0 ? "-inf" : "inf"; return; }
+    if (v == 0) { out += std::signbit(v) ? "-0" : "0"; return; }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    std::string s(buf, r.ptr);                      // d[.ddd]e[+-]XX
+    bool neg = s[0] == '-'; if (neg) s.erase(0, 1);
+    const auto epos = s.find('e');
+    std::string digits = s.substr(0, epos); const int ex = std::stoi(s.substr(epos + 1));
+    digits.erase(std::remove(digits.begin(), digits.end(), '.'), digits.end());
+    if (neg) out += '-';
+    const int nd = (int)digits.size();
+    if (ex < -4 || ex >= 16) {
+        out += digits[0];
+        if (nd > 1) { out += '.'; out.append(digits, 1, std::string::npos); }
+        char eb[16]; std::snprintf(eb, sizeof eb, "e%c%02d", ex < 0 ? '-' : '+', std::abs(ex)); out += eb;
+    } else if (ex >= 0) {
+        if (nd <= ex + 1) { out += digits; out.append(ex + 1 - nd, '0'); }
+        else { out.append(digits, 0, ex + 1); out += '.'; out.append(digits, ex + 1, std::string::npos); }
+    } else { out += "0."; out.append(-ex - 1, '0'); out += digits; }
+}
+
+struct Sketches { std::vector<double> sig, card; std::vector<uint64_t> ids; std::vector<std::string> names; uint64_t S = 0; int mode = D2G_MODE_OPMH; };
+
+// ---- sketch all inputs through libd2gpu in batches -----------------------------------------------
+void sketch_inputs(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
+    const size_t n = o.paths.size(), S = o.S;
+    sk.S = S; sk.mode = o.mode; sk.names = o.paths;
+    sk.sig.assign(n * S, 0.); sk.card.assign(n, 0.);
+    if (o.save_kmers) sk.ids.assign(n * S, 0);
+    d2g_sketch_params p{};
+    p.k = o.k; p.w = o.w; p.canon = o.canon; p.mode = o.mode; p.sketchsize = (uint32_t)S;
+    p.xormask = 0;
+    if (o.seed) { // Wang(seed), src/enums.cpp:133-140
+        uint64_t key = o.seed; key = (~key) + (key << 21); key ^= key >> 24; key = (key + (key << 3)) + (key << 8); key ^= key >> 14;
+        key = (key + (key << 2)) + (key << 4); key ^= key >> 28; key += key << 31; p.xormask = key;
+    }
+    std::vector<char> todo(n, 1);
+    if (o.cache) {   // cache hit = load the per-file sketch (src/fastxsketch.cpp:327-373)
+        for (size_t i = 0; i < n; ++i) {
+            const std::string dest = makedest(o, o.paths[i]);
+            struct stat st;
+            if (::stat(dest.c_str(), &st) == 0 && (size_t)st.st_size == 8 + S * 8 && !o.save_kmers) {
+                std::FILE *fp = std::fopen(dest.c_str(), "rb");
+                if (fp && std::fread(&sk.card[i], 8, 1, fp) == 1 && std::fread(&sk.sig[i * S], 8, S, fp) == S) todo[i] = 0;
+                if (fp) std::fclose(fp);
+            }
+        }
+    }
+    const size_t batch_bytes = size_t(1) << 30;
+    size_t i = 0;
+    while (i < n) {
+        // gather a batch of files (parsed on host threads)
+        std::vector<size_t> idx; size_t est = 0;
+        while (i < n && (idx.empty() || est < batch_bytes)) {
+            if (todo[i]) { struct stat st; est += ::stat(o.paths[i].c_str(), &st) == 0 ? (size_t)st.st_size : 0; idx.push_back(i); }
+            ++i;
+        }
+        if (idx.empty()) break;
+        std::vector<FileRecords> recs(idx.size());
+        {
+            std::vector<std::thread> th; std::atomic<size_t> next{0};
+            const unsigned nt = (unsigned)std::min<size_t>(o.nthreads, idx.size());
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] { for (size_t j; (j = next++) < idx.size();) read_fastx(o.paths[idx[j]], recs[j]); });
+            for (auto &t : th) t.join();
+        }
+        std::string seq; std::vector<uint64_t> off{0}; std::vector<uint32_t> ent;
+        for (size_t j = 0; j < idx.size(); ++j) {
+            const uint64_t base = seq.size(); seq += recs[j].seq;
+            for (uint64_t e : recs[j].ends) { off.push_back(base + e); ent.push_back((uint32_t)j); }
+            recs[j] = FileRecords();
+        }
+        seq.append(64, '\0');
+        const uint32_t ne = (uint32_t)idx.size();
+        std::vector<double> sig((size_t)ne * S), card(ne); std::vector<uint64_t> ids(o.save_kmers ? (size_t)ne * S : 0);
+        chk(d2g_sketch_batch(ctx, &p, seq.data(), off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
+                             o.save_kmers ? ids.data() : nullptr, nullptr));
+        for (size_t j = 0; j < idx.size(); ++j) {
+            std::copy(sig.begin() + j * S, sig.begin() + (j + 1) * S, sk.sig.begin() + idx[j] * S);
+            sk.card[idx[j]] = card[j];
+            if (o.save_kmers) std::copy(ids.begin() + j * S, ids.begin() + (j + 1) * S, sk.ids.begin() + idx[j] * S);
+            if (o.cache) {
+                const std::string dest = makedest(o, o.paths[idx[j]]);
+                std::FILE *fp = std::fopen(dest.c_str(), "wb");
+                if (!fp) die("Failed to open file " + dest + " for writing sketch.");
+                std::fwrite(&card[j], 8, 1, fp); std::fwrite(&sig[j * S], 8, S, fp); std::fclose(fp);
+            }
+        }
+    }
+}
+
+void write_stacked(const Opts &o, const Sketches &sk) {
+    const uint64_t n = sk.card.size(), S = sk.S;
+    std::FILE *fp = std::fopen(o.outfile.c_str(), "wb");
+    if (!fp) die("Failed to open file " + o.outfile);
+    std::fwrite(&n, 8, 1, fp); std::fwrite(&S, 8, 1, fp);
+    std::fwrite(sk.card.data(), 8, n, fp); std::fwrite(sk.sig.data(), 8, n * S, fp); std::fclose(fp);
+    fp = std::fopen((o.outfile + ".names.txt").c_str(), "wb");
+    if (!fp) die("Failed to open outfile at " + o.outfile + ".names.txt");
+    std::fputs("#Name\tCardinality\n", fp);
+    for (size_t i = 0; i < n; ++i) std::fprintf(fp, "%s\t%0.24g\n", sk.names[i].c_str(), sk.card[i]);
+    std::fclose(fp);
+    if (o.save_kmers) {
+        const std::string kp = o.outfile + ".kmer64";
+        fp = std::fopen(kp.c_str(), "wb");
+        const uint32_t hdr[4] = {uint32_t(0) | (uint32_t(o.canon) << 8), (uint32_t)S, (uint32_t)o.k, (uint32_t)(o.w < 0 ? o.k : o.w)};
+        std::fwrite(hdr, 4, 4, fp); std::fwrite(&o.seed, 8, 1, fp); std::fwrite(sk.ids.data(), 8, n * S, fp); std::fclose(fp);
+        fp = std::fopen((kp + ".names.txt").c_str(), "wb");
+        for (auto &nm : sk.names) { std::fputs(nm.c_str(), fp); std::fputc('\n', fp); }
+        std::fclose(fp);
+    }
+}
+
+void load_stacked(const std::string &path, Sketches &sk) {   // src/cmp_main.cpp:24-198 (single stacked file branch)
+    std::FILE *fp = std::fopen(path.c_str(), "rb");
+    if (!fp) die("Failed to open " + path);
+    uint64_t n, S;
+    if (std::fread(&n, 8, 1, fp) != 1 || std::fread(&S, 8, 1, fp) != 1) die("short stacked sketch file " + path);
+    sk.S = S; sk.card.resize(n); sk.sig.resize(n * S);
+    if (std::fread(sk.card.data(), 8, n, fp) != n || std::fread(sk.sig.data(), 8, n * S, fp) != n * S) die("truncated stacked sketch file " + path);
+    std::fclose(fp);
+    std::ifstream ifs(path + ".names.txt");
+    for (std::string l; std::getline(ifs, l);) { if (l.empty() || l[0] == '#') continue; sk.names.push_back(l.substr(0, l.find('\t'))); }
+    auto ends = [&](const char *s) { const size_t L = strlen(s); return path.size() >= L && path.compare(path.size() - L, L, s) == 0; };
+    sk.mode = ends(".opss") ? D2G_MODE_OPMH : ends(".bmh") ? D2G_MODE_BAGMINHASH : ends(".pmh") ? D2G_MODE_PROBMINHASH : D2G_MODE_FULL_SETSKETCH; // cmp_main.cpp:318-351
+}
+
+std::string options_string(const Opts &o, int mode) {   // Dashing2Options::to_string, src/d2.cpp:10-43
+    std::string r = "Dashing2Options;k:" + std::to_string(o.k);
+    if (o.w > 0) r += ";w:" + std::to_string(o.w);
+    r += ";parsebyfile;trimchr;sketchsize:" + std::to_string(o.S) + ";sketchtype:";
+    r += mode == D2G_MODE_OPMH ? "onepermsetsketch" : mode == D2G_MODE_FULL_SETSKETCH ? "fullsetsketch" : mode == D2G_MODE_BAGMINHASH ? "bagminhash" : "probminhash";
+    r += ";Fastx";
+    if (!o.outprefix.empty()) r += ";outprefix:" + o.outprefix;
+    if (o.canon) r += ";canon";
+    return r;
+}
+
+struct Writer {
+    const Opts &o; const Sketches &sk; std::FILE *fp; size_t ns, nq; std::string line;
+    static int sink(void *u, const float *blk, uint64_t first_row, uint64_t n_rows, uint64_t n_vals) {
+        Writer *w = (Writer *)u;
+        if (w->o.binary) return std::fwrite(blk, 4, n_vals, w->fp) == n_vals ? 0 : 1;
+        const float *p = blk;
+        for (uint64_t i = first_row; i < first_row + n_rows; ++i) {   // src/emitrect.cpp:172-187
+            std::string &l = w->line; l.clear();
+            std::string fn = i < w->sk.names.size() && !w->sk.names[i].empty() ? w->sk.names[i] : "E" + std::to_string(i);
+            if (fn.size() < 9) fn.append(9 - fn.size(), ' ');
+            l += fn;
+            const size_t jend = w->o.shape == D2G_PANEL ? w->nq : w->o.shape == D2G_ASYMMETRIC ? w->ns : w->ns - i - 1;
+            if (w->o.shape == D2G_SYMMETRIC && !w->o.phylip) for (uint64_t t = 0; t < i + 1; ++t) l += "\t-";
+            for (size_t j = 0; j < jend; ++j) { l += '\t'; fmt_float(*p++, l); }
+            l += '\n';
+            if (std::fwrite(l.data(), 1, l.size(), w->fp) != l.size()) return 1;
+        }
+        return 0;
+    }
+};
+
+void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
+    const uint64_t n = sk.card.size(), S = sk.S;
+    if (o.topk > 0) die("--topk (LSH nearest-neighbour graphs) is not implemented in the GPU front-end yet");
+    if (sk.mode == D2G_MODE_OPMH) chk(d2g_densify(ctx, sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), n, (uint32_t)S));  // cmp_core.cpp:686-718
+    d2g_cmp_params cp{};
+    cp.sketchsize = (uint32_t)S; cp.measure = o.measure; cp.k = o.k; cp.shape = o.shape; cp.n = n; cp.nq = o.nq;
+    cp.cmp_kind = (sk.mode == D2G_MODE_OPMH || sk.mode == D2G_MODE_FULL_SETSKETCH) ? D2G_CMP_GTLT : D2G_CMP_EQ;
+    const bool to_stdout = o.cmpout.empty() || o.cmpout[0] == '-';
+    std::FILE *fp = to_stdout ? stdout : std::fopen(o.cmpout.c_str(), "wb");
+    if (!fp) die("Failed to open path " + o.cmpout + " for writing");
+    Writer w{o, sk, fp, (size_t)n, (size_t)o.nq, {}};
+    if (!o.binary) {   // header, src/emitrect.cpp:136-151
+        if (!o.phylip) {
+            const char *label = o.shape == D2G_ASYMMETRIC ? "Asymmetric pairwise" : o.shape == D2G_PANEL ? "Panel (Query/Refernce)" : "Symmetric pairwise";
+            std::fprintf(fp, "#Dashing2 %s Output\n#Dashing2Options: %s\n#Sources", label, options_string(o, sk.mode).c_str());
+            for (uint64_t i = 0; i < n; ++i) { if (i < sk.names.size()) std::fprintf(fp, "\t%s", sk.names[i].c_str()); else std::fprintf(fp, "\tE%llu", (unsigned long long)i); }
+            std::fputc('\n', fp);
+        } else std::fprintf(fp, "%llu\n", (unsigned long long)n);
+    }
+    const uint64_t nrows = o.shape == D2G_PANEL ? n - o.nq : n;
+    const double *regs = sk.sig.data();
+    // equality branch compares the sampled k-mers when they were saved (cmp_core.cpp:501-504)
+    if (cp.cmp_kind == D2G_CMP_EQ && sk.ids.size() == sk.sig.size()) regs = reinterpret_cast<const double *>(sk.ids.data());
+    chk(d2g_cmp_stream(ctx, &cp, regs, sk.card.data(), 0, nrows, Writer::sink, &w));
+    if (!to_stdout) std::fclose(fp); else std::fflush(fp);
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 2) die("subcommands: sketch, cmp (alias dist). See `dashing2-gpu sketch -h`");
+    const std::string sub = argv[1];
+    const bool is_cmp = sub == "cmp" || sub == "dist";
+    if (!is_cmp && sub != "sketch") die("subcommand '" + sub + "' is outside the GPU hot paths (only sketch and cmp are provided)");
+    Opts o = parse(argc - 2, argv + 2, is_cmp);
+    d2g_ctx *ctx = nullptr;
+    chk(d2g_init(&ctx, 0));
+    Sketches sk;
+    if (is_cmp && o.presketched) {
+        if (o.paths.size() != 1) die("--presketched: pass one stacked sketch file (the reference's multi-file branch is degenerate for panels, SURVEY 8a b9)");
+        load_stacked(o.paths[0], sk);
+        o.S = sk.S;
+    } else {
+        sketch_inputs(ctx, o, sk);
+        if (!o.outfile.empty()) {
+            // the reference densifies signatures_ in place before the stacked file is closed when --cmpout is given
+            if (!o.cmpout.empty() && sk.mode == D2G_MODE_OPMH) chk(d2g_densify(ctx, sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), sk.card.size(), (uint32_t)sk.S));
+            write_stacked(o, sk);
+        }
+    }
+    if (is_cmp || !o.cmpout.empty()) {
+        if (is_cmp && o.cmpout.empty()) o.cmpout = "-";
+        compare_and_emit(ctx, o, sk);
+    }
+    d2g_destroy(ctx);
+    return 0;
+}

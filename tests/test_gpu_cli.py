@@ -1,0 +1,96 @@
+"""The drop-in front-end (dashing2_b200/bin/dashing2-gpu) against reference-binary goldens: same argv as
+`dashing2 sketch|cmp`, byte-identical stacked files / binary matrices / text tables."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, expected, GOLD
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "dashing2_b200", "bin", "dashing2-gpu")
+
+
+def run(args, cwd=None):
+    r = subprocess.run([EXE] + args, cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def read_stacked(path):
+    n, s = (int(x) for x in np.fromfile(path, dtype=np.uint64, count=2))
+    d = np.fromfile(path, dtype=np.float64, offset=16)
+    return d[:n], d[n:].reshape(n, s)
+
+
+@pytest.mark.parametrize("case,argv", [("opmh_k31_S1024", ["-k31", "-S1024"]), ("opmh_k31_w51_S512", ["-k31", "-w51", "-S512"]),
+                                       ("opmh_k31_S256_seed17", ["-k31", "-S256", "--seed", "17"]),
+                                       ("fss_k31_w51_S1024", ["-k31", "-w51", "-S1024", "--full-setsketch"])])
+def test_sketch_stacked_file(case, argv, golden_inputs, tmp_path):
+    names, paths = golden_inputs
+    flist = tmp_path / "files.txt"; flist.write_text("\n".join(paths) + "\n")
+    out = str(tmp_path / "out.stk")
+    run(["sketch", "-p4", "-F", str(flist), "-o", out] + argv)
+    cards, sigs = read_stacked(out)
+    z = np.load(expected(case + ".npz"))
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64))
+    if case.startswith("opmh"):
+        assert np.array_equal(cards, z["cards"])
+    else:
+        np.testing.assert_allclose(cards, z["cards"], rtol=1e-12)
+    lines = open(out + ".names.txt").read().splitlines()
+    assert lines[0] == "#Name\tCardinality" and [l.split("\t")[0] for l in lines[1:]] == paths
+    if case.startswith("opmh"):
+        assert [l.split("\t")[1] for l in lines[1:]] == ["%0.24g" % c for c in z["cards"]]
+
+
+def test_sketch_cmpout_binary_text_and_cache(golden_inputs, tmp_path):
+    names, paths = golden_inputs
+    flist = tmp_path / "files.txt"; flist.write_text("\n".join(paths) + "\n")
+    work = os.path.dirname(paths[0])
+    for kind, argv in (("sim_sym", []), ("sim_asym", ["--asymmetric-all-pairs"]), ("containment_sym", ["--containment"]),
+                       ("mash_sym", ["--mash-distance"]), ("usz_sym", ["--union-size"])):
+        mat = str(tmp_path / (kind + ".f32"))
+        run(["sketch", "-F", str(flist), "-k31", "-S1024", "--binary-output", "--cmpout", mat] + argv)
+        exp = np.load(expected(f"cmp_opmh_k31_S1024_{kind}.npy"))
+        assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), exp.view(np.uint32)), kind
+    for tag, argv in (("phylip", ["--phylip"]), ("table", [])):
+        mat = str(tmp_path / (tag + ".txt"))
+        run(["sketch", "-F", str(flist), "-k31", "-S1024", "--cmpout", mat] + argv)
+        got = open(mat).read().replace(work + "/", "")
+        assert got == open(expected(f"cmp_opmh_k31_S1024_{tag}.txt")).read(), tag
+    # --cache writes reference-named per-file sketches that a second run (and `cmp --cache`) reloads
+    cdir = tmp_path / "cache"; cdir.mkdir()
+    run(["sketch", "-F", str(flist), "-k31", "-S1024", "--cache", "--outprefix", str(cdir)])
+    f0 = cdir / (os.path.basename(paths[0]) + ".rc_canon.sketchsize1024.k31.SetSpace.DNA.opss")
+    assert f0.exists() and f0.stat().st_size == 8 + 1024 * 8
+    z = np.load(expected("opmh_k31_S1024.npz"))
+    d = np.fromfile(f0, dtype=np.float64)
+    assert d[0] == z["cards"][0] and np.array_equal(d[1:], z["sigs"][0])
+    mat = str(tmp_path / "fromcache.f32")
+    run(["cmp", "--cache", "--outprefix", str(cdir), "-k31", "-S1024", "--binary-output", "--cmpout", mat, "-F", str(flist)])
+    exp = np.load(expected("cmp_opmh_k31_S1024_sim_sym.npy"))
+    assert np.array_equal(np.fromfile(mat, dtype=np.float32), exp)
+
+
+def test_cmp_presketched_and_panel(tmp_path):
+    from dashing2_b200 import synth
+    import oracle_lib as O
+    z = np.load(os.path.join(GOLD, "inputs", "sk48x256.npz"))
+    for suffix, cmp_kind in ((".ss", 0), (".bmh", 1)):
+        stk = str(tmp_path / ("sk48" + suffix))
+        synth.write_stacked(stk, z["regs"], z["cards"], names=[f"s{i}" for i in range(48)])
+        for kind, argv in (("sim_sym", []), ("symcontainment_sym", ["--symmetric-containment"]), ("isz_sym", ["--intersection"])):
+            mat = str(tmp_path / "m.f32")
+            run(["cmp", "--presketched", "--binary-output", "--cmpout", mat, stk] + argv)
+            exp = np.load(expected(f"cmp_sk48{suffix}_{kind}.npy"))
+            assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), exp.view(np.uint32)), (suffix, kind)
+
+
+def test_unsupported_options_fail_loudly(golden_inputs):
+    names, paths = golden_inputs
+    for argv in (["sketch", "-k31", "--multiset", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0]],
+                 ["contain", paths[0]]):
+        r = subprocess.run([EXE] + argv, capture_output=True, text=True)
+        assert r.returncode != 0 and r.stderr.strip()
