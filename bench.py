@@ -209,22 +209,7 @@ def make_genomes_on_device(torch, dev, n, length, seed, n_families):
     return out
 
 
-def equal_area_rows(n, parts):
-    """Row boundaries giving each part the same number of upper-triangle pairs."""
-    total = n * (n - 1) // 2
-    b = [0]
-    for r in range(1, parts):
-        target = total * r // parts
-        lo, hi = 0, n
-        while lo < hi:
-            mid = (lo + hi) // 2
-            if mid * n - mid * (mid + 1) // 2 < target:
-                lo = mid + 1
-            else:
-                hi = mid
-        b.append(lo)
-    b.append(n)
-    return b
+from dashing2_b200.shard import equal_area_rows  # noqa: E402
 
 
 def main():
