@@ -21,6 +21,9 @@
 #include "cmp_kernels.cuh"
 #include "sketch_kernels.cuh"
 #include "fss_kernels.cuh"
+#include "weighted_kernels.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace {
 
@@ -69,6 +72,7 @@ struct d2g_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::atomic<uint64_t> launches{0};
     DevBuf seq, recoff, recent, regs, sig, card, ids, aux, aux2;   // sketch scratch
+    DevBuf wbuf, wtmp;                                              // counting scratch (BagMinHash / ProbMinHash)
     DevBuf cregs, ccards, cout, clut, ctmp, cktmp;                 // compare scratch
     PinBuf pin[2];
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -182,9 +186,10 @@ int check_sketch_params(const d2g_sketch_params *p) {
         if (p->w > d2g::SK_MAX_W) return fail(D2G_EUNSUPPORTED, "window %d > %d not supported", p->w, d2g::SK_MAX_W);
         if (!p->canon) return fail(D2G_EUNSUPPORTED, "windowed minimizers without canonicalisation (-C -w) are not implemented on the GPU");
     }
-    if (p->mode != D2G_MODE_OPMH && p->mode != D2G_MODE_FULL_SETSKETCH)
-        return fail(D2G_EUNSUPPORTED, "sketch mode %d not implemented yet (OPMH and Full SetSketch are)", p->mode);
-    if (p->count_threshold > 1) return fail(D2G_EUNSUPPORTED, "--count-threshold > 1 not implemented on the GPU");
+    if (p->mode < D2G_MODE_OPMH || p->mode > D2G_MODE_PROBMINHASH) return fail(D2G_EINVAL, "bad sketch mode %d", p->mode);
+    if ((p->mode == D2G_MODE_BAGMINHASH || p->mode == D2G_MODE_PROBMINHASH) && p->sketchsize < 2) return fail(D2G_EINVAL, "weighted sketches need sketchsize >= 2");
+    if (p->count_threshold > 1 && (p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH))
+        return fail(D2G_EUNSUPPORTED, "--count-threshold > 1 is implemented for the counting sketches (--multiset/--prob) only");
     if (p->countsketch_size) return fail(D2G_EUNSUPPORTED, "--countsketch-size not implemented on the GPU");
     return D2G_OK;
 }
@@ -308,6 +313,136 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const 
     return D2G_OK;
 }
 
+// BagMinHash / ProbMinHash (see weighted_kernels.cuh): emit -> sort -> run-length encode -> sketch -> verify loop.
+// sig_d [n_ent][S], card_d [n_ent].  Synchronises (needs the number of distinct elements and the redo count).
+__global__ void weighted_finalize_kernel(const uint64_t *keys, const unsigned long long *wsum, uint32_t n_ent, uint32_t m, double *sig, double *card) {
+    const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (sig && e < (uint64_t)n_ent * m) sig[e] = d2g::dunkey(keys[e]);
+    if (card && e < n_ent) card[e] = (double)wsum[e];
+}
+
+int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+                    uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d) {
+    if (ids_d) return fail(D2G_EUNSUPPORTED, "--save-kmers ids for BagMinHash/ProbMinHash are not implemented on the GPU yet");
+    const uint32_t m = p->sketchsize;
+    const uint64_t n = total_len, nreg = (uint64_t)n_ent * m;
+    if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "counting sketches: at most 2^32 bases per batch (got %llu)", (unsigned long long)n);
+    const bool windowed = p->w > p->k;
+    const uint64_t ovf_cap = 1ULL << 20;
+    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
+    // wbuf layout
+    uint64_t off = 0;
+    const uint64_t o_hvA = off; off += al(n * 8 + 8);
+    const uint64_t o_hvB = off; off += al(n * 8 + 8);
+    const uint64_t o_entA = off; off += al(n * 4 + 4);
+    const uint64_t o_entB = off; off += al(n * 4 + 4);
+    const uint64_t o_flag = off; off += al(n * 4 + 4);
+    const uint64_t o_excl = off; off += al(n * 4 + 4);
+    const uint64_t o_pos = off; off += al(n * 4 + 4);
+    const uint64_t o_keys = off; off += al(nreg * 8);
+    const uint64_t o_wsum = off; off += al((uint64_t)n_ent * 8);
+    const uint64_t o_T = off; off += al((uint64_t)n_ent * 8);
+    const uint64_t o_state = off; off += al((uint64_t)n_ent * 4);
+    const uint64_t o_misc = off; off += 256;            // n_valid, ovf_count, n_redo, error
+    const uint64_t o_ovf = off; off += al(ovf_cap * 8);
+    if (int rc = c->wbuf.reserve(off)) return rc;
+    unsigned char *B = c->wbuf.as<unsigned char>();
+    uint64_t *hvA = (uint64_t *)(B + o_hvA), *hvB = (uint64_t *)(B + o_hvB);
+    uint32_t *entA = (uint32_t *)(B + o_entA), *entB = (uint32_t *)(B + o_entB);
+    uint32_t *flag = (uint32_t *)(B + o_flag), *excl = (uint32_t *)(B + o_excl), *pos = (uint32_t *)(B + o_pos);
+    uint64_t *keys = (uint64_t *)(B + o_keys);
+    unsigned long long *wsum = (unsigned long long *)(B + o_wsum);
+    double *T = (double *)(B + o_T);
+    uint32_t *state = (uint32_t *)(B + o_state);
+    unsigned long long *n_valid = (unsigned long long *)(B + o_misc), *ovf_count = n_valid + 1;
+    unsigned int *n_redo = (unsigned int *)(n_valid + 2), *error = n_redo + 1;
+    uint64_t *ovf = (uint64_t *)(B + o_ovf);
+    cudaStream_t st = c->stream;
+    CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
+    CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
+    CU(cudaMemsetAsync(B + o_wsum, 0, al((uint64_t)n_ent * 8), st));
+    CU(cudaMemsetAsync(B + o_misc, 0, 256, st));
+    fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, st>>>(keys, nreg, d2g::FSS_KEY_EMPTY);
+    c->launches++;
+    uint64_t nu = 0;
+    if (n && n_rec) {
+        d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, 0);
+        if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
+        d2g::EmitConsumer::Params ep{hvA, entA, a.span};
+        if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, windowed, D2G_T_SKETCH_MAIN)) return rc;
+        // sort by (entity, value): LSD radix -- value first, then a stable pass over the entity
+        size_t t1 = 0, t2 = 0, t3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, t3, flag, excl, n, st);
+        const size_t tb = std::max(t1, std::max(t2, t3));
+        if (int rc = c->wtmp.reserve(tb + 256)) return rc;
+        size_t tbytes = tb;
+        CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
+        tbytes = tb;
+        CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+        c->launches += 2 * 9;
+        const unsigned gb = (unsigned)((n + 255) / 256);
+        d2g::rle_flag_kernel<<<gb, 256, 0, st>>>(hvA, entA, n, flag);
+        tbytes = tb;
+        CU(cub::DeviceScan::ExclusiveSum(c->wtmp.p, tbytes, flag, excl, n, st));
+        d2g::rle_scatter_kernel<<<gb, 256, 0, st>>>(flag, excl, entA, n, pos, n_valid);
+        c->launches += 3;
+        uint32_t h_last[2] = {0, 0};
+        CU(cudaMemcpyAsync(&h_last[0], excl + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&h_last[1], flag + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        nu = (uint64_t)h_last[0] + h_last[1];
+    }
+    const double threshold = (double)p->count_threshold;
+    if (nu) {
+        const unsigned gu = (unsigned)((nu + 127) / 128);
+        d2g::weight_sum_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(entA, pos, nu, n_valid, threshold, wsum);
+        d2g::weighted_guess_kernel<<<(n_ent + 255) / 256, 256, 0, st>>>(wsum, n_ent, m, T, state);
+        c->launches += 2;
+        d2g::WeightedArgs wa{hvA, entA, pos, nu, n_valid, threshold, m, T, state, keys, ovf, ovf_count, ovf_cap, error};
+        d2g::TexpConsts tc{};
+        if (p->mode == D2G_MODE_PROBMINHASH) {   // bmh.h:490-502
+            const long double lambda = log1pl(1.L / (m - 1));
+            const long double c1 = (expl(lambda) - 1.L) / lambda, c2 = logl(2.L / (1.L + expl(-lambda))) / lambda, c3 = (1.L - expl(-lambda)) / lambda;
+            tc = d2g::TexpConsts{(double)lambda, (double)c1, (double)c2, (double)c3, (double)(c1 * lambda)};
+        }
+        uint64_t nslots = std::min<uint64_t>(4096, (256ULL << 20) / ((uint64_t)m * 8));
+        nslots = std::max<uint64_t>(32, nslots / 32 * 32);
+        if (p->mode == D2G_MODE_PROBMINHASH) { if (int rc = c->aux2.reserve(nslots * 2ULL * m * 4)) return rc; }
+        for (int round = 0; round < 40; ++round) {
+            CU(cudaMemsetAsync(n_redo, 0, 4, st));
+            CU(cudaMemsetAsync(ovf_count, 0, 8, st));
+            {
+                KernelTimer kt(c, D2G_T_SKETCH_BOOT);
+                if (p->mode == D2G_MODE_PROBMINHASH) {
+                    d2g::pmh_kernel<<<gu, 128, 0, st>>>(wa, tc);
+                    CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, st));
+                    d2g::pmh_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, st>>>(wa, tc, c->aux2.as<uint32_t>());
+                    c->launches += 2;
+                } else {
+                    d2g::bmh_kernel<<<gu, 128, 0, st>>>(wa);
+                    c->launches++;
+                }
+            }
+            d2g::weighted_verify_kernel<<<n_ent, 256, 0, st>>>(keys, m, T, state, n_redo);
+            c->launches++;
+            unsigned int h[2] = {0, 0};
+            CU(cudaMemcpyAsync(h, n_redo, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            CU(cudaGetLastError());
+            if (h[1]) return fail(D2G_EUNSUPPORTED, "weighted sketch: device work queue overflow (code %u); split the batch", h[1]);
+            if (!h[0]) break;
+            if (round == 39) return fail(D2G_ECUDA, "weighted sketch: bound verification did not converge");
+        }
+    }
+    const uint64_t nthreads = std::max<uint64_t>(nreg, n_ent);
+    weighted_finalize_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(keys, wsum, n_ent, m, sig_d, card_d);
+    c->launches++;
+    CU(cudaGetLastError());
+    return D2G_OK;
+}
+
 // Host finalisation of one-permutation registers: x87 long double, as the reference does on the host
 // (src/oph.h:240-263).  Threads over entities.
 void opmh_finalize_host(const uint64_t *regs, uint32_t n_ent, uint32_t m, uint32_t S, double *sig, double *card) {
@@ -367,7 +502,9 @@ extern "C" int d2g_sketch_batch_dev(d2g_ctx *c, const d2g_sketch_params *p, cons
         }
         return D2G_OK;
     }
-    return launch_fss(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, sig_out_d, card_out_d, ids_out_d);
+    if (p->mode == D2G_MODE_FULL_SETSKETCH)
+        return launch_fss(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, sig_out_d, card_out_d, ids_out_d);
+    return launch_weighted(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, sig_out_d, card_out_d, ids_out_d);
 }
 
 extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const char *seq, const uint64_t *rec_off,
@@ -416,8 +553,13 @@ extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const ch
     if (int rc = c->sig.reserve((uint64_t)n_entities * S * 8)) return rc;
     if (int rc = c->card.reserve((uint64_t)n_entities * 8)) return rc;
     if (ids_out) if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) return rc;
-    if (int rc = launch_fss(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len,
-                            c->sig.as<double>(), c->card.as<double>(), ids_out ? c->ids.as<uint64_t>() : nullptr)) return rc;
+    if (p->mode == D2G_MODE_FULL_SETSKETCH) {
+        if (int rc = launch_fss(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len,
+                                c->sig.as<double>(), c->card.as<double>(), ids_out ? c->ids.as<uint64_t>() : nullptr)) return rc;
+    } else {
+        if (int rc = launch_weighted(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len,
+                                     c->sig.as<double>(), c->card.as<double>(), ids_out ? c->ids.as<uint64_t>() : nullptr)) return rc;
+    }
     if (sig_out) CU(cudaMemcpyAsync(sig_out, c->sig.p, (uint64_t)n_entities * S * 8, cudaMemcpyDeviceToHost, c->stream));
     if (card_out) CU(cudaMemcpyAsync(card_out, c->card.p, (uint64_t)n_entities * 8, cudaMemcpyDeviceToHost, c->stream));
     if (ids_out) CU(cudaMemcpyAsync(ids_out, c->ids.p, (uint64_t)n_entities * S * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -62,7 +62,8 @@ struct FssBootConsumer {
         p = pp; s = reinterpret_cast<uint64_t *>(smem);
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) s[i] = 0;
     }
-    __device__ __forceinline__ void begin_entity(uint32_t) {}
+    static constexpr bool kEveryWindow = false;
+    __device__ __forceinline__ void begin_entity(uint32_t, uint64_t) {}
     __device__ __forceinline__ void consume(uint64_t hv) {
         const uint64_t rv = cehash(hv ^ FSS_XOR);
         uint64_t st = rv;
@@ -190,7 +191,8 @@ struct FssMainConsumer {
         const double scaled = exp(-t * (double)m) * (1. - 1e-6) * 18446744073709551616.0;
         return scaled >= 18446744073709549568.0 ? 0xFFFFFFFFFFFFF800ULL : (scaled <= 0. ? 0 : (uint64_t)scaled);
     }
-    __device__ __forceinline__ void begin_entity(uint32_t ent) {
+    static constexpr bool kEveryWindow = false;
+    __device__ __forceinline__ void begin_entity(uint32_t ent, uint64_t) {
         T = *reinterpret_cast<volatile double *>(p.T + ent); rvmin = rvmin_for(T, p.m);
     }
     __device__ __forceinline__ void consume(uint64_t hv) {

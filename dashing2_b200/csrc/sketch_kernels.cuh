@@ -101,7 +101,8 @@ struct OpmhConsumer {
         p = pp; sreg = reinterpret_cast<uint64_t *>(smem);
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) sreg[i] = ~0ULL;
     }
-    __device__ __forceinline__ void begin_entity(uint32_t) {}
+    static constexpr bool kEveryWindow = false;   // set semantics: consecutive equal minimizers feed the sketch once
+    __device__ __forceinline__ void begin_entity(uint32_t, uint64_t) {}
     __device__ __forceinline__ void consume(uint64_t hv) {
         const uint64_t id = dhash(hv);                       // oph.h:178
         const uint32_t idx = fastmod32((uint32_t)id, p.fm);  // oph.h:184 (32-bit truncation, div.h:256-262)
@@ -156,7 +157,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
         if (ent != cur_ent) {
             if (cur_ent != 0xFFFFFFFFu) cons.flush(cur_ent);
             cur_ent = ent;
-            cons.begin_entity(ent);
+            cons.begin_entity(ent, p0 - span_lo);
         }
         for (uint64_t t0 = p0; t0 < p1; t0 += SK_TILE) {
             if (a.tile_stride > 1 && ((t0 / SK_TILE) % a.tile_stride) != 0) continue;
@@ -228,7 +229,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                             if (j < jn) {
                                 if (j) run = min(run, score[sk_pad(j0 + wsz - 1 + j)]);
                                 const uint64_t mn = min(min(left[j], common), run);
-                                if (!have_prev || mn != prev) {
+                                if (Consumer::kEveryWindow || !have_prev || mn != prev) {
                                     const uint64_t km = frev64_inv(mn);
                                     if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask));
                                 }
@@ -239,7 +240,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                         for (int j = 0; j < jn; ++j) {
                             uint64_t mn = ~0ULL;
                             for (int q = 0; q < wsz; ++q) mn = min(mn, score[sk_pad(j0 + j + q)]);
-                            if (!have_prev || mn != prev) {
+                            if (Consumer::kEveryWindow || !have_prev || mn != prev) {
                                 const uint64_t km = frev64_inv(mn);
                                 if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask));
                             }

@@ -488,3 +488,182 @@ void d2o_panel(const double *regs, const double *cards, uint64_t nf, uint64_t nq
         for (uint64_t j = 0; j < nq; ++j)
             *out++ = d2o_compare(regs + i * S, regs + (nf + j) * S, S, cards[i], cards[nf + j], measure, k, cmp_kind);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* exact counting + ProbMinHash3 + BagMinHash2                                                 */
+/* ------------------------------------------------------------------------------------------ */
+static int cmp_u64(const void *a, const void *b) { uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }
+uint64_t d2o_count_exact(uint64_t *hv, uint64_t n, uint64_t *keys, double *counts) {
+    qsort(hv, n, 8, cmp_u64);
+    uint64_t nd = 0;
+    for (uint64_t i = 0; i < n;) {
+        uint64_t j = i; while (j < n && hv[j] == hv[i]) ++j;
+        keys[nd] = hv[i]; counts[nd] = (double)(int32_t)(j - i); ++nd; i = j;
+    }
+    return nd;
+}
+
+/* value tree of bmh.h:53-91 (update returns -1 on equality, 1 when lowered, 0 otherwise) */
+static int bmh_mvt_update(double *d, uint32_t m, uint64_t index, double x) {
+    const uint64_t sz = 2ULL * m - 1;
+    if (x == d[index]) return -1;
+    if (x < d[index]) {
+        do {
+            d[index] = x;
+            index = m + (index >> 1);
+            if (index >= sz) break;
+            const uint64_t lhi = (index - m) << 1, rhi = lhi + 1;
+            x = d[lhi] > d[rhi] ? d[lhi] : d[rhi];
+        } while (x < d[index]);
+        return 1;
+    }
+    return 0;
+}
+
+void d2o_pmh_reset(double *regs, uint64_t *ids, uint32_t m) {
+    for (uint64_t i = 0; i < 2ULL * m - 1; ++i) regs[i] = DBL_MAX;
+    if (ids) memset(ids, 0, 8ULL * m);
+}
+
+typedef struct { double lambda, c1, c2, c3, c4; } texp_t;
+static texp_t texp_constants(uint32_t m) { /* bmh.h:490-502, long double then narrowed */
+    const long double lambda = log1pl(1.L / (m - 1));
+    const long double c1 = (expl(lambda) - 1.L) / lambda;
+    const long double c2 = logl(2.L / (1.L + expl(-lambda))) / lambda;
+    const long double c3 = (1.L - expl(-lambda)) / lambda;
+    const long double c4 = c1 * lambda;
+    texp_t t = {(double)lambda, (double)c1, (double)c2, (double)c3, (double)c4};
+    return t;
+}
+static double texp_sample(uint64_t rngstate, const texp_t *c) { /* truncexpsamplestepped, bmh.h:507-525 */
+    double x = (0x1p-64 * (double)rngstate) * c->c1;
+    if (x >= 1.) {
+        for (;;) {
+            if ((x = 0x1p-64 * (double)d2o_wyhash64(&rngstate)) < c->c2) break;
+            double yhat = 0.5 * (0x1p-64 * (double)d2o_wyhash64(&rngstate));
+            double omx = 1. - x;
+            if (yhat > omx) { x = omx; yhat = 1. - yhat; }
+            omx = 1. - x;
+            if (x <= c->c3 * (1. - yhat) || (yhat * c->c1 <= omx)) break;
+            if (fma(yhat, c->c4, 1.) <= exp(c->lambda * omx)) break;
+        }
+    }
+    return x;
+}
+
+double d2o_pmh_update(double *regs, uint64_t *ids, uint32_t m, const uint64_t *keys, const double *wts, uint64_t n, double threshold) {
+    lazyshuf_t ls; ls.n = m; ls.c = 0;
+    ls.g = (uint32_t *)calloc(m, 4); ls.v = (uint32_t *)calloc(m, 4);
+    const texp_t tc = texp_constants(m);
+    double tw = 0., twc = 0.;
+    for (uint64_t e = 0; e < n; ++e) {
+        const uint64_t id = keys[e]; const double w = wts[e];
+        if (!(w > threshold) || w <= 0.) continue;
+        { double inc = w - twc; const double tmp = tw + inc; twc = (tmp - tw) - inc; tw = tmp; }
+        uint64_t hi = id;
+        const double wi = 1. / w;
+        uint64_t i = 0;
+        uint64_t rv = d2o_wyhash64(&hi);
+        double maxv = regs[2ULL * m - 2];
+        double hv = wi * texp_sample(rv, &tc);
+        if (hv >= maxv) continue;
+        ls.i = 0; ++ls.c; ls.state = rv; ls.off = 16;
+        while (hv < maxv) {
+            const uint32_t idx = ls_step(&ls);
+            if (bmh_mvt_update(regs, m, idx, hv)) {
+                if (ids) ids[idx] = id;
+                maxv = regs[2ULL * m - 2];
+                if (hv >= maxv) break;
+            }
+            if ((hv = wi * (double)(++i)) > maxv) break;
+            hv = fma(wi, texp_sample(d2o_wyhash64(&rv), &tc), hv);
+        }
+    }
+    free(ls.g); free(ls.v);
+    return tw;
+}
+
+/* ---- BagMinHash2 ---- */
+typedef struct { double x, weight, minp, maxq, carry; uint64_t idx, wyv, id; } pproc_t;
+static inline uint64_t d2bits(double d) { uint64_t b; memcpy(&b, &d, 8); return b; }
+static inline double bits2d(uint64_t b) { double d; memcpy(&d, &b, 8); return d; }
+static void pp_step(pproc_t *p, uint32_t m) { /* bmh.h:170-176 */
+    const uint64_t xi = d2o_wyhash64(&p->wyv);
+    double inc = -log((double)(xi >> 12) * 2.220446049250313e-16) / (p->maxq - p->minp);
+    inc -= p->carry;
+    const double tmp = p->x + inc;
+    p->carry = (tmp - p->x) - inc;
+    p->x = tmp;
+    p->idx = xi % m;
+}
+static inline int pp_partially(const pproc_t *p) { return bits2d(d2bits(p->minp) + 1) <= p->weight; }
+static inline int pp_fully(const pproc_t *p) { return p->maxq <= p->weight; }
+static inline int pp_can_split(const pproc_t *p) { return d2bits(p->maxq) > d2bits(p->minp) + 1; }
+static pproc_t pp_split(pproc_t *p) { /* bmh.h:182-206 */
+    uint64_t midpoint = (d2bits(p->minp) + d2bits(p->maxq)) / 2;
+    const double midval = bits2d(midpoint);
+    const uint64_t rval = d2o_wyhash64(&midpoint);
+    uint64_t xval = d2bits(p->x) ^ rval;
+    const double pr = (midval - p->minp) / (p->maxq - p->minp);
+    const double rv = (double)d2o_wyhash64(&xval) * 5.421010862427522e-20;
+    const int goleft = rv < pr;
+    pproc_t r = *p;
+    r.minp = goleft ? midval : p->minp; r.maxq = goleft ? p->maxq : midval; r.wyv = xval;
+    r.idx = ~0ULL; /* a fresh process has no index until it steps; it is never used before */
+    if (goleft) p->maxq = midval; else p->minp = midval;
+    return r;
+}
+static void bmh_hv_update(double *regs, uint64_t *ids, uint32_t m, const pproc_t *p) {
+    if (bmh_mvt_update(regs, m, p->idx, p->x) && ids) ids[p->idx] = p->id;
+}
+/* binary min-heap on x (the reference's priority queue pops the smallest x first: operator< is reversed, bmh.h:165-166) */
+typedef struct { pproc_t *v; size_t n, cap; } pheap_t;
+static void ph_push(pheap_t *h, pproc_t p) {
+    if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 64; h->v = (pproc_t *)realloc(h->v, h->cap * sizeof(pproc_t)); }
+    size_t i = h->n++; h->v[i] = p;
+    while (i && h->v[(i - 1) / 2].x > h->v[i].x) { pproc_t t = h->v[i]; h->v[i] = h->v[(i - 1) / 2]; h->v[(i - 1) / 2] = t; i = (i - 1) / 2; }
+}
+static pproc_t ph_pop(pheap_t *h) {
+    pproc_t top = h->v[0]; h->v[0] = h->v[--h->n];
+    size_t i = 0;
+    for (;;) { size_t l = 2 * i + 1, r = l + 1, s = i;
+        if (l < h->n && h->v[l].x < h->v[s].x) s = l;
+        if (r < h->n && h->v[r].x < h->v[s].x) s = r;
+        if (s == i) break; pproc_t t = h->v[i]; h->v[i] = h->v[s]; h->v[s] = t; i = s; }
+    return top;
+}
+
+double d2o_bmh_update(double *regs, uint64_t *ids, uint32_t m, const uint64_t *keys, const double *wts, uint64_t n, double threshold) {
+    pheap_t heap = {0, 0, 0};
+    double tw = 0., twc = 0.;
+    const uint64_t top = 2ULL * m - 2;
+    for (uint64_t e = 0; e < n; ++e) {
+        const double w = wts[e];
+        if (!(w > threshold) || w <= 0.) continue;
+        { double inc = w - twc; const double tmp = tw + inc; twc = (tmp - tw) - inc; tw = tmp; }
+        pproc_t p = {0., w, 0., DBL_MAX, 0., ~0ULL, keys[e], keys[e]};
+        pp_step(&p, m);
+        if (pp_fully(&p)) bmh_hv_update(regs, ids, m, &p);
+        heap.n = 0;
+        while (p.x < regs[top]) {
+            while (pp_can_split(&p) && pp_partially(&p)) {
+                pproc_t q = pp_split(&p);
+                if (pp_fully(&p)) bmh_hv_update(regs, ids, m, &p);
+                if (pp_partially(&q)) {
+                    pp_step(&q, m);
+                    if (pp_fully(&q)) bmh_hv_update(regs, ids, m, &q);
+                    if (pp_partially(&q)) ph_push(&heap, q);
+                }
+            }
+            if (pp_fully(&p)) {
+                pp_step(&p, m);
+                bmh_hv_update(regs, ids, m, &p);
+                if (p.x <= regs[top]) ph_push(&heap, p);
+            }
+            if (heap.n == 0) break;
+            p = ph_pop(&heap);
+        }
+    }
+    free(heap.v);
+    return tw;
+}

@@ -82,3 +82,22 @@ void d2o_panel(const double *regs, const double *cards, uint64_t nf, uint64_t nq
 }
 #endif
 #endif
+
+/* ---- weighted sketches over (hashed k-mer, count) pairs: src/counter.h:68-77,118-138 ------------------ */
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* Sorts hv in place and run-length encodes it: keys[i] with counts[i]; returns the number of distinct keys.
+ * (The reference counts in a hash map; sketches below are order independent, so sorted order is as good.) */
+uint64_t d2o_count_exact(uint64_t *hv, uint64_t n, uint64_t *keys, double *counts);
+/* ProbMinHash3 (bonsai/hll/include/sketch/bmh.h:662-700; base :545-661; truncated exponential :490-525).
+ * regs f64[2m-1] (value tree), ids u64[m]; returns total weight. Elements with count <= threshold are skipped
+ * (src/counter.h:123). */
+void d2o_pmh_reset(double *regs, uint64_t *ids, uint32_t m);
+double d2o_pmh_update(double *regs, uint64_t *ids, uint32_t m, const uint64_t *keys, const double *w, uint64_t n, double threshold);
+/* BagMinHash2 (bmh.h:269-316 update_2, poisson_process_t :129-207), restated per element without the carried heap
+ * (the carried heap only ever holds points that cannot lower a register). */
+double d2o_bmh_update(double *regs, uint64_t *ids, uint32_t m, const uint64_t *keys, const double *w, uint64_t n, double threshold);
+#ifdef __cplusplus
+}
+#endif

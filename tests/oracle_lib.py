@@ -59,6 +59,11 @@ def lib():
     for nm in ("d2o_allpairs_symmetric", "d2o_allpairs_asymmetric"):
         getattr(L, nm).argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
     L.d2o_panel.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
+    L.d2o_count_exact.restype = C.c_uint64; L.d2o_count_exact.argtypes = [u64p, C.c_uint64, u64p, f64p]
+    L.d2o_pmh_reset.argtypes = [f64p, C.c_void_p, C.c_uint32]
+    for nm in ("d2o_pmh_update", "d2o_bmh_update"):
+        getattr(L, nm).restype = C.c_double
+        getattr(L, nm).argtypes = [f64p, C.c_void_p, C.c_uint32, u64p, f64p, C.c_uint64, C.c_double]
     _lib = L
     return L
 
@@ -132,7 +137,21 @@ def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool =
         ids = np.zeros(S, dtype=np.uint64)
         L.d2o_css_update(regs, S, hv, len(hv), ids.ctypes.data)
         return dict(card=L.d2o_css_card(regs, S), sig=regs[:S].copy(), ids=ids, n_hashed=len(hv))
+    if mode in ("pmh", "bmh"):
+        return weighted_sketch(hv, mode, S, count_threshold)
     raise ValueError(mode)
+
+
+def weighted_sketch(hv: np.ndarray, mode: str, S: int, count_threshold: float = 0.0):
+    """Counter (exact) + ProbMinHash3 / BagMinHash2 over a hashed k-mer stream (src/fastxsketch.cpp:429-449)."""
+    L = lib()
+    keys = np.empty(len(hv) + 1, dtype=np.uint64); cnt = np.empty(len(hv) + 1, dtype=np.float64)
+    nd = L.d2o_count_exact(hv.copy(), len(hv), keys, cnt)
+    regs = np.empty(2 * S - 1, dtype=np.float64)
+    L.d2o_pmh_reset(regs, None, S)
+    fn = L.d2o_pmh_update if mode == "pmh" else L.d2o_bmh_update
+    tw = fn(regs, None, S, keys[:nd].copy(), cnt[:nd].copy(), nd, float(count_threshold))
+    return dict(card=tw, sig=regs[:S].copy(), n_hashed=len(hv), n_distinct=nd)
 
 
 def densify(sig: np.ndarray) -> np.ndarray:

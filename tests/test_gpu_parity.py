@@ -22,6 +22,8 @@ SKETCH = {
     "opmh_k31_S1000": dict(mode="opmh", S=1000, k=31),
     "fss_k31_S256": dict(mode="fss", S=256, k=31),
     "fss_k31_w51_S1024": dict(mode="fss", S=1024, k=31, w=51),
+    "pmh_k31_S128": dict(mode="pmh", S=128, k=31),
+    "bmh_k31_S128": dict(mode="bmh", S=128, k=31),
 }
 
 
@@ -38,7 +40,7 @@ def test_sketch_matches_reference_golden(case, golden_inputs):
     r = c.sketch_batch(seq, off, ent, len(paths), c.params(**SKETCH[case]))
     for i, nm in enumerate(names):
         assert np.array_equal(u64(r["sig"][i]), u64(z["sigs"][i])), (case, nm)
-    if SKETCH[case]["mode"] == "opmh":
+    if SKETCH[case]["mode"] in ("opmh", "pmh", "bmh"):
         assert np.array_equal(u64(r["card"]), u64(z["cards"]))
     else:
         np.testing.assert_allclose(r["card"], z["cards"], rtol=1e-12)
@@ -103,6 +105,29 @@ def test_sketch_matches_oracle_seeded(mode, S, k, w, tmp_path):
             L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), None)
             assert np.array_equal(u64(r["sig"][e]), u64(regs[:S])), (mode, S, e)
             np.testing.assert_allclose(r["card"][e], L.d2o_css_card(regs, S), rtol=1e-12)
+
+
+@pytest.mark.parametrize("mode,S,k,w,thr", [("pmh", 256, 31, -1, 0), ("bmh", 256, 31, -1, 0), ("pmh", 1024, 21, 40, 0), ("bmh", 64, 21, 40, 0),
+                                             ("pmh", 512, 31, -1, 1), ("bmh", 8192, 31, -1, 0), ("pmh", 8192, 31, -1, 0)])
+def test_weighted_sketch_matches_oracle_seeded(mode, S, k, w, thr):
+    """Counting sketches: duplicated content (counts > 1), windows (every window counts), --count-threshold,
+    entities too small for the first bound guess, S up to the BASELINE config-3 value 8192."""
+    from dashing2_b200 import synth
+    files = []
+    for g, s in synth.family_genomes(3, 120_000, seed=300 + S, dup_frac=0.3):
+        b = s.tobytes()
+        files.append([b[:70_000], b[70_000:], b"ACGTNNNN" + b[:500]])
+    files.append([b"ACGT" * 20])        # tiny entity
+    files.append([])
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    r = c.sketch_batch(seq, off, ent, len(files), c.params(mode=mode, S=S, k=k, w=w, count_threshold=thr))
+    for e, recs in enumerate(files):
+        hv = [O.hash_stream(x, k, w) for x in recs]
+        hv = np.concatenate(hv) if hv else np.empty(0, dtype=np.uint64)
+        o = O.weighted_sketch(hv, mode, S, thr)
+        assert np.array_equal(u64(r["sig"][e]), u64(o["sig"])), (mode, S, e, int((r["sig"][e] != o["sig"]).sum()))
+        assert r["card"][e] == o["card"]
 
 
 def test_sketch_merge_property_full_size():
