@@ -88,9 +88,25 @@ def test_cmp_presketched_and_panel(tmp_path):
             assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), exp.view(np.uint32)), (suffix, kind)
 
 
+def test_multiset_and_prob_cache_files(golden_inputs, tmp_path):
+    """--multiset / --prob --cache: reference-named .bmh / .pmh cache files with reference bytes."""
+    names, paths = golden_inputs
+    flist = tmp_path / "files.txt"; flist.write_text("\n".join(paths) + "\n")
+    for flag, tag, space, suf in (("--multiset", "bmh", "MultisetSpace", ".bmh"), ("--prob", "pmh", "ProbsetSpace", ".pmh")):
+        cdir = tmp_path / tag; cdir.mkdir()
+        out = str(tmp_path / (tag + ".stk"))
+        run(["sketch", "-F", str(flist), "-k31", "-S128", flag, "--cache", "--outprefix", str(cdir), "-o", out])
+        z = np.load(expected(f"{tag}_k31_S128.npz"))
+        cards, sigs = read_stacked(out)
+        assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64)) and np.array_equal(cards, z["cards"])
+        f0 = cdir / (os.path.basename(paths[0]) + f".rc_canon.sketchsize128.k31.ExactCounting.{space}.DNA{suf}")
+        d = np.fromfile(f0, dtype=np.float64)
+        assert d[0] == z["cards"][0] and np.array_equal(d[1:], z["sigs"][0])
+
+
 def test_unsupported_options_fail_loudly(golden_inputs):
     names, paths = golden_inputs
-    for argv in (["sketch", "-k31", "--multiset", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0]],
+    for argv in (["sketch", "-k31", "--countsketch-size", "1000", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0]],
                  ["contain", paths[0]]):
         r = subprocess.run([EXE] + argv, capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.strip()
