@@ -325,7 +325,6 @@ struct Writer {
 
 void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
     const uint64_t n = sk.card.size(), S = sk.S;
-    if (o.topk > 0) die("--topk (LSH nearest-neighbour graphs) is not implemented in the GPU front-end yet");
     if (sk.mode == D2G_MODE_OPMH) chk(d2g_densify(ctx, sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), n, (uint32_t)S));  // cmp_core.cpp:686-718
     d2g_cmp_params cp{};
     cp.sketchsize = (uint32_t)S; cp.measure = o.measure; cp.k = o.k; cp.shape = o.shape; cp.n = n; cp.nq = o.nq;
@@ -333,6 +332,28 @@ void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
     const bool to_stdout = o.cmpout.empty() || o.cmpout[0] == '-';
     std::FILE *fp = to_stdout ? stdout : std::fopen(o.cmpout.c_str(), "wb");
     if (!fp) die("Failed to open path " + o.cmpout + " for writing");
+    if (o.topk > 0) {   // KNN graph: build_index + refine_results + emit_neighbors (src/cmp_core.cpp:756-799, src/emitnn.cpp:12-52)
+        cp.shape = D2G_SYMMETRIC;
+        std::vector<uint64_t> indptr(n + 1); uint32_t *idx = nullptr; float *val = nullptr;
+        const double *r = sk.sig.data();
+        if (cp.cmp_kind == D2G_CMP_EQ && sk.ids.size() == sk.sig.size()) r = reinterpret_cast<const double *>(sk.ids.data());
+        chk(d2g_lsh_topk(ctx, &cp, r, sk.card.data(), o.topk, indptr.data(), &idx, &val));
+        const uint64_t nnz = indptr[n];
+        if (o.binary) {
+            const uint64_t dims[2] = {n, nnz};
+            std::fwrite(dims, 8, 2, fp); std::fwrite(indptr.data(), 8, n + 1, fp); std::fwrite(idx, 4, nnz, fp); std::fwrite(val, 4, nnz, fp);
+        } else {
+            std::fputs("#Collection\tNeighbor lists -- name:distance, separated by tabs\n", fp);
+            for (uint64_t i = 0; i < n; ++i) {
+                std::fputs(i < sk.names.size() ? sk.names[i].c_str() : "", fp);
+                for (uint64_t j = indptr[i]; j < indptr[i + 1]; ++j) std::fprintf(fp, "\t%s:%.8g", idx[j] < sk.names.size() ? sk.names[idx[j]].c_str() : "", val[j]);
+                std::fputc('\n', fp);
+            }
+        }
+        d2g_free(idx); d2g_free(val);
+        if (!to_stdout) std::fclose(fp); else std::fflush(fp);
+        return;
+    }
     Writer w{o, sk, fp, (size_t)n, (size_t)o.nq, {}};
     if (!o.binary) {   // header, src/emitrect.cpp:136-151
         if (!o.phylip) {

@@ -1,0 +1,194 @@
+// lsh_kernels.cuh -- K8: LSH candidate generation + bounded neighbour lists + refinement for --topk.
+//
+// Reference: SetSketchIndex (/root/reference/src/ssi.h:290-453), build_index + heap update
+// (src/index_build.cpp:20-165), refine_results (src/refine.cpp:6-81), emit_neighbors (src/emitnn.cpp:12-52),
+// table geometry src/cmp_core.cpp:757-772.  The reference's output depends on thread timing;
+// the contract implemented here is its sequential (-p1) order, reproduced exactly:
+//   keys    : 32-bit key of every (table, sketch): table type 0 hashes one register, type 1 two registers;
+//   index   : per table, (key, id) sorted by key with ids ascending inside a bucket (= insertion order under -p1)
+//             -- a segmented radix sort replaces 1.5*S hash maps;
+//   query   : one warp per sketch walks the tables most-specific first; 32 tables are looked up at a time, their
+//             buckets are then merged strictly in table order, stopping the moment `maxcand` distinct ids were seen;
+//   arrivals: every candidate edge (q, pos) contributes (count, q) to list[cand] and (count, cand) to list[q]; a stable
+//             sort by list keeps the (q, pos, side) order, and one thread per list replays the bounded-heap rule;
+//   refine  : exact compare() of every survivor (one warp per edge), sort, drop zeros, keep top-k plus ties -> CSR.
+#pragma once
+#include "cmp_kernels.cuh"
+#include "common.cuh"
+
+namespace d2g {
+
+__device__ __forceinline__ uint32_t lsh_key(const double *sig, uint32_t type, uint64_t j) {   // ssi.h:320-331
+    if (type == 0) return (uint32_t)wang64((uint64_t)__double_as_longlong(sig[j]));
+    const uint64_t v0 = wang64((uint64_t)__double_as_longlong(sig[2 * j]));
+    const uint64_t v1 = wang64((uint64_t)__double_as_longlong(sig[2 * j + 1]) ^ v0);
+    return (uint32_t)(v0 ^ v1);
+}
+
+// keys[t][i], ids[t][i] = i ; table t < S: type 0 register t ; t >= S: type 1 registers 2(t-S), 2(t-S)+1
+__global__ void lsh_keys_kernel(const double *regs, uint64_t n, uint32_t S, uint32_t t0, uint32_t nt, uint32_t *keys, uint32_t *ids) {
+    const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= (uint64_t)nt * n) return;
+    const uint32_t t = t0 + (uint32_t)(e / n); const uint64_t i = e % n;
+    keys[e] = t < S ? lsh_key(regs + i * S, 0, t) : lsh_key(regs + i * S, 1, t - S);
+    ids[e] = (uint32_t)i;
+}
+
+// One warp per query.  skeys/sids: [ntab][n] sorted per table.  Outputs cand[q][maxcand], cnt[q][maxcand], ncand[q].
+__global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, const uint32_t *skeys, const uint32_t *sids,
+                                 uint32_t maxcand, uint32_t *cand, uint32_t *cnt, uint32_t *ncand) {
+    extern __shared__ uint32_t sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const uint64_t q = (uint64_t)blockIdx.x * wpb + wib;
+    if (q >= n) return;
+    uint32_t *set_id = sm + (size_t)wib * 2 * maxcand, *set_ct = set_id + maxcand;
+    const double *sig = regs + q * S;
+    uint32_t nset = 0;
+    const uint32_t ntab = S + S / 2;
+    // scan order: type 1 tables j = 0..S/2-1 (global index S + j), then type 0 tables j = 0..S-1 (ssi.h:425)
+    for (uint32_t base = 0; base < ntab && nset < maxcand; base += 32) {
+        const uint32_t o = base + lane;                  // position in scan order
+        uint32_t lo = 0, hi = 0;
+        if (o < ntab) {
+            const uint32_t t = o < S / 2 ? S + o : o - S / 2;
+            const uint32_t key = t < S ? lsh_key(sig, 0, t) : lsh_key(sig, 1, t - S);
+            const uint32_t *K = skeys + (uint64_t)t * n;
+            uint32_t a = 0, b = (uint32_t)n;
+            while (a < b) { const uint32_t mid = (a + b) >> 1; if (K[mid] < key) a = mid + 1; else b = mid; }
+            lo = a; b = (uint32_t)n;
+            while (a < b) { const uint32_t mid = (a + b) >> 1; if (K[mid] <= key) a = mid + 1; else b = mid; }
+            hi = a;
+        }
+        for (int l = 0; l < 32 && nset < maxcand; ++l) {     // merge the 32 buckets strictly in table order
+            const uint32_t blo = __shfl_sync(0xffffffffu, lo, l), bhi = __shfl_sync(0xffffffffu, hi, l);
+            const uint32_t oo = base + l;
+            if (oo >= ntab) break;
+            const uint32_t t = oo < S / 2 ? S + oo : oo - S / 2;
+            const uint32_t *I = sids + (uint64_t)t * n;
+            for (uint32_t p = blo; p < bhi && nset < maxcand; p += 32) {
+                const bool have = p + lane < bhi;
+                const uint32_t id = have ? I[p + lane] : 0xFFFFFFFFu;
+                int found = -1;
+                if (have) for (uint32_t f = 0; f < nset; ++f) if (set_id[f] == id) { found = (int)f; break; }
+                const uint32_t newmask = __ballot_sync(0xffffffffu, have && found < 0);
+                const uint32_t room = maxcand - nset;
+                // lane index at which the set becomes full (the room-th new id), if it does within this chunk
+                uint32_t stop_lane = 32;
+                if ((uint32_t)__popc(newmask) >= room) {          // 0-based lane of the room-th set bit
+                    uint32_t mm = newmask;
+                    for (uint32_t r = 1; r < room; ++r) mm &= mm - 1;
+                    stop_lane = (uint32_t)__ffs((int)mm) - 1;
+                }
+                if (have && (uint32_t)lane <= stop_lane) {
+                    if (found >= 0) ++set_ct[found];          // ids inside one bucket are distinct: no two lanes share an entry
+                    else { const uint32_t pos = nset + __popc(newmask & ((1u << lane) - 1)); set_id[pos] = id; set_ct[pos] = 1; }
+                }
+                nset += min((uint32_t)__popc(newmask), room);
+                __syncwarp();
+            }
+        }
+    }
+    for (uint32_t f = lane; f < nset; f += 32) { cand[q * maxcand + f] = set_id[f]; cnt[q * maxcand + f] = set_ct[f]; }
+    if (lane == 0) ncand[q] = nset;
+}
+
+// arrival records in (q, pos, side) order: index a = (q*maxcand + pos)*2 + side ; key = destination list
+__global__ void lsh_arrivals_kernel(const uint32_t *cand, const uint32_t *cnt, const uint32_t *ncand, uint64_t n, uint32_t maxcand,
+                                    uint32_t *alist, uint64_t *apay) {
+    const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= n * maxcand) return;
+    const uint64_t q = e / maxcand; const uint32_t pos = (uint32_t)(e % maxcand);
+    uint32_t l0 = 0xFFFFFFFFu, l1 = 0xFFFFFFFFu; uint64_t p0 = 0, p1 = 0;
+    if (pos < ncand[q]) {
+        const uint32_t oid = cand[e];
+        if (oid != (uint32_t)q) {                                       // index_build.cpp:131
+            const uint32_t cd = __float_as_uint(-(float)cnt[e]);
+            l0 = oid; p0 = ((uint64_t)(uint32_t)q << 32) | cd;          // update(neighbor_lists[oid], {cd, id})
+            l1 = (uint32_t)q; p1 = ((uint64_t)oid << 32) | cd;          // update(neighbor_lists[id], {cd, oid})
+        }
+    }
+    alist[2 * e] = l0; apay[2 * e] = p0; alist[2 * e + 1] = l1; apay[2 * e + 1] = p1;
+}
+
+struct Nb { float d; uint32_t id; };
+__device__ __forceinline__ bool nb_less(const Nb &a, const Nb &b) { return a.d < b.d || (a.d == b.d && a.id < b.id); }
+
+// one thread per list: replay update() (index_build.cpp:20-44) over its arrivals [seg[x], seg[x+1]); the list lives in
+// lst[seg[x]..] (sorted ascending, so back = priority-queue top), the dedup set in dset[seg[x]..]
+__global__ void lsh_replay_kernel(const uint64_t *apay, const uint32_t *seg, uint64_t n, uint32_t k, Nb *lst, uint32_t *dset, uint32_t *lsize) {
+    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const uint32_t s0 = seg[x], s1 = seg[x + 1];
+    Nb *L = lst + s0; uint32_t *D = dset + s0;
+    uint32_t nl = 0, nd = 0;
+    auto push = [&](Nb it) { uint32_t i = nl++; while (i && nb_less(it, L[i - 1])) { L[i] = L[i - 1]; --i; } L[i] = it; };
+    for (uint32_t a = s0; a < s1; ++a) {
+        const uint64_t pay = apay[a];
+        const Nb it{__uint_as_float((uint32_t)pay), (uint32_t)(pay >> 32)};
+        bool in = false;
+        for (uint32_t f = 0; f < nd; ++f) if (D[f] == it.id) { in = true; break; }
+        if (in) continue;
+        if (nl < k) { D[nd++] = it.id; push(it); continue; }
+        const Nb top = L[nl - 1];
+        if (it.d <= top.d) {
+            if (top.d != it.d) { for (uint32_t f = 0; f < nd; ++f) if (D[f] == top.id) { D[f] = D[--nd]; break; } --nl; }
+            push(it);                                                      // not added to the dedup set (reference quirk)
+        }
+    }
+    lsize[x] = nl;
+}
+
+// one warp per surviving edge: exact compare() of list owner x and neighbour id
+template <int KIND>
+__global__ void lsh_refine_kernel(const double *regs, const double *cards, uint64_t n, const uint32_t *seg, const uint32_t *lsize,
+                                  Nb *lst, const CmpConsts c, float mult) {
+    const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+    // edges are addressed by arrival slot: slot e belongs to list x if seg[x] <= e < seg[x] + lsize[x]
+    const uint32_t total = seg[n];
+    if (w >= total) return;
+    // find the list that owns slot w (seg is sorted)
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (seg[mid + 1] > w) hi = mid; else lo = mid + 1; }
+    const uint64_t x = lo;
+    if (w - seg[x] >= lsize[x]) return;
+    const uint32_t id = lst[w].id;
+    const double *A = regs + x * c.S, *B = regs + (uint64_t)id * c.S;
+    uint32_t g = 0, l = 0;
+    for (uint32_t r = lane; r < c.S; r += 32) {
+        const double a = A[r], b = B[r];
+        if (KIND == 0) { g += a > b; l += a < b; } else g += __double_as_longlong(a) != __double_as_longlong(b);
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); l += __shfl_xor_sync(0xffffffffu, l, o); }
+    if (lane == 0) lst[w].d = mult * finalize_pair(c, KIND == 0 ? g : c.S - g, l, cards[x], cards[id]);
+}
+
+// one thread per list: sort by (d, id), drop zero similarities, keep top-k plus ties, undo the sign (refine.cpp:30-74)
+__global__ void lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
+    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    Nb *L = lst + seg[x]; uint32_t nl = lsize[x];
+    for (uint32_t i = 1; i < nl; ++i) { const Nb it = L[i]; uint32_t j = i; while (j && nb_less(it, L[j - 1])) { L[j] = L[j - 1]; --j; } L[j] = it; }
+    if (!is_dist) { uint32_t j = 0; while (j < nl && L[j].d != 0.f) ++j; nl = j; }
+    if (topk < nl) { const float bs = L[topk - 1].d; uint32_t j = topk; while (j < nl && !(L[j].d > bs)) ++j; nl = j; }
+    if (!is_dist) for (uint32_t j = 0; j < nl; ++j) L[j].d = -L[j].d;
+    lsize[x] = nl;
+}
+
+__global__ void lsh_csr_kernel(const uint32_t *seg, const uint32_t *lsize, const uint64_t *indptr, uint64_t n, const Nb *lst, uint32_t *idx, float *val) {
+    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const Nb *L = lst + seg[x]; const uint64_t o = indptr[x];
+    for (uint32_t j = 0; j < lsize[x]; ++j) { idx[o + j] = L[j].id; val[o + j] = L[j].d; }
+}
+
+// seg[x] = first arrival slot whose list >= x (lists sorted ascending; 0xFFFFFFFF = unused slots at the end)
+__global__ void lsh_segments_kernel(const uint32_t *alist_sorted, uint64_t na, uint64_t n, uint32_t *seg) {
+    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (x > n) return;
+    uint64_t lo = 0, hi = na;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (alist_sorted[mid] < (uint32_t)x) lo = mid + 1; else hi = mid; }
+    seg[x] = (uint32_t)lo;
+}
+
+} // namespace d2g

@@ -150,6 +150,17 @@ int d2g_cmp_counts(d2g_ctx *ctx, uint32_t sketchsize, int32_t cmp_kind,
                    const double *rows, uint64_t n_rows, const double *cols, uint64_t n_cols,
                    uint32_t *c0_out, uint32_t *c1_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * LSH-assisted top-k neighbour graph (--topk K).  Replaces build_index (src/index_build.cpp:53-165) over
+ * SetSketchIndex (src/ssi.h:290-453, default --nLSH 2), refine_results (src/refine.cpp:6-81) and the CSR
+ * assembly of emit_neighbors (src/emitnn.cpp:12-52).  Output is the reference's sequential (-p1) result
+ * (its multi-threaded output is timing dependent).  regs f64[n][S] (already densified for OPMH), cards f64[n]:
+ * host memory.  indptr_out: caller-allocated u64[n+1]; *idx_out / *val_out are malloc'ed (release with
+ * d2g_free) and hold indptr_out[n] entries: neighbour ids and similarities (or distances), best first.
+ * ---------------------------------------------------------------------------------------------- */
+int d2g_lsh_topk(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards,
+                 int32_t topk, uint64_t *indptr_out, uint32_t **idx_out, float **val_out);
+
 void d2g_free(void *p);
 
 #ifdef __cplusplus

@@ -667,3 +667,127 @@ double d2o_bmh_update(double *regs, uint64_t *ids, uint32_t m, const uint64_t *k
     free(heap.v);
     return tw;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* LSH top-k                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+uint32_t d2o_lsh_key(const double *sig, uint32_t table_type, uint64_t j) { /* ssi.h:320-331,355-378 */
+    if (table_type == 0) return (uint32_t)d2o_wang64(d2bits(sig[j]));
+    uint64_t v0 = d2o_wang64(d2bits(sig[2 * j]));
+    uint64_t v1 = d2o_wang64(d2bits(sig[2 * j + 1]) ^ v0);
+    return (uint32_t)(v0 ^ v1);
+}
+
+typedef struct { uint32_t key, id; } kid_t;
+static int cmp_kid(const void *a, const void *b) {
+    const kid_t *x = (const kid_t *)a, *y = (const kid_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->id < y->id ? -1 : (x->id > y->id);
+}
+typedef struct { kid_t *tab; uint64_t n, S, ntab; } lshidx_t; /* table t occupies tab[t*n, (t+1)*n), sorted by (key,id) */
+static lshidx_t lsh_build(const double *regs, uint64_t n, uint64_t S) {
+    lshidx_t ix; ix.n = n; ix.S = S; ix.ntab = S + S / 2;
+    ix.tab = (kid_t *)malloc(sizeof(kid_t) * ix.ntab * n);
+    for (uint64_t t = 0; t < ix.ntab; ++t) {
+        const uint32_t type = t < S ? 0 : 1; const uint64_t j = t < S ? t : t - S;
+        kid_t *T = ix.tab + t * n;
+        for (uint64_t i = 0; i < n; ++i) { T[i].key = d2o_lsh_key(regs + i * S, type, j); T[i].id = (uint32_t)i; }
+        qsort(T, n, sizeof(kid_t), cmp_kid); /* bucket order = insertion order = ascending id under -p1 */
+    }
+    return ix;
+}
+static uint64_t lsh_query(const lshidx_t *ix, const double *sig, uint64_t maxcand, uint32_t *ids, uint32_t *counts) {
+    uint64_t nc = 0;
+    const uint64_t n = ix->n, S = ix->S;
+    for (int type = 1; type >= 0 && nc < maxcand; --type) { /* most specific table type first, ssi.h:425 */
+        const uint64_t nsubs = type ? S / 2 : S;
+        for (uint64_t j = 0; j < nsubs; ++j) {
+            const uint32_t key = d2o_lsh_key(sig, (uint32_t)type, j);
+            const kid_t *T = ix->tab + (type ? S + j : j) * n;
+            uint64_t lo = 0, hi = n;
+            while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (T[mid].key < key) lo = mid + 1; else hi = mid; }
+            for (uint64_t q = lo; q < n && T[q].key == key; ++q) {
+                const uint32_t id = T[q].id;
+                uint64_t f = 0; for (; f < nc; ++f) if (ids[f] == id) break;
+                if (f < nc) { ++counts[f]; continue; }
+                ids[nc] = id; counts[nc] = 1; ++nc;
+                if (nc == maxcand) return nc; /* early stop the moment maxcand distinct ids are seen, ssi.h:437-440 */
+            }
+        }
+    }
+    return nc;
+}
+uint64_t d2o_lsh_query(const double *regs, uint64_t n, uint64_t S, uint64_t query, uint64_t maxcand, uint32_t *ids, uint32_t *counts) {
+    lshidx_t ix = lsh_build(regs, n, S);
+    uint64_t r = lsh_query(&ix, regs + query * S, maxcand, ids, counts);
+    free(ix.tab);
+    return r;
+}
+
+/* neighbour list = std::priority_queue<pair<float,uint32>> (max-heap) + dedup set; kept as a sorted array */
+typedef struct { float d; uint32_t id; } nb_t;
+typedef struct { nb_t *v; uint32_t n, cap; uint32_t *set; uint32_t nset, capset; } nlist_t;
+static int nb_less(nb_t a, nb_t b) { return a.d < b.d || (a.d == b.d && a.id < b.id); }
+static void nl_push(nlist_t *l, nb_t x) {
+    if (l->n == l->cap) { l->cap = l->cap ? l->cap * 2 : 16; l->v = (nb_t *)realloc(l->v, l->cap * sizeof(nb_t)); }
+    uint32_t i = l->n++;
+    while (i && nb_less(x, l->v[i - 1])) { l->v[i] = l->v[i - 1]; --i; }
+    l->v[i] = x;
+}
+static int nl_inset(const nlist_t *l, uint32_t id) { for (uint32_t i = 0; i < l->nset; ++i) if (l->set[i] == id) return 1; return 0; }
+static void nl_setadd(nlist_t *l, uint32_t id) {
+    if (l->nset == l->capset) { l->capset = l->capset ? l->capset * 2 : 16; l->set = (uint32_t *)realloc(l->set, l->capset * 4); }
+    l->set[l->nset++] = id;
+}
+static void nl_setdel(nlist_t *l, uint32_t id) { for (uint32_t i = 0; i < l->nset; ++i) if (l->set[i] == id) { l->set[i] = l->set[--l->nset]; return; } }
+static void nl_update(nlist_t *l, nb_t item, uint64_t k) { /* index_build.cpp:20-44 with topk > 0 */
+    if (nl_inset(l, item.id)) return;
+    if (l->n < k) { nl_setadd(l, item.id); nl_push(l, item); return; }
+    const nb_t top = l->v[l->n - 1];
+    if (item.d <= top.d) {
+        if (top.d != item.d) { nl_setdel(l, top.id); --l->n; }
+        nl_push(l, item); /* note: the id is NOT added to the dedup set on this branch */
+    }
+}
+static int cmp_nb(const void *a, const void *b) { nb_t x = *(const nb_t *)a, y = *(const nb_t *)b; return nb_less(x, y) ? -1 : nb_less(y, x); }
+
+uint64_t d2o_topk(const double *regs, const double *cards, uint64_t n, uint64_t S, int topk, int measure, int k, int cmp_kind,
+                  uint64_t *indptr, uint32_t **idx, float **val) {
+    lshidx_t ix = lsh_build(regs, n, S);
+    uint64_t ntoquery = (uint64_t)((float)topk * 3.5f); /* index_build.cpp:57-60 (LSHDistType = float) */
+    if (ntoquery > n - 1) ntoquery = n - 1;
+    nlist_t *L = (nlist_t *)calloc(n, sizeof(nlist_t));
+    uint32_t *ids = (uint32_t *)malloc(4 * (ntoquery + 1)), *cnt = (uint32_t *)malloc(4 * (ntoquery + 1));
+    for (uint64_t q = 0; q < n; ++q) {
+        const uint64_t nc = ntoquery ? lsh_query(&ix, regs + q * S, ntoquery, ids, cnt) : 0;
+        for (uint64_t j = 0; j < nc; ++j) {
+            const uint32_t oid = ids[j];
+            if (oid == q) continue;
+            const float cd = -(float)cnt[j];
+            nl_update(&L[oid], (nb_t){cd, (uint32_t)q}, ntoquery);
+            nl_update(&L[q], (nb_t){cd, oid}, ntoquery);
+        }
+    }
+    /* cmp_main.h:44-49: everything except union/intersection/similarity/containment counts as a distance
+     * (including symmetric containment -- a quirk of the reference that the output order depends on) */
+    const int is_dist = !(measure == D2O_UNION_SIZE || measure == D2O_INTERSECTION || measure == D2O_SIMILARITY || measure == D2O_CONTAINMENT);
+    const float mult = is_dist ? 1.f : -1.f;
+    uint64_t nnz = 0;
+    for (uint64_t i = 0; i < n; ++i) { /* refine.cpp:20-76, num_neighbors_ > 0 branch */
+        nlist_t *l = &L[i];
+        for (uint32_t j = 0; j < l->n; ++j)
+            l->v[j].d = mult * d2o_compare(regs + i * S, regs + (uint64_t)l->v[j].id * S, S, cards[i], cards[l->v[j].id], measure, k, cmp_kind);
+        qsort(l->v, l->n, sizeof(nb_t), cmp_nb);
+        if (!is_dist) { uint32_t j = 0; while (j < l->n && l->v[j].d != 0.f) ++j; l->n = j; }
+        if ((uint32_t)topk < l->n) { const float bs = l->v[topk - 1].d; uint32_t j = (uint32_t)topk; while (j < l->n && !(l->v[j].d > bs)) ++j; l->n = j; }
+        if (!is_dist) for (uint32_t j = 0; j < l->n; ++j) l->v[j].d = -l->v[j].d;
+        indptr[i] = nnz; nnz += l->n;
+    }
+    indptr[n] = nnz;
+    *idx = (uint32_t *)malloc(4 * (nnz + 1)); *val = (float *)malloc(4 * (nnz + 1));
+    for (uint64_t i = 0, o = 0; i < n; ++i) for (uint32_t j = 0; j < L[i].n; ++j, ++o) { (*idx)[o] = L[i].v[j].id; (*val)[o] = L[i].v[j].d; }
+    for (uint64_t i = 0; i < n; ++i) { free(L[i].v); free(L[i].set); }
+    free(L); free(ids); free(cnt); free(ix.tab);
+    return nnz;
+}
+void d2o_free(void *p) { free(p); }

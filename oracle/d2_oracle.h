@@ -101,3 +101,20 @@ double d2o_bmh_update(double *regs, uint64_t *ids, uint32_t m, const uint64_t *k
 #ifdef __cplusplus
 }
 #endif
+
+/* ---- LSH top-k nearest-neighbour graph: src/ssi.h:290-453, src/index_build.cpp:20-165, src/refine.cpp:6-81,
+ * src/emitnn.cpp:12-52, table geometry src/cmp_core.cpp:757-772.  Sequential (-p1) semantics. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* LSH keys: table type 0 = one register, type 1 = two registers (default --nLSH 2); truncated to 32 bits. */
+uint32_t d2o_lsh_key(const double *sig, uint32_t table_type, uint64_t j);
+/* candidate scan for one query; ids/counts must hold maxcand entries; returns the number of candidates. */
+uint64_t d2o_lsh_query(const double *regs, uint64_t n, uint64_t S, uint64_t query, uint64_t maxcand, uint32_t *ids, uint32_t *counts);
+/* whole pipeline -> CSR (indptr[n+1], idx/val malloc'ed; free with d2o_free). Returns nnz. */
+uint64_t d2o_topk(const double *regs, const double *cards, uint64_t n, uint64_t S, int topk, int measure, int k, int cmp_kind,
+                  uint64_t *indptr, uint32_t **idx, float **val);
+void d2o_free(void *p);
+#ifdef __cplusplus
+}
+#endif

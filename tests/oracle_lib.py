@@ -64,6 +64,10 @@ def lib():
     for nm in ("d2o_pmh_update", "d2o_bmh_update"):
         getattr(L, nm).restype = C.c_double
         getattr(L, nm).argtypes = [f64p, C.c_void_p, C.c_uint32, u64p, f64p, C.c_uint64, C.c_double]
+    L.d2o_topk.restype = C.c_uint64
+    L.d2o_topk.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, u64p,
+                           C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
+    L.d2o_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -179,3 +183,26 @@ def allpairs(regs: np.ndarray, cards: np.ndarray, kind: str = "symmetric", measu
     else:
         raise ValueError(kind)
     return out
+
+
+def topk(regs, cards, K, measure="similarity", k=31, cmp_kind=0):
+    """Reference -p1 top-k pipeline -> CSR (indptr, indices, data)."""
+    L = lib()
+    regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
+    n, S = regs.shape
+    indptr = np.zeros(n + 1, dtype=np.uint64)
+    pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()
+    nnz = L.d2o_topk(regs, cards, n, S, K, MEASURES[measure], k, cmp_kind, indptr, C.byref(pi), C.byref(pv))
+    idx = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
+    val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()
+    L.d2o_free(pi); L.d2o_free(pv)
+    return indptr, idx, val
+
+
+def read_csr(path):
+    raw = open(path, "rb").read()
+    n, nnz = (int(x) for x in np.frombuffer(raw, np.uint64, 2))
+    ip = np.frombuffer(raw, np.uint64, n + 1, 16)
+    ix = np.frombuffer(raw, np.uint32, nnz, 16 + 8 * (n + 1))
+    dv = np.frombuffer(raw, np.float32, nnz, 16 + 8 * (n + 1) + 4 * nnz)
+    return ip, ix, dv

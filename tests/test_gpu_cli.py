@@ -104,6 +104,17 @@ def test_multiset_and_prob_cache_files(golden_inputs, tmp_path):
         assert d[0] == z["cards"][0] and np.array_equal(d[1:], z["sigs"][0])
 
 
+def test_cmp_topk_csr_file(tmp_path):
+    from dashing2_b200 import synth
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    stk = str(tmp_path / "sk600.ss")
+    synth.write_stacked(stk, z["regs"], z["cards"], names=[f"s{i}" for i in range(600)])
+    for K in (5, 32):
+        out = str(tmp_path / f"top{K}.csr")
+        run(["cmp", "--presketched", "--binary-output", "--topk", str(K), "--cmpout", out, stk])
+        assert open(out, "rb").read() == open(expected(f"topk{K}_sk600.csr"), "rb").read()
+
+
 def test_unsupported_options_fail_loudly(golden_inputs):
     names, paths = golden_inputs
     for argv in (["sketch", "-k31", "--countsketch-size", "1000", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0]],

@@ -232,3 +232,23 @@ def test_compare_full_size_properties():
     iu = np.triu_indices(n, 1)
     assert np.array_equal(sym, full[iu])
     assert np.array_equal(full, full.T) and np.all(np.diag(full) == 1.0)
+
+
+@pytest.mark.parametrize("K", [5, 32])
+def test_topk_matches_reference_golden(K):
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    ip, ix, dv = O.read_csr(expected(f"topk{K}_sk600.csr"))
+    gp, gi, gv = ctx().lsh_topk(z["regs"], z["cards"], K, "similarity", k=32)
+    assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,S,K,measure,cmp_kind", [(3000, 128, 10, "similarity", 0), (1500, 256, 32, "containment", 0),
+                                                     (2000, 64, 7, "poisson_llr", 0), (1200, 128, 16, "similarity", 1),
+                                                     (700, 1024, 32, "symmetric_containment", 0)])
+def test_topk_matches_oracle_seeded(n, S, K, measure, cmp_kind):
+    from dashing2_b200 import synth
+    regs, cards = synth.synthetic_sketches(n, S, seed=n + S, n_families=max(2, n // 40), p_lo=0.02, p_hi=0.7)
+    cards = cards * (1 + np.arange(n) % 3)
+    ep, ei, ev = O.topk(regs, cards, K, measure, k=31, cmp_kind=cmp_kind)
+    gp, gi, gv = ctx().lsh_topk(regs, cards, K, measure, k=31, cmp_kind=cmp_kind)
+    assert np.array_equal(gp, ep) and np.array_equal(gi, ei) and np.array_equal(gv.view(np.uint32), ev.view(np.uint32))

@@ -102,3 +102,12 @@ def test_wang_inverse_roundtrip():
     L = O.lib()
     for x in (0, 1, 133348, 0xdeadbeefcafebabe, 2**64 - 1):
         assert L.d2o_wang64_inv(L.d2o_wang64(x)) == x
+
+
+@pytest.mark.parametrize("K", [5, 32])
+def test_topk_csr_matches_reference(K):
+    """LSH candidate scan + bounded lists + refinement == `dashing2 cmp --presketched --topk K -p1` CSR."""
+    z = np.load(os.path.join(os.path.dirname(expected("x")), "..", "inputs", "sk600x64.npz"))
+    ip, ix, dv = O.read_csr(expected(f"topk{K}_sk600.csr"))
+    gp, gi, gv = O.topk(z["regs"], z["cards"], K, "similarity", k=32)
+    assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
