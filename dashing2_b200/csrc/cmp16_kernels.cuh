@@ -1,0 +1,270 @@
+// cmp16_kernels.cuh -- K7b: all-pairs register comparison on 16-bit order codes.
+//
+// compare() (/root/reference/src/cmp_core.cpp:458-517) only needs, per pair of sketches, HOW MANY of
+// the S register positions hold a larger / smaller / different value (count_gtlt<double> and count_eq,
+// bonsai/hll/include/sketch/count_eq.h:412-445,40-56).  Those counts are invariant under any strictly
+// increasing map applied to one register position of all sketches at once.  So, per comparison job,
+// every register position (column of the n x S register matrix) is replaced by the DENSE RANK of the
+// value among the sketches of the job, and the rank is stored as the rank-th smallest finite IEEE
+// binary16 value (63 487 distinct finite halfs: -65504 .. -2^-24, +0 .. +65504).  Two registers
+// compare exactly like their codes, and the SM compares two codes per instruction (HSET2 on a packed
+// half2).  Per two register pairs the inner loop issues 2 HSET2 (mask output) + 1 IADD3 (two masks
+// accumulated at once) instead of 4 DSETP + 4 IADD of the f64 kernel, on a quarter of the shared-memory
+// bytes.  The counts (and therefore the float32 results, finalised by the same finalize_pair) are
+// bit-identical to the f64 kernel's; jobs the codes cannot express (NaN registers, more than 63 487
+// sketches per block pair) run on cmp_tile_kernel.
+//
+// Layout in HBM.  codes: uint32 words [code block][k-pair][64]; code block b holds sketches
+// 64b..64b+63 of the job, word (b, kp, r) = code(register 2kp) | code(register 2kp+1) << 16 of sketch
+// 64b + r.  A chunk of C16_KC k-pairs of one block is one contiguous 8 KiB run, fetched with a single
+// bulk asynchronous copy (cp.async.bulk -> UBLKCP) into a C16_STAGES-deep shared-memory ring guarded by
+// mbarriers.  A CTA owns 128 x 64 pairs (two row blocks x one column block); a thread owns 8 x 4 pairs.
+#pragma once
+#include <cuda_fp16.h>
+#include "cmp_kernels.cuh"
+
+namespace d2g {
+
+constexpr int C16_BLK = 64;          // sketches per code block
+constexpr int C16_KC = 32;           // k-pairs per chunk (64 registers)
+constexpr int C16_STAGES = 4;
+constexpr int C16_THREADS = 256;
+constexpr int C16_TM = 128, C16_TN = 64;
+constexpr uint32_t C16_MAXRANK = 63487;   // distinct finite binary16 values (one zero)
+constexpr int C16_CHUNK_WORDS = C16_KC * C16_BLK;                 // 2048 words = 8 KiB
+constexpr size_t C16_SMEM = (size_t)C16_STAGES * 3 * C16_CHUNK_WORDS * 4 + C16_STAGES * 8 + 64;
+
+// rank (0-based, < C16_MAXRANK) -> bit pattern of the rank-th smallest finite half
+__host__ __device__ __forceinline__ uint16_t rank_to_half(uint32_t r) {
+    return r < 31743u ? (uint16_t)(0xfbffu - r) : (uint16_t)(r - 31743u);
+}
+
+struct C16Args {
+    const uint32_t *codes;   // [nblocks][KP][64]
+    uint32_t KP;             // k-pairs per sketch, multiple of C16_KC (registers >= S hold code 0 everywhere)
+    uint32_t a_blk0, b_blk0; // first code block of the row / column operand
+    uint32_t n_a, n_b;       // row / column sketches of this job
+    uint64_t gi0, gj0;       // global sketch index of local row 0 / local column 0
+    uint32_t tiles_j;
+    const int *use_flag;     // device flag: run only when *use_flag == want (nullptr = always)
+    int want;
+    CmpArgs o;               // output mapping + finalisation constants (regs unused)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t hgt2m(uint32_t a, uint32_t b) { uint32_t d; asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hlt2m(uint32_t a, uint32_t b) { uint32_t d; asm("set.lt.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hne2m(uint32_t a, uint32_t b) { uint32_t d; asm("set.ne.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+
+// Sum (mod 2^32) of masks whose 16-bit lanes are 0x0000 / 0xffff -> number of set lanes.
+// sum = (L - H) * 2^16 - L with L, H the low / high lane counts (each < 2^16).
+__device__ __forceinline__ uint32_t mask_sum_count(uint32_t s) {
+    const uint32_t L = (0u - s) & 0xffffu;
+    const uint32_t H = (L - ((s + L) >> 16)) & 0xffffu;
+    return L + H;
+}
+
+// MODE 0: count (a > b, a < b); MODE 1: count (a != b)
+template <int MODE>
+__global__ void __launch_bounds__(C16_THREADS, 2)
+cmp16_tile_kernel(const C16Args a) {
+    extern __shared__ __align__(128) unsigned char c16_smem[];
+    if (a.use_flag && *a.use_flag != a.want) return;
+    uint32_t *sA = reinterpret_cast<uint32_t *>(c16_smem);                      // [STAGES][2][KC][64]
+    uint32_t *sB = sA + C16_STAGES * 2 * C16_CHUNK_WORDS;                        // [STAGES][KC][64]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sB + C16_STAGES * C16_CHUNK_WORDS);
+    const uint32_t tj = blockIdx.x % a.tiles_j, ti = blockIdx.x / a.tiles_j;
+    const uint32_t li0 = ti * C16_TM, lj0 = tj * C16_TN;                         // local first row / column
+    const uint64_t i0 = a.gi0 + li0, j0 = a.gj0 + lj0;
+    if (a.o.shape == 0 && j0 + C16_TN <= i0 + 1) return;                          // tile entirely on/below the diagonal
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const uint32_t nchunks = a.KP / C16_KC;
+    const uint32_t *gA = a.codes + (uint64_t)(a.a_blk0 + 2 * ti) * a.KP * C16_BLK;
+    const uint32_t *gB = a.codes + (uint64_t)(a.b_blk0 + tj) * a.KP * C16_BLK;
+    const uint64_t blk_stride = (uint64_t)a.KP * C16_BLK;                        // words between code blocks
+
+    if (tid == 0) {
+        #pragma unroll
+        for (int s = 0; s < C16_STAGES; ++s) mbar_init(bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint32_t st, uint32_t chunk) {
+        mbar_expect_tx(bar + st, 3 * C16_CHUNK_WORDS * 4);
+        const uint64_t off = (uint64_t)chunk * C16_CHUNK_WORDS;
+        bulk_g2s(sA + (st * 2 + 0) * C16_CHUNK_WORDS, gA + off, C16_CHUNK_WORDS * 4, bar + st);
+        bulk_g2s(sA + (st * 2 + 1) * C16_CHUNK_WORDS, gA + blk_stride + off, C16_CHUNK_WORDS * 4, bar + st);
+        bulk_g2s(sB + st * C16_CHUNK_WORDS, gB + off, C16_CHUNK_WORDS * 4, bar + st);
+    };
+    if (tid == 0)
+        for (uint32_t s = 0; s < (uint32_t)C16_STAGES && s < nchunks; ++s) issue(s, s);
+
+    uint32_t acc0[8][4], acc1[8][4];
+    #pragma unroll
+    for (int u = 0; u < 8; ++u)
+        #pragma unroll
+        for (int v = 0; v < 4; ++v) { acc0[u][v] = 0; acc1[u][v] = 0; }
+
+    // thread's operands inside a stage: rows ty*8..+7 -> block ty>>3, offset (ty&7)*8; columns tx*4..+3
+    const uint32_t aoff = (ty >> 3) * C16_CHUNK_WORDS + (ty & 7) * 8;
+    const uint32_t boff = tx * 4;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t st = c % C16_STAGES, ph = (c / C16_STAGES) & 1;
+        mbar_wait(bar + st, ph);
+        const uint32_t *pa = sA + st * 2 * C16_CHUNK_WORDS + aoff;
+        const uint32_t *pb = sB + st * C16_CHUNK_WORDS + boff;
+        #pragma unroll 2
+        for (int kp = 0; kp < C16_KC; kp += 2) {
+            uint32_t av[2][8], bv[2][4];
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 x0 = *reinterpret_cast<const uint4 *>(pa + (kp + h) * C16_BLK);
+                const uint4 x1 = *reinterpret_cast<const uint4 *>(pa + (kp + h) * C16_BLK + 4);
+                const uint4 y = *reinterpret_cast<const uint4 *>(pb + (kp + h) * C16_BLK);
+                av[h][0] = x0.x; av[h][1] = x0.y; av[h][2] = x0.z; av[h][3] = x0.w;
+                av[h][4] = x1.x; av[h][5] = x1.y; av[h][6] = x1.z; av[h][7] = x1.w;
+                bv[h][0] = y.x; bv[h][1] = y.y; bv[h][2] = y.z; bv[h][3] = y.w;
+            }
+            #pragma unroll
+            for (int u = 0; u < 8; ++u)
+                #pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (MODE == 0) {
+                        acc0[u][v] += hgt2m(av[0][u], bv[0][v]) + hgt2m(av[1][u], bv[1][v]);
+                        acc1[u][v] += hlt2m(av[0][u], bv[0][v]) + hlt2m(av[1][u], bv[1][v]);
+                    } else {
+                        acc0[u][v] += hne2m(av[0][u], bv[0][v]) + hne2m(av[1][u], bv[1][v]);
+                    }
+                }
+        }
+        __syncthreads();                                   // every thread is done reading stage st
+        if (tid == 0 && c + C16_STAGES < nchunks) issue(st, c + C16_STAGES);
+    }
+
+    const uint32_t S = a.o.c.S;
+    #pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const uint32_t li = li0 + ty * 8 + u;
+        if (li >= a.n_a) continue;
+        const uint64_t i = a.gi0 + li;
+        if (i < a.o.row0 || i >= a.o.row1) continue;      // operand blocks may start before / end after the rows of this launch
+        const double lhc = a.o.cards ? __ldg(a.o.cards + i) : 0.;
+        #pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const uint32_t lj = lj0 + tx * 4 + v;
+            if (lj >= a.n_b) continue;
+            const uint64_t j = a.gj0 + lj;
+            if (j < a.o.col0 || j >= a.o.col1) continue;
+            if (a.o.shape == 0 && j <= i) continue;
+            const uint32_t n0 = mask_sum_count(acc0[u][v]);
+            const uint32_t c0 = MODE == 0 ? n0 : S - n0;
+            const uint32_t c1 = MODE == 0 ? mask_sum_count(acc1[u][v]) : 0;
+            const uint64_t oi = out_index(a.o, i, j);
+            if (a.o.c0_out) { a.o.c0_out[oi] = c0; if (a.o.c1_out) a.o.c1_out[oi] = c1; }
+            if (a.o.out) a.o.out[oi] = finalize_pair(a.o.c, c0, c1, lhc, a.o.cards ? __ldg(a.o.cards + j) : 0.);
+        }
+    }
+}
+
+// ---- building the codes ---------------------------------------------------------------------------
+// (1) keys: transposes f64 registers of the job's sketches into column-major order-preserving u64 keys.
+//     Job sketch u (0 <= u < U) is global sketch (u < nA ? gA0 + u : gB0 + u - nA).
+//     GTLT: key = dkey(value) with -0 folded onto +0 (they compare equal); a NaN raises *nan_flag (NaN is
+//     unordered: neither >, < nor expressible as a rank).  EQ: key = the raw bit pattern (cmp_kernels.cuh
+//     counts bitwise-different registers).
+struct C16Job {
+    const double *regs; uint32_t S;
+    uint64_t gA0, gB0; uint32_t nA, nB;      // two ranges of global sketches; nB may be 0
+    uint32_t posB0;                          // position (in sketches, multiple of 64) of the first column sketch in code space
+    uint32_t KP;
+};
+__device__ __forceinline__ uint64_t job_sketch(const C16Job &j, uint32_t u) { return u < j.nA ? j.gA0 + u : j.gB0 + (u - j.nA); }
+__device__ __forceinline__ uint32_t job_pos(const C16Job &j, uint32_t u) { return u < j.nA ? u : j.posB0 + (u - j.nA); }
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+c16_keys_kernel(const C16Job j, uint64_t *keysT, uint32_t *idxT, int *nan_flag) {
+    __shared__ uint64_t t[32][33];
+    const uint32_t U = j.nA + j.nB;
+    const uint32_t u0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;   // 32 x 8
+    bool nan = false;
+    #pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t u = u0 + ly + 8 * r, s = s0 + lx;
+        uint64_t key = 0;
+        if (u < U && s < j.S) {
+            const double d = __ldg(j.regs + job_sketch(j, u) * j.S + s);
+            if (KIND == 0) { nan |= d != d; key = dkey(d == 0. ? 0. : d); }
+            else key = (uint64_t)__double_as_longlong(d);
+        }
+        t[ly + 8 * r][lx] = key;
+    }
+    if (nan) *nan_flag = 1;
+    __syncthreads();
+    #pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t s = s0 + ly + 8 * r, u = u0 + lx;
+        if (u < U && s < j.S) { keysT[(uint64_t)s * U + u] = t[lx][ly + 8 * r]; idxT[(uint64_t)s * U + u] = u; }
+    }
+}
+
+// (2) after the per-column sort: dense ranks -> half codes, scattered into the blocked code layout.
+//     One CTA per register position; codes16 is the uint16 view of the code words.
+__global__ void __launch_bounds__(256)
+c16_rank_kernel(const C16Job j, const uint64_t *keys_sorted, const uint32_t *idx_sorted, uint16_t *codes16, int *overflow_flag) {
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t carry_s;
+    const uint32_t U = j.nA + j.nB, s = blockIdx.x;
+    const uint64_t *k = keys_sorted + (uint64_t)s * U;
+    const uint32_t *ix = idx_sorted + (uint64_t)s * U;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < U; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t f = 0;
+        if (i < U && i > 0) f = k[i] != k[i - 1];
+        uint32_t x = f;                                   // inclusive scan of the "new value" flags
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        uint32_t pre = carry_s;
+        for (int q = 0; q < w; ++q) pre += wsum[q];
+        const uint32_t rank = pre + x;
+        if (i < U) {
+            if (rank >= C16_MAXRANK) *overflow_flag = 1;
+            const uint32_t pos = job_pos(j, ix[i]);
+            const uint64_t word = ((uint64_t)(pos / C16_BLK) * j.KP + (s >> 1)) * C16_BLK + (pos % C16_BLK);
+            codes16[word * 2 + (s & 1)] = rank_to_half(rank);
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = rank;
+        __syncthreads();
+    }
+}
+
+} // namespace d2g

@@ -38,13 +38,17 @@ struct CmpArgs {
     const double *regs;    // [n][S]
     const double *cards;   // [n]
     uint64_t n;            // total sketches
-    uint64_t row0, row1;   // output rows [row0, row1)
-    uint64_t col_base;     // first column sketch index (PANEL: n - nq, else 0)
-    uint64_t ncols;        // number of column sketches
+    uint64_t row0, row1;   // rows (global sketch ids) this launch computes
+    uint64_t col0, col1;   // columns (global sketch ids) this launch computes
+    uint64_t out_row0;     // first row held by the packed output buffer
+    uint64_t col_base;     // output geometry: first column sketch index (PANEL: n - nq, else 0)
+    uint64_t ncols;        // output geometry: number of column sketches
     int shape;             // 0 symmetric, 1 asymmetric, 2 panel
-    float *out;            // packed output for rows [row0,row1)
+    float *out;            // packed output for rows >= out_row0
     uint32_t *c0_out, *c1_out; // optional raw counts (row-major rows x cols), out may be null then
     uint64_t tiles_j;      // number of column tiles
+    const int *use_flag;   // device flag: the launch only runs when *use_flag == want (nullptr = always)
+    int want;
     CmpConsts c;
 };
 
@@ -94,13 +98,13 @@ __device__ __forceinline__ float finalize_pair(const CmpConsts &c, uint32_t c0, 
     return to_float(ret);
 }
 
-// position of pair (i, j) in the packed output of rows >= row0
+// position of pair (i, j) in the packed output of rows >= out_row0
 __device__ __forceinline__ uint64_t out_index(const CmpArgs &a, uint64_t i, uint64_t j) {
     if (a.shape == 0) { // condensed upper triangle: row i holds j = i+1..n-1
-        const uint64_t base = i * a.n - i * (i + 1) / 2 - (a.row0 * a.n - a.row0 * (a.row0 + 1) / 2);
+        const uint64_t base = i * a.n - i * (i + 1) / 2 - (a.out_row0 * a.n - a.out_row0 * (a.out_row0 + 1) / 2);
         return base + (j - i - 1);
     }
-    return (i - a.row0) * a.ncols + (j - a.col_base);
+    return (i - a.out_row0) * a.ncols + (j - a.col_base);
 }
 
 template <int KIND>
@@ -110,8 +114,9 @@ cmp_tile_kernel(const CmpArgs a) {
     __shared__ double sB[CMP_T * CMP_LD];
     const uint64_t tj = blockIdx.x % a.tiles_j, ti = blockIdx.x / a.tiles_j;
     const uint64_t i0 = a.row0 + ti * CMP_T;          // first row sketch of the tile
-    const uint64_t j0 = a.col_base + tj * CMP_T;      // first column sketch of the tile
-    const uint64_t jend = a.col_base + a.ncols;
+    const uint64_t j0 = a.col0 + tj * CMP_T;          // first column sketch of the tile
+    const uint64_t jend = a.col1;
+    if (a.use_flag && *a.use_flag != a.want) return;
     if (a.shape == 0 && j0 + CMP_T <= i0 + 1) return; // tile entirely on/below the diagonal
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const uint32_t S = a.c.S;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #define D2G_HD __host__ __device__ __forceinline__
 
@@ -100,6 +101,25 @@ __device__ __forceinline__ uint32_t fastmod32(uint32_t a, const FastMod32 &f) {
     if (f.pow2mask) return a & f.pow2mask;
     const uint64_t low = f.M * a;
     return (uint32_t)__umul64hi(low, f.d);
+}
+
+// order-preserving u64 key of a double (and back)
+__host__ __device__ __forceinline__ uint64_t dkey(double d) {   // order-preserving u64 key of a double
+    uint64_t b;
+#if defined(__CUDA_ARCH__)
+    b = (uint64_t)__double_as_longlong(d);
+#else
+    memcpy(&b, &d, 8);
+#endif
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ double dunkey(uint64_t k) {
+    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d; memcpy(&d, &b, 8); return d;
+#endif
 }
 
 } // namespace d2g

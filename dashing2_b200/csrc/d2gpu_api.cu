@@ -19,6 +19,7 @@
 
 #include "../../include/d2gpu.h"
 #include "cmp_kernels.cuh"
+#include "cmp16_kernels.cuh"
 #include "sketch_kernels.cuh"
 #include "fss_kernels.cuh"
 #include "weighted_kernels.cuh"
@@ -76,6 +77,8 @@ struct d2g_ctx {
     DevBuf seq, recoff, recent, regs, sig, card, ids, aux, aux2;   // sketch scratch
     DevBuf wbuf, wtmp, lbuf;                                              // counting scratch (BagMinHash / ProbMinHash)
     DevBuf cregs, ccards, cout, clut, ctmp, cktmp;                 // compare scratch
+    DevBuf c16buf, c16codes;                                       // order-code compare scratch (keys, sort buffers, codes)
+    struct { bool valid = false; const double *regs = nullptr; uint64_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0; uint32_t S = 0; int kind = 0; } c16cache; // codes built earlier in the same API call
     PinBuf pin[2];
     cudaEvent_t ev[2] = {nullptr, nullptr};
     uint32_t lut_S = 0; int lut_k = -1;
@@ -624,23 +627,149 @@ int make_consts(d2g_ctx *c, const d2g_cmp_params *p, d2g::CmpConsts *k) {
     return D2G_OK;
 }
 
-int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, const double *regs_d, const double *cards_d,
-               uint64_t r0, uint64_t r1, float *out_d, uint32_t *c0_d, uint32_t *c1_d) {
-    if (r1 <= r0) return D2G_OK;
-    d2g::CmpArgs a;
-    a.regs = regs_d; a.cards = cards_d; a.n = p->n; a.row0 = r0; a.row1 = r1;
-    a.col_base = p->shape == D2G_PANEL ? p->n - p->nq : 0;
-    a.ncols = n_cols(p); a.shape = p->shape; a.out = out_d; a.c0_out = c0_d; a.c1_out = c1_d; a.c = k;
-    if (a.ncols == 0) return D2G_OK;
+// f64 tile kernel over rows [r0,r1) x columns [c0,c1) (global sketch ids); `base` carries the output mapping.
+int launch_cmp_f64(d2g_ctx *c, const d2g_cmp_params *p, d2g::CmpArgs a, uint64_t r0, uint64_t r1, uint64_t c0, uint64_t c1,
+                   const int *use_flag, int want) {
+    if (r1 <= r0 || c1 <= c0) return D2G_OK;
+    a.row0 = r0; a.row1 = r1; a.col0 = c0; a.col1 = c1; a.use_flag = use_flag; a.want = want;
     const uint64_t tiles_i = (r1 - r0 + d2g::CMP_T - 1) / d2g::CMP_T;
-    a.tiles_j = (a.ncols + d2g::CMP_T - 1) / d2g::CMP_T;
+    a.tiles_j = (c1 - c0 + d2g::CMP_T - 1) / d2g::CMP_T;
     const uint64_t grid = tiles_i * a.tiles_j;
     if (grid > 0x7fffffffULL) return fail(D2G_EINVAL, "row block too large for one launch");
-    KernelTimer kt(c, D2G_T_CMP);
+    KernelTimer kt(c, use_flag ? D2G_T_CMP_PREP : D2G_T_CMP);
     if (p->cmp_kind == D2G_CMP_GTLT) d2g::cmp_tile_kernel<0><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
     else d2g::cmp_tile_kernel<1><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
     c->launches++;
     CU(cudaGetLastError());
+    return D2G_OK;
+}
+
+__global__ void fill_offsets_kernel(int64_t *offs, uint32_t nseg, uint64_t stride) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nseg) offs[i] = (int64_t)((uint64_t)i * stride);
+}
+
+// One comparison job on 16-bit order codes (cmp16_kernels.cuh): the sketches [lo1,hi1) (and [lo2,hi2) when
+// hi2 > lo2) are ranked per register position, coded, and rows [r0,r1) x columns [c0,c1) are compared.
+// [r0,r1) must lie inside range 1; [c0,c1) inside range 2 when it exists, else inside range 1.
+int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base, uint64_t lo1, uint64_t hi1, uint64_t lo2, uint64_t hi2,
+                  uint64_t r0, uint64_t r1, uint64_t c0, uint64_t c1) {
+    using namespace d2g;
+    if (r1 <= r0 || c1 <= c0) return D2G_OK;
+    const uint32_t S = p->sketchsize;
+    const bool two = hi2 > lo2;
+    C16Job j;
+    j.regs = base.regs; j.S = S; j.gA0 = lo1; j.nA = (uint32_t)(hi1 - lo1); j.gB0 = two ? lo2 : 0; j.nB = two ? (uint32_t)(hi2 - lo2) : 0;
+    j.posB0 = (j.nA + C16_BLK - 1) / C16_BLK * C16_BLK;
+    j.KP = ((S + 1) / 2 + C16_KC - 1) / C16_KC * C16_KC;
+    const uint64_t U = (uint64_t)j.nA + j.nB, items = U * S;
+    const uint64_t nblocks = (uint64_t)j.posB0 / C16_BLK + (j.nB + C16_BLK - 1) / C16_BLK + 2;   // +2: a row tile reads two blocks
+    const uint64_t code_bytes = nblocks * j.KP * C16_BLK * 4;
+    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
+    uint64_t off = 0;
+    const uint64_t o_kA = off; off += al(items * 8); const uint64_t o_kB = off; off += al(items * 8);
+    const uint64_t o_iA = off; off += al(items * 4); const uint64_t o_iB = off; off += al(items * 4);
+    const uint64_t o_offs = off; off += al(((uint64_t)S + 1) * 8);
+    const uint64_t o_flag = off; off += 256;
+    if (int rc = c->c16buf.reserve(off)) return rc;
+    if (int rc = c->c16codes.reserve(code_bytes)) return rc;
+    unsigned char *B = c->c16buf.as<unsigned char>();
+    uint64_t *kA = (uint64_t *)(B + o_kA), *kB = (uint64_t *)(B + o_kB);
+    uint32_t *iA = (uint32_t *)(B + o_iA), *iB = (uint32_t *)(B + o_iB);
+    int64_t *offs = (int64_t *)(B + o_offs);
+    int *flag = (int *)(B + o_flag);
+    cudaStream_t st = c->stream;
+    auto &cc = c->c16cache;
+    const bool cached = cc.valid && cc.regs == base.regs && cc.lo1 == lo1 && cc.hi1 == hi1 && cc.lo2 == lo2 && cc.hi2 == hi2 && cc.S == S && cc.kind == p->cmp_kind;
+    if (!cached) {
+        KernelTimer kt(c, D2G_T_CMP_PREP);
+        cc.valid = true; cc.regs = base.regs; cc.lo1 = lo1; cc.hi1 = hi1; cc.lo2 = lo2; cc.hi2 = hi2; cc.S = S; cc.kind = p->cmp_kind;
+        CU(cudaMemsetAsync(flag, 0, 4, st));
+        CU(cudaMemsetAsync(c->c16codes.p, 0, code_bytes, st));
+        fill_offsets_kernel<<<(S + 1 + 255) / 256, 256, 0, st>>>(offs, S, U);
+        const dim3 gk((unsigned)((U + 31) / 32), (S + 31) / 32);
+        if (p->cmp_kind == D2G_CMP_GTLT) c16_keys_kernel<0><<<gk, 256, 0, st>>>(j, kA, iA, flag);
+        else c16_keys_kernel<1><<<gk, 256, 0, st>>>(j, kA, iA, flag);
+        size_t need = 0;
+        cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, kA, kB, iA, iB, (int)items, (int)S, offs, offs + 1, 0, 64, st);
+        if (int rc = c->wtmp.reserve(need + 256)) return rc;
+        size_t tbytes = c->wtmp.cap;
+        CU(cub::DeviceSegmentedRadixSort::SortPairs(c->wtmp.p, tbytes, kA, kB, iA, iB, (int)items, (int)S, offs, offs + 1, 0, 64, st));
+        c16_rank_kernel<<<S, 256, 0, st>>>(j, kB, iB, c->c16codes.as<uint16_t>(), flag);
+        c->launches += 3 + 8;
+        CU(cudaGetLastError());
+    }
+    C16Args a;
+    a.codes = c->c16codes.as<uint32_t>(); a.KP = j.KP;
+    auto view = [&](uint64_t lo, uint64_t hi, uint64_t rlo, uint32_t rpos0, uint32_t &blk0, uint32_t &n, uint64_t &g0) {
+        const uint64_t blk = (lo - rlo) / C16_BLK;
+        g0 = rlo + blk * C16_BLK; blk0 = rpos0 / C16_BLK + (uint32_t)blk; n = (uint32_t)(hi - g0);
+    };
+    view(r0, r1, lo1, 0, a.a_blk0, a.n_a, a.gi0);
+    if (two) view(c0, c1, lo2, j.posB0, a.b_blk0, a.n_b, a.gj0);
+    else view(c0, c1, lo1, 0, a.b_blk0, a.n_b, a.gj0);
+    a.o = base; a.o.row0 = r0; a.o.row1 = r1; a.o.col0 = c0; a.o.col1 = c1; a.o.use_flag = nullptr; a.o.want = 0;
+    a.use_flag = flag; a.want = 0;
+    const uint64_t tiles_i = (a.n_a + C16_TM - 1) / C16_TM;
+    a.tiles_j = (a.n_b + C16_TN - 1) / C16_TN;
+    const uint64_t grid = tiles_i * a.tiles_j;
+    if (grid > 0x7fffffffULL) return fail(D2G_EINVAL, "comparison job too large for one launch");
+    {
+        KernelTimer kt(c, D2G_T_CMP);
+        if (p->cmp_kind == D2G_CMP_GTLT) {
+            CU(cudaFuncSetAttribute(cmp16_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C16_SMEM));
+            cmp16_tile_kernel<0><<<(unsigned)grid, C16_THREADS, C16_SMEM, st>>>(a);
+        } else {
+            CU(cudaFuncSetAttribute(cmp16_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C16_SMEM));
+            cmp16_tile_kernel<1><<<(unsigned)grid, C16_THREADS, C16_SMEM, st>>>(a);
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    // registers the codes cannot express (NaN): the f64 kernel recomputes the job, gated on the device flag
+    return launch_cmp_f64(c, p, base, r0, r1, c0, c1, flag, 1);
+}
+
+// rows [r0,r1) of the output into out_d / counts (packed from row r0)
+int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, const double *regs_d, const double *cards_d,
+               uint64_t r0, uint64_t r1, float *out_d, uint32_t *c0_d, uint32_t *c1_d, uint64_t sym_lo = ~0ULL) {
+    if (r1 <= r0) return D2G_OK;
+    d2g::CmpArgs a{};
+    a.regs = regs_d; a.cards = cards_d; a.n = p->n; a.out_row0 = r0;
+    a.col_base = p->shape == D2G_PANEL ? p->n - p->nq : 0;
+    a.ncols = n_cols(p); a.shape = p->shape; a.out = out_d; a.c0_out = c0_d; a.c1_out = c1_d; a.c = k;
+    if (a.ncols == 0) return D2G_OK;
+    const uint32_t S = p->sketchsize;
+    // columns this row range needs; sym_lo lets successive row blocks of one call share one code space
+    const uint64_t cb = p->shape == D2G_SYMMETRIC ? std::min(r0, sym_lo) : a.col_base, ce = a.col_base + a.ncols;
+    const uint64_t nR = r1 - r0, nC = ce - cb;
+    // path choice: codes pay a per-job sort of the registers, worth it from ~4e9 register comparisons on
+    int path = (double)nR * (double)nC * (double)S >= 4.0e9 ? 1 : 0;
+    if (const char *ev = getenv("D2G_CMP_PATH")) path = !strcmp(ev, "codes") ? 1 : (!strcmp(ev, "f64") ? 0 : path);
+    uint64_t M = 63232;                                                 // sketches per job: <= 63487 ranks, multiple of 128
+    if (const char *ev = getenv("D2G_C16_MAXJOB")) M = std::max<uint64_t>(256, std::min<uint64_t>(M, strtoull(ev, nullptr, 10) / 128 * 128));  // test knob
+    M = std::min<uint64_t>(M, (0x7fffffffULL / S) / 128 * 128);          // one segmented sort holds < 2^31 items
+    if (S > 65536 * 2 - 2 || M < 256) path = 0;                          // 16-bit lane counters / degenerate blocks
+    if (!path) return launch_cmp_f64(c, p, a, r0, r1, cb, ce, nullptr, 0);
+    auto up64 = [](uint64_t x) { return (x + 63) / 64 * 64; };
+    if (cb <= r0 && r1 <= ce && nC <= M) return run_cmp16_job(c, p, a, cb, ce, 0, 0, r0, r1, cb, ce);
+    if (up64(nR) + nC <= M) return run_cmp16_job(c, p, a, r0, r1, cb, ce, r0, r1, cb, ce);
+    uint64_t BR, BC;
+    if (p->shape == D2G_SYMMETRIC) BR = BC = M / 2;
+    else if (up64(nR) <= M / 2) { BR = nR; BC = (M - up64(nR)) / 64 * 64; }
+    else if (nC <= M / 2) { BC = nC; BR = (M - nC) / 128 * 128; }
+    else BR = BC = M / 2;
+    for (uint64_t rb = r0; rb < r1; rb += BR) {
+        const uint64_t re = std::min(r1, rb + BR);
+        for (uint64_t cc = cb; cc < ce; cc += BC) {
+            const uint64_t cf = std::min(ce, cc + BC);
+            if (p->shape == D2G_SYMMETRIC && cf <= rb + 1) continue;     // block entirely on/below the diagonal
+            int rc;
+            if (cc == rb && cf == re) rc = run_cmp16_job(c, p, a, rb, re, 0, 0, rb, re, cc, cf);
+            else rc = run_cmp16_job(c, p, a, rb, re, cc, cf, rb, re, cc, cf);
+            if (rc) return rc;
+        }
+    }
     return D2G_OK;
 }
 
@@ -692,6 +821,7 @@ int d2g_cmp_rows_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *regs_d, 
     if (int rc = check_cmp_params(p)) return rc;
     if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
     CU(cudaSetDevice(c->device));
+    c->c16cache.valid = false;
     d2g::CmpConsts k;
     if (int rc = make_consts(c, p, &k)) return rc;
     return launch_cmp(c, p, k, regs_d, cards_d, r0, r1, out_d, nullptr, nullptr);
@@ -705,6 +835,7 @@ int d2g_cmp_stream(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, cons
     if (!sink) return fail(D2G_EINVAL, "null sink");
     if (r0 == r1 || p->n == 0) return D2G_OK;
     CU(cudaSetDevice(c->device));
+    c->c16cache.valid = false;
     const uint32_t S = p->sketchsize;
     if (int rc = c->cregs.reserve(p->n * S * 8)) return rc;
     if (int rc = c->ccards.reserve(p->n * 8)) return rc;
@@ -726,7 +857,7 @@ int d2g_cmp_stream(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, cons
     for (uint64_t b = r0; b < r1; b += rows_per) {
         const uint64_t e = std::min(r1, b + rows_per), nv = rows_size(p, b, e);
         float *out_d = c->cout.as<float>() + (uint64_t)slot * cap_vals;
-        if (int rc = launch_cmp(c, p, k, c->cregs.as<double>(), c->ccards.as<double>(), b, e, out_d, nullptr, nullptr)) return rc;
+        if (int rc = launch_cmp(c, p, k, c->cregs.as<double>(), c->ccards.as<double>(), b, e, out_d, nullptr, nullptr, r0)) return rc;
         CU(cudaMemcpyAsync(c->pin[slot].p, out_d, nv * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaEventRecord(c->ev[slot], c->stream));
         if (pend.live) {
@@ -764,6 +895,7 @@ int d2g_cmp_counts(d2g_ctx *c, uint32_t S, int32_t cmp_kind, const double *rows,
     d2g_cmp_params p{};
     p.sketchsize = S; p.cmp_kind = cmp_kind; p.measure = D2G_SIMILARITY; p.k = 31; p.shape = D2G_PANEL; p.n = nr + nc; p.nq = nc;
     if (int rc = check_cmp_params(&p)) return rc;
+    c->c16cache.valid = false;
     if (int rc = c->cregs.reserve(p.n * S * 8)) return rc;
     CU(cudaMemcpyAsync(c->cregs.p, rows, nr * S * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->cregs.as<double>() + nr * S, cols, nc * S * 8, cudaMemcpyHostToDevice, c->stream));

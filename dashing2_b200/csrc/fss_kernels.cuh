@@ -29,23 +29,6 @@ namespace d2g {
 constexpr uint64_t FSS_XOR = 0xb2069fc679a8da0bULL;   // setsketch.h:376
 constexpr int FSS_SPARSE = 24;                         // walk steps kept in the per-thread sparse permutation
 
-__host__ __device__ __forceinline__ uint64_t dkey(double d) {   // order-preserving u64 key of a double
-    uint64_t b;
-#if defined(__CUDA_ARCH__)
-    b = (uint64_t)__double_as_longlong(d);
-#else
-    memcpy(&b, &d, 8);
-#endif
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
-}
-__host__ __device__ __forceinline__ double dunkey(uint64_t k) {
-    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
-#if defined(__CUDA_ARCH__)
-    return __longlong_as_double((long long)b);
-#else
-    double d; memcpy(&d, &b, 8); return d;
-#endif
-}
 constexpr uint64_t FSS_KEY_EMPTY = 0x7fefffffffffffffULL | 0x8000000000000000ULL; // dkey(DBL_MAX), setsketch.h:130
 
 // flog.h:14-20

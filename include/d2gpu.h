@@ -42,7 +42,8 @@ uint64_t d2g_launch_count(const d2g_ctx *ctx);
 /* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket the dominant
  * kernels on the ctx stream. d2g_get_timing synchronises, returns accumulated milliseconds and launch
  * count for one kernel class and resets that class. */
-enum { D2G_T_SKETCH_MAIN = 0, D2G_T_SKETCH_BOOT = 1, D2G_T_CMP = 2, D2G_T_NCLASSES = 3 };
+enum { D2G_T_SKETCH_MAIN = 0, D2G_T_SKETCH_BOOT = 1, D2G_T_CMP = 2 /* the pair-comparison tile kernel */,
+       D2G_T_CMP_PREP = 3 /* order-code construction: keys, per-register sort, ranks */, D2G_T_NCLASSES = 4 };
 int d2g_set_timing(d2g_ctx *ctx, int enabled);
 int d2g_get_timing(d2g_ctx *ctx, int kernel_class, double *ms_total, uint64_t *n_launches);
 

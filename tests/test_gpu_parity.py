@@ -154,6 +154,13 @@ def test_densify_matches_reference_golden():
     assert np.array_equal(c.cmp_matrix(got, den["cards"], p).view(np.uint32), den["mat"].view(np.uint32))
 
 
+@pytest.fixture(params=["f64", "codes"])
+def cmp_path(request, monkeypatch):
+    """Both comparison kernels: the f64 tile kernel and the 16-bit order-code kernel (cmp16_kernels.cuh)."""
+    monkeypatch.setenv("D2G_CMP_PATH", request.param)
+    return request.param
+
+
 CMP = {"sim_sym": ("symmetric", "similarity"), "sim_asym": ("asymmetric", "similarity"),
        "containment_sym": ("symmetric", "containment"), "symcontainment_sym": ("symmetric", "symmetric_containment"),
        "mash_sym": ("symmetric", "poisson_llr"), "isz_sym": ("symmetric", "intersection"),
@@ -161,7 +168,7 @@ CMP = {"sim_sym": ("symmetric", "similarity"), "sim_asym": ("asymmetric", "simil
 
 
 @pytest.mark.parametrize("kind", sorted(CMP))
-def test_compare_opmh_golden(kind):
+def test_compare_opmh_golden(kind, cmp_path):
     z = np.load(expected("opmh_k31_S1024.npz"))
     c = ctx()
     sigs = c.densify(z["sigs"])
@@ -173,7 +180,7 @@ def test_compare_opmh_golden(kind):
 
 @pytest.mark.parametrize("suffix,cmp_kind", [(".ss", 0), (".bmh", 1)])
 @pytest.mark.parametrize("kind", sorted(CMP))
-def test_compare_presketched_golden(kind, suffix, cmp_kind):
+def test_compare_presketched_golden(kind, suffix, cmp_kind, cmp_path):
     f = expected(f"cmp_sk48{suffix}_{kind}.npy")
     if not os.path.exists(f):
         pytest.skip("no golden for this combination")
@@ -186,7 +193,7 @@ def test_compare_presketched_golden(kind, suffix, cmp_kind):
 
 @pytest.mark.parametrize("S", [1024, 1000, 4096, 77])
 @pytest.mark.parametrize("shape", ["symmetric", "asymmetric", "panel"])
-def test_compare_matches_oracle_seeded(S, shape):
+def test_compare_matches_oracle_seeded(S, shape, cmp_path):
     """Ragged sizes (n not a multiple of the 64-pair tile, S not a multiple of the 32-register chunk),
     all measures and both comparison kinds, against the oracle."""
     from dashing2_b200 import synth
@@ -204,7 +211,7 @@ def test_compare_matches_oracle_seeded(S, shape):
             assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (S, shape, measure, cmp_kind)
 
 
-def test_compare_counts_and_stream_blocks():
+def test_compare_counts_and_stream_blocks(cmp_path):
     from dashing2_b200 import synth
     regs, cards = synth.synthetic_sketches(150, 512, seed=9, n_families=5)
     c = ctx()
@@ -220,7 +227,7 @@ def test_compare_counts_and_stream_blocks():
     assert np.array_equal(np.concatenate(parts), full)
 
 
-def test_compare_full_size_properties():
+def test_compare_full_size_properties(cmp_path):
     """BASELINE-scale property checks (S=4096, n=1500): the condensed symmetric matrix equals the upper
     triangle of the asymmetric one; the asymmetric similarity matrix is symmetric with unit diagonal."""
     from dashing2_b200 import synth
@@ -232,6 +239,68 @@ def test_compare_full_size_properties():
     iu = np.triu_indices(n, 1)
     assert np.array_equal(sym, full[iu])
     assert np.array_equal(full, full.T) and np.all(np.diag(full) == 1.0)
+
+
+@pytest.mark.parametrize("shape", ["symmetric", "asymmetric", "panel"])
+@pytest.mark.parametrize("maxjob", [256, 384])
+def test_compare_codes_blocked_jobs(shape, maxjob, monkeypatch):
+    """Order-code path with the per-job sketch limit forced down so one call is split into many block-pair
+    jobs (diagonal, off-diagonal, ragged last blocks), streamed in row ranges."""
+    from dashing2_b200 import synth
+    monkeypatch.setenv("D2G_CMP_PATH", "codes")
+    monkeypatch.setenv("D2G_C16_MAXJOB", str(maxjob))
+    n, nq, S = 1000, 390, 130
+    regs, cards = synth.synthetic_sketches(n, S, seed=77, n_families=9)
+    c = ctx()
+    for cmp_kind, measure in ((0, "containment"), (1, "similarity")):
+        p = c.cmp_params(S, n, shape, measure, k=31, cmp_kind=cmp_kind, nq=nq if shape == "panel" else 0)
+        exp = O.allpairs(regs, cards, shape, measure, k=31, cmp_kind=cmp_kind, nq=nq)
+        assert np.array_equal(c.cmp_matrix(regs, cards, p).view(np.uint32), exp.view(np.uint32)), (shape, cmp_kind)
+        nrows = n - nq if shape == "panel" else n
+        parts = []
+        for r0, r1 in ((0, 131), (131, 500), (500, nrows)):
+            if r0 < r1:
+                c.cmp_stream(regs, cards, p, r0, min(r1, nrows), lambda blk, fr, nr: parts.append(blk.copy()))
+        assert np.array_equal(np.concatenate(parts).view(np.uint32), exp.view(np.uint32)), (shape, cmp_kind, "stream")
+
+
+def test_compare_codes_special_values(monkeypatch):
+    """Signed zeros, infinities, subnormals, negative registers and ties rank exactly like the doubles compare;
+    NaN registers (unordered) make the job fall back to the f64 kernel on the device."""
+    from dashing2_b200 import synth
+    n, S = 300, 96
+    rng = np.random.default_rng(5)
+    pool = np.array([0.0, -0.0, np.inf, -np.inf, 5e-324, -5e-324, 1.0, -1.0, 2.5, 1e308, np.nextafter(1.0, 2.0)])
+    regs = pool[rng.integers(0, len(pool), size=(n, S))]
+    cards = rng.random(n) * 1e6 + 1
+    c = ctx()
+    for with_nan in (False, True):
+        if with_nan:
+            regs = regs.copy(); regs[7, 3] = np.nan; regs[250, 95] = np.nan
+        for cmp_kind in (0, 1):
+            p = c.cmp_params(S, n, "symmetric", "similarity", k=31, cmp_kind=cmp_kind)
+            monkeypatch.setenv("D2G_CMP_PATH", "f64"); a = c.cmp_matrix(regs, cards, p)
+            monkeypatch.setenv("D2G_CMP_PATH", "codes"); b = c.cmp_matrix(regs, cards, p)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (with_nan, cmp_kind)
+            if not with_nan:
+                exp = O.allpairs(regs, cards, "symmetric", "similarity", k=31, cmp_kind=cmp_kind)
+                assert np.array_equal(b.view(np.uint32), exp.view(np.uint32)), cmp_kind
+
+
+def test_compare_codes_more_sketches_than_ranks(monkeypatch):
+    """70 000 column sketches (> 63 487 half codes): the panel is split into column blocks."""
+    from dashing2_b200 import synth
+    monkeypatch.setenv("D2G_CMP_PATH", "codes")
+    nf, nq, S = 150, 70000, 64
+    regs, cards = synth.synthetic_sketches(nf + nq, S, seed=12, n_families=50)
+    c = ctx()
+    p = c.cmp_params(S, nf + nq, "panel", "similarity", k=31, nq=nq)
+    got = c.cmp_matrix(regs, cards, p)
+    monkeypatch.setenv("D2G_CMP_PATH", "f64")
+    assert np.array_equal(got.view(np.uint32), c.cmp_matrix(regs, cards, p).view(np.uint32))
+    a, b = regs[:nf, None, :], regs[None, nf:nf + 2000, :]
+    eq = S - (a > b).sum(-1) - (a < b).sum(-1)
+    assert np.array_equal(got.reshape(nf, nq)[:, :2000], (eq / S).astype(np.float32))
 
 
 @pytest.mark.parametrize("K", [5, 32])
