@@ -48,6 +48,8 @@ struct C16Args {
     uint32_t tiles_j;
     const int *use_flag;     // device flag: run only when *use_flag == want (nullptr = always)
     int want;
+    uint32_t one;            // = 1; multiplier of the IMAD accumulation (a kernel parameter so that ptxas keeps the IMAD)
+    int ne_is_gt;            // MODE 1 on gt/lt registers with power-of-two S: pass (ne, 0) as (gt, lt), see cmp16_tile_kernel
     CmpArgs o;               // output mapping + finalisation constants (regs unused)
 };
 
@@ -86,8 +88,19 @@ __device__ __forceinline__ uint32_t mask_sum_count(uint32_t s) {
     return L + H;
 }
 
-// MODE 0: count (a > b, a < b); MODE 1: count (a != b)
-template <int MODE>
+// acc += m on the FMA pipe (IMAD) instead of the ALU pipe (IADD3): HSET2 executes on the ALU pipe, which
+// is the bound of this kernel (ncu: pipe_alu 98 %, pipe_fma 0.5 % with IADD3 accumulation).
+__device__ __forceinline__ void acc_imad(uint32_t &acc, uint32_t m, uint32_t one) {
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(m), "r"(one));
+}
+
+// MODE 0: count (a > b, a < b); MODE 1: count (a != b).
+// MODE 1 also serves gt/lt registers when S is a power of two (ne_is_gt): gt/S, lt/S and every sum the
+// reference forms from them (cmp_core.cpp:461-470: 1 - a - b, 2 - a - b) are then exact in long double, so the
+// result depends on gt + lt only and (ne, 0) finalises to the same float as (gt, lt).
+// ACC: 1 = IMAD accumulation (FMA pipe; the shipped path), 0 = IADD3 (two masks per instruction, ALU pipe; kept as the
+// measured alternative: 17.6 ms vs 13.1 ms gt/lt, 9.0 ms vs 7.1 ms != on 10 000 x 4096, profiles/r1b_*).
+template <int MODE, int ACC>
 __global__ void __launch_bounds__(C16_THREADS, 2)
 cmp16_tile_kernel(const C16Args a) {
     extern __shared__ __align__(128) unsigned char c16_smem[];
@@ -128,6 +141,7 @@ cmp16_tile_kernel(const C16Args a) {
         for (int v = 0; v < 4; ++v) { acc0[u][v] = 0; acc1[u][v] = 0; }
 
     // thread's operands inside a stage: rows ty*8..+7 -> block ty>>3, offset (ty&7)*8; columns tx*4..+3
+    const uint32_t one = a.one;
     const uint32_t aoff = (ty >> 3) * C16_CHUNK_WORDS + (ty & 7) * 8;
     const uint32_t boff = tx * 4;
     for (uint32_t c = 0; c < nchunks; ++c) {
@@ -135,6 +149,24 @@ cmp16_tile_kernel(const C16Args a) {
         mbar_wait(bar + st, ph);
         const uint32_t *pa = sA + st * 2 * C16_CHUNK_WORDS + aoff;
         const uint32_t *pb = sB + st * C16_CHUNK_WORDS + boff;
+        if (ACC == 1) {
+            // one k-pair per step: every mask goes straight into an IMAD, operands stay at 12 registers
+            #pragma unroll 4
+            for (int kp = 0; kp < C16_KC; ++kp) {
+                const uint4 x0 = *reinterpret_cast<const uint4 *>(pa + kp * C16_BLK);
+                const uint4 x1 = *reinterpret_cast<const uint4 *>(pa + kp * C16_BLK + 4);
+                const uint4 y = *reinterpret_cast<const uint4 *>(pb + kp * C16_BLK);
+                const uint32_t av[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const uint32_t bv[4] = {y.x, y.y, y.z, y.w};
+                #pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    #pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (MODE == 0) { acc_imad(acc0[u][v], hgt2m(av[u], bv[v]), one); acc_imad(acc1[u][v], hlt2m(av[u], bv[v]), one); }
+                        else acc_imad(acc0[u][v], hne2m(av[u], bv[v]), one);
+                    }
+            }
+        } else {
         #pragma unroll 2
         for (int kp = 0; kp < C16_KC; kp += 2) {
             uint32_t av[2][8], bv[2][4];
@@ -159,32 +191,37 @@ cmp16_tile_kernel(const C16Args a) {
                     }
                 }
         }
+        }
         __syncthreads();                                   // every thread is done reading stage st
         if (tid == 0 && c + C16_STAGES < nchunks) issue(st, c + C16_STAGES);
     }
 
-    const uint32_t S = a.o.c.S;
+    // Epilogue through shared memory (the ring is free now: the last iteration ended with a barrier and no copy is
+    // in flight): counts are parked as (c0 | c1 << 16), then consecutive threads finalise consecutive columns of a
+    // row -- one copy of finalize_pair, coalesced stores.
+    uint32_t *sC = sA;                                         // [C16_TM][C16_TN]
     #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const uint32_t li = li0 + ty * 8 + u;
-        if (li >= a.n_a) continue;
-        const uint64_t i = a.gi0 + li;
-        if (i < a.o.row0 || i >= a.o.row1) continue;      // operand blocks may start before / end after the rows of this launch
-        const double lhc = a.o.cards ? __ldg(a.o.cards + i) : 0.;
+    for (int u = 0; u < 8; ++u)
         #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            const uint32_t lj = lj0 + tx * 4 + v;
-            if (lj >= a.n_b) continue;
-            const uint64_t j = a.gj0 + lj;
-            if (j < a.o.col0 || j >= a.o.col1) continue;
-            if (a.o.shape == 0 && j <= i) continue;
             const uint32_t n0 = mask_sum_count(acc0[u][v]);
-            const uint32_t c0 = MODE == 0 ? n0 : S - n0;
-            const uint32_t c1 = MODE == 0 ? mask_sum_count(acc1[u][v]) : 0;
-            const uint64_t oi = out_index(a.o, i, j);
-            if (a.o.c0_out) { a.o.c0_out[oi] = c0; if (a.o.c1_out) a.o.c1_out[oi] = c1; }
-            if (a.o.out) a.o.out[oi] = finalize_pair(a.o.c, c0, c1, lhc, a.o.cards ? __ldg(a.o.cards + j) : 0.);
+            const uint32_t n1 = MODE == 0 ? mask_sum_count(acc1[u][v]) : 0;
+            sC[(ty * 8 + u) * C16_TN + tx * 4 + v] = n0 | (n1 << 16);
         }
+    __syncthreads();
+    const uint32_t S = a.o.c.S;
+    for (int e = tid; e < C16_TM * C16_TN; e += C16_THREADS) {
+        const uint32_t li = li0 + e / C16_TN, lj = lj0 + e % C16_TN;
+        if (li >= a.n_a || lj >= a.n_b) continue;
+        const uint64_t i = a.gi0 + li, j = a.gj0 + lj;
+        if (i < a.o.row0 || i >= a.o.row1 || j < a.o.col0 || j >= a.o.col1) continue;   // operand blocks may overhang the launch's rows / columns
+        if (a.o.shape == 0 && j <= i) continue;
+        const uint32_t pk = sC[e], n0 = pk & 0xffffu;
+        const uint32_t c0 = (MODE == 0 || a.ne_is_gt) ? n0 : S - n0;
+        const uint32_t c1 = pk >> 16;
+        const uint64_t oi = out_index(a.o, i, j);
+        if (a.o.c0_out) { a.o.c0_out[oi] = c0; if (a.o.c1_out) a.o.c1_out[oi] = c1; }
+        if (a.o.out) a.o.out[oi] = finalize_pair(a.o.c, c0, c1, a.o.cards ? __ldg(a.o.cards + i) : 0., a.o.cards ? __ldg(a.o.cards + j) : 0.);
     }
 }
 

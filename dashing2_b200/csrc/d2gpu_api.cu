@@ -715,14 +715,23 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
     const uint64_t grid = tiles_i * a.tiles_j;
     if (grid > 0x7fffffffULL) return fail(D2G_EINVAL, "comparison job too large for one launch");
     {
+        // gt/lt registers with power-of-two S and no raw counts wanted: the != count alone determines the result
+        const bool pow2 = (S & (S - 1)) == 0;
+        const int mode = (p->cmp_kind == D2G_CMP_EQ || (pow2 && !base.c0_out && !getenv("D2G_C16_NO_NE"))) ? 1 : 0;
+        a.ne_is_gt = (mode == 1 && p->cmp_kind == D2G_CMP_GTLT) ? 1 : 0;
+        a.one = 1;
+        int acc = 1;
+        if (const char *ev = getenv("D2G_C16_ACC")) acc = atoi(ev);
         KernelTimer kt(c, D2G_T_CMP);
-        if (p->cmp_kind == D2G_CMP_GTLT) {
-            CU(cudaFuncSetAttribute(cmp16_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C16_SMEM));
-            cmp16_tile_kernel<0><<<(unsigned)grid, C16_THREADS, C16_SMEM, st>>>(a);
-        } else {
-            CU(cudaFuncSetAttribute(cmp16_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C16_SMEM));
-            cmp16_tile_kernel<1><<<(unsigned)grid, C16_THREADS, C16_SMEM, st>>>(a);
-        }
+        auto go = [&](auto kern) -> int {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C16_SMEM));
+            kern<<<(unsigned)grid, C16_THREADS, C16_SMEM, st>>>(a);
+            return D2G_OK;
+        };
+        int rc;
+        if (mode == 0) rc = acc == 0 ? go(cmp16_tile_kernel<0, 0>) : go(cmp16_tile_kernel<0, 1>);
+        else rc = acc == 0 ? go(cmp16_tile_kernel<1, 0>) : go(cmp16_tile_kernel<1, 1>);
+        if (rc) return rc;
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -749,7 +758,7 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     uint64_t M = 63232;                                                 // sketches per job: <= 63487 ranks, multiple of 128
     if (const char *ev = getenv("D2G_C16_MAXJOB")) M = std::max<uint64_t>(256, std::min<uint64_t>(M, strtoull(ev, nullptr, 10) / 128 * 128));  // test knob
     M = std::min<uint64_t>(M, (0x7fffffffULL / S) / 128 * 128);          // one segmented sort holds < 2^31 items
-    if (S > 65536 * 2 - 2 || M < 256) path = 0;                          // 16-bit lane counters / degenerate blocks
+    if (S > 65535 || M < 256) path = 0;                                  // 16-bit counters / degenerate blocks
     if (!path) return launch_cmp_f64(c, p, a, r0, r1, cb, ce, nullptr, 0);
     auto up64 = [](uint64_t x) { return (x + 63) / 64 * 64; };
     if (cb <= r0 && r1 <= ce && nC <= M) return run_cmp16_job(c, p, a, cb, ce, 0, 0, r0, r1, cb, ce);
