@@ -41,7 +41,7 @@ struct FssBootConsumer {
     struct Params { uint64_t *maxrv; FastMod32 fm; uint32_t m; };   // maxrv [n_entities][m], zero-initialised
     static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8; }
     uint64_t *s; Params p;
-    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp) {
+    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool) {
         p = pp; s = reinterpret_cast<uint64_t *>(smem);
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) s[i] = 0;
     }
@@ -158,11 +158,15 @@ struct FssMainConsumer {
         uint64_t *ovf; unsigned long long *ovf_count; uint64_t ovf_cap;   // (x, entity) pairs for the long-walk kernel
         uint32_t m;
     };
-    static constexpr int QCAP = SK_TILE + 512; // survivors are batched over tiles so the walk runs on full warps
-    static constexpr int DCAP = 256;          // walks that outran the sparse state wait here for a tighter threshold
+    static constexpr int QCAP = SK_TILE + 64; // survivors are batched over tiles so the walk runs on full warps
+    static constexpr int DCAP = 192;          // walks that outran the sparse state wait here for a tighter threshold
     static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8 + (size_t)(QCAP + DCAP) * 8 + 64; }
-    uint64_t *skeys, *queue, *defer, *bcast; int *qn, *dn; Params p; double T; uint64_t rvmin;
-    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp) {
+    uint64_t *skeys, *queue, *defer, *bcast; int *qn, *dn; Params p; double T; uint64_t rvmin; int drain_at; uint32_t cur;
+    // Between two end_tile calls a tile pushes at most SK_TILE survivors (unwindowed) or, in windowed mode, the staged
+    // minimizers (SK_SCAP) -- more only for adversarial windows that change their minimizer at every position, which
+    // then overflow to the long-walk list.
+    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool windowed) {
+        drain_at = QCAP - (windowed ? SK_SCAP : SK_TILE); cur = 0;
         p = pp; skeys = reinterpret_cast<uint64_t *>(smem); queue = skeys + p.m; defer = queue + QCAP; bcast = defer + DCAP;
         qn = reinterpret_cast<int *>(bcast + 4); dn = qn + 1;
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) skeys[i] = FSS_KEY_EMPTY;
@@ -176,11 +180,16 @@ struct FssMainConsumer {
     }
     static constexpr bool kEveryWindow = false;
     __device__ __forceinline__ void begin_entity(uint32_t ent, uint64_t) {
-        T = *reinterpret_cast<volatile double *>(p.T + ent); rvmin = rvmin_for(T, p.m);
+        T = *reinterpret_cast<volatile double *>(p.T + ent); rvmin = rvmin_for(T, p.m); cur = ent;
     }
     __device__ __forceinline__ void consume(uint64_t hv) {
         if (cehash(hv ^ FSS_XOR) < rvmin) return;
-        queue[atomicAdd(qn, 1)] = hv;
+        const int slot = atomicAdd(qn, 1);
+        if (slot < QCAP) queue[slot] = hv;
+        else {
+            const unsigned long long g = atomicAdd(p.ovf_count, 1ULL);
+            if (g < p.ovf_cap) { p.ovf[2 * g] = hv; p.ovf[2 * g + 1] = cur; }
+        }
     }
     // All threads.  Replays the queued elements against the CTA-local registers, then tightens the threshold:
     // the final registers are element-wise <= the local ones, so the largest local register bounds the final
@@ -189,7 +198,7 @@ struct FssMainConsumer {
     // only if that does not help do they go to the long-walk kernel.
     __device__ __forceinline__ void drain(uint32_t ent, bool final) {
         for (int round = 0;; ++round) {
-            const int n = *qn;
+            const int n = min(*qn, QCAP);
             for (int q = threadIdx.x; q < n; q += SK_THREADS) {
                 const uint64_t x = queue[q];
                 SparsePerm sp;
@@ -254,7 +263,7 @@ struct FssMainConsumer {
     }
     __device__ __forceinline__ void end_tile(uint32_t ent) {
         __syncthreads();
-        if (*qn > QCAP - SK_TILE) drain(ent, false);     // uniform: every thread reads the same counter after the barrier
+        if (*qn > drain_at) drain(ent, false);           // uniform: every thread reads the same counter after the barrier
     }
     __device__ __forceinline__ void flush(uint32_t ent) {
         __syncthreads();

@@ -97,7 +97,7 @@ struct OpmhConsumer {
     struct Params { uint64_t *regs; FastMod32 fm; uint32_t m; };   // regs [n_entities][m], initialised to ~0
     static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8; }
     uint64_t *sreg; Params p;
-    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp) {
+    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool) {
         p = pp; sreg = reinterpret_cast<uint64_t *>(smem);
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) sreg[i] = ~0ULL;
     }
@@ -120,9 +120,55 @@ struct OpmhConsumer {
     }
 };
 
+// ---- eight consecutive k-mers out of the packed tile ------------------------------------------------
+// km[j] = canonical (or forward) k-mer starting at local base b + j, j = 0..7, rolled with fixed shifts
+// (encoder.h:241-272; kmerutil.h:83-90,137-140).  The reverse complement gains its new base at bit 2k-2;
+// for k >= 17 that is the high word and the insertion is one IMAD.  Returns a bitmask of the j whose
+// k-mer holds a non-ACGT base (0 in the common case, tested once for all eight).
+__device__ __forceinline__ uint32_t kmers8(const uint64_t *W, const uint32_t *M, int b, int k, uint64_t kmask, bool canon, uint64_t km[8]) {
+    uint64_t fw = tile_kmer(W, b, k);
+    uint64_t rc = revcomp(fw, k);
+    const uint32_t nx = (uint32_t)tile_kmer(W, b + k, 7);          // the next seven base codes, first in bits 13:12
+    const int sh = 2 * k - 2;
+    const uint32_t mlo = (uint32_t)kmask, mhi = (uint32_t)(kmask >> 32);
+    uint32_t flo = (uint32_t)fw, fhi = (uint32_t)(fw >> 32), rlo = (uint32_t)rc, rhi = (uint32_t)(rc >> 32);
+    km[0] = canon ? (fw < rc ? fw : rc) : fw;
+    if (sh >= 32) {
+        const uint32_t ph = 1u << (sh - 32);
+        #pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            const uint32_t c = (nx >> (14 - 2 * j)) & 3u;
+            fhi = __funnelshift_l(flo, fhi, 2) & mhi; flo = ((flo << 2) | c) & mlo;
+            rlo = __funnelshift_r(rlo, rhi, 2); rhi = (c ^ 3u) * ph + (rhi >> 2);
+            const uint64_t f = ((uint64_t)fhi << 32) | flo, r = ((uint64_t)rhi << 32) | rlo;
+            km[j] = canon ? (f < r ? f : r) : f;
+        }
+    } else {
+        #pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            const uint32_t c = (nx >> (14 - 2 * j)) & 3u;
+            fhi = __funnelshift_l(flo, fhi, 2) & mhi; flo = ((flo << 2) | c) & mlo;
+            rlo = __funnelshift_r(rlo, rhi, 2) | ((c ^ 3u) << sh); rhi = rhi >> 2;
+            const uint64_t f = ((uint64_t)fhi << 32) | flo, r = ((uint64_t)rhi << 32) | rlo;
+            km[j] = canon ? (f < r ? f : r) : f;
+        }
+    }
+    // invalid bases among b .. b+k+6 (at most 39): none in the common case
+    const int n = k + 7;
+    uint32_t any = tile_invalid(M, b, n < 32 ? n : 32);
+    if (n > 32) any |= tile_invalid(M, b + 32, n - 32);
+    if (any == 0) return 0;
+    uint32_t bad = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) bad |= (tile_invalid(M, b + j, k) ? 1u : 0u) << j;
+    return bad;
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
+constexpr int SK_SCAP = 512;   // staged window minima per tile (expected ~2/(wsz+1) of the tile); the rest take the direct path
+
 template <bool WINDOWED, class Consumer>
-__global__ void __launch_bounds__(SK_THREADS)
+__global__ void __launch_bounds__(SK_THREADS, 3)
 sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = a.k;
@@ -131,9 +177,12 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     uint64_t *W = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *M = reinterpret_cast<uint32_t *>(W + SK_NWORDS);
     uint64_t *score = reinterpret_cast<uint64_t *>(M + SK_NWORDS + (SK_NWORDS & 1));
-    unsigned char *csmem = reinterpret_cast<unsigned char *>(score + (WINDOWED ? a.score_slots : 0));
+    uint64_t *stage = score + (WINDOWED ? a.score_slots : 0);
+    int *scount = reinterpret_cast<int *>(stage + (WINDOWED ? SK_SCAP : 0));
+    unsigned char *csmem = reinterpret_cast<unsigned char *>(scount + (WINDOWED ? 2 : 0));
     Consumer cons;
-    cons.init(csmem, cp);
+    cons.init(csmem, cp, WINDOWED);
+    if (WINDOWED && threadIdx.x == 0) *scount = 0;
 
     const uint64_t span_lo = (uint64_t)blockIdx.x * a.span;
     const uint64_t span_hi = min(span_lo + a.span, a.total_len);
@@ -144,7 +193,21 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (a.rec_off[mid + 1] > span_lo) hi = mid; else lo = mid + 1; }
     uint32_t cur_ent = 0xFFFFFFFFu;
     const uint64_t kmask = k < 32 ? ((1ULL << (2 * k)) - 1) : ~0ULL;
+    const bool canon = a.canon != 0;
+    const int lane = threadIdx.x & 31;
     __syncthreads();
+
+    // Windowed mode stages the minimizers of a tile (as window keys) and hashes them densely at the start of the
+    // next tile: frev64_inv + maskfn + the consumer run on full warps instead of on the ~10 % of lanes whose
+    // window changed its minimizer.  All threads; the caller guarantees a barrier since the last staging.
+    auto drain_stage = [&]() {
+        if (!WINDOWED) return;
+        const int n = min(*scount, SK_SCAP);
+        for (int i = threadIdx.x; i < n; i += SK_THREADS) {
+            const uint64_t km = frev64_inv(stage[i]);
+            if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask));
+        }
+    };
 
     for (uint64_t r = lo; r < a.n_rec; ++r) {
         const uint64_t rs = a.rec_off[r], re = a.rec_off[r + 1];
@@ -155,7 +218,13 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
         if (p0 >= p1) continue;
         const uint32_t ent = a.rec_entity[r];
         if (ent != cur_ent) {
-            if (cur_ent != 0xFFFFFFFFu) cons.flush(cur_ent);
+            if (cur_ent != 0xFFFFFFFFu) {
+                __syncthreads();
+                drain_stage();
+                __syncthreads();
+                if (WINDOWED && threadIdx.x == 0) *scount = 0;
+                cons.flush(cur_ent);
+            }
             cur_ent = ent;
             cons.begin_entity(ent, p0 - span_lo);
         }
@@ -165,100 +234,109 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
             const int off = (int)(t0 - o);
             const int nstart = (int)min((uint64_t)SK_TILE, p1 - t0);  // start positions in this tile
             const int nbases = off + nstart + need - 1;
-            __syncthreads();                                          // previous tile fully consumed
+            __syncthreads();                                          // previous tile fully consumed, its minimizers staged
+            drain_stage();
+            cons.end_tile(cur_ent);
             load_tile(a, reinterpret_cast<uint32_t *>(W), reinterpret_cast<uint16_t *>(M), o, (nbases + 15) >> 4);
             __syncthreads();
+            if (WINDOWED && threadIdx.x == 0) *scount = 0;
             if (!WINDOWED) {
                 const int j0 = threadIdx.x * SK_PPT;
                 if (j0 < nstart) {
-                    int b = off + j0;
-                    uint64_t fw = tile_kmer(W, b, k);
-                    uint64_t rc = revcomp(fw, k);
+                    uint64_t km[8];
+                    const uint32_t bad = kmers8(W, M, off + j0, k, kmask, canon, km);
                     const int jn = min(SK_PPT, nstart - j0);
-                    for (int j = 0; j < jn; ++j, ++b) {
-                        if (j) {
-                            const uint64_t c = tile_code(W, b + k - 1);
-                            fw = ((fw << 2) | c) & kmask;
-                            rc = (rc >> 2) | ((3ULL - c) << (2 * k - 2));
-                        }
-                        if (tile_invalid(M, b, k)) continue;          // encoder.h:254 -- k-mers holding a non-ACGT base are skipped
-                        const uint64_t km = a.canon ? (fw < rc ? fw : rc) : fw;
-                        cons.consume(wang64(km ^ a.xormask));         // maskfn, src/enums.h:136-140
-                    }
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j)
+                        if (j < jn && !((bad >> j) & 1u))             // encoder.h:254 -- k-mers holding a non-ACGT base are skipped
+                            cons.consume(wang64(km[j] ^ a.xormask));  // maskfn, src/enums.h:136-140
                 }
             } else {
                 // per-position keys for k-mer positions [0, nstart + wsz - 1) of the tile
                 const int npos = nstart + wsz - 1;
                 for (int q0 = threadIdx.x * SK_PPT; q0 < npos; q0 += SK_TILE) {
-                    int b = off + q0;
-                    uint64_t fw = tile_kmer(W, b, k);
-                    uint64_t rc = revcomp(fw, k);
-                    const int qn = min(SK_PPT, npos - q0);
-                    for (int j = 0; j < qn; ++j, ++b) {
-                        if (j) {
-                            const uint64_t c = tile_code(W, b + k - 1);
-                            fw = ((fw << 2) | c) & kmask;
-                            rc = (rc >> 2) | ((3ULL - c) << (2 * k - 2));
-                        }
+                    uint64_t km[8];
+                    const uint32_t bad = kmers8(W, M, off + q0, k, kmask, true, km);
+                    uint64_t *dst = score + sk_pad(q0);               // q0 is a multiple of 8: slots dst[0..7]
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j)
                         // canonical windowed path: a k-mer holding an invalid base enters the window as
                         // k-mer 0 (encoder.h:568-571 + kmerutil.h:137-140)
-                        const uint64_t km = tile_invalid(M, b, k) ? 0ULL : (fw < rc ? fw : rc);
-                        score[sk_pad(q0 + j)] = frev64(km);
-                    }
+                        if (q0 + j < npos) dst[j] = frev64(((bad >> j) & 1u) ? 0ULL : km[j]);
                 }
                 __syncthreads();
+                // window j0+j covers score[j0+j .. j0+j+wsz-1]; consecutive windows that share their minimizer feed
+                // the (idempotent) set sketches once -- also across the threads of a warp (shuffle of the last minimum)
                 const int j0 = threadIdx.x * SK_PPT;
-                if (j0 < nstart) {
-                    const int jn = min(SK_PPT, nstart - j0);
-                    // window j0+j covers score[j0+j .. j0+j+wsz-1]; consecutive windows that share their
-                    // minimizer feed the (idempotent) set sketches once
-                    uint64_t prev = 0; bool have_prev = false;
+                const int jn = max(0, min(SK_PPT, nstart - j0));
+                uint64_t mn[SK_PPT];
+                if (jn > 0) {
                     if (wsz >= SK_PPT) {
                         uint64_t common = ~0ULL;                       // entries shared by all windows of this thread
                         for (int q = j0 + jn - 1; q <= j0 + wsz - 1; ++q) common = min(common, score[sk_pad(q)]);
                         uint64_t left[SK_PPT];                          // suffix minima of the leading entries
                         uint64_t run = ~0ULL;
+                        const uint64_t *own = score + sk_pad(j0);
                         #pragma unroll
                         for (int j = SK_PPT - 1; j >= 0; --j) {
-                            if (j < jn - 1) run = min(run, score[sk_pad(j0 + j)]);
+                            if (j < jn - 1) run = min(run, own[j]);
                             left[j] = run;
                         }
                         run = ~0ULL;
                         #pragma unroll
                         for (int j = 0; j < SK_PPT; ++j) {
-                            if (j < jn) {
-                                if (j) run = min(run, score[sk_pad(j0 + wsz - 1 + j)]);
-                                const uint64_t mn = min(min(left[j], common), run);
-                                if (Consumer::kEveryWindow || !have_prev || mn != prev) {
-                                    const uint64_t km = frev64_inv(mn);
-                                    if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask));
-                                }
-                                prev = mn; have_prev = true;
-                            }
+                            if (j && j < jn) run = min(run, score[sk_pad(j0 + wsz - 1 + j)]);
+                            mn[j] = min(min(left[j], common), run);
                         }
                     } else {
-                        for (int j = 0; j < jn; ++j) {
-                            uint64_t mn = ~0ULL;
-                            for (int q = 0; q < wsz; ++q) mn = min(mn, score[sk_pad(j0 + j + q)]);
-                            if (Consumer::kEveryWindow || !have_prev || mn != prev) {
-                                const uint64_t km = frev64_inv(mn);
-                                if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask));
+                        #pragma unroll
+                        for (int j = 0; j < SK_PPT; ++j) {
+                            uint64_t v = ~0ULL;
+                            if (j < jn) for (int q = 0; q < wsz; ++q) v = min(v, score[sk_pad(j0 + j + q)]);
+                            mn[j] = v;
+                        }
+                    }
+                }
+                uint64_t last = 0;
+                #pragma unroll
+                for (int j = 0; j < SK_PPT; ++j) if (j < jn) last = mn[j];
+                uint64_t prev = __shfl_up_sync(0xffffffffu, last, 1);   // lane 0 and the first thread of a tile always emit
+                bool have_prev = lane != 0;
+                #pragma unroll
+                for (int j = 0; j < SK_PPT; ++j) {
+                    const bool e = j < jn && (Consumer::kEveryWindow || !have_prev || mn[j] != prev);
+                    if (j < jn) { prev = mn[j]; have_prev = true; }
+                    if (Consumer::kEveryWindow) {
+                        if (e) { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
+                    } else {
+                        const unsigned bal = __ballot_sync(0xffffffffu, e);
+                        if (bal) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(scount, __popc(bal));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (e) {
+                                const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                                if (slot < SK_SCAP) stage[slot] = mn[j];
+                                else { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
                             }
-                            prev = mn; have_prev = true;
                         }
                     }
                 }
             }
-            cons.end_tile(cur_ent);
         }
     }
-    if (cur_ent != 0xFFFFFFFFu) cons.flush(cur_ent);
+    if (cur_ent != 0xFFFFFFFFu) {
+        __syncthreads();
+        drain_stage();
+        cons.flush(cur_ent);
+    }
 }
 
 inline uint32_t sketch_score_slots(int k, int w) { return w > k ? (uint32_t)sk_pad(SK_TILE + (w - k + 1)) + 2 : 0; }
 template <class Consumer>
 inline size_t sketch_smem_bytes(uint32_t m, uint32_t score_slots) {
     size_t b = (size_t)SK_NWORDS * 8 + (size_t)(SK_NWORDS + (SK_NWORDS & 1)) * 4;
+    if (score_slots) b += (size_t)SK_SCAP * 8 + 8;      // windowed: staged minimizers + counter
     return b + (size_t)score_slots * 8 + Consumer::smem_bytes(m);
 }
 

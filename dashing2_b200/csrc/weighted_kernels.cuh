@@ -25,7 +25,7 @@ struct EmitConsumer {
     static constexpr bool kEveryWindow = true;
     static __host__ __device__ size_t smem_bytes(uint32_t) { return 16; }
     Params p; unsigned int *cur; uint32_t ent; uint64_t base;
-    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp) {
+    __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool) {
         p = pp; cur = reinterpret_cast<unsigned int *>(smem); base = (uint64_t)blockIdx.x * p.span; ent = 0xFFFFFFFFu;
         if (threadIdx.x == 0) *cur = 0;
     }
