@@ -302,24 +302,32 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                 for (int j = 0; j < SK_PPT; ++j) if (j < jn) last = mn[j];
                 uint64_t prev = __shfl_up_sync(0xffffffffu, last, 1);   // lane 0 and the first thread of a tile always emit
                 bool have_prev = lane != 0;
-                #pragma unroll
-                for (int j = 0; j < SK_PPT; ++j) {
-                    const bool e = j < jn && (Consumer::kEveryWindow || !have_prev || mn[j] != prev);
-                    if (j < jn) { prev = mn[j]; have_prev = true; }
-                    if (Consumer::kEveryWindow) {
-                        if (e) { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
-                    } else {
-                        const unsigned bal = __ballot_sync(0xffffffffu, e);
-                        if (bal) {
-                            int base = 0;
-                            if (lane == 0) base = atomicAdd(scount, __popc(bal));
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            if (e) {
-                                const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                if (Consumer::kEveryWindow) {
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j)
+                        if (j < jn) { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
+                } else {
+                    uint32_t emask = 0;
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j)
+                        if (j < jn) { emask |= (uint32_t)(!have_prev || mn[j] != prev) << j; prev = mn[j]; have_prev = true; }
+                    // one slot range per warp: exclusive scan of the per-thread counts, one atomic
+                    const int cnt = __popc(emask);
+                    int incl = cnt;
+                    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(scount, total);
+                        int slot = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
+                        #pragma unroll
+                        for (int j = 0; j < SK_PPT; ++j)
+                            if ((emask >> j) & 1u) {
                                 if (slot < SK_SCAP) stage[slot] = mn[j];
                                 else { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
+                                ++slot;
                             }
-                        }
                     }
                 }
             }
