@@ -38,7 +38,7 @@ EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stre
            "d2g_set_timing", "d2g_get_timing",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
-           "d2g_cmp_stream", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_free"]
+           "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_free"]
 
 _lib = None
 
@@ -77,6 +77,7 @@ def load():
     L.d2g_cmp_rows_size.argtypes = [C.POINTER(CmpParams), u64, u64, C.POINTER(u64)]; L.d2g_cmp_rows_size.restype = C.c_int
     L.d2g_cmp_matrix.argtypes = [vp, C.POINTER(CmpParams), vp, vp, vp]; L.d2g_cmp_matrix.restype = C.c_int
     L.d2g_cmp_stream.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, SINK_FN, vp]; L.d2g_cmp_stream.restype = C.c_int
+    L.d2g_cmp_rows.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, vp]; L.d2g_cmp_rows.restype = C.c_int
     L.d2g_cmp_rows_dev.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, vp]; L.d2g_cmp_rows_dev.restype = C.c_int
     L.d2g_cmp_counts.argtypes = [vp, u32, i32, vp, u64, vp, u64, vp, vp]; L.d2g_cmp_counts.restype = C.c_int
     L.d2g_lsh_topk.argtypes = [vp, C.POINTER(CmpParams), vp, vp, i32, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
@@ -207,6 +208,16 @@ class Context:
             return int(callback(arr, int(first_row), int(n_rows)) or 0)
         fn = SINK_FN(_sink)
         _check(self.L.d2g_cmp_stream(self.h, C.byref(p), _ptr(regs), _ptr(cards), row_begin, row_end, fn, None))
+
+    def cmp_rows(self, regs, cards, p: CmpParams, row_begin, row_end, out: np.ndarray | None = None) -> np.ndarray:
+        """Rows [row_begin,row_end) host in / host out (d2g_cmp_rows); `out` may be a caller (pinned) float32 buffer."""
+        regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
+        nv = self.cmp_rows_size(p, row_begin, row_end)
+        if out is None:
+            out = np.empty(nv, dtype=np.float32)
+        assert out.dtype == np.float32 and out.size >= nv and out.flags.c_contiguous
+        _check(self.L.d2g_cmp_rows(self.h, C.byref(p), _ptr(regs), _ptr(cards), row_begin, row_end, _ptr(out)))
+        return out[:nv]
 
     def cmp_rows_dev(self, p: CmpParams, regs_d, cards_d, row_begin, row_end, out_d):
         _check(self.L.d2g_cmp_rows_dev(self.h, C.byref(p), regs_d, cards_d, row_begin, row_end, out_d))

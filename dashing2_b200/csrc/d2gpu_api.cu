@@ -80,7 +80,7 @@ struct d2g_ctx {
     DevBuf c16buf, c16codes;                                       // order-code compare scratch (keys, sort buffers, codes)
     struct { bool valid = false; const double *regs = nullptr; uint64_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0; uint32_t S = 0; int kind = 0; } c16cache; // codes built earlier in the same API call
     PinBuf pin[2];
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr}, evd[2] = {nullptr, nullptr};
     uint32_t lut_S = 0; int lut_k = -1;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev[D2G_T_NCLASSES];
@@ -126,6 +126,8 @@ int d2g_init(d2g_ctx **out, int device) {
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->evd[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->evd[1], cudaEventDisableTiming));
     *out = c;
     return D2G_OK;
 }
@@ -136,6 +138,8 @@ void d2g_destroy(d2g_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    if (c->evd[0]) cudaEventDestroy(c->evd[0]);
+    if (c->evd[1]) cudaEventDestroy(c->evd[1]);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -208,13 +212,18 @@ uint64_t pick_span(const d2g_ctx *c, uint64_t total_len, uint32_t m) {
     return span;
 }
 
+// A launch may cover only part of a batch (chunked host uploads): start positions [pos_base, pos_end) of the
+// sequence buffer, whose records are rec_off_d[0..n_rec] (absolute offsets) and whose entities start at ent_base.
+struct SketchRange { uint64_t pos_base, pos_end; uint32_t ent_base; };
+
 d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
-                                 const uint32_t *rec_ent_d, uint64_t n_rec, uint64_t total_len, uint32_t m) {
+                                 const uint32_t *rec_ent_d, uint64_t n_rec, uint64_t total_len, uint32_t m, const SketchRange &rg) {
     d2g::SketchArgs a;
     a.seq = reinterpret_cast<const uint8_t *>(seq_d); a.rec_off = rec_off_d; a.rec_entity = rec_ent_d;
     a.n_rec = n_rec; a.total_len = total_len; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
+    a.pos_base = rg.pos_base; a.pos_end = rg.pos_end; a.ent_base = rg.ent_base;
     a.m = m; a.tile_stride = 1; a.score_slots = d2g::sketch_score_slots(p->k, p->w);
-    a.span = pick_span(c, total_len, m);
+    a.span = pick_span(c, rg.pos_end - rg.pos_base, m);
     return a;
 }
 
@@ -223,7 +232,7 @@ int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer:
     KernelTimer kt(c, tcls);
     const size_t smem = d2g::sketch_smem_bytes<Consumer>(a.m, a.score_slots);
     if (smem > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sketch with %u registers needs %zu bytes of shared memory per CTA (max 200 KiB)", a.m, smem);
-    const uint64_t grid = (a.total_len + a.span - 1) / a.span;
+    const uint64_t grid = (a.pos_end - a.pos_base + a.span - 1) / a.span;
     if (windowed) {
         CU(cudaFuncSetAttribute(d2g::sketch_kernel<true, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         d2g::sketch_kernel<true, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
@@ -238,14 +247,15 @@ int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer:
 
 // regs_d: [n_ent][m] u64 for OPMH.  Launches the OPMH sketch kernels on the ctx stream.
 int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
-                const uint32_t *rec_ent_d, uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d) {
+                const uint32_t *rec_ent_d, uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d,
+                const SketchRange *range = nullptr) {
+    const SketchRange rg = range ? *range : SketchRange{0, total_len, 0};
     const uint32_t m = d2g_opmh_m(p->sketchsize);
     const uint64_t nreg = (uint64_t)n_ent * m;
-    fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, c->stream>>>(regs_d, nreg, ~0ULL);
-    c->launches++;
-    if (total_len == 0 || n_rec == 0) return D2G_OK;
+    if (nreg) { fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, c->stream>>>(regs_d, nreg, ~0ULL); c->launches++; }
+    if (rg.pos_end <= rg.pos_base || n_rec == 0) return D2G_OK;
     const bool windowed = p->w > p->k;
-    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m);
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m, rg);
     d2g::OpmhConsumer::Params cp{regs_d, d2g::make_fastmod32(m), m};
     return launch_sketch<d2g::OpmhConsumer>(c, a, cp, windowed);
 }
@@ -253,8 +263,12 @@ int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const
 // Full SetSketch (see fss_kernels.cuh): boot -> threshold -> main -> long walks -> finalize.
 // sig_d [n_ent][S] / card_d [n_ent] may be null.  Synchronises the stream to check the long-walk queue.
 int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
-               uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d) {
+               uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d,
+               const SketchRange *range = nullptr) {
     if (ids_d) return fail(D2G_EUNSUPPORTED, "--save-kmers ids for Full SetSketch are not implemented on the GPU yet");
+    if (n_ent == 0) return D2G_OK;
+    const SketchRange rg = range ? *range : SketchRange{0, total_len, 0};
+    const uint64_t work_len = rg.pos_end > rg.pos_base ? rg.pos_end - rg.pos_base : 0;
     const uint32_t m = p->sketchsize;
     const uint64_t nreg = (uint64_t)n_ent * m;
     const uint64_t ovf_cap = 1ULL << 20;
@@ -271,13 +285,13 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const 
     fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, c->stream>>>(keys, nreg, d2g::FSS_KEY_EMPTY);
     c->launches++;
     const bool windowed = p->w > p->k;
-    if (total_len && n_rec) {
-        d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m);
+    if (work_len && n_rec) {
+        d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m, rg);
         // Boot on every stride-th tile: a cheap first bound T per entity so the first walks of the main pass are
         // short; the main kernel keeps tightening it.  n_eff = elements fed to the sketch per entity (with
         // minimizer windows only ~2/(window+1) of the positions emit).  Cost model per position: 1/stride for the
         // boot pass plus the extra walkers a looser threshold admits => stride ~ sqrt(n_eff / (2 m ln m)).
-        const double per_ent = (double)total_len / std::max(1u, n_ent);
+        const double per_ent = (double)work_len / std::max(1u, n_ent);
         const double n_eff = windowed ? per_ent * 2. / (p->w - p->k + 2) : per_ent;
         const double mlnm = (double)m * std::log((double)m + 2.);
         uint32_t stride = 1;
@@ -371,7 +385,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
     c->launches++;
     uint64_t nu = 0;
     if (n && n_rec) {
-        d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, 0);
+        d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, 0, SketchRange{0, total_len, 0});
         if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
         d2g::EmitConsumer::Params ep{hvA, entA, a.span};
         if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, windowed, D2G_T_SKETCH_MAIN)) return rc;
@@ -531,39 +545,85 @@ extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const ch
     if (int rc = c->seq.reserve(total_len + 64)) return rc;
     if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
     if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
-    if (total_len) CU(cudaMemcpyAsync(c->seq.p, seq, total_len, cudaMemcpyHostToDevice, c->stream));
     if (n_rec) {
         CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, c->stream));
     }
+    const char *seq_d = c->seq.as<char>();
+    const uint64_t *off_d = c->recoff.as<uint64_t>();
+    const uint32_t *ent_d = c->recent.as<uint32_t>();
+    const bool chunked = p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH;
+    auto off_at = [&](uint64_t r) -> uint64_t { return n_rec ? rec_off[r] : 0; };
+    // Chunks of whole entities (~D2G_CHUNK_BYTES of sequence each, default 256 MiB): the upload of chunk i+1 runs on the copy
+    // stream while chunk i is sketched, so a large batch moves at PCIe speed instead of copy + compute.
+    struct Chunk { uint64_t r0, r1; uint32_t e0, e1; };
+    std::vector<Chunk> chunks;
+    {
+        uint64_t target = 256ULL << 20;
+        if (const char *ev = getenv("D2G_CHUNK_BYTES")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
+        if (!chunked) target = ~0ULL;
+        uint64_t r0 = 0; uint32_t e0 = 0;
+        for (uint64_t r = 0; r < n_rec; ++r) {
+            const bool last = r + 1 == n_rec;
+            if (last || (rec_entity[r + 1] != rec_entity[r] && rec_off[r + 1] - rec_off[r0] >= target)) {
+                const uint32_t e1 = last ? n_entities : rec_entity[r + 1];
+                chunks.push_back({r0, r + 1, e0, e1});
+                r0 = r + 1; e0 = e1;
+            }
+        }
+        if (chunks.empty()) chunks.push_back({0, 0, 0, n_entities});
+    }
+    std::vector<cudaEvent_t> evs(chunks.size(), nullptr);
+    auto free_evs = [&]() { for (auto e : evs) if (e) cudaEventDestroy(e); };
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        const uint64_t b0 = off_at(chunks[i].r0), b1 = off_at(chunks[i].r1);
+        if (b1 > b0) {
+            cudaError_t e1 = cudaMemcpyAsync(c->seq.as<char>() + b0, seq + b0, b1 - b0, cudaMemcpyHostToDevice, chunks.size() > 1 ? c->copy_stream : c->stream);
+            if (e1 != cudaSuccess) { free_evs(); return fail(D2G_ECUDA, "sequence upload failed: %s", cudaGetErrorString(e1)); }
+        }
+        if (chunks.size() > 1) {
+            cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming);
+            cudaEventRecord(evs[i], c->copy_stream);
+        }
+    }
     if (p->mode == D2G_MODE_OPMH) {
-        if (int rc = c->regs.reserve((uint64_t)n_entities * m * 8)) return rc;
-        if (int rc = launch_opmh(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len, c->regs.as<uint64_t>())) return rc;
+        if (int rc = c->regs.reserve((uint64_t)n_entities * m * 8)) { free_evs(); return rc; }
+    } else {
+        if (int rc = c->sig.reserve((uint64_t)n_entities * S * 8)) { free_evs(); return rc; }
+        if (int rc = c->card.reserve((uint64_t)n_entities * 8)) { free_evs(); return rc; }
+        if (ids_out) if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) { free_evs(); return rc; }
+    }
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        const Chunk &ch = chunks[i];
+        if (evs[i]) cudaStreamWaitEvent(c->stream, evs[i], 0);
+        const uint64_t nr = ch.r1 - ch.r0; const uint32_t ne = ch.e1 - ch.e0;
+        const SketchRange rg{off_at(ch.r0), off_at(ch.r1), ch.e0};
+        int rc;
+        if (p->mode == D2G_MODE_OPMH)
+            rc = launch_opmh(c, p, seq_d, off_d + ch.r0, ent_d + ch.r0, nr, ne, rg.pos_end, c->regs.as<uint64_t>() + (uint64_t)ch.e0 * m, &rg);
+        else if (p->mode == D2G_MODE_FULL_SETSKETCH)
+            rc = launch_fss(c, p, seq_d, off_d + ch.r0, ent_d + ch.r0, nr, ne, rg.pos_end, c->sig.as<double>() + (uint64_t)ch.e0 * S,
+                            c->card.as<double>() + ch.e0, ids_out ? c->ids.as<uint64_t>() : nullptr, &rg);
+        else
+            rc = launch_weighted(c, p, seq_d, off_d, ent_d, n_rec, n_entities, total_len, c->sig.as<double>(), c->card.as<double>(),
+                                 ids_out ? c->ids.as<uint64_t>() : nullptr);
+        if (rc) { cudaStreamSynchronize(c->copy_stream); free_evs(); return rc; }
+    }
+    free_evs();
+    if (p->mode == D2G_MODE_OPMH) {
         std::vector<uint64_t> tmp;
         uint64_t *hregs = regs_u64_out;
         if (!hregs) { tmp.resize((uint64_t)n_entities * m); hregs = tmp.data(); }
         if (ids_out) {
             if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) return rc;
             const uint64_t n = (uint64_t)n_entities * S;
-            opmh_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->regs.as<uint64_t>(), c->ids.as<uint64_t>(), n_entities, m, S);
-            c->launches++;
+            if (n) { opmh_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->regs.as<uint64_t>(), c->ids.as<uint64_t>(), n_entities, m, S); c->launches++; }
             CU(cudaMemcpyAsync(ids_out, c->ids.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
         }
         CU(cudaMemcpyAsync(hregs, c->regs.p, (uint64_t)n_entities * m * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         if (sig_out || card_out) opmh_finalize_host(hregs, n_entities, m, S, sig_out, card_out);
         return D2G_OK;
-    }
-    // Full SetSketch: registers are doubles produced on the device
-    if (int rc = c->sig.reserve((uint64_t)n_entities * S * 8)) return rc;
-    if (int rc = c->card.reserve((uint64_t)n_entities * 8)) return rc;
-    if (ids_out) if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) return rc;
-    if (p->mode == D2G_MODE_FULL_SETSKETCH) {
-        if (int rc = launch_fss(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len,
-                                c->sig.as<double>(), c->card.as<double>(), ids_out ? c->ids.as<uint64_t>() : nullptr)) return rc;
-    } else {
-        if (int rc = launch_weighted(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n_entities, total_len,
-                                     c->sig.as<double>(), c->card.as<double>(), ids_out ? c->ids.as<uint64_t>() : nullptr)) return rc;
     }
     if (sig_out) CU(cudaMemcpyAsync(sig_out, c->sig.p, (uint64_t)n_entities * S * 8, cudaMemcpyDeviceToHost, c->stream));
     if (card_out) CU(cudaMemcpyAsync(card_out, c->card.p, (uint64_t)n_entities * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -836,13 +896,11 @@ int d2g_cmp_rows_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *regs_d, 
     return launch_cmp(c, p, k, regs_d, cards_d, r0, r1, out_d, nullptr, nullptr);
 }
 
-int d2g_cmp_stream(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards,
-                   uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user) {
-    if (!c) return fail(D2G_EINVAL, "null ctx");
-    if (int rc = check_cmp_params(p)) return rc;
-    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
-    if (!sink) return fail(D2G_EINVAL, "null sink");
-    if (r0 == r1 || p->n == 0) return D2G_OK;
+// Rows [r0,r1) in row blocks of <= ~64M values.  Kernels run on the ctx stream, the device->host copies on the copy
+// stream (block b+1 computes while block b drains).  direct_out != nullptr: results go straight into the caller's
+// buffer (full speed when it is pinned); otherwise through two pinned staging buffers to the sink, in row order.
+static int cmp_blocks(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards,
+                      uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user, float *direct_out) {
     CU(cudaSetDevice(c->device));
     c->c16cache.valid = false;
     const uint32_t S = p->sketchsize;
@@ -852,48 +910,70 @@ int d2g_cmp_stream(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, cons
     CU(cudaMemcpyAsync(c->ccards.p, cards, p->n * 8, cudaMemcpyHostToDevice, c->stream));
     d2g::CmpConsts k;
     if (int rc = make_consts(c, p, &k)) return rc;
-    // row blocks of <= ~64M values, double-buffered: block b+1 computes while block b drains to the sink
     const uint64_t max_vals = 64ULL << 20;
     const uint64_t ncol = n_cols(p);
     uint64_t rows_per = std::max<uint64_t>(d2g::CMP_T, max_vals / std::max<uint64_t>(1, ncol) / d2g::CMP_T * d2g::CMP_T);
     uint64_t cap_vals = 0;
     for (uint64_t b = r0; b < r1; b += rows_per) cap_vals = std::max(cap_vals, rows_size(p, b, std::min(r1, b + rows_per)));
     if (int rc = c->cout.reserve(2 * cap_vals * 4)) return rc;
-    if (int rc = c->pin[0].reserve(cap_vals * 4)) return rc;
-    if (int rc = c->pin[1].reserve(cap_vals * 4)) return rc;
+    if (!direct_out) {
+        if (int rc = c->pin[0].reserve(cap_vals * 4)) return rc;
+        if (int rc = c->pin[1].reserve(cap_vals * 4)) return rc;
+    }
     struct Pending { uint64_t b0, b1, nv; int slot; bool live; } pend{0, 0, 0, 0, false};
-    int slot = 0;
-    for (uint64_t b = r0; b < r1; b += rows_per) {
+    uint64_t done_vals = 0, iblk = 0;
+    for (uint64_t b = r0; b < r1; b += rows_per, ++iblk) {
+        const int slot = (int)(iblk & 1);
         const uint64_t e = std::min(r1, b + rows_per), nv = rows_size(p, b, e);
         float *out_d = c->cout.as<float>() + (uint64_t)slot * cap_vals;
+        if (iblk >= 2) CU(cudaStreamWaitEvent(c->stream, c->evd[slot], 0));       // the copy of block b-2 has left this slot
         if (int rc = launch_cmp(c, p, k, c->cregs.as<double>(), c->ccards.as<double>(), b, e, out_d, nullptr, nullptr, r0)) return rc;
-        CU(cudaMemcpyAsync(c->pin[slot].p, out_d, nv * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaEventRecord(c->ev[slot], c->stream));
-        if (pend.live) {
-            CU(cudaEventSynchronize(c->ev[pend.slot]));
-            if (sink(user, (const float *)c->pin[pend.slot].p, pend.b0, pend.b1 - pend.b0, pend.nv)) return fail(D2G_EIO, "sink aborted");
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev[slot], 0));
+        float *dst = direct_out ? direct_out + done_vals : (float *)c->pin[slot].p;
+        CU(cudaMemcpyAsync(dst, out_d, nv * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaEventRecord(c->evd[slot], c->copy_stream));
+        done_vals += nv;
+        if (!direct_out) {
+            if (pend.live) {
+                CU(cudaEventSynchronize(c->evd[pend.slot]));
+                if (sink(user, (const float *)c->pin[pend.slot].p, pend.b0, pend.b1 - pend.b0, pend.nv)) return fail(D2G_EIO, "sink aborted");
+            }
+            pend = {b, e, nv, slot, true};
         }
-        pend = {b, e, nv, slot, true};
-        slot ^= 1;
     }
     if (pend.live) {
-        CU(cudaEventSynchronize(c->ev[pend.slot]));
+        CU(cudaEventSynchronize(c->evd[pend.slot]));
         if (sink(user, (const float *)c->pin[pend.slot].p, pend.b0, pend.b1 - pend.b0, pend.nv)) return fail(D2G_EIO, "sink aborted");
     }
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
     return D2G_OK;
 }
 
-static int copy_sink(void *user, const float *block, uint64_t, uint64_t, uint64_t n_vals) {
-    float **dst = (float **)user;
-    memcpy(*dst, block, n_vals * 4);
-    *dst += n_vals;
-    return 0;
+int d2g_cmp_stream(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards,
+                   uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    if (!sink) return fail(D2G_EINVAL, "null sink");
+    if (r0 == r1 || p->n == 0) return D2G_OK;
+    return cmp_blocks(c, p, regs, cards, r0, r1, sink, user, nullptr);
+}
+
+int d2g_cmp_rows(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards,
+                 uint64_t r0, uint64_t r1, float *out) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    if (r0 == r1 || p->n == 0) return D2G_OK;
+    if (!out) return fail(D2G_EINVAL, "null output");
+    return cmp_blocks(c, p, regs, cards, r0, r1, nullptr, nullptr, out);
 }
 
 int d2g_cmp_matrix(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards, float *out) {
     if (int rc = check_cmp_params(p)) return rc;
-    float *cursor = out;
-    return d2g_cmp_stream(c, p, regs, cards, 0, n_rows(p), copy_sink, &cursor);
+    return d2g_cmp_rows(c, p, regs, cards, 0, n_rows(p), out);
 }
 
 int d2g_cmp_counts(d2g_ctx *c, uint32_t S, int32_t cmp_kind, const double *rows, uint64_t nr, const double *cols, uint64_t nc,

@@ -36,7 +36,9 @@ struct SketchArgs {
     const uint64_t *rec_off;     // [n_rec + 1]
     const uint32_t *rec_entity;  // [n_rec]
     uint64_t n_rec;
-    uint64_t total_len;
+    uint64_t total_len;          // bytes of seq that may be read (bound of the 16-byte tile loads)
+    uint64_t pos_base, pos_end;  // this launch covers start positions [pos_base, pos_end); rec_off values are absolute
+    uint32_t ent_base;           // subtracted from rec_entity: the consumer's registers start at this entity
     uint64_t span;               // start positions per CTA (multiple of SK_TILE)
     int k, w, canon;
     uint64_t xormask;
@@ -184,8 +186,8 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     cons.init(csmem, cp, WINDOWED);
     if (WINDOWED && threadIdx.x == 0) *scount = 0;
 
-    const uint64_t span_lo = (uint64_t)blockIdx.x * a.span;
-    const uint64_t span_hi = min(span_lo + a.span, a.total_len);
+    const uint64_t span_lo = a.pos_base + (uint64_t)blockIdx.x * a.span;
+    const uint64_t span_hi = min(span_lo + a.span, a.pos_end);
     if (span_lo >= span_hi) return;
 
     // first record whose end lies beyond span_lo (records are sorted by offset)
@@ -216,7 +218,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
         const uint64_t p0 = max(span_lo, rs);
         const uint64_t p1 = min(span_hi, re - need + 1);   // owned, usable start positions [p0, p1)
         if (p0 >= p1) continue;
-        const uint32_t ent = a.rec_entity[r];
+        const uint32_t ent = a.rec_entity[r] - a.ent_base;
         if (ent != cur_ent) {
             if (cur_ent != 0xFFFFFFFFu) {
                 __syncthreads();
@@ -226,7 +228,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                 cons.flush(cur_ent);
             }
             cur_ent = ent;
-            cons.begin_entity(ent, p0 - span_lo);
+            cons.begin_entity(ent, p0 - span_lo);   // offset inside this CTA's span
         }
         for (uint64_t t0 = p0; t0 < p1; t0 += SK_TILE) {
             if (a.tile_stride > 1 && ((t0 / SK_TILE) % a.tile_stride) != 0) continue;

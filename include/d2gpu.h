@@ -136,6 +136,10 @@ int d2g_cmp_rows_size(const d2g_cmp_params *p, uint64_t row_begin, uint64_t row_
 
 /* Whole matrix, host in / host out (regs f64[n][S], cards f64[n], out f32[d2g_cmp_output_size]). */
 int d2g_cmp_matrix(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards, float *out);
+/* Rows [row_begin,row_end) of the matrix, host in / host out (out holds d2g_cmp_rows_size values).  Device->host
+ * copies overlap the kernels and land directly in `out` (page-locked `out` moves at full PCIe speed). */
+int d2g_cmp_rows(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards,
+                 uint64_t row_begin, uint64_t row_end, float *out);
 /* Row range with a sink: results are delivered in row order in blocks (host memory valid only during
  * the callback), so a front-end can stream them to the reference's output format. sink returns 0 to continue. */
 typedef int (*d2g_sink_fn)(void *user, const float *block, uint64_t first_row, uint64_t n_rows, uint64_t n_vals);

@@ -130,6 +130,24 @@ def test_weighted_sketch_matches_oracle_seeded(mode, S, k, w, thr):
         assert r["card"][e] == o["card"]
 
 
+@pytest.mark.parametrize("mode,S,w", [("opmh", 512, -1), ("opmh", 256, 40), ("fss", 256, 51), ("fss", 128, -1)])
+def test_sketch_chunked_upload_equals_single_upload(mode, S, w, monkeypatch):
+    """d2g_sketch_batch uploads large batches in chunks of whole entities overlapped with the kernels; forcing tiny
+    chunks (including empty entities between them) must give the same registers as one upload."""
+    from dashing2_b200 import synth
+    gen = [[s.tobytes()] for _, s in synth.family_genomes(7, 40_000, seed=11)]
+    gen.insert(3, []); gen.insert(0, []); gen.append([])          # entities without records
+    gen[5] = [gen[5][0][:15000], gen[5][0][15000:]]              # a multi-record entity
+    seq, off, ent = pack_batch(gen)
+    c = ctx()
+    p = c.params(mode=mode, S=S, k=31, w=w)
+    monkeypatch.setenv("D2G_CHUNK_BYTES", str(1 << 40)); a = c.sketch_batch(seq, off, ent, len(gen), p)
+    monkeypatch.setenv("D2G_CHUNK_BYTES", "50000"); b = c.sketch_batch(seq, off, ent, len(gen), p)
+    assert np.array_equal(u64(a["sig"]), u64(b["sig"])) and np.array_equal(u64(a["card"]), u64(b["card"]))
+    if mode == "opmh":
+        assert np.array_equal(a["regs_u64"], b["regs_u64"])
+
+
 def test_sketch_merge_property_full_size():
     """Size-independent property at BASELINE scale (1 Mbp genomes, S=1024 / 4096): bucket minima are a
     min-monoid, so sketch(A ++ B) == min(sketch(A), sketch(B)) register-wise, and sketching the same
@@ -225,6 +243,7 @@ def test_compare_counts_and_stream_blocks(cmp_path):
     for r0, r1 in ((0, 10), (10, 99), (99, 150)):
         c.cmp_stream(regs, cards, p, r0, r1, lambda blk, fr, nr: parts.append(blk.copy()))
     assert np.array_equal(np.concatenate(parts), full)
+    assert np.array_equal(np.concatenate([c.cmp_rows(regs, cards, p, a, b) for a, b in ((0, 70), (70, 71), (71, 150))]), full)
 
 
 def test_compare_full_size_properties(cmp_path):
