@@ -360,6 +360,15 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
+    # DRAM traffic of the two dominant kernels, measured once under ncu at exactly this configuration (profiles/)
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        tc = tj.get("config", {})
+        if tc.get("genomes_per_gpu") == G and tc.get("genome_len") == Lg and tc.get("sketchsize") == S and tc.get("n_gpus") == world:
+            traffic = tj
+    except (OSError, ValueError):
+        pass
     steps = args.steps
     total_kmers = kmers_rank * world
     total_pairs = n_all * (n_all - 1) // 2
@@ -375,13 +384,13 @@ def main():
         "ms_per_step": all_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64+f64", "data": "synthetic", "config": workload_config(args, world),
         "phases_ms_per_step": {"sketch": sk_ms / steps, "allgather": ag_ms / steps, "cmp": cmp_ms / steps, "wall": wall_ms / steps},
-        "roofline": {"bound": "hbm", "achieved": sk_ach, "peak": hbm_peak, "unit": "GB/s", "frac": sk_ach / hbm_peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": sk_ach, "peak": hbm_peak, "unit": "GB/s", "frac": sk_ach / hbm_peak, "traffic": traffic.get("sketch_main_bytes_per_launch"),
                      "kernel": "sketch_kernel<windowed, FssMainConsumer>", "launch_ms": k_main_ms / max(1, k_main_n),
                      "algorithmic_bytes_per_launch": sk_bytes, "peak_source": peak_src,
                      "note": "1 B per k-mer position; the kernel is integer-ALU bound (~hundreds of int ops per k-mer), see DESIGN.md",
                      "boot_kernel_ms": k_boot_ms / max(1, k_boot_n)},
         "cmp": {"value": cmp_rate, "unit": "pairs/s", "pairs_per_step": total_pairs, "ms_per_step": cmp_ms / steps,
-                "roofline": {"bound": "hbm", "achieved": cmp_ach, "peak": hbm_peak, "unit": "GB/s", "frac": cmp_ach / hbm_peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": cmp_ach, "peak": hbm_peak, "unit": "GB/s", "frac": cmp_ach / hbm_peak, "traffic": traffic.get("cmp_tile_bytes_per_launch"),
                              "kernel": "cmp16_tile_kernel<ne, imad> (16-bit order codes; S is a power of two)", "launch_ms": k_cmp_ms / max(1, k_cmp_n),
                              "algorithmic_bytes_per_launch": cmp_bytes,
                              "no_reuse_bytes_per_pair": 2 * S * 8,

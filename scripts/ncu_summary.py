@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (raw page) into the handful of metrics the roofline discussion needs.
-usage: scripts/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.txt"""
+usage: scripts/ncu_summary.py gpurun_out/prof.ncu-rep|prof.raw.csv > profiles/<name>.txt"""
 import csv, subprocess, sys
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
