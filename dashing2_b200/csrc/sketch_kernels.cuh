@@ -230,15 +230,26 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
             cur_ent = ent;
             cons.begin_entity(ent, p0 - span_lo);   // offset inside this CTA's span
         }
+        // Windowed mode: window keys live at slot OFF + (key - E0), E0 = first NEW key of the tile; the wsz-1 keys
+        // before it are carried over from the previous tile (copied to slots [OFF-(wsz-1), OFF)), so only the first
+        // tile of a record segment computes them.  A window is identified by its LAST key: thread t owns the
+        // windows ending at its own eight keys.
+        const int OFF = (wsz - 1 + 7) & ~7;
+        bool first = true;
         for (uint64_t t0 = p0; t0 < p1; t0 += SK_TILE) {
-            if (a.tile_stride > 1 && ((t0 / SK_TILE) % a.tile_stride) != 0) continue;
-            const uint64_t o = t0 & ~15ULL;
-            const int off = (int)(t0 - o);
-            const int nstart = (int)min((uint64_t)SK_TILE, p1 - t0);  // start positions in this tile
-            const int nbases = off + nstart + need - 1;
+            if (a.tile_stride > 1 && ((t0 / SK_TILE) % a.tile_stride) != 0) { first = true; continue; }
+            const int nstart = (int)min((uint64_t)SK_TILE, p1 - t0);  // start positions (= windows = new keys) in this tile
+            const int npre = (WINDOWED && first) ? wsz - 1 : 0;        // keys before E0 this tile has to compute itself
+            const uint64_t kb = WINDOWED ? (first ? t0 : t0 + (uint64_t)(wsz - 1)) : t0;   // first key / k-mer whose bases are needed
+            const uint64_t o = kb & ~15ULL;
+            const int off = (int)(kb - o);
+            const int nbases = off + npre + nstart + k - 1;
             __syncthreads();                                          // previous tile fully consumed, its minimizers staged
             drain_stage();
             cons.end_tile(cur_ent);
+            if (WINDOWED && !first)                                   // carry the last wsz-1 keys of the previous (full) tile
+                for (int i = threadIdx.x; i < wsz - 1; i += SK_THREADS)
+                    score[sk_pad(OFF - (wsz - 1) + i)] = score[sk_pad(OFF + SK_TILE - (wsz - 1) + i)];
             load_tile(a, reinterpret_cast<uint32_t *>(W), reinterpret_cast<uint16_t *>(M), o, (nbases + 15) >> 4);
             __syncthreads();
             if (WINDOWED && threadIdx.x == 0) *scount = 0;
@@ -254,47 +265,56 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                             cons.consume(wang64(km[j] ^ a.xormask));  // maskfn, src/enums.h:136-140
                 }
             } else {
-                // per-position keys for k-mer positions [0, nstart + wsz - 1) of the tile
-                const int npos = nstart + wsz - 1;
-                for (int q0 = threadIdx.x * SK_PPT; q0 < npos; q0 += SK_TILE) {
-                    uint64_t km[8];
-                    const uint32_t bad = kmers8(W, M, off + q0, k, kmask, true, km);
-                    uint64_t *dst = score + sk_pad(q0);               // q0 is a multiple of 8: slots dst[0..7]
-                    #pragma unroll
-                    for (int j = 0; j < SK_PPT; ++j)
-                        // canonical windowed path: a k-mer holding an invalid base enters the window as
-                        // k-mer 0 (encoder.h:568-571 + kmerutil.h:137-140)
-                        if (q0 + j < npos) dst[j] = frev64(((bad >> j) & 1u) ? 0ULL : km[j]);
-                }
-                __syncthreads();
-                // window j0+j covers score[j0+j .. j0+j+wsz-1]; consecutive windows that share their minimizer feed
-                // the (idempotent) set sketches once -- also across the threads of a warp (shuffle of the last minimum)
+                // canonical windowed path: a k-mer holding an invalid base enters the window as k-mer 0
+                // (encoder.h:568-571 + kmerutil.h:137-140)
+                if (first)
+                    for (int i = threadIdx.x * SK_PPT; i < npre; i += SK_TILE) {
+                        uint64_t km[8];
+                        const uint32_t bad = kmers8(W, M, off + i, k, kmask, true, km);
+                        #pragma unroll
+                        for (int j = 0; j < SK_PPT; ++j)
+                            if (i + j < npre) score[sk_pad(OFF - npre + i + j)] = frev64(((bad >> j) & 1u) ? 0ULL : km[j]);
+                    }
                 const int j0 = threadIdx.x * SK_PPT;
                 const int jn = max(0, min(SK_PPT, nstart - j0));
+                if (jn > 0) {
+                    uint64_t km[8];
+                    const uint32_t bad = kmers8(W, M, off + npre + j0, k, kmask, true, km);
+                    uint64_t *dst = score + sk_pad(OFF + j0);         // OFF + j0 is a multiple of 8: slots dst[0..7]
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j)
+                        if (j < jn) dst[j] = frev64(((bad >> j) & 1u) ? 0ULL : km[j]);
+                }
+                first = false;
+                __syncthreads();
+                // window j (ending at own key j) covers slots [OFF+j0+j-(wsz-1), OFF+j0+j]; consecutive windows that share
+                // their minimizer feed the (idempotent) set sketches once -- also across the threads of a warp
                 uint64_t mn[SK_PPT];
                 if (jn > 0) {
+                    const int B0 = OFF + j0;
+                    const uint64_t *own = score + sk_pad(B0);
                     if (wsz >= SK_PPT) {
-                        uint64_t common = ~0ULL;                       // entries shared by all windows of this thread
-                        for (int q = j0 + jn - 1; q <= j0 + wsz - 1; ++q) common = min(common, score[sk_pad(q)]);
-                        uint64_t left[SK_PPT];                          // suffix minima of the leading entries
+                        uint64_t common = ~0ULL;                       // slots shared by all eight windows of this thread
+                        for (int q = B0 + 7 - (wsz - 1); q < B0; ++q) common = min(common, score[sk_pad(q)]);
+                        uint64_t left[SK_PPT];                          // suffix minima of the slots only the earlier windows reach
                         uint64_t run = ~0ULL;
-                        const uint64_t *own = score + sk_pad(j0);
+                        left[SK_PPT - 1] = run;
                         #pragma unroll
-                        for (int j = SK_PPT - 1; j >= 0; --j) {
-                            if (j < jn - 1) run = min(run, own[j]);
+                        for (int j = SK_PPT - 2; j >= 0; --j) {
+                            run = min(run, score[sk_pad(B0 + j - (wsz - 1))]);
                             left[j] = run;
                         }
-                        run = ~0ULL;
+                        run = ~0ULL;                                    // prefix minima of the own keys
                         #pragma unroll
                         for (int j = 0; j < SK_PPT; ++j) {
-                            if (j && j < jn) run = min(run, score[sk_pad(j0 + wsz - 1 + j)]);
+                            if (j < jn) run = min(run, own[j]);
                             mn[j] = min(min(left[j], common), run);
                         }
                     } else {
                         #pragma unroll
                         for (int j = 0; j < SK_PPT; ++j) {
                             uint64_t v = ~0ULL;
-                            if (j < jn) for (int q = 0; q < wsz; ++q) v = min(v, score[sk_pad(j0 + j + q)]);
+                            if (j < jn) for (int q = 0; q < wsz; ++q) v = min(v, score[sk_pad(B0 + j - q)]);
                             mn[j] = v;
                         }
                     }
@@ -342,7 +362,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     }
 }
 
-inline uint32_t sketch_score_slots(int k, int w) { return w > k ? (uint32_t)sk_pad(SK_TILE + (w - k + 1)) + 2 : 0; }
+inline uint32_t sketch_score_slots(int k, int w) { return w > k ? (uint32_t)sk_pad(SK_TILE + (w - k + 1) + 8) + 2 : 0; }
 template <class Consumer>
 inline size_t sketch_smem_bytes(uint32_t m, uint32_t score_slots) {
     size_t b = (size_t)SK_NWORDS * 8 + (size_t)(SK_NWORDS + (SK_NWORDS & 1)) * 4;
