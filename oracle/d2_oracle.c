@@ -490,6 +490,112 @@ void d2o_panel(const double *regs, const double *cards, uint64_t nf, uint64_t nq
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* compressed registers: make_compressed (src/cmp_core.cpp:209-322) and the compressed branch   */
+/* of compare() (src/cmp_core.cpp:362-449).  Quantised registers are returned as doubles (exact */
+/* small integers) so that every counting routine above applies unchanged.                      */
+/* ------------------------------------------------------------------------------------------ */
+static int64_t ld_to_i64_x86(long double v) { /* static_cast<int64_t>(long double) as x86 executes it: out of range / NaN -> INT64_MIN */
+    if (!(v > -9223372036854775809.0L && v < 9223372036854775808.0L)) return INT64_MIN;
+    return (int64_t)v;
+}
+static uint64_t reg2sig(double x) { /* cmp_core.cpp:19-37, sizeof(T) == 8 */
+    uint64_t v; memcpy(&v, &x, 8);
+    return d2o_wang64(v ^ 0xa3407fb23cd20efULL);
+}
+/* fd in {1, 2, 4}; truncation <= 0: setsketch quantisation with (a, b) (fitted from the data when a or b <= 0, cmp_core.cpp:250-266;
+ * setsketch.cpp:7-10), falling back to b-bit when the fit degenerates (:267-270); truncation > 0: b-bit signatures (:293-321).
+ * Returns the truncation method actually used; *a, *b hold the parameters used. */
+int d2o_make_compressed(const double *sigs, const uint64_t *kmers, uint64_t nsigs, double fd, int truncation,
+                        long double *a_io, long double *b_io, double *out) {
+    long double a = *a_io, b = *b_io;
+    if (truncation <= 0) {
+        const long double q = fd == 1. ? 254.3L : fd == 2. ? 65534.L : fd == 4. ? 4294967294.L : 15.4L;
+        if (a <= 0. || b <= 0.) {
+            double minreg = DBL_MAX, maxreg = -DBL_MAX;
+            for (uint64_t i = 0; i < nsigs; ++i) {
+                const double v = sigs[i];
+                if (v <= 0 || v == DBL_MAX) continue;
+                if (v < minreg) minreg = v;
+                if (v > maxreg) maxreg = v;
+            }
+            long double mx = minreg, mn = maxreg;          /* optimal_parameters(minreg, maxreg, q): named (maxreg, minreg), swapped if needed */
+            if (mx < mn) { const long double t = mx; mx = mn; mn = t; }
+            b = expl(logl(mx / mn) / q);
+            a = mx / b;
+        }
+        if (a == 0. || isinf(b)) truncation = 1;
+        else {
+            *a_io = a; *b_io = b;
+            const long double logbinv = 1.L / log1pl(b - 1.L);
+            const int64_t top = (int64_t)(q + 1);
+            for (uint64_t i = 0; i < nsigs; ++i) {
+                const long double sub = 1.L - logl((long double)sigs[i] / a) * logbinv;
+                int64_t isub = ld_to_i64_x86(sub);
+                if (isub > top) isub = top;
+                if (isub < 0) isub = 0;
+                out[i] = (double)isub;
+            }
+            return 0;
+        }
+    }
+    const int shift = fd == 1. ? 58 : fd == 2. ? 48 : fd == 4. ? 32 : 0;
+    for (uint64_t i = 0; i < nsigs; ++i) {
+        const uint64_t sig = (kmers ? d2o_wang64(kmers[i]) : reg2sig(sigs[i])) >> shift;
+        out[i] = (double)sig;
+    }
+    return 1;
+}
+
+static long double g_b(long double b, long double arg) { return (1.L - powl(b, -arg)) / (1.L - 1.L / b); } /* cmp_core.cpp:323-325 */
+
+float d2o_finalize_compressed(uint64_t c0, uint64_t c1, uint64_t S, double lhc, double rhc, int measure, int k,
+                              int bbit, double fd, long double b) {
+    long double ret;
+    const long double lhcard = lhc, rhcard = rhc;
+    const long double invdenom = 1.L / S;
+    const double poisson_mult = -1. / (k > 1 ? k : 1);
+    if (bbit) { /* cmp_core.cpp:406-424 */
+        const long double b2pow = -ldexpl(1.L, -(int)(fd * 8.));
+        ret = ldmax(0.L, fmal((long double)c0, invdenom, b2pow) / (1.L + b2pow));
+        if (measure == D2O_INTERSECTION || measure == D2O_UNION_SIZE) {
+            const long double isz = ldmax((lhcard + rhcard) / (2.L - (1.L - ret)), 0.L);
+            ret = measure == D2O_INTERSECTION ? isz : lhcard + rhcard - isz;
+        } else if (measure == D2O_CONTAINMENT) ret = ldmax((lhcard + rhcard) / (2.L - (1.L - ret)), 0.L) * ret / lhcard;
+        else if (measure == D2O_POISSON_LLR) ret = ret ? (double)(logl(2. * ret / (1. + ret)) * poisson_mult) : (double)INFINITY;
+        else if (measure == D2O_SYMMETRIC_CONTAINMENT) ret = ldmax((lhcard + rhcard) / (2.L - (1.L - ret)), 0.L) * ret / ldmin(lhcard, rhcard);
+    } else { /* cmp_core.cpp:425-448 */
+        long double alpha = c0 * invdenom, beta = c1 * invdenom, mu;
+        alpha = g_b(b, alpha); beta = g_b(b, beta);            /* fd < sizeof(RegT) always holds here */
+        if (alpha + beta >= 1.) mu = lhcard + rhcard;
+        else mu = ldmax((lhcard + rhcard) / (2.L - alpha - beta), 0.L);
+        ret = ldmax(1.L - (alpha + beta), 0.L);
+        switch (measure) {
+            case D2O_INTERSECTION: ret *= mu; break;
+            case D2O_UNION_SIZE: ret = lhcard + rhcard - (ret * mu); break;
+            case D2O_CONTAINMENT: ret = ret * mu / lhcard; break;
+            case D2O_SYMMETRIC_CONTAINMENT: ret = (ret * mu) / ldmin(lhcard, rhcard); break;
+            case D2O_POISSON_LLR: ret = ret ? (double)(logl(2. * ret / (1. + ret)) * poisson_mult) : (double)INFINITY; break;
+            default: ;
+        }
+    }
+    if (isnan(ret) || isinf(ret)) ret = LDBL_MAX; /* cmp_core.cpp:573 */
+    return (float)ret;
+}
+
+/* shape: 0 symmetric, 1 asymmetric, 2 panel (rows = first n - nq, columns = last nq) */
+void d2o_allpairs_compressed(const double *cregs, const double *cards, uint64_t n, uint64_t nq, uint64_t S, int shape,
+                             int measure, int k, int bbit, double fd, long double b, float *out) {
+    const uint64_t nr = shape == 2 ? n - nq : n, c0 = shape == 2 ? n - nq : 0;
+    for (uint64_t i = 0; i < nr; ++i)
+        for (uint64_t j = (shape == 0 ? i + 1 : c0); j < n; ++j) {
+            uint64_t x = 0, y = 0;
+            if (bbit) x = d2o_count_eq((const uint64_t *)(cregs + i * S), (const uint64_t *)(cregs + j * S), S);
+            else d2o_count_gtlt(cregs + i * S, cregs + j * S, S, &x, &y);
+            *out++ = d2o_finalize_compressed(x, y, S, cards[i], cards[j], measure, k, bbit, fd, b);
+        }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* exact counting + ProbMinHash3 + BagMinHash2                                                 */
 /* ------------------------------------------------------------------------------------------ */
 static int cmp_u64(const void *a, const void *b) { uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }

@@ -71,6 +71,13 @@ float d2o_finalize(uint64_t gt_or_eq, uint64_t lt, uint64_t sketchsize, double l
 float d2o_compare(const double *a, const double *b, uint64_t sketchsize, double lhcard, double rhcard,
                   int measure, int k, int cmp_kind);
 /* all-pairs drivers restating src/emitrect.cpp:229-326 orderings. out sizes: n(n-1)/2, n*n, nf*nq */
+/* compressed registers: make_compressed (src/cmp_core.cpp:209-322), compressed compare branch (:362-449) */
+int d2o_make_compressed(const double *sigs, const uint64_t *kmers /*nullable*/, uint64_t nsigs, double fd, int truncation,
+                        long double *a_io, long double *b_io, double *out);
+float d2o_finalize_compressed(uint64_t c0, uint64_t c1, uint64_t sketchsize, double lhcard, double rhcard, int measure, int k,
+                              int bbit, double fd, long double b);
+void d2o_allpairs_compressed(const double *cregs, const double *cards, uint64_t n, uint64_t nq, uint64_t S, int shape,
+                             int measure, int k, int bbit, double fd, long double b, float *out);
 void d2o_allpairs_symmetric(const double *regs, const double *cards, uint64_t n, uint64_t S,
                             int measure, int k, int cmp_kind, float *out);
 void d2o_allpairs_asymmetric(const double *regs, const double *cards, uint64_t n, uint64_t S,

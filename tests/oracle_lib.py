@@ -67,6 +67,10 @@ def lib():
     L.d2o_topk.restype = C.c_uint64
     L.d2o_topk.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, u64p,
                            C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
+    L.d2o_make_compressed.restype = C.c_int
+    L.d2o_make_compressed.argtypes = [f64p, C.c_void_p, C.c_uint64, C.c_double, C.c_int, C.POINTER(C.c_longdouble), C.POINTER(C.c_longdouble), f64p]
+    L.d2o_allpairs_compressed.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_double, C.c_longdouble, f32p]
     L.d2o_free.argtypes = [C.c_void_p]
     _lib = L
     return L
@@ -182,6 +186,28 @@ def allpairs(regs: np.ndarray, cards: np.ndarray, kind: str = "symmetric", measu
         L.d2o_panel(regs, cards, nf, nq, S, me, k, cmp_kind, out)
     else:
         raise ValueError(kind)
+    return out
+
+
+def make_compressed(regs: np.ndarray, fd: float, bbit: bool, a: float = -1.0, b: float = -1.0, kmers=None):
+    """make_compressed (src/cmp_core.cpp:209-322): returns (quantised registers as f64, truncation used, a, b)."""
+    L = lib()
+    regs = np.ascontiguousarray(regs, dtype=np.float64)
+    out = np.empty_like(regs)
+    la = C.c_longdouble(a); lb = C.c_longdouble(b)
+    kp = None if kmers is None else np.ascontiguousarray(kmers, dtype=np.uint64).ctypes.data
+    trunc = L.d2o_make_compressed(regs.reshape(-1), kp, regs.size, float(fd), 1 if bbit else 0, C.byref(la), C.byref(lb), out.reshape(-1))
+    return out, trunc, la, lb
+
+
+def allpairs_compressed(cregs, cards, kind, measure, fd, bbit, b, k=31, nq=0):
+    L = lib()
+    cregs = np.ascontiguousarray(cregs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
+    n, S = cregs.shape
+    shape = {"symmetric": 0, "asymmetric": 1, "panel": 2}[kind]
+    nout = n * (n - 1) // 2 if shape == 0 else n * n if shape == 1 else (n - nq) * nq
+    out = np.empty(nout, dtype=np.float32)
+    L.d2o_allpairs_compressed(cregs, cards, n, nq, S, shape, MEASURES[measure], k, 1 if bbit else 0, float(fd), b, out)
     return out
 
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from conftest import expected
+from conftest import expected, GOLD
 
 SKETCH = {
     "opmh_k31_S1024": dict(mode="opmh", S=1024, k=31),
@@ -111,3 +111,26 @@ def test_topk_csr_matches_reference(K):
     ip, ix, dv = O.read_csr(expected(f"topk{K}_sk600.csr"))
     gp, gi, gv = O.topk(z["regs"], z["cards"], K, "similarity", k=32)
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
+
+
+CMPC = {"sim_sym": ("symmetric", "similarity"), "sim_asym": ("asymmetric", "similarity"),
+        "containment_sym": ("symmetric", "containment"), "symcontainment_sym": ("symmetric", "symmetric_containment"),
+        "mash_sym": ("symmetric", "poisson_llr"), "isz_sym": ("symmetric", "intersection"), "usz_sym": ("symmetric", "union_size")}
+
+
+@pytest.mark.parametrize("bbit", [False, True])
+@pytest.mark.parametrize("fd", [1, 2, 4])
+def test_compressed_compare_matches_reference(fd, bbit):
+    """--fastcmp N [--bbit-sigs] on f64 registers: quantisation (a, b fitted from the data) + compressed compare,
+    against the float32 matrices the reference binary wrote (tests/golden/make_golden_compressed.py)."""
+    import json
+    z = np.load(os.path.join(GOLD, "inputs", "sk48x256.npz"))
+    creg, trunc, a, b = O.make_compressed(z["regs"], fd, bbit)
+    assert trunc == (1 if bbit else 0)
+    if not bbit:
+        ab = json.load(open(expected("cmpc_fitted_ab.json")))[f"fd{fd}"]
+        assert "%0.20Lg" % a.value == ab[0] or abs(float(a.value) - float(ab[0])) <= 1e-15 * float(ab[0])
+    for kind, (shape, measure) in CMPC.items():
+        exp = np.load(expected(f"cmpc_sk48_fd{fd}_{'bbit' if bbit else 'ss'}_{kind}.npy"))
+        got = O.allpairs_compressed(creg, z["cards"], shape, measure, fd, bbit, b, k=32)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (fd, bbit, kind)
