@@ -28,7 +28,8 @@ class SketchParams(C.Structure):
 
 class CmpParams(C.Structure):
     _fields_ = [("sketchsize", C.c_uint32), ("cmp_kind", C.c_int32), ("measure", C.c_int32), ("k", C.c_int32),
-                ("shape", C.c_int32), ("n", C.c_uint64), ("nq", C.c_uint64)]
+                ("shape", C.c_int32), ("n", C.c_uint64), ("nq", C.c_uint64), ("regbytes", C.c_double),
+                ("compressed_b", C.c_longdouble)]
 
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c_uint64, C.c_uint64)
@@ -37,7 +38,7 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c
 EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stream", "d2g_sync", "d2g_launch_count",
            "d2g_set_timing", "d2g_get_timing",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
-           "d2g_densify", "d2g_densify_dev", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
+           "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_free"]
 
 _lib = None
@@ -73,6 +74,8 @@ def load():
     L.d2g_sketch_batch_dev.restype = C.c_int
     L.d2g_densify.argtypes = [vp, vp, vp, u64, u32]; L.d2g_densify.restype = C.c_int
     L.d2g_densify_dev.argtypes = [vp, vp, vp, u64, u32]; L.d2g_densify_dev.restype = C.c_int
+    L.d2g_make_compressed.argtypes = [vp, vp, u64, u32, C.c_double, i32, C.POINTER(C.c_longdouble), C.POINTER(C.c_longdouble), vp, C.POINTER(i32)]
+    L.d2g_make_compressed.restype = C.c_int
     L.d2g_cmp_output_size.argtypes = [C.POINTER(CmpParams)]; L.d2g_cmp_output_size.restype = u64
     L.d2g_cmp_rows_size.argtypes = [C.POINTER(CmpParams), u64, u64, C.POINTER(u64)]; L.d2g_cmp_rows_size.restype = C.c_int
     L.d2g_cmp_matrix.argtypes = [vp, C.POINTER(CmpParams), vp, vp, vp]; L.d2g_cmp_matrix.restype = C.c_int
@@ -185,8 +188,20 @@ class Context:
 
     # ---- compare ----
     @staticmethod
-    def cmp_params(S, n, shape="symmetric", measure="similarity", k=31, cmp_kind=0, nq=0):
-        return CmpParams(S, cmp_kind, MEASURE[measure], k, SHAPE[shape], n, nq)
+    def cmp_params(S, n, shape="symmetric", measure="similarity", k=31, cmp_kind=0, nq=0, regbytes=8.0, compressed_b=0.0):
+        return CmpParams(S, cmp_kind, MEASURE[measure], k, SHAPE[shape], n, nq, regbytes, compressed_b)
+
+    def make_compressed(self, regs: np.ndarray, regbytes: float, bbit: bool, a=-1.0, b=-1.0, kmers: np.ndarray | None = None):
+        """make_compressed (--fastcmp N [--bbit-sigs]): returns (quantised registers f64, cmp_kind to compare them with, a, b);
+        a and b are ctypes.c_longdouble -- hand b to cmp_params(compressed_b=b) as is (its .value is only a double)."""
+        regs = np.ascontiguousarray(regs, dtype=np.float64)
+        n, S = regs.shape
+        out = np.empty_like(regs)
+        la = C.c_longdouble(a); lb = C.c_longdouble(b); used = C.c_int32(0)
+        if kmers is not None:
+            kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        _check(self.L.d2g_make_compressed(_ptr(regs), _ptr(kmers), n, S, float(regbytes), int(bool(bbit)), C.byref(la), C.byref(lb), _ptr(out), C.byref(used)))
+        return out, (3 if used.value else 2), la, lb
 
     def densify(self, sig: np.ndarray, kmers: np.ndarray | None = None):
         sig = np.ascontiguousarray(sig, dtype=np.float64).copy()

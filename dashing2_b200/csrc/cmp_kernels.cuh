@@ -29,10 +29,13 @@ struct CmpConsts {
     double poisson_mult;   // -1. / max(1, k)     (cmp_core.cpp:361)
     uint32_t S;
     int measure;
-    int cmp_kind;          // 0 gt/lt, 1 equality
+    int cmp_kind;          // 0 gt/lt, 1 equality, 2 log-quantised registers (gt/lt through g_b), 3 b-bit signatures
     int fast_sim;          // S power of two and measure == SIMILARITY: sim = (S-gt-lt)/S exactly
-    const float *eq_llr_lut; // [S+1] equality-branch POISSON_LLR values (host long double logl)
+    const float *eq_llr_lut; // [S+1] equality-branch POISSON_LLR values (host long double logl); kind 3: by equal count;
+                             // kind 2: triangular [(gt, lt), gt + lt <= S], see tri_index
+    const xf::f80 *lut80;    // kind 2: g_b(b, c/S) for c = 0..S (powl on the host); kind 3: the collision-corrected similarity by equal count
 };
+__host__ __device__ __forceinline__ uint64_t tri_index(uint64_t gt, uint64_t lt, uint64_t S) { return gt * (S + 1) - gt * (gt - 1) / 2 + lt; }
 
 struct CmpArgs {
     const double *regs;    // [n][S]
@@ -62,7 +65,32 @@ __device__ __forceinline__ float finalize_pair(const CmpConsts &c, uint32_t c0, 
     const f80 lhcard = from_double(lhc), rhcard = from_double(rhc);
     const f80 one = from_u64(1), two = from_u64(2);
     f80 ret;
-    if (c.cmp_kind == 0) {
+    if (c.cmp_kind == 3) {                       // cmp_core.cpp:406-424
+        if (c.measure == MEAS_LLR) return c.eq_llr_lut[c0];
+        ret = c.lut80[c0];
+        if (c.measure != MEAS_SIM) {
+            const f80 mu = max_std(div(add(lhcard, rhcard), sub(two, sub(one, ret))), zero());
+            switch (c.measure) {
+                case MEAS_ISZ: ret = mu; break;
+                case MEAS_USZ: ret = sub(add(lhcard, rhcard), mu); break;
+                case MEAS_CONTAIN: ret = div(mul(mu, ret), lhcard); break;
+                case MEAS_SYMCONTAIN: ret = div(mul(mu, ret), min_std(lhcard, rhcard)); break;
+                default: break;
+            }
+        }
+    } else if (c.cmp_kind == 2) {                // cmp_core.cpp:425-448
+        if (c.measure == MEAS_LLR) return c.eq_llr_lut[tri_index(c0, c1, c.S)];
+        const f80 alpha = c.lut80[c0], beta = c.lut80[c1], ab = add(alpha, beta);
+        const f80 mu = le(one, ab) ? add(lhcard, rhcard) : max_std(div(add(lhcard, rhcard), sub(sub(two, alpha), beta)), zero());
+        ret = max_std(sub(one, ab), zero());
+        switch (c.measure) {
+            case MEAS_ISZ: ret = mul(ret, mu); break;
+            case MEAS_USZ: ret = sub(add(lhcard, rhcard), mul(ret, mu)); break;
+            case MEAS_CONTAIN: ret = div(mul(ret, mu), lhcard); break;
+            case MEAS_SYMCONTAIN: ret = div(mul(ret, mu), min_std(lhcard, rhcard)); break;
+            default: break;
+        }
+    } else if (c.cmp_kind == 0) {
         const f80 alpha = mul(from_u64(c0), c.invdenom), beta = mul(from_u64(c1), c.invdenom);
         f80 eq = sub(sub(one, alpha), beta);
         const f80 ucard = max_std(div(add(lhcard, rhcard), sub(sub(two, alpha), beta)), zero());

@@ -76,7 +76,7 @@ struct d2g_ctx {
     std::atomic<uint64_t> launches{0};
     DevBuf seq, recoff, recent, regs, sig, card, ids, aux, aux2;   // sketch scratch
     DevBuf wbuf, wtmp, lbuf;                                              // counting scratch (BagMinHash / ProbMinHash)
-    DevBuf cregs, ccards, cout, clut, ctmp, cktmp;                 // compare scratch
+    DevBuf cregs, ccards, cout, clut, clut80, ctmp, cktmp;         // compare scratch
     DevBuf c16buf, c16codes;                                       // order-code compare scratch (keys, sort buffers, codes)
     struct { bool valid = false; const double *regs = nullptr; uint64_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0; uint32_t S = 0; int kind = 0; } c16cache; // codes built earlier in the same API call
     PinBuf pin[2];
@@ -641,7 +641,12 @@ namespace {
 int check_cmp_params(const d2g_cmp_params *p) {
     if (!p) return fail(D2G_EINVAL, "null params");
     if (p->sketchsize == 0) return fail(D2G_EINVAL, "sketchsize must be > 0");
-    if (p->cmp_kind != D2G_CMP_GTLT && p->cmp_kind != D2G_CMP_EQ) return fail(D2G_EINVAL, "bad cmp_kind %d", p->cmp_kind);
+    if (p->cmp_kind < D2G_CMP_GTLT || p->cmp_kind > D2G_CMP_BBIT) return fail(D2G_EINVAL, "bad cmp_kind %d", p->cmp_kind);
+    if (p->cmp_kind >= D2G_CMP_SS_COMPRESSED) {
+        if (p->regbytes != 1. && p->regbytes != 2. && p->regbytes != 4.) return fail(D2G_EINVAL, "compressed registers: regbytes must be 1, 2 or 4 (got %g)", p->regbytes);
+        if (p->cmp_kind == D2G_CMP_SS_COMPRESSED && !(p->compressed_b > 1.L)) return fail(D2G_EINVAL, "compressed registers: base b must be > 1");
+        if (p->sketchsize > 65535) return fail(D2G_EUNSUPPORTED, "compressed registers: sketchsize > 65535 not supported");
+    }
     if (p->measure < 0 || p->measure > D2G_UNION_SIZE) return fail(D2G_EINVAL, "bad measure %d", p->measure);
     if (p->shape < 0 || p->shape > D2G_PANEL) return fail(D2G_EINVAL, "bad shape %d", p->shape);
     if (p->shape == D2G_PANEL && p->nq > p->n) return fail(D2G_EINVAL, "nq > n");
@@ -664,7 +669,54 @@ int make_consts(d2g_ctx *c, const d2g_cmp_params *p, d2g::CmpConsts *k) {
     k->poisson_mult = -1. / std::max(1, p->k);
     k->S = S; k->measure = p->measure; k->cmp_kind = p->cmp_kind;
     k->fast_sim = (p->measure == D2G_SIMILARITY && p->cmp_kind == D2G_CMP_GTLT && (S & (S - 1)) == 0) ? 1 : 0;
-    k->eq_llr_lut = nullptr;
+    k->eq_llr_lut = nullptr; k->lut80 = nullptr;
+    if (p->cmp_kind >= D2G_CMP_SS_COMPRESSED) {
+        // Everything that depends on the integer counts alone is x87 long-double arithmetic on the host in the reference
+        // (powl in g_b, fmal, logl); tabulate it over the S + 1 possible counts (cmp_core.cpp:323-325,406-432).
+        const long double invdenom = 1.L / S;
+        std::vector<xf::f80> l80(S + 1);
+        std::vector<long double> lv(S + 1);
+        if (p->cmp_kind == D2G_CMP_BBIT) {
+            const long double b2pow = -ldexpl(1.L, -(int)(p->regbytes * 8.));
+            for (uint32_t e = 0; e <= S; ++e) lv[e] = std::max(0.L, fmal((long double)(uint64_t)e, invdenom, b2pow) / (1.L + b2pow));
+        } else {
+            const long double b = p->compressed_b;
+            for (uint32_t e = 0; e <= S; ++e) lv[e] = (1.L - powl(b, -((uint64_t)e * invdenom))) / (1.L - 1.L / b);
+        }
+        for (uint32_t e = 0; e <= S; ++e) l80[e] = xf::from_long_double(lv[e]);
+        if (int rc = c->clut80.reserve((S + 1) * sizeof(xf::f80))) return rc;
+        CU(cudaMemcpyAsync(c->clut80.p, l80.data(), (S + 1) * sizeof(xf::f80), cudaMemcpyHostToDevice, c->stream));
+        k->lut80 = c->clut80.as<xf::f80>();
+        if (p->measure == D2G_POISSON_LLR) {
+            auto llr = [&](long double ret) -> float {   // sim2dist on a long double argument (cmp_core.cpp:361) + :573
+                ret = ret ? (long double)(double)(logl(2. * ret / (1. + ret)) * k->poisson_mult) : (long double)INFINITY;
+                if (isnan(ret) || isinf(ret)) ret = __LDBL_MAX__;
+                return (float)ret;
+            };
+            std::vector<float> lut;
+            if (p->cmp_kind == D2G_CMP_BBIT) {
+                lut.resize(S + 1);
+                for (uint32_t e = 0; e <= S; ++e) lut[e] = llr(lv[e]);
+            } else {
+                lut.resize((size_t)(S + 1) * (S + 2) / 2);
+                auto work = [&](uint32_t g0, uint32_t g1) {
+                    for (uint32_t g = g0; g < g1; ++g)
+                        for (uint32_t l = 0; l + g <= S; ++l)
+                            lut[d2g::tri_index(g, l, S)] = llr(std::max(1.L - (lv[g] + lv[l]), 0.L));
+                };
+                const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 32u));
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() { for (uint32_t g = t; g <= S; g += nt) work(g, g + 1); });
+                for (auto &x : th) x.join();
+            }
+            if (int rc = c->clut.reserve(lut.size() * 4)) return rc;
+            CU(cudaMemcpyAsync(c->clut.p, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            c->lut_S = 0; c->lut_k = -1;              // the equality-branch cache below no longer describes clut
+            k->eq_llr_lut = c->clut.as<float>();
+        }
+        CU(cudaStreamSynchronize(c->stream));           // the host vectors go out of scope
+        return D2G_OK;
+    }
     if (p->cmp_kind == D2G_CMP_EQ && p->measure == D2G_POISSON_LLR) {
         if (c->lut_S != S || c->lut_k != p->k) {
             // equality branch of the Mash distance is long-double logl on the host in the reference
@@ -687,6 +739,9 @@ int make_consts(d2g_ctx *c, const d2g_cmp_params *p, d2g::CmpConsts *k) {
     return D2G_OK;
 }
 
+// kinds 0 and 2 count (a > b, a < b); kinds 1 and 3 count bitwise-equal registers
+inline bool counts_gtlt(int cmp_kind) { return cmp_kind == D2G_CMP_GTLT || cmp_kind == D2G_CMP_SS_COMPRESSED; }
+
 // f64 tile kernel over rows [r0,r1) x columns [c0,c1) (global sketch ids); `base` carries the output mapping.
 int launch_cmp_f64(d2g_ctx *c, const d2g_cmp_params *p, d2g::CmpArgs a, uint64_t r0, uint64_t r1, uint64_t c0, uint64_t c1,
                    const int *use_flag, int want) {
@@ -697,7 +752,7 @@ int launch_cmp_f64(d2g_ctx *c, const d2g_cmp_params *p, d2g::CmpArgs a, uint64_t
     const uint64_t grid = tiles_i * a.tiles_j;
     if (grid > 0x7fffffffULL) return fail(D2G_EINVAL, "row block too large for one launch");
     KernelTimer kt(c, use_flag ? D2G_T_CMP_PREP : D2G_T_CMP);
-    if (p->cmp_kind == D2G_CMP_GTLT) d2g::cmp_tile_kernel<0><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
+    if (counts_gtlt(p->cmp_kind)) d2g::cmp_tile_kernel<0><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
     else d2g::cmp_tile_kernel<1><<<(unsigned)grid, d2g::CMP_THREADS, 0, c->stream>>>(a);
     c->launches++;
     CU(cudaGetLastError());
@@ -748,7 +803,7 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
         CU(cudaMemsetAsync(c->c16codes.p, 0, code_bytes, st));
         fill_offsets_kernel<<<(S + 1 + 255) / 256, 256, 0, st>>>(offs, S, U);
         const dim3 gk((unsigned)((U + 31) / 32), (S + 31) / 32);
-        if (p->cmp_kind == D2G_CMP_GTLT) c16_keys_kernel<0><<<gk, 256, 0, st>>>(j, kA, iA, flag);
+        if (counts_gtlt(p->cmp_kind)) c16_keys_kernel<0><<<gk, 256, 0, st>>>(j, kA, iA, flag);
         else c16_keys_kernel<1><<<gk, 256, 0, st>>>(j, kA, iA, flag);
         size_t need = 0;
         cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, kA, kB, iA, iB, (int)items, (int)S, offs, offs + 1, 0, 64, st);
@@ -777,7 +832,7 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
     {
         // gt/lt registers with power-of-two S and no raw counts wanted: the != count alone determines the result
         const bool pow2 = (S & (S - 1)) == 0;
-        const int mode = (p->cmp_kind == D2G_CMP_EQ || (pow2 && !base.c0_out && !getenv("D2G_C16_NO_NE"))) ? 1 : 0;
+        const int mode = (!counts_gtlt(p->cmp_kind) || (p->cmp_kind == D2G_CMP_GTLT && pow2 && !base.c0_out && !getenv("D2G_C16_NO_NE"))) ? 1 : 0;
         a.ne_is_gt = (mode == 1 && p->cmp_kind == D2G_CMP_GTLT) ? 1 : 0;
         a.one = 1;
         int acc = 1;
@@ -843,6 +898,64 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
 }
 
 } // namespace
+
+extern "C" int d2g_make_compressed(const double *regs, const uint64_t *kmers, uint64_t n, uint32_t S, double fd, int32_t bbit,
+                                   long double *a_io, long double *b_io, double *out, int32_t *bbit_used) {
+    if (!regs || !out || !a_io || !b_io) return fail(D2G_EINVAL, "null argument");
+    if (fd != 1. && fd != 2. && fd != 4.) return fail(D2G_EINVAL, "regbytes must be 1, 2 or 4 (got %g)", fd);
+    const uint64_t nsigs = n * S;
+    long double a = *a_io, b = *b_io;
+    auto parallel = [&](auto fn) {
+        unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 64u));
+        if (nsigs < (1u << 16)) nt = 1;
+        std::vector<std::thread> th;
+        const uint64_t per = (nsigs + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t) { const uint64_t lo = t * per, hi = std::min(nsigs, lo + per); if (lo < hi) th.emplace_back(fn, lo, hi); }
+        for (auto &x : th) x.join();
+    };
+    if (!bbit) {
+        const long double q = fd == 1. ? 254.3 : fd == 2. ? 65534 : 4294967294;   // double literals, as in the reference (cmp_core.cpp:249)
+        if (a <= 0. || b <= 0.) {                       // cmp_core.cpp:250-266
+            double minreg = __DBL_MAX__, maxreg = -__DBL_MAX__;
+            for (uint64_t i = 0; i < nsigs; ++i) {
+                const double v = regs[i];
+                if (v <= 0 || v == __DBL_MAX__) continue;
+                minreg = std::min(minreg, v); maxreg = std::max(maxreg, v);
+            }
+            long double mx = minreg, mn = maxreg;       // optimal_parameters(minreg, maxreg, q), src/setsketch.h:563-566
+            if (mx < mn) std::swap(mx, mn);
+            b = expl(logl(mx / mn) / q);                // src/setsketch.cpp:7-10
+            a = mx / b;
+        }
+        if (a == 0. || isinf(b)) bbit = 1;              // cmp_core.cpp:267-270
+        else {
+            *a_io = a; *b_io = b;
+            const long double logbinv = 1.L / log1pl(b - 1.L);
+            const int64_t top = (int64_t)(q + 1);
+            parallel([&](uint64_t lo, uint64_t hi) {
+                for (uint64_t i = lo; i < hi; ++i) {
+                    const long double sub = 1.L - logl((long double)regs[i] / a) * logbinv;
+                    // static_cast<int64_t>(long double) as x86 executes it: out of range / NaN -> INT64_MIN
+                    int64_t isub = (sub > -9223372036854775809.0L && sub < 9223372036854775808.0L) ? (int64_t)sub : INT64_MIN;
+                    out[i] = (double)std::max<int64_t>(0, std::min(top, isub));
+                }
+            });
+            if (bbit_used) *bbit_used = 0;
+            return D2G_OK;
+        }
+    }
+    const int shift = fd == 1. ? 58 : fd == 2. ? 48 : 32;   // cmp_core.cpp:306-320
+    parallel([&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            uint64_t v;
+            if (kmers) v = d2g::wang64(kmers[i]);
+            else { memcpy(&v, regs + i, 8); v = d2g::wang64(v ^ 0xa3407fb23cd20efULL); }   // reg2sig, cmp_core.cpp:19-37
+            out[i] = (double)(v >> shift);
+        }
+    });
+    if (bbit_used) *bbit_used = 1;
+    return D2G_OK;
+}
 
 extern "C" {
 
@@ -1009,6 +1122,7 @@ extern "C" int d2g_lsh_topk(d2g_ctx *c, const d2g_cmp_params *p, const double *r
     if (!c) return fail(D2G_EINVAL, "null ctx");
     if (int rc = check_cmp_params(p)) return rc;
     if (topk <= 0) return fail(D2G_EINVAL, "topk must be > 0 (similarity-threshold graphs are not implemented)");
+    if (p->cmp_kind >= D2G_CMP_SS_COMPRESSED) return fail(D2G_EUNSUPPORTED, "top-k over compressed registers (--fastcmp with --topk) is not implemented on the GPU");
     if (!indptr_out || !idx_out || !val_out) return fail(D2G_EINVAL, "null output");
     const uint64_t n = p->n; const uint32_t S = p->sketchsize;
     if (n < 2) { for (uint64_t i = 0; i <= n; ++i) indptr_out[i] = 0; *idx_out = (uint32_t *)malloc(4); *val_out = (float *)malloc(4); return D2G_OK; }

@@ -41,6 +41,7 @@ struct Opts {
     int measure = D2G_SIMILARITY;
     int shape = D2G_SYMMETRIC; bool phylip = false;
     int topk = -1;
+    double fastcmp = 8.; bool bbit = false;   // --fastcmp/--regsize N, --bbit-sigs (src/options.h:76,101)
     std::string ffile, qfile, outfile, cmpout, outprefix;
     std::vector<std::string> paths;
     size_t nq = 0;
@@ -70,6 +71,11 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else if (a == "--outprefix" || a == "--prefix") o.outprefix = arg();
         else if (a == "--seed") o.seed = std::stoull(arg());
         else if (a == "--topk" || a == "--top-k" || shortarg("-K")) o.topk = std::stoi(arg());
+        else if (a == "--fastcmp" || a == "--regsize") {
+            o.fastcmp = std::atof(arg().c_str());
+            if (o.fastcmp != 8. && o.fastcmp != 4. && o.fastcmp != 2. && o.fastcmp != 1.) die("--fastcmp must have 8, 4, 2, or 1 as the argument. These are the only register sizes supported.");
+        }
+        else if (a == "--bbit-sigs") o.bbit = true;
         else if (a == "--binary-output" || a == "--emit-binary" || a == "--binary") o.binary = true;
         else if (a == "--phylip") o.phylip = true;
         else if (a == "--asymmetric-all-pairs" || a == "--asymmetric" || a == "--square") o.shape = D2G_ASYMMETRIC;
@@ -91,7 +97,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
             std::printf("dashing2-gpu %s: drop-in for `dashing2 sketch|cmp` (k<=32 DNA; OPMH / Full SetSketch; dense all-pairs / panel).\n"
                         "Options follow the reference: -k -w -S -p -F -Q -o --cmpout --binary-output --phylip --asymmetric-all-pairs\n"
                         "--full-setsketch --oneperm -C/--no-canon --seed --cache --outprefix --save-kmers --presketched\n"
-                        "--containment --symmetric-containment --mash-distance --intersection --union-size\n", d2g_version());
+                        "--containment --symmetric-containment --mash-distance --intersection --union-size --topk --fastcmp --bbit-sigs\n", d2g_version());
             std::exit(0);
         } else if (!a.empty() && a[0] == '-' && a.size() > 1) die("option " + a + " is not supported by the GPU front-end (see DESIGN.md section 7)");
         else o.paths.push_back(a);
@@ -329,6 +335,16 @@ void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
     d2g_cmp_params cp{};
     cp.sketchsize = (uint32_t)S; cp.measure = o.measure; cp.k = o.k; cp.shape = o.shape; cp.n = n; cp.nq = o.nq;
     cp.cmp_kind = (sk.mode == D2G_MODE_OPMH || sk.mode == D2G_MODE_FULL_SETSKETCH) ? D2G_CMP_GTLT : D2G_CMP_EQ;
+    // --fastcmp N: make_compressed (src/cmp_core.cpp:741 -> :209-322); the compressed registers replace the signatures
+    std::vector<double> creg;
+    if (o.fastcmp < 8.) {
+        long double a = -1.L, b = -1.L; int32_t used = 0;
+        creg.resize(sk.sig.size());
+        chk(d2g_make_compressed(sk.sig.data(), sk.ids.size() == sk.sig.size() ? sk.ids.data() : nullptr, n, (uint32_t)S, o.fastcmp, o.bbit ? 1 : 0, &a, &b, creg.data(), &used));
+        if (!o.bbit && !used) std::fprintf(stderr, "Truncated via setsketch, a = %0.20Lg and b = %0.24Lg\n", a, b);
+        if (!o.bbit && used) std::fprintf(stderr, "Note: setsketch compression yielded infinite value; falling back to b-bit compression\n");
+        cp.cmp_kind = used ? D2G_CMP_BBIT : D2G_CMP_SS_COMPRESSED; cp.regbytes = o.fastcmp; cp.compressed_b = b;
+    }
     const bool to_stdout = o.cmpout.empty() || o.cmpout[0] == '-';
     std::FILE *fp = to_stdout ? stdout : std::fopen(o.cmpout.c_str(), "wb");
     if (!fp) die("Failed to open path " + o.cmpout + " for writing");
@@ -367,6 +383,7 @@ void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
     const double *regs = sk.sig.data();
     // equality branch compares the sampled k-mers when they were saved (cmp_core.cpp:501-504)
     if (cp.cmp_kind == D2G_CMP_EQ && sk.ids.size() == sk.sig.size()) regs = reinterpret_cast<const double *>(sk.ids.data());
+    if (!creg.empty()) regs = creg.data();
     chk(d2g_cmp_stream(ctx, &cp, regs, sk.card.data(), 0, nrows, Writer::sink, &w));
     if (!to_stdout) std::fclose(fp); else std::fflush(fp);
 }

@@ -109,7 +109,11 @@ int d2g_sketch_batch_dev(d2g_ctx *ctx, const d2g_sketch_params *p,
 enum { D2G_SIMILARITY = 0, D2G_CONTAINMENT = 1, D2G_SYMMETRIC_CONTAINMENT = 2, D2G_POISSON_LLR = 3,
        D2G_INTERSECTION = 4, D2G_UNION_SIZE = 5 };
 enum { D2G_CMP_GTLT = 0,   /* SetSketch / OPMH registers: count a>b and a<b (cmp_core.cpp:458-494) */
-       D2G_CMP_EQ = 1 };   /* BagMinHash / ProbMinHash / b-bit: count bitwise-equal (cmp_core.cpp:495-517) */
+       D2G_CMP_EQ = 1,     /* BagMinHash / ProbMinHash: count bitwise-equal (cmp_core.cpp:495-517) */
+       D2G_CMP_SS_COMPRESSED = 2, /* --fastcmp N: log-quantised registers from d2g_make_compressed, gt/lt counts through
+                                     g_b with base compressed_b (cmp_core.cpp:425-448) */
+       D2G_CMP_BBIT = 3 };        /* --fastcmp N --bbit-sigs: truncated register hashes, equal count with the b-bit collision
+                                     correction for regbytes*8 bits (cmp_core.cpp:406-424) */
 enum { D2G_SYMMETRIC = 0,  /* condensed upper triangle, rows i<j (emitrect.cpp:290-323) */
        D2G_ASYMMETRIC = 1, /* full n x n (emitrect.cpp:249-268) */
        D2G_PANEL = 2 };    /* rows = first n-nq sketches (-F), cols = last nq (-Q) (emitrect.cpp:229-246) */
@@ -122,11 +126,23 @@ typedef struct {
     int32_t shape;         /* D2G_SYMMETRIC / D2G_ASYMMETRIC / D2G_PANEL */
     uint64_t n;            /* total sketches */
     uint64_t nq;           /* PANEL: number of query (column) sketches */
+    double regbytes;       /* D2G_CMP_BBIT / D2G_CMP_SS_COMPRESSED: --fastcmp register size in bytes (1, 2 or 4); else ignored */
+    long double compressed_b; /* D2G_CMP_SS_COMPRESSED: base b of the quantisation (from d2g_make_compressed); else ignored */
 } d2g_cmp_params;
 
 /* In-place densification of OPMH signatures (empty == 0.0), src/cmp_core.cpp:577-613. */
 int d2g_densify(d2g_ctx *ctx, double *sig, uint64_t *kmers /*nullable*/, uint64_t n, uint32_t sketchsize);
 int d2g_densify_dev(d2g_ctx *ctx, double *sig_d, uint64_t *kmers_d, uint64_t n, uint32_t sketchsize);
+
+/* Register compression, make_compressed (src/cmp_core.cpp:209-322) for --fastcmp N (regbytes 1, 2 or 4) applied to f64
+ * registers after sketching.  bbit == 0: SetSketch log-quantisation 1 - log(reg/a)/log(b) clamped to [0, q+1]; *a_io / *b_io
+ * <= 0 asks for the data-fitted parameters (optimal_parameters, src/setsketch.cpp:7-10) and returns them.  A degenerate fit
+ * falls back to b-bit exactly as the reference does.  bbit != 0: top bits of Wang(register bits ^ 0xa3407fb23cd20ef), or of
+ * Wang(kmers[i]) when kmers is given.  The arithmetic is x87 long double on the host in the reference and here.  out[n][S]
+ * receives the quantised registers as doubles (exact small integers): every compare entry point takes them unchanged with
+ * cmp_kind = D2G_CMP_SS_COMPRESSED (and compressed_b = *b_io) or D2G_CMP_BBIT, according to *bbit_used.  Host pointers. */
+int d2g_make_compressed(const double *regs, const uint64_t *kmers /*nullable*/, uint64_t n, uint32_t sketchsize, double regbytes,
+                        int32_t bbit, long double *a_io, long double *b_io, double *out, int32_t *bbit_used);
 
 /* Number of float32 values the full output holds for these parameters. */
 uint64_t d2g_cmp_output_size(const d2g_cmp_params *p);

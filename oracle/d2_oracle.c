@@ -509,7 +509,7 @@ int d2o_make_compressed(const double *sigs, const uint64_t *kmers, uint64_t nsig
                         long double *a_io, long double *b_io, double *out) {
     long double a = *a_io, b = *b_io;
     if (truncation <= 0) {
-        const long double q = fd == 1. ? 254.3L : fd == 2. ? 65534.L : fd == 4. ? 4294967294.L : 15.4L;
+        const long double q = fd == 1. ? 254.3 : fd == 2. ? 65534 : fd == 4. ? 4294967294 : 15.4; /* double literals, as in the reference */
         if (a <= 0. || b <= 0.) {
             double minreg = DBL_MAX, maxreg = -DBL_MAX;
             for (uint64_t i = 0; i < nsigs; ++i) {
@@ -735,7 +735,8 @@ static pproc_t ph_pop(pheap_t *h) {
     for (;;) { size_t l = 2 * i + 1, r = l + 1, s = i;
         if (l < h->n && h->v[l].x < h->v[s].x) s = l;
         if (r < h->n && h->v[r].x < h->v[s].x) s = r;
-        if (s == i) break; pproc_t t = h->v[i]; h->v[i] = h->v[s]; h->v[s] = t; i = s; }
+        if (s == i) break;
+        pproc_t t = h->v[i]; h->v[i] = h->v[s]; h->v[s] = t; i = s; }
     return top;
 }
 

@@ -88,6 +88,26 @@ def test_cmp_presketched_and_panel(tmp_path):
             assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), exp.view(np.uint32)), (suffix, kind)
 
 
+def test_cmp_fastcmp_and_bbit_sigs(tmp_path):
+    """`cmp --presketched --fastcmp N [--bbit-sigs]`: byte-identical matrices to the reference binary, and the same fitted
+    (a, b) on stderr."""
+    import json
+    from dashing2_b200 import synth
+    z = np.load(os.path.join(GOLD, "inputs", "sk48x256.npz"))
+    stk = str(tmp_path / "sk48.ss")
+    synth.write_stacked(stk, z["regs"], z["cards"], names=[f"s{i}" for i in range(48)])
+    ab = json.load(open(expected("cmpc_fitted_ab.json")))
+    for fd in ("1", "2", "4"):
+        for bbit in (False, True):
+            for kind, argv in (("sim_sym", []), ("mash_sym", ["--mash-distance"]), ("containment_sym", ["--containment"]), ("sim_asym", ["--asymmetric-all-pairs"])):
+                mat = str(tmp_path / "m.f32")
+                r = run(["cmp", "--presketched", "--binary-output", "--cmpout", mat, "--fastcmp", fd] + (["--bbit-sigs"] if bbit else []) + argv + [stk])
+                exp = np.load(expected(f"cmpc_sk48_fd{fd}_{'bbit' if bbit else 'ss'}_{kind}.npy"))
+                assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), exp.view(np.uint32)), (fd, bbit, kind)
+                if not bbit:
+                    assert f"a = {ab['fd' + fd][0]} and b = {ab['fd' + fd][1]}" in r.stderr
+
+
 def test_multiset_and_prob_cache_files(golden_inputs, tmp_path):
     """--multiset / --prob --cache: reference-named .bmh / .pmh cache files with reference bytes."""
     names, paths = golden_inputs

@@ -209,6 +209,41 @@ def test_compare_presketched_golden(kind, suffix, cmp_kind, cmp_path):
     assert np.array_equal(got.view(np.uint32), np.load(f).view(np.uint32))
 
 
+@pytest.mark.parametrize("bbit", [False, True])
+@pytest.mark.parametrize("fd", [1, 2, 4])
+def test_compressed_compare_golden(fd, bbit, cmp_path):
+    """--fastcmp N [--bbit-sigs]: d2g_make_compressed + compressed compare against the reference binary's matrices."""
+    z = np.load(os.path.join(GOLD, "inputs", "sk48x256.npz"))
+    c = ctx()
+    creg, kind, a, b = c.make_compressed(z["regs"], fd, bbit)
+    oreg, trunc, oa, ob = O.make_compressed(z["regs"], fd, bbit)
+    assert np.array_equal(creg, oreg) and kind == (3 if bbit else 2) and (bbit or (a.value == oa.value and b.value == ob.value))
+    for name, (shape, measure) in CMP.items():
+        p = c.cmp_params(256, 48, shape, measure, k=32, cmp_kind=kind, regbytes=fd, compressed_b=b)
+        got = c.cmp_matrix(creg, z["cards"], p)
+        exp = np.load(expected(f"cmpc_sk48_fd{fd}_{'bbit' if bbit else 'ss'}_{name}.npy"))
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (fd, bbit, name)
+
+
+@pytest.mark.parametrize("S,fd,bbit", [(1024, 1, False), (333, 2, False), (4096, 4, False), (512, 1, True), (1000, 2, True), (64, 4, True)])
+def test_compressed_compare_matches_oracle_seeded(S, fd, bbit, cmp_path):
+    from dashing2_b200 import synth
+    n, nq = 150, 60
+    regs, cards = synth.synthetic_sketches(n, S, seed=S + fd, n_families=6)
+    regs *= 1e-3; regs[5, : S // 3] = 0.0; regs[9] = regs[8]
+    cards = cards * (1 + np.arange(n) % 7) / 2.0
+    c = ctx()
+    creg, kind, a, b = c.make_compressed(regs, fd, bbit)
+    oreg, trunc, oa, ob = O.make_compressed(regs, fd, bbit)
+    assert np.array_equal(creg, oreg)
+    for shape in ("symmetric", "panel"):
+        for measure in ("similarity", "containment", "symmetric_containment", "poisson_llr", "intersection", "union_size"):
+            p = c.cmp_params(S, n, shape, measure, k=21, cmp_kind=kind, nq=nq if shape == "panel" else 0, regbytes=fd, compressed_b=b)
+            got = c.cmp_matrix(creg, cards, p)
+            exp = O.allpairs_compressed(oreg, cards, shape, measure, fd, bbit, ob, k=21, nq=nq)
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (S, fd, bbit, shape, measure)
+
+
 @pytest.mark.parametrize("S", [1024, 1000, 4096, 77])
 @pytest.mark.parametrize("shape", ["symmetric", "asymmetric", "panel"])
 def test_compare_matches_oracle_seeded(S, shape, cmp_path):
