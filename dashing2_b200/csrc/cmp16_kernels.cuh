@@ -236,6 +236,7 @@ struct C16Job {
     uint64_t gA0, gB0; uint32_t nA, nB;      // two ranges of global sketches; nB may be 0
     uint32_t posB0;                          // position (in sketches, multiple of 64) of the first column sketch in code space
     uint32_t KP;
+    uint32_t s_begin, s_count;               // register positions [s_begin, s_begin + s_count) handled by this launch (sort buffers hold s_count columns)
 };
 __device__ __forceinline__ uint64_t job_sketch(const C16Job &j, uint32_t u) { return u < j.nA ? j.gA0 + u : j.gB0 + (u - j.nA); }
 __device__ __forceinline__ uint32_t job_pos(const C16Job &j, uint32_t u) { return u < j.nA ? u : j.posB0 + (u - j.nA); }
@@ -245,15 +246,15 @@ __global__ void __launch_bounds__(256)
 c16_keys_kernel(const C16Job j, uint64_t *keysT, uint32_t *idxT, int *nan_flag) {
     __shared__ uint64_t t[32][33];
     const uint32_t U = j.nA + j.nB;
-    const uint32_t u0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const uint32_t u0 = blockIdx.x * 32, s0 = blockIdx.y * 32;      // s: column index inside this launch's group
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;   // 32 x 8
     bool nan = false;
     #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const uint32_t u = u0 + ly + 8 * r, s = s0 + lx;
         uint64_t key = 0;
-        if (u < U && s < j.S) {
-            const double d = __ldg(j.regs + job_sketch(j, u) * j.S + s);
+        if (u < U && s < j.s_count) {
+            const double d = __ldg(j.regs + job_sketch(j, u) * j.S + j.s_begin + s);
             if (KIND == 0) { nan |= d != d; key = dkey(d == 0. ? 0. : d); }
             else key = (uint64_t)__double_as_longlong(d);
         }
@@ -264,19 +265,21 @@ c16_keys_kernel(const C16Job j, uint64_t *keysT, uint32_t *idxT, int *nan_flag) 
     #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const uint32_t s = s0 + ly + 8 * r, u = u0 + lx;
-        if (u < U && s < j.S) { keysT[(uint64_t)s * U + u] = t[lx][ly + 8 * r]; idxT[(uint64_t)s * U + u] = u; }
+        if (u < U && s < j.s_count) { keysT[(uint64_t)s * U + u] = t[lx][ly + 8 * r]; idxT[(uint64_t)s * U + u] = u; }
     }
 }
 
 // (2) after the per-column sort: dense ranks -> half codes, scattered into the blocked code layout.
 //     One CTA per register position; codes16 is the uint16 view of the code words.
+// grank != nullptr: the job is the whole sketch range of a multi-job comparison; write the dense ranks themselves
+// (u32 [S][U]) instead of codes -- c16_local_codes_kernel turns them into per-job codes without sorting again.
 __global__ void __launch_bounds__(256)
-c16_rank_kernel(const C16Job j, const uint64_t *keys_sorted, const uint32_t *idx_sorted, uint16_t *codes16, int *overflow_flag) {
+c16_rank_kernel(const C16Job j, const uint64_t *keys_sorted, const uint32_t *idx_sorted, uint16_t *codes16, uint32_t *grank, int *overflow_flag) {
     __shared__ uint32_t wsum[8];
     __shared__ uint32_t carry_s;
-    const uint32_t U = j.nA + j.nB, s = blockIdx.x;
-    const uint64_t *k = keys_sorted + (uint64_t)s * U;
-    const uint32_t *ix = idx_sorted + (uint64_t)s * U;
+    const uint32_t U = j.nA + j.nB, sl = blockIdx.x, s = j.s_begin + sl;
+    const uint64_t *k = keys_sorted + (uint64_t)sl * U;
+    const uint32_t *ix = idx_sorted + (uint64_t)sl * U;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -293,14 +296,53 @@ c16_rank_kernel(const C16Job j, const uint64_t *keys_sorted, const uint32_t *idx
         for (int q = 0; q < w; ++q) pre += wsum[q];
         const uint32_t rank = pre + x;
         if (i < U) {
-            if (rank >= C16_MAXRANK) *overflow_flag = 1;
-            const uint32_t pos = job_pos(j, ix[i]);
-            const uint64_t word = ((uint64_t)(pos / C16_BLK) * j.KP + (s >> 1)) * C16_BLK + (pos % C16_BLK);
-            codes16[word * 2 + (s & 1)] = rank_to_half(rank);
+            if (grank) grank[(uint64_t)s * U + ix[i]] = rank;
+            else {
+                if (rank >= C16_MAXRANK) *overflow_flag = 1;
+                const uint32_t pos = job_pos(j, ix[i]);
+                const uint64_t word = ((uint64_t)(pos / C16_BLK) * j.KP + (s >> 1)) * C16_BLK + (pos % C16_BLK);
+                codes16[word * 2 + (s & 1)] = rank_to_half(rank);
+            }
         }
         __syncthreads();
         if (threadIdx.x == 255) carry_s = rank;
         __syncthreads();
+    }
+}
+
+// (3) multi-job comparisons: global dense ranks (u32 [S][N], sketch g at column g - g0) -> codes of one job.
+//     One CTA per register position: presence bitmap of the ranks the job's sketches hold, exclusive prefix popcount,
+//     local rank = number of present ranks below.  Shared memory: 2 * ceil(N / 32) words.
+__global__ void __launch_bounds__(256)
+c16_local_codes_kernel(const C16Job j, const uint32_t *grank, uint64_t g0, uint32_t N, uint16_t *codes16) {
+    extern __shared__ uint32_t lc_smem[];
+    __shared__ uint32_t part[256];
+    const uint32_t W = (N + 31) / 32, U = j.nA + j.nB, s = blockIdx.x;
+    uint32_t *bits = lc_smem, *pre = lc_smem + W;
+    const uint32_t *gr = grank + (uint64_t)s * N;
+    for (uint32_t i = threadIdx.x; i < W; i += 256) bits[i] = 0;
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < U; u += 256) {
+        const uint32_t r = gr[job_sketch(j, u) - g0];
+        atomicOr(bits + (r >> 5), 1u << (r & 31));
+    }
+    __syncthreads();
+    const uint32_t per = (W + 255) / 256, w0 = threadIdx.x * per, w1 = min(W, w0 + per);
+    uint32_t sum = 0;
+    for (uint32_t i = w0; i < w1; ++i) sum += __popc(bits[i]);
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t acc = 0; for (int t = 0; t < 256; ++t) { const uint32_t v = part[t]; part[t] = acc; acc += v; } }
+    __syncthreads();
+    uint32_t acc = part[threadIdx.x];
+    for (uint32_t i = w0; i < w1; ++i) { pre[i] = acc; acc += __popc(bits[i]); }
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < U; u += 256) {
+        const uint32_t r = gr[job_sketch(j, u) - g0];
+        const uint32_t local = pre[r >> 5] + __popc(bits[r >> 5] & ((1u << (r & 31)) - 1u));
+        const uint32_t pos = job_pos(j, u);
+        const uint64_t word = ((uint64_t)(pos / C16_BLK) * j.KP + (s >> 1)) * C16_BLK + (pos % C16_BLK);
+        codes16[word * 2 + (s & 1)] = rank_to_half(local);
     }
 }
 

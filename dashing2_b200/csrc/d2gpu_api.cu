@@ -77,7 +77,8 @@ struct d2g_ctx {
     DevBuf seq, recoff, recent, regs, sig, card, ids, aux, aux2;   // sketch scratch
     DevBuf wbuf, wtmp, lbuf;                                              // counting scratch (BagMinHash / ProbMinHash)
     DevBuf cregs, ccards, cout, clut, clut80, ctmp, cktmp;         // compare scratch
-    DevBuf c16buf, c16codes;                                       // order-code compare scratch (keys, sort buffers, codes)
+    DevBuf c16buf, c16codes, c16grank, c16flag;                    // order-code compare scratch (keys, sort buffers, codes, global ranks)
+    struct { bool valid = false; const double *regs = nullptr; uint64_t g0 = 0, N = 0; uint32_t S = 0; int kind = 0; } c16g;   // global ranks built earlier in the same API call
     struct { bool valid = false; const double *regs = nullptr; uint64_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0; uint32_t S = 0; int kind = 0; } c16cache; // codes built earlier in the same API call
     PinBuf pin[2];
     cudaEvent_t ev[2] = {nullptr, nullptr}, evd[2] = {nullptr, nullptr};
@@ -764,6 +765,64 @@ __global__ void fill_offsets_kernel(int64_t *offs, uint32_t nseg, uint64_t strid
     if (i <= nseg) offs[i] = (int64_t)((uint64_t)i * stride);
 }
 
+// Per-register-position sort of the job's sketches + dense ranks, in groups of register positions so that one segmented
+// sort holds < 2^31 items.  Writes half codes into codes16 (blocked layout) or, when grank != nullptr, the u32 ranks.
+int c16_sort_rank(d2g_ctx *c, const d2g_cmp_params *p, d2g::C16Job j, uint16_t *codes16, uint32_t *grank, int *flag) {
+    using namespace d2g;
+    const uint32_t S = j.S;
+    const uint64_t U = (uint64_t)j.nA + j.nB;
+    const uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(S, 0x7fffffffULL / std::max<uint64_t>(1, U)));
+    const uint64_t items_max = U * group;
+    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
+    uint64_t off = 0;
+    const uint64_t o_kA = off; off += al(items_max * 8); const uint64_t o_kB = off; off += al(items_max * 8);
+    const uint64_t o_iA = off; off += al(items_max * 4); const uint64_t o_iB = off; off += al(items_max * 4);
+    const uint64_t o_offs = off; off += al(((uint64_t)group + 1) * 8);
+    if (int rc = c->c16buf.reserve(off)) return rc;
+    unsigned char *B = c->c16buf.as<unsigned char>();
+    uint64_t *kA = (uint64_t *)(B + o_kA), *kB = (uint64_t *)(B + o_kB);
+    uint32_t *iA = (uint32_t *)(B + o_iA), *iB = (uint32_t *)(B + o_iB);
+    int64_t *offs = (int64_t *)(B + o_offs);
+    cudaStream_t st = c->stream;
+    fill_offsets_kernel<<<(group + 1 + 255) / 256, 256, 0, st>>>(offs, group, U);
+    c->launches++;
+    for (uint32_t s0 = 0; s0 < S; s0 += group) {
+        j.s_begin = s0; j.s_count = std::min(group, S - s0);
+        const uint64_t items = U * j.s_count;
+        const dim3 gk((unsigned)((U + 31) / 32), (j.s_count + 31) / 32);
+        if (counts_gtlt(p->cmp_kind)) c16_keys_kernel<0><<<gk, 256, 0, st>>>(j, kA, iA, flag);
+        else c16_keys_kernel<1><<<gk, 256, 0, st>>>(j, kA, iA, flag);
+        size_t need = 0;
+        cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, kA, kB, iA, iB, (int)items, (int)j.s_count, offs, offs + 1, 0, 64, st);
+        if (int rc = c->wtmp.reserve(need + 256)) return rc;
+        size_t tbytes = c->wtmp.cap;
+        CU(cub::DeviceSegmentedRadixSort::SortPairs(c->wtmp.p, tbytes, kA, kB, iA, iB, (int)items, (int)j.s_count, offs, offs + 1, 0, 64, st));
+        c16_rank_kernel<<<j.s_count, 256, 0, st>>>(j, kB, iB, codes16, grank, flag);
+        c->launches += 2 + 11;
+        CU(cudaGetLastError());
+    }
+    return D2G_OK;
+}
+
+// Multi-job comparisons: rank ALL sketches [g0, g0 + N) once per register position (u32 ranks in HBM); each job then
+// derives its own dense codes from them with c16_local_codes_kernel instead of sorting its sketches again.
+int c16_build_global(d2g_ctx *c, const d2g_cmp_params *p, const double *regs_d, uint64_t g0, uint64_t N) {
+    using namespace d2g;
+    auto &g = c->c16g;
+    const uint32_t S = p->sketchsize;
+    if (g.valid && g.regs == regs_d && g.g0 == g0 && g.N == N && g.S == S && g.kind == p->cmp_kind) return D2G_OK;
+    g.valid = false;
+    if (int rc = c->c16grank.reserve(N * S * 4)) return rc;
+    if (int rc = c->c16flag.reserve(256)) return rc;
+    KernelTimer kt(c, D2G_T_CMP_PREP);
+    CU(cudaMemsetAsync(c->c16flag.p, 0, 4, c->stream));
+    C16Job j{};
+    j.regs = regs_d; j.S = S; j.gA0 = g0; j.nA = (uint32_t)N; j.nB = 0; j.posB0 = 0; j.KP = 0;
+    if (int rc = c16_sort_rank(c, p, j, nullptr, c->c16grank.as<uint32_t>(), c->c16flag.as<int>())) return rc;
+    g.valid = true; g.regs = regs_d; g.g0 = g0; g.N = N; g.S = S; g.kind = p->cmp_kind;
+    return D2G_OK;
+}
+
 // One comparison job on 16-bit order codes (cmp16_kernels.cuh): the sketches [lo1,hi1) (and [lo2,hi2) when
 // hi2 > lo2) are ranked per register position, coded, and rows [r0,r1) x columns [c0,c1) are compared.
 // [r0,r1) must lie inside range 1; [c0,c1) inside range 2 when it exists, else inside range 1.
@@ -773,47 +832,39 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
     if (r1 <= r0 || c1 <= c0) return D2G_OK;
     const uint32_t S = p->sketchsize;
     const bool two = hi2 > lo2;
-    C16Job j;
+    C16Job j{};
     j.regs = base.regs; j.S = S; j.gA0 = lo1; j.nA = (uint32_t)(hi1 - lo1); j.gB0 = two ? lo2 : 0; j.nB = two ? (uint32_t)(hi2 - lo2) : 0;
     j.posB0 = (j.nA + C16_BLK - 1) / C16_BLK * C16_BLK;
     j.KP = ((S + 1) / 2 + C16_KC - 1) / C16_KC * C16_KC;
-    const uint64_t U = (uint64_t)j.nA + j.nB, items = U * S;
+    j.s_begin = 0; j.s_count = S;
+    const uint64_t U = (uint64_t)j.nA + j.nB;
     const uint64_t nblocks = (uint64_t)j.posB0 / C16_BLK + (j.nB + C16_BLK - 1) / C16_BLK + 2;   // +2: a row tile reads two blocks
     const uint64_t code_bytes = nblocks * j.KP * C16_BLK * 4;
-    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
-    uint64_t off = 0;
-    const uint64_t o_kA = off; off += al(items * 8); const uint64_t o_kB = off; off += al(items * 8);
-    const uint64_t o_iA = off; off += al(items * 4); const uint64_t o_iB = off; off += al(items * 4);
-    const uint64_t o_offs = off; off += al(((uint64_t)S + 1) * 8);
-    const uint64_t o_flag = off; off += 256;
-    if (int rc = c->c16buf.reserve(off)) return rc;
     if (int rc = c->c16codes.reserve(code_bytes)) return rc;
-    unsigned char *B = c->c16buf.as<unsigned char>();
-    uint64_t *kA = (uint64_t *)(B + o_kA), *kB = (uint64_t *)(B + o_kB);
-    uint32_t *iA = (uint32_t *)(B + o_iA), *iB = (uint32_t *)(B + o_iB);
-    int64_t *offs = (int64_t *)(B + o_offs);
-    int *flag = (int *)(B + o_flag);
+    if (int rc = c->c16flag.reserve(256)) return rc;
+    int *flag = c->c16flag.as<int>();
     cudaStream_t st = c->stream;
     auto &cc = c->c16cache;
+    auto &gl = c->c16g;
     const bool cached = cc.valid && cc.regs == base.regs && cc.lo1 == lo1 && cc.hi1 == hi1 && cc.lo2 == lo2 && cc.hi2 == hi2 && cc.S == S && cc.kind == p->cmp_kind;
     if (!cached) {
         KernelTimer kt(c, D2G_T_CMP_PREP);
         cc.valid = true; cc.regs = base.regs; cc.lo1 = lo1; cc.hi1 = hi1; cc.lo2 = lo2; cc.hi2 = hi2; cc.S = S; cc.kind = p->cmp_kind;
-        CU(cudaMemsetAsync(flag, 0, 4, st));
         CU(cudaMemsetAsync(c->c16codes.p, 0, code_bytes, st));
-        fill_offsets_kernel<<<(S + 1 + 255) / 256, 256, 0, st>>>(offs, S, U);
-        const dim3 gk((unsigned)((U + 31) / 32), (S + 31) / 32);
-        if (counts_gtlt(p->cmp_kind)) c16_keys_kernel<0><<<gk, 256, 0, st>>>(j, kA, iA, flag);
-        else c16_keys_kernel<1><<<gk, 256, 0, st>>>(j, kA, iA, flag);
-        size_t need = 0;
-        cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, kA, kB, iA, iB, (int)items, (int)S, offs, offs + 1, 0, 64, st);
-        if (int rc = c->wtmp.reserve(need + 256)) return rc;
-        size_t tbytes = c->wtmp.cap;
-        CU(cub::DeviceSegmentedRadixSort::SortPairs(c->wtmp.p, tbytes, kA, kB, iA, iB, (int)items, (int)S, offs, offs + 1, 0, 64, st));
-        c16_rank_kernel<<<S, 256, 0, st>>>(j, kB, iB, c->c16codes.as<uint16_t>(), flag);
-        c->launches += 3 + 8;
-        CU(cudaGetLastError());
+        const bool use_global = gl.valid && gl.regs == base.regs && gl.S == S && gl.kind == p->cmp_kind && lo1 >= gl.g0 && hi1 <= gl.g0 + gl.N &&
+                                (!two || (lo2 >= gl.g0 && hi2 <= gl.g0 + gl.N));
+        if (use_global) {
+            const size_t smem = 2 * ((gl.N + 31) / 32) * 4;
+            CU(cudaFuncSetAttribute(c16_local_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c16_local_codes_kernel<<<S, 256, smem, st>>>(j, c->c16grank.as<uint32_t>(), gl.g0, (uint32_t)gl.N, c->c16codes.as<uint16_t>());
+            c->launches++;
+            CU(cudaGetLastError());
+        } else {
+            CU(cudaMemsetAsync(flag, 0, 4, st));
+            if (int rc = c16_sort_rank(c, p, j, c->c16codes.as<uint16_t>(), nullptr, flag)) return rc;
+        }
     }
+    (void)U;
     C16Args a;
     a.codes = c->c16codes.as<uint32_t>(); a.KP = j.KP;
     auto view = [&](uint64_t lo, uint64_t hi, uint64_t rlo, uint32_t rpos0, uint32_t &blk0, uint32_t &n, uint64_t &g0) {
@@ -878,6 +929,12 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     auto up64 = [](uint64_t x) { return (x + 63) / 64 * 64; };
     if (cb <= r0 && r1 <= ce && nC <= M) return run_cmp16_job(c, p, a, cb, ce, 0, 0, r0, r1, cb, ce);
     if (up64(nR) + nC <= M) return run_cmp16_job(c, p, a, r0, r1, cb, ce, r0, r1, cb, ce);
+    // more than one job: rank everything once (u32 ranks), jobs derive their codes from the ranks
+    {
+        const uint64_t g0 = std::min(r0, cb), g1 = std::max(r1, ce), N = g1 - g0;
+        const bool fits = 2 * ((N + 31) / 32) * 4 <= 200 * 1024 && N < 0xFFFFFFF0ULL && !getenv("D2G_C16_NO_GLOBAL");   // bitmap + prefix in shared memory
+        if (fits) { if (int rc = c16_build_global(c, p, regs_d, g0, N)) return rc; }
+    }
     uint64_t BR, BC;
     if (p->shape == D2G_SYMMETRIC) BR = BC = M / 2;
     else if (up64(nR) <= M / 2) { BR = nR; BC = (M - up64(nR)) / 64 * 64; }
@@ -1003,7 +1060,7 @@ int d2g_cmp_rows_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *regs_d, 
     if (int rc = check_cmp_params(p)) return rc;
     if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
     CU(cudaSetDevice(c->device));
-    c->c16cache.valid = false;
+    c->c16cache.valid = false; c->c16g.valid = false;
     d2g::CmpConsts k;
     if (int rc = make_consts(c, p, &k)) return rc;
     return launch_cmp(c, p, k, regs_d, cards_d, r0, r1, out_d, nullptr, nullptr);
@@ -1015,7 +1072,7 @@ int d2g_cmp_rows_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *regs_d, 
 static int cmp_blocks(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards,
                       uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user, float *direct_out) {
     CU(cudaSetDevice(c->device));
-    c->c16cache.valid = false;
+    c->c16cache.valid = false; c->c16g.valid = false;
     const uint32_t S = p->sketchsize;
     if (int rc = c->cregs.reserve(p->n * S * 8)) return rc;
     if (int rc = c->ccards.reserve(p->n * 8)) return rc;
@@ -1097,7 +1154,7 @@ int d2g_cmp_counts(d2g_ctx *c, uint32_t S, int32_t cmp_kind, const double *rows,
     d2g_cmp_params p{};
     p.sketchsize = S; p.cmp_kind = cmp_kind; p.measure = D2G_SIMILARITY; p.k = 31; p.shape = D2G_PANEL; p.n = nr + nc; p.nq = nc;
     if (int rc = check_cmp_params(&p)) return rc;
-    c->c16cache.valid = false;
+    c->c16cache.valid = false; c->c16g.valid = false;
     if (int rc = c->cregs.reserve(p.n * S * 8)) return rc;
     CU(cudaMemcpyAsync(c->cregs.p, rows, nr * S * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->cregs.as<double>() + nr * S, cols, nc * S * 8, cudaMemcpyHostToDevice, c->stream));

@@ -296,13 +296,16 @@ def test_compare_full_size_properties(cmp_path):
 
 
 @pytest.mark.parametrize("shape", ["symmetric", "asymmetric", "panel"])
-@pytest.mark.parametrize("maxjob", [256, 384])
-def test_compare_codes_blocked_jobs(shape, maxjob, monkeypatch):
+@pytest.mark.parametrize("maxjob,global_ranks", [(256, True), (384, True), (384, False)])
+def test_compare_codes_blocked_jobs(shape, maxjob, global_ranks, monkeypatch):
     """Order-code path with the per-job sketch limit forced down so one call is split into many block-pair
-    jobs (diagonal, off-diagonal, ragged last blocks), streamed in row ranges."""
+    jobs (diagonal, off-diagonal, ragged last blocks), streamed in row ranges.  Jobs take their codes from
+    global ranks computed once per call, or (global_ranks False) sort their own sketches."""
     from dashing2_b200 import synth
     monkeypatch.setenv("D2G_CMP_PATH", "codes")
     monkeypatch.setenv("D2G_C16_MAXJOB", str(maxjob))
+    if not global_ranks:
+        monkeypatch.setenv("D2G_C16_NO_GLOBAL", "1")
     n, nq, S = 1000, 390, 130
     regs, cards = synth.synthetic_sketches(n, S, seed=77, n_families=9)
     c = ctx()
