@@ -342,14 +342,23 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                     if (total) {
                         int base = 0;
                         if (lane == 0) base = atomicAdd(scount, total);
-                        int slot = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
-                        #pragma unroll
-                        for (int j = 0; j < SK_PPT; ++j)
-                            if ((emask >> j) & 1u) {
-                                if (slot < SK_SCAP) stage[slot] = mn[j];
-                                else { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
-                                ++slot;
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        int slot = base + incl - cnt;
+                        if (base + total <= SK_SCAP) {                 // warp-uniform: plain predicated stores
+                            #pragma unroll
+                            for (int j = 0; j < SK_PPT; ++j) {
+                                if ((emask >> j) & 1u) stage[slot] = mn[j];
+                                slot += (emask >> j) & 1u;
                             }
+                        } else {
+                            #pragma unroll
+                            for (int j = 0; j < SK_PPT; ++j)
+                                if ((emask >> j) & 1u) {
+                                    if (slot < SK_SCAP) stage[slot] = mn[j];
+                                    else { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
+                                    ++slot;
+                                }
+                        }
                     }
                 }
             }
