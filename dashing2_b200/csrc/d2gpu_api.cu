@@ -222,7 +222,7 @@ d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, c
     d2g::SketchArgs a;
     a.seq = reinterpret_cast<const uint8_t *>(seq_d); a.rec_off = rec_off_d; a.rec_entity = rec_ent_d;
     a.n_rec = n_rec; a.total_len = total_len; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
-    a.pos_base = rg.pos_base; a.pos_end = rg.pos_end; a.ent_base = rg.ent_base;
+    a.pos_base = rg.pos_base; a.pos_end = rg.pos_end; a.ent_base = rg.ent_base; a.ent_state = nullptr; a.want_state = 0;
     a.m = m; a.tile_stride = 1; a.score_slots = d2g::sketch_score_slots(p->k, p->w);
     a.span = pick_span(c, rg.pos_end - rg.pos_base, m);
     return a;
@@ -273,39 +273,57 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const 
     const uint32_t m = p->sketchsize;
     const uint64_t nreg = (uint64_t)n_ent * m;
     const uint64_t ovf_cap = 1ULL << 20;
-    // aux layout: maxrv[nreg] | keys[nreg] | T[n_ent] | rvmin[n_ent] | ovf_count[1] (+pad) | ovf[2*ovf_cap]
-    const size_t aux_bytes = (nreg * 2 + (uint64_t)n_ent * 2 + 2 + 2 * ovf_cap) * 8;
+    // aux layout: maxrv[nreg] | keys[nreg] | T[n_ent] | Tguess[n_ent] | npos[n_ent] | state[n_ent] (u32, padded) | ovf_count, n_redo | ovf[2*ovf_cap]
+    const size_t aux_bytes = (nreg * 2 + (uint64_t)n_ent * 4 + 4 + 2 * ovf_cap) * 8;
     if (int rc = c->aux.reserve(aux_bytes)) return rc;
     uint64_t *maxrv = c->aux.as<uint64_t>(), *keys = maxrv + nreg;
-    double *T = reinterpret_cast<double *>(keys + nreg);
-    uint64_t *rvmin = reinterpret_cast<uint64_t *>(T + n_ent);
-    unsigned long long *ovf_count = reinterpret_cast<unsigned long long *>(rvmin + n_ent);
-    uint64_t *ovf = reinterpret_cast<uint64_t *>(ovf_count + 2);
-    CU(cudaMemsetAsync(maxrv, 0, nreg * 8, c->stream));
-    CU(cudaMemsetAsync(ovf_count, 0, 16, c->stream));
+    double *T = reinterpret_cast<double *>(keys + nreg), *Tguess = T + n_ent;
+    unsigned long long *npos = reinterpret_cast<unsigned long long *>(Tguess + n_ent);
+    uint32_t *state = reinterpret_cast<uint32_t *>(npos + n_ent);
+    unsigned long long *ovf_count = reinterpret_cast<unsigned long long *>(npos + 2 * (uint64_t)n_ent);
+    unsigned int *n_redo = reinterpret_cast<unsigned int *>(ovf_count + 1);
+    uint64_t *ovf = reinterpret_cast<uint64_t *>(ovf_count + 4);
+    CU(cudaMemsetAsync(npos, 0, (uint64_t)n_ent * 8, c->stream));
+    CU(cudaMemsetAsync(ovf_count, 0, 32, c->stream));
     fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, c->stream>>>(keys, nreg, d2g::FSS_KEY_EMPTY);
     c->launches++;
     const bool windowed = p->w > p->k;
     if (work_len && n_rec) {
         d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m, rg);
-        // Boot on every stride-th tile: a cheap first bound T per entity so the first walks of the main pass are
-        // short; the main kernel keeps tightening it.  n_eff = elements fed to the sketch per entity (with
-        // minimizer windows only ~2/(window+1) of the positions emit).  Cost model per position: 1/stride for the
-        // boot pass plus the extra walkers a looser threshold admits => stride ~ sqrt(n_eff / (2 m ln m)).
-        const double per_ent = (double)work_len / std::max(1u, n_ent);
-        const double n_eff = windowed ? per_ent * 2. / (p->w - p->k + 2) : per_ent;
-        const double mlnm = (double)m * std::log((double)m + 2.);
-        uint32_t stride = 1;
-        while (stride < 64 && (double)(stride * 2) <= std::sqrt(n_eff / (2. * mlnm)) * 4.) stride *= 2;
-        if (const char *ev = getenv("D2G_FSS_BOOT_STRIDE")) stride = (uint32_t)std::max(1, atoi(ev));   // tuning knob
-        a.tile_stride = stride;
-        d2g::FssBootConsumer::Params bp{maxrv, d2g::make_fastmod32(m), m};
-        if (int rc = launch_sketch<d2g::FssBootConsumer>(c, a, bp, windowed, D2G_T_SKETCH_BOOT)) return rc;
-        d2g::fss_threshold_kernel<<<n_ent, 256, 0, c->stream>>>(maxrv, m, T);
-        c->launches++;
-        a.tile_stride = 1;
+        const int wsz = windowed ? p->w - p->k + 1 : 1;
         d2g::FssMainConsumer::Params mp{keys, T, ovf, ovf_count, ovf_cap, m};
+        // Pass A: bound guessed from the sequence length, verified afterwards (fss_kernels.cuh); only inputs with many elements per register
+        d2g::fss_entity_positions_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, c->stream>>>(rec_off_d, rec_ent_d, n_rec, rg.ent_base, windowed ? p->w : p->k, npos);
+        d2g::fss_guess_kernel<<<(n_ent + 255) / 256, 256, 0, c->stream>>>(npos, n_ent, m, wsz, getenv("D2G_FSS_NO_GUESS") ? 0 : 1, T, Tguess, state);
+        c->launches += 2;
+        a.ent_state = state; a.want_state = 0;
         if (int rc = launch_sketch<d2g::FssMainConsumer>(c, a, mp, windowed)) return rc;
+        d2g::fss_verify_kernel<<<n_ent, 256, 0, c->stream>>>(keys, m, Tguess, state, n_redo);
+        c->launches++;
+        unsigned int h_redo = 0;
+        CU(cudaMemcpyAsync(&h_redo, n_redo, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (getenv("D2G_DEBUG")) fprintf(stderr, "[d2g] fss: %u of %u entities take the boot pass\n", h_redo, n_ent);
+        if (h_redo) {
+            // Pass B (small inputs, failed guesses): boot on every stride-th tile gives a first bound T per entity so the first
+            // walks of the main pass are short; the main kernel keeps tightening it.  n_eff = elements fed to the sketch per
+            // entity (with minimizer windows only ~2/(window+1) of the positions emit).  Cost model per position: 1/stride for
+            // the boot pass plus the extra walkers a looser threshold admits => stride ~ sqrt(n_eff / (2 m ln m)).
+            CU(cudaMemsetAsync(maxrv, 0, nreg * 8, c->stream));
+            const double per_ent = (double)work_len / std::max(1u, n_ent);
+            const double n_eff = windowed ? per_ent * 2. / (p->w - p->k + 2) : per_ent;
+            const double mlnm = (double)m * std::log((double)m + 2.);
+            uint32_t stride = 1;
+            while (stride < 64 && (double)(stride * 2) <= std::sqrt(n_eff / (2. * mlnm)) * 4.) stride *= 2;
+            if (const char *ev = getenv("D2G_FSS_BOOT_STRIDE")) stride = (uint32_t)std::max(1, atoi(ev));   // tuning knob
+            a.tile_stride = stride; a.want_state = 1;
+            d2g::FssBootConsumer::Params bp{maxrv, d2g::make_fastmod32(m), m};
+            if (int rc = launch_sketch<d2g::FssBootConsumer>(c, a, bp, windowed, D2G_T_SKETCH_BOOT)) return rc;
+            d2g::fss_threshold_kernel<<<n_ent, 256, 0, c->stream>>>(maxrv, m, T, state);
+            c->launches++;
+            a.tile_stride = 1;
+            if (int rc = launch_sketch<d2g::FssMainConsumer>(c, a, mp, windowed)) return rc;
+        }
         // long walks (normally none): dense permutation state per thread slot
         uint64_t nslots = std::min<uint64_t>(4096, (256ULL << 20) / ((uint64_t)m * 8));
         nslots = std::max<uint64_t>(32, nslots / 32 * 32);

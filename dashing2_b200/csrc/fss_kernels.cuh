@@ -64,10 +64,52 @@ struct FssBootConsumer {
     }
 };
 
+// ---- guess and verify: the bound T without a boot pass ---------------------------------------------
+// Every element reaches register i at a time that is marginally Exp(1) (the m arrival times of one element are the
+// order statistics of m iid exponentials), so a register of n elements is Exp(n) and the largest of m registers is about
+// (ln m + gamma) / n.  For inputs with many elements per register the bound is GUESSED as three times that, with n
+// estimated from the sequence length (P(max > guess) ~ m^-2 when the estimate is right), and VERIFIED afterwards: if every
+// final register is <= the guess, nothing the guess pruned could have lowered a register and the result is exact; an
+// entity that fails (repetitive sequence: far fewer distinct elements than estimated) is redone through the boot pass.
+__global__ void fss_entity_positions_kernel(const uint64_t *rec_off, const uint32_t *rec_entity, uint64_t n_rec, uint32_t ent_base, int need,
+                                            unsigned long long *npos) {
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint64_t l = rec_off[r + 1] - rec_off[r];
+    if (l >= (uint64_t)need) atomicAdd(npos + (rec_entity[r] - ent_base), (unsigned long long)(l - need + 1));
+}
+// state: 0 = guessed bound (main pass A), 1 = boot pass + main pass B
+__global__ void fss_guess_kernel(const unsigned long long *npos, uint32_t n_ent, uint32_t m, int wsz, int allow_guess, double *T, double *Tguess, uint32_t *state) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    const double n_est = (double)npos[e] * (wsz > 1 ? 2. / (wsz + 1.) : 1.);
+    const double lm = log((double)m) + 0.5772156649;
+    const bool guess = allow_guess && n_est >= 4. * (double)m * lm;
+    const double g = guess ? 3. * lm / n_est : 1.7976931348623157e308;
+    T[e] = g; Tguess[e] = g; state[e] = guess ? 0u : 1u;
+}
+// one CTA per entity in state 0: exact iff every register is filled and the largest is <= the guess; else -> state 1, registers cleared
+__global__ void fss_verify_kernel(uint64_t *keys, uint32_t m, const double *Tguess, uint32_t *state, unsigned int *n_redo) {
+    __shared__ uint64_t red[256];
+    const uint32_t ent = blockIdx.x;
+    if (state[ent] != 0) { if (threadIdx.x == 0) atomicAdd(n_redo, 1u); return; }
+    uint64_t mx = 0;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) mx = max(mx, keys[(uint64_t)ent * m + i]);
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if ((int)threadIdx.x < s) red[threadIdx.x] = max(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    const bool ok = red[0] < FSS_KEY_EMPTY && dunkey(red[0]) <= Tguess[ent];
+    __syncthreads();
+    if (ok) return;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) keys[(uint64_t)ent * m + i] = FSS_KEY_EMPTY;
+    if (threadIdx.x == 0) { state[ent] = 1; atomicAdd(n_redo, 1u); }
+}
+
 // one CTA per entity: T = max_i ev_0(maxrv_i) (DBL_MAX when some register was never hit by the sample)
-__global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *T) {
+__global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *T, const uint32_t *state) {
     __shared__ double red[256];
     const uint32_t ent = blockIdx.x;
+    if (state && state[ent] != 1) return;
     const double bv0 = -1. / m;
     double mx = 0.;
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {

@@ -39,6 +39,8 @@ struct SketchArgs {
     uint64_t total_len;          // bytes of seq that may be read (bound of the 16-byte tile loads)
     uint64_t pos_base, pos_end;  // this launch covers start positions [pos_base, pos_end); rec_off values are absolute
     uint32_t ent_base;           // subtracted from rec_entity: the consumer's registers start at this entity
+    const uint32_t *ent_state;   // optional [entities of this launch]: only records whose entity has ent_state == want_state are processed
+    uint32_t want_state;
     uint64_t span;               // start positions per CTA (multiple of SK_TILE)
     int k, w, canon;
     uint64_t xormask;
@@ -219,6 +221,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
         const uint64_t p1 = min(span_hi, re - need + 1);   // owned, usable start positions [p0, p1)
         if (p0 >= p1) continue;
         const uint32_t ent = a.rec_entity[r] - a.ent_base;
+        if (a.ent_state && a.ent_state[ent] != a.want_state) continue;
         if (ent != cur_ent) {
             if (cur_ent != 0xFFFFFFFFu) {
                 __syncthreads();

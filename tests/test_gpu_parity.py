@@ -107,6 +107,35 @@ def test_sketch_matches_oracle_seeded(mode, S, k, w, tmp_path):
             np.testing.assert_allclose(r["card"][e], L.d2o_css_card(regs, S), rtol=1e-12)
 
 
+@pytest.mark.parametrize("S,w", [(64, -1), (64, 40), (256, -1), (128, 51)])
+def test_fss_guessed_bound_and_its_fallback(S, w, monkeypatch):
+    """Full SetSketch takes its pruning bound from a guess (sequence length) that is verified afterwards.  Entities:
+    random genomes (guess holds), a short tandem repeat (far fewer distinct elements than the length suggests: the guess
+    fails and the entity is redone through the boot pass), inputs too small to guess for.  All bit-identical to the
+    oracle, and to the library with guessing disabled."""
+    from dashing2_b200 import synth
+    k = 31
+    rng = np.random.default_rng(S + 7)
+    files = [[s.tobytes()] for _, s in synth.family_genomes(3, 150_000, seed=40 + S)]
+    unit = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 173))
+    files.append([unit * 900])                                       # ~156 kb of a 173-bp repeat
+    files.append([unit * 400, files[0][0][:60_000]])                 # repeat + some random sequence
+    files.append([files[1][0][:3000]])                               # small input
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    p = c.params(mode="fss", S=S, k=k, w=w)
+    r = c.sketch_batch(seq, off, ent, len(files), p)
+    monkeypatch.setenv("D2G_FSS_NO_GUESS", "1")
+    r0 = c.sketch_batch(seq, off, ent, len(files), p)
+    assert np.array_equal(u64(r["sig"]), u64(r0["sig"])) and np.array_equal(u64(r["card"]), u64(r0["card"]))
+    L = O.lib()
+    for e, recs in enumerate(files):
+        hv = np.concatenate([O.hash_stream(x, k, w) for x in recs])
+        regs = np.empty(2 * S - 1, dtype=np.float64)
+        L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), None)
+        assert np.array_equal(u64(r["sig"][e]), u64(regs[:S])), (S, w, e)
+
+
 @pytest.mark.parametrize("mode,S,k,w,thr", [("pmh", 256, 31, -1, 0), ("bmh", 256, 31, -1, 0), ("pmh", 1024, 21, 40, 0), ("bmh", 64, 21, 40, 0),
                                              ("pmh", 512, 31, -1, 1), ("bmh", 8192, 31, -1, 0), ("pmh", 8192, 31, -1, 0)])
 def test_weighted_sketch_matches_oracle_seeded(mode, S, k, w, thr):
