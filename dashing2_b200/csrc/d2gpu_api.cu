@@ -1293,7 +1293,7 @@ extern "C" int d2g_lsh_topk(d2g_ctx *c, const d2g_cmp_params *p, const double *r
         else d2g::lsh_refine_kernel<1><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(regs_d, cards_d, n, seg, lsz, lst, k, mult);
         c->launches++;
     }
-    d2g::lsh_trim_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seg, n, (uint32_t)topk, is_dist, lst, lsz);
+    d2g::lsh_trim_kernel<<<(unsigned)((n + d2g::LSH_TRIM_WARPS - 1) / d2g::LSH_TRIM_WARPS), d2g::LSH_TRIM_WARPS * 32, 0, st>>>(seg, n, (uint32_t)topk, is_dist, lst, lsz);
     c->launches++;
     // 6. CSR: indptr = exclusive scan of list sizes
     {

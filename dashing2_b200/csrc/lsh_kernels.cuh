@@ -154,8 +154,9 @@ __global__ void lsh_refine_kernel(const double *regs, const double *cards, uint6
     const uint32_t id = lst[w].id;
     const double *A = regs + x * c.S, *B = regs + (uint64_t)id * c.S;
     uint32_t g = 0, l = 0;
-    for (uint32_t r = lane; r < c.S; r += 32) {
-        const double a = A[r], b = B[r];
+    #pragma unroll 8
+    for (uint32_t r = lane; r < c.S; r += 32) {            // 8 independent 256-byte row segments in flight per warp
+        const double a = __ldg(A + r), b = __ldg(B + r);
         if (KIND == 0) { g += a > b; l += a < b; } else g += __double_as_longlong(a) != __double_as_longlong(b);
     }
     #pragma unroll
@@ -163,16 +164,79 @@ __global__ void lsh_refine_kernel(const double *regs, const double *cards, uint6
     if (lane == 0) lst[w].d = mult * finalize_pair(c, KIND == 0 ? g : c.S - g, l, cards[x], cards[id]);
 }
 
-// one thread per list: sort by (d, id), drop zero similarities, keep top-k plus ties, undo the sign (refine.cpp:30-74)
-__global__ void lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
-    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+// one WARP per list: sort by (d, id), drop zero similarities, keep top-k plus ties, undo the sign (refine.cpp:30-74).
+// Lists of up to LSH_TRIM_CAP entries are sorted by a bitonic network in shared memory on 64-bit keys
+// (order-preserving image of d, then id); longer ones (the bounded-heap rule keeps lists near 3.5 K) fall back to an
+// insertion sort by one lane.
+constexpr int LSH_TRIM_CAP = 1024, LSH_TRIM_WARPS = 4;
+// key order == nb_less order: -0.0 and +0.0 compare equal there, so zeros share one key image and the sign of a zero
+// travels in bit 0 of the low word, below the id (ids are < 2^31)
+__device__ __forceinline__ uint64_t nb_key(const Nb &e) {
+    const uint32_t raw = __float_as_uint(e.d);
+    uint32_t f = e.d == 0.f ? 0u : raw;
+    f = (f >> 31) ? ~f : (f | 0x80000000u);
+    return ((uint64_t)f << 32) | ((uint64_t)e.id << 1) | (e.d == 0.f ? raw >> 31 : 0u);
+}
+__device__ __forceinline__ Nb nb_unkey(uint64_t k) {
+    uint32_t f = (uint32_t)(k >> 32);
+    f = (f >> 31) ? (f & 0x7fffffffu) : ~f;
+    Nb e; e.id = (uint32_t)k >> 1;
+    e.d = __uint_as_float(f);
+    if (e.d == 0.f && (k & 1u)) e.d = -0.f;
+    return e;
+}
+__global__ void __launch_bounds__(LSH_TRIM_WARPS * 32)
+lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
+    __shared__ uint64_t buf[LSH_TRIM_WARPS][LSH_TRIM_CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t x = blockIdx.x * (uint64_t)LSH_TRIM_WARPS + wid;
     if (x >= n) return;
     Nb *L = lst + seg[x]; uint32_t nl = lsize[x];
-    for (uint32_t i = 1; i < nl; ++i) { const Nb it = L[i]; uint32_t j = i; while (j && nb_less(it, L[j - 1])) { L[j] = L[j - 1]; --j; } L[j] = it; }
-    if (!is_dist) { uint32_t j = 0; while (j < nl && L[j].d != 0.f) ++j; nl = j; }
-    if (topk < nl) { const float bs = L[topk - 1].d; uint32_t j = topk; while (j < nl && !(L[j].d > bs)) ++j; nl = j; }
-    if (!is_dist) for (uint32_t j = 0; j < nl; ++j) L[j].d = -L[j].d;
-    lsize[x] = nl;
+    if (nl > LSH_TRIM_CAP) {
+        if (lane == 0) {
+            for (uint32_t i = 1; i < nl; ++i) { const Nb it = L[i]; uint32_t j = i; while (j && nb_less(it, L[j - 1])) { L[j] = L[j - 1]; --j; } L[j] = it; }
+            if (!is_dist) { uint32_t j = 0; while (j < nl && L[j].d != 0.f) ++j; nl = j; }
+            if (topk < nl) { const float bs = L[topk - 1].d; uint32_t j = topk; while (j < nl && !(L[j].d > bs)) ++j; nl = j; }
+            if (!is_dist) for (uint32_t j = 0; j < nl; ++j) L[j].d = -L[j].d;
+            lsize[x] = nl;
+        }
+        return;
+    }
+    uint64_t *B = buf[wid];
+    uint32_t P = 32; while (P < nl) P <<= 1;
+    for (uint32_t i = lane; i < P; i += 32) B[i] = i < nl ? nb_key(L[i]) : ~0ULL;
+    __syncwarp();
+    for (uint32_t k = 2; k <= P; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < P; i += 32) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const uint64_t a = B[i], c = B[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) { B[i] = c; B[l] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    // sorted ascending.  Similarities are stored negated: zeros sort last and are dropped; distances keep theirs.
+    uint32_t keep = nl;
+    if (!is_dist) {
+        uint32_t nz = 0;
+        for (uint32_t i = lane; i < nl; i += 32) nz += nb_unkey(B[i]).d != 0.f;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        keep = nz;
+    }
+    if (topk < keep) {                       // everything tied with the k-th entry stays (refine.cpp:39-42)
+        const float bs = nb_unkey(B[topk - 1]).d;
+        uint32_t le = 0;
+        for (uint32_t i = lane; i < keep; i += 32) le += !(nb_unkey(B[i]).d > bs);
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) le += __shfl_xor_sync(0xffffffffu, le, o);
+        keep = le;
+    }
+    for (uint32_t i = lane; i < keep; i += 32) { Nb e = nb_unkey(B[i]); if (!is_dist) e.d = -e.d; L[i] = e; }
+    if (lane == 0) lsize[x] = keep;
 }
 
 __global__ void lsh_csr_kernel(const uint32_t *seg, const uint32_t *lsize, const uint64_t *indptr, uint64_t n, const Nb *lst, uint32_t *idx, float *val) {
