@@ -310,6 +310,46 @@ c16_rank_kernel(const C16Job j, const uint64_t *keys_sorted, const uint32_t *idx
     }
 }
 
+// (2b) jobs that only need to know WHICH registers differ (MODE 1) and are small enough for a shared-memory table skip
+//      the sort: any injective code per register position will do, and the slot a value lands in in an open-addressing
+//      table of the position's values is one.  A CTA handles four adjacent register positions one after the other (one
+//      32-byte sector of a sketch row serves all four), 64-bit keys, linear probing, code = rank_to_half(slot).
+constexpr uint32_t C16_HASH_MAX_SKETCHES = 16384;     // table of <= 24576 slots (192 KiB) at load <= 2/3
+constexpr uint64_t C16_HASH_EMPTY = ~0ULL;            // KIND 0: an unused NaN image; KIND 1: handled as a value of its own
+template <int KIND>
+__global__ void __launch_bounds__(512)
+c16_hash_codes_kernel(const C16Job j, uint32_t TS, uint16_t *codes16, int *nan_flag) {
+    extern __shared__ unsigned long long hc_tab[];
+    const uint32_t U = j.nA + j.nB;
+    bool nan = false;
+    for (uint32_t s = blockIdx.x * 4; s < min(j.S, blockIdx.x * 4 + 4); ++s) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < TS; i += blockDim.x) hc_tab[i] = C16_HASH_EMPTY;
+        __syncthreads();
+        for (uint32_t u = threadIdx.x; u < U; u += blockDim.x) {
+            const double d = __ldg(j.regs + job_sketch(j, u) * j.S + s);
+            uint64_t key;
+            if (KIND == 0) { nan |= d != d; key = dkey(d == 0. ? 0. : d); }
+            else key = (uint64_t)__double_as_longlong(d);
+            uint32_t slot;
+            if (key == C16_HASH_EMPTY) slot = TS;                        // cannot live in the table: its own code
+            else {
+                uint64_t h = key * 0x9E3779B97F4A7C15ULL; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL;
+                slot = (uint32_t)(((h >> 32) * TS) >> 32);
+                for (;;) {
+                    const unsigned long long old = atomicCAS(hc_tab + slot, (unsigned long long)C16_HASH_EMPTY, (unsigned long long)key);
+                    if (old == C16_HASH_EMPTY || old == key) break;
+                    if (++slot == TS) slot = 0;
+                }
+            }
+            const uint32_t pos = job_pos(j, u);
+            const uint64_t word = ((uint64_t)(pos / C16_BLK) * j.KP + (s >> 1)) * C16_BLK + (pos % C16_BLK);
+            codes16[word * 2 + (s & 1)] = rank_to_half(slot);
+        }
+    }
+    if (nan) *nan_flag = 1;
+}
+
 // (3) multi-job comparisons: global dense ranks (u32 [S][N], sketch g at column g - g0) -> codes of one job.
 //     One CTA per register position: presence bitmap of the ranks the job's sketches hold, exclusive prefix popcount,
 //     local rank = number of present ranks below.  Shared memory: 2 * ceil(N / 32) words.

@@ -79,7 +79,7 @@ struct d2g_ctx {
     DevBuf cregs, ccards, cout, clut, clut80, ctmp, cktmp;         // compare scratch
     DevBuf c16buf, c16codes, c16grank, c16flag;                    // order-code compare scratch (keys, sort buffers, codes, global ranks)
     struct { bool valid = false; const double *regs = nullptr; uint64_t g0 = 0, N = 0; uint32_t S = 0; int kind = 0; } c16g;   // global ranks built earlier in the same API call
-    struct { bool valid = false; const double *regs = nullptr; uint64_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0; uint32_t S = 0; int kind = 0; } c16cache; // codes built earlier in the same API call
+    struct { bool valid = false; const double *regs = nullptr; uint64_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0; uint32_t S = 0; int kind = 0, mode = 0; } c16cache; // codes built earlier in the same API call
     PinBuf pin[2];
     cudaEvent_t ev[2] = {nullptr, nullptr}, evd[2] = {nullptr, nullptr};
     uint32_t lut_S = 0; int lut_k = -1;
@@ -864,12 +864,31 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
     cudaStream_t st = c->stream;
     auto &cc = c->c16cache;
     auto &gl = c->c16g;
-    const bool cached = cc.valid && cc.regs == base.regs && cc.lo1 == lo1 && cc.hi1 == hi1 && cc.lo2 == lo2 && cc.hi2 == hi2 && cc.S == S && cc.kind == p->cmp_kind;
+    // gt/lt registers with power-of-two S and no raw counts wanted: the != count alone determines the result
+    const bool pow2 = (S & (S - 1)) == 0;
+    const int mode = (!counts_gtlt(p->cmp_kind) || (p->cmp_kind == D2G_CMP_GTLT && pow2 && !base.c0_out && !getenv("D2G_C16_NO_NE"))) ? 1 : 0;
+    const bool cached = cc.valid && cc.regs == base.regs && cc.lo1 == lo1 && cc.hi1 == hi1 && cc.lo2 == lo2 && cc.hi2 == hi2 && cc.S == S && cc.kind == p->cmp_kind && cc.mode == mode;
     if (!cached) {
         KernelTimer kt(c, D2G_T_CMP_PREP);
-        cc.valid = true; cc.regs = base.regs; cc.lo1 = lo1; cc.hi1 = hi1; cc.lo2 = lo2; cc.hi2 = hi2; cc.S = S; cc.kind = p->cmp_kind;
+        cc.valid = true; cc.regs = base.regs; cc.lo1 = lo1; cc.hi1 = hi1; cc.lo2 = lo2; cc.hi2 = hi2; cc.S = S; cc.kind = p->cmp_kind; cc.mode = mode;
         CU(cudaMemsetAsync(c->c16codes.p, 0, code_bytes, st));
-        const bool use_global = gl.valid && gl.regs == base.regs && gl.S == S && gl.kind == p->cmp_kind && lo1 >= gl.g0 && hi1 <= gl.g0 + gl.N &&
+        const bool use_hash = mode == 1 && U <= C16_HASH_MAX_SKETCHES && !getenv("D2G_C16_NO_HASH");
+        if (use_hash) {
+            // != only: injective codes suffice -> open-addressing table per register position, no sort
+            const uint32_t TS = (uint32_t)std::max<uint64_t>(64, U + U / 2);
+            const size_t smem = (size_t)TS * 8;
+            CU(cudaMemsetAsync(flag, 0, 4, st));
+            if (counts_gtlt(p->cmp_kind)) {
+                CU(cudaFuncSetAttribute(c16_hash_codes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                c16_hash_codes_kernel<0><<<(S + 3) / 4, 512, smem, st>>>(j, TS, c->c16codes.as<uint16_t>(), flag);
+            } else {
+                CU(cudaFuncSetAttribute(c16_hash_codes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                c16_hash_codes_kernel<1><<<(S + 3) / 4, 512, smem, st>>>(j, TS, c->c16codes.as<uint16_t>(), flag);
+            }
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        const bool use_global = !use_hash && gl.valid && gl.regs == base.regs && gl.S == S && gl.kind == p->cmp_kind && lo1 >= gl.g0 && hi1 <= gl.g0 + gl.N &&
                                 (!two || (lo2 >= gl.g0 && hi2 <= gl.g0 + gl.N));
         if (use_global) {
             const size_t smem = 2 * ((gl.N + 31) / 32) * 4;
@@ -877,7 +896,7 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
             c16_local_codes_kernel<<<S, 256, smem, st>>>(j, c->c16grank.as<uint32_t>(), gl.g0, (uint32_t)gl.N, c->c16codes.as<uint16_t>());
             c->launches++;
             CU(cudaGetLastError());
-        } else {
+        } else if (!use_hash) {
             CU(cudaMemsetAsync(flag, 0, 4, st));
             if (int rc = c16_sort_rank(c, p, j, c->c16codes.as<uint16_t>(), nullptr, flag)) return rc;
         }
@@ -899,9 +918,6 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
     const uint64_t grid = tiles_i * a.tiles_j;
     if (grid > 0x7fffffffULL) return fail(D2G_EINVAL, "comparison job too large for one launch");
     {
-        // gt/lt registers with power-of-two S and no raw counts wanted: the != count alone determines the result
-        const bool pow2 = (S & (S - 1)) == 0;
-        const int mode = (!counts_gtlt(p->cmp_kind) || (p->cmp_kind == D2G_CMP_GTLT && pow2 && !base.c0_out && !getenv("D2G_C16_NO_NE"))) ? 1 : 0;
         a.ne_is_gt = (mode == 1 && p->cmp_kind == D2G_CMP_GTLT) ? 1 : 0;
         a.one = 1;
         int acc = 1;
@@ -936,8 +952,11 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     // columns this row range needs; sym_lo lets successive row blocks of one call share one code space
     const uint64_t cb = p->shape == D2G_SYMMETRIC ? std::min(r0, sym_lo) : a.col_base, ce = a.col_base + a.ncols;
     const uint64_t nR = r1 - r0, nC = ce - cb;
-    // path choice: codes pay a per-job sort of the registers, worth it from ~4e9 register comparisons on
-    int path = (double)nR * (double)nC * (double)S >= 4.0e9 ? 1 : 0;
+    // path choice: codes pay a per-job sort of the registers, worth it from ~4e9 register comparisons on; jobs that only
+    // count != and fit the shared-memory table (run_cmp16_job) build their codes in one cheap pass: from ~2e8 on
+    const bool ne_only = !counts_gtlt(p->cmp_kind) || (p->cmp_kind == D2G_CMP_GTLT && (S & (S - 1)) == 0 && !c0_d);
+    const bool hashable = ne_only && nR + nC <= d2g::C16_HASH_MAX_SKETCHES;
+    int path = (double)nR * (double)nC * (double)S >= (hashable ? 2.0e8 : 4.0e9) ? 1 : 0;
     if (const char *ev = getenv("D2G_CMP_PATH")) path = !strcmp(ev, "codes") ? 1 : (!strcmp(ev, "f64") ? 0 : path);
     uint64_t M = 63232;                                                 // sketches per job: <= 63487 ranks, multiple of 128
     if (const char *ev = getenv("D2G_C16_MAXJOB")) M = std::max<uint64_t>(256, std::min<uint64_t>(M, strtoull(ev, nullptr, 10) / 128 * 128));  // test knob

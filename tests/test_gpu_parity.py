@@ -201,10 +201,13 @@ def test_densify_matches_reference_golden():
     assert np.array_equal(c.cmp_matrix(got, den["cards"], p).view(np.uint32), den["mat"].view(np.uint32))
 
 
-@pytest.fixture(params=["f64", "codes"])
+@pytest.fixture(params=["f64", "codes", "codes-sorted"])
 def cmp_path(request, monkeypatch):
-    """Both comparison kernels: the f64 tile kernel and the 16-bit order-code kernel (cmp16_kernels.cuh)."""
-    monkeypatch.setenv("D2G_CMP_PATH", request.param)
+    """Both comparison kernels: the f64 tile kernel and the 16-bit order-code kernel (cmp16_kernels.cuh), the latter with
+    its codes from the shared-memory hash table where only != matters (default) and from the per-register sort."""
+    monkeypatch.setenv("D2G_CMP_PATH", request.param.split("-")[0])
+    if request.param == "codes-sorted":
+        monkeypatch.setenv("D2G_C16_NO_HASH", "1")
     return request.param
 
 
