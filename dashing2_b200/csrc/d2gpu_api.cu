@@ -955,7 +955,7 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     // path choice: codes pay a per-job sort of the registers, worth it from ~4e9 register comparisons on; jobs that only
     // count != and fit the shared-memory table (run_cmp16_job) build their codes in one cheap pass: from ~2e8 on
     const bool ne_only = !counts_gtlt(p->cmp_kind) || (p->cmp_kind == D2G_CMP_GTLT && (S & (S - 1)) == 0 && !c0_d);
-    const bool hashable = ne_only && nR + nC <= d2g::C16_HASH_MAX_SKETCHES;
+    const bool hashable = ne_only && ((cb <= r0 && r1 <= ce) ? nC : nR + nC) <= d2g::C16_HASH_MAX_SKETCHES;
     int path = (double)nR * (double)nC * (double)S >= (hashable ? 2.0e8 : 4.0e9) ? 1 : 0;
     if (const char *ev = getenv("D2G_CMP_PATH")) path = !strcmp(ev, "codes") ? 1 : (!strcmp(ev, "f64") ? 0 : path);
     uint64_t M = 63232;                                                 // sketches per job: <= 63487 ranks, multiple of 128
