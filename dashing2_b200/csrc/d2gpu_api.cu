@@ -964,30 +964,47 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     if (S > 65535 || M < 256) path = 0;                                  // 16-bit counters / degenerate blocks
     if (!path) return launch_cmp_f64(c, p, a, r0, r1, cb, ce, nullptr, 0);
     auto up64 = [](uint64_t x) { return (x + 63) / 64 * 64; };
-    if (cb <= r0 && r1 <= ce && nC <= M) return run_cmp16_job(c, p, a, cb, ce, 0, 0, r0, r1, cb, ce);
-    if (up64(nR) + nC <= M) return run_cmp16_job(c, p, a, r0, r1, cb, ce, r0, r1, cb, ce);
-    // more than one job: rank everything once (u32 ranks), jobs derive their codes from the ranks
-    {
-        const uint64_t g0 = std::min(r0, cb), g1 = std::max(r1, ce), N = g1 - g0;
-        const bool fits = 2 * ((N + 31) / 32) * 4 <= 200 * 1024 && N < 0xFFFFFFF0ULL && !getenv("D2G_C16_NO_GLOBAL");   // bitmap + prefix in shared memory
-        if (fits) { if (int rc = c16_build_global(c, p, regs_d, g0, N)) return rc; }
-    }
-    uint64_t BR, BC;
-    if (p->shape == D2G_SYMMETRIC) BR = BC = M / 2;
-    else if (up64(nR) <= M / 2) { BR = nR; BC = (M - up64(nR)) / 64 * 64; }
-    else if (nC <= M / 2) { BC = nC; BR = (M - nC) / 128 * 128; }
-    else BR = BC = M / 2;
-    for (uint64_t rb = r0; rb < r1; rb += BR) {
-        const uint64_t re = std::min(r1, rb + BR);
-        for (uint64_t cc = cb; cc < ce; cc += BC) {
-            const uint64_t cf = std::min(ce, cc + BC);
-            if (p->shape == D2G_SYMMETRIC && cf <= rb + 1) continue;     // block entirely on/below the diagonal
-            int rc;
-            if (cc == rb && cf == re) rc = run_cmp16_job(c, p, a, rb, re, 0, 0, rb, re, cc, cf);
-            else rc = run_cmp16_job(c, p, a, rb, re, cc, cf, rb, re, cc, cf);
-            if (rc) return rc;
+    // Decomposition into jobs of at most Mj sketches: one range when the rows lie inside the columns, two ranges
+    // otherwise, block pairs when that is too many sketches (diagonal blocks of a symmetric comparison share one range).
+    struct Job { uint64_t lo1, hi1, lo2, hi2, r0, r1, c0, c1; };
+    auto plan = [&](uint64_t Mj, std::vector<Job> &jobs) {
+        jobs.clear();
+        if (cb <= r0 && r1 <= ce && nC <= Mj) { jobs.push_back({cb, ce, 0, 0, r0, r1, cb, ce}); return; }
+        if (up64(nR) + nC <= Mj) { jobs.push_back({r0, r1, cb, ce, r0, r1, cb, ce}); return; }
+        uint64_t BR, BC;
+        if (p->shape == D2G_SYMMETRIC) BR = BC = Mj / 2;
+        else if (up64(nR) <= Mj / 2) { BR = nR; BC = (Mj - up64(nR)) / 64 * 64; }
+        else if (nC <= Mj / 2) { BC = nC; BR = (Mj - nC) / 128 * 128; }
+        else BR = BC = Mj / 2;
+        for (uint64_t rb = r0; rb < r1; rb += BR) {
+            const uint64_t re = std::min(r1, rb + BR);
+            for (uint64_t cc = cb; cc < ce; cc += BC) {
+                const uint64_t cf = std::min(ce, cc + BC);
+                if (p->shape == D2G_SYMMETRIC && cf <= rb + 1) continue;     // block entirely on/below the diagonal
+                if (cc == rb && cf == re) jobs.push_back({rb, re, 0, 0, rb, re, cc, cf});
+                else jobs.push_back({rb, re, cc, cf, rb, re, cc, cf});
+            }
         }
+    };
+    auto job_sketches = [](const Job &j) { return (j.hi1 - j.lo1) + (j.hi2 - j.lo2); };
+    std::vector<Job> jobs, hjobs;
+    plan(M, jobs);
+    const uint64_t g0 = std::min(r0, cb), g1 = std::max(r1, ce), N = g1 - g0;
+    bool use_global = jobs.size() > 1 && 2 * ((N + 31) / 32) * 4 <= 200 * 1024 && N < 0xFFFFFFF0ULL && !getenv("D2G_C16_NO_GLOBAL");   // bitmap + prefix in shared memory
+    if (ne_only && !getenv("D2G_C16_NO_HASH") && M > d2g::C16_HASH_MAX_SKETCHES) {
+        // != only: jobs of <= 16 384 sketches take their codes from a hash table (no sort).  Pick the cheaper plan with measured
+        // per-element costs (B200, S=4096): segmented sort + ranks 1.2e-10 s, local codes from global ranks 0.8e-11 s, hash codes 2.8e-11 s.
+        plan(d2g::C16_HASH_MAX_SKETCHES, hjobs);
+        double cost_sorted = 0, cost_hashed = 0;
+        for (const Job &j : jobs) cost_sorted += (double)job_sketches(j) * S * (use_global ? 0.8e-11 : 1.2e-10);
+        if (use_global) cost_sorted += (double)N * S * 1.2e-10;
+        if (jobs.size() == 1 && job_sketches(jobs[0]) <= d2g::C16_HASH_MAX_SKETCHES) cost_sorted = 1e30;   // hashed inside run_cmp16_job anyway
+        for (const Job &j : hjobs) cost_hashed += (double)job_sketches(j) * S * 2.8e-11 + 15e-6;
+        if (cost_hashed < cost_sorted) { jobs.swap(hjobs); use_global = false; }
     }
+    if (use_global) { if (int rc = c16_build_global(c, p, regs_d, g0, N)) return rc; }
+    for (const Job &j : jobs)
+        if (int rc = run_cmp16_job(c, p, a, j.lo1, j.hi1, j.lo2, j.hi2, j.r0, j.r1, j.c0, j.c1)) return rc;
     return D2G_OK;
 }
 
