@@ -39,7 +39,7 @@ EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stre
            "d2g_set_timing", "d2g_get_timing",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
-           "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_free"]
+           "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_free"]
 
 _lib = None
 
@@ -85,6 +85,8 @@ def load():
     L.d2g_cmp_counts.argtypes = [vp, u32, i32, vp, u64, vp, u64, vp, vp]; L.d2g_cmp_counts.restype = C.c_int
     L.d2g_lsh_topk.argtypes = [vp, C.POINTER(CmpParams), vp, vp, i32, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
     L.d2g_lsh_topk.restype = C.c_int
+    L.d2g_lsh_topk_rows.argtypes = [vp, C.POINTER(CmpParams), vp, vp, i32, u64, u64, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
+    L.d2g_lsh_topk_rows.restype = C.c_int
     L.d2g_free.argtypes = [vp]; L.d2g_free.restype = None
     _lib = L
     return L
@@ -249,14 +251,16 @@ class Context:
         _check(self.L.d2g_cmp_counts(self.h, S, cmp_kind, _ptr(rows), nr, _ptr(cols), nc, _ptr(c0), _ptr(c1)))
         return c0, c1
 
-    def lsh_topk(self, regs: np.ndarray, cards: np.ndarray, topk: int, measure="similarity", k=31, cmp_kind=0):
-        """--topk neighbour graph (d2g_lsh_topk): returns CSR (indptr u64[n+1], indices u32[nnz], data f32[nnz])."""
+    def lsh_topk(self, regs: np.ndarray, cards: np.ndarray, topk: int, measure="similarity", k=31, cmp_kind=0, rows=None):
+        """--topk neighbour graph (d2g_lsh_topk / d2g_lsh_topk_rows for rows=(begin, end)): returns CSR
+        (indptr u64[rows+1], indices u32[nnz], data f32[nnz])."""
         regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
         n, S = regs.shape
         p = self.cmp_params(S, n, "symmetric", measure, k=k, cmp_kind=cmp_kind)
-        indptr = np.zeros(n + 1, dtype=np.uint64)
+        x0, x1 = rows if rows is not None else (0, n)
+        indptr = np.zeros(x1 - x0 + 1, dtype=np.uint64)
         pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()
-        _check(self.L.d2g_lsh_topk(self.h, C.byref(p), _ptr(regs), _ptr(cards), topk, _ptr(indptr), C.byref(pi), C.byref(pv)))
+        _check(self.L.d2g_lsh_topk_rows(self.h, C.byref(p), _ptr(regs), _ptr(cards), topk, x0, x1, _ptr(indptr), C.byref(pi), C.byref(pv)))
         nnz = int(indptr[-1])
         idx = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
         val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()

@@ -1230,13 +1230,19 @@ int d2g_cmp_counts(d2g_ctx *c, uint32_t S, int32_t cmp_kind, const double *rows,
 // -------------------------------------------------------------------------------------------------
 extern "C" int d2g_lsh_topk(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards, int32_t topk,
                             uint64_t *indptr_out, uint32_t **idx_out, float **val_out) {
+    return d2g_lsh_topk_rows(c, p, regs, cards, topk, 0, p ? p->n : 0, indptr_out, idx_out, val_out);
+}
+
+extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards, int32_t topk,
+                                 uint64_t x0, uint64_t x1, uint64_t *indptr_out, uint32_t **idx_out, float **val_out) {
     if (!c) return fail(D2G_EINVAL, "null ctx");
     if (int rc = check_cmp_params(p)) return rc;
+    if (x0 > x1 || x1 > p->n) return fail(D2G_EINVAL, "bad row range");
     if (topk <= 0) return fail(D2G_EINVAL, "topk must be > 0 (similarity-threshold graphs are not implemented)");
     if (p->cmp_kind >= D2G_CMP_SS_COMPRESSED) return fail(D2G_EUNSUPPORTED, "top-k over compressed registers (--fastcmp with --topk) is not implemented on the GPU");
     if (!indptr_out || !idx_out || !val_out) return fail(D2G_EINVAL, "null output");
     const uint64_t n = p->n; const uint32_t S = p->sketchsize;
-    if (n < 2) { for (uint64_t i = 0; i <= n; ++i) indptr_out[i] = 0; *idx_out = (uint32_t *)malloc(4); *val_out = (float *)malloc(4); return D2G_OK; }
+    if (n < 2 || x0 == x1) { for (uint64_t i = 0; i <= x1 - x0; ++i) indptr_out[i] = 0; *idx_out = (uint32_t *)malloc(4); *val_out = (float *)malloc(4); return D2G_OK; }
     if (n >= 0x7FFFFFFFULL) return fail(D2G_EINVAL, "too many sketches for 32-bit LSH ids");
     if (S < 2) return fail(D2G_EINVAL, "sketchsize must be >= 2 for the default two LSH table types");
     CU(cudaSetDevice(c->device));
@@ -1304,7 +1310,7 @@ extern "C" int d2g_lsh_topk(d2g_ctx *c, const d2g_cmp_params *p, const double *r
         c->launches++;
     }
     // 4. arrivals, stable sort by destination list, segment starts, replay
-    d2g::lsh_arrivals_kernel<<<(unsigned)((n * maxcand + 255) / 256), 256, 0, st>>>(cand, cnt, ncand, n, maxcand, alA, apA);
+    d2g::lsh_arrivals_kernel<<<(unsigned)((n * maxcand + 255) / 256), 256, 0, st>>>(cand, cnt, ncand, n, maxcand, (uint32_t)x0, (uint32_t)x1, alA, apA);
     {
         size_t need = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, need, alA, alB, apA, apB, (int)na, 0, 32, st);
@@ -1337,12 +1343,14 @@ extern "C" int d2g_lsh_topk(d2g_ctx *c, const d2g_cmp_params *p, const double *r
         std::vector<uint32_t> hs(n);
         CU(cudaMemcpyAsync(hs.data(), lsz, n * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        indptr_out[0] = 0;
-        for (uint64_t i = 0; i < n; ++i) indptr_out[i + 1] = indptr_out[i] + hs[i];
-        CU(cudaMemcpyAsync(indptr_d, indptr_out, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        std::vector<uint64_t> full(n + 1, 0);                 // lists outside [x0, x1) are empty
+        for (uint64_t i = 0; i < n; ++i) full[i + 1] = full[i] + ((i >= x0 && i < x1) ? hs[i] : 0);
+        for (uint64_t i = x0; i <= x1; ++i) indptr_out[i - x0] = full[i];
+        CU(cudaMemcpyAsync(indptr_d, full.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
     }
     (void)lsz64;
-    const uint64_t nnz = indptr_out[n];
+    const uint64_t nnz = indptr_out[x1 - x0];
     uint32_t *hidx = (uint32_t *)malloc((nnz + 1) * 4); float *hval = (float *)malloc((nnz + 1) * 4);
     if (!hidx || !hval) { free(hidx); free(hval); return fail(D2G_ENOMEM, "malloc failed for %llu neighbours", (unsigned long long)nnz); }
     if (nnz) {

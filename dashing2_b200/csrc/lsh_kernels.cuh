@@ -93,8 +93,9 @@ __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, con
 }
 
 // arrival records in (q, pos, side) order: index a = (q*maxcand + pos)*2 + side ; key = destination list
+// only arrivals whose destination list lies in [x0, x1) are kept (lists are sharded over GPUs; every GPU scans all queries)
 __global__ void lsh_arrivals_kernel(const uint32_t *cand, const uint32_t *cnt, const uint32_t *ncand, uint64_t n, uint32_t maxcand,
-                                    uint32_t *alist, uint64_t *apay) {
+                                    uint32_t x0, uint32_t x1, uint32_t *alist, uint64_t *apay) {
     const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (e >= n * maxcand) return;
     const uint64_t q = e / maxcand; const uint32_t pos = (uint32_t)(e % maxcand);
@@ -107,6 +108,8 @@ __global__ void lsh_arrivals_kernel(const uint32_t *cand, const uint32_t *cnt, c
             l1 = (uint32_t)q; p1 = ((uint64_t)oid << 32) | cd;          // update(neighbor_lists[id], {cd, oid})
         }
     }
+    if (l0 < x0 || l0 >= x1) l0 = 0xFFFFFFFFu;
+    if (l1 < x0 || l1 >= x1) l1 = 0xFFFFFFFFu;
     alist[2 * e] = l0; apay[2 * e] = p0; alist[2 * e + 1] = l1; apay[2 * e + 1] = p1;
 }
 

@@ -182,6 +182,12 @@ int d2g_cmp_counts(d2g_ctx *ctx, uint32_t sketchsize, int32_t cmp_kind,
 int d2g_lsh_topk(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards,
                  int32_t topk, uint64_t *indptr_out, uint32_t **idx_out, float **val_out);
 
+/* Lists [row_begin,row_end) of the same graph (indptr_out: u64[row_end-row_begin+1], starting at 0).  The neighbour lists are
+ * independent once the candidates of ALL queries are known, so several GPUs each build the (replicated) index, scan all
+ * queries and replay / refine / trim only their own range of lists; concatenated in rank order the pieces are the graph. */
+int d2g_lsh_topk_rows(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards,
+                      int32_t topk, uint64_t row_begin, uint64_t row_end, uint64_t *indptr_out, uint32_t **idx_out, float **val_out);
+
 void d2g_free(void *p);
 
 #ifdef __cplusplus

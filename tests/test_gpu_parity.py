@@ -400,6 +400,20 @@ def test_topk_matches_reference_golden(K):
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
 
 
+def test_topk_row_ranges_concatenate_to_the_graph():
+    """d2g_lsh_topk_rows: the lists of a range of sketches (how several GPUs share one graph) concatenate to the golden CSR."""
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    ip, ix, dv = O.read_csr(expected("topk32_sk600.csr"))
+    c = ctx()
+    ptr = [np.zeros(1, dtype=np.uint64)]; idx = []; val = []; base = np.uint64(0)
+    for r0, r1 in ((0, 100), (100, 101), (101, 101), (101, 600)):
+        gp, gi, gv = c.lsh_topk(z["regs"], z["cards"], 32, "similarity", k=32, rows=(r0, r1))
+        assert gp[0] == 0 and len(gp) == r1 - r0 + 1
+        ptr.append(gp[1:] + base); base += gp[-1]; idx.append(gi); val.append(gv)
+    assert np.array_equal(np.concatenate(ptr), ip) and np.array_equal(np.concatenate(idx), ix)
+    assert np.array_equal(np.concatenate(val).view(np.uint32), dv.view(np.uint32))
+
+
 @pytest.mark.parametrize("n,S,K,measure,cmp_kind", [(3000, 128, 10, "similarity", 0), (1500, 256, 32, "containment", 0),
                                                      (2000, 64, 7, "poisson_llr", 0), (1200, 128, 16, "similarity", 1),
                                                      (700, 1024, 32, "symmetric_containment", 0)])
