@@ -315,6 +315,8 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const 
             const double mlnm = (double)m * std::log((double)m + 2.);
             uint32_t stride = 1;
             while (stride < 64 && (double)(stride * 2) <= std::sqrt(n_eff / (2. * mlnm)) * 4.) stride *= 2;
+            // ... but every register must be hit by the sample (an unhit register leaves T infinite): >= 24 sampled elements per register
+            while (stride > 1 && n_eff / stride < 24. * m) stride /= 2;
             if (const char *ev = getenv("D2G_FSS_BOOT_STRIDE")) stride = (uint32_t)std::max(1, atoi(ev));   // tuning knob
             a.tile_stride = stride; a.want_state = 1;
             d2g::FssBootConsumer::Params bp{maxrv, d2g::make_fastmod32(m), m};

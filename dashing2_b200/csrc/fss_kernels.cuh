@@ -84,7 +84,7 @@ __global__ void fss_guess_kernel(const unsigned long long *npos, uint32_t n_ent,
     if (e >= n_ent) return;
     const double n_est = (double)npos[e] * (wsz > 1 ? 2. / (wsz + 1.) : 1.);
     const double lm = log((double)m) + 0.5772156649;
-    const bool guess = allow_guess && n_est >= 4. * (double)m * lm;
+    const bool guess = allow_guess && n_est >= 2. * (double)m * lm;
     const double g = guess ? 3. * lm / n_est : 1.7976931348623157e308;
     T[e] = g; Tguess[e] = g; state[e] = guess ? 0u : 1u;
 }

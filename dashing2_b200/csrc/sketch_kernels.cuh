@@ -297,8 +297,17 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                     const int B0 = OFF + j0;
                     const uint64_t *own = score + sk_pad(B0);
                     if (wsz >= SK_PPT) {
-                        uint64_t common = ~0ULL;                       // slots shared by all eight windows of this thread
-                        for (int q = B0 + 7 - (wsz - 1); q < B0; ++q) common = min(common, score[sk_pad(q)]);
+                        // slots [B0 + 7 - (wsz-1), B0) are shared by all eight windows of this thread.  B0 is a multiple of 8, so
+                        // walking backwards they are whole padded groups of eight (consecutive words) and one partial group.
+                        uint64_t common = ~0ULL;
+                        int rem = wsz - 8;
+                        const uint64_t *g = own - 9;                   // group of slots B0-8 .. B0-1
+                        for (; rem >= 8; rem -= 8, g -= 9) {
+                            #pragma unroll
+                            for (int i = 0; i < 8; ++i) common = min(common, g[i]);
+                        }
+                        #pragma unroll
+                        for (int i = 1; i < 8; ++i) if (i >= 8 - rem) common = min(common, g[i]);
                         uint64_t left[SK_PPT];                          // suffix minima of the slots only the earlier windows reach
                         uint64_t run = ~0ULL;
                         left[SK_PPT - 1] = run;
@@ -310,23 +319,25 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                         run = ~0ULL;                                    // prefix minima of the own keys
                         #pragma unroll
                         for (int j = 0; j < SK_PPT; ++j) {
-                            if (j < jn) run = min(run, own[j]);
-                            mn[j] = min(min(left[j], common), run);
+                            if (j < jn) { run = min(run, own[j]); mn[j] = min(min(left[j], common), run); }
+                            else mn[j] = mn[j - 1];                     // j >= jn >= 1: repeat the last window (never emits)
                         }
                     } else {
                         #pragma unroll
                         for (int j = 0; j < SK_PPT; ++j) {
                             uint64_t v = ~0ULL;
                             if (j < jn) for (int q = 0; q < wsz; ++q) v = min(v, score[sk_pad(B0 + j - q)]);
-                            mn[j] = v;
+                            mn[j] = j < jn ? v : mn[j > 0 ? j - 1 : 0];
                         }
                     }
                 }
-                uint64_t last = 0;
-                #pragma unroll
-                for (int j = 0; j < SK_PPT; ++j) if (j < jn) last = mn[j];
-                uint64_t prev = __shfl_up_sync(0xffffffffu, last, 1);   // lane 0 and the first thread of a tile always emit
-                bool have_prev = lane != 0;
+                if (jn == 0) {
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j) mn[j] = 0;
+                }
+                // mn[j >= jn] repeats mn[jn-1], so mn[7] is the last window of the thread and needs no guard below
+                uint64_t prev = __shfl_up_sync(0xffffffffu, mn[SK_PPT - 1], 1);
+                if (lane == 0) prev = ~mn[0];                           // lane 0 (and so the first thread of a tile) always emits
                 if (Consumer::kEveryWindow) {
                     #pragma unroll
                     for (int j = 0; j < SK_PPT; ++j)
@@ -334,8 +345,8 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                 } else {
                     uint32_t emask = 0;
                     #pragma unroll
-                    for (int j = 0; j < SK_PPT; ++j)
-                        if (j < jn) { emask |= (uint32_t)(!have_prev || mn[j] != prev) << j; prev = mn[j]; have_prev = true; }
+                    for (int j = 0; j < SK_PPT; ++j) { emask |= (uint32_t)(mn[j] != prev) << j; prev = mn[j]; }
+                    if (jn == 0) emask = 0;
                     // one slot range per warp: exclusive scan of the per-thread counts, one atomic
                     const int cnt = __popc(emask);
                     int incl = cnt;
