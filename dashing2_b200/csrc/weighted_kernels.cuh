@@ -62,10 +62,25 @@ __global__ void rle_scatter_kernel(const uint32_t *flag, const uint32_t *excl, c
 __global__ void weight_sum_kernel(const uint32_t *ent, const uint32_t *pos, uint64_t nu, const unsigned long long *n_valid, double threshold,
                                   unsigned long long *wsum) {
     const uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (u >= nu) return;
-    const uint64_t i = pos[u], end = (u + 1 < nu) ? pos[u + 1] : *n_valid;
-    const uint64_t c = end - i;
-    if ((double)c > threshold) atomicAdd(wsum + ent[i], (unsigned long long)c);
+    uint32_t e = 0xFFFFFFFFu; unsigned long long c = 0;
+    if (u < nu) {
+        const uint64_t i = pos[u], end = (u + 1 < nu) ? pos[u + 1] : *n_valid;
+        e = ent[i];
+        c = end - i;
+        if (!((double)c > threshold)) c = 0;
+    }
+    // the runs are sorted by entity: a warp almost always holds one entity -> one atomic per warp and entity, not per element
+    unsigned todo = __ballot_sync(0xffffffffu, c != 0);
+    while (todo) {
+        const int leader = __ffs((int)todo) - 1;
+        const uint32_t le = __shfl_sync(0xffffffffu, e, leader);
+        const bool mine = c != 0 && e == le;
+        unsigned long long v = mine ? c : 0;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(wsum + le, v);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
 }
 
 // per-entity first guess of the bound: registers receive points at total rate W/m, so their maximum is about
