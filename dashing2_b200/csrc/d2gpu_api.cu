@@ -1252,6 +1252,7 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     const uint32_t ntab = S + S / 2;                                   // cmp_core.cpp:757-770 with nLSH = 2
     uint64_t ntoquery = (uint64_t)((float)topk * 3.5f);                // index_build.cpp:57-60
     ntoquery = std::min<uint64_t>(ntoquery, n - 1);
+    CU(cudaFuncSetAttribute(d2g::lsh_trim_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d2g::LSH_TRIM_BIG_CAP * 8));
     if (ntoquery == 0 || ntoquery > 4096) return fail(D2G_EUNSUPPORTED, "topk %d out of the supported range", topk);
     const uint32_t maxcand = (uint32_t)ntoquery;
     if (int rc = c->cregs.reserve(n * S * 8)) return rc;
@@ -1326,6 +1327,14 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     uint32_t h_total = 0;
     CU(cudaMemcpyAsync(&h_total, seg + n, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (getenv("D2G_DEBUG")) {
+        std::vector<uint32_t> hs(n);
+        cudaMemcpy(hs.data(), lsz, n * 4, cudaMemcpyDeviceToHost);
+        uint64_t sum = 0, big256 = 0, big1024 = 0; uint32_t mx = 0;
+        for (uint32_t v : hs) { sum += v; mx = std::max(mx, v); big256 += v > 256; big1024 += v > 1024; }
+        fprintf(stderr, "[d2g] topk: %llu lists, %u arrival slots, list entries before refinement: total %llu, mean %.1f, max %u, >256: %llu, >1024: %llu\n",
+                (unsigned long long)n, h_total, (unsigned long long)sum, (double)sum / n, mx, (unsigned long long)big256, (unsigned long long)big1024);
+    }
     // 5. refine + trim
     d2g::CmpConsts k;
     if (int rc = make_consts(c, p, &k)) return rc;
@@ -1337,8 +1346,10 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
         else d2g::lsh_refine_kernel<1><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(regs_d, cards_d, n, seg, lsz, lst, k, mult);
         c->launches++;
     }
+    // short lists first: a list the second kernel has trimmed (> LSH_TRIM_CAP entries before) must not be seen as short afterwards
     d2g::lsh_trim_kernel<<<(unsigned)((n + d2g::LSH_TRIM_WARPS - 1) / d2g::LSH_TRIM_WARPS), d2g::LSH_TRIM_WARPS * 32, 0, st>>>(seg, n, (uint32_t)topk, is_dist, lst, lsz);
-    c->launches++;
+    d2g::lsh_trim_big_kernel<<<(unsigned)n, d2g::LSH_TRIM_BIG_THREADS, d2g::LSH_TRIM_BIG_CAP * 8, st>>>(seg, n, (uint32_t)topk, is_dist, lst, lsz);
+    c->launches += 2;
     // 6. CSR: indptr = exclusive scan of list sizes
     {
         // widen to u64 on the host side of the scan: sizes are small, sum may exceed 2^32

@@ -167,11 +167,12 @@ __global__ void lsh_refine_kernel(const double *regs, const double *cards, uint6
     if (lane == 0) lst[w].d = mult * finalize_pair(c, KIND == 0 ? g : c.S - g, l, cards[x], cards[id]);
 }
 
-// one WARP per list: sort by (d, id), drop zero similarities, keep top-k plus ties, undo the sign (refine.cpp:30-74).
-// Lists of up to LSH_TRIM_CAP entries are sorted by a bitonic network in shared memory on 64-bit keys
-// (order-preserving image of d, then id); longer ones (the bounded-heap rule keeps lists near 3.5 K) fall back to an
-// insertion sort by one lane.
-constexpr int LSH_TRIM_CAP = 1024, LSH_TRIM_WARPS = 4;
+// Sort by (d, id), drop zero similarities, keep top-k plus ties, undo the sign (refine.cpp:30-74).
+// lsh_trim_kernel: one WARP per list of up to LSH_TRIM_CAP entries, bitonic network in shared memory on 64-bit keys
+// (order-preserving image of d, then id).  lsh_trim_big_kernel: one CTA per longer list (the bounded-heap rule keeps
+// ties, so a few lists grow past a thousand entries), same network over LSH_TRIM_BIG_CAP slots; beyond that one thread
+// sorts by insertion.
+constexpr int LSH_TRIM_CAP = 512, LSH_TRIM_WARPS = 4, LSH_TRIM_BIG_CAP = 8192, LSH_TRIM_BIG_THREADS = 256;
 // key order == nb_less order: -0.0 and +0.0 compare equal there, so zeros share one key image and the sign of a zero
 // travels in bit 0 of the low word, below the id (ids are < 2^31)
 __device__ __forceinline__ uint64_t nb_key(const Nb &e) {
@@ -188,30 +189,15 @@ __device__ __forceinline__ Nb nb_unkey(uint64_t k) {
     if (e.d == 0.f && (k & 1u)) e.d = -0.f;
     return e;
 }
-__global__ void __launch_bounds__(LSH_TRIM_WARPS * 32)
-lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
-    __shared__ uint64_t buf[LSH_TRIM_WARPS][LSH_TRIM_CAP];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint64_t x = blockIdx.x * (uint64_t)LSH_TRIM_WARPS + wid;
-    if (x >= n) return;
-    Nb *L = lst + seg[x]; uint32_t nl = lsize[x];
-    if (nl > LSH_TRIM_CAP) {
-        if (lane == 0) {
-            for (uint32_t i = 1; i < nl; ++i) { const Nb it = L[i]; uint32_t j = i; while (j && nb_less(it, L[j - 1])) { L[j] = L[j - 1]; --j; } L[j] = it; }
-            if (!is_dist) { uint32_t j = 0; while (j < nl && L[j].d != 0.f) ++j; nl = j; }
-            if (topk < nl) { const float bs = L[topk - 1].d; uint32_t j = topk; while (j < nl && !(L[j].d > bs)) ++j; nl = j; }
-            if (!is_dist) for (uint32_t j = 0; j < nl; ++j) L[j].d = -L[j].d;
-            lsize[x] = nl;
-        }
-        return;
-    }
-    uint64_t *B = buf[wid];
+// NT threads (a warp or a CTA) sort B[0..P) ascending and trim; SYNC() separates the steps
+template <int NT, class Sync>
+__device__ __forceinline__ void trim_sorted_list(uint64_t *B, Nb *L, uint32_t nl, uint32_t topk, int is_dist, uint32_t *lsize_x, int t, uint32_t *scratch, Sync sync) {
     uint32_t P = 32; while (P < nl) P <<= 1;
-    for (uint32_t i = lane; i < P; i += 32) B[i] = i < nl ? nb_key(L[i]) : ~0ULL;
-    __syncwarp();
+    for (uint32_t i = t; i < P; i += NT) B[i] = i < nl ? nb_key(L[i]) : ~0ULL;
+    sync();
     for (uint32_t k = 2; k <= P; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < P; i += 32) {
+            for (uint32_t i = t; i < P; i += NT) {
                 const uint32_t l = i ^ j;
                 if (l > i) {
                     const uint64_t a = B[i], c = B[l];
@@ -219,27 +205,54 @@ lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb 
                     if ((a > c) == up) { B[i] = c; B[l] = a; }
                 }
             }
-            __syncwarp();
+            sync();
         }
     // sorted ascending.  Similarities are stored negated: zeros sort last and are dropped; distances keep theirs.
-    uint32_t keep = nl;
-    if (!is_dist) {
-        uint32_t nz = 0;
-        for (uint32_t i = lane; i < nl; i += 32) nz += nb_unkey(B[i]).d != 0.f;
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
-        keep = nz;
-    }
+    // Both cut-offs are prefixes of the sorted list, so counting suffices.
+    if (t == 0) { scratch[0] = 0; scratch[1] = 0; }
+    sync();
+    uint32_t nz = 0;
+    if (!is_dist) { for (uint32_t i = t; i < nl; i += NT) nz += nb_unkey(B[i]).d != 0.f; if (nz) atomicAdd(scratch, nz); }
+    sync();
+    uint32_t keep = is_dist ? nl : scratch[0];
     if (topk < keep) {                       // everything tied with the k-th entry stays (refine.cpp:39-42)
         const float bs = nb_unkey(B[topk - 1]).d;
         uint32_t le = 0;
-        for (uint32_t i = lane; i < keep; i += 32) le += !(nb_unkey(B[i]).d > bs);
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) le += __shfl_xor_sync(0xffffffffu, le, o);
-        keep = le;
+        for (uint32_t i = t; i < keep; i += NT) le += !(nb_unkey(B[i]).d > bs);
+        if (le) atomicAdd(scratch + 1, le);
+        sync();
+        keep = scratch[1];
     }
-    for (uint32_t i = lane; i < keep; i += 32) { Nb e = nb_unkey(B[i]); if (!is_dist) e.d = -e.d; L[i] = e; }
-    if (lane == 0) lsize[x] = keep;
+    for (uint32_t i = t; i < keep; i += NT) { Nb e = nb_unkey(B[i]); if (!is_dist) e.d = -e.d; L[i] = e; }
+    if (t == 0) *lsize_x = keep;
+}
+__global__ void __launch_bounds__(LSH_TRIM_WARPS * 32)
+lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
+    __shared__ uint64_t buf[LSH_TRIM_WARPS][LSH_TRIM_CAP];
+    __shared__ uint32_t scr[LSH_TRIM_WARPS][2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t x = blockIdx.x * (uint64_t)LSH_TRIM_WARPS + wid;
+    if (x >= n) return;
+    const uint32_t nl = lsize[x];
+    if (nl > LSH_TRIM_CAP) return;           // lsh_trim_big_kernel
+    trim_sorted_list<32>(buf[wid], lst + seg[x], nl, topk, is_dist, lsize + x, lane, scr[wid], [] { __syncwarp(); });
+}
+__global__ void __launch_bounds__(LSH_TRIM_BIG_THREADS)
+lsh_trim_big_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
+    extern __shared__ uint64_t bigbuf[];
+    __shared__ uint32_t scr[2];
+    const uint64_t x = blockIdx.x;
+    uint32_t nl = lsize[x];
+    if (nl <= LSH_TRIM_CAP) return;
+    Nb *L = lst + seg[x];
+    if (nl <= LSH_TRIM_BIG_CAP) { trim_sorted_list<LSH_TRIM_BIG_THREADS>(bigbuf, L, nl, topk, is_dist, lsize + x, (int)threadIdx.x, scr, [] { __syncthreads(); }); return; }
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 1; i < nl; ++i) { const Nb it = L[i]; uint32_t j = i; while (j && nb_less(it, L[j - 1])) { L[j] = L[j - 1]; --j; } L[j] = it; }
+        if (!is_dist) { uint32_t j = 0; while (j < nl && L[j].d != 0.f) ++j; nl = j; }
+        if (topk < nl) { const float bs = L[topk - 1].d; uint32_t j = topk; while (j < nl && !(L[j].d > bs)) ++j; nl = j; }
+        if (!is_dist) for (uint32_t j = 0; j < nl; ++j) L[j].d = -L[j].d;
+        lsize[x] = nl;
+    }
 }
 
 __global__ void lsh_csr_kernel(const uint32_t *seg, const uint32_t *lsize, const uint64_t *indptr, uint64_t n, const Nb *lst, uint32_t *idx, float *val) {
