@@ -66,7 +66,8 @@ elif cmd == "c4":
 elif cmd == "c5":
     n, S, K = (args + [250_000, 1024, 32][len(args):])[:3]
     regs, cards = sketches_on_device(n, S, 5, max(1, n // 1000))
-    h_regs = regs.cpu().numpy(); h_cards = cards.cpu().numpy()
+    h_regs_t = torch.empty(regs.shape, dtype=torch.float64).pin_memory(); h_regs_t.copy_(regs)     # page-locked host registers
+    h_regs = h_regs_t.numpy(); h_cards = cards.cpu().numpy()
     del regs; torch.cuda.empty_cache()
     for rep in range(2):
         l0 = ctx.launch_count(); t0 = time.perf_counter()
