@@ -12,6 +12,7 @@
 #include <zlib.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
@@ -25,10 +26,22 @@
 #include <thread>
 #include <vector>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../../include/d2gpu.h"
 
 namespace {
+
+// phase timing on stderr with -v
+struct PhaseTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0; int verbosity = 0;
+    void mark(const char *what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (verbosity > 0) std::fprintf(stderr, "[dashing2-gpu] %-28s %8.1f ms (total %8.1f ms)\n", what,
+                                        std::chrono::duration<double, std::milli>(now - last).count(), std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+} g_timer;
 
 [[noreturn]] void die(const std::string &m) { std::fprintf(stderr, "dashing2-gpu: %s\n", m.c_str()); std::exit(1); }
 void chk(int rc) { if (rc) die(std::string("libd2gpu: ") + d2g_last_error()); }
@@ -192,10 +205,20 @@ void fmt_float(float v, std::string &out) {
     } else { out += "0."; out.append(-ex - 1, '0'); out += digits; }
 }
 
+// The CUDA context comes up on its own thread (1-2 s on a B200 box) while the host threads read and parse the first batch.
+struct LazyCtx {
+    d2g_ctx *ctx = nullptr; int rc = 0; std::string err; std::thread th; bool joined = false;
+    void start() { th = std::thread([this] { rc = d2g_init(&ctx, 0); if (rc) err = d2g_last_error(); }); }
+    d2g_ctx *get() {
+        if (!joined) { th.join(); joined = true; g_timer.mark("d2g_init (overlapped)"); if (rc) die("libd2gpu: " + err); }
+        return ctx;
+    }
+};
+
 struct Sketches { std::vector<double> sig, card; std::vector<uint64_t> ids; std::vector<std::string> names; uint64_t S = 0; int mode = D2G_MODE_OPMH; };
 
 // ---- sketch all inputs through libd2gpu in batches -----------------------------------------------
-void sketch_inputs(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
+void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
     const size_t n = o.paths.size(), S = o.S;
     sk.S = S; sk.mode = o.mode; sk.names = o.paths;
     sk.sig.assign(n * S, 0.); sk.card.assign(n, 0.);
@@ -236,17 +259,27 @@ void sketch_inputs(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
             for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] { for (size_t j; (j = next++) < idx.size();) read_fastx(o.paths[idx[j]], recs[j]); });
             for (auto &t : th) t.join();
         }
-        std::string seq; std::vector<uint64_t> off{0}; std::vector<uint32_t> ent;
-        for (size_t j = 0; j < idx.size(); ++j) {
-            const uint64_t base = seq.size(); seq += recs[j].seq;
-            for (uint64_t e : recs[j].ends) { off.push_back(base + e); ent.push_back((uint32_t)j); }
-            recs[j] = FileRecords();
+        g_timer.mark("read + parse batch");
+        // one buffer for the batch: sized once, filled by the host threads in parallel
+        std::vector<uint64_t> base(idx.size() + 1, 0);
+        for (size_t j = 0; j < idx.size(); ++j) base[j + 1] = base[j] + recs[j].seq.size();
+        std::vector<char> seq(base.back() + 64);
+        std::vector<uint64_t> off{0}; std::vector<uint32_t> ent;
+        for (size_t j = 0; j < idx.size(); ++j)
+            for (uint64_t e : recs[j].ends) { off.push_back(base[j] + e); ent.push_back((uint32_t)j); }
+        {
+            std::vector<std::thread> th; std::atomic<size_t> next{0};
+            const unsigned nt = (unsigned)std::min<size_t>(o.nthreads, idx.size());
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] {
+                for (size_t j; (j = next++) < idx.size();) { memcpy(seq.data() + base[j], recs[j].seq.data(), recs[j].seq.size()); recs[j] = FileRecords(); } });
+            for (auto &t : th) t.join();
         }
-        seq.append(64, '\0');
+        g_timer.mark("concatenate batch");
         const uint32_t ne = (uint32_t)idx.size();
         std::vector<double> sig((size_t)ne * S), card(ne); std::vector<uint64_t> ids(o.save_kmers ? (size_t)ne * S : 0);
-        chk(d2g_sketch_batch(ctx, &p, seq.data(), off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
+        chk(d2g_sketch_batch(lctx.get(), &p, seq.data(), off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
                              o.save_kmers ? ids.data() : nullptr, nullptr));
+        g_timer.mark("d2g_sketch_batch");
         for (size_t j = 0; j < idx.size(); ++j) {
             std::copy(sig.begin() + j * S, sig.begin() + (j + 1) * S, sk.sig.begin() + idx[j] * S);
             sk.card[idx[j]] = card[j];
@@ -396,25 +429,35 @@ int main(int argc, char **argv) {
     const bool is_cmp = sub == "cmp" || sub == "dist";
     if (!is_cmp && sub != "sketch") die("subcommand '" + sub + "' is outside the GPU hot paths (only sketch and cmp are provided)");
     Opts o = parse(argc - 2, argv + 2, is_cmp);
-    d2g_ctx *ctx = nullptr;
-    chk(d2g_init(&ctx, 0));
+    g_timer.verbosity = o.verbosity;
+    // this front-end drives one GPU: hiding the others from the CUDA driver cuts its start-up (context creation touches
+    // every visible device) from seconds to a fraction of a second on an 8-GPU box.  An existing setting is respected.
+    setenv("CUDA_VISIBLE_DEVICES", "0", 0);
+    LazyCtx lctx;
+    lctx.start();
     Sketches sk;
     if (is_cmp && o.presketched) {
         if (o.paths.size() != 1) die("--presketched: pass one stacked sketch file (the reference's multi-file branch is degenerate for panels, SURVEY 8a b9)");
         load_stacked(o.paths[0], sk);
         o.S = sk.S;
     } else {
-        sketch_inputs(ctx, o, sk);
+        sketch_inputs(lctx, o, sk);
         if (!o.outfile.empty()) {
             // the reference densifies signatures_ in place before the stacked file is closed when --cmpout is given
-            if (!o.cmpout.empty() && sk.mode == D2G_MODE_OPMH) chk(d2g_densify(ctx, sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), sk.card.size(), (uint32_t)sk.S));
+            if (!o.cmpout.empty() && sk.mode == D2G_MODE_OPMH) chk(d2g_densify(lctx.get(), sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), sk.card.size(), (uint32_t)sk.S));
             write_stacked(o, sk);
         }
     }
+    g_timer.mark("sketches ready / written");
     if (is_cmp || !o.cmpout.empty()) {
         if (is_cmp && o.cmpout.empty()) o.cmpout = "-";
-        compare_and_emit(ctx, o, sk);
+        compare_and_emit(lctx.get(), o, sk);
+        g_timer.mark("compare + emit");
     }
-    d2g_destroy(ctx);
+    // every output file is closed / flushed; tearing the CUDA context down costs another 0.2-0.5 s and frees nothing the
+    // process exit does not free
+    lctx.get();
+    std::fflush(nullptr);
+    _exit(0);
     return 0;
 }
