@@ -1322,7 +1322,11 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
         CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, alA, alB, apA, apB, (int)na, 0, 32, st));
     }
     d2g::lsh_segments_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(alB, na, n, seg);
-    d2g::lsh_replay_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(apB, seg, n, maxcand, lst, dset, lsz);
+    {
+        const bool warp_ok = maxcand <= (uint32_t)d2g::LSH_REPLAY_DCAP;
+        if (warp_ok) d2g::lsh_replay_warp_kernel<<<(unsigned)((n + d2g::LSH_REPLAY_WARPS - 1) / d2g::LSH_REPLAY_WARPS), d2g::LSH_REPLAY_WARPS * 32, 0, st>>>(apB, seg, n, maxcand, lst, lsz);
+        else d2g::lsh_replay_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(apB, seg, n, maxcand, 0u, lst, dset, lsz);
+    }
     c->launches += 8;
     uint32_t h_total = 0;
     CU(cudaMemcpyAsync(&h_total, seg + n, 4, cudaMemcpyDeviceToHost, st));

@@ -116,12 +116,22 @@ __global__ void lsh_arrivals_kernel(const uint32_t *cand, const uint32_t *cnt, c
 struct Nb { float d; uint32_t id; };
 __device__ __forceinline__ bool nb_less(const Nb &a, const Nb &b) { return a.d < b.d || (a.d == b.d && a.id < b.id); }
 
-// one thread per list: replay update() (index_build.cpp:20-44) over its arrivals [seg[x], seg[x+1]); the list lives in
-// lst[seg[x]..] (sorted ascending, so back = priority-queue top), the dedup set in dset[seg[x]..]
-__global__ void lsh_replay_kernel(const uint64_t *apay, const uint32_t *seg, uint64_t n, uint32_t k, Nb *lst, uint32_t *dset, uint32_t *lsize) {
+// Replay of update() (index_build.cpp:20-44) over the arrivals [seg[x], seg[x+1]) of list x, in arrival order.
+// What the rule needs from the list is its LARGEST element (the priority-queue top) and membership in the dedup set; the
+// order of the other entries is irrelevant (refinement recomputes every value and the trim step sorts).
+//
+// lsh_replay_warp_kernel: one WARP per list: list (unsorted, as 64-bit keys in nb_less order; in shared memory up to
+// LSH_REPLAY_LCAP arrivals, else in place in HBM) and dedup set (shared memory, k <= LSH_REPLAY_DCAP), membership /
+// maximum / removal as warp-wide scans.  lsh_replay_kernel: one thread per list, list kept sorted in HBM (larger k).
+__device__ __forceinline__ uint64_t nb_key(const Nb &e);
+__device__ __forceinline__ Nb nb_unkey(uint64_t k);
+constexpr int LSH_REPLAY_LCAP = 1024, LSH_REPLAY_DCAP = 512, LSH_REPLAY_WARPS = 4;
+
+__global__ void lsh_replay_kernel(const uint64_t *apay, const uint32_t *seg, uint64_t n, uint32_t k, uint32_t min_arrivals, Nb *lst, uint32_t *dset, uint32_t *lsize) {
     const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (x >= n) return;
     const uint32_t s0 = seg[x], s1 = seg[x + 1];
+    if (s1 - s0 <= min_arrivals) return;
     Nb *L = lst + s0; uint32_t *D = dset + s0;
     uint32_t nl = 0, nd = 0;
     auto push = [&](Nb it) { uint32_t i = nl++; while (i && nb_less(it, L[i - 1])) { L[i] = L[i - 1]; --i; } L[i] = it; };
@@ -139,6 +149,60 @@ __global__ void lsh_replay_kernel(const uint64_t *apay, const uint32_t *seg, uin
         }
     }
     lsize[x] = nl;
+}
+
+__global__ void __launch_bounds__(LSH_REPLAY_WARPS * 32)
+lsh_replay_warp_kernel(const uint64_t *apay, const uint32_t *seg, uint64_t n, uint32_t k, Nb *lst, uint32_t *lsize) {
+    __shared__ uint64_t sL[LSH_REPLAY_WARPS][LSH_REPLAY_LCAP];
+    __shared__ uint32_t sD[LSH_REPLAY_WARPS][LSH_REPLAY_DCAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t x = blockIdx.x * (uint64_t)LSH_REPLAY_WARPS + wid;
+    if (x >= n) return;
+    const uint32_t s0 = seg[x], s1 = seg[x + 1];
+    // longer lists keep their keys in place in HBM (the list region itself: an entry and its key are both 8 bytes)
+    uint64_t *L = s1 - s0 <= LSH_REPLAY_LCAP ? sL[wid] : reinterpret_cast<uint64_t *>(lst + s0);
+    uint32_t *D = sD[wid];
+    uint32_t nl = 0, nd = 0;
+    uint64_t topkey = 0; uint32_t toppos = 0;                              // largest key of the list and where it sits
+    for (uint32_t a = s0; a < s1; ++a) {
+        const uint64_t pay = apay[a];
+        const Nb it{__uint_as_float((uint32_t)pay), (uint32_t)(pay >> 32)};
+        bool in = false;
+        for (uint32_t f = lane; f < nd; f += 32) in |= D[f] == it.id;
+        if (__any_sync(0xffffffffu, in)) continue;
+        const uint64_t key = nb_key(it);
+        if (nl >= k) {
+            const Nb top = nb_unkey(topkey);
+            if (!(it.d <= top.d)) continue;
+            if (top.d != it.d) {
+                // pop the top: out of the dedup set (if it is there), out of the list, new maximum
+                uint32_t where = 0xFFFFFFFFu;
+                for (uint32_t f = lane; f < nd; f += 32) if (D[f] == top.id) where = f;
+                const unsigned found = __ballot_sync(0xffffffffu, where != 0xFFFFFFFFu);
+                if (found) { const uint32_t f = __shfl_sync(0xffffffffu, where, __ffs((int)found) - 1); if (lane == 0) D[f] = D[nd - 1]; --nd; }
+                if (lane == 0) L[toppos] = L[nl - 1];
+                --nl;
+                __syncwarp();
+                uint64_t mk = 0; uint32_t mp = 0;
+                for (uint32_t i = lane; i < nl; i += 32) { const uint64_t v = L[i]; if (v >= mk) { mk = v; mp = i; } }
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, o); const uint32_t op = __shfl_xor_sync(0xffffffffu, mp, o);
+                    if (ok > mk || (ok == mk && op > mp)) { mk = ok; mp = op; }
+                }
+                topkey = mk; toppos = mp;
+            }
+        } else {
+            if (lane == 0) D[nd] = it.id;
+            ++nd;
+        }
+        if (lane == 0) L[nl] = key;
+        if (nl == 0 || key >= topkey) { topkey = key; toppos = nl; }
+        ++nl;
+        __syncwarp();
+    }
+    for (uint32_t i = lane; i < nl; i += 32) lst[s0 + i] = nb_unkey(L[i]);
+    if (lane == 0) lsize[x] = nl;
 }
 
 // one warp per surviving edge: exact compare() of list owner x and neighbour id
