@@ -21,6 +21,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -263,7 +264,9 @@ void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
         // one buffer for the batch: sized once, filled by the host threads in parallel
         std::vector<uint64_t> base(idx.size() + 1, 0);
         for (size_t j = 0; j < idx.size(); ++j) base[j + 1] = base[j] + recs[j].seq.size();
-        std::vector<char> seq(base.back() + 64);
+        std::unique_ptr<char[]> seq_store(new char[base.back() + 64]);   // not zero-filled: the copy threads touch the pages first, in parallel
+        char *const seqbuf = seq_store.get();
+        memset(seqbuf + base.back(), 0, 64);
         std::vector<uint64_t> off{0}; std::vector<uint32_t> ent;
         for (size_t j = 0; j < idx.size(); ++j)
             for (uint64_t e : recs[j].ends) { off.push_back(base[j] + e); ent.push_back((uint32_t)j); }
@@ -271,13 +274,13 @@ void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
             std::vector<std::thread> th; std::atomic<size_t> next{0};
             const unsigned nt = (unsigned)std::min<size_t>(o.nthreads, idx.size());
             for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] {
-                for (size_t j; (j = next++) < idx.size();) { memcpy(seq.data() + base[j], recs[j].seq.data(), recs[j].seq.size()); recs[j] = FileRecords(); } });
+                for (size_t j; (j = next++) < idx.size();) { memcpy(seqbuf + base[j], recs[j].seq.data(), recs[j].seq.size()); recs[j] = FileRecords(); } });
             for (auto &t : th) t.join();
         }
         g_timer.mark("concatenate batch");
         const uint32_t ne = (uint32_t)idx.size();
         std::vector<double> sig((size_t)ne * S), card(ne); std::vector<uint64_t> ids(o.save_kmers ? (size_t)ne * S : 0);
-        chk(d2g_sketch_batch(lctx.get(), &p, seq.data(), off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
+        chk(d2g_sketch_batch(lctx.get(), &p, seqbuf, off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
                              o.save_kmers ? ids.data() : nullptr, nullptr));
         g_timer.mark("d2g_sketch_batch");
         for (size_t j = 0; j < idx.size(); ++j) {
