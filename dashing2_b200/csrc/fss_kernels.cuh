@@ -46,6 +46,7 @@ struct FssBootConsumer {
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) s[i] = 0;
     }
     static constexpr bool kEveryWindow = false;
+    static constexpr int kMinBlocks = 4;
     __device__ __forceinline__ void begin_entity(uint32_t, uint64_t) {}
     __device__ __forceinline__ void consume(uint64_t hv) {
         const uint64_t rv = cehash(hv ^ FSS_XOR);
@@ -221,6 +222,7 @@ struct FssMainConsumer {
         return scaled >= 18446744073709549568.0 ? 0xFFFFFFFFFFFFF800ULL : (scaled <= 0. ? 0 : (uint64_t)scaled);
     }
     static constexpr bool kEveryWindow = false;
+    static constexpr int kMinBlocks = 3;          // shared memory (registers + queue, ~75 KiB at S = 4096) allows three CTAs per SM anyway
     __device__ __forceinline__ void begin_entity(uint32_t ent, uint64_t) {
         T = *reinterpret_cast<volatile double *>(p.T + ent); rvmin = rvmin_for(T, p.m); cur = ent;
     }

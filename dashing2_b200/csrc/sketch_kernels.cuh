@@ -106,6 +106,7 @@ struct OpmhConsumer {
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) sreg[i] = ~0ULL;
     }
     static constexpr bool kEveryWindow = false;   // set semantics: consecutive equal minimizers feed the sketch once
+    static constexpr int kMinBlocks = 4;          // 64 registers/thread: four CTAs per SM when the registers fit in shared memory (S <= 4096 windowed)
     __device__ __forceinline__ void begin_entity(uint32_t, uint64_t) {}
     __device__ __forceinline__ void consume(uint64_t hv) {
         const uint64_t id = dhash(hv);                       // oph.h:178
@@ -172,7 +173,7 @@ __device__ __forceinline__ uint32_t kmers8(const uint64_t *W, const uint32_t *M,
 constexpr int SK_SCAP = 512;   // staged window minima per tile (expected ~2/(wsz+1) of the tile); the rest take the direct path
 
 template <bool WINDOWED, class Consumer>
-__global__ void __launch_bounds__(SK_THREADS, 3)
+__global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
 sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = a.k;
