@@ -39,7 +39,7 @@ __device__ __forceinline__ double flog_d(double x) {
 // ---- boot: t = 0 contributions only --------------------------------------------------------------
 struct FssBootConsumer {
     struct Params { uint64_t *maxrv; FastMod32 fm; uint32_t m; };   // maxrv [n_entities][m], zero-initialised
-    static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8; }
+    static __host__ __device__ size_t smem_bytes(uint32_t m, bool) { return (size_t)m * 8; }
     uint64_t *s; Params p;
     __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool) {
         p = pp; s = reinterpret_cast<uint64_t *>(smem);
@@ -137,10 +137,31 @@ struct WalkRng {   // WyRand<uint32_t, 2>: two 64-bit draws per refill, served a
     }
 };
 
-// Replays the sequence of one element against registers `keys` (shared or global) with threshold T.
+// Where a walk delivers (register, key): plain u64 keys (HBM), or the CTA-local 32-bit filter in front of the HBM keys.
+struct Keys64Sink {
+    uint64_t *keys;
+    __device__ __forceinline__ void put(uint32_t idx, uint64_t kk) const {
+        if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
+    }
+};
+// approx[i] = high word of the smallest key THIS CTA has delivered to register i (0xFFFFFFFF = none yet): a key whose high
+// word is larger cannot lower the register, everything else goes to the entity's keys in HBM with atomicMin.  16 KiB
+// instead of 32 KiB of shared memory per CTA at S = 4096 (four CTAs per SM), and the CTA-local maximum that tightens the
+// bound T is still available (rounded up to the next high word).
+struct ApproxSink {
+    uint32_t *approx; uint64_t *gkeys;
+    __device__ __forceinline__ void put(uint32_t idx, uint64_t kk) const {
+        const uint32_t h = (uint32_t)(kk >> 32), cur = approx[idx];
+        if (h > cur) return;
+        if (h < cur) atomicMin(approx + idx, h);
+        if (kk < gkeys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(gkeys + idx), (unsigned long long)kk);
+    }
+};
+
+// Replays the sequence of one element against a register sink with threshold T.
 // PermState provides step(i, samp) -> register index (lazy Fisher-Yates) and may report overflow.
-template <class PermState>
-__device__ __forceinline__ bool fss_walk(uint64_t x, uint32_t m, double T, uint64_t *keys, PermState &ps) {
+template <class PermState, class Sink>
+__device__ __forceinline__ bool fss_walk(uint64_t x, uint32_t m, double T, const Sink &sink, PermState &ps) {
     uint64_t hid = x;
     uint64_t rv = cehash(x ^ FSS_XOR);
     const double tv = __dmul_rn(__ull2double_rn(rv), 0x1p-64);
@@ -154,8 +175,7 @@ __device__ __forceinline__ bool fss_walk(uint64_t x, uint32_t m, double T, uint6
         const uint32_t samp = rng.next() % (m - i);
         uint32_t idx;
         if (!ps.step(i, samp, idx)) return false;                       // sparse state exhausted
-        const uint64_t kk = dkey(ev);
-        if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
+        sink.put(idx, dkey(ev));
         if (bi == m) return true;
         rv = wyhash64(hid);
         const double bv = -(1. / (double)(m - bi)); ++bi;               // getbeta, setsketch.h:300-302
@@ -201,18 +221,20 @@ struct FssMainConsumer {
         uint64_t *ovf; unsigned long long *ovf_count; uint64_t ovf_cap;   // (x, entity) pairs for the long-walk kernel
         uint32_t m;
     };
-    static constexpr int QCAP = SK_TILE + 64; // survivors are batched over tiles so the walk runs on full warps
+    // survivors are batched over tiles so the walk runs on full warps.  Between two end_tile calls a tile pushes at most
+    // SK_TILE survivors (unwindowed) or, in windowed mode, the staged minimizers (SK_SCAP) -- more only for adversarial
+    // windows that change their minimizer at every position, which then overflow to the long-walk list.
+    static __host__ __device__ constexpr int qcap(bool windowed) { return windowed ? SK_SCAP + 960 : SK_TILE + 64; }
     static constexpr int DCAP = 192;          // walks that outran the sparse state wait here for a tighter threshold
-    static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8 + (size_t)(QCAP + DCAP) * 8 + 64; }
-    uint64_t *skeys, *queue, *defer, *bcast; int *qn, *dn; Params p; double T; uint64_t rvmin; int drain_at; uint32_t cur;
-    // Between two end_tile calls a tile pushes at most SK_TILE survivors (unwindowed) or, in windowed mode, the staged
-    // minimizers (SK_SCAP) -- more only for adversarial windows that change their minimizer at every position, which
-    // then overflow to the long-walk list.
+    static constexpr uint32_t APPROX_EMPTY = 0xFFFFFFFFu, APPROX_DBLMAX = (uint32_t)(FSS_KEY_EMPTY >> 32);
+    static __host__ __device__ size_t smem_bytes(uint32_t m, bool windowed) { return (size_t)((m + 1) / 2) * 8 + (size_t)(qcap(windowed) + DCAP) * 8 + 64; }
+    uint32_t *approx; uint64_t *queue, *defer, *bcast; int *qn, *dn; Params p; double T; uint64_t rvmin; int drain_at, QCAP; uint32_t cur;
     __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool windowed) {
+        QCAP = qcap(windowed);
         drain_at = QCAP - (windowed ? SK_SCAP : SK_TILE); cur = 0;
-        p = pp; skeys = reinterpret_cast<uint64_t *>(smem); queue = skeys + p.m; defer = queue + QCAP; bcast = defer + DCAP;
+        p = pp; approx = reinterpret_cast<uint32_t *>(smem); queue = reinterpret_cast<uint64_t *>(smem) + (p.m + 1) / 2; defer = queue + QCAP; bcast = defer + DCAP;
         qn = reinterpret_cast<int *>(bcast + 4); dn = qn + 1;
-        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) skeys[i] = FSS_KEY_EMPTY;
+        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) approx[i] = APPROX_EMPTY;
         if (threadIdx.x == 0) { *qn = 0; *dn = 0; }
         T = 1.7976931348623157e308; rvmin = 0;
     }
@@ -222,7 +244,7 @@ struct FssMainConsumer {
         return scaled >= 18446744073709549568.0 ? 0xFFFFFFFFFFFFF800ULL : (scaled <= 0. ? 0 : (uint64_t)scaled);
     }
     static constexpr bool kEveryWindow = false;
-    static constexpr int kMinBlocks = 3;          // shared memory (registers + queue, ~75 KiB at S = 4096) allows three CTAs per SM anyway
+    static constexpr int kMinBlocks = 4;
     __device__ __forceinline__ void begin_entity(uint32_t ent, uint64_t) {
         T = *reinterpret_cast<volatile double *>(p.T + ent); rvmin = rvmin_for(T, p.m); cur = ent;
     }
@@ -235,18 +257,19 @@ struct FssMainConsumer {
             if (g < p.ovf_cap) { p.ovf[2 * g] = hv; p.ovf[2 * g + 1] = cur; }
         }
     }
-    // All threads.  Replays the queued elements against the CTA-local registers, then tightens the threshold:
-    // the final registers are element-wise <= the local ones, so the largest local register bounds the final
-    // maximum; the bound is shared with the other CTAs working on the same entity through p.T (atomicMin).
+    // All threads.  Replays the queued elements (register updates go to the entity's keys in HBM through the CTA-local
+    // filter), then tightens the threshold: the final registers are element-wise <= what this CTA delivered, so the largest
+    // local entry bounds the final maximum; the bound is shared with the other CTAs working on the same entity through p.T.
     // Walks that outrun the sparse permutation state (threshold still loose) are retried after the tightening;
     // only if that does not help do they go to the long-walk kernel.
     __device__ __forceinline__ void drain(uint32_t ent, bool final) {
         for (int round = 0;; ++round) {
             const int n = min(*qn, QCAP);
+            const ApproxSink sink{approx, p.keys + (uint64_t)ent * p.m};
             for (int q = threadIdx.x; q < n; q += SK_THREADS) {
                 const uint64_t x = queue[q];
                 SparsePerm sp;
-                if (!fss_walk(x, p.m, T, skeys, sp)) {
+                if (!fss_walk(x, p.m, T, sink, sp)) {
                     const int slot = atomicAdd(dn, 1);
                     if (slot < DCAP) defer[slot] = x;
                     else {
@@ -256,18 +279,18 @@ struct FssMainConsumer {
                 }
             }
             __syncthreads();
-            uint64_t mx = 0;
-            for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) mx = max(mx, skeys[i]);
+            uint32_t mx = 0;
+            for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) mx = max(mx, approx[i]);
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if ((threadIdx.x & 31) == 0) queue[threadIdx.x >> 5] = mx;      // queue is free now
             __syncthreads();
             if (threadIdx.x == 0) {
-                uint64_t m2 = 0;
-                for (int w = 0; w < SK_THREADS / 32; ++w) m2 = max(m2, queue[w]);
+                uint32_t m2 = 0;
+                for (int w = 0; w < SK_THREADS / 32; ++w) m2 = max(m2, (uint32_t)queue[w]);
                 double t = T;
-                if (m2 < FSS_KEY_EMPTY) {
-                    const double tl = dunkey(m2);
+                if (m2 < APPROX_DBLMAX) {                                   // every register has been delivered a finite value
+                    const double tl = dunkey(((uint64_t)m2 << 32) | 0xFFFFFFFFULL);   // largest key with that high word
                     if (tl < t && tl >= 0.) { t = tl; atomicMin(reinterpret_cast<unsigned long long *>(p.T + ent), (unsigned long long)__double_as_longlong(tl)); }
                 }
                 const double tg = *reinterpret_cast<volatile double *>(p.T + ent);
@@ -312,10 +335,7 @@ struct FssMainConsumer {
     __device__ __forceinline__ void flush(uint32_t ent) {
         __syncthreads();
         drain(ent, true);
-        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) {
-            const uint64_t v = skeys[i];
-            if (v != FSS_KEY_EMPTY) { atomicMin(reinterpret_cast<unsigned long long *>(p.keys + (uint64_t)ent * p.m + i), (unsigned long long)v); skeys[i] = FSS_KEY_EMPTY; }
-        }
+        for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) approx[i] = APPROX_EMPTY;   // the keys themselves are already in HBM
         __syncthreads();
     }
 };
@@ -330,7 +350,7 @@ __global__ void fss_longwalk_kernel(const uint64_t *ovf, const unsigned long lon
     for (uint64_t e = slot; e < n; e += nslots) {
         const uint64_t x = ovf[2 * e]; const uint32_t ent = (uint32_t)ovf[2 * e + 1];
         ++dp.c;
-        fss_walk(x, m, T[ent], keys + (uint64_t)ent * m, dp);
+        fss_walk(x, m, T[ent], Keys64Sink{keys + (uint64_t)ent * m}, dp);
     }
 }
 

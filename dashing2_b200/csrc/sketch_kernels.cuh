@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t tile_invalid(const uint32_t *M, int b, int k
 // ---- one-permutation MinHash consumer (src/oph.h:176-211) ---------------------------------------
 struct OpmhConsumer {
     struct Params { uint64_t *regs; FastMod32 fm; uint32_t m; };   // regs [n_entities][m], initialised to ~0
-    static __host__ __device__ size_t smem_bytes(uint32_t m) { return (size_t)m * 8; }
+    static __host__ __device__ size_t smem_bytes(uint32_t m, bool) { return (size_t)m * 8; }
     uint64_t *sreg; Params p;
     __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool) {
         p = pp; sreg = reinterpret_cast<uint64_t *>(smem);
@@ -391,7 +391,7 @@ template <class Consumer>
 inline size_t sketch_smem_bytes(uint32_t m, uint32_t score_slots) {
     size_t b = (size_t)SK_NWORDS * 8 + (size_t)(SK_NWORDS + (SK_NWORDS & 1)) * 4;
     if (score_slots) b += (size_t)SK_SCAP * 8 + 8;      // windowed: staged minimizers + counter
-    return b + (size_t)score_slots * 8 + Consumer::smem_bytes(m);
+    return b + (size_t)score_slots * 8 + Consumer::smem_bytes(m, score_slots != 0);
 }
 
 } // namespace d2g

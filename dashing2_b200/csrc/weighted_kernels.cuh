@@ -24,7 +24,7 @@ struct EmitConsumer {
     struct Params { uint64_t *out_hv; uint32_t *out_ent; uint64_t span; };   // both arrays have one slot per base, pre-filled with ~0
     static constexpr bool kEveryWindow = true;
     static constexpr int kMinBlocks = 4;
-    static __host__ __device__ size_t smem_bytes(uint32_t) { return 16; }
+    static __host__ __device__ size_t smem_bytes(uint32_t, bool) { return 16; }
     Params p; unsigned int *cur; uint32_t ent; uint64_t base;
     __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool) {
         p = pp; cur = reinterpret_cast<unsigned int *>(smem); base = (uint64_t)blockIdx.x * p.span; ent = 0xFFFFFFFFu;
