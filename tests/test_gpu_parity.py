@@ -68,7 +68,10 @@ def test_save_kmers_ids(golden_inputs):
 
 
 @pytest.mark.parametrize("mode,S,k,w", [("opmh", 1024, 31, -1), ("opmh", 4096, 31, 51), ("opmh", 333, 17, 40),
-                                         ("fss", 512, 31, -1), ("fss", 2048, 31, 51), ("opmh", 8192, 32, -1)])
+                                         ("fss", 512, 31, -1), ("fss", 2048, 31, 51), ("opmh", 8192, 32, -1),
+                                         # window shapes: 2, 4 (< 8 keys: direct scan), exactly 8, 9, many groups of eight, > one thread's reach
+                                         ("opmh", 256, 31, 32), ("opmh", 256, 31, 34), ("fss", 128, 31, 38), ("opmh", 512, 31, 39),
+                                         ("opmh", 256, 31, 200), ("fss", 64, 15, 400), ("opmh", 128, 11, 1000)])
 def test_sketch_matches_oracle_seeded(mode, S, k, w, tmp_path):
     """Seeded inputs larger than the goldens (multi-tile, multi-CTA, several entities per CTA span)."""
     from dashing2_b200 import synth
