@@ -285,9 +285,14 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                     uint64_t km[8];
                     const uint32_t bad = kmers8(W, M, off + npre + j0, k, kmask, true, km);
                     uint64_t *dst = score + sk_pad(OFF + j0);         // OFF + j0 is a multiple of 8: slots dst[0..7]
-                    #pragma unroll
-                    for (int j = 0; j < SK_PPT; ++j)
-                        if (j < jn) dst[j] = frev64(((bad >> j) & 1u) ? 0ULL : km[j]);
+                    if (jn == SK_PPT && bad == 0) {                     // the common case: a full chunk of valid k-mers
+                        #pragma unroll
+                        for (int j = 0; j < SK_PPT; ++j) dst[j] = frev64(km[j]);
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < SK_PPT; ++j)
+                            if (j < jn) dst[j] = frev64(((bad >> j) & 1u) ? 0ULL : km[j]);
+                    }
                 }
                 first = false;
                 __syncthreads();
@@ -318,10 +323,15 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                             left[j] = run;
                         }
                         run = ~0ULL;                                    // prefix minima of the own keys
-                        #pragma unroll
-                        for (int j = 0; j < SK_PPT; ++j) {
-                            if (j < jn) { run = min(run, own[j]); mn[j] = min(min(left[j], common), run); }
-                            else mn[j] = mn[j - 1];                     // j >= jn >= 1: repeat the last window (never emits)
+                        if (jn == SK_PPT) {
+                            #pragma unroll
+                            for (int j = 0; j < SK_PPT; ++j) { run = min(run, own[j]); mn[j] = min(min(left[j], common), run); }
+                        } else {
+                            #pragma unroll
+                            for (int j = 0; j < SK_PPT; ++j) {
+                                if (j < jn) { run = min(run, own[j]); mn[j] = min(min(left[j], common), run); }
+                                else mn[j] = mn[j - 1];                 // j >= jn >= 1: repeat the last window (never emits)
+                            }
                         }
                     } else {
                         #pragma unroll
