@@ -37,7 +37,7 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c
 # every symbol include/d2gpu.h declares
 EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stream", "d2g_sync", "d2g_launch_count",
            "d2g_set_timing", "d2g_get_timing",
-           "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
+           "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_distinct_kmers", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_free"]
 
@@ -70,6 +70,7 @@ def load():
     L.d2g_sketch_batch.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, vp, vp, vp, vp, C.POINTER(u64)]
     L.d2g_sketch_batch.restype = C.c_int
     L.d2g_opmh_finalize.argtypes = [vp, u32, u32, vp, vp]; L.d2g_opmh_finalize.restype = C.c_int
+    L.d2g_distinct_kmers.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, vp]; L.d2g_distinct_kmers.restype = C.c_int
     L.d2g_sketch_batch_dev.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, u64, vp, vp, vp, vp]
     L.d2g_sketch_batch_dev.restype = C.c_int
     L.d2g_densify.argtypes = [vp, vp, vp, u64, u32]; L.d2g_densify.restype = C.c_int
@@ -174,6 +175,15 @@ class Context:
         _check(self.L.d2g_sketch_batch(self.h, C.byref(p), _ptr(seq), _ptr(rec_off), _ptr(rec_entity), n_rec, n_entities,
                                        _ptr(regs), _ptr(sig), _ptr(card), _ptr(ids), C.byref(nk)))
         return dict(regs_u64=regs, sig=sig, card=card, ids=ids, n_kmers=int(nk.value))
+
+    def distinct_kmers(self, seq: np.ndarray, rec_off: np.ndarray, rec_entity: np.ndarray, n_entities: int, p: SketchParams) -> np.ndarray:
+        """Exact distinct k-mers (minimizers) per entity, host in / host out (d2g_distinct_kmers)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        rec_entity = np.ascontiguousarray(rec_entity, dtype=np.uint32)
+        out = np.empty(n_entities, dtype=np.uint64)
+        _check(self.L.d2g_distinct_kmers(self.h, C.byref(p), _ptr(seq), _ptr(rec_off), _ptr(rec_entity), len(rec_entity), n_entities, _ptr(out)))
+        return out
 
     def sketch_batch_dev(self, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
                          regs_u64_d=0, sig_d=0, card_d=0, ids_d=0):

@@ -517,6 +517,86 @@ void opmh_finalize_host(const uint64_t *regs, uint32_t n_ent, uint32_t m, uint32
 
 } // namespace
 
+// ---- exact distinct k-mers per entity (the --parse-by-seq small-cardinality fallback) -----------------
+namespace {
+// sorted (entity, value) stream: one count per run head, aggregated per warp and entity
+__global__ void distinct_count_kernel(const uint64_t *hv, const uint32_t *ent, uint64_t n, unsigned long long *cnt) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t e = 0xFFFFFFFFu; bool head = false;
+    if (i < n) { e = ent[i]; head = e != 0xFFFFFFFFu && (i == 0 || ent[i - 1] != e || hv[i - 1] != hv[i]); }
+    unsigned todo = __ballot_sync(0xffffffffu, head);
+    while (todo) {
+        const int leader = __ffs((int)todo) - 1;
+        const uint32_t le = __shfl_sync(0xffffffffu, e, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, head && e == le);
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(cnt + le, (unsigned long long)__popc(same));
+        todo &= ~same;
+    }
+}
+}
+
+extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const char *seq, const uint64_t *rec_off,
+                                  const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities, uint64_t *distinct_out) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    if (!distinct_out && n_entities) return fail(D2G_EINVAL, "null output");
+    if (n_rec && (!rec_off || !rec_entity)) return fail(D2G_EINVAL, "null record tables");
+    CU(cudaSetDevice(c->device));
+    const uint64_t n = n_rec ? rec_off[n_rec] : 0;
+    if (n && !seq) return fail(D2G_EINVAL, "null sequence buffer");
+    if (n_rec && rec_off[0] != 0) return fail(D2G_EINVAL, "rec_off[0] must be 0");
+    if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "distinct k-mers: at most 2^32 bases per call (got %llu)", (unsigned long long)n);
+    for (uint64_t r = 0; r < n_rec; ++r) {
+        if (rec_off[r + 1] < rec_off[r]) return fail(D2G_EINVAL, "rec_off not monotone at %llu", (unsigned long long)r);
+        if (rec_entity[r] >= n_entities) return fail(D2G_EINVAL, "rec_entity[%llu]=%u >= n_entities", (unsigned long long)r, rec_entity[r]);
+        if (r && rec_entity[r] < rec_entity[r - 1]) return fail(D2G_EINVAL, "rec_entity must be non-decreasing");
+    }
+    for (uint32_t e = 0; e < n_entities; ++e) distinct_out[e] = 0;
+    if (!n || !n_rec || !n_entities) return D2G_OK;
+    if (int rc = c->seq.reserve(n + 64)) return rc;
+    if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
+    if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->seq.p, seq, n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, st));
+    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
+    uint64_t off = 0;
+    const uint64_t o_hvA = off; off += al(n * 8 + 8);
+    const uint64_t o_hvB = off; off += al(n * 8 + 8);
+    const uint64_t o_entA = off; off += al(n * 4 + 4);
+    const uint64_t o_entB = off; off += al(n * 4 + 4);
+    const uint64_t o_cnt = off; off += al((uint64_t)n_entities * 8);
+    if (int rc = c->wbuf.reserve(off)) return rc;
+    unsigned char *B = c->wbuf.as<unsigned char>();
+    uint64_t *hvA = (uint64_t *)(B + o_hvA), *hvB = (uint64_t *)(B + o_hvB);
+    uint32_t *entA = (uint32_t *)(B + o_entA), *entB = (uint32_t *)(B + o_entB);
+    unsigned long long *cnt = (unsigned long long *)(B + o_cnt);
+    CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
+    CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
+    CU(cudaMemsetAsync(cnt, 0, (uint64_t)n_entities * 8, st));
+    d2g::SketchArgs a = make_sketch_args(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
+    if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
+    d2g::EmitConsumer::Params ep{hvA, entA, a.span};
+    if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    const size_t tb = std::max(t1, t2);
+    if (int rc = c->wtmp.reserve(tb + 256)) return rc;
+    size_t tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
+    tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    c->launches += 2 * 9;
+    distinct_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvA, entA, n, cnt);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(distinct_out, cnt, (uint64_t)n_entities * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return D2G_OK;
+}
+
 extern "C" int d2g_opmh_finalize(const uint64_t *regs_u64, uint32_t n_entities, uint32_t sketchsize, double *sig_out, double *card_out) {
     if (!regs_u64) return fail(D2G_EINVAL, "null registers");
     opmh_finalize_host(regs_u64, n_entities, d2g_opmh_m(sketchsize), sketchsize, sig_out, card_out);

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <chrono>
 #include <charconv>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -50,7 +51,7 @@ void chk(int rc) { if (rc) die(std::string("libd2gpu: ") + d2g_last_error()); }
 struct Opts {
     int k = -1, w = -1, nthreads = 1;
     uint64_t S = 1024, seed = 0;
-    bool canon = true, cache = false, save_kmers = false, presketched = false, binary = false;
+    bool canon = true, cache = false, save_kmers = false, presketched = false, binary = false, parse_by_seq = false;
     int mode = D2G_MODE_OPMH;            // ONE_PERM default (src/sketch_main.cpp:27)
     int measure = D2G_SIMILARITY;
     int shape = D2G_SYMMETRIC; bool phylip = false;
@@ -101,6 +102,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else if (a == "--cache" || a == "--cache-sketches" || a == "-W") o.cache = true;
         else if (a == "--save-kmers" || a == "-s") o.save_kmers = true;
         else if (a == "--presketched") o.presketched = true;
+        else if (a == "--parse-by-seq") o.parse_by_seq = true;
         else if (a == "--containment") o.measure = D2G_CONTAINMENT;
         else if (a == "--symmetric-containment") o.measure = D2G_SYMMETRIC_CONTAINMENT;
         else if (a == "--mash-distance" || a == "--distance" || a == "--poisson-distance") o.measure = D2G_POISSON_LLR;
@@ -111,7 +113,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
             std::printf("dashing2-gpu %s: drop-in for `dashing2 sketch|cmp` (k<=32 DNA; OPMH / Full SetSketch; dense all-pairs / panel).\n"
                         "Options follow the reference: -k -w -S -p -F -Q -o --cmpout --binary-output --phylip --asymmetric-all-pairs\n"
                         "--full-setsketch --oneperm -C/--no-canon --seed --cache --outprefix --save-kmers --presketched\n"
-                        "--containment --symmetric-containment --mash-distance --intersection --union-size --topk --fastcmp --bbit-sigs\n", d2g_version());
+                        "--containment --symmetric-containment --mash-distance --intersection --union-size --topk --fastcmp --bbit-sigs --parse-by-seq\n", d2g_version());
             std::exit(0);
         } else if (!a.empty() && a[0] == '-' && a.size() > 1) die("option " + a + " is not supported by the GPU front-end (see DESIGN.md section 7)");
         else o.paths.push_back(a);
@@ -149,8 +151,8 @@ std::string makedest(const Opts &o, const std::string &path) {   // src/fastxmer
 }
 
 // ---- FASTA/FASTQ records, kseq semantics ---------------------------------------------------------
-struct FileRecords { std::string seq; std::vector<uint64_t> ends; };
-void read_fastx(const std::string &path, FileRecords &out) {
+struct FileRecords { std::string seq; std::vector<uint64_t> ends; std::vector<std::string> names; };
+void read_fastx(const std::string &path, FileRecords &out, bool want_names = false) {
     gzFile fp = gzopen(path.c_str(), "rb");
     if (!fp) die("Could not open file at " + path + ". Abort!");
     gzbuffer(fp, 1 << 18);
@@ -164,7 +166,13 @@ void read_fastx(const std::string &path, FileRecords &out) {
         while (p < e && *p != '>' && *p != '@') { const char *le; next_line(p, le); p = le < e ? le + 1 : e; }
         if (p >= e) break;
         const bool fastq = *p == '@';
-        const char *le; next_line(p, le); p = le < e ? le + 1 : e;          // header line
+        const char *le; next_line(p, le);
+        if (want_names) {   // kseq: the name runs to the first white space; --parse-by-seq drops a leading '>' of the name itself (src/fastxsketchbyseq.cpp:276-277)
+            const char *b = p + 1, *t = b; while (t < le && !isspace((unsigned char)*t)) ++t;
+            if (b < t && *b == '>') ++b;
+            out.names.emplace_back(b, t - b);
+        }
+        p = le < e ? le + 1 : e;          // header line
         const size_t start = out.seq.size();
         while (p < e && *p != '>' && *p != '+' && *p != '@') {
             next_line(p, le);
@@ -218,19 +226,24 @@ struct LazyCtx {
 
 struct Sketches { std::vector<double> sig, card; std::vector<uint64_t> ids; std::vector<std::string> names; uint64_t S = 0; int mode = D2G_MODE_OPMH; };
 
+d2g_sketch_params sketch_params(const Opts &o) {
+    d2g_sketch_params p{};
+    p.k = o.k; p.w = o.w; p.canon = o.canon; p.mode = o.mode; p.sketchsize = (uint32_t)o.S;
+    p.xormask = 0;
+    if (o.seed) { // Wang(seed), src/enums.cpp:133-140
+        uint64_t key = o.seed; key = (~key) + (key << 21); key ^= key >> 24; key = (key + (key << 3)) + (key << 8); key ^= key >> 14;
+        key = (key + (key << 2)) + (key << 4); key ^= key >> 28; key += key << 31; p.xormask = key;
+    }
+    return p;
+}
+
 // ---- sketch all inputs through libd2gpu in batches -----------------------------------------------
 void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
     const size_t n = o.paths.size(), S = o.S;
     sk.S = S; sk.mode = o.mode; sk.names = o.paths;
     sk.sig.assign(n * S, 0.); sk.card.assign(n, 0.);
     if (o.save_kmers) sk.ids.assign(n * S, 0);
-    d2g_sketch_params p{};
-    p.k = o.k; p.w = o.w; p.canon = o.canon; p.mode = o.mode; p.sketchsize = (uint32_t)S;
-    p.xormask = 0;
-    if (o.seed) { // Wang(seed), src/enums.cpp:133-140
-        uint64_t key = o.seed; key = (~key) + (key << 21); key ^= key >> 24; key = (key + (key << 3)) + (key << 8); key ^= key >> 14;
-        key = (key + (key << 2)) + (key << 4); key ^= key >> 28; key += key << 31; p.xormask = key;
-    }
+    d2g_sketch_params p = sketch_params(o);
     std::vector<char> todo(n, 1);
     if (o.cache) {   // cache hit = load the per-file sketch (src/fastxsketch.cpp:327-373)
         for (size_t i = 0; i < n; ++i) {
@@ -297,6 +310,57 @@ void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
     }
 }
 
+// ---- --parse-by-seq: one sketch per record of ONE file (fastx2sketch_byseq, src/fastxsketchbyseq.cpp:102-283,284-531) ----
+// Records are the entities of d2g_sketch_batch; set sketches whose cardinality estimate is below 10 * S get the exact number
+// of distinct k-mers instead (:405-430), from d2g_distinct_kmers.
+void sketch_by_seq(LazyCtx &lctx, const Opts &o, Sketches &sk) {
+    if (o.paths.size() != 1) die("parse-by-seq currently only handles one file at a time. To process multiple files, simply concatenate them into one file, and run dashing2 on that.");
+    const size_t S = o.S;
+    FileRecords recs;
+    read_fastx(o.paths[0], recs, true);
+    g_timer.mark("read + parse records");
+    const size_t n = recs.ends.size();
+    sk.S = S; sk.mode = o.mode; sk.names = std::move(recs.names);
+    sk.sig.assign(n * S, 0.); sk.card.assign(n, 0.);
+    if (o.save_kmers) sk.ids.assign(n * S, 0);
+    d2g_sketch_params p = sketch_params(o);
+    const bool set_space = o.mode == D2G_MODE_OPMH || o.mode == D2G_MODE_FULL_SETSKETCH;
+    const size_t max_bases = size_t(1) << 30, max_ent = std::max<size_t>(1, (size_t(1) << 31) / (S * 8));
+    recs.seq.append(64, '\0');
+    std::vector<uint64_t> off; std::vector<uint32_t> ent;
+    for (size_t r0 = 0; r0 < n;) {
+        const uint64_t b0 = r0 ? recs.ends[r0 - 1] : 0;
+        size_t r1 = r0 + 1;
+        while (r1 < n && r1 - r0 < max_ent && recs.ends[r1] - b0 <= max_bases) ++r1;
+        const uint32_t ne = (uint32_t)(r1 - r0);
+        off.assign(1, 0); ent.clear();
+        for (size_t r = r0; r < r1; ++r) { off.push_back(recs.ends[r] - b0); ent.push_back((uint32_t)(r - r0)); }
+        chk(d2g_sketch_batch(lctx.get(), &p, recs.seq.data() + b0, off.data(), ent.data(), ne, ne, nullptr, sk.sig.data() + r0 * S, sk.card.data() + r0,
+                             o.save_kmers ? sk.ids.data() + r0 * S : nullptr, nullptr));
+        if (set_space) {
+            std::vector<size_t> small;
+            for (size_t r = r0; r < r1; ++r) {
+                if (std::isnan(sk.card[r])) sk.card[r] = 0.;
+                if (sk.card[r] < 10. * S) small.push_back(r);
+            }
+            if (!small.empty()) {
+                std::string sub; std::vector<uint64_t> soff{0}; std::vector<uint32_t> sent;
+                for (size_t r : small) {
+                    const uint64_t b = r ? recs.ends[r - 1] : 0;
+                    sub.append(recs.seq, b, recs.ends[r] - b);
+                    soff.push_back(sub.size()); sent.push_back((uint32_t)sent.size());
+                }
+                sub.append(64, '\0');
+                std::vector<uint64_t> distinct(small.size());
+                chk(d2g_distinct_kmers(lctx.get(), &p, sub.data(), soff.data(), sent.data(), sent.size(), (uint32_t)sent.size(), distinct.data()));
+                for (size_t t = 0; t < small.size(); ++t) sk.card[small[t]] = (double)distinct[t];
+            }
+        }
+        r0 = r1;
+    }
+    g_timer.mark("sketch records");
+}
+
 void write_stacked(const Opts &o, const Sketches &sk) {
     const uint64_t n = sk.card.size(), S = sk.S;
     std::FILE *fp = std::fopen(o.outfile.c_str(), "wb");
@@ -336,7 +400,7 @@ void load_stacked(const std::string &path, Sketches &sk) {   // src/cmp_main.cpp
 std::string options_string(const Opts &o, int mode) {   // Dashing2Options::to_string, src/d2.cpp:10-43
     std::string r = "Dashing2Options;k:" + std::to_string(o.k);
     if (o.w > 0) r += ";w:" + std::to_string(o.w);
-    r += ";parsebyfile;trimchr;sketchsize:" + std::to_string(o.S) + ";sketchtype:";
+    r += o.parse_by_seq ? ";parsebyseq" : ";parsebyfile"; r += ";trimchr;sketchsize:" + std::to_string(o.S) + ";sketchtype:";
     r += mode == D2G_MODE_OPMH ? "onepermsetsketch" : mode == D2G_MODE_FULL_SETSKETCH ? "fullsetsketch" : mode == D2G_MODE_BAGMINHASH ? "bagminhash" : "probminhash";
     r += ";Fastx";
     if (!o.outprefix.empty()) r += ";outprefix:" + o.outprefix;
@@ -444,7 +508,7 @@ int main(int argc, char **argv) {
         load_stacked(o.paths[0], sk);
         o.S = sk.S;
     } else {
-        sketch_inputs(lctx, o, sk);
+        if (o.parse_by_seq) sketch_by_seq(lctx, o, sk); else sketch_inputs(lctx, o, sk);
         if (!o.outfile.empty()) {
             // the reference densifies signatures_ in place before the stacked file is closed when --cmpout is given
             if (!o.cmpout.empty() && sk.mode == D2G_MODE_OPMH) chk(d2g_densify(lctx.get(), sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), sk.card.size(), (uint32_t)sk.S));

@@ -90,6 +90,15 @@ int d2g_sketch_batch(d2g_ctx *ctx, const d2g_sketch_params *p,
                      uint64_t *regs_u64_out, double *sig_out, double *card_out, uint64_t *ids_out,
                      uint64_t *n_kmers_hashed);
 
+/* Exact number of distinct k-mers (minimizers when w > k) per entity.  Replaces the small-cardinality fallback of
+ * --parse-by-seq (src/fastxsketchbyseq.cpp:405-430): when a set sketch's estimate is below 10 * sketchsize the reference walks
+ * the record again into a hash set of maskfn'd k-mers and stores its size as the cardinality.  Same record tables as
+ * d2g_sketch_batch (rec_off[0] == 0, at most 2^32 bases per call); only k, w, canon and xormask of the parameters matter
+ * (maskfn is a bijection, so the count does not depend on the seed).  distinct_out [n_entities], host memory. */
+int d2g_distinct_kmers(d2g_ctx *ctx, const d2g_sketch_params *p,
+                       const char *seq, const uint64_t *rec_off, const uint32_t *rec_entity,
+                       uint64_t n_rec, uint32_t n_entities, uint64_t *distinct_out);
+
 /* Host-side transform of OPMH bucket minima (host memory) into the reference's f64 signatures and
  * cardinality: sig = -1/(m-nempty) * logl(2^-64 * (2^64 - reg)), card = m*m / sum(reg * 2^-64), both in
  * x87 long double exactly as src/oph.h:240-263 does on the host. regs_u64 [n][d2g_opmh_m(S)]. */

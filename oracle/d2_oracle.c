@@ -609,6 +609,18 @@ uint64_t d2o_count_exact(uint64_t *hv, uint64_t n, uint64_t *keys, double *count
     return nd;
 }
 
+/* --parse-by-seq cardinality of one record's set sketch, src/fastxsketchbyseq.cpp:393-430: a NaN estimate becomes 0 (:398-402);
+ * an estimate below 10 * sketchsize is replaced by the exact number of distinct maskfn'd k-mers (minimizers) of the record,
+ * which the reference collects in a flat_hash_set by walking the record a second time (:405-422).  hv is sorted in place. */
+double d2o_byseq_cardinality(double estimate, uint64_t sketchsize, uint64_t *hv, uint64_t n) {
+    if (estimate != estimate) estimate = 0.;
+    if (!(estimate < 10. * (double)sketchsize)) return estimate;
+    qsort(hv, n, 8, cmp_u64);
+    uint64_t nd = 0;
+    for (uint64_t i = 0; i < n; ++i) nd += (i == 0 || hv[i] != hv[i - 1]);
+    return (double)nd;
+}
+
 /* value tree of bmh.h:53-91 (update returns -1 on equality, 1 when lowered, 0 otherwise) */
 static int bmh_mvt_update(double *d, uint32_t m, uint64_t index, double x) {
     const uint64_t sz = 2ULL * m - 1;

@@ -97,6 +97,9 @@ extern "C" {
 /* Sorts hv in place and run-length encodes it: keys[i] with counts[i]; returns the number of distinct keys.
  * (The reference counts in a hash map; sketches below are order independent, so sorted order is as good.) */
 uint64_t d2o_count_exact(uint64_t *hv, uint64_t n, uint64_t *keys, double *counts);
+/* --parse-by-seq (one sketch per record) cardinality rule for set sketches, src/fastxsketchbyseq.cpp:393-430: NaN -> 0, and an
+ * estimate < 10 * sketchsize is replaced by the exact number of distinct hashed k-mers of the record (hv is sorted in place). */
+double d2o_byseq_cardinality(double estimate, uint64_t sketchsize, uint64_t *hv, uint64_t n);
 /* ProbMinHash3 (bonsai/hll/include/sketch/bmh.h:662-700; base :545-661; truncated exponential :490-525).
  * regs f64[2m-1] (value tree), ids u64[m]; returns total weight. Elements with count <= threshold are skipped
  * (src/counter.h:123). */

@@ -60,6 +60,7 @@ def lib():
         getattr(L, nm).argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
     L.d2o_panel.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
     L.d2o_count_exact.restype = C.c_uint64; L.d2o_count_exact.argtypes = [u64p, C.c_uint64, u64p, f64p]
+    L.d2o_byseq_cardinality.restype = C.c_double; L.d2o_byseq_cardinality.argtypes = [C.c_double, C.c_uint64, u64p, C.c_uint64]
     L.d2o_pmh_reset.argtypes = [f64p, C.c_void_p, C.c_uint32]
     for nm in ("d2o_pmh_update", "d2o_bmh_update"):
         getattr(L, nm).restype = C.c_double
@@ -148,6 +149,24 @@ def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool =
     if mode in ("pmh", "bmh"):
         return weighted_sketch(hv, mode, S, count_threshold)
     raise ValueError(mode)
+
+
+def sketch_records_byseq(records, mode: str, S: int, k: int, w: int = -1, canon: bool = True, seed: int = 0):
+    """Oracle equivalent of --parse-by-seq (resize_fill, src/fastxsketchbyseq.cpp:284-531): one sketch per record; set sketches
+    with an estimate below 10 * S carry the exact distinct count.  Returns (cards f64[n], sigs f64[n][S])."""
+    import tempfile
+    L = lib()
+    cards, sigs = [], []
+    for rec in records:
+        with tempfile.NamedTemporaryFile(suffix=".fa") as f:
+            f.write(b">r\n" + rec + b"\n"); f.flush()
+            o = sketch_file(f.name, mode, S, k, w, canon, seed)
+        card = o["card"]
+        if mode in ("opmh", "fss"):
+            hv = hash_stream(rec, k, w, canon, seed)
+            card = L.d2o_byseq_cardinality(card, S, hv, len(hv))
+        cards.append(card); sigs.append(o["sig"])
+    return np.asarray(cards), np.stack(sigs) if sigs else np.empty((0, S))
 
 
 def weighted_sketch(hv: np.ndarray, mode: str, S: int, count_threshold: float = 0.0):

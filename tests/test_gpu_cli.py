@@ -124,6 +124,31 @@ def test_multiset_and_prob_cache_files(golden_inputs, tmp_path):
         assert d[0] == z["cards"][0] and np.array_equal(d[1:], z["sigs"][0])
 
 
+@pytest.mark.parametrize("case,argv", [("byseq_opmh_k31_S64", ["-k31", "-S64"]), ("byseq_opmh_k21_w30_S64", ["-k21", "-w30", "-S64"]),
+                                       ("byseq_fss_k31_S64", ["-k31", "-S64", "--full-setsketch"]), ("byseq_bmh_k31_S32", ["-k31", "-S32", "--multiset"]),
+                                       ("byseq_pmh_k31_S32", ["-k31", "-S32", "--prob"])])
+def test_parse_by_seq_stacked_file_names_and_matrix(case, argv, tmp_path):
+    """`sketch --parse-by-seq`: one sketch per record, record names, exact cardinalities below 10 * S, and the all-pairs matrix
+    of the same run -- the stacked file and the matrix byte for byte as the reference binary wrote them."""
+    import gzip
+    fa = str(tmp_path / "byseq.fa")
+    open(fa, "wb").write(gzip.open(os.path.join(GOLD, "inputs", "byseq.fa.gz"), "rb").read())
+    z = np.load(expected(case + ".npz"))
+    out = str(tmp_path / "out.stk"); mat = str(tmp_path / "out.f32")
+    extra = ["--binary-output", "--cmpout", mat] if "mat" in z.files else []
+    run(["sketch", "--parse-by-seq", "-p2", "-o", out] + argv + extra + [fa])
+    cards, sigs = read_stacked(out)
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64))
+    if "fss" in case:
+        np.testing.assert_allclose(cards, z["cards"], rtol=1e-12)
+    else:
+        assert np.array_equal(cards, z["cards"])
+    lines = open(out + ".names.txt").read().splitlines()
+    assert [l.split("\t")[0] for l in lines[1:]] == list(z["names"])
+    if extra:   # similarity does not involve the cardinalities
+        assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), z["mat"].view(np.uint32))
+
+
 def test_cmp_topk_csr_file(tmp_path):
     from dashing2_b200 import synth
     z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
@@ -137,7 +162,7 @@ def test_cmp_topk_csr_file(tmp_path):
 
 def test_unsupported_options_fail_loudly(golden_inputs):
     names, paths = golden_inputs
-    for argv in (["sketch", "-k31", "--countsketch-size", "1000", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0]],
+    for argv in (["sketch", "-k31", "--countsketch-size", "1000", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0], paths[1]],
                  ["contain", paths[0]]):
         r = subprocess.run([EXE] + argv, capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.strip()

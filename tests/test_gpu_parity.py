@@ -67,6 +67,99 @@ def test_save_kmers_ids(golden_inputs):
     assert np.array_equal(r["ids"], z["ids"])
 
 
+BYSEQ = {
+    "byseq_opmh_k31_S64": dict(mode="opmh", S=64, k=31),
+    "byseq_opmh_k21_w30_S64": dict(mode="opmh", S=64, k=21, w=30),
+    "byseq_opmh_k15_S16_nocanon": dict(mode="opmh", S=16, k=15, canon=False),
+    "byseq_fss_k31_S64": dict(mode="fss", S=64, k=31),
+    "byseq_fss_k21_w30_S32": dict(mode="fss", S=32, k=21, w=30),
+    "byseq_bmh_k31_S32": dict(mode="bmh", S=32, k=31),
+    "byseq_pmh_k31_S32": dict(mode="pmh", S=32, k=31),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BYSEQ))
+def test_parse_by_seq_matches_reference_golden(case):
+    """--parse-by-seq (src/fastxsketchbyseq.cpp:284-531): records are the entities of d2g_sketch_batch (empty records, records
+    shorter than k / w, Ns, entity changes inside a tile); estimates below 10 * S are replaced by d2g_distinct_kmers."""
+    kw = BYSEQ[case]; S = kw["S"]
+    z = np.load(expected(case + ".npz"))
+    recs = O.read_fastx(os.path.join(GOLD, "inputs", "byseq.fa.gz"))
+    c = ctx()
+    seq, off, ent = pack_batch([[r] for r in recs])
+    p = c.params(**kw)
+    r = c.sketch_batch(seq, off, ent, len(recs), p)
+    sig, card = r["sig"], r["card"].copy()
+    if "mat" in z.files and kw["mode"] == "opmh":
+        sig = c.densify(sig)
+    assert np.array_equal(u64(sig), u64(z["sigs"]))
+    if kw["mode"] in ("opmh", "fss"):
+        card[np.isnan(card)] = 0.
+        small = np.flatnonzero(card < 10 * S)
+        assert len(small) >= 6
+        sseq, soff, sent = pack_batch([[recs[i]] for i in small])
+        d = c.distinct_kmers(sseq, soff, sent, len(small), p)
+        card[small] = d
+        assert np.array_equal(card[small], z["cards"][small])
+        # every record at once gives the same counts
+        assert np.array_equal(c.distinct_kmers(seq, off, ent, len(recs), p)[small], d)
+    if kw["mode"] == "fss":
+        np.testing.assert_allclose(card, z["cards"], rtol=1e-12)
+    else:
+        assert np.array_equal(card, z["cards"])
+    if "mat" in z.files:
+        got = c.cmp_matrix(sig, card if kw["mode"] != "fss" else z["cards"], c.cmp_params(S, len(recs), "symmetric", "similarity", k=kw["k"]))
+        assert np.array_equal(got.view(np.uint32), z["mat"].view(np.uint32))
+
+
+@pytest.mark.parametrize("k,w,canon", [(31, -1, True), (21, 30, True), (15, -1, False), (11, 50, True), (32, -1, True)])
+def test_distinct_kmers_matches_oracle_seeded(k, w, canon):
+    """Exact distinct k-mers / minimizers per entity against the oracle's hashed stream, on reads with repeats, Ns, lower case,
+    empty records, several records per entity and entities of very different sizes."""
+    rng = np.random.default_rng(1000 + k + (w if w > 0 else 0))
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    ents = []
+    for e in range(300):
+        nrec = 1 if e % 7 else 3
+        recs = []
+        for _ in range(nrec):
+            L = int(rng.choice([0, 5, k - 1, k, k + 3, 80, 150, 151, 1000, 20000 if e % 50 == 0 else 300]))
+            a = acgt[rng.integers(0, 4 if e % 3 else 2, size=L)].copy()
+            if L > 60 and e % 4 == 0:
+                a[L // 2:L // 2 + 30] = a[:30]           # repeated content
+            if L > 40 and e % 5 == 0:
+                a[rng.integers(0, L, size=2)] = ord("N")
+            b = a.tobytes()
+            recs.append(b.lower() if e % 11 == 0 else b)
+        ents.append(recs)
+    c = ctx()
+    seq, off, ent = pack_batch(ents)
+    got = c.distinct_kmers(seq, off, ent, len(ents), c.params(mode="opmh", S=64, k=k, w=w, canon=canon))
+    exp = np.array([len(np.unique(np.concatenate([O.hash_stream(r, k, w, canon) for r in recs] + [np.empty(0, np.uint64)]))) for recs in ents], dtype=np.uint64)
+    assert np.array_equal(got, exp)
+    # seed independence (maskfn is a bijection)
+    assert np.array_equal(c.distinct_kmers(seq, off, ent, len(ents), c.params(mode="opmh", S=64, k=k, w=w, canon=canon, seed=9)), exp)
+
+
+@pytest.mark.parametrize("mode,S,k,w", [("opmh", 64, 31, -1), ("opmh", 256, 21, 30), ("fss", 64, 31, -1), ("fss", 32, 15, 40)])
+def test_many_small_entities_match_oracle(mode, S, k, w):
+    """Thousands of read-sized entities in one batch (the --parse-by-seq shape): every record's registers against the oracle."""
+    rng = np.random.default_rng(77 + S + k)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs = []
+    for e in range(1500):
+        L = int(rng.choice([0, 20, k, 100, 150, 250, 700]))
+        a = acgt[rng.integers(0, 4, size=L)].copy()
+        if L > 40 and e % 9 == 0:
+            a[rng.integers(0, L)] = ord("N")
+        recs.append(a.tobytes())
+    c = ctx()
+    seq, off, ent = pack_batch([[r] for r in recs])
+    r = c.sketch_batch(seq, off, ent, len(recs), c.params(mode=mode, S=S, k=k, w=w))
+    cards, sigs = O.sketch_records_byseq(recs, mode, S, k, w)
+    assert np.array_equal(u64(r["sig"]), u64(sigs))
+
+
 @pytest.mark.parametrize("mode,S,k,w", [("opmh", 1024, 31, -1), ("opmh", 4096, 31, 51), ("opmh", 333, 17, 40),
                                          ("fss", 512, 31, -1), ("fss", 2048, 31, 51), ("opmh", 8192, 32, -1),
                                          # window shapes: 2, 4 (< 8 keys: direct scan), exactly 8, 9, many groups of eight, > one thread's reach

@@ -138,3 +138,36 @@ def test_compressed_compare_matches_reference(fd, bbit):
         exp = np.load(expected(f"cmpc_sk48_fd{fd}_{'bbit' if bbit else 'ss'}_{kind}.npy"))
         got = O.allpairs_compressed(creg, z["cards"], shape, measure, fd, bbit, b, k=32)
         assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (fd, bbit, kind)
+
+
+BYSEQ = {
+    "byseq_opmh_k31_S64": dict(mode="opmh", S=64, k=31),
+    "byseq_opmh_k21_w30_S64": dict(mode="opmh", S=64, k=21, w=30),
+    "byseq_opmh_k15_S16_nocanon": dict(mode="opmh", S=16, k=15, canon=False),
+    "byseq_fss_k31_S64": dict(mode="fss", S=64, k=31),
+    "byseq_fss_k21_w30_S32": dict(mode="fss", S=32, k=21, w=30),
+    "byseq_bmh_k31_S32": dict(mode="bmh", S=32, k=31),
+    "byseq_pmh_k31_S32": dict(mode="pmh", S=32, k=31),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BYSEQ))
+def test_parse_by_seq_matches_reference(case):
+    """--parse-by-seq (src/fastxsketchbyseq.cpp): one sketch per record, exact distinct count below 10 * S, against the
+    stacked files the reference binary wrote (tests/golden/make_golden_byseq.py)."""
+    z = np.load(expected(case + ".npz"))
+    recs = O.read_fastx(os.path.join(GOLD, "inputs", "byseq.fa.gz"))
+    assert len(recs) == len(z["cards"]) == 16
+    cards, sigs = O.sketch_records_byseq(recs, **BYSEQ[case])
+    if "mat" in z.files and BYSEQ[case]["mode"] == "opmh":      # sketch --cmpout densifies the signatures in place before the file is closed
+        sigs = np.stack([O.densify(s) for s in sigs])
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64))
+    if BYSEQ[case]["mode"] == "fss":
+        np.testing.assert_allclose(cards, z["cards"], rtol=1e-12)
+        small = z["cards"] < 10 * BYSEQ[case]["S"]
+        assert small.any() and np.array_equal(cards[small], z["cards"][small])     # the exact counts are exact
+    else:
+        assert np.array_equal(cards, z["cards"])
+    if "mat" in z.files:
+        got = O.allpairs(sigs, cards, "symmetric", "similarity", k=BYSEQ[case]["k"])
+        assert np.array_equal(got.view(np.uint32), z["mat"].view(np.uint32))
