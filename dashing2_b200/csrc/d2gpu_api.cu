@@ -198,8 +198,9 @@ int check_sketch_params(const d2g_sketch_params *p) {
     }
     if (p->mode < D2G_MODE_OPMH || p->mode > D2G_MODE_PROBMINHASH) return fail(D2G_EINVAL, "bad sketch mode %d", p->mode);
     if ((p->mode == D2G_MODE_BAGMINHASH || p->mode == D2G_MODE_PROBMINHASH) && p->sketchsize < 2) return fail(D2G_EINVAL, "weighted sketches need sketchsize >= 2");
-    if (p->count_threshold > 1 && (p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH))
-        return fail(D2G_EUNSUPPORTED, "--count-threshold > 1 is implemented for the counting sketches (--multiset/--prob) only");
+    if (p->count_threshold > 1 && p->mode == D2G_MODE_FULL_SETSKETCH)
+        return fail(D2G_EUNSUPPORTED, "--count-threshold > 1 with --full-setsketch (CountFilteredCSetSketch, src/setsketch.h:1000-1132: the result depends on "
+                                      "the order of the k-mers) is not implemented on the GPU; one-permutation and the counting sketches are");
     if (p->countsketch_size) return fail(D2G_EUNSUPPORTED, "--countsketch-size not implemented on the GPU");
     return D2G_OK;
 }
@@ -517,6 +518,68 @@ void opmh_finalize_host(const uint64_t *regs, uint32_t n_ent, uint32_t m, uint32
 
 } // namespace
 
+// ---- One-permutation MinHash with --count-threshold c > 1 (oph.h:188-205) ----------------------------
+// The reference promotes a candidate of a bucket once it has been seen c times while it is below the bucket's register, and then
+// drops the candidates above it; candidates below survive.  The register therefore ends as the minimum over the ids of the bucket seen
+// at least c times, whatever the order -- only the multiplicity field (not part of the signature) depends on the order.  Device:
+// emit every k-mer / window (as the counting sketches do), sort by (entity, value), and let the head of every run that is at least c
+// long update its bucket.
+namespace {
+__global__ void opmh_mincount_kernel(const uint64_t *hv, const uint32_t *ent, uint64_t n, uint32_t c, uint64_t *regs, d2g::FastMod32 fm, uint32_t m) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t e = ent[i];
+    if (e == 0xFFFFFFFFu) return;
+    const uint64_t v = hv[i];
+    if (i && ent[i - 1] == e && hv[i - 1] == v) return;              // not a run head
+    const uint64_t last = i + c - 1;                                  // sorted: the run is at least c long iff element i+c-1 still belongs to it
+    if (last >= n || ent[last] != e || hv[last] != v) return;
+    const uint64_t id = d2g::dhash(v);                                // oph.h:178
+    const uint32_t idx = d2g::fastmod32((uint32_t)id, fm);            // oph.h:184
+    atomicMin(reinterpret_cast<unsigned long long *>(regs + (uint64_t)e * m + idx), (unsigned long long)id);
+}
+
+int launch_opmh_mincount(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+                         uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d) {
+    const uint32_t m = d2g_opmh_m(p->sketchsize);
+    const uint64_t n = total_len, nreg = (uint64_t)n_ent * m;
+    cudaStream_t st = c->stream;
+    if (nreg) { fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, st>>>(regs_d, nreg, ~0ULL); c->launches++; }
+    if (!n || !n_rec) return D2G_OK;
+    if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "--count-threshold: at most 2^32 bases per batch (got %llu)", (unsigned long long)n);
+    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
+    uint64_t off = 0;
+    const uint64_t o_hvA = off; off += al(n * 8 + 8);
+    const uint64_t o_hvB = off; off += al(n * 8 + 8);
+    const uint64_t o_entA = off; off += al(n * 4 + 4);
+    const uint64_t o_entB = off; off += al(n * 4 + 4);
+    if (int rc = c->wbuf.reserve(off)) return rc;
+    unsigned char *B = c->wbuf.as<unsigned char>();
+    uint64_t *hvA = (uint64_t *)(B + o_hvA), *hvB = (uint64_t *)(B + o_hvB);
+    uint32_t *entA = (uint32_t *)(B + o_entA), *entB = (uint32_t *)(B + o_entB);
+    CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
+    CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, 0, SketchRange{0, total_len, 0});
+    if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
+    d2g::EmitConsumer::Params ep{hvA, entA, a.span};
+    if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    const size_t tb = std::max(t1, t2);
+    if (int rc = c->wtmp.reserve(tb + 256)) return rc;
+    size_t tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
+    tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    c->launches += 2 * 9;
+    opmh_mincount_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvA, entA, n, p->count_threshold, regs_d, d2g::make_fastmod32(m), m);
+    c->launches++;
+    CU(cudaGetLastError());
+    return D2G_OK;
+}
+}
+
 // ---- exact distinct k-mers per entity (the --parse-by-seq small-cardinality fallback) -----------------
 namespace {
 // sorted (entity, value) stream: one count per run head, aggregated per warp and entity
@@ -614,7 +677,8 @@ extern "C" int d2g_sketch_batch_dev(d2g_ctx *c, const d2g_sketch_params *p, cons
             return fail(D2G_EINVAL, "OPMH signatures/cardinalities are x87 long-double transforms of the u64 minima (src/oph.h:240-263): "
                                     "take regs_u64_out_d and call d2g_opmh_finalize on the host");
         if (!regs_u64_out_d) return fail(D2G_EINVAL, "regs_u64_out_d required for OPMH");
-        if (int rc = launch_opmh(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, regs_u64_out_d)) return rc;
+        if (int rc = p->count_threshold > 1 ? launch_opmh_mincount(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, regs_u64_out_d)
+                                             : launch_opmh(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, regs_u64_out_d)) return rc;
         if (ids_out_d) {
             const uint64_t n = (uint64_t)n_entities * p->sketchsize;
             opmh_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(regs_u64_out_d, ids_out_d, n_entities, d2g_opmh_m(p->sketchsize), p->sketchsize);
@@ -653,7 +717,8 @@ extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const ch
     const char *seq_d = c->seq.as<char>();
     const uint64_t *off_d = c->recoff.as<uint64_t>();
     const uint32_t *ent_d = c->recent.as<uint32_t>();
-    const bool chunked = p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH;
+    const bool opmh_mincount = p->mode == D2G_MODE_OPMH && p->count_threshold > 1;   // counts need the whole batch sorted at once
+    const bool chunked = (p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH) && !opmh_mincount;
     auto off_at = [&](uint64_t r) -> uint64_t { return n_rec ? rec_off[r] : 0; };
     // Chunks of whole entities (~D2G_CHUNK_BYTES of sequence each, default 256 MiB): the upload of chunk i+1 runs on the copy
     // stream while chunk i is sketched, so a large batch moves at PCIe speed instead of copy + compute.
@@ -700,7 +765,9 @@ extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const ch
         const uint64_t nr = ch.r1 - ch.r0; const uint32_t ne = ch.e1 - ch.e0;
         const SketchRange rg{off_at(ch.r0), off_at(ch.r1), ch.e0};
         int rc;
-        if (p->mode == D2G_MODE_OPMH)
+        if (opmh_mincount)
+            rc = launch_opmh_mincount(c, p, seq_d, off_d, ent_d, n_rec, n_entities, total_len, c->regs.as<uint64_t>());
+        else if (p->mode == D2G_MODE_OPMH)
             rc = launch_opmh(c, p, seq_d, off_d + ch.r0, ent_d + ch.r0, nr, ne, rg.pos_end, c->regs.as<uint64_t>() + (uint64_t)ch.e0 * m, &rg);
         else if (p->mode == D2G_MODE_FULL_SETSKETCH)
             rc = launch_fss(c, p, seq_d, off_d + ch.r0, ent_d + ch.r0, nr, ne, rg.pos_end, c->sig.as<double>() + (uint64_t)ch.e0 * S,

@@ -56,6 +56,7 @@ struct Opts {
     int measure = D2G_SIMILARITY;
     int shape = D2G_SYMMETRIC; bool phylip = false;
     int topk = -1;
+    unsigned count_threshold = 0;          // -m / --count-threshold (src/options.h:83-84,352)
     double fastcmp = 8.; bool bbit = false;   // --fastcmp/--regsize N, --bbit-sigs (src/options.h:76,101)
     std::string ffile, qfile, outfile, cmpout, outprefix;
     std::vector<std::string> paths;
@@ -85,6 +86,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else if (a == "--cmpout" || a == "--distout" || a == "--cmp-outfile") o.cmpout = arg();
         else if (a == "--outprefix" || a == "--prefix") o.outprefix = arg();
         else if (a == "--seed") o.seed = std::stoull(arg());
+        else if (a == "--count-threshold" || a == "--threshold" || shortarg("-m")) o.count_threshold = (unsigned)std::max(0, std::atoi(arg().c_str()));
         else if (a == "--topk" || a == "--top-k" || shortarg("-K")) o.topk = std::stoi(arg());
         else if (a == "--fastcmp" || a == "--regsize") {
             o.fastcmp = std::atof(arg().c_str());
@@ -113,7 +115,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
             std::printf("dashing2-gpu %s: drop-in for `dashing2 sketch|cmp` (k<=32 DNA; OPMH / Full SetSketch; dense all-pairs / panel).\n"
                         "Options follow the reference: -k -w -S -p -F -Q -o --cmpout --binary-output --phylip --asymmetric-all-pairs\n"
                         "--full-setsketch --oneperm -C/--no-canon --seed --cache --outprefix --save-kmers --presketched\n"
-                        "--containment --symmetric-containment --mash-distance --intersection --union-size --topk --fastcmp --bbit-sigs --parse-by-seq\n", d2g_version());
+                        "--containment --symmetric-containment --mash-distance --intersection --union-size --topk --fastcmp --bbit-sigs --parse-by-seq -m/--count-threshold\n", d2g_version());
             std::exit(0);
         } else if (!a.empty() && a[0] == '-' && a.size() > 1) die("option " + a + " is not supported by the GPU front-end (see DESIGN.md section 7)");
         else o.paths.push_back(a);
@@ -143,6 +145,7 @@ std::string makedest(const Opts &o, const std::string &path) {   // src/fastxmer
     if (o.canon) ret += ".rc_canon";
     ret += ".sketchsize" + std::to_string(o.S) + ".k" + std::to_string(o.k);
     if (o.w > o.k) ret += ".w" + std::to_string(o.w);
+    if (o.count_threshold > 0) ret += ".ct_threshold" + std::to_string(o.count_threshold);
     const bool counted = o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH;
     if (counted) ret += ".ExactCounting";
     ret += '.';
@@ -228,7 +231,7 @@ struct Sketches { std::vector<double> sig, card; std::vector<uint64_t> ids; std:
 
 d2g_sketch_params sketch_params(const Opts &o) {
     d2g_sketch_params p{};
-    p.k = o.k; p.w = o.w; p.canon = o.canon; p.mode = o.mode; p.sketchsize = (uint32_t)o.S;
+    p.k = o.k; p.w = o.w; p.canon = o.canon; p.mode = o.mode; p.sketchsize = (uint32_t)o.S; p.count_threshold = o.count_threshold;
     p.xormask = 0;
     if (o.seed) { // Wang(seed), src/enums.cpp:133-140
         uint64_t key = o.seed; key = (~key) + (key << 21); key ^= key >> 24; key = (key + (key << 3)) + (key << 8); key ^= key >> 14;
@@ -325,6 +328,10 @@ void sketch_by_seq(LazyCtx &lctx, const Opts &o, Sketches &sk) {
     if (o.save_kmers) sk.ids.assign(n * S, 0);
     d2g_sketch_params p = sketch_params(o);
     const bool set_space = o.mode == D2G_MODE_OPMH || o.mode == D2G_MODE_FULL_SETSKETCH;
+    // The reference's per-thread copies of the sketcher are made by OptSketcher's copy constructor, which builds a fresh
+    // OPSetSketch(size) (src/fastxsketchbyseq.cpp:36,46,220-225): the one-permutation sketch loses its mincount, so -m has no
+    // effect on set sketches here (verified against the binary, tests/golden/make_golden_mincount.py).  Counting sketches keep it (:462,470).
+    if (o.mode == D2G_MODE_OPMH) p.count_threshold = 0;
     const size_t max_bases = size_t(1) << 30, max_ent = std::max<size_t>(1, (size_t(1) << 31) / (S * 8));
     recs.seq.append(64, '\0');
     std::vector<uint64_t> off; std::vector<uint32_t> ent;
@@ -400,7 +407,9 @@ void load_stacked(const std::string &path, Sketches &sk) {   // src/cmp_main.cpp
 std::string options_string(const Opts &o, int mode) {   // Dashing2Options::to_string, src/d2.cpp:10-43
     std::string r = "Dashing2Options;k:" + std::to_string(o.k);
     if (o.w > 0) r += ";w:" + std::to_string(o.w);
-    r += o.parse_by_seq ? ";parsebyseq" : ";parsebyfile"; r += ";trimchr;sketchsize:" + std::to_string(o.S) + ";sketchtype:";
+    r += o.parse_by_seq ? ";parsebyseq" : ";parsebyfile"; r += ";trimchr;sketchsize:" + std::to_string(o.S);
+    if (o.count_threshold > 0) r += ";" + std::to_string(o.count_threshold);
+    r += ";sketchtype:";
     r += mode == D2G_MODE_OPMH ? "onepermsetsketch" : mode == D2G_MODE_FULL_SETSKETCH ? "fullsetsketch" : mode == D2G_MODE_BAGMINHASH ? "bagminhash" : "probminhash";
     r += ";Fastx";
     if (!o.outprefix.empty()) r += ";outprefix:" + o.outprefix;

@@ -62,7 +62,8 @@ typedef struct {
     int32_t mode;              /* D2G_MODE_* */
     uint64_t xormask;          /* maskfn XOR mask: 0 for --seed 0, else Wang(seed) (src/enums.cpp:133) */
     uint32_t sketchsize;       /* S */
-    uint32_t count_threshold;  /* --count-threshold; 0/1 = off */
+    uint32_t count_threshold;  /* -m / --count-threshold; 0/1 = off.  OPMH: register = min id seen >= c times (oph.h:188-205); counting
+                                  sketches: elements with count <= c are skipped (counter.h:123); Full SetSketch: D2G_EUNSUPPORTED */
     uint64_t countsketch_size; /* --countsketch-size; 0 = exact counting */
 } d2g_sketch_params;
 

@@ -149,6 +149,25 @@ def test_parse_by_seq_stacked_file_names_and_matrix(case, argv, tmp_path):
         assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), z["mat"].view(np.uint32))
 
 
+def test_count_threshold_per_file_and_by_seq(tmp_path):
+    """`sketch -m 2`: reference-named cache files (.ct_threshold2) and stacked file; `--parse-by-seq -m 2` reproduces the reference,
+    whose per-record one-permutation sketches ignore the threshold."""
+    import gzip
+    paths = []
+    for f in ("rep.fa", "dup.fa", "g0.fa", "adv.fa"):
+        p = str(tmp_path / f); open(p, "wb").write(gzip.open(os.path.join(GOLD, "inputs", f + ".gz"), "rb").read()); paths.append(p)
+    z = np.load(expected("mincount2_opmh_k31_S64.npz"))
+    out = str(tmp_path / "out.stk"); cdir = tmp_path / "cache"; cdir.mkdir()
+    run(["sketch", "-k31", "-S64", "-m", "2", "-o", out, "--cache", "--outprefix", str(cdir)] + paths)
+    cards, sigs = read_stacked(out)
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64)) and np.array_equal(cards, z["cards"])
+    assert (cdir / "rep.fa.rc_canon.sketchsize64.k31.ct_threshold2.SetSpace.DNA.opss").exists()
+    out2 = str(tmp_path / "byseq.stk")
+    run(["sketch", "--parse-by-seq", "-k31", "-S64", "--count-threshold", "2", "-o", out2, paths[0]])
+    cards, sigs = read_stacked(out2)
+    assert np.array_equal(sigs.view(np.uint64), z["byseq_sigs"].view(np.uint64)) and np.array_equal(cards, z["byseq_cards"])
+
+
 def test_cmp_topk_csr_file(tmp_path):
     from dashing2_b200 import synth
     z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))

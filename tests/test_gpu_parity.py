@@ -112,6 +112,49 @@ def test_parse_by_seq_matches_reference_golden(case):
         assert np.array_equal(got.view(np.uint32), z["mat"].view(np.uint32))
 
 
+MINCOUNT = {
+    "mincount2_opmh_k31_S64": dict(S=64, k=31, count_threshold=2),
+    "mincount3_opmh_k21_S128": dict(S=128, k=21, count_threshold=3),
+    "mincount2_opmh_k21_w30_S64": dict(S=64, k=21, w=30, count_threshold=2),
+}
+
+
+@pytest.mark.parametrize("case", sorted(MINCOUNT))
+def test_opmh_count_threshold_matches_reference_golden(case):
+    """-m c with the one-permutation sketch (src/oph.h:188-205): register = minimum over the ids of the bucket seen >= c times."""
+    z = np.load(expected(case + ".npz"))
+    paths = [os.path.join(GOLD, "inputs", f) for f in ("rep.fa.gz", "dup.fa.gz", "g0.fa.gz", "adv.fa.gz")]
+    c = ctx()
+    seq, off, ent = pack_files(paths)
+    r = c.sketch_batch(seq, off, ent, len(paths), c.params(mode="opmh", **MINCOUNT[case]))
+    assert np.array_equal(u64(r["sig"]), u64(z["sigs"])) and np.array_equal(r["card"], z["cards"])
+
+
+@pytest.mark.parametrize("S,k,w,thr", [(256, 31, -1, 2), (333, 17, 40, 3), (1024, 21, -1, 3), (64, 31, 51, 2)])
+def test_opmh_count_threshold_matches_oracle_seeded(S, k, w, thr):
+    from dashing2_b200 import synth
+    files = []
+    for g, s in synth.family_genomes(5, 40000, seed=300 + S, dup_frac=0.4):
+        b = s.tobytes() if hasattr(s, "tobytes") else bytes(s)
+        files.append([b[:25000], b[20000:] + b"N" + b[:3000], b"", b[100:100 + k - 1]])
+    files.append([b""])                                   # an entity without a single k-mer
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    r = c.sketch_batch(seq, off, ent, len(files), c.params(mode="opmh", S=S, k=k, w=w, count_threshold=thr))
+    L = O.lib(); m = L.d2o_opmh_m(S)
+    for e, recs in enumerate(files):
+        hv = np.concatenate([O.hash_stream(x, k, w) for x in recs] + [np.empty(0, np.uint64)])
+        regs = np.empty(m, dtype=np.uint64); counts = np.empty(m, dtype=np.float64)
+        L.d2o_opmh_reset(regs, counts, m)
+        L.d2o_opmh_update_mincount(regs, counts, m, hv, len(hv), float(thr))
+        assert np.array_equal(r["regs_u64"][e], regs), e
+        # order independence of the registers (the reference's candidate maps are order dependent only in the multiplicities)
+        L.d2o_opmh_reset(regs, counts, m); hv2 = hv[::-1].copy()
+        L.d2o_opmh_update_mincount(regs, counts, m, hv2, len(hv2), float(thr))
+        assert np.array_equal(r["regs_u64"][e], regs), e
+    assert (r["regs_u64"][:5] != np.uint64(2**64 - 1)).any()
+
+
 @pytest.mark.parametrize("k,w,canon", [(31, -1, True), (21, 30, True), (15, -1, False), (11, 50, True), (32, -1, True)])
 def test_distinct_kmers_matches_oracle_seeded(k, w, canon):
     """Exact distinct k-mers / minimizers per entity against the oracle's hashed stream, on reads with repeats, Ns, lower case,

@@ -171,3 +171,29 @@ def test_parse_by_seq_matches_reference(case):
     if "mat" in z.files:
         got = O.allpairs(sigs, cards, "symmetric", "similarity", k=BYSEQ[case]["k"])
         assert np.array_equal(got.view(np.uint32), z["mat"].view(np.uint32))
+
+
+MINCOUNT = {
+    "mincount2_opmh_k31_S64": dict(S=64, k=31, count_threshold=2),
+    "mincount3_opmh_k21_S128": dict(S=128, k=21, count_threshold=3),
+    "mincount2_opmh_k21_w30_S64": dict(S=64, k=21, w=30, count_threshold=2),
+}
+MINCOUNT_FILES = ["rep.fa.gz", "dup.fa.gz", "g0.fa.gz", "adv.fa.gz"]
+
+
+@pytest.mark.parametrize("case", sorted(MINCOUNT))
+def test_opmh_count_threshold_matches_reference(case):
+    """-m c (src/oph.h:188-205) per file, and the reference's --parse-by-seq quirk: its per-thread sketcher copies drop the
+    mincount, so the one-permutation sketch of a record is the unfiltered one (tests/golden/make_golden_mincount.py)."""
+    z = np.load(expected(case + ".npz"))
+    kw = MINCOUNT[case]
+    for i, f in enumerate(MINCOUNT_FILES):
+        o = O.sketch_file(os.path.join(GOLD, "inputs", f), mode="opmh", **kw)
+        assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)) and o["card"] == z["cards"][i], (case, f)
+    assert (z["sigs"] != 0).any()
+    if "w" not in kw:
+        assert (z["sigs"][2] == 0).all()                                # g0 has no repeated k-mer at all (every window counts when w > k)
+    recs = O.read_fastx(os.path.join(GOLD, "inputs", "rep.fa.gz"))
+    kw0 = {k: v for k, v in kw.items() if k != "count_threshold"}
+    cards, sigs = O.sketch_records_byseq(recs, "opmh", **kw0)
+    assert np.array_equal(sigs.view(np.uint64), z["byseq_sigs"].view(np.uint64)) and np.array_equal(cards, z["byseq_cards"])
