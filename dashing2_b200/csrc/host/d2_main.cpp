@@ -23,6 +23,7 @@
 #include <fstream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -57,6 +58,7 @@ struct Opts {
     int shape = D2G_SYMMETRIC; bool phylip = false;
     int topk = -1;
     unsigned count_threshold = 0;          // -m / --count-threshold (src/options.h:83-84,352)
+    int ngpus = 1;                         // --gpus N (not a reference option; also D2G_GPUS): files / output rows sharded over N devices
     double fastcmp = 8.; bool bbit = false;   // --fastcmp/--regsize N, --bbit-sigs (src/options.h:76,101)
     std::string ffile, qfile, outfile, cmpout, outprefix;
     std::vector<std::string> paths;
@@ -92,6 +94,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
             o.fastcmp = std::atof(arg().c_str());
             if (o.fastcmp != 8. && o.fastcmp != 4. && o.fastcmp != 2. && o.fastcmp != 1.) die("--fastcmp must have 8, 4, 2, or 1 as the argument. These are the only register sizes supported.");
         }
+        else if (a == "--gpus") o.ngpus = std::max(1, std::stoi(arg()));
         else if (a == "--bbit-sigs") o.bbit = true;
         else if (a == "--binary-output" || a == "--emit-binary" || a == "--binary") o.binary = true;
         else if (a == "--phylip") o.phylip = true;
@@ -121,6 +124,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else o.paths.push_back(a);
     }
     if (o.k < 0) o.k = 32;   // nregperitem(DNA, 64-bit), src/sketch_main.cpp:70
+    if (const char *ev = getenv("D2G_GPUS")) if (o.ngpus == 1) o.ngpus = std::max(1, atoi(ev));
     auto read_list = [](const std::string &f, std::vector<std::string> &dst) {
         std::ifstream ifs(f); if (!ifs) die("No path found at " + f);
         for (std::string l; std::getline(ifs, l);) dst.push_back(l);
@@ -220,11 +224,30 @@ void fmt_float(float v, std::string &out) {
 // The CUDA context comes up on its own thread (1-2 s on a B200 box) while the host threads read and parse the first batch.
 struct LazyCtx {
     d2g_ctx *ctx = nullptr; int rc = 0; std::string err; std::thread th; bool joined = false;
-    void start() { th = std::thread([this] { rc = d2g_init(&ctx, 0); if (rc) err = d2g_last_error(); }); }
+    void start(int device = 0) {
+        th = std::thread([this, device] {
+            rc = d2g_init(&ctx, device);
+            // test knob: with D2G_SHARE_DEVICE set, contexts beyond the devices present share device 0 (own stream and scratch each), so the
+            // file / row sharding of --gpus N can be exercised on a one-GPU box
+            if (rc == D2G_EINVAL && device > 0 && getenv("D2G_SHARE_DEVICE")) rc = d2g_init(&ctx, 0);
+            if (rc) err = d2g_last_error();
+        });
+    }
     d2g_ctx *get() {
         if (!joined) { th.join(); joined = true; g_timer.mark("d2g_init (overlapped)"); if (rc) die("libd2gpu: " + err); }
         return ctx;
     }
+};
+
+// One context per device (--gpus N): the sketch phase hands whole batches of files to whichever device is free, the compare phase
+// gives every device a range of output rows -- the reference's own decomposition (files: src/fastxsketch.cpp:302, rows:
+// src/emitrect.cpp:198-326), without any device-to-device traffic because the front-end keeps the sketches in host memory.
+struct Gpus {
+    std::vector<std::unique_ptr<LazyCtx>> c;
+    void start(int n) { for (int g = 0; g < n; ++g) { c.emplace_back(new LazyCtx); c.back()->start(g); } }
+    size_t size() const { return c.size(); }
+    d2g_ctx *get(size_t g = 0) { return c[g]->get(); }
+    LazyCtx &lazy(size_t g = 0) { return *c[g]; }
 };
 
 struct Sketches { std::vector<double> sig, card; std::vector<uint64_t> ids; std::vector<std::string> names; uint64_t S = 0; int mode = D2G_MODE_OPMH; };
@@ -241,7 +264,7 @@ d2g_sketch_params sketch_params(const Opts &o) {
 }
 
 // ---- sketch all inputs through libd2gpu in batches -----------------------------------------------
-void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
+void sketch_inputs(Gpus &gpus, const Opts &o, Sketches &sk) {
     const size_t n = o.paths.size(), S = o.S;
     sk.S = S; sk.mode = o.mode; sk.names = o.paths;
     sk.sig.assign(n * S, 0.); sk.card.assign(n, 0.);
@@ -259,24 +282,34 @@ void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
             }
         }
     }
-    const size_t batch_bytes = size_t(1) << 30;
+    const size_t G = gpus.size();
+    // several devices: smaller batches so that every device gets work (the reference balances files over threads the same way)
+    size_t total_bytes = 0;
+    if (G > 1) for (size_t j = 0; j < n; ++j) if (todo[j]) { struct stat st; total_bytes += ::stat(o.paths[j].c_str(), &st) == 0 ? (size_t)st.st_size : 0; }
+    const size_t batch_bytes = G > 1 ? std::min<size_t>(size_t(1) << 30, std::max<size_t>(size_t(32) << 20, total_bytes / (2 * G) + 1)) : size_t(1) << 30;
     size_t i = 0;
-    while (i < n) {
-        // gather a batch of files (parsed on host threads)
-        std::vector<size_t> idx; size_t est = 0;
+    std::mutex batch_mu;
+    auto next_batch = [&](std::vector<size_t> &idx) {   // a batch of files, in input order
+        std::lock_guard<std::mutex> lk(batch_mu);
+        idx.clear(); size_t est = 0;
         while (i < n && (idx.empty() || est < batch_bytes)) {
             if (todo[i]) { struct stat st; est += ::stat(o.paths[i].c_str(), &st) == 0 ? (size_t)st.st_size : 0; idx.push_back(i); }
             ++i;
         }
-        if (idx.empty()) break;
+        return !idx.empty();
+    };
+    const unsigned threads_per_worker = (unsigned)std::max<size_t>(1, o.nthreads / G);
+    auto worker = [&](size_t g) {
+      std::vector<size_t> idx;
+      while (next_batch(idx)) {
         std::vector<FileRecords> recs(idx.size());
         {
             std::vector<std::thread> th; std::atomic<size_t> next{0};
-            const unsigned nt = (unsigned)std::min<size_t>(o.nthreads, idx.size());
+            const unsigned nt = (unsigned)std::min<size_t>(threads_per_worker, idx.size());
             for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] { for (size_t j; (j = next++) < idx.size();) read_fastx(o.paths[idx[j]], recs[j]); });
             for (auto &t : th) t.join();
         }
-        g_timer.mark("read + parse batch");
+        if (G == 1) g_timer.mark("read + parse batch");
         // one buffer for the batch: sized once, filled by the host threads in parallel
         std::vector<uint64_t> base(idx.size() + 1, 0);
         for (size_t j = 0; j < idx.size(); ++j) base[j + 1] = base[j] + recs[j].seq.size();
@@ -288,17 +321,17 @@ void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
             for (uint64_t e : recs[j].ends) { off.push_back(base[j] + e); ent.push_back((uint32_t)j); }
         {
             std::vector<std::thread> th; std::atomic<size_t> next{0};
-            const unsigned nt = (unsigned)std::min<size_t>(o.nthreads, idx.size());
+            const unsigned nt = (unsigned)std::min<size_t>(threads_per_worker, idx.size());
             for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] {
                 for (size_t j; (j = next++) < idx.size();) { memcpy(seqbuf + base[j], recs[j].seq.data(), recs[j].seq.size()); recs[j] = FileRecords(); } });
             for (auto &t : th) t.join();
         }
-        g_timer.mark("concatenate batch");
+        if (G == 1) g_timer.mark("concatenate batch");
         const uint32_t ne = (uint32_t)idx.size();
         std::vector<double> sig((size_t)ne * S), card(ne); std::vector<uint64_t> ids(o.save_kmers ? (size_t)ne * S : 0);
-        chk(d2g_sketch_batch(lctx.get(), &p, seqbuf, off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
+        chk(d2g_sketch_batch(gpus.get(g), &p, seqbuf, off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
                              o.save_kmers ? ids.data() : nullptr, nullptr));
-        g_timer.mark("d2g_sketch_batch");
+        if (G == 1) g_timer.mark("d2g_sketch_batch");
         for (size_t j = 0; j < idx.size(); ++j) {
             std::copy(sig.begin() + j * S, sig.begin() + (j + 1) * S, sk.sig.begin() + idx[j] * S);
             sk.card[idx[j]] = card[j];
@@ -310,6 +343,14 @@ void sketch_inputs(LazyCtx &lctx, const Opts &o, Sketches &sk) {
                 std::fwrite(&card[j], 8, 1, fp); std::fwrite(&sig[j * S], 8, S, fp); std::fclose(fp);
             }
         }
+      }
+    };
+    if (G == 1) worker(0);
+    else {
+        std::vector<std::thread> ws;
+        for (size_t g = 0; g < G; ++g) ws.emplace_back(worker, g);
+        for (auto &t : ws) t.join();
+        g_timer.mark("sketch batches (all devices)");
     }
 }
 
@@ -419,9 +460,17 @@ std::string options_string(const Opts &o, int mode) {   // Dashing2Options::to_s
 
 struct Writer {
     const Opts &o; const Sketches &sk; std::FILE *fp; size_t ns, nq; std::string line;
+    // several devices: a row range either lands at its byte offset of the binary file (fd >= 0) or is kept in `mem` until the ranges
+    // before it have been written
+    int fd = -1; uint64_t file_off = 0; std::string *mem = nullptr;
+    bool put(const void *p, size_t nbytes) {
+        if (mem) { mem->append((const char *)p, nbytes); return true; }
+        if (fd >= 0) { const bool ok = ::pwrite(fd, p, nbytes, (off_t)file_off) == (ssize_t)nbytes; file_off += nbytes; return ok; }
+        return std::fwrite(p, 1, nbytes, fp) == nbytes;
+    }
     static int sink(void *u, const float *blk, uint64_t first_row, uint64_t n_rows, uint64_t n_vals) {
         Writer *w = (Writer *)u;
-        if (w->o.binary) return std::fwrite(blk, 4, n_vals, w->fp) == n_vals ? 0 : 1;
+        if (w->o.binary) return w->put(blk, 4 * n_vals) ? 0 : 1;
         const float *p = blk;
         for (uint64_t i = first_row; i < first_row + n_rows; ++i) {   // src/emitrect.cpp:172-187
             std::string &l = w->line; l.clear();
@@ -432,13 +481,29 @@ struct Writer {
             if (w->o.shape == D2G_SYMMETRIC && !w->o.phylip) for (uint64_t t = 0; t < i + 1; ++t) l += "\t-";
             for (size_t j = 0; j < jend; ++j) { l += '\t'; fmt_float(*p++, l); }
             l += '\n';
-            if (std::fwrite(l.data(), 1, l.size(), w->fp) != l.size()) return 1;
+            if (!w->put(l.data(), l.size())) return 1;
         }
         return 0;
     }
 };
 
-void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
+// output rows [b[g], b[g+1]) for device g: equal numbers of pairs (row i of the condensed triangle holds n-1-i of them), else equal rows
+std::vector<uint64_t> row_ranges(uint64_t nrows, uint64_t n, int shape, size_t G) {
+    std::vector<uint64_t> b(G + 1, nrows);
+    b[0] = 0;
+    if (shape != D2G_SYMMETRIC) { for (size_t g = 1; g < G; ++g) b[g] = nrows * g / G; return b; }
+    const long double total = (long double)n * (n - 1) / 2;
+    uint64_t row = 0; long double acc = 0;
+    for (size_t g = 1; g < G; ++g) {
+        while (row < nrows && acc < total * g / G) { acc += (long double)(n - 1 - row); ++row; }
+        b[g] = row;
+    }
+    return b;
+}
+
+void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
+    d2g_ctx *ctx = gpus.get(0);
+    const size_t G = gpus.size();
     const uint64_t n = sk.card.size(), S = sk.S;
     if (sk.mode == D2G_MODE_OPMH) chk(d2g_densify(ctx, sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), n, (uint32_t)S));  // cmp_core.cpp:686-718
     d2g_cmp_params cp{};
@@ -462,7 +527,28 @@ void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
         std::vector<uint64_t> indptr(n + 1); uint32_t *idx = nullptr; float *val = nullptr;
         const double *r = sk.sig.data();
         if (cp.cmp_kind == D2G_CMP_EQ && sk.ids.size() == sk.sig.size()) r = reinterpret_cast<const double *>(sk.ids.data());
-        chk(d2g_lsh_topk(ctx, &cp, r, sk.card.data(), o.topk, indptr.data(), &idx, &val));
+        if (G == 1) chk(d2g_lsh_topk(ctx, &cp, r, sk.card.data(), o.topk, indptr.data(), &idx, &val));
+        else {   // every device builds the index and scans all queries, but replays / refines / trims only its own range of lists
+            std::vector<std::vector<uint64_t>> ip(G); std::vector<uint32_t *> ix(G, nullptr); std::vector<float *> vl(G, nullptr);
+            std::vector<std::thread> ws;
+            for (size_t g = 0; g < G; ++g) ws.emplace_back([&, g] {
+                const uint64_t x0 = n * g / G, x1 = n * (g + 1) / G;
+                ip[g].assign(x1 - x0 + 1, 0);
+                chk(d2g_lsh_topk_rows(gpus.get(g), &cp, r, sk.card.data(), o.topk, x0, x1, ip[g].data(), &ix[g], &vl[g]));
+            });
+            for (auto &t : ws) t.join();
+            uint64_t tot = 0; for (size_t g = 0; g < G; ++g) tot += ip[g].back();
+            idx = (uint32_t *)std::malloc(std::max<uint64_t>(tot, 1) * 4); val = (float *)std::malloc(std::max<uint64_t>(tot, 1) * 4);
+            if (!idx || !val) die("out of memory");
+            uint64_t at = 0;
+            for (size_t g = 0; g < G; ++g) {
+                const uint64_t x0 = n * g / G, cnt = ip[g].back();
+                for (size_t t = 0; t + 1 < ip[g].size(); ++t) indptr[x0 + t] = at + ip[g][t];
+                if (cnt) { std::memcpy(idx + at, ix[g], cnt * 4); std::memcpy(val + at, vl[g], cnt * 4); }
+                at += cnt; d2g_free(ix[g]); d2g_free(vl[g]);
+            }
+            indptr[n] = at;
+        }
         const uint64_t nnz = indptr[n];
         if (o.binary) {
             const uint64_t dims[2] = {n, nnz};
@@ -475,7 +561,7 @@ void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
                 std::fputc('\n', fp);
             }
         }
-        d2g_free(idx); d2g_free(val);
+        if (G == 1) { d2g_free(idx); d2g_free(val); } else { std::free(idx); std::free(val); }
         if (!to_stdout) std::fclose(fp); else std::fflush(fp);
         return;
     }
@@ -493,7 +579,22 @@ void compare_and_emit(d2g_ctx *ctx, const Opts &o, Sketches &sk) {
     // equality branch compares the sampled k-mers when they were saved (cmp_core.cpp:501-504)
     if (cp.cmp_kind == D2G_CMP_EQ && sk.ids.size() == sk.sig.size()) regs = reinterpret_cast<const double *>(sk.ids.data());
     if (!creg.empty()) regs = creg.data();
-    chk(d2g_cmp_stream(ctx, &cp, regs, sk.card.data(), 0, nrows, Writer::sink, &w));
+    if (G == 1) chk(d2g_cmp_stream(ctx, &cp, regs, sk.card.data(), 0, nrows, Writer::sink, &w));
+    else {
+        const std::vector<uint64_t> b = row_ranges(nrows, n, cp.shape, G);
+        const bool positioned = o.binary && !to_stdout;      // raw float32 file: every range is written at its own offset
+        std::fflush(fp);
+        std::vector<std::string> mem(G);
+        std::vector<std::thread> ws;
+        for (size_t g = 0; g < G; ++g) ws.emplace_back([&, g] {
+            Writer wg{o, sk, fp, (size_t)n, (size_t)o.nq, {}};
+            if (positioned) { uint64_t before = 0; chk(d2g_cmp_rows_size(&cp, 0, b[g], &before)); wg.fd = fileno(fp); wg.file_off = before * 4; }
+            else wg.mem = &mem[g];
+            if (b[g + 1] > b[g]) chk(d2g_cmp_stream(gpus.get(g), &cp, regs, sk.card.data(), b[g], b[g + 1], Writer::sink, &wg));
+        });
+        for (auto &t : ws) t.join();
+        if (!positioned) for (size_t g = 0; g < G; ++g) if (std::fwrite(mem[g].data(), 1, mem[g].size(), fp) != mem[g].size()) die("short write to " + o.cmpout);
+    }
     if (!to_stdout) std::fclose(fp); else std::fflush(fp);
 }
 
@@ -508,31 +609,35 @@ int main(int argc, char **argv) {
     g_timer.verbosity = o.verbosity;
     // this front-end drives one GPU: hiding the others from the CUDA driver cuts its start-up (context creation touches
     // every visible device) from seconds to a fraction of a second on an 8-GPU box.  An existing setting is respected.
-    setenv("CUDA_VISIBLE_DEVICES", "0", 0);
-    LazyCtx lctx;
-    lctx.start();
+    {
+        std::string vis;
+        for (int g = 0; g < o.ngpus; ++g) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+    }
+    Gpus gpus;
+    gpus.start(o.ngpus);
     Sketches sk;
     if (is_cmp && o.presketched) {
         if (o.paths.size() != 1) die("--presketched: pass one stacked sketch file (the reference's multi-file branch is degenerate for panels, SURVEY 8a b9)");
         load_stacked(o.paths[0], sk);
         o.S = sk.S;
     } else {
-        if (o.parse_by_seq) sketch_by_seq(lctx, o, sk); else sketch_inputs(lctx, o, sk);
+        if (o.parse_by_seq) sketch_by_seq(gpus.lazy(0), o, sk); else sketch_inputs(gpus, o, sk);
         if (!o.outfile.empty()) {
             // the reference densifies signatures_ in place before the stacked file is closed when --cmpout is given
-            if (!o.cmpout.empty() && sk.mode == D2G_MODE_OPMH) chk(d2g_densify(lctx.get(), sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), sk.card.size(), (uint32_t)sk.S));
+            if (!o.cmpout.empty() && sk.mode == D2G_MODE_OPMH) chk(d2g_densify(gpus.get(0), sk.sig.data(), sk.ids.empty() ? nullptr : sk.ids.data(), sk.card.size(), (uint32_t)sk.S));
             write_stacked(o, sk);
         }
     }
     g_timer.mark("sketches ready / written");
     if (is_cmp || !o.cmpout.empty()) {
         if (is_cmp && o.cmpout.empty()) o.cmpout = "-";
-        compare_and_emit(lctx.get(), o, sk);
+        compare_and_emit(gpus, o, sk);
         g_timer.mark("compare + emit");
     }
     // every output file is closed / flushed; tearing the CUDA context down costs another 0.2-0.5 s and frees nothing the
     // process exit does not free
-    lctx.get();
+    for (size_t g = 0; g < gpus.size(); ++g) gpus.get(g);
     std::fflush(nullptr);
     _exit(0);
     return 0;

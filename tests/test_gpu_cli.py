@@ -12,8 +12,8 @@ pytestmark = pytest.mark.gpu
 EXE = os.path.join(ROOT, "dashing2_b200", "bin", "dashing2-gpu")
 
 
-def run(args, cwd=None):
-    r = subprocess.run([EXE] + args, cwd=cwd, capture_output=True, text=True)
+def run(args, cwd=None, env=None):
+    r = subprocess.run([EXE] + args, cwd=cwd, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     return r
 
@@ -166,6 +166,66 @@ def test_count_threshold_per_file_and_by_seq(tmp_path):
     run(["sketch", "--parse-by-seq", "-k31", "-S64", "--count-threshold", "2", "-o", out2, paths[0]])
     cards, sigs = read_stacked(out2)
     assert np.array_equal(sigs.view(np.uint64), z["byseq_sigs"].view(np.uint64)) and np.array_equal(cards, z["byseq_cards"])
+
+
+@pytest.mark.parametrize("share", [True, False])
+def test_gpus_option_shards_files_and_rows(share, golden_inputs, tmp_path, monkeypatch):
+    """--gpus N (front-end only): batches of files go to whichever device is free, every device computes a range of output rows /
+    neighbour lists; outputs stay byte-identical to the reference goldens.  share=True runs three contexts on one device
+    (D2G_SHARE_DEVICE), share=False two contexts on two devices."""
+    from dashing2_b200 import synth
+    if share:
+        monkeypatch.setenv("D2G_SHARE_DEVICE", "1")
+    else:
+        import torch
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs 2 GPUs")
+    ng = "3" if share else "2"
+    names, paths = golden_inputs
+    flist = tmp_path / "files.txt"; flist.write_text("\n".join(paths) + "\n")
+    work = os.path.dirname(paths[0])
+    out = str(tmp_path / "out.stk"); mat = str(tmp_path / "m.f32")
+    run(["sketch", "--gpus", ng, "-p6", "-F", str(flist), "-k31", "-S1024", "-o", out, "--binary-output", "--cmpout", mat])
+    exp = np.load(expected("cmp_opmh_k31_S1024_sim_sym.npy"))
+    assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), exp.view(np.uint32))
+    cards, _ = read_stacked(out)
+    assert np.array_equal(cards, np.load(expected("opmh_k31_S1024.npz"))["cards"])
+    for tag, argv in (("phylip", ["--phylip"]), ("table", [])):
+        txt = str(tmp_path / (tag + ".txt"))
+        run(["sketch", "--gpus", ng, "-F", str(flist), "-k31", "-S1024", "--cmpout", txt] + argv)
+        assert open(txt).read().replace(work + "/", "") == open(expected(f"cmp_opmh_k31_S1024_{tag}.txt")).read(), tag
+    mat = str(tmp_path / "asym.f32")
+    run(["sketch", "--gpus", ng, "-F", str(flist), "-k31", "-S1024", "--binary-output", "--asymmetric-all-pairs", "--cmpout", mat])
+    exp = np.load(expected("cmp_opmh_k31_S1024_sim_asym.npy"))
+    assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), exp.view(np.uint32))
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    stk = str(tmp_path / "sk600.ss")
+    synth.write_stacked(stk, z["regs"], z["cards"], names=[f"s{i}" for i in range(600)])
+    csr = str(tmp_path / "top5.csr")
+    run(["cmp", "--gpus", ng, "--presketched", "--binary-output", "--topk", "5", "--cmpout", csr, stk])
+    assert open(csr, "rb").read() == open(expected("topk5_sk600.csr"), "rb").read()
+    z = np.load(os.path.join(GOLD, "inputs", "sk48x256.npz"))
+    stk = str(tmp_path / "sk48.ss")
+    synth.write_stacked(stk, z["regs"], z["cards"], names=[f"s{i}" for i in range(48)])
+    run(["cmp", "--gpus", ng, "--presketched", "--binary-output", "--cmpout", mat, stk])
+    assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), np.load(expected("cmp_sk48.ss_sim_sym.npy")).view(np.uint32))
+
+
+@pytest.mark.parametrize("case,argv", [("panel_opmh_k31_S1024_sim", ["-k31", "-S1024"]), ("panel_opmh_k31_S1024_containment", ["-k31", "-S1024", "--containment"]),
+                                       ("panel_fss_k31_S256_mash", ["-k31", "-S256", "--full-setsketch", "--mash-distance"])])
+def test_panel_from_fasta_lists(case, argv, golden_inputs, tmp_path):
+    """`sketch -F refs -Q queries --cmpout`: |F| x |Q| matrix, binary and text, byte for byte as the reference binary wrote them."""
+    names, paths = golden_inputs
+    work = os.path.dirname(paths[0])
+    ff = tmp_path / "refs.txt"; ff.write_text("\n".join(paths[:4]) + "\n")
+    qf = tmp_path / "queries.txt"; qf.write_text("\n".join(paths[4:]) + "\n")
+    mat = str(tmp_path / "p.f32"); txt = str(tmp_path / "p.txt")
+    run(["sketch", "-F", str(ff), "-Q", str(qf), "--binary-output", "--cmpout", mat] + argv)
+    assert np.array_equal(np.fromfile(mat, dtype=np.float32).view(np.uint32), np.load(expected(case + ".npy")).view(np.uint32))
+    run(["sketch", "-F", str(ff), "-Q", str(qf), "--cmpout", txt] + argv)
+    assert open(txt).read().replace(work + "/", "") == open(expected(case + ".txt")).read()
+    run(["sketch", "--gpus", "2", "-F", str(ff), "-Q", str(qf), "--cmpout", txt] + argv, env=dict(os.environ, D2G_SHARE_DEVICE="1"))
+    assert open(txt).read().replace(work + "/", "") == open(expected(case + ".txt")).read()
 
 
 def test_cmp_topk_csr_file(tmp_path):

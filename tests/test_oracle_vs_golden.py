@@ -197,3 +197,19 @@ def test_opmh_count_threshold_matches_reference(case):
     kw0 = {k: v for k, v in kw.items() if k != "count_threshold"}
     cards, sigs = O.sketch_records_byseq(recs, "opmh", **kw0)
     assert np.array_equal(sigs.view(np.uint64), z["byseq_sigs"].view(np.uint64)) and np.array_equal(cards, z["byseq_cards"])
+
+
+PANEL = {"panel_opmh_k31_S1024_sim": ("opmh_k31_S1024", "similarity", True), "panel_opmh_k31_S1024_containment": ("opmh_k31_S1024", "containment", True),
+         "panel_fss_k31_S256_mash": ("fss_k31_S256", "poisson_llr", False)}
+
+
+@pytest.mark.parametrize("case", sorted(PANEL))
+def test_panel_orientation_matches_reference(case):
+    """-F refs -Q queries: rows = references, columns = queries (src/emitrect.cpp:229-246), against the matrix the reference binary
+    wrote for 4 references x 5 queries (tests/golden/make_golden_panel.py)."""
+    sk, measure, dens = PANEL[case]
+    z = np.load(expected(sk + ".npz"))
+    sigs = np.stack([O.densify(s) for s in z["sigs"]]) if dens else z["sigs"]
+    got = O.allpairs(sigs, z["cards"], "panel", measure, k=31, nq=len(sigs) - 4)
+    exp = np.load(expected(case + ".npy"))
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
