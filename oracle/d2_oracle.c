@@ -609,6 +609,26 @@ uint64_t d2o_count_exact(uint64_t *hv, uint64_t n, uint64_t *keys, double *count
     return nd;
 }
 
+/* Counter::add with a count sketch, src/counter.h:68-77: bucket Wang(x) % cssize gets +1, or -1 when the top bit of Wang(x) is clear
+ * (Counter::ct() reports COUNTSKETCH_COUNTING whenever the table exists, :18); float accumulation (exact: integers below 2^24).
+ * Counter::finalize(Sketch&), :131-137: every bucket i with |count| >= threshold feeds dst.update(i, |count|) -- the element id is the bucket
+ * index.  Buckets with weight 0 (threshold 0) are no-ops in both weighted sketches and are dropped here.  keys/counts need cssize slots;
+ * returns the number of elements written (ascending bucket index). */
+uint64_t d2o_count_sketch(const uint64_t *hv, uint64_t n, uint64_t cssize, double threshold, uint64_t *keys, double *counts) {
+    float *cs = (float *)calloc(cssize, sizeof(float));
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t h = d2o_wang64(hv[i]);
+        cs[h % cssize] += (h & 0x8000000000000000ULL) == 0 ? -1.f : 1.f;
+    }
+    uint64_t nd = 0;
+    for (uint64_t i = 0; i < cssize; ++i) {
+        const float v = fabsf(cs[i]);
+        if ((double)v >= threshold && v > 0.f) { keys[nd] = i; counts[nd] = (double)v; ++nd; }
+    }
+    free(cs);
+    return nd;
+}
+
 /* --parse-by-seq cardinality of one record's set sketch, src/fastxsketchbyseq.cpp:393-430: a NaN estimate becomes 0 (:398-402);
  * an estimate below 10 * sketchsize is replaced by the exact number of distinct maskfn'd k-mers (minimizers) of the record,
  * which the reference collects in a flat_hash_set by walking the record a second time (:405-422).  hv is sorted in place. */

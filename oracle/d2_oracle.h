@@ -97,6 +97,9 @@ extern "C" {
 /* Sorts hv in place and run-length encodes it: keys[i] with counts[i]; returns the number of distinct keys.
  * (The reference counts in a hash map; sketches below are order independent, so sorted order is as good.) */
 uint64_t d2o_count_exact(uint64_t *hv, uint64_t n, uint64_t *keys, double *counts);
+/* --countsketch-size n (src/counter.h:68-77,131-137): signed count-sketch table of n floats over the hashed k-mer stream; the elements fed to
+ * the weighted sketch are (bucket index, |count|) for |count| >= threshold (zero-weight buckets dropped: no-ops). Returns their number. */
+uint64_t d2o_count_sketch(const uint64_t *hv, uint64_t n, uint64_t cssize, double threshold, uint64_t *keys, double *counts);
 /* --parse-by-seq (one sketch per record) cardinality rule for set sketches, src/fastxsketchbyseq.cpp:393-430: NaN -> 0, and an
  * estimate < 10 * sketchsize is replaced by the exact number of distinct hashed k-mers of the record (hv is sorted in place). */
 double d2o_byseq_cardinality(double estimate, uint64_t sketchsize, uint64_t *hv, uint64_t n);

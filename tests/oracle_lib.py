@@ -60,6 +60,7 @@ def lib():
         getattr(L, nm).argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
     L.d2o_panel.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p]
     L.d2o_count_exact.restype = C.c_uint64; L.d2o_count_exact.argtypes = [u64p, C.c_uint64, u64p, f64p]
+    L.d2o_count_sketch.restype = C.c_uint64; L.d2o_count_sketch.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_double, u64p, f64p]
     L.d2o_byseq_cardinality.restype = C.c_double; L.d2o_byseq_cardinality.argtypes = [C.c_double, C.c_uint64, u64p, C.c_uint64]
     L.d2o_pmh_reset.argtypes = [f64p, C.c_void_p, C.c_uint32]
     for nm in ("d2o_pmh_update", "d2o_bmh_update"):
@@ -119,7 +120,7 @@ def hash_stream(seq: bytes, k: int, w: int = -1, canon: bool = True, seed: int =
 
 
 def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool = True, seed: int = 0,
-                count_threshold: float = 0.0):
+                count_threshold: float = 0.0, cssize: int = 0):
     """Oracle equivalent of one iteration of the per-file loop (src/fastxsketch.cpp:303-624).
 
     Returns dict(card=..., sig=f64[S], regs_u64=..., ids=...)."""
@@ -147,7 +148,7 @@ def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool =
         L.d2o_css_update(regs, S, hv, len(hv), ids.ctypes.data)
         return dict(card=L.d2o_css_card(regs, S), sig=regs[:S].copy(), ids=ids, n_hashed=len(hv))
     if mode in ("pmh", "bmh"):
-        return weighted_sketch(hv, mode, S, count_threshold)
+        return weighted_sketch(hv, mode, S, count_threshold, cssize)
     raise ValueError(mode)
 
 
@@ -169,11 +170,17 @@ def sketch_records_byseq(records, mode: str, S: int, k: int, w: int = -1, canon:
     return np.asarray(cards), np.stack(sigs) if sigs else np.empty((0, S))
 
 
-def weighted_sketch(hv: np.ndarray, mode: str, S: int, count_threshold: float = 0.0):
-    """Counter (exact) + ProbMinHash3 / BagMinHash2 over a hashed k-mer stream (src/fastxsketch.cpp:429-449)."""
+def weighted_sketch(hv: np.ndarray, mode: str, S: int, count_threshold: float = 0.0, cssize: int = 0):
+    """Counter (exact, or a count sketch of cssize buckets) + ProbMinHash3 / BagMinHash2 over a hashed k-mer stream
+    (src/fastxsketch.cpp:429-449)."""
     L = lib()
-    keys = np.empty(len(hv) + 1, dtype=np.uint64); cnt = np.empty(len(hv) + 1, dtype=np.float64)
-    nd = L.d2o_count_exact(hv.copy(), len(hv), keys, cnt)
+    if cssize:
+        keys = np.empty(cssize, dtype=np.uint64); cnt = np.empty(cssize, dtype=np.float64)
+        nd = L.d2o_count_sketch(np.ascontiguousarray(hv), len(hv), cssize, float(count_threshold), keys, cnt)
+        count_threshold = 0.0            # already applied (>=, src/counter.h:135)
+    else:
+        keys = np.empty(len(hv) + 1, dtype=np.uint64); cnt = np.empty(len(hv) + 1, dtype=np.float64)
+        nd = L.d2o_count_exact(hv.copy(), len(hv), keys, cnt)
     regs = np.empty(2 * S - 1, dtype=np.float64)
     L.d2o_pmh_reset(regs, None, S)
     fn = L.d2o_pmh_update if mode == "pmh" else L.d2o_bmh_update

@@ -213,3 +213,22 @@ def test_panel_orientation_matches_reference(case):
     got = O.allpairs(sigs, z["cards"], "panel", measure, k=31, nq=len(sigs) - 4)
     exp = np.load(expected(case + ".npy"))
     assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+COUNTSKETCH = {
+    "cs5000_bmh_k31_S32": dict(mode="bmh", S=32, k=31, cssize=5000),
+    "cs5000_pmh_k31_S32": dict(mode="pmh", S=32, k=31, cssize=5000),
+    "cs300_pmh_k21_w30_S64": dict(mode="pmh", S=64, k=21, w=30, cssize=300),
+    "cs100000_bmh_k31_S16": dict(mode="bmh", S=16, k=31, cssize=100000),
+    "cs700_pmh_k31_S32_m3": dict(mode="pmh", S=32, k=31, cssize=700, count_threshold=3),
+}
+COUNTSKETCH_FILES = ["dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz"]
+
+
+@pytest.mark.parametrize("case", sorted(COUNTSKETCH))
+def test_count_sketch_weighted_matches_reference(case):
+    """--countsketch-size n (src/counter.h:68-77,131-137): signed float count sketch, elements (bucket index, |count|), threshold with >=."""
+    z = np.load(expected(case + ".npz"))
+    for i, f in enumerate(COUNTSKETCH_FILES):
+        o = O.sketch_file(os.path.join(GOLD, "inputs", f), **COUNTSKETCH[case])
+        assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)) and o["card"] == z["cards"][i], (case, f)
