@@ -155,8 +155,8 @@ class Context:
 
     # ---- sketch ----
     @staticmethod
-    def params(mode="opmh", S=1024, k=31, w=-1, canon=True, seed=0, count_threshold=0):
-        return SketchParams(k, w, int(canon), MODE[mode], xormask_for_seed(seed), S, int(count_threshold), 0)
+    def params(mode="opmh", S=1024, k=31, w=-1, canon=True, seed=0, count_threshold=0, cssize=0):
+        return SketchParams(k, w, int(canon), MODE[mode], xormask_for_seed(seed), S, int(count_threshold), int(cssize))
 
     def sketch_batch(self, seq: np.ndarray, rec_off: np.ndarray, rec_entity: np.ndarray, n_entities: int,
                      p: SketchParams, want_ids=False, want_regs=True):

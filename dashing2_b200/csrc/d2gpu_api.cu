@@ -201,7 +201,9 @@ int check_sketch_params(const d2g_sketch_params *p) {
     if (p->count_threshold > 1 && p->mode == D2G_MODE_FULL_SETSKETCH)
         return fail(D2G_EUNSUPPORTED, "--count-threshold > 1 with --full-setsketch (CountFilteredCSetSketch, src/setsketch.h:1000-1132: the result depends on "
                                       "the order of the k-mers) is not implemented on the GPU; one-permutation and the counting sketches are");
-    if (p->countsketch_size) return fail(D2G_EUNSUPPORTED, "--countsketch-size not implemented on the GPU");
+    if (p->countsketch_size && p->mode != D2G_MODE_BAGMINHASH && p->mode != D2G_MODE_PROBMINHASH)
+        return fail(D2G_EINVAL, "--countsketch-size applies to the counting sketches (--multiset / --prob) only");
+    if (p->countsketch_size >> 40) return fail(D2G_EINVAL, "--countsketch-size too large");
     return D2G_OK;
 }
 
@@ -380,6 +382,8 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
     const uint64_t o_flag = off; off += al(n * 4 + 4);
     const uint64_t o_excl = off; off += al(n * 4 + 4);
     const uint64_t o_pos = off; off += al(n * 4 + 4);
+    const uint64_t cssize = p->countsketch_size;
+    const uint64_t o_wts = off; off += cssize ? al(n * 4 + 4) : 0;
     const uint64_t o_keys = off; off += al(nreg * 8);
     const uint64_t o_wsum = off; off += al((uint64_t)n_ent * 8);
     const uint64_t o_T = off; off += al((uint64_t)n_ent * 8);
@@ -391,6 +395,8 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
     uint64_t *hvA = (uint64_t *)(B + o_hvA), *hvB = (uint64_t *)(B + o_hvB);
     uint32_t *entA = (uint32_t *)(B + o_entA), *entB = (uint32_t *)(B + o_entB);
     uint32_t *flag = (uint32_t *)(B + o_flag), *excl = (uint32_t *)(B + o_excl), *pos = (uint32_t *)(B + o_pos);
+    uint32_t *wts = cssize ? (uint32_t *)(B + o_wts) : nullptr;
+    const int id_shift = cssize ? 1 : 0;
     uint64_t *keys = (uint64_t *)(B + o_keys);
     unsigned long long *wsum = (unsigned long long *)(B + o_wsum);
     double *T = (double *)(B + o_T);
@@ -411,6 +417,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
         if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
         d2g::EmitConsumer::Params ep{hvA, entA, a.span};
         if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, windowed, D2G_T_SKETCH_MAIN)) return rc;
+        if (cssize) { d2g::cs_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvA, entA, n, cssize); c->launches++; }
         // sort by (entity, value): LSD radix -- value first, then a stable pass over the entity
         size_t t1 = 0, t2 = 0, t3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
@@ -424,7 +431,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
         CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
         c->launches += 2 * 9;
         const unsigned gb = (unsigned)((n + 255) / 256);
-        d2g::rle_flag_kernel<<<gb, 256, 0, st>>>(hvA, entA, n, flag);
+        d2g::rle_flag_kernel<<<gb, 256, 0, st>>>(hvA, entA, n, flag, id_shift);
         tbytes = tb;
         CU(cub::DeviceScan::ExclusiveSum(c->wtmp.p, tbytes, flag, excl, n, st));
         d2g::rle_scatter_kernel<<<gb, 256, 0, st>>>(flag, excl, entA, n, pos, n_valid);
@@ -435,13 +442,15 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
         CU(cudaStreamSynchronize(st));
         nu = (uint64_t)h_last[0] + h_last[1];
     }
-    const double threshold = (double)p->count_threshold;
+    // exact counts pass with count > threshold (counter.h:123); count-sketch buckets with |count| >= threshold (:135), and never with weight 0
+    const double threshold = cssize ? (p->count_threshold >= 1 ? (double)p->count_threshold - 0.5 : 0.) : (double)p->count_threshold;
     if (nu) {
         const unsigned gu = (unsigned)((nu + 127) / 128);
-        d2g::weight_sum_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(entA, pos, nu, n_valid, threshold, wsum);
+        if (cssize) { d2g::cs_run_weight_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(hvA, pos, nu, n_valid, wts); c->launches++; }
+        d2g::weight_sum_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(entA, pos, nu, n_valid, threshold, wsum, wts);
         d2g::weighted_guess_kernel<<<(n_ent + 255) / 256, 256, 0, st>>>(wsum, n_ent, m, T, state);
         c->launches += 2;
-        d2g::WeightedArgs wa{hvA, entA, pos, nu, n_valid, threshold, m, T, state, keys, ovf, ovf_count, ovf_cap, error};
+        d2g::WeightedArgs wa{hvA, entA, pos, nu, n_valid, threshold, m, T, state, keys, ovf, ovf_count, ovf_cap, error, wts, id_shift};
         d2g::TexpConsts tc{};
         if (p->mode == D2G_MODE_PROBMINHASH) {   // bmh.h:490-502
             const long double lambda = log1pl(1.L / (m - 1));

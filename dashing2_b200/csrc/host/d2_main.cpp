@@ -58,6 +58,7 @@ struct Opts {
     int shape = D2G_SYMMETRIC; bool phylip = false;
     int topk = -1;
     unsigned count_threshold = 0;          // -m / --count-threshold (src/options.h:83-84,352)
+    uint64_t cssize = 0;                   // -c / --countsketch-size / --countmin-size (src/options.h:78-79,357)
     int ngpus = 1;                         // --gpus N (not a reference option; also D2G_GPUS): files / output rows sharded over N devices
     double fastcmp = 8.; bool bbit = false;   // --fastcmp/--regsize N, --bbit-sigs (src/options.h:76,101)
     std::string ffile, qfile, outfile, cmpout, outprefix;
@@ -94,6 +95,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
             o.fastcmp = std::atof(arg().c_str());
             if (o.fastcmp != 8. && o.fastcmp != 4. && o.fastcmp != 2. && o.fastcmp != 1.) die("--fastcmp must have 8, 4, 2, or 1 as the argument. These are the only register sizes supported.");
         }
+        else if (a == "--countsketch-size" || a == "--countmin-size" || shortarg("-c")) o.cssize = std::strtoull(arg().c_str(), nullptr, 10);
         else if (a == "--gpus") o.ngpus = std::max(1, std::stoi(arg()));
         else if (a == "--bbit-sigs") o.bbit = true;
         else if (a == "--binary-output" || a == "--emit-binary" || a == "--binary") o.binary = true;
@@ -118,7 +120,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
             std::printf("dashing2-gpu %s: drop-in for `dashing2 sketch|cmp` (k<=32 DNA; OPMH / Full SetSketch; dense all-pairs / panel).\n"
                         "Options follow the reference: -k -w -S -p -F -Q -o --cmpout --binary-output --phylip --asymmetric-all-pairs\n"
                         "--full-setsketch --oneperm -C/--no-canon --seed --cache --outprefix --save-kmers --presketched\n"
-                        "--containment --symmetric-containment --mash-distance --intersection --union-size --topk --fastcmp --bbit-sigs --parse-by-seq -m/--count-threshold\n", d2g_version());
+                        "--containment --symmetric-containment --mash-distance --intersection --union-size --topk --fastcmp --bbit-sigs --parse-by-seq -m/--count-threshold -c/--countsketch-size --gpus\n", d2g_version());
             std::exit(0);
         } else if (!a.empty() && a[0] == '-' && a.size() > 1) die("option " + a + " is not supported by the GPU front-end (see DESIGN.md section 7)");
         else o.paths.push_back(a);
@@ -151,7 +153,7 @@ std::string makedest(const Opts &o, const std::string &path) {   // src/fastxmer
     if (o.w > o.k) ret += ".w" + std::to_string(o.w);
     if (o.count_threshold > 0) ret += ".ct_threshold" + std::to_string(o.count_threshold);
     const bool counted = o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH;
-    if (counted) ret += ".ExactCounting";
+    if (counted) ret += o.cssize ? ".CountMinCounting" + std::to_string(o.cssize) : std::string(".ExactCounting");
     ret += '.';
     ret += o.mode == D2G_MODE_BAGMINHASH ? "MultisetSpace" : o.mode == D2G_MODE_PROBMINHASH ? "ProbsetSpace" : "SetSpace";
     return ret + ".DNA" + suffix(o.mode);
@@ -255,6 +257,7 @@ struct Sketches { std::vector<double> sig, card; std::vector<uint64_t> ids; std:
 d2g_sketch_params sketch_params(const Opts &o) {
     d2g_sketch_params p{};
     p.k = o.k; p.w = o.w; p.canon = o.canon; p.mode = o.mode; p.sketchsize = (uint32_t)o.S; p.count_threshold = o.count_threshold;
+    if (o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH) p.countsketch_size = o.cssize;   // set sketches never count (src/fastxsketch.cpp:425-427)
     p.xormask = 0;
     if (o.seed) { // Wang(seed), src/enums.cpp:133-140
         uint64_t key = o.seed; key = (~key) + (key << 21); key ^= key >> 24; key = (key + (key << 3)) + (key << 8); key ^= key >> 14;
@@ -454,6 +457,7 @@ std::string options_string(const Opts &o, int mode) {   // Dashing2Options::to_s
     r += mode == D2G_MODE_OPMH ? "onepermsetsketch" : mode == D2G_MODE_FULL_SETSKETCH ? "fullsetsketch" : mode == D2G_MODE_BAGMINHASH ? "bagminhash" : "probminhash";
     r += ";Fastx";
     if (!o.outprefix.empty()) r += ";outprefix:" + o.outprefix;
+    if (o.cssize) r += ";counting=countsketch" + std::to_string(o.cssize) + "\n";   // the newline is the reference's (src/d2.cpp:34)
     if (o.canon) r += ";canon";
     return r;
 }

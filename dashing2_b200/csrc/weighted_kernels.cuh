@@ -46,11 +46,32 @@ struct EmitConsumer {
 };
 
 // ---- run-length encode of the sorted (entity, value) stream ----------------------------------------
-__global__ void rle_flag_kernel(const uint64_t *hv, const uint32_t *ent, uint64_t n, uint32_t *flag) {
+// `shift` drops low bits that do not take part in the identity of an element (the sign bit of a count-sketch key, below)
+__global__ void rle_flag_kernel(const uint64_t *hv, const uint32_t *ent, uint64_t n, uint32_t *flag, int shift = 0) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t e = ent[i];
-    flag[i] = (e != 0xFFFFFFFFu && (i == 0 || ent[i - 1] != e || hv[i - 1] != hv[i])) ? 1u : 0u;
+    flag[i] = (e != 0xFFFFFFFFu && (i == 0 || ent[i - 1] != e || (hv[i - 1] >> shift) != (hv[i] >> shift))) ? 1u : 0u;
+}
+// ---- --countsketch-size n: Counter::add / finalize with a count sketch (src/counter.h:68-77,131-137) ----------------
+// The reference adds +1 / -1 (top bit of Wang(x) set / clear) to bucket Wang(x) % n of a float table and afterwards feeds every bucket i
+// with |count| >= threshold to the weighted sketch as element (i, |count|).  Device: every emitted value becomes the key
+// (bucket << 1) | positive; after the sort by (entity, key) a bucket is one run with its negative entries first, so its signed sum is
+// (#positive - #negative) from one binary search for the boundary -- integers, as the float sums are below 2^24.
+__global__ void cs_key_kernel(uint64_t *hv, const uint32_t *ent, uint64_t n, uint64_t cssize) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n || ent[i] == 0xFFFFFFFFu) return;
+    const uint64_t h = wang64(hv[i]);
+    hv[i] = ((h % cssize) << 1) | (h >> 63);
+}
+__global__ void cs_run_weight_kernel(const uint64_t *hv, const uint32_t *pos, uint64_t nu, const unsigned long long *n_valid, uint32_t *wts) {
+    const uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (u >= nu) return;
+    const uint64_t i = pos[u], end = (u + 1 < nu) ? pos[u + 1] : *n_valid;
+    uint64_t a = i, b = end;                              // first entry of the run with the positive bit
+    while (a < b) { const uint64_t mid = (a + b) >> 1; if (hv[mid] & 1ULL) b = mid; else a = mid + 1; }
+    const long long sum = (long long)(end - a) - (long long)(a - i);
+    wts[u] = (uint32_t)(sum < 0 ? -sum : sum);
 }
 // pos[u] = index of the u-th run head; the element count per run is pos[u+1]-pos[u] (sentinel slots sort last)
 __global__ void rle_scatter_kernel(const uint32_t *flag, const uint32_t *excl, const uint32_t *ent, uint64_t n, uint32_t *pos, unsigned long long *n_valid) {
@@ -61,13 +82,13 @@ __global__ void rle_scatter_kernel(const uint32_t *flag, const uint32_t *excl, c
 }
 // total weight per entity (sum of counts above the threshold; integers, so exact in double)
 __global__ void weight_sum_kernel(const uint32_t *ent, const uint32_t *pos, uint64_t nu, const unsigned long long *n_valid, double threshold,
-                                  unsigned long long *wsum) {
+                                  unsigned long long *wsum, const uint32_t *wts = nullptr) {
     const uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint32_t e = 0xFFFFFFFFu; unsigned long long c = 0;
     if (u < nu) {
         const uint64_t i = pos[u], end = (u + 1 < nu) ? pos[u + 1] : *n_valid;
         e = ent[i];
-        c = end - i;
+        c = wts ? wts[u] : end - i;
         if (!((double)c > threshold)) c = 0;
     }
     // the runs are sorted by entity: a warp almost always holds one entity -> one atomic per warp and entity, not per element
@@ -156,6 +177,7 @@ struct WeightedArgs {
     const double *T; const uint32_t *state; uint64_t *keys;
     uint64_t *ovf; unsigned long long *ovf_count; uint64_t ovf_cap;   // (unique index) of elements needing the dense walk
     unsigned int *error;
+    const uint32_t *wts; int id_shift;   // count sketch: weight of run u (else its length), element id = key >> id_shift (else the key)
 };
 
 __global__ void pmh_kernel(const WeightedArgs a, const TexpConsts tc) {
@@ -164,10 +186,10 @@ __global__ void pmh_kernel(const WeightedArgs a, const TexpConsts tc) {
     const uint64_t i = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
     const uint32_t e = a.ent[i];
     if (a.state[e] == 2u) return;
-    const double w = (double)(end - i);
+    const double w = a.wts ? (double)a.wts[u] : (double)(end - i);
     if (!(w > a.threshold)) return;
     SparsePerm sp;
-    if (!pmh_walk(a.hv[i], w, a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, sp)) {
+    if (!pmh_walk(a.hv[i] >> a.id_shift, w, a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, sp)) {
         const unsigned long long g = atomicAdd(a.ovf_count, 1ULL);
         if (g < a.ovf_cap) a.ovf[g] = u; else atomicExch(a.error, 1u);
     }
@@ -181,7 +203,7 @@ __global__ void pmh_longwalk_kernel(const WeightedArgs a, const TexpConsts tc, u
         const uint64_t i = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
         const uint32_t e = a.ent[i];
         ++dp.c;
-        pmh_walk(a.hv[i], (double)(end - i), a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, dp);
+        pmh_walk(a.hv[i] >> a.id_shift, a.wts ? (double)a.wts[u] : (double)(end - i), a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, dp);
     }
 }
 
@@ -226,7 +248,7 @@ __global__ void bmh_kernel(const WeightedArgs a) {
     const uint64_t i0 = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
     const uint32_t e = a.ent[i0];
     if (a.state[e] == 2u) return;
-    const double w = (double)(end - i0);
+    const double w = a.wts ? (double)a.wts[u] : (double)(end - i0);
     if (!(w > a.threshold)) return;
     const double T = a.T[e];
     uint64_t *keys = a.keys + (uint64_t)e * a.m;
@@ -236,7 +258,7 @@ __global__ void bmh_kernel(const WeightedArgs a) {
         if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
     };
     PProc stack[BMH_STACK]; uint32_t sidx[BMH_STACK]; int sp = 0;
-    PProc p{0., 0., 1.7976931348623157e308, 0., a.hv[i0]};
+    PProc p{0., 0., 1.7976931348623157e308, 0., a.hv[i0] >> a.id_shift};
     uint32_t pidx = bmh_step(p, a.m, fm);
     if (p.maxq <= w) apply(pidx, p.x);
     for (;;) {

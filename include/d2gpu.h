@@ -64,7 +64,8 @@ typedef struct {
     uint32_t sketchsize;       /* S */
     uint32_t count_threshold;  /* -m / --count-threshold; 0/1 = off.  OPMH: register = min id seen >= c times (oph.h:188-205); counting
                                   sketches: elements with count <= c are skipped (counter.h:123); Full SetSketch: D2G_EUNSUPPORTED */
-    uint64_t countsketch_size; /* --countsketch-size; 0 = exact counting */
+    uint64_t countsketch_size; /* -c / --countsketch-size n, counting sketches only; 0 = exact counting.  n > 0: signed count sketch of n buckets,
+                                  elements (bucket index, |count|) for |count| >= count_threshold (counter.h:68-77,131-137) */
 } d2g_sketch_params;
 
 /* Number of registers per entity the OPMH sketch keeps (S rounded up to even, src/oph.h:145). */

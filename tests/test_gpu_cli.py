@@ -228,6 +228,24 @@ def test_panel_from_fasta_lists(case, argv, golden_inputs, tmp_path):
     assert open(txt).read().replace(work + "/", "") == open(expected(case + ".txt")).read()
 
 
+def test_countsketch_size_cache_names_and_registers(tmp_path):
+    """`sketch --prob --countsketch-size 700 -m 3 --cache`: reference file names (.ct_threshold3.CountMinCounting700.) and bytes."""
+    import gzip
+    paths = []
+    for f in ("dup.fa", "g0.fa", "rep.fa", "adv.fa"):
+        p = str(tmp_path / f); open(p, "wb").write(gzip.open(os.path.join(GOLD, "inputs", f + ".gz"), "rb").read()); paths.append(p)
+    z = np.load(expected("cs700_pmh_k31_S32_m3.npz"))
+    out = str(tmp_path / "out.stk"); cdir = tmp_path / "cache"; cdir.mkdir()
+    run(["sketch", "-k31", "-S32", "--prob", "--countsketch-size", "700", "-m", "3", "-o", out, "--cache", "--outprefix", str(cdir)] + paths)
+    cards, sigs = read_stacked(out)
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64)) and np.array_equal(cards, z["cards"])
+    assert sorted(os.listdir(cdir)) == list(z["cache_names"])
+    z = np.load(expected("cs100000_bmh_k31_S16.npz"))
+    run(["sketch", "-k31", "-S16", "--multiset", "-c", "100000", "-o", out] + paths)
+    cards, sigs = read_stacked(out)
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64)) and np.array_equal(cards, z["cards"])
+
+
 def test_cmp_topk_csr_file(tmp_path):
     from dashing2_b200 import synth
     z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
@@ -241,7 +259,7 @@ def test_cmp_topk_csr_file(tmp_path):
 
 def test_unsupported_options_fail_loudly(golden_inputs):
     names, paths = golden_inputs
-    for argv in (["sketch", "-k31", "--countsketch-size", "1000", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0], paths[1]],
+    for argv in (["sketch", "-k31", "--full-setsketch", "-m", "2", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0], paths[1]],
                  ["contain", paths[0]]):
         r = subprocess.run([EXE] + argv, capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.strip()

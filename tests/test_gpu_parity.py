@@ -155,6 +155,46 @@ def test_opmh_count_threshold_matches_oracle_seeded(S, k, w, thr):
     assert (r["regs_u64"][:5] != np.uint64(2**64 - 1)).any()
 
 
+COUNTSKETCH = {
+    "cs5000_bmh_k31_S32": dict(mode="bmh", S=32, k=31, cssize=5000),
+    "cs5000_pmh_k31_S32": dict(mode="pmh", S=32, k=31, cssize=5000),
+    "cs300_pmh_k21_w30_S64": dict(mode="pmh", S=64, k=21, w=30, cssize=300),
+    "cs100000_bmh_k31_S16": dict(mode="bmh", S=16, k=31, cssize=100000),
+    "cs700_pmh_k31_S32_m3": dict(mode="pmh", S=32, k=31, cssize=700, count_threshold=3),
+}
+
+
+@pytest.mark.parametrize("case", sorted(COUNTSKETCH))
+def test_count_sketch_weighted_matches_reference_golden(case):
+    """--countsketch-size n (src/counter.h:68-77,131-137) feeding BagMinHash / ProbMinHash: registers and total weights bit for bit."""
+    z = np.load(expected(case + ".npz"))
+    paths = [os.path.join(GOLD, "inputs", f) for f in ("dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz")]
+    c = ctx()
+    seq, off, ent = pack_files(paths)
+    r = c.sketch_batch(seq, off, ent, len(paths), c.params(**COUNTSKETCH[case]))
+    assert np.array_equal(u64(r["sig"]), u64(z["sigs"])) and np.array_equal(r["card"], z["cards"])
+
+
+@pytest.mark.parametrize("mode,S,k,w,cs,thr", [("pmh", 256, 31, -1, 4096, 0), ("bmh", 128, 21, 40, 1000, 2), ("pmh", 64, 17, -1, 37, 0), ("bmh", 64, 31, -1, 1 << 20, 0)])
+def test_count_sketch_weighted_matches_oracle_seeded(mode, S, k, w, cs, thr):
+    from dashing2_b200 import synth
+    files = []
+    for g, s in synth.family_genomes(4, 30000, seed=500 + S, dup_frac=0.3):
+        b = s.tobytes()
+        files.append([b[:20000], b[15000:] + b"N" + b[:2000], b""])
+    files.append([b"ACGT"])                                # an entity without a single k-mer
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    r = c.sketch_batch(seq, off, ent, len(files), c.params(mode=mode, S=S, k=k, w=w, cssize=cs, count_threshold=thr))
+    for e, recs in enumerate(files):
+        hv = np.concatenate([O.hash_stream(x, k, w) for x in recs] + [np.empty(0, np.uint64)])
+        o = O.weighted_sketch(hv, mode, S, thr, cs)
+        if len(hv) == 0:
+            assert r["card"][e] == 0
+            continue
+        assert np.array_equal(u64(r["sig"][e]), u64(o["sig"])) and r["card"][e] == o["card"], e
+
+
 @pytest.mark.parametrize("k,w,canon", [(31, -1, True), (21, 30, True), (15, -1, False), (11, 50, True), (32, -1, True)])
 def test_distinct_kmers_matches_oracle_seeded(k, w, canon):
     """Exact distinct k-mers / minimizers per entity against the oracle's hashed stream, on reads with repeats, Ns, lower case,
