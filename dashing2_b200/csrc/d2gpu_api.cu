@@ -366,7 +366,6 @@ __global__ void weighted_finalize_kernel(const uint64_t *keys, const unsigned lo
 
 int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                     uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d) {
-    if (ids_d) return fail(D2G_EUNSUPPORTED, "--save-kmers ids for BagMinHash/ProbMinHash are not implemented on the GPU yet");
     const uint32_t m = p->sketchsize;
     const uint64_t n = total_len, nreg = (uint64_t)n_ent * m;
     if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "counting sketches: at most 2^32 bases per batch (got %llu)", (unsigned long long)n);
@@ -450,7 +449,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
         d2g::weight_sum_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(entA, pos, nu, n_valid, threshold, wsum, wts);
         d2g::weighted_guess_kernel<<<(n_ent + 255) / 256, 256, 0, st>>>(wsum, n_ent, m, T, state);
         c->launches += 2;
-        d2g::WeightedArgs wa{hvA, entA, pos, nu, n_valid, threshold, m, T, state, keys, ovf, ovf_count, ovf_cap, error, wts, id_shift};
+        d2g::WeightedArgs wa{hvA, entA, pos, nu, n_valid, threshold, m, T, state, keys, ovf, ovf_count, ovf_cap, error, wts, id_shift, nullptr};
         d2g::TexpConsts tc{};
         if (p->mode == D2G_MODE_PROBMINHASH) {   // bmh.h:490-502
             const long double lambda = log1pl(1.L / (m - 1));
@@ -485,7 +484,27 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, c
             if (!h[0]) break;
             if (round == 39) return fail(D2G_ECUDA, "weighted sketch: bound verification did not converge");
         }
-    }
+        if (ids_d) {   // --save-kmers (bmh.h: ids_[idx] = id where a register is lowered): replay every element once more against the final
+                       // registers with the verified bounds; the element whose point equals a register is the one that set it
+            CU(cudaMemsetAsync(ids_d, 0, nreg * 8, st));
+            CU(cudaMemsetAsync(ovf_count, 0, 8, st));
+            wa.ids = ids_d;
+            if (p->mode == D2G_MODE_PROBMINHASH) {
+                d2g::pmh_kernel<<<gu, 128, 0, st>>>(wa, tc);
+                CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, st));
+                d2g::pmh_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, st>>>(wa, tc, c->aux2.as<uint32_t>());
+                c->launches += 2;
+            } else {
+                d2g::bmh_kernel<<<gu, 128, 0, st>>>(wa);
+                c->launches++;
+            }
+            unsigned int h[2] = {0, 0};
+            CU(cudaMemcpyAsync(h, n_redo, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            CU(cudaGetLastError());
+            if (h[1]) return fail(D2G_EUNSUPPORTED, "weighted sketch: device work queue overflow in the ids pass (code %u); split the batch", h[1]);
+        }
+    } else if (ids_d && nreg) CU(cudaMemsetAsync(ids_d, 0, nreg * 8, st));
     const uint64_t nthreads = std::max<uint64_t>(nreg, n_ent);
     weighted_finalize_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(keys, wsum, n_ent, m, sig_d, card_d);
     c->launches++;

@@ -150,7 +150,7 @@ __device__ __forceinline__ double texp_sample(uint64_t rngstate, const TexpConst
 }
 
 template <class PermState>
-__device__ __forceinline__ bool pmh_walk(uint64_t id, double w, uint32_t m, double T, const TexpConsts &tc, uint64_t *keys, PermState &ps) {
+__device__ __forceinline__ bool pmh_walk(uint64_t id, double w, uint32_t m, double T, const TexpConsts &tc, uint64_t *keys, PermState &ps, uint64_t *ids = nullptr) {
     uint64_t hi = id;
     const double wi = 1. / w;
     uint64_t rv = wyhash64(hi);
@@ -162,7 +162,8 @@ __device__ __forceinline__ bool pmh_walk(uint64_t id, double w, uint32_t m, doub
         uint32_t idx;
         if (!ps.step(i, samp, idx)) return false;
         const uint64_t kk = dkey(hv);
-        if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
+        if (ids) { if (kk == keys[idx]) ids[idx] = id; }             // ids pass: the registers are final, the element that equals one owns it
+        else if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
         if (++i >= m) return true;                                   // one full permutation touches every register
         hv = __dmul_rn(wi, (double)i);
         if (hv > T) return true;
@@ -178,6 +179,7 @@ struct WeightedArgs {
     uint64_t *ovf; unsigned long long *ovf_count; uint64_t ovf_cap;   // (unique index) of elements needing the dense walk
     unsigned int *error;
     const uint32_t *wts; int id_shift;   // count sketch: weight of run u (else its length), element id = key >> id_shift (else the key)
+    uint64_t *ids;                       // non-null: --save-kmers pass over final registers (every entity, no register update), ids [n_ent][m]
 };
 
 __global__ void pmh_kernel(const WeightedArgs a, const TexpConsts tc) {
@@ -185,11 +187,11 @@ __global__ void pmh_kernel(const WeightedArgs a, const TexpConsts tc) {
     if (u >= a.nu) return;
     const uint64_t i = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
     const uint32_t e = a.ent[i];
-    if (a.state[e] == 2u) return;
+    if (!a.ids && a.state[e] == 2u) return;
     const double w = a.wts ? (double)a.wts[u] : (double)(end - i);
     if (!(w > a.threshold)) return;
     SparsePerm sp;
-    if (!pmh_walk(a.hv[i] >> a.id_shift, w, a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, sp)) {
+    if (!pmh_walk(a.hv[i] >> a.id_shift, w, a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, sp, a.ids ? a.ids + (uint64_t)e * a.m : nullptr)) {
         const unsigned long long g = atomicAdd(a.ovf_count, 1ULL);
         if (g < a.ovf_cap) a.ovf[g] = u; else atomicExch(a.error, 1u);
     }
@@ -203,7 +205,8 @@ __global__ void pmh_longwalk_kernel(const WeightedArgs a, const TexpConsts tc, u
         const uint64_t i = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
         const uint32_t e = a.ent[i];
         ++dp.c;
-        pmh_walk(a.hv[i] >> a.id_shift, a.wts ? (double)a.wts[u] : (double)(end - i), a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, dp);
+        pmh_walk(a.hv[i] >> a.id_shift, a.wts ? (double)a.wts[u] : (double)(end - i), a.m, a.T[e], tc, a.keys + (uint64_t)e * a.m, dp,
+                 a.ids ? a.ids + (uint64_t)e * a.m : nullptr);
     }
 }
 
@@ -247,18 +250,21 @@ __global__ void bmh_kernel(const WeightedArgs a) {
     if (u >= a.nu) return;
     const uint64_t i0 = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
     const uint32_t e = a.ent[i0];
-    if (a.state[e] == 2u) return;
+    if (!a.ids && a.state[e] == 2u) return;
     const double w = a.wts ? (double)a.wts[u] : (double)(end - i0);
     if (!(w > a.threshold)) return;
     const double T = a.T[e];
     uint64_t *keys = a.keys + (uint64_t)e * a.m;
     const FastMod32 fm{};
+    const uint64_t id = a.hv[i0] >> a.id_shift;
+    uint64_t *ids = a.ids ? a.ids + (uint64_t)e * a.m : nullptr;
     auto apply = [&](uint32_t idx, double x) {
         const uint64_t kk = dkey(x);
-        if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
+        if (ids) { if (kk == keys[idx]) ids[idx] = id; }
+        else if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
     };
     PProc stack[BMH_STACK]; uint32_t sidx[BMH_STACK]; int sp = 0;
-    PProc p{0., 0., 1.7976931348623157e308, 0., a.hv[i0] >> a.id_shift};
+    PProc p{0., 0., 1.7976931348623157e308, 0., id};
     uint32_t pidx = bmh_step(p, a.m, fm);
     if (p.maxq <= w) apply(pidx, p.x);
     for (;;) {

@@ -182,10 +182,11 @@ def weighted_sketch(hv: np.ndarray, mode: str, S: int, count_threshold: float = 
         keys = np.empty(len(hv) + 1, dtype=np.uint64); cnt = np.empty(len(hv) + 1, dtype=np.float64)
         nd = L.d2o_count_exact(hv.copy(), len(hv), keys, cnt)
     regs = np.empty(2 * S - 1, dtype=np.float64)
-    L.d2o_pmh_reset(regs, None, S)
+    ids = np.zeros(S, dtype=np.uint64)
+    L.d2o_pmh_reset(regs, ids.ctypes.data, S)
     fn = L.d2o_pmh_update if mode == "pmh" else L.d2o_bmh_update
-    tw = fn(regs, None, S, keys[:nd].copy(), cnt[:nd].copy(), nd, float(count_threshold))
-    return dict(card=tw, sig=regs[:S].copy(), n_hashed=len(hv), n_distinct=nd)
+    tw = fn(regs, ids.ctypes.data, S, keys[:nd].copy(), cnt[:nd].copy(), nd, float(count_threshold))
+    return dict(card=tw, sig=regs[:S].copy(), ids=ids, n_hashed=len(hv), n_distinct=nd)
 
 
 def densify(sig: np.ndarray) -> np.ndarray:

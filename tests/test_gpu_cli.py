@@ -246,6 +246,23 @@ def test_countsketch_size_cache_names_and_registers(tmp_path):
     assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64)) and np.array_equal(cards, z["cards"])
 
 
+def test_save_kmers_with_counting_sketches(tmp_path):
+    """`sketch --multiset --save-kmers -o FILE`: FILE.kmer64 (header + ids) as the reference binary wrote it."""
+    import gzip
+    paths = []
+    for f in ("dup.fa", "g0.fa", "rep.fa", "adv.fa", "reads.fq"):
+        p = str(tmp_path / f); open(p, "wb").write(gzip.open(os.path.join(GOLD, "inputs", f + ".gz"), "rb").read()); paths.append(p)
+    for case, argv in (("ids_bmh_k31_S64", ["-k31", "-S64", "--multiset"]), ("ids_pmh_k21_w30_S32_seed5", ["-k21", "-w30", "-S32", "--prob", "--seed", "5"])):
+        z = np.load(expected(case + ".npz"))
+        out = str(tmp_path / (case + ".stk"))
+        run(["sketch", "--save-kmers", "-o", out] + argv + paths)
+        S = z["sigs"].shape[1]
+        assert np.array_equal(np.fromfile(out + ".kmer64", dtype=np.uint32, count=4), z["hdr"])
+        assert np.array_equal(np.fromfile(out + ".kmer64", dtype=np.uint64, offset=24).reshape(len(paths), S), z["ids"])
+        cards, sigs = read_stacked(out)
+        assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64)) and np.array_equal(cards, z["cards"])
+
+
 def test_cmp_topk_csr_file(tmp_path):
     from dashing2_b200 import synth
     z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))

@@ -155,6 +155,44 @@ def test_opmh_count_threshold_matches_oracle_seeded(S, k, w, thr):
     assert (r["regs_u64"][:5] != np.uint64(2**64 - 1)).any()
 
 
+WEIGHTED_IDS = {
+    "ids_bmh_k31_S64": dict(mode="bmh", S=64, k=31),
+    "ids_pmh_k31_S64": dict(mode="pmh", S=64, k=31),
+    "ids_pmh_k21_w30_S32_seed5": dict(mode="pmh", S=32, k=21, w=30, seed=5),
+    "ids_bmh_k15_S512": dict(mode="bmh", S=512, k=15),
+}
+
+
+@pytest.mark.parametrize("case", sorted(WEIGHTED_IDS))
+def test_weighted_save_kmers_ids_match_reference_golden(case):
+    """--save-kmers with --multiset / --prob: ids of the elements that set the registers (second pass over the final registers)."""
+    z = np.load(expected(case + ".npz"))
+    paths = [os.path.join(GOLD, "inputs", f) for f in ("dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz", "reads.fq.gz")]
+    c = ctx()
+    seq, off, ent = pack_files(paths)
+    r = c.sketch_batch(seq, off, ent, len(paths), c.params(**WEIGHTED_IDS[case]), want_ids=True)
+    assert np.array_equal(u64(r["sig"]), u64(z["sigs"])) and np.array_equal(r["card"], z["cards"])
+    assert np.array_equal(r["ids"], z["ids"])
+
+
+@pytest.mark.parametrize("mode,S,k,w,cs", [("pmh", 1024, 31, -1, 0), ("bmh", 256, 21, 40, 0), ("pmh", 128, 31, -1, 2000), ("bmh", 2048, 31, -1, 0)])
+def test_weighted_save_kmers_ids_match_oracle_seeded(mode, S, k, w, cs):
+    from dashing2_b200 import synth
+    files = []
+    for g, s in synth.family_genomes(3, 30000, seed=700 + S, dup_frac=0.3):
+        b = s.tobytes()
+        files.append([b[:20000], b[15000:] + b"N" + b[:2000]])
+    files.append([b"ACGT"])
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    r = c.sketch_batch(seq, off, ent, len(files), c.params(mode=mode, S=S, k=k, w=w, cssize=cs), want_ids=True)
+    for e, recs in enumerate(files[:-1]):
+        hv = np.concatenate([O.hash_stream(x, k, w) for x in recs])
+        o = O.weighted_sketch(hv, mode, S, 0, cs)
+        assert np.array_equal(u64(r["sig"][e]), u64(o["sig"])) and np.array_equal(r["ids"][e], o["ids"]), e
+    assert (r["ids"][-1] == 0).all()
+
+
 COUNTSKETCH = {
     "cs5000_bmh_k31_S32": dict(mode="bmh", S=32, k=31, cssize=5000),
     "cs5000_pmh_k31_S32": dict(mode="pmh", S=32, k=31, cssize=5000),

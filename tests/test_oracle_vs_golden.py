@@ -232,3 +232,22 @@ def test_count_sketch_weighted_matches_reference(case):
     for i, f in enumerate(COUNTSKETCH_FILES):
         o = O.sketch_file(os.path.join(GOLD, "inputs", f), **COUNTSKETCH[case])
         assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)) and o["card"] == z["cards"][i], (case, f)
+
+
+WEIGHTED_IDS = {
+    "ids_bmh_k31_S64": dict(mode="bmh", S=64, k=31),
+    "ids_pmh_k31_S64": dict(mode="pmh", S=64, k=31),
+    "ids_pmh_k21_w30_S32_seed5": dict(mode="pmh", S=32, k=21, w=30, seed=5),
+    "ids_bmh_k15_S512": dict(mode="bmh", S=512, k=15),
+}
+WEIGHTED_IDS_FILES = ["dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz", "reads.fq.gz"]
+
+
+@pytest.mark.parametrize("case", sorted(WEIGHTED_IDS))
+def test_weighted_save_kmers_ids_match_reference(case):
+    """--save-kmers with --multiset / --prob: the id (maskfn'd k-mer) of the element that set each register (FILE.kmer64)."""
+    z = np.load(expected(case + ".npz"))
+    for i, f in enumerate(WEIGHTED_IDS_FILES):
+        o = O.sketch_file(os.path.join(GOLD, "inputs", f), **WEIGHTED_IDS[case])
+        assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)) and o["card"] == z["cards"][i], (case, f)
+        assert np.array_equal(o["ids"], z["ids"][i]), (case, f)
