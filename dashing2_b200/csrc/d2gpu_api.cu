@@ -269,7 +269,6 @@ int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const
 int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d,
                const SketchRange *range = nullptr) {
-    if (ids_d) return fail(D2G_EUNSUPPORTED, "--save-kmers ids for Full SetSketch are not implemented on the GPU yet");
     if (n_ent == 0) return D2G_OK;
     const SketchRange rg = range ? *range : SketchRange{0, total_len, 0};
     const uint64_t work_len = rg.pos_end > rg.pos_base ? rg.pos_end - rg.pos_base : 0;
@@ -336,7 +335,23 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const 
         CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, c->stream));
         d2g::fss_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, c->stream>>>(ovf, ovf_count, ovf_cap, m, T, keys, c->aux2.as<uint32_t>());
         c->launches++;
-    }
+        if (ids_d) {   // --save-kmers: second pass over the final registers (FssIdsConsumer, fss_kernels.cuh)
+            unsigned long long h1 = 0;
+            CU(cudaMemcpyAsync(&h1, ovf_count, 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (h1 > ovf_cap) return fail(D2G_EUNSUPPORTED, "Full SetSketch: %llu elements needed a long register walk (queue holds %llu)", h1, (unsigned long long)ovf_cap);
+            // the bound of the ids pass: the largest final register of the entity (every point at or below it is replayed)
+            d2g::fss_final_bound_kernel<<<n_ent, 256, 0, c->stream>>>(keys, m, T);
+            CU(cudaMemsetAsync(ids_d, 0, nreg * 8, c->stream));
+            CU(cudaMemsetAsync(ovf_count, 0, 8, c->stream));
+            a.ent_state = nullptr; a.tile_stride = 1;
+            d2g::FssIdsConsumer::Params ip{keys, T, ids_d, ovf, ovf_count, ovf_cap, m};
+            if (int rc = launch_sketch<d2g::FssIdsConsumer>(c, a, ip, windowed, D2G_T_SKETCH_BOOT)) return rc;
+            CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, c->stream));
+            d2g::fss_longwalk_ids_kernel<<<(unsigned)(nslots / 32), 32, 0, c->stream>>>(ovf, ovf_count, ovf_cap, m, T, keys, ids_d, c->aux2.as<uint32_t>());
+            c->launches += 2;
+        }
+    } else if (ids_d && nreg) CU(cudaMemsetAsync(ids_d, 0, nreg * 8, c->stream));
     const uint64_t nthreads = std::max<uint64_t>(nreg, n_ent);
     d2g::fss_finalize_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, c->stream>>>(keys, n_ent, m, sig_d, card_d);
     c->launches++;
@@ -799,7 +814,7 @@ extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const ch
             rc = launch_opmh(c, p, seq_d, off_d + ch.r0, ent_d + ch.r0, nr, ne, rg.pos_end, c->regs.as<uint64_t>() + (uint64_t)ch.e0 * m, &rg);
         else if (p->mode == D2G_MODE_FULL_SETSKETCH)
             rc = launch_fss(c, p, seq_d, off_d + ch.r0, ent_d + ch.r0, nr, ne, rg.pos_end, c->sig.as<double>() + (uint64_t)ch.e0 * S,
-                            c->card.as<double>() + ch.e0, ids_out ? c->ids.as<uint64_t>() : nullptr, &rg);
+                            c->card.as<double>() + ch.e0, ids_out ? c->ids.as<uint64_t>() + (uint64_t)ch.e0 * S : nullptr, &rg);
         else
             rc = launch_weighted(c, p, seq_d, off_d, ent_d, n_rec, n_entities, total_len, c->sig.as<double>(), c->card.as<double>(),
                                  ids_out ? c->ids.as<uint64_t>() : nullptr);

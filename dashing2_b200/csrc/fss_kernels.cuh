@@ -340,6 +340,58 @@ struct FssMainConsumer {
     }
 };
 
+// one CTA per entity: T[e] = largest final register (keys are order preserving; an entity without elements keeps its bound)
+__global__ void fss_final_bound_kernel(const uint64_t *keys, uint32_t m, double *T) {
+    __shared__ uint64_t red[256];
+    const uint32_t e = blockIdx.x;
+    uint64_t mx = 0;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) mx = max(mx, keys[(uint64_t)e * m + i]);
+    red[threadIdx.x] = mx; __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if ((int)threadIdx.x < s) red[threadIdx.x] = max(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    if (threadIdx.x == 0 && red[0] != FSS_KEY_EMPTY) T[e] = dunkey(red[0]);
+}
+
+// ---- --save-kmers: ids_[idx] = id wherever CSetSketch::update lowers a register (setsketch.h:400-404) -----------------
+// A second, read-only pass once the registers are final: every element whose first point is not above the entity's verified bound
+// T replays its walk, and a point that EQUALS its register names the element that set it.  No 128-bit atomics in the hot pass,
+// and no cost at all without --save-kmers.  Walks that outrun the sparse permutation state go to the long-walk kernel below.
+struct IdsSink {
+    const uint64_t *keys; uint64_t *ids; uint64_t x;
+    __device__ __forceinline__ void put(uint32_t idx, uint64_t kk) const { if (kk == keys[idx]) ids[idx] = x; }
+};
+struct FssIdsConsumer {
+    struct Params { const uint64_t *keys; const double *T; uint64_t *ids; uint64_t *ovf; unsigned long long *ovf_count; uint64_t ovf_cap; uint32_t m; };
+    static __host__ __device__ size_t smem_bytes(uint32_t, bool) { return 16; }
+    static constexpr bool kEveryWindow = false;
+    static constexpr int kMinBlocks = 2;
+    Params p; double T; uint64_t rvmin; uint32_t cur;
+    __device__ __forceinline__ void init(unsigned char *, const Params &pp, bool) { p = pp; T = 1.7976931348623157e308; rvmin = 0; cur = 0; }
+    __device__ __forceinline__ void begin_entity(uint32_t ent, uint64_t) { T = p.T[ent]; rvmin = FssMainConsumer::rvmin_for(T, p.m); cur = ent; }
+    __device__ __forceinline__ void consume(uint64_t hv) {
+        if (cehash(hv ^ FSS_XOR) < rvmin) return;
+        SparsePerm sp;
+        const IdsSink sink{p.keys + (uint64_t)cur * p.m, p.ids + (uint64_t)cur * p.m, hv};
+        if (!fss_walk(hv, p.m, T, sink, sp)) {
+            const unsigned long long g = atomicAdd(p.ovf_count, 1ULL);
+            if (g < p.ovf_cap) { p.ovf[2 * g] = hv; p.ovf[2 * g + 1] = cur; }
+        }
+    }
+    __device__ __forceinline__ void end_tile(uint32_t) {}
+    __device__ __forceinline__ void flush(uint32_t) {}
+};
+__global__ void fss_longwalk_ids_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,
+                                        const double *T, const uint64_t *keys, uint64_t *ids, uint32_t *scratch) {
+    const uint64_t slot = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t nslots = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n = min((uint64_t)*ovf_count, ovf_cap);
+    DensePerm dp; dp.g = scratch + slot * 2ULL * m; dp.v = dp.g + m; dp.c = 0;
+    for (uint64_t e = slot; e < n; e += nslots) {
+        const uint64_t x = ovf[2 * e]; const uint32_t ent = (uint32_t)ovf[2 * e + 1];
+        ++dp.c;
+        fss_walk(x, m, T[ent], IdsSink{keys + (uint64_t)ent * m, ids + (uint64_t)ent * m, x}, dp);
+    }
+}
+
 // long walks: one thread per queued element, dense permutation state in HBM scratch (slot-private)
 __global__ void fss_longwalk_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,
                                     const double *T, uint64_t *keys, uint32_t *scratch) {

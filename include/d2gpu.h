@@ -84,7 +84,7 @@ uint64_t d2g_count_kmers(const uint64_t *rec_off, uint64_t n_rec, int32_t k);
  *                                 SketchingResult::signatures_ (src/fastxsketch.h:47)
  *   card_out     [n_entities]     cardinality estimate (oph.h:240-247 / setsketch.h:553-561 / total weight)
  *   ids_out      [n_entities][S]  --save-kmers ids: the hashed k-mer behind each register (oph.h:264-271; bmh.h ids_ of BagMinHash /
- *                                 ProbMinHash, the bucket index under countsketch_size); not for Full SetSketch (D2G_EUNSUPPORTED)
+ *                                 ProbMinHash, the bucket index under countsketch_size; setsketch.h:400-404 for the Full SetSketch)
  * All pointers are HOST memory; the call copies in, runs the kernels, copies out and synchronises.
  */
 int d2g_sketch_batch(d2g_ctx *ctx, const d2g_sketch_params *p,

@@ -253,6 +253,7 @@ def test_save_kmers_with_counting_sketches(tmp_path):
     for f in ("dup.fa", "g0.fa", "rep.fa", "adv.fa", "reads.fq"):
         p = str(tmp_path / f); open(p, "wb").write(gzip.open(os.path.join(GOLD, "inputs", f + ".gz"), "rb").read()); paths.append(p)
     for case, argv in (("ids_bmh_k31_S64", ["-k31", "-S64", "--multiset"]), ("ids_pmh_k21_w30_S32_seed5", ["-k21", "-w30", "-S32", "--prob", "--seed", "5"])):
+        assert case  # the Full SetSketch .kmer64 file is covered by tests/test_gpu_parity.py::test_fss_save_kmers_ids_match_reference_golden
         z = np.load(expected(case + ".npz"))
         out = str(tmp_path / (case + ".stk"))
         run(["sketch", "--save-kmers", "-o", out] + argv + paths)

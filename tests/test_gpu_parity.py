@@ -193,6 +193,43 @@ def test_weighted_save_kmers_ids_match_oracle_seeded(mode, S, k, w, cs):
     assert (r["ids"][-1] == 0).all()
 
 
+FSS_IDS = {"ids_fss_k31_S256": dict(S=256, k=31), "ids_fss_k21_w30_S64_seed5": dict(S=64, k=21, w=30, seed=5), "ids_fss_k15_S1024": dict(S=1024, k=15)}
+
+
+@pytest.mark.parametrize("case", sorted(FSS_IDS))
+def test_fss_save_kmers_ids_match_reference_golden(case):
+    """--save-kmers --full-setsketch: ids from the read-only second pass (FssIdsConsumer), including inputs far smaller than the sketch
+    (reads.fq: every element walks all registers -> long-walk kernel)."""
+    z = np.load(expected(case + ".npz"))
+    paths = [os.path.join(GOLD, "inputs", f) for f in ("dup.fa.gz", "g0.fa.gz", "g1.fa.gz", "adv.fa.gz", "reads.fq.gz")]
+    c = ctx()
+    seq, off, ent = pack_files(paths)
+    r = c.sketch_batch(seq, off, ent, len(paths), c.params(mode="fss", **FSS_IDS[case]), want_ids=True)
+    assert np.array_equal(u64(r["sig"]), u64(z["sigs"]))
+    assert np.array_equal(r["ids"], z["ids"])
+
+
+@pytest.mark.parametrize("S,k,w,chunk", [(512, 31, -1, 0), (2048, 31, 51, 0), (128, 17, 40, 60000), (4096, 31, -1, 0)])
+def test_fss_save_kmers_ids_match_oracle_seeded(S, k, w, chunk, monkeypatch, tmp_path):
+    from dashing2_b200 import synth
+    if chunk:
+        monkeypatch.setenv("D2G_CHUNK_BYTES", str(chunk))      # several launches: ids land at their entity's offset
+    files = []
+    for g, s in synth.family_genomes(4, 60000, seed=900 + S):
+        b = s.tobytes()
+        files.append([b[:40000], b[40000:] + b"N" + b[:100]])
+    files.append([b"ACGT"])
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    r = c.sketch_batch(seq, off, ent, len(files), c.params(mode="fss", S=S, k=k, w=w), want_ids=True)
+    for e, recs in enumerate(files[:-1]):
+        f = tmp_path / f"e{e}.fa"
+        f.write_bytes(b"".join(b">r\n" + x + b"\n" for x in recs))
+        o = O.sketch_file(str(f), "fss", S, k, w)
+        assert np.array_equal(u64(r["sig"][e]), u64(o["sig"])) and np.array_equal(r["ids"][e], o["ids"]), e
+    assert (r["ids"][-1] == 0).all()
+
+
 COUNTSKETCH = {
     "cs5000_bmh_k31_S32": dict(mode="bmh", S=32, k=31, cssize=5000),
     "cs5000_pmh_k31_S32": dict(mode="pmh", S=32, k=31, cssize=5000),

@@ -251,3 +251,17 @@ def test_weighted_save_kmers_ids_match_reference(case):
         o = O.sketch_file(os.path.join(GOLD, "inputs", f), **WEIGHTED_IDS[case])
         assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)) and o["card"] == z["cards"][i], (case, f)
         assert np.array_equal(o["ids"], z["ids"][i]), (case, f)
+
+
+FSS_IDS = {"ids_fss_k31_S256": dict(S=256, k=31), "ids_fss_k21_w30_S64_seed5": dict(S=64, k=21, w=30, seed=5), "ids_fss_k15_S1024": dict(S=1024, k=15)}
+FSS_IDS_FILES = ["dup.fa.gz", "g0.fa.gz", "g1.fa.gz", "adv.fa.gz", "reads.fq.gz"]
+
+
+@pytest.mark.parametrize("case", sorted(FSS_IDS))
+def test_fss_save_kmers_ids_match_reference(case):
+    """--save-kmers --full-setsketch: the hashed k-mer that set each register (src/setsketch.h:400-404)."""
+    z = np.load(expected(case + ".npz"))
+    for i, f in enumerate(FSS_IDS_FILES):
+        o = O.sketch_file(os.path.join(GOLD, "inputs", f), mode="fss", **FSS_IDS[case])
+        assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)), (case, f)
+        assert np.array_equal(o["ids"], z["ids"][i]), (case, f)
