@@ -29,7 +29,7 @@ class SketchParams(C.Structure):
 class CmpParams(C.Structure):
     _fields_ = [("sketchsize", C.c_uint32), ("cmp_kind", C.c_int32), ("measure", C.c_int32), ("k", C.c_int32),
                 ("shape", C.c_int32), ("n", C.c_uint64), ("nq", C.c_uint64), ("regbytes", C.c_double),
-                ("compressed_b", C.c_longdouble)]
+                ("compressed_b", C.c_longdouble), ("nlsh", C.c_int32)]
 
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c_uint64, C.c_uint64)
@@ -261,12 +261,13 @@ class Context:
         _check(self.L.d2g_cmp_counts(self.h, S, cmp_kind, _ptr(rows), nr, _ptr(cols), nc, _ptr(c0), _ptr(c1)))
         return c0, c1
 
-    def lsh_topk(self, regs: np.ndarray, cards: np.ndarray, topk: int, measure="similarity", k=31, cmp_kind=0, rows=None):
+    def lsh_topk(self, regs: np.ndarray, cards: np.ndarray, topk: int, measure="similarity", k=31, cmp_kind=0, rows=None, nlsh=0):
         """--topk neighbour graph (d2g_lsh_topk / d2g_lsh_topk_rows for rows=(begin, end)): returns CSR
         (indptr u64[rows+1], indices u32[nnz], data f32[nnz])."""
         regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
         n, S = regs.shape
         p = self.cmp_params(S, n, "symmetric", measure, k=k, cmp_kind=cmp_kind)
+        p.nlsh = nlsh
         x0, x1 = rows if rows is not None else (0, n)
         indptr = np.zeros(x1 - x0 + 1, dtype=np.uint64)
         pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()

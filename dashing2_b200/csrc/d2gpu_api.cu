@@ -1439,7 +1439,10 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     if (S < 2) return fail(D2G_EINVAL, "sketchsize must be >= 2 for the default two LSH table types");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    const uint32_t ntab = S + S / 2;                                   // cmp_core.cpp:757-770 with nLSH = 2
+    if (p->nlsh != 0 && p->nlsh != 1 && p->nlsh != 2)
+        return fail(D2G_EUNSUPPORTED, "--nLSH %d: only 1 and 2 (the default) are implemented; larger values add XXH64-keyed tables (src/ssi.h:379-392)", p->nlsh);
+    const uint32_t n1 = p->nlsh == 1 ? 0 : S / 2;                      // two-register tables
+    const uint32_t ntab = S + n1;                                      // cmp_core.cpp:757-770
     uint64_t ntoquery = (uint64_t)((float)topk * 3.5f);                // index_build.cpp:57-60
     ntoquery = std::min<uint64_t>(ntoquery, n - 1);
     CU(cudaFuncSetAttribute(d2g::lsh_trim_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d2g::LSH_TRIM_BIG_CAP * 8));
@@ -1499,7 +1502,7 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
         const int wpb = 4;
         const size_t smem = (size_t)wpb * 2 * maxcand * 4;
         KernelTimer kt(c, D2G_T_CMP);
-        d2g::lsh_query_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(regs_d, n, S, kB, iB, maxcand, cand, cnt, ncand);
+        d2g::lsh_query_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(regs_d, n, S, kB, iB, maxcand, cand, cnt, ncand, n1);
         c->launches++;
     }
     // 4. arrivals, stable sort by destination list, segment starts, replay

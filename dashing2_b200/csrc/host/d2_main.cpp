@@ -58,6 +58,7 @@ struct Opts {
     int shape = D2G_SYMMETRIC; bool phylip = false;
     int topk = -1;
     unsigned count_threshold = 0;          // -m / --count-threshold (src/options.h:83-84,352)
+    int nlsh = 2;                          // --nLSH (src/options.h:162-163,380)
     uint64_t cssize = 0;                   // -c / --countsketch-size / --countmin-size (src/options.h:78-79,357)
     int ngpus = 1;                         // --gpus N (not a reference option; also D2G_GPUS): files / output rows sharded over N devices
     double fastcmp = 8.; bool bbit = false;   // --fastcmp/--regsize N, --bbit-sigs (src/options.h:76,101)
@@ -96,6 +97,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
             if (o.fastcmp != 8. && o.fastcmp != 4. && o.fastcmp != 2. && o.fastcmp != 1.) die("--fastcmp must have 8, 4, 2, or 1 as the argument. These are the only register sizes supported.");
         }
         else if (a == "--countsketch-size" || a == "--countmin-size" || shortarg("-c")) o.cssize = std::strtoull(arg().c_str(), nullptr, 10);
+        else if (a == "--nLSH" || a == "--nlsh") o.nlsh = std::stoi(arg());
         else if (a == "--gpus") o.ngpus = std::max(1, std::stoi(arg()));
         else if (a == "--bbit-sigs") o.bbit = true;
         else if (a == "--binary-output" || a == "--emit-binary" || a == "--binary") o.binary = true;
@@ -526,6 +528,7 @@ void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
     const bool to_stdout = o.cmpout.empty() || o.cmpout[0] == '-';
     std::FILE *fp = to_stdout ? stdout : std::fopen(o.cmpout.c_str(), "wb");
     if (!fp) die("Failed to open path " + o.cmpout + " for writing");
+    cp.nlsh = o.nlsh;
     if (o.topk > 0) {   // KNN graph: build_index + refine_results + emit_neighbors (src/cmp_core.cpp:756-799, src/emitnn.cpp:12-52)
         cp.shape = D2G_SYMMETRIC;
         std::vector<uint64_t> indptr(n + 1); uint32_t *idx = nullptr; float *val = nullptr;

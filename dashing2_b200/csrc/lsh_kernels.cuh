@@ -36,7 +36,7 @@ __global__ void lsh_keys_kernel(const double *regs, uint64_t n, uint32_t S, uint
 
 // One warp per query.  skeys/sids: [ntab][n] sorted per table.  Outputs cand[q][maxcand], cnt[q][maxcand], ncand[q].
 __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, const uint32_t *skeys, const uint32_t *sids,
-                                 uint32_t maxcand, uint32_t *cand, uint32_t *cnt, uint32_t *ncand) {
+                                 uint32_t maxcand, uint32_t *cand, uint32_t *cnt, uint32_t *ncand, uint32_t n1) {
     extern __shared__ uint32_t sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const uint64_t q = (uint64_t)blockIdx.x * wpb + wib;
@@ -44,13 +44,13 @@ __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, con
     uint32_t *set_id = sm + (size_t)wib * 2 * maxcand, *set_ct = set_id + maxcand;
     const double *sig = regs + q * S;
     uint32_t nset = 0;
-    const uint32_t ntab = S + S / 2;
-    // scan order: type 1 tables j = 0..S/2-1 (global index S + j), then type 0 tables j = 0..S-1 (ssi.h:425)
+    const uint32_t ntab = S + n1;    // n1 = number of two-register tables: S / 2 (--nLSH 2, the default) or 0 (--nLSH 1)
+    // scan order: type 1 tables j = 0..n1-1 (global index S + j), then type 0 tables j = 0..S-1 (ssi.h:425)
     for (uint32_t base = 0; base < ntab && nset < maxcand; base += 32) {
         const uint32_t o = base + lane;                  // position in scan order
         uint32_t lo = 0, hi = 0;
         if (o < ntab) {
-            const uint32_t t = o < S / 2 ? S + o : o - S / 2;
+            const uint32_t t = o < n1 ? S + o : o - n1;
             const uint32_t key = t < S ? lsh_key(sig, 0, t) : lsh_key(sig, 1, t - S);
             const uint32_t *K = skeys + (uint64_t)t * n;
             uint32_t a = 0, b = (uint32_t)n;
@@ -63,7 +63,7 @@ __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, con
             const uint32_t blo = __shfl_sync(0xffffffffu, lo, l), bhi = __shfl_sync(0xffffffffu, hi, l);
             const uint32_t oo = base + l;
             if (oo >= ntab) break;
-            const uint32_t t = oo < S / 2 ? S + oo : oo - S / 2;
+            const uint32_t t = oo < n1 ? S + oo : oo - n1;
             const uint32_t *I = sids + (uint64_t)t * n;
             for (uint32_t p = blo; p < bhi && nset < maxcand; p += 32) {
                 const bool have = p + lane < bhi;

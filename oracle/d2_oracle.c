@@ -823,9 +823,12 @@ static int cmp_kid(const void *a, const void *b) {
     if (x->key != y->key) return x->key < y->key ? -1 : 1;
     return x->id < y->id ? -1 : (x->id > y->id);
 }
-typedef struct { kid_t *tab; uint64_t n, S, ntab; } lshidx_t; /* table t occupies tab[t*n, (t+1)*n), sorted by (key,id) */
+typedef struct { kid_t *tab; uint64_t n, S, ntab; int nlsh; } lshidx_t; /* table t occupies tab[t*n, (t+1)*n), sorted by (key,id) */
+/* --nLSH: table types 0 .. nlsh-1 with 1, 2, ... registers per key (src/cmp_core.cpp:757-770); 1 and 2 (the default) are restated */
+static int g_nlsh = 2;
+void d2o_set_nlsh(int nlsh) { g_nlsh = nlsh == 1 ? 1 : 2; }
 static lshidx_t lsh_build(const double *regs, uint64_t n, uint64_t S) {
-    lshidx_t ix; ix.n = n; ix.S = S; ix.ntab = S + S / 2;
+    lshidx_t ix; ix.n = n; ix.S = S; ix.nlsh = g_nlsh; ix.ntab = S + (ix.nlsh > 1 ? S / 2 : 0);
     ix.tab = (kid_t *)malloc(sizeof(kid_t) * ix.ntab * n);
     for (uint64_t t = 0; t < ix.ntab; ++t) {
         const uint32_t type = t < S ? 0 : 1; const uint64_t j = t < S ? t : t - S;
@@ -838,7 +841,7 @@ static lshidx_t lsh_build(const double *regs, uint64_t n, uint64_t S) {
 static uint64_t lsh_query(const lshidx_t *ix, const double *sig, uint64_t maxcand, uint32_t *ids, uint32_t *counts) {
     uint64_t nc = 0;
     const uint64_t n = ix->n, S = ix->S;
-    for (int type = 1; type >= 0 && nc < maxcand; --type) { /* most specific table type first, ssi.h:425 */
+    for (int type = ix->nlsh - 1; type >= 0 && nc < maxcand; --type) { /* most specific table type first, ssi.h:425 */
         const uint64_t nsubs = type ? S / 2 : S;
         for (uint64_t j = 0; j < nsubs; ++j) {
             const uint32_t key = d2o_lsh_key(sig, (uint32_t)type, j);

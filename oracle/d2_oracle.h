@@ -120,6 +120,8 @@ double d2o_bmh_update(double *regs, uint64_t *ids, uint32_t m, const uint64_t *k
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* --nLSH for the calls below: 2 (default: table types 0 and 1) or 1 (type 0 only); src/cmp_core.cpp:757-770. */
+void d2o_set_nlsh(int nlsh);
 /* LSH keys: table type 0 = one register, type 1 = two registers (default --nLSH 2); truncated to 32 bits. */
 uint32_t d2o_lsh_key(const double *sig, uint32_t table_type, uint64_t j);
 /* candidate scan for one query; ids/counts must hold maxcand entries; returns the number of candidates. */

@@ -66,6 +66,7 @@ def lib():
     for nm in ("d2o_pmh_update", "d2o_bmh_update"):
         getattr(L, nm).restype = C.c_double
         getattr(L, nm).argtypes = [f64p, C.c_void_p, C.c_uint32, u64p, f64p, C.c_uint64, C.c_double]
+    L.d2o_set_nlsh.argtypes = [C.c_int]
     L.d2o_topk.restype = C.c_uint64
     L.d2o_topk.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, u64p,
                            C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
@@ -238,14 +239,18 @@ def allpairs_compressed(cregs, cards, kind, measure, fd, bbit, b, k=31, nq=0):
     return out
 
 
-def topk(regs, cards, K, measure="similarity", k=31, cmp_kind=0):
+def topk(regs, cards, K, measure="similarity", k=31, cmp_kind=0, nlsh=2):
     """Reference -p1 top-k pipeline -> CSR (indptr, indices, data)."""
     L = lib()
     regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
     n, S = regs.shape
     indptr = np.zeros(n + 1, dtype=np.uint64)
     pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()
-    nnz = L.d2o_topk(regs, cards, n, S, K, MEASURES[measure], k, cmp_kind, indptr, C.byref(pi), C.byref(pv))
+    L.d2o_set_nlsh(int(nlsh))
+    try:
+        nnz = L.d2o_topk(regs, cards, n, S, K, MEASURES[measure], k, cmp_kind, indptr, C.byref(pi), C.byref(pv))
+    finally:
+        L.d2o_set_nlsh(2)
     idx = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
     val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()
     L.d2o_free(pi); L.d2o_free(pv)

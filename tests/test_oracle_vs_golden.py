@@ -265,3 +265,12 @@ def test_fss_save_kmers_ids_match_reference(case):
         o = O.sketch_file(os.path.join(GOLD, "inputs", f), mode="fss", **FSS_IDS[case])
         assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)), (case, f)
         assert np.array_equal(o["ids"], z["ids"][i]), (case, f)
+
+
+@pytest.mark.parametrize("K", [5, 32])
+def test_topk_nlsh1_matches_reference(K):
+    """--nLSH 1: only the S one-register tables are built and scanned (src/cmp_core.cpp:757-770)."""
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    ip, ix, dv = O.read_csr(expected(f"topk{K}_nlsh1_sk600.csr"))
+    gp, gi, gv = O.topk(z["regs"], z["cards"], K, "similarity", k=32, nlsh=1)
+    assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
