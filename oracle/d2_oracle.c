@@ -216,6 +216,100 @@ uint64_t d2o_hash_stream(const char *seq, uint64_t len, int k, int w, int canon,
 #undef EMIT
 
 /* ------------------------------------------------------------------------------------------ */
+/* k > 32: RollingHasher<uint64_t> over CyclicHash (bonsai encoder.h:644-865, rollinghash/cyclichash.h,
+ * rollinghash/characterhash.h).  Word size 64, so every rotation is a plain 64-bit rotate.  Character tables:
+ * 256 draws of WyRand<uint64_t> seeded with (seed1 ^ seed2) for the forward hasher and (seed2 * seed1) ^ (seed2 ^ seed1)
+ * for the reverse-complement hasher, truncated to 32 bits (CyclicHash::seed -> CharacterHash::seed(uint32_t)), with the
+ * constructor defaults seed1 = 1337, seed2 = 137 (encoder.h:673, src/d2.h:136). */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t tab[256]; uint64_t h; int myr; } cyc_t;
+static inline uint64_t rotl64(uint64_t x, int r) { r &= 63; return r ? (x << r) | (x >> (64 - r)) : x; }
+static void cyc_init(cyc_t *c, int k, uint64_t s1, uint64_t s2) {
+    uint64_t state = (uint32_t)(s1 ^ s2);          /* CyclicHash::seed: s1 ^= s2; CharacterHash::seed takes uint32_t */
+    if (!state) state = 1337;                      /* WyRand(seed): seed ? seed : 1337 (wy.h:112) */
+    for (int i = 0; i < 256; ++i) c->tab[i] = d2o_wyhash64(&state);   /* clear_hashvalues: next &= all-ones, never above maxval */
+    c->h = 0; c->myr = k % 64;
+}
+static inline void cyc_eat(cyc_t *c, uint8_t in) { c->h = rotl64(c->h, 1) ^ c->tab[in]; }                                   /* cyclichash.h:118-121 */
+static inline void cyc_update(cyc_t *c, uint8_t out, uint8_t in) { c->h = rotl64(c->h, 1) ^ rotl64(c->tab[out], c->myr) ^ c->tab[in]; } /* :101-108 */
+static inline void cyc_reverse_update(cyc_t *c, uint8_t out, uint8_t in) {                                                  /* :110-116 */
+    c->h ^= rotl64(c->tab[out], c->myr) ^ c->tab[in];
+    c->h = (c->h >> 1) | ((c->h & 1) << 63);
+}
+static inline uint8_t rc_code(unsigned char ch) { const int c = dna_code(ch); return c < 0 ? (uint8_t)255 : (uint8_t)(3 - c); } /* cstr_rc_lut */
+
+/* RollingHasher::for_each_hash of ONE record (encoder.h:692-797), each value through maskfn.  Canonical: min(forward, reverse
+ * complement) per position, or -- windowed -- BOTH hashes pushed into the window of w-k+1 entries (two pushes per position, the
+ * window is not reset at an N), tail flush of a partially filled window.  An N skips k further bases (the `fixup` jump) and
+ * ends the record when fewer than 2k bases remain (canonical path only). */
+#define EMIT(v) do { if (nout < cap) out[nout] = d2o_wang64((v) ^ xormask); ++nout; } while (0)
+uint64_t d2o_hash_stream_rolling(const char *seq, uint64_t len, int k, int w, int canon, uint64_t xormask,
+                                 uint64_t *out, uint64_t cap) {
+    uint64_t nout = 0;
+    const unsigned char *s = (const unsigned char *)seq;
+    const uint64_t l = len, K = (uint64_t)k;
+    if (l < K) return 0;
+    cyc_t fw, rc;
+    cyc_init(&fw, k, 1337, 137);
+    cyc_init(&rc, k, 137ULL * 1337ULL, 137ULL ^ 1337ULL);
+    const int windowed = w > k;
+    window_t win; win_init(&win, windowed ? (uint32_t)(w - k + 1) : 1);
+    uint64_t i = 0, nf = 0, mn;
+    if (canon) {
+        for (;;) {
+            /* fill */
+            int ended = 0;
+            for (; nf < K && i < l; ++i) {
+                const int v1 = dna_code(s[i]);
+                if (v1 < 0) {
+                    if (i + 2 * K >= l) { ended = 1; break; }
+                    i += K; nf = 0; fw.h = 0; rc.h = 0;
+                } else { cyc_eat(&fw, (uint8_t)v1); cyc_eat(&rc, rc_code(s[i - nf + K - 1])); ++nf; }
+            }
+            if (ended || nf < K) break;
+            if (windowed) { if (win_push(&win, fw.h, d2o_frev64(fw.h), &mn)) EMIT(mn); if (win_push(&win, rc.h, d2o_frev64(rc.h), &mn)) EMIT(mn); }
+            else EMIT(fw.h < rc.h ? fw.h : rc.h);
+            int hitn = 0;
+            for (; i < l; ++i) {
+                const int v1 = dna_code(s[i]);
+                if (v1 < 0) { hitn = 1; break; }
+                cyc_update(&fw, (uint8_t)dna_code(s[i - K]), (uint8_t)v1);
+                cyc_reverse_update(&rc, rc_code(s[i]), rc_code(s[i - K]));
+                if (windowed) { if (win_push(&win, fw.h, d2o_frev64(fw.h), &mn)) EMIT(mn); if (win_push(&win, rc.h, d2o_frev64(rc.h), &mn)) EMIT(mn); }
+                else EMIT(fw.h < rc.h ? fw.h : rc.h);
+            }
+            if (!hitn) break;
+            /* goto fixup: the same jump as in the fill loop, then the fill loop's ++i */
+            if (i + 2 * K >= l) break;
+            i += K; nf = 0; fw.h = 0; rc.h = 0; ++i;
+        }
+        if (windowed && win.n > 0 && win.n < win.wsz) EMIT(win_min(&win).el);
+    } else {
+        for (;;) {
+            for (; nf < K && i < l; ++i) {
+                const int v1 = dna_code(s[i]);
+                if (v1 < 0) { i += K; nf = 0; fw.h = 0; }
+                else { cyc_eat(&fw, (uint8_t)v1); ++nf; }
+            }
+            if (nf < K) { free(win.ring); return nout; }      /* "All failed": returns without the tail flush (encoder.h:776) */
+            if (windowed) { if (win_push(&win, fw.h, d2o_frev64(fw.h), &mn)) EMIT(mn); } else EMIT(fw.h);
+            int hitn = 0;
+            for (; i < l; ++i) {
+                if (dna_code(s[i]) < 0) { hitn = 1; break; }
+                cyc_update(&fw, (uint8_t)dna_code(s[i - K]), (uint8_t)dna_code(s[i]));
+                if (windowed) { if (win_push(&win, fw.h, d2o_frev64(fw.h), &mn)) EMIT(mn); } else EMIT(fw.h);
+            }
+            if (!hitn) break;
+            i += K; nf = 0; fw.h = 0; ++i;
+        }
+        if (windowed && win.n > 0 && win.n < win.wsz) EMIT(win_min(&win).el);
+    }
+    free(win.ring);
+    return nout;
+}
+#undef EMIT
+
+/* ------------------------------------------------------------------------------------------ */
 /* One-permutation MinHash (LazyOnePermSetSketch<uint64_t>)                                     */
 /* ------------------------------------------------------------------------------------------ */
 

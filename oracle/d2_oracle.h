@@ -39,6 +39,10 @@ uint64_t d2o_kmer_positions(uint64_t len, int k);
 uint64_t d2o_hash_stream(const char *seq, uint64_t len, int k, int w, int canon, uint64_t xormask,
                          uint64_t *out, uint64_t cap);
 
+/* Same for k > 32: RollingHasher<uint64_t> over CyclicHash (bonsai encoder.h:644-865, rollinghash/cyclichash.h). */
+uint64_t d2o_hash_stream_rolling(const char *seq, uint64_t len, int k, int w, int canon, uint64_t xormask,
+                                 uint64_t *out, uint64_t cap);
+
 /* ---- One-permutation MinHash (src/oph.h) --------------------------------------------------- */
 #define D2O_OPH_SEED 0x8f1896f3f85ef4a3ULL  /* std::mt19937_64(0x321b919a61cb41f7)(), oph.h:59,142 */
 uint32_t d2o_opmh_m(uint32_t sketchsize);   /* oph.h:145 (rounded up to even) */

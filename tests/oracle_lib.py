@@ -43,6 +43,8 @@ def lib():
     L.d2o_xormask_for_seed.restype = C.c_uint64; L.d2o_xormask_for_seed.argtypes = [C.c_uint64]
     L.d2o_hash_stream.restype = C.c_uint64
     L.d2o_hash_stream.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, C.c_uint64]
+    L.d2o_hash_stream_rolling.restype = C.c_uint64
+    L.d2o_hash_stream_rolling.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, C.c_uint64]
     L.d2o_opmh_m.restype = C.c_uint32; L.d2o_opmh_m.argtypes = [C.c_uint32]
     L.d2o_opmh_reset.argtypes = [u64p, f64p, C.c_uint32]
     L.d2o_opmh_update.argtypes = [u64p, f64p, C.c_uint32, u64p, C.c_uint64]
@@ -115,8 +117,9 @@ def read_fastx(path: str):
 
 def hash_stream(seq: bytes, k: int, w: int = -1, canon: bool = True, seed: int = 0) -> np.ndarray:
     L = lib()
-    out = np.empty(len(seq) + 2, dtype=np.uint64)
-    n = L.d2o_hash_stream(seq, len(seq), k, w, int(canon), L.d2o_xormask_for_seed(seed), out, len(out))
+    out = np.empty(2 * len(seq) + 4, dtype=np.uint64)
+    fn = L.d2o_hash_stream_rolling if k > 32 else L.d2o_hash_stream      # k > 32: RollingHasher (src/fastxsketch.cpp:399-410)
+    n = fn(seq, len(seq), k, w, int(canon), L.d2o_xormask_for_seed(seed), out, len(out))
     return out[:n].copy()
 
 

@@ -274,3 +274,25 @@ def test_topk_nlsh1_matches_reference(K):
     ip, ix, dv = O.read_csr(expected(f"topk{K}_nlsh1_sk600.csr"))
     gp, gi, gv = O.topk(z["regs"], z["cards"], K, "similarity", k=32, nlsh=1)
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
+
+
+ROLLING = {
+    "roll_opmh_k40_S128": dict(mode="opmh", S=128, k=40),
+    "roll_opmh_k64_S64_nocanon": dict(mode="opmh", S=64, k=64, canon=False),
+    "roll_opmh_k40_w60_S64": dict(mode="opmh", S=64, k=40, w=60),
+    "roll_opmh_k33_w50_S64_nocanon": dict(mode="opmh", S=64, k=33, w=50, canon=False),
+    "roll_fss_k45_S64_seed3": dict(mode="fss", S=64, k=45, seed=3),
+}
+ROLLING_FILES = ["g0.fa.gz", "g1.fa.gz", "dup.fa.gz", "adv.fa.gz", "reads.fq.gz"]
+
+
+@pytest.mark.parametrize("case", sorted(ROLLING))
+def test_rolling_hash_kmers_match_reference(case):
+    """k > 32: the oracle's RollingHasher / CyclicHash stream (bonsai encoder.h:644-865) against sketches of the reference binary.
+    Oracle only -- libd2gpu rejects k > 32; this pins the restatement the GPU path will be built against."""
+    z = np.load(expected(case + ".npz"))
+    for i, f in enumerate(ROLLING_FILES):
+        o = O.sketch_file(os.path.join(GOLD, "inputs", f), **ROLLING[case])
+        assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)), (case, f)
+        if ROLLING[case]["mode"] == "opmh":
+            assert o["card"] == z["cards"][i], (case, f)
