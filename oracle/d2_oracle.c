@@ -1026,4 +1026,57 @@ uint64_t d2o_topk(const double *regs, const double *cards, uint64_t n, uint64_t 
     free(L); free(ids); free(cnt); free(ix.tab);
     return nnz;
 }
+/* --similarity-threshold x (NN_GRAPH_THRESHOLD), sequential (-p1) semantics: build_index with topk = -1 (src/index_build.cpp:56,26-31: every
+ * candidate of every query is appended to both endpoints' lists unless already there; candidate scan up to n-1 distinct ids, :59), lists
+ * sorted by (-hit count, id) (:139-141), then refine_results' threshold branch (src/refine.cpp:43-68): walk the list in that order, keep
+ * entries whose measure passes the threshold, stop after 20 consecutive failures, sort by (-similarity, id).  Distances pass with v < x. */
+uint64_t d2o_nn_threshold(const double *regs, const double *cards, uint64_t n, uint64_t S, double min_sim, int measure, int k, int cmp_kind,
+                          uint64_t *indptr, uint32_t **idx, float **val) {
+    lshidx_t ix = lsh_build(regs, n, S);
+    const uint64_t ntoquery = n - 1;
+    nlist_t *L = (nlist_t *)calloc(n, sizeof(nlist_t));
+    uint32_t *ids = (uint32_t *)malloc(4 * (ntoquery + 1)), *cnt = (uint32_t *)malloc(4 * (ntoquery + 1));
+    unsigned char *seen = (unsigned char *)calloc(n, 1);     /* per-list dedup sets, kept as one n x n bit table would be too big: rebuilt per query */
+    for (uint64_t q = 0; q < n; ++q) {
+        const uint64_t nc = ntoquery ? lsh_query(&ix, regs + q * S, ntoquery, ids, cnt) : 0;
+        for (uint64_t j = 0; j < nc; ++j) {
+            const uint32_t oid = ids[j];
+            if (oid == q) continue;
+            const float cd = -(float)cnt[j];
+            if (!nl_inset(&L[oid], (uint32_t)q)) { nl_setadd(&L[oid], (uint32_t)q); nl_push(&L[oid], (nb_t){cd, (uint32_t)q}); }
+            if (!nl_inset(&L[q], oid)) { nl_setadd(&L[q], oid); nl_push(&L[q], (nb_t){cd, oid}); }
+        }
+    }
+    free(seen);
+    const int is_dist = !(measure == D2O_UNION_SIZE || measure == D2O_INTERSECTION || measure == D2O_SIMILARITY || measure == D2O_CONTAINMENT);
+    const float mult = is_dist ? 1.f : -1.f, MDIST = 3.402823466e+38f, ms = (float)min_sim;   /* LSHDistType = float; min_similarity_ is a double compared against float values */
+    uint64_t nnz = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        nlist_t *l = &L[i];                                   /* nl_push keeps the list sorted by (d, id) = (-count, id) */
+        uint32_t failures = 0, lsz = l->n;
+        for (uint32_t j = 0; j < lsz; ++j) {
+            const float v = d2o_compare(regs + i * S, regs + (uint64_t)l->v[j].id * S, S, cards[i], cards[l->v[j].id], measure, k, cmp_kind);
+            const int pass = is_dist ? (double)v < min_sim : (double)v >= min_sim;
+            if (!pass) { l->v[j].d = MDIST; if (++failures == 20) { l->n = j; break; } }
+            else { l->v[j].d = v * mult; failures = 0; }
+        }
+        uint32_t o = 0;
+        for (uint32_t j = 0; j < l->n; ++j) {
+            const nb_t x = l->v[j];
+            const int drop = x.d == MDIST || (is_dist ? (double)x.d > min_sim : (double)(-x.d) < min_sim);
+            if (!drop) l->v[o++] = x;
+        }
+        l->n = o;
+        qsort(l->v, l->n, sizeof(nb_t), cmp_nb);
+        if (!is_dist) for (uint32_t j = 0; j < l->n; ++j) l->v[j].d = -l->v[j].d;
+        indptr[i] = nnz; nnz += l->n;
+    }
+    (void)ms;
+    indptr[n] = nnz;
+    *idx = (uint32_t *)malloc(4 * (nnz + 1)); *val = (float *)malloc(4 * (nnz + 1));
+    for (uint64_t i = 0, o = 0; i < n; ++i) for (uint32_t j = 0; j < L[i].n; ++j, ++o) { (*idx)[o] = L[i].v[j].id; (*val)[o] = L[i].v[j].d; }
+    for (uint64_t i = 0; i < n; ++i) { free(L[i].v); free(L[i].set); }
+    free(L); free(ids); free(cnt); free(ix.tab);
+    return nnz;
+}
 void d2o_free(void *p) { free(p); }

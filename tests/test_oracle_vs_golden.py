@@ -296,3 +296,13 @@ def test_rolling_hash_kmers_match_reference(case):
         assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)), (case, f)
         if ROLLING[case]["mode"] == "opmh":
             assert o["card"] == z["cards"][i], (case, f)
+
+
+@pytest.mark.parametrize("tag,thr,measure", [("t0.5", 0.5, "similarity"), ("t0.8", 0.8, "similarity"), ("t0.3_containment", 0.3, "containment")])
+def test_similarity_threshold_graph_matches_reference(tag, thr, measure):
+    """--similarity-threshold x: candidate lists without a cap, ordered by hit count, refined with the 20-consecutive-failures rule
+    (src/index_build.cpp:53-165 with topk = -1, src/refine.cpp:43-68).  Oracle only -- the GPU path for threshold graphs is not built."""
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    ip, ix, dv = O.read_csr(expected(f"nnthr_{tag}_sk600.csr"))
+    gp, gi, gv = O.nn_threshold(z["regs"], z["cards"], thr, measure, k=32)
+    assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
