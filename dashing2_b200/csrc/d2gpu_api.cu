@@ -1439,10 +1439,12 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     if (S < 2) return fail(D2G_EINVAL, "sketchsize must be >= 2 for the default two LSH table types");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    if (p->nlsh != 0 && p->nlsh != 1 && p->nlsh != 2)
-        return fail(D2G_EUNSUPPORTED, "--nLSH %d: only 1 and 2 (the default) are implemented; larger values add XXH64-keyed tables (src/ssi.h:379-392)", p->nlsh);
+    if (p->nlsh < 0 || p->nlsh > 3)
+        return fail(D2G_EUNSUPPORTED, "--nLSH %d: 1, 2 (the default) and 3 are implemented; 4 and up add six-register tables keyed by XXH3 (src/ssi.h:345-352)", p->nlsh);
+    if (p->nlsh == 3 && S < 4) return fail(D2G_EINVAL, "--nLSH 3 needs at least four registers");
     const uint32_t n1 = p->nlsh == 1 ? 0 : S / 2;                      // two-register tables
-    const uint32_t ntab = S + n1;                                      // cmp_core.cpp:757-770
+    const uint32_t n2 = p->nlsh == 3 ? (uint32_t)((uint64_t)S * 8 / 4) : 0;   // four-register tables: 8S / 4 (cmp_core.cpp:767)
+    const uint32_t ntab = S + n1 + n2;                                 // cmp_core.cpp:757-770
     uint64_t ntoquery = (uint64_t)((float)topk * 3.5f);                // index_build.cpp:57-60
     ntoquery = std::min<uint64_t>(ntoquery, n - 1);
     CU(cudaFuncSetAttribute(d2g::lsh_trim_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d2g::LSH_TRIM_BIG_CAP * 8));
@@ -1488,7 +1490,7 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
         CU(cudaMemcpyAsync(offs, ho.data(), (nt + 1) * 8, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
         const uint64_t items = (uint64_t)nt * n;
-        d2g::lsh_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(regs_d, n, S, t0, nt, kA + (uint64_t)t0 * n, iA + (uint64_t)t0 * n);
+        d2g::lsh_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(regs_d, n, S, t0, nt, kA + (uint64_t)t0 * n, iA + (uint64_t)t0 * n, n1);
         size_t need = 0;
         cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, kA, kB, iA, iB, (int)items, (int)nt, offs, offs + 1, 0, 32, st);
         if (need > tb) { tb = need; if (int rc = c->wtmp.reserve(tb + 256)) return rc; }
@@ -1502,7 +1504,7 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
         const int wpb = 4;
         const size_t smem = (size_t)wpb * 2 * maxcand * 4;
         KernelTimer kt(c, D2G_T_CMP);
-        d2g::lsh_query_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(regs_d, n, S, kB, iB, maxcand, cand, cnt, ncand, n1);
+        d2g::lsh_query_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(regs_d, n, S, kB, iB, maxcand, cand, cnt, ncand, n1, n2);
         c->launches++;
     }
     // 4. arrivals, stable sort by destination list, segment starts, replay

@@ -18,25 +18,56 @@
 
 namespace d2g {
 
-__device__ __forceinline__ uint32_t lsh_key(const double *sig, uint32_t type, uint64_t j) {   // ssi.h:320-331
+// XXH64 (the published algorithm; the reference vendors xxHash) of four 64-bit words
+__device__ __forceinline__ uint64_t xxh_round(uint64_t acc, uint64_t in) { acc += in * 0xC2B2AE3D27D4EB4FULL; acc = (acc << 31) | (acc >> 33); return acc * 0x9E3779B185EBCA87ULL; }
+__device__ __forceinline__ uint64_t xxh_merge(uint64_t h, uint64_t v) { h ^= xxh_round(0, v); return h * 0x9E3779B185EBCA87ULL + 0x85EBCA77C2B2AE63ULL; }
+__device__ __forceinline__ uint64_t xxh64_4words(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, uint64_t seed) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL;
+    const uint64_t v1 = xxh_round(seed + P1 + P2, w0), v2 = xxh_round(seed + P2, w1), v3 = xxh_round(seed, w2), v4 = xxh_round(seed - P1, w3);
+    uint64_t h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
+    h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    h += 32;
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+// key of table (type, j), hash_index ssi.h:355-392: type 0 one register (hashmem64), type 1 two (hashmem128), type 2 four: hashmem256
+// while 4(j+1) <= S, else XXH64 seeded with (type << 32) | j over four registers picked by wyhash64(seed) -- 32 bits of it -- mod S
+__device__ __forceinline__ uint32_t lsh_key(const double *sig, uint32_t S, uint32_t type, uint64_t j) {
     if (type == 0) return (uint32_t)wang64((uint64_t)__double_as_longlong(sig[j]));
-    const uint64_t v0 = wang64((uint64_t)__double_as_longlong(sig[2 * j]));
-    const uint64_t v1 = wang64((uint64_t)__double_as_longlong(sig[2 * j + 1]) ^ v0);
-    return (uint32_t)(v0 ^ v1);
+    if (type == 1) {
+        const uint64_t v0 = wang64((uint64_t)__double_as_longlong(sig[2 * j]));
+        const uint64_t v1 = wang64((uint64_t)__double_as_longlong(sig[2 * j + 1]) ^ v0);
+        return (uint32_t)(v0 ^ v1);
+    }
+    uint64_t v[4];
+    if ((j + 1) * 4 <= S) {
+        #pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = (uint64_t)__double_as_longlong(sig[4 * j + r]);
+        return (uint32_t)wang64(cehash(v[0]) ^ (cehash(v[1]) * cehash(v[2]) - v[3]));
+    }
+    uint64_t seed = ((uint64_t)type << 32) | j;
+    const uint64_t seed0 = seed;
+    #pragma unroll
+    for (int r = 0; r < 4; ++r) { const uint32_t pick = (uint32_t)wyhash64(seed) % S; v[r] = (uint64_t)__double_as_longlong(sig[pick]); }
+    return (uint32_t)xxh64_4words(v[0], v[1], v[2], v[3], seed0);
+}
+// table geometry: global table index t in [0, S) is type 0, [S, S + n1) type 1 (n1 = S/2 or 0), [S + n1, S + n1 + n2) type 2 (n2 = 2S or 0)
+__device__ __forceinline__ uint32_t lsh_key_of_table(const double *sig, uint32_t S, uint32_t n1, uint32_t t) {
+    return t < S ? lsh_key(sig, S, 0, t) : t < S + n1 ? lsh_key(sig, S, 1, t - S) : lsh_key(sig, S, 2, t - S - n1);
 }
 
 // keys[t][i], ids[t][i] = i ; table t < S: type 0 register t ; t >= S: type 1 registers 2(t-S), 2(t-S)+1
-__global__ void lsh_keys_kernel(const double *regs, uint64_t n, uint32_t S, uint32_t t0, uint32_t nt, uint32_t *keys, uint32_t *ids) {
+__global__ void lsh_keys_kernel(const double *regs, uint64_t n, uint32_t S, uint32_t t0, uint32_t nt, uint32_t *keys, uint32_t *ids, uint32_t n1) {
     const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (e >= (uint64_t)nt * n) return;
     const uint32_t t = t0 + (uint32_t)(e / n); const uint64_t i = e % n;
-    keys[e] = t < S ? lsh_key(regs + i * S, 0, t) : lsh_key(regs + i * S, 1, t - S);
+    keys[e] = lsh_key_of_table(regs + i * S, S, n1, t);
     ids[e] = (uint32_t)i;
 }
 
 // One warp per query.  skeys/sids: [ntab][n] sorted per table.  Outputs cand[q][maxcand], cnt[q][maxcand], ncand[q].
 __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, const uint32_t *skeys, const uint32_t *sids,
-                                 uint32_t maxcand, uint32_t *cand, uint32_t *cnt, uint32_t *ncand, uint32_t n1) {
+                                 uint32_t maxcand, uint32_t *cand, uint32_t *cnt, uint32_t *ncand, uint32_t n1, uint32_t n2) {
     extern __shared__ uint32_t sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const uint64_t q = (uint64_t)blockIdx.x * wpb + wib;
@@ -44,14 +75,14 @@ __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, con
     uint32_t *set_id = sm + (size_t)wib * 2 * maxcand, *set_ct = set_id + maxcand;
     const double *sig = regs + q * S;
     uint32_t nset = 0;
-    const uint32_t ntab = S + n1;    // n1 = number of two-register tables: S / 2 (--nLSH 2, the default) or 0 (--nLSH 1)
-    // scan order: type 1 tables j = 0..n1-1 (global index S + j), then type 0 tables j = 0..S-1 (ssi.h:425)
+    const uint32_t ntab = S + n1 + n2;    // n1 two-register tables (S / 2, or 0 under --nLSH 1), n2 four-register tables (2S under --nLSH 3)
+    // scan order, most specific first (ssi.h:425): type 2 tables j = 0..n2-1, type 1 tables j = 0..n1-1, then type 0 tables j = 0..S-1
     for (uint32_t base = 0; base < ntab && nset < maxcand; base += 32) {
         const uint32_t o = base + lane;                  // position in scan order
         uint32_t lo = 0, hi = 0;
         if (o < ntab) {
-            const uint32_t t = o < n1 ? S + o : o - n1;
-            const uint32_t key = t < S ? lsh_key(sig, 0, t) : lsh_key(sig, 1, t - S);
+            const uint32_t t = o < n2 ? S + n1 + o : o < n2 + n1 ? S + (o - n2) : o - n2 - n1;
+            const uint32_t key = lsh_key_of_table(sig, S, n1, t);
             const uint32_t *K = skeys + (uint64_t)t * n;
             uint32_t a = 0, b = (uint32_t)n;
             while (a < b) { const uint32_t mid = (a + b) >> 1; if (K[mid] < key) a = mid + 1; else b = mid; }
@@ -63,7 +94,7 @@ __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, con
             const uint32_t blo = __shfl_sync(0xffffffffu, lo, l), bhi = __shfl_sync(0xffffffffu, hi, l);
             const uint32_t oo = base + l;
             if (oo >= ntab) break;
-            const uint32_t t = oo < n1 ? S + oo : oo - n1;
+            const uint32_t t = oo < n2 ? S + n1 + oo : oo < n2 + n1 ? S + (oo - n2) : oo - n2 - n1;
             const uint32_t *I = sids + (uint64_t)t * n;
             for (uint32_t p = blo; p < bhi && nset < maxcand; p += 32) {
                 const bool have = p + lane < bhi;

@@ -140,7 +140,7 @@ typedef struct {
     uint64_t nq;           /* PANEL: number of query (column) sketches */
     double regbytes;       /* D2G_CMP_BBIT / D2G_CMP_SS_COMPRESSED: --fastcmp register size in bytes (1, 2 or 4); else ignored */
     long double compressed_b; /* D2G_CMP_SS_COMPRESSED: base b of the quantisation (from d2g_make_compressed); else ignored */
-    int32_t nlsh;          /* d2g_lsh_topk*: --nLSH, number of table types of the index (src/cmp_core.cpp:757-770); 0 = the reference default 2 */
+    int32_t nlsh;          /* d2g_lsh_topk*: --nLSH, number of table types of the index (src/cmp_core.cpp:757-770); 0 = the reference default 2; 1..3 implemented */
 } d2g_cmp_params;
 
 /* In-place densification of OPMH signatures (empty == 0.0), src/cmp_core.cpp:577-613. */

@@ -918,16 +918,50 @@ static int cmp_kid(const void *a, const void *b) {
     return x->id < y->id ? -1 : (x->id > y->id);
 }
 typedef struct { kid_t *tab; uint64_t n, S, ntab; int nlsh; } lshidx_t; /* table t occupies tab[t*n, (t+1)*n), sorted by (key,id) */
-/* --nLSH: table types 0 .. nlsh-1 with 1, 2, ... registers per key (src/cmp_core.cpp:757-770); 1 and 2 (the default) are restated */
+/* --nLSH: table types 0 .. nlsh-1 with 1, 2, 4 registers per key and S, S/2, 8S/4 tables (src/cmp_core.cpp:757-770); 1 to 3 are
+ * restated (type 3 keys of 6 registers go through XXH3, not restated) */
 static int g_nlsh = 2;
-void d2o_set_nlsh(int nlsh) { g_nlsh = nlsh == 1 ? 1 : 2; }
+void d2o_set_nlsh(int nlsh) { g_nlsh = nlsh < 1 ? 2 : nlsh > 3 ? 3 : nlsh; }
+/* XXH64 (the published algorithm; the reference vendors xxHash) over len bytes, len a multiple of 8 */
+static inline uint64_t xxh_round(uint64_t acc, uint64_t in) { acc += in * 0xC2B2AE3D27D4EB4FULL; acc = (acc << 31) | (acc >> 33); return acc * 0x9E3779B185EBCA87ULL; }
+static inline uint64_t xxh_merge(uint64_t h, uint64_t v) { h ^= xxh_round(0, v); return h * 0x9E3779B185EBCA87ULL + 0x85EBCA77C2B2AE63ULL; }
+static uint64_t xxh64_words(const uint64_t *w, uint64_t nwords, uint64_t seed) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
+    uint64_t h, i = 0;
+    if (nwords >= 4) {
+        uint64_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        for (; i + 4 <= nwords; i += 4) { v1 = xxh_round(v1, w[i]); v2 = xxh_round(v2, w[i + 1]); v3 = xxh_round(v3, w[i + 2]); v4 = xxh_round(v4, w[i + 3]); }
+        h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
+        h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    } else h = seed + P5;
+    h += nwords * 8;
+    for (; i < nwords; ++i) { h ^= xxh_round(0, w[i]); h = ((h << 27) | (h >> 37)) * P1 + P4; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+/* key of table (type, j): hash_index, ssi.h:355-392.  type 2 = four registers: hashmem256 (:313-318) while 4(j+1) <= S, else XXH64
+ * seeded with ((type << 32) ^ (type >> 32)) | j over four registers picked by wyhash64(seed) -- truncated to 32 bits -- mod S. */
+static uint32_t lsh_key_any(const double *sig, uint64_t S, uint32_t type, uint64_t j) {
+    if (type < 2) return d2o_lsh_key(sig, type, j);
+    uint64_t v[4];
+    if ((j + 1) * 4 <= S) {
+        memcpy(v, sig + 4 * j, 32);
+        return (uint32_t)d2o_wang64(d2o_cehash(v[0]) ^ (d2o_cehash(v[1]) * d2o_cehash(v[2]) - v[3]));
+    }
+    uint64_t seed = (((uint64_t)type << 32) ^ ((uint64_t)type >> 32)) | j;
+    const uint64_t seed0 = seed;
+    for (int r = 0; r < 4; ++r) { const uint32_t pick = (uint32_t)d2o_wyhash64(&seed) % (uint32_t)S; memcpy(&v[r], sig + pick, 8); }
+    return (uint32_t)xxh64_words(v, 4, seed0);
+}
+static uint64_t lsh_nsubs(uint64_t S, int type) { return type == 0 ? S : type == 1 ? S / 2 : S * 8 / 4; }
+static uint64_t lsh_tab0(uint64_t S, int type) { uint64_t t = 0; for (int q = 0; q < type; ++q) t += lsh_nsubs(S, q); return t; }
 static lshidx_t lsh_build(const double *regs, uint64_t n, uint64_t S) {
-    lshidx_t ix; ix.n = n; ix.S = S; ix.nlsh = g_nlsh; ix.ntab = S + (ix.nlsh > 1 ? S / 2 : 0);
+    lshidx_t ix; ix.n = n; ix.S = S; ix.nlsh = g_nlsh; ix.ntab = lsh_tab0(S, ix.nlsh);
     ix.tab = (kid_t *)malloc(sizeof(kid_t) * ix.ntab * n);
     for (uint64_t t = 0; t < ix.ntab; ++t) {
-        const uint32_t type = t < S ? 0 : 1; const uint64_t j = t < S ? t : t - S;
+        const uint32_t type = t < S ? 0 : t < S + S / 2 ? 1 : 2; const uint64_t j = t - lsh_tab0(S, (int)type);
         kid_t *T = ix.tab + t * n;
-        for (uint64_t i = 0; i < n; ++i) { T[i].key = d2o_lsh_key(regs + i * S, type, j); T[i].id = (uint32_t)i; }
+        for (uint64_t i = 0; i < n; ++i) { T[i].key = lsh_key_any(regs + i * S, S, type, j); T[i].id = (uint32_t)i; }
         qsort(T, n, sizeof(kid_t), cmp_kid); /* bucket order = insertion order = ascending id under -p1 */
     }
     return ix;
@@ -936,10 +970,10 @@ static uint64_t lsh_query(const lshidx_t *ix, const double *sig, uint64_t maxcan
     uint64_t nc = 0;
     const uint64_t n = ix->n, S = ix->S;
     for (int type = ix->nlsh - 1; type >= 0 && nc < maxcand; --type) { /* most specific table type first, ssi.h:425 */
-        const uint64_t nsubs = type ? S / 2 : S;
+        const uint64_t nsubs = lsh_nsubs(S, type);
         for (uint64_t j = 0; j < nsubs; ++j) {
-            const uint32_t key = d2o_lsh_key(sig, (uint32_t)type, j);
-            const kid_t *T = ix->tab + (type ? S + j : j) * n;
+            const uint32_t key = lsh_key_any(sig, S, (uint32_t)type, j);
+            const kid_t *T = ix->tab + (lsh_tab0(S, type) + j) * n;
             uint64_t lo = 0, hi = n;
             while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (T[mid].key < key) lo = mid + 1; else hi = mid; }
             for (uint64_t q = lo; q < n && T[q].key == key; ++q) {

@@ -273,8 +273,9 @@ def test_cmp_topk_csr_file(tmp_path):
         out = str(tmp_path / f"top{K}.csr")
         run(["cmp", "--presketched", "--binary-output", "--topk", str(K), "--cmpout", out, stk])
         assert open(out, "rb").read() == open(expected(f"topk{K}_sk600.csr"), "rb").read()
-        run(["cmp", "--presketched", "--binary-output", "--nLSH", "1", "--topk", str(K), "--cmpout", out, stk])
-        assert open(out, "rb").read() == open(expected(f"topk{K}_nlsh1_sk600.csr"), "rb").read()
+        for nlsh in ("1", "3"):
+            run(["cmp", "--presketched", "--binary-output", "--nLSH", nlsh, "--topk", str(K), "--cmpout", out, stk])
+            assert open(out, "rb").read() == open(expected(f"topk{K}_nlsh{nlsh}_sk600.csr"), "rb").read()
 
 
 def test_unsupported_options_fail_loudly(golden_inputs):

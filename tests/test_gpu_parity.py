@@ -654,12 +654,14 @@ def test_topk_matches_reference_golden(K):
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
 
 
+@pytest.mark.parametrize("nlsh", [1, 3])
 @pytest.mark.parametrize("K", [5, 32])
-def test_topk_nlsh1_matches_reference_golden(K):
-    """--nLSH 1: the index holds only the S one-register tables (src/cmp_core.cpp:757-770)."""
+def test_topk_nlsh1_matches_reference_golden(K, nlsh):
+    """--nLSH 1: the index holds only the S one-register tables; --nLSH 3: 2S four-register tables on top (hashmem256 / XXH64 keys),
+    scanned first (src/cmp_core.cpp:757-770, src/ssi.h:355-392)."""
     z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
-    ip, ix, dv = O.read_csr(expected(f"topk{K}_nlsh1_sk600.csr"))
-    gp, gi, gv = ctx().lsh_topk(z["regs"], z["cards"], K, "similarity", k=32, nlsh=1)
+    ip, ix, dv = O.read_csr(expected(f"topk{K}_nlsh{nlsh}_sk600.csr"))
+    gp, gi, gv = ctx().lsh_topk(z["regs"], z["cards"], K, "similarity", k=32, nlsh=nlsh)
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
 
 
@@ -667,11 +669,12 @@ def test_topk_nlsh1_matches_oracle_seeded_and_nlsh3_fails():
     from dashing2_b200 import synth
     from dashing2_b200.capi import D2GError
     regs, cards = synth.synthetic_sketches(2500, 128, seed=77, n_families=40)
-    ip, ix, dv = O.topk(regs, cards, 10, "similarity", k=31, nlsh=1)
-    gp, gi, gv = ctx().lsh_topk(regs, cards, 10, "similarity", k=31, nlsh=1)
-    assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
+    for nlsh in (1, 3):
+        ip, ix, dv = O.topk(regs, cards, 10, "similarity", k=31, nlsh=nlsh)
+        gp, gi, gv = ctx().lsh_topk(regs, cards, 10, "similarity", k=31, nlsh=nlsh)
+        assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32)), nlsh
     with pytest.raises(D2GError):
-        ctx().lsh_topk(regs[:100], cards[:100], 5, nlsh=3)
+        ctx().lsh_topk(regs[:100], cards[:100], 5, nlsh=4)
 
 
 def test_topk_row_ranges_concatenate_to_the_graph():

@@ -267,12 +267,14 @@ def test_fss_save_kmers_ids_match_reference(case):
         assert np.array_equal(o["ids"], z["ids"][i]), (case, f)
 
 
+@pytest.mark.parametrize("nlsh", [1, 3])
 @pytest.mark.parametrize("K", [5, 32])
-def test_topk_nlsh1_matches_reference(K):
-    """--nLSH 1: only the S one-register tables are built and scanned (src/cmp_core.cpp:757-770)."""
+def test_topk_nlsh1_matches_reference(K, nlsh):
+    """--nLSH 1: only the S one-register tables are built and scanned; --nLSH 3: 2S four-register tables on top, scanned first, three
+    quarters of them keyed by XXH64 over wyhash-picked registers (src/cmp_core.cpp:757-770, src/ssi.h:355-392).  The GPU path has 1 and 2."""
     z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
-    ip, ix, dv = O.read_csr(expected(f"topk{K}_nlsh1_sk600.csr"))
-    gp, gi, gv = O.topk(z["regs"], z["cards"], K, "similarity", k=32, nlsh=1)
+    ip, ix, dv = O.read_csr(expected(f"topk{K}_nlsh{nlsh}_sk600.csr"))
+    gp, gi, gv = O.topk(z["regs"], z["cards"], K, "similarity", k=32, nlsh=nlsh)
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
 
 
