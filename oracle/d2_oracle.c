@@ -216,6 +216,64 @@ uint64_t d2o_hash_stream(const char *seq, uint64_t len, int k, int w, int canon,
 #undef EMIT
 
 /* ------------------------------------------------------------------------------------------ */
+/* Protein alphabets (--protein/--protein20, --protein14, --protein6, --protein8; src/options.h:328-331, canon = false).
+ * Tables: bonsai alphabet.h:107-120 built by make_lut (:30-58): comma-separated groups get codes 0, 1, ..., both cases; the "OU:KC"
+ * alias is a no-op because it indexes the table by CODE, not by character (same as "U:T" for DNA), so O and U stay invalid.
+ * Rolling encode (encoder.h:241-306): min = (min * mul) | code -- an OR even when mul is not a power of two -- then
+ * min %= mul^k (PROTEIN20 / 14 / 6, rhtraits.h:59-62) or min &= (1 << k) - 1 (the 3-bit alphabet: k bits, not 3k; rhtraits.h:57-58).
+ * The reduced value is carried on as the rolling state. */
+/* ------------------------------------------------------------------------------------------ */
+static void alpha_lut(const char *groups, int8_t lut[256]) {
+    memset(lut, -1, 256);
+    int id = 0;
+    for (const char *p = groups; *p; ++p) {
+        if (*p == ',') { ++id; continue; }
+        lut[(unsigned char)(*p | 32)] = (int8_t)id; lut[(unsigned char)(*p & 0xdf)] = (int8_t)id;
+    }
+}
+/* alphabet: 20 = AMINO20, 14 = SE-B(14), 6 = SE-B(6), 8 = SE-B(8) with the 3-bit encoding */
+uint64_t d2o_hash_stream_protein(const char *seq, uint64_t len, int k, int w, int alphabet, uint64_t xormask, uint64_t *out, uint64_t cap) {
+#define EMIT(v) do { if (nout < cap) out[nout] = d2o_wang64((v) ^ xormask); ++nout; } while (0)
+    uint64_t nout = 0;
+    int8_t lut[256];
+    alpha_lut(alphabet == 20 ? "A,C,D,E,F,G,H,I,K,L,M,N,P,Q,R,S,T,V,W,Y" : alphabet == 14 ? "A,C,D,EQ,FY,G,H,IV,KR,LM,N,P,ST,W"
+              : alphabet == 6 ? "AST,CP,DHNEKQR,FWY,G,ILMV" : "AST,C,DHN,EKQR,FWY,G,ILMV,P", lut);
+    const uint64_t mul = (uint64_t)alphabet;
+    uint64_t mask;
+    if (alphabet == 8) mask = ~0ULL >> (64 - k);
+    else mask = (uint64_t)pow((double)alphabet, (double)k);            /* rhtraits.h:59-61: std::pow narrowed to the k-mer type */
+    const int windowed = w > k;
+    window_t win; win_init(&win, windowed ? (uint32_t)(w - k + 1) : 1);
+    uint64_t kmer = 0, pos = 0; int filled = 0;
+    while (pos < len) {
+        int restart = 0;
+        while (filled < k && pos < len) {
+            const int8_t nv = lut[(unsigned char)seq[pos++]];
+            if (!windowed) {
+                if (nv == -1) { restart = 1; break; }
+                kmer = (kmer * mul) | (uint64_t)nv;
+            } else {
+                kmer *= mul;
+                kmer |= (uint64_t)(int64_t)nv;                         /* -1 sign-extends to all ones, encoder.h:285 */
+                if (kmer == ~0ULL) { restart = 1; break; }
+            }
+            ++filled;
+        }
+        if (restart) { kmer = 0; filled = 0; continue; }
+        if (filled == k) {
+            if (alphabet == 8) kmer &= mask; else kmer %= mask;
+            if (!windowed) EMIT(kmer);
+            else { uint64_t m; if (win_push(&win, kmer, d2o_frev64(kmer), &m) && m != ~0ULL) EMIT(m); }
+            --filled;
+        }
+    }
+    if (windowed && win.n > 0 && win.n < win.wsz) EMIT(win_min(&win).el);
+    free(win.ring);
+    return nout;
+#undef EMIT
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* k > 32: RollingHasher<uint64_t> over CyclicHash (bonsai encoder.h:644-865, rollinghash/cyclichash.h,
  * rollinghash/characterhash.h).  Word size 64, so every rotation is a plain 64-bit rotate.  Character tables:
  * 256 draws of WyRand<uint64_t> seeded with (seed1 ^ seed2) for the forward hasher and (seed2 * seed1) ^ (seed2 ^ seed1)

@@ -39,6 +39,9 @@ uint64_t d2o_kmer_positions(uint64_t len, int k);
 uint64_t d2o_hash_stream(const char *seq, uint64_t len, int k, int w, int canon, uint64_t xormask,
                          uint64_t *out, uint64_t cap);
 
+/* Same for the protein alphabets (alphabet = 20, 14, 6, or 8 for the 3-bit encoding; never canonical): alphabet.h:107-120,
+ * rhtraits.h:52-62, encoder.h:241-306. */
+uint64_t d2o_hash_stream_protein(const char *seq, uint64_t len, int k, int w, int alphabet, uint64_t xormask, uint64_t *out, uint64_t cap);
 /* Same for k > 32: RollingHasher<uint64_t> over CyclicHash (bonsai encoder.h:644-865, rollinghash/cyclichash.h). */
 uint64_t d2o_hash_stream_rolling(const char *seq, uint64_t len, int k, int w, int canon, uint64_t xormask,
                                  uint64_t *out, uint64_t cap);

@@ -45,6 +45,8 @@ def lib():
     L.d2o_hash_stream.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, C.c_uint64]
     L.d2o_hash_stream_rolling.restype = C.c_uint64
     L.d2o_hash_stream_rolling.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, C.c_uint64]
+    L.d2o_hash_stream_protein.restype = C.c_uint64
+    L.d2o_hash_stream_protein.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, C.c_uint64]
     L.d2o_opmh_m.restype = C.c_uint32; L.d2o_opmh_m.argtypes = [C.c_uint32]
     L.d2o_opmh_reset.argtypes = [u64p, f64p, C.c_uint32]
     L.d2o_opmh_update.argtypes = [u64p, f64p, C.c_uint32, u64p, C.c_uint64]
@@ -118,21 +120,24 @@ def read_fastx(path: str):
     return recs
 
 
-def hash_stream(seq: bytes, k: int, w: int = -1, canon: bool = True, seed: int = 0) -> np.ndarray:
+def hash_stream(seq: bytes, k: int, w: int = -1, canon: bool = True, seed: int = 0, alphabet: int = 4) -> np.ndarray:
     L = lib()
     out = np.empty(2 * len(seq) + 4, dtype=np.uint64)
+    if alphabet != 4:                                                       # protein alphabets: never canonical (src/options.h:328-331)
+        n = L.d2o_hash_stream_protein(seq, len(seq), k, w, alphabet, L.d2o_xormask_for_seed(seed), out, len(out))
+        return out[:n].copy()
     fn = L.d2o_hash_stream_rolling if k > 32 else L.d2o_hash_stream      # k > 32: RollingHasher (src/fastxsketch.cpp:399-410)
     n = fn(seq, len(seq), k, w, int(canon), L.d2o_xormask_for_seed(seed), out, len(out))
     return out[:n].copy()
 
 
 def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool = True, seed: int = 0,
-                count_threshold: float = 0.0, cssize: int = 0):
+                count_threshold: float = 0.0, cssize: int = 0, alphabet: int = 4):
     """Oracle equivalent of one iteration of the per-file loop (src/fastxsketch.cpp:303-624).
 
     Returns dict(card=..., sig=f64[S], regs_u64=..., ids=...)."""
     L = lib()
-    streams = [hash_stream(r, k, w, canon, seed) for r in read_fastx(path)]
+    streams = [hash_stream(r, k, w, canon, seed, alphabet) for r in read_fastx(path)]
     hv = np.concatenate(streams) if streams else np.empty(0, dtype=np.uint64)
     if mode == "opmh":
         m = L.d2o_opmh_m(S)
@@ -159,7 +164,7 @@ def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool =
     raise ValueError(mode)
 
 
-def sketch_records_byseq(records, mode: str, S: int, k: int, w: int = -1, canon: bool = True, seed: int = 0):
+def sketch_records_byseq(records, mode: str, S: int, k: int, w: int = -1, canon: bool = True, seed: int = 0, alphabet: int = 4):
     """Oracle equivalent of --parse-by-seq (resize_fill, src/fastxsketchbyseq.cpp:284-531): one sketch per record; set sketches
     with an estimate below 10 * S carry the exact distinct count.  Returns (cards f64[n], sigs f64[n][S])."""
     import tempfile
@@ -168,10 +173,10 @@ def sketch_records_byseq(records, mode: str, S: int, k: int, w: int = -1, canon:
     for rec in records:
         with tempfile.NamedTemporaryFile(suffix=".fa") as f:
             f.write(b">r\n" + rec + b"\n"); f.flush()
-            o = sketch_file(f.name, mode, S, k, w, canon, seed)
+            o = sketch_file(f.name, mode, S, k, w, canon, seed, alphabet=alphabet)
         card = o["card"]
         if mode in ("opmh", "fss"):
-            hv = hash_stream(rec, k, w, canon, seed)
+            hv = hash_stream(rec, k, w, canon, seed, alphabet)
             card = L.d2o_byseq_cardinality(card, S, hv, len(hv))
         cards.append(card); sigs.append(o["sig"])
     return np.asarray(cards), np.stack(sigs) if sigs else np.empty((0, S))

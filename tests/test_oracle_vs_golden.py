@@ -308,3 +308,31 @@ def test_similarity_threshold_graph_matches_reference(tag, thr, measure):
     ip, ix, dv = O.read_csr(expected(f"nnthr_{tag}_sk600.csr"))
     gp, gi, gv = O.nn_threshold(z["regs"], z["cards"], thr, measure, k=32)
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
+
+
+PROTEIN = {
+    "prot20_opmh_k7_S64": dict(mode="opmh", S=64, k=7, alphabet=20),
+    "prot20_opmh_k14_S64": dict(mode="opmh", S=64, k=14, alphabet=20),
+    "prot14_opmh_k10_S64": dict(mode="opmh", S=64, k=10, alphabet=14),
+    "prot6_opmh_k20_S64": dict(mode="opmh", S=64, k=20, alphabet=6),
+    "prot8_opmh_k12_S64": dict(mode="opmh", S=64, k=12, alphabet=8),
+    "prot20_opmh_k5_w12_S32": dict(mode="opmh", S=32, k=5, w=12, alphabet=20),
+    "prot20_fss_k7_S64": dict(mode="fss", S=64, k=7, alphabet=20),
+}
+
+
+@pytest.mark.parametrize("case", sorted(PROTEIN))
+def test_protein_alphabets_match_reference(case):
+    """--protein / --protein14 / --protein6 / --protein8 under --parse-by-seq: the oracle's protein k-mer stream (alphabet.h:107-120,
+    rhtraits.h:52-62, encoder.h:241-306: `(min * mul) | code`, `% mul^k` or the k-bit mask of the 3-bit alphabet) against the reference
+    binary.  Oracle only -- the GPU encode for these alphabets is not built.  Per FILE the reference binary sketches nothing for protein
+    input (empty registers, recorded in the fixture), so only the per-record mode is pinned."""
+    z = np.load(expected(case + ".npz"))
+    recs = O.read_fastx(os.path.join(GOLD, "inputs", "prot.fa.gz"))
+    cards, sigs = O.sketch_records_byseq(recs, canon=False, **PROTEIN[case])
+    assert np.array_equal(sigs.view(np.uint64), z["byseq_sigs"].view(np.uint64))
+    if PROTEIN[case]["mode"] == "opmh":
+        assert np.array_equal(cards, z["byseq_cards"])
+    else:
+        np.testing.assert_allclose(cards, z["byseq_cards"], rtol=1e-12)
+    assert (z["sigs"] == 0).all() or (z["sigs"] == np.finfo(np.float64).max).all()        # the per-file quirk: empty sketches
