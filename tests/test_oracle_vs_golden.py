@@ -336,3 +336,12 @@ def test_protein_alphabets_match_reference(case):
     else:
         np.testing.assert_allclose(cards, z["byseq_cards"], rtol=1e-12)
     assert (z["sigs"] == 0).all() or (z["sigs"] == np.finfo(np.float64).max).all()        # the per-file quirk: empty sketches
+
+
+@pytest.mark.parametrize("case,kw", [("kmercounts_opmh_k31_S64", dict(S=64, k=31)), ("kmercounts_opmh_k21_w30_S128", dict(S=128, k=21, w=30))])
+def test_opmh_kmercounts_match_reference(case, kw):
+    """--save-kmercounts: multiplicity of each register's minimum (src/oph.h:206-209), float32 in FILE.kmercounts.f64.  Oracle only."""
+    z = np.load(expected(case + ".npz"))
+    for i, f in enumerate(["dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz"]):
+        o = O.sketch_file(os.path.join(GOLD, "inputs", f), mode="opmh", **kw)
+        assert np.array_equal(o["counts"].astype(np.float32), z["counts"][i]), (case, f)
