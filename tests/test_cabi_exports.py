@@ -57,3 +57,25 @@ def test_host_only_entry_points_work_without_device():
     assert L.d2g_cmp_output_size(ctypes.byref(p)) == 45
     off = np.array([0, 10, 40, 100], dtype=np.uint64)
     assert L.d2g_count_kmers(off.ctypes.data, 3, 31) == 0 + 0 + 30
+
+
+def test_front_end_fails_loudly_without_device(tmp_path):
+    """dashing2-gpu has no CPU path either: without a CUDA device it exits non-zero with the library's message (and writes no output)."""
+    import subprocess
+    exe = os.path.join(ROOT, "dashing2_b200", "bin", "dashing2-gpu")
+    if not os.path.exists(exe):
+        pytest.skip("front-end not built")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    fa = tmp_path / "x.fa"; fa.write_text(">r\n" + "ACGT" * 50 + "\n")
+    out = tmp_path / "x.stk"
+    r = subprocess.run([exe, "sketch", "-k31", "-S64", "-o", str(out), str(fa)], capture_output=True, text=True)
+    assert r.returncode != 0 and ("no CUDA device" in r.stderr or "CPU fallback" in r.stderr), r.stderr
+    assert not out.exists()
+    # option errors are reported before any device work
+    r = subprocess.run([exe, "sketch", "--similarity-threshold", "0.5", str(fa)], capture_output=True, text=True)
+    assert r.returncode != 0 and "not supported" in r.stderr
