@@ -22,6 +22,15 @@ def main():
         counts = np.fromfile(out + ".kmercounts.f64", dtype=np.float32).reshape(len(paths), S)
         np.savez_compressed(os.path.join(EXP, name + ".npz"), counts=counts)
         print(name, counts.sum(1), counts.max())
+    # the other sketch types: the count kept with a register is the multiplicity (Full SetSketch, setsketch.h:405-406) or the weight
+    # (BagMinHash / ProbMinHash) of the k-mer that owns it
+    for name, argv, S in (("kmercounts_fss_k31_S64", ["-k31", "-S64", "--full-setsketch"], 64), ("kmercounts_bmh_k31_S32", ["-k31", "-S32", "--multiset", "--cache"], 32),
+                          ("kmercounts_pmh_k31_S32", ["-k31", "-S32", "--prob", "--cache"], 32)):
+        out = os.path.join(work, name + ".stk"); cdir = os.path.join(work, "c_" + name); os.makedirs(cdir)
+        refbin.run_ref(["sketch", "-p1", "-o", out, "--save-kmers", "--save-kmercounts", "--outprefix", cdir] + argv + paths, threads=1)
+        counts = np.fromfile(out + ".kmercounts.f64", dtype=np.float32).reshape(len(paths), S)
+        np.savez_compressed(os.path.join(EXP, name + ".npz"), counts=counts)
+        print(name, counts.sum(1), counts.max())
     shutil.rmtree(work)
 
 

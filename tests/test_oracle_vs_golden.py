@@ -345,3 +345,19 @@ def test_opmh_kmercounts_match_reference(case, kw):
     for i, f in enumerate(["dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz"]):
         o = O.sketch_file(os.path.join(GOLD, "inputs", f), mode="opmh", **kw)
         assert np.array_equal(o["counts"].astype(np.float32), z["counts"][i]), (case, f)
+
+
+@pytest.mark.parametrize("case,kw", [("kmercounts_fss_k31_S64", dict(mode="fss", S=64, k=31)), ("kmercounts_bmh_k31_S32", dict(mode="bmh", S=32, k=31)),
+                                     ("kmercounts_pmh_k31_S32", dict(mode="pmh", S=32, k=31))])
+def test_owner_kmercounts_match_reference(case, kw):
+    """--save-kmercounts for the other sketches: the count kept with a register is the multiplicity of the k-mer that owns it (its weight
+    for BagMinHash / ProbMinHash), i.e. a function of the ids alone -- which is how a GPU pass would produce it.  Oracle only."""
+    z = np.load(expected(case + ".npz"))
+    for i, f in enumerate(["dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz"]):
+        path = os.path.join(GOLD, "inputs", f)
+        o = O.sketch_file(path, **kw)
+        hv = np.concatenate([O.hash_stream(r, kw["k"]) for r in O.read_fastx(path)])
+        u, c = np.unique(hv, return_counts=True)
+        mult = dict(zip(u.tolist(), c.tolist()))
+        got = np.array([mult[int(x)] for x in o["ids"]], dtype=np.float32)
+        assert np.array_equal(got, z["counts"][i]), (case, f)
