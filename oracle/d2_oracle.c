@@ -1078,6 +1078,17 @@ static void nl_update(nlist_t *l, nb_t item, uint64_t k) { /* index_build.cpp:20
     }
 }
 static int cmp_nb(const void *a, const void *b) { nb_t x = *(const nb_t *)a, y = *(const nb_t *)b; return nb_less(x, y) ? -1 : nb_less(y, x); }
+/* --topk with --fastcmp N: the LSH index is built over the f64 signatures (index_build.cpp:93, sketch_compressed_set is false), while
+ * compare() in refine_results takes the compressed branch (cmp_core.cpp:362-449) over make_compressed's registers.  Set by
+ * d2o_topk_compressed around d2o_topk. */
+static const double *g_cregs = NULL; static int g_c_bbit = 0; static double g_c_fd = 0.; static long double g_c_b = 0.L;
+static float refine_compare(const double *regs, uint64_t S, uint64_t i, uint64_t j, const double *cards, int measure, int k, int cmp_kind) {
+    if (!g_cregs) return d2o_compare(regs + i * S, regs + j * S, S, cards[i], cards[j], measure, k, cmp_kind);
+    uint64_t x = 0, y = 0;
+    if (g_c_bbit) x = d2o_count_eq((const uint64_t *)(g_cregs + i * S), (const uint64_t *)(g_cregs + j * S), S);
+    else d2o_count_gtlt(g_cregs + i * S, g_cregs + j * S, S, &x, &y);
+    return d2o_finalize_compressed(x, y, S, cards[i], cards[j], measure, k, g_c_bbit, g_c_fd, g_c_b);
+}
 
 uint64_t d2o_topk(const double *regs, const double *cards, uint64_t n, uint64_t S, int topk, int measure, int k, int cmp_kind,
                   uint64_t *indptr, uint32_t **idx, float **val) {
@@ -1104,7 +1115,7 @@ uint64_t d2o_topk(const double *regs, const double *cards, uint64_t n, uint64_t 
     for (uint64_t i = 0; i < n; ++i) { /* refine.cpp:20-76, num_neighbors_ > 0 branch */
         nlist_t *l = &L[i];
         for (uint32_t j = 0; j < l->n; ++j)
-            l->v[j].d = mult * d2o_compare(regs + i * S, regs + (uint64_t)l->v[j].id * S, S, cards[i], cards[l->v[j].id], measure, k, cmp_kind);
+            l->v[j].d = mult * refine_compare(regs, S, i, l->v[j].id, cards, measure, k, cmp_kind);
         qsort(l->v, l->n, sizeof(nb_t), cmp_nb);
         if (!is_dist) { uint32_t j = 0; while (j < l->n && l->v[j].d != 0.f) ++j; l->n = j; }
         if ((uint32_t)topk < l->n) { const float bs = l->v[topk - 1].d; uint32_t j = (uint32_t)topk; while (j < l->n && !(l->v[j].d > bs)) ++j; l->n = j; }
@@ -1117,6 +1128,13 @@ uint64_t d2o_topk(const double *regs, const double *cards, uint64_t n, uint64_t 
     for (uint64_t i = 0; i < n; ++i) { free(L[i].v); free(L[i].set); }
     free(L); free(ids); free(cnt); free(ix.tab);
     return nnz;
+}
+uint64_t d2o_topk_compressed(const double *regs, const double *cregs, const double *cards, uint64_t n, uint64_t S, int topk, int measure, int k,
+                             int bbit, double fd, long double b, uint64_t *indptr, uint32_t **idx, float **val) {
+    g_cregs = cregs; g_c_bbit = bbit; g_c_fd = fd; g_c_b = b;
+    const uint64_t r = d2o_topk(regs, cards, n, S, topk, measure, k, 0, indptr, idx, val);
+    g_cregs = NULL;
+    return r;
 }
 /* --similarity-threshold x (NN_GRAPH_THRESHOLD), sequential (-p1) semantics: build_index with topk = -1 (src/index_build.cpp:56,26-31: every
  * candidate of every query is appended to both endpoints' lists unless already there; candidate scan up to n-1 distinct ids, :59), lists

@@ -136,6 +136,10 @@ uint64_t d2o_lsh_query(const double *regs, uint64_t n, uint64_t S, uint64_t quer
 /* whole pipeline -> CSR (indptr[n+1], idx/val malloc'ed; free with d2o_free). Returns nnz. */
 uint64_t d2o_topk(const double *regs, const double *cards, uint64_t n, uint64_t S, int topk, int measure, int k, int cmp_kind,
                   uint64_t *indptr, uint32_t **idx, float **val);
+/* --topk with --fastcmp N [--bbit-sigs]: index over the f64 signatures, refinement through the compressed compare branch over cregs
+ * (from d2o_make_compressed). */
+uint64_t d2o_topk_compressed(const double *regs, const double *cregs, const double *cards, uint64_t n, uint64_t S, int topk, int measure, int k,
+                             int bbit, double fd, long double b, uint64_t *indptr, uint32_t **idx, float **val);
 /* --similarity-threshold x: every id sharing an LSH bucket, refined with the 20-consecutive-failures rule (src/refine.cpp:43-68) -> CSR. */
 uint64_t d2o_nn_threshold(const double *regs, const double *cards, uint64_t n, uint64_t S, double min_sim, int measure, int k, int cmp_kind,
                           uint64_t *indptr, uint32_t **idx, float **val);

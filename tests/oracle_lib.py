@@ -71,6 +71,9 @@ def lib():
         getattr(L, nm).restype = C.c_double
         getattr(L, nm).argtypes = [f64p, C.c_void_p, C.c_uint32, u64p, f64p, C.c_uint64, C.c_double]
     L.d2o_set_nlsh.argtypes = [C.c_int]
+    L.d2o_topk_compressed.restype = C.c_uint64
+    L.d2o_topk_compressed.argtypes = [f64p, f64p, f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_longdouble, u64p,
+                                      C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
     L.d2o_nn_threshold.restype = C.c_uint64
     L.d2o_nn_threshold.argtypes = [f64p, f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, u64p,
                                    C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
@@ -262,6 +265,21 @@ def topk(regs, cards, K, measure="similarity", k=31, cmp_kind=0, nlsh=2):
         nnz = L.d2o_topk(regs, cards, n, S, K, MEASURES[measure], k, cmp_kind, indptr, C.byref(pi), C.byref(pv))
     finally:
         L.d2o_set_nlsh(2)
+    idx = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
+    val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()
+    L.d2o_free(pi); L.d2o_free(pv)
+    return indptr, idx, val
+
+
+def topk_compressed(regs, cregs, cards, K, fd, bbit, b, measure="similarity", k=31):
+    """--topk K with --fastcmp fd [--bbit-sigs]: CSR (indptr, indices, data)."""
+    L = lib()
+    regs = np.ascontiguousarray(regs, dtype=np.float64); cregs = np.ascontiguousarray(cregs, dtype=np.float64)
+    cards = np.ascontiguousarray(cards, dtype=np.float64)
+    n, S = regs.shape
+    indptr = np.zeros(n + 1, dtype=np.uint64)
+    pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()
+    nnz = L.d2o_topk_compressed(regs, cregs, cards, n, S, K, MEASURES[measure], k, 1 if bbit else 0, float(fd), b, indptr, C.byref(pi), C.byref(pv))
     idx = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
     val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()
     L.d2o_free(pi); L.d2o_free(pv)

@@ -361,3 +361,14 @@ def test_owner_kmercounts_match_reference(case, kw):
         mult = dict(zip(u.tolist(), c.tolist()))
         got = np.array([mult[int(x)] for x in o["ids"]], dtype=np.float32)
         assert np.array_equal(got, z["counts"][i]), (case, f)
+
+
+@pytest.mark.parametrize("tag,fd,bbit", [("fd1", 1, False), ("fd2_bbit", 2, True)])
+def test_topk_with_fastcmp_matches_reference(tag, fd, bbit):
+    """--topk 8 --fastcmp N [--bbit-sigs]: LSH index over the f64 signatures, refinement through the compressed compare branch.
+    Oracle only -- libd2gpu rejects the combination."""
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    creg, trunc, a, b = O.make_compressed(z["regs"], fd, bbit)
+    ip, ix, dv = O.read_csr(expected(f"topk8_{tag}_sk600.csr"))
+    gp, gi, gv = O.topk_compressed(z["regs"], creg, z["cards"], 8, fd, bbit, b, "similarity", k=32)
+    assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
