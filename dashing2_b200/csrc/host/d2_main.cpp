@@ -29,6 +29,7 @@
 #include <thread>
 #include <vector>
 #include <sys/stat.h>
+#include <cerrno>
 #include <unistd.h>
 
 #include "../../../include/d2gpu.h"
@@ -471,7 +472,16 @@ struct Writer {
     int fd = -1; uint64_t file_off = 0; std::string *mem = nullptr;
     bool put(const void *p, size_t nbytes) {
         if (mem) { mem->append((const char *)p, nbytes); return true; }
-        if (fd >= 0) { const bool ok = ::pwrite(fd, p, nbytes, (off_t)file_off) == (ssize_t)nbytes; file_off += nbytes; return ok; }
+        if (fd >= 0) {   // pwrite may move less than asked (2 GiB per call at most): continue until the block is out
+            const char *q = (const char *)p; size_t left = nbytes;
+            while (left) {
+                const ssize_t w = ::pwrite(fd, q, left, (off_t)file_off);
+                if (w < 0 && errno == EINTR) continue;
+                if (w <= 0) return false;
+                q += w; left -= (size_t)w; file_off += (uint64_t)w;
+            }
+            return true;
+        }
         return std::fwrite(p, 1, nbytes, fp) == nbytes;
     }
     static int sink(void *u, const float *blk, uint64_t first_row, uint64_t n_rows, uint64_t n_vals) {
