@@ -136,7 +136,7 @@ __device__ __forceinline__ uint64_t out_index(const CmpArgs &a, uint64_t i, uint
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(CMP_THREADS)
+static __global__ void __launch_bounds__(CMP_THREADS)
 cmp_tile_kernel(const CmpArgs a) {
     __shared__ double sA[CMP_T * CMP_LD];
     __shared__ double sB[CMP_T * CMP_LD];
@@ -206,7 +206,7 @@ cmp_tile_kernel(const CmpArgs a) {
 }
 
 // ---- densify (src/cmp_core.cpp:577-613): one thread per empty register --------------------------
-__global__ void densify_kernel(double *sig, uint64_t *kmers, uint64_t n, uint32_t S, double *tmp, uint64_t *ktmp) {
+static __global__ void densify_kernel(double *sig, uint64_t *kmers, uint64_t n, uint32_t S, double *tmp, uint64_t *ktmp) {
     const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (e >= n * S) return;
     const uint64_t g = e / S; const uint32_t i = (uint32_t)(e % S);

@@ -72,7 +72,7 @@ struct FssBootConsumer {
 // estimated from the sequence length (P(max > guess) ~ m^-2 when the estimate is right), and VERIFIED afterwards: if every
 // final register is <= the guess, nothing the guess pruned could have lowered a register and the result is exact; an
 // entity that fails (repetitive sequence: far fewer distinct elements than estimated) is redone through the boot pass.
-__global__ void fss_entity_positions_kernel(const uint64_t *rec_off, const uint32_t *rec_entity, uint64_t n_rec, uint32_t ent_base, int need,
+static __global__ void fss_entity_positions_kernel(const uint64_t *rec_off, const uint32_t *rec_entity, uint64_t n_rec, uint32_t ent_base, int need,
                                             unsigned long long *npos) {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
@@ -80,7 +80,7 @@ __global__ void fss_entity_positions_kernel(const uint64_t *rec_off, const uint3
     if (l >= (uint64_t)need) atomicAdd(npos + (rec_entity[r] - ent_base), (unsigned long long)(l - need + 1));
 }
 // state: 0 = guessed bound (main pass A), 1 = boot pass + main pass B
-__global__ void fss_guess_kernel(const unsigned long long *npos, uint32_t n_ent, uint32_t m, int wsz, int allow_guess, double *T, double *Tguess, uint32_t *state) {
+static __global__ void fss_guess_kernel(const unsigned long long *npos, uint32_t n_ent, uint32_t m, int wsz, int allow_guess, double *T, double *Tguess, uint32_t *state) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ent) return;
     const double n_est = (double)npos[e] * (wsz > 1 ? 2. / (wsz + 1.) : 1.);
@@ -90,7 +90,7 @@ __global__ void fss_guess_kernel(const unsigned long long *npos, uint32_t n_ent,
     T[e] = g; Tguess[e] = g; state[e] = guess ? 0u : 1u;
 }
 // one CTA per entity in state 0: exact iff every register is filled and the largest is <= the guess; else -> state 1, registers cleared
-__global__ void fss_verify_kernel(uint64_t *keys, uint32_t m, const double *Tguess, uint32_t *state, unsigned int *n_redo) {
+static __global__ void fss_verify_kernel(uint64_t *keys, uint32_t m, const double *Tguess, uint32_t *state, unsigned int *n_redo) {
     __shared__ uint64_t red[256];
     const uint32_t ent = blockIdx.x;
     if (state[ent] != 0) { if (threadIdx.x == 0) atomicAdd(n_redo, 1u); return; }
@@ -107,7 +107,7 @@ __global__ void fss_verify_kernel(uint64_t *keys, uint32_t m, const double *Tgue
 }
 
 // one CTA per entity: T = max_i ev_0(maxrv_i) (DBL_MAX when some register was never hit by the sample)
-__global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *T, const uint32_t *state) {
+static __global__ void fss_threshold_kernel(const uint64_t *maxrv, uint32_t m, double *T, const uint32_t *state) {
     __shared__ double red[256];
     const uint32_t ent = blockIdx.x;
     if (state && state[ent] != 1) return;
@@ -341,7 +341,7 @@ struct FssMainConsumer {
 };
 
 // one CTA per entity: T[e] = largest final register (keys are order preserving; an entity without elements keeps its bound)
-__global__ void fss_final_bound_kernel(const uint64_t *keys, uint32_t m, double *T) {
+static __global__ void fss_final_bound_kernel(const uint64_t *keys, uint32_t m, double *T) {
     __shared__ uint64_t red[256];
     const uint32_t e = blockIdx.x;
     uint64_t mx = 0;
@@ -379,7 +379,7 @@ struct FssIdsConsumer {
     __device__ __forceinline__ void end_tile(uint32_t) {}
     __device__ __forceinline__ void flush(uint32_t) {}
 };
-__global__ void fss_longwalk_ids_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,
+static __global__ void fss_longwalk_ids_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,
                                         const double *T, const uint64_t *keys, uint64_t *ids, uint32_t *scratch) {
     const uint64_t slot = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint64_t nslots = (uint64_t)gridDim.x * blockDim.x;
@@ -393,7 +393,7 @@ __global__ void fss_longwalk_ids_kernel(const uint64_t *ovf, const unsigned long
 }
 
 // long walks: one thread per queued element, dense permutation state in HBM scratch (slot-private)
-__global__ void fss_longwalk_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,
+static __global__ void fss_longwalk_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,
                                     const double *T, uint64_t *keys, uint32_t *scratch) {
     const uint64_t slot = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint64_t nslots = (uint64_t)gridDim.x * blockDim.x;
@@ -408,7 +408,7 @@ __global__ void fss_longwalk_kernel(const uint64_t *ovf, const unsigned long lon
 
 // keys -> doubles (first S registers) and cardinality m / sum(reg) (setsketch.h:553-561; the reference
 // sums under `omp simd`, i.e. in compiler-chosen order: sequential here, agreement ~1e-15 relative)
-__global__ void fss_finalize_kernel(const uint64_t *keys, uint32_t n_ent, uint32_t m, double *sig, double *card) {
+static __global__ void fss_finalize_kernel(const uint64_t *keys, uint32_t n_ent, uint32_t m, double *sig, double *card) {
     const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (sig && e < (uint64_t)n_ent * m) sig[e] = dunkey(keys[e]);
     if (card && e < n_ent) {
