@@ -7,13 +7,17 @@ NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -ccbin $(CXX_HOST) 
 CSRC := dashing2_b200/csrc
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/d2gpu.h
 UNITS := api_core api_sketch api_weighted api_cmp api_lsh
-OBJS := $(patsubst %,build/%.o,$(UNITS))
+OBJS := $(patsubst %,build/%.o,$(UNITS)) build/pack_host.o
 
 all: dashing2_b200/libd2gpu.so dashing2_b200/bin/dashing2-gpu
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+build/pack_host.o: $(CSRC)/host/pack_host.cpp $(CSRC)/host/pack_host.h
+	@mkdir -p build
+	$(CXX_HOST) -O3 -std=c++17 -fPIC -Wall -c -o $@ $<
 
 dashing2_b200/libd2gpu.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -ccbin $(CXX_HOST) -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt

@@ -38,6 +38,7 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c
 EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stream", "d2g_sync", "d2g_launch_count",
            "d2g_set_timing", "d2g_get_timing",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_distinct_kmers", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
+           "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_free"]
 
@@ -73,6 +74,13 @@ def load():
     L.d2g_distinct_kmers.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, vp]; L.d2g_distinct_kmers.restype = C.c_int
     L.d2g_sketch_batch_dev.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, u64, vp, vp, vp, vp]
     L.d2g_sketch_batch_dev.restype = C.c_int
+    L.d2g_packed_words.argtypes = [u64]; L.d2g_packed_words.restype = u64
+    L.d2g_pack_sequences.argtypes = [vp, vp, u64, vp, vp, C.POINTER(u64)]; L.d2g_pack_sequences.restype = C.c_int
+    L.d2g_pack_dev.argtypes = [vp, vp, u64, vp, vp]; L.d2g_pack_dev.restype = C.c_int
+    L.d2g_sketch_batch_packed.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, vp, u64, u32, vp, vp, vp, vp, C.POINTER(u64)]
+    L.d2g_sketch_batch_packed.restype = C.c_int
+    L.d2g_sketch_batch_packed_dev.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, vp, u64, u32, u64, vp, vp, vp, vp]
+    L.d2g_sketch_batch_packed_dev.restype = C.c_int
     L.d2g_densify.argtypes = [vp, vp, vp, u64, u32]; L.d2g_densify.restype = C.c_int
     L.d2g_densify_dev.argtypes = [vp, vp, vp, u64, u32]; L.d2g_densify_dev.restype = C.c_int
     L.d2g_make_compressed.argtypes = [vp, vp, u64, u32, C.c_double, i32, C.POINTER(C.c_longdouble), C.POINTER(C.c_longdouble), vp, C.POINTER(i32)]
@@ -116,6 +124,21 @@ def xormask_for_seed(seed: int) -> int:
     key ^= key >> 28
     key = (key + (key << 31)) & M
     return key
+
+
+def pack_sequences(pieces):
+    """Host packer (d2g_pack_sequences): list of bytes-like ASCII pieces -> (codes u64[], mask u32[], n_invalid_words).
+    Needs no device."""
+    L = load()
+    bufs = [np.frombuffer(bytes(x), dtype=np.uint8) if not isinstance(x, np.ndarray) else np.ascontiguousarray(x, dtype=np.uint8) for x in pieces]
+    n = len(bufs)
+    ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data if b.size else None for b in bufs])
+    lens = np.asarray([b.size for b in bufs], dtype=np.uint64)
+    nw = int(L.d2g_packed_words(int(lens.sum())))
+    codes = np.empty(nw, dtype=np.uint64); mask = np.empty(nw, dtype=np.uint32)
+    nz = C.c_uint64(0)
+    _check(L.d2g_pack_sequences(ptrs, _ptr(lens), n, _ptr(codes), _ptr(mask), C.byref(nz)))
+    return codes, mask, int(nz.value)
 
 
 class Context:
@@ -176,6 +199,24 @@ class Context:
                                        _ptr(regs), _ptr(sig), _ptr(card), _ptr(ids), C.byref(nk)))
         return dict(regs_u64=regs, sig=sig, card=card, ids=ids, n_kmers=int(nk.value))
 
+    def sketch_batch_packed(self, codes: np.ndarray, mask, rec_off: np.ndarray, rec_entity: np.ndarray, n_entities: int,
+                            p: SketchParams, want_ids=False, want_regs=True):
+        """The same with the sequence packed by the caller (d2g_sketch_batch_packed); mask may be None."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        rec_entity = np.ascontiguousarray(rec_entity, dtype=np.uint32)
+        S = p.sketchsize
+        m = self.L.d2g_opmh_m(S)
+        regs = np.empty((n_entities, m), dtype=np.uint64) if (p.mode == 0 and want_regs) else None
+        sig = np.empty((n_entities, S), dtype=np.float64)
+        card = np.empty(n_entities, dtype=np.float64)
+        ids = np.empty((n_entities, S), dtype=np.uint64) if want_ids else None
+        nk = C.c_uint64(0)
+        _check(self.L.d2g_sketch_batch_packed(self.h, C.byref(p), _ptr(codes), _ptr(mask), _ptr(rec_off), _ptr(rec_entity), len(rec_entity),
+                                              n_entities, _ptr(regs), _ptr(sig), _ptr(card), _ptr(ids), C.byref(nk)))
+        return dict(regs_u64=regs, sig=sig, card=card, ids=ids, n_kmers=int(nk.value))
+
     def distinct_kmers(self, seq: np.ndarray, rec_off: np.ndarray, rec_entity: np.ndarray, n_entities: int, p: SketchParams) -> np.ndarray:
         """Exact distinct k-mers (minimizers) per entity, host in / host out (d2g_distinct_kmers)."""
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
@@ -190,6 +231,14 @@ class Context:
         """Device pointers (ints) in/out; asynchronous on self.stream (d2g_sketch_batch_dev)."""
         _check(self.L.d2g_sketch_batch_dev(self.h, C.byref(p), seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
                                            regs_u64_d or None, sig_d or None, card_d or None, ids_d or None))
+
+    def pack_dev(self, seq_d, total_len, codes_d, mask_d):
+        _check(self.L.d2g_pack_dev(self.h, seq_d, total_len, codes_d, mask_d))
+
+    def sketch_batch_packed_dev(self, p, codes_d, mask_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
+                                regs_u64_d=0, sig_d=0, card_d=0, ids_d=0):
+        _check(self.L.d2g_sketch_batch_packed_dev(self.h, C.byref(p), codes_d, mask_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
+                                                  regs_u64_d or None, sig_d or None, card_d or None, ids_d or None))
 
     def opmh_finalize(self, regs_u64: np.ndarray, S: int):
         regs_u64 = np.ascontiguousarray(regs_u64, dtype=np.uint64)

@@ -50,6 +50,7 @@ void d2g_destroy(d2g_ctx *c) {
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
     if (c->evd[0]) cudaEventDestroy(c->evd[0]);
     if (c->evd[1]) cudaEventDestroy(c->evd[1]);
+    for (auto &e : c->stage_free) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;

@@ -51,7 +51,8 @@ struct d2g_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::atomic<uint64_t> launches{0};
-    DevBuf seq, recoff, recent, regs, sig, card, ids, aux, aux2;   // sketch scratch
+    DevBuf seq, pcodes, pmask, recoff, recent, regs, sig, card, ids, aux, aux2;   // sketch scratch (pcodes / pmask: the packed batch)
+    PinBuf stage[3]; cudaEvent_t stage_free[3] = {nullptr, nullptr, nullptr};        // pinned staging ring of the host packer
     DevBuf wbuf, wtmp, lbuf;                                              // counting scratch (BagMinHash / ProbMinHash)
     DevBuf cregs, ccards, cout, clut, clut80, ctmp, cktmp;         // compare scratch
     DevBuf c16buf, c16codes, c16grank, c16flag;                    // order-code compare scratch (keys, sort buffers, codes, global ranks)
@@ -81,12 +82,13 @@ struct KernelTimer {
 
 // ---- shared between the sketch translation units ----
 #include "common.cuh"
+#include "pack_kernels.cuh"
 namespace d2g { struct SketchArgs; }
 struct SketchRange { uint64_t pos_base, pos_end; uint32_t ent_base; };
 int check_sketch_params(const d2g_sketch_params *p);
-int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                     uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d);
-int launch_opmh_mincount(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+int launch_opmh_mincount(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                          uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d);
 static __global__ void fill_u64_kernel(uint64_t *p, uint64_t n, uint64_t v) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;

@@ -88,11 +88,14 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     }
     // 3. ordered candidate scan, one warp per query
     {
-        const int wpb = 4;
+        int wpb = 4;                                                  // queries (warps) per CTA; fewer when the candidate lists are long
+        while (wpb > 1 && (size_t)wpb * 2 * maxcand * 4 > 96 * 1024) wpb >>= 1;
         const size_t smem = (size_t)wpb * 2 * maxcand * 4;
+        CU(cudaFuncSetAttribute(d2g::lsh_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(c, D2G_T_CMP);
         d2g::lsh_query_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(regs_d, n, S, kB, iB, maxcand, cand, cnt, ncand, n1, n2);
         c->launches++;
+        CU(cudaGetLastError());
     }
     // 4. arrivals, stable sort by destination list, segment starts, replay
     d2g::lsh_arrivals_kernel<<<(unsigned)((n * maxcand + 255) / 256), 256, 0, st>>>(cand, cnt, ncand, n, maxcand, (uint32_t)x0, (uint32_t)x1, alA, apA);

@@ -3,6 +3,7 @@
 // arithmetic on the host in the reference too (/root/reference/src/oph.h:240-263).
 #include "api_sketch_launch.h"
 #include "fss_kernels.cuh"
+#include "host/pack_host.h"
 
 namespace {
 __global__ void opmh_ids_kernel(const uint64_t *regs, uint64_t *ids, uint64_t n_ent, uint32_t m, uint32_t S) {
@@ -34,7 +35,7 @@ int check_sketch_params(const d2g_sketch_params *p) {
 
 namespace {
 // regs_d: [n_ent][m] u64 for OPMH.  Launches the OPMH sketch kernels on the ctx stream.
-int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
+int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d,
                 const uint32_t *rec_ent_d, uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d,
                 const SketchRange *range = nullptr) {
     const SketchRange rg = range ? *range : SketchRange{0, total_len, 0};
@@ -50,7 +51,7 @@ int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const
 
 // Full SetSketch (see fss_kernels.cuh): boot -> threshold -> main -> long walks -> finalize.
 // sig_d [n_ent][S] / card_d [n_ent] may be null.  Synchronises the stream to check the long-walk queue.
-int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d,
                const SketchRange *range = nullptr) {
     if (n_ent == 0) return D2G_OK;
@@ -195,12 +196,13 @@ extern "C" int d2g_opmh_finalize(const uint64_t *regs_u64, uint32_t n_entities, 
     return D2G_OK;
 }
 
-extern "C" int d2g_sketch_batch_dev(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
-                                    const uint32_t *rec_entity_d, uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
-                                    uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d) {
-    if (!c) return fail(D2G_EINVAL, "null ctx");
-    if (int rc = check_sketch_params(p)) return rc;
-    CU(cudaSetDevice(c->device));
+// ---- device-resident entry points ---------------------------------------------------------------------------------------
+namespace {
+// Sketch kernels over a packed batch that is resident on the device; outputs on the device.  Asynchronous on the ctx stream
+// except where a launcher has to read a counter back (Full SetSketch, counting sketches).
+int sketch_packed_dev(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d,
+                      const uint32_t *rec_entity_d, uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
+                      uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d) {
     if (p->mode == D2G_MODE_OPMH) {
         if (sig_out_d || card_out_d)
             return fail(D2G_EINVAL, "OPMH signatures/cardinalities are x87 long-double transforms of the u64 minima (src/oph.h:240-263): "
@@ -220,77 +222,183 @@ extern "C" int d2g_sketch_batch_dev(d2g_ctx *c, const d2g_sketch_params *p, cons
     return launch_weighted(c, p, seq_d, rec_off_d, rec_entity_d, n_rec, n_entities, total_len, sig_out_d, card_out_d, ids_out_d);
 }
 
-extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const char *seq, const uint64_t *rec_off,
-                                const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities, uint64_t *regs_u64_out,
-                                double *sig_out, double *card_out, uint64_t *ids_out, uint64_t *n_kmers_hashed) {
-    if (!c) return fail(D2G_EINVAL, "null ctx");
-    if (int rc = check_sketch_params(p)) return rc;
+int check_records(const uint64_t *rec_off, const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities) {
     if (n_rec && (!rec_off || !rec_entity)) return fail(D2G_EINVAL, "null record tables");
-    CU(cudaSetDevice(c->device));
-    const uint64_t total_len = n_rec ? rec_off[n_rec] : 0;
-    if (total_len && !seq) return fail(D2G_EINVAL, "null sequence buffer");
     for (uint64_t r = 0; r < n_rec; ++r) {
         if (rec_off[r + 1] < rec_off[r]) return fail(D2G_EINVAL, "rec_off not monotone at %llu", (unsigned long long)r);
         if (rec_entity[r] >= n_entities) return fail(D2G_EINVAL, "rec_entity[%llu]=%u >= n_entities", (unsigned long long)r, rec_entity[r]);
         if (r && rec_entity[r] < rec_entity[r - 1]) return fail(D2G_EINVAL, "rec_entity must be non-decreasing");
     }
+    return D2G_OK;
+}
+} // namespace
+
+extern "C" uint64_t d2g_packed_words(uint64_t n_bases) { return d2g::packed_words(n_bases); }
+
+extern "C" int d2g_pack_sequences(const char *const *pieces, const uint64_t *piece_len, uint64_t n_pieces, uint64_t *codes, uint32_t *mask,
+                                  uint64_t *n_invalid_words) {
+    if (n_pieces && (!pieces || !piece_len)) return fail(D2G_EINVAL, "null pieces");
+    if (!codes || !mask) return fail(D2G_EINVAL, "null output");
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n_pieces; ++i) { if (piece_len[i] && !pieces[i]) return fail(D2G_EINVAL, "null piece %llu", (unsigned long long)i); total += piece_len[i]; }
+    const uint64_t nz = d2g_host::pack_pieces(pieces, piece_len, n_pieces, d2g::packed_words(total), codes, mask);
+    if (n_invalid_words) *n_invalid_words = nz;
+    return D2G_OK;
+}
+
+extern "C" int d2g_pack_dev(d2g_ctx *c, const char *seq_d, uint64_t total_len, uint64_t *codes_d, uint32_t *mask_d) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (!codes_d || !mask_d || (total_len && !seq_d)) return fail(D2G_EINVAL, "null buffer");
+    CU(cudaSetDevice(c->device));
+    const uint64_t nw = d2g::packed_words(total_len);
+    KernelTimer kt(c, D2G_T_PACK);
+    d2g::pack_ascii_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint8_t *>(seq_d), total_len, nw, codes_d, mask_d);
+    c->launches++;
+    CU(cudaGetLastError());
+    return D2G_OK;
+}
+
+extern "C" int d2g_sketch_batch_packed_dev(d2g_ctx *c, const d2g_sketch_params *p, const uint64_t *codes_d, const uint32_t *mask_d,
+                                           const uint64_t *rec_off_d, const uint32_t *rec_entity_d, uint64_t n_rec, uint32_t n_entities,
+                                           uint64_t total_len, uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    if (total_len && (!codes_d || !mask_d)) return fail(D2G_EINVAL, "null packed sequence");
+    CU(cudaSetDevice(c->device));
+    return sketch_packed_dev(c, p, d2g::PackedSeq{codes_d, mask_d}, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
+                             regs_u64_out_d, sig_out_d, card_out_d, ids_out_d);
+}
+
+extern "C" int d2g_sketch_batch_dev(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
+                                    const uint32_t *rec_entity_d, uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
+                                    uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    CU(cudaSetDevice(c->device));
+    const uint64_t nw = d2g::packed_words(total_len);
+    if (int rc = c->pcodes.reserve(nw * 8)) return rc;
+    if (int rc = c->pmask.reserve(nw * 4)) return rc;
+    if (int rc = d2g_pack_dev(c, seq_d, total_len, c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>())) return rc;
+    return sketch_packed_dev(c, p, d2g::PackedSeq{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()}, rec_off_d, rec_entity_d, n_rec, n_entities,
+                             total_len, regs_u64_out_d, sig_out_d, card_out_d, ids_out_d);
+}
+
+// ---- host entry points ------------------------------------------------------------------------------------------------
+namespace {
+// Whole-entity chunks of ~target bases: the upload of chunk i+1 overlaps the kernels of chunk i.
+struct Chunk { uint64_t r0, r1; uint32_t e0, e1; };
+std::vector<Chunk> make_chunks(const uint64_t *rec_off, const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities, uint64_t target) {
+    std::vector<Chunk> chunks;
+    uint64_t r0 = 0; uint32_t e0 = 0;
+    for (uint64_t r = 0; r < n_rec; ++r) {
+        const bool last = r + 1 == n_rec;
+        if (last || (rec_entity[r + 1] != rec_entity[r] && rec_off[r + 1] - rec_off[r0] >= target)) {
+            const uint32_t e1 = last ? n_entities : rec_entity[r + 1];
+            chunks.push_back({r0, r + 1, e0, e1});
+            r0 = r + 1; e0 = e1;
+        }
+    }
+    if (chunks.empty()) chunks.push_back({0, 0, 0, n_entities});
+    return chunks;
+}
+
+// What feeds the device: either ASCII the library packs itself (host threads, pinned staging ring), or arrays the caller packed.
+struct HostSeq {
+    const char *ascii = nullptr;                      // concatenated record bytes
+    const uint64_t *codes = nullptr; const uint32_t *mask = nullptr;   // packed by the caller (mask may be null: no invalid base)
+};
+
+// Shared body of d2g_sketch_batch / d2g_sketch_batch_packed: upload (packing on the way when the input is ASCII), kernels per chunk,
+// results back to the host.
+int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs, const uint64_t *rec_off, const uint32_t *rec_entity,
+                      uint64_t n_rec, uint32_t n_entities, uint64_t *regs_u64_out, double *sig_out, double *card_out, uint64_t *ids_out,
+                      uint64_t *n_kmers_hashed) {
+    if (int rc = check_records(rec_off, rec_entity, n_rec, n_entities)) return rc;
+    CU(cudaSetDevice(c->device));
+    const uint64_t total_len = n_rec ? rec_off[n_rec] : 0;
     if (n_kmers_hashed) *n_kmers_hashed = d2g_count_kmers(rec_off, n_rec, p->k);
     const uint32_t S = p->sketchsize, m = d2g_opmh_m(S);
-    if (int rc = c->seq.reserve(total_len + 64)) return rc;
+    const uint64_t nw_total = d2g::packed_words(total_len);
+    if (int rc = c->pcodes.reserve(nw_total * 8)) return rc;
+    if (int rc = c->pmask.reserve(nw_total * 4)) return rc;
     if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
     if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
     if (n_rec) {
         CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    const char *seq_d = c->seq.as<char>();
+    uint64_t *codes_d = c->pcodes.as<uint64_t>(); uint32_t *mask_d = c->pmask.as<uint32_t>();
+    const d2g::PackedSeq seq_d{codes_d, mask_d};
     const uint64_t *off_d = c->recoff.as<uint64_t>();
     const uint32_t *ent_d = c->recent.as<uint32_t>();
     const bool opmh_mincount = p->mode == D2G_MODE_OPMH && p->count_threshold > 1;   // counts need the whole batch sorted at once
     const bool chunked = (p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH) && !opmh_mincount;
     auto off_at = [&](uint64_t r) -> uint64_t { return n_rec ? rec_off[r] : 0; };
-    // Chunks of whole entities (~D2G_CHUNK_BYTES of sequence each, default 256 MiB): the upload of chunk i+1 runs on the copy
-    // stream while chunk i is sketched, so a large batch moves at PCIe speed instead of copy + compute.
-    struct Chunk { uint64_t r0, r1; uint32_t e0, e1; };
-    std::vector<Chunk> chunks;
-    {
-        uint64_t target = 256ULL << 20;
-        if (const char *ev = getenv("D2G_CHUNK_BYTES")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
-        if (!chunked) target = ~0ULL;
-        uint64_t r0 = 0; uint32_t e0 = 0;
-        for (uint64_t r = 0; r < n_rec; ++r) {
-            const bool last = r + 1 == n_rec;
-            if (last || (rec_entity[r + 1] != rec_entity[r] && rec_off[r + 1] - rec_off[r0] >= target)) {
-                const uint32_t e1 = last ? n_entities : rec_entity[r + 1];
-                chunks.push_back({r0, r + 1, e0, e1});
-                r0 = r + 1; e0 = e1;
+    uint64_t target = 128ULL << 20;                   // bases per chunk
+    if (const char *ev = getenv("D2G_CHUNK_BYTES")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
+    if (!chunked) target = ~0ULL;
+    const std::vector<Chunk> chunks = make_chunks(rec_off, rec_entity, n_rec, n_entities, target);
+    const size_t nch = chunks.size();
+    // word range of a chunk: whole 128-base blocks (16-byte granules of both arrays); a block that straddles two chunks goes up with both
+    auto w_lo = [&](size_t i) { return off_at(chunks[i].r0) / 128 * 4; };
+    auto w_hi = [&](size_t i) { return i + 1 == nch ? nw_total : (off_at(chunks[i].r1) + 127) / 128 * 4; };
+
+    std::vector<cudaEvent_t> up(nch, nullptr);        // upload of chunk i complete
+    auto free_evs = [&]() { for (auto e : up) if (e) cudaEventDestroy(e); };
+    for (size_t i = 0; i < nch; ++i) if (cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming) != cudaSuccess) { free_evs(); return fail(D2G_ECUDA, "cudaEventCreate failed"); }
+
+    // Producer: runs on its own host thread so that packing and uploading chunk i+1 overlap the kernels of chunk i, whose launcher
+    // may block on the stream (Full SetSketch reads a counter back per chunk).
+    std::atomic<size_t> uploaded{0}; std::atomic<int> prc{0};
+    std::string perr;
+    auto producer = [&]() {
+        cudaSetDevice(c->device);
+        for (size_t i = 0; i < nch; ++i) {
+            const uint64_t a = w_lo(i), b = w_hi(i);
+            cudaError_t e = cudaSuccess;
+            if (b > a) {
+                if (hs.ascii) {
+                    const int slot = (int)(i % 3);
+                    if (!c->stage_free[slot]) cudaEventCreateWithFlags(&c->stage_free[slot], cudaEventDisableTiming);
+                    else cudaEventSynchronize(c->stage_free[slot]);          // the copy that last used this slot has left it
+                    if (c->stage[slot].reserve((b - a) * 12) != D2G_OK) { perr = d2g_last_error(); prc = D2G_ENOMEM; break; }
+                    uint64_t *sc = reinterpret_cast<uint64_t *>(c->stage[slot].p);
+                    uint32_t *sm = reinterpret_cast<uint32_t *>(sc + (b - a));
+                    const uint64_t nz = d2g_host::pack_contiguous(hs.ascii, total_len, a, b, sc, sm);
+                    e = cudaMemcpyAsync(codes_d + a, sc, (b - a) * 8, cudaMemcpyHostToDevice, c->copy_stream);
+                    // mask words only travel when the chunk holds an invalid base at all
+                    if (e == cudaSuccess) e = nz ? cudaMemcpyAsync(mask_d + a, sm, (b - a) * 4, cudaMemcpyHostToDevice, c->copy_stream)
+                                                 : cudaMemsetAsync(mask_d + a, 0, (b - a) * 4, c->copy_stream);
+                    cudaEventRecord(c->stage_free[slot], c->copy_stream);
+                } else {
+                    e = cudaMemcpyAsync(codes_d + a, hs.codes + a, (b - a) * 8, cudaMemcpyHostToDevice, c->copy_stream);
+                    if (e == cudaSuccess) e = hs.mask ? cudaMemcpyAsync(mask_d + a, hs.mask + a, (b - a) * 4, cudaMemcpyHostToDevice, c->copy_stream)
+                                                      : cudaMemsetAsync(mask_d + a, 0, (b - a) * 4, c->copy_stream);
+                }
             }
+            if (e != cudaSuccess) { perr = std::string("sequence upload failed: ") + cudaGetErrorString(e); prc = D2G_ECUDA; break; }
+            cudaEventRecord(up[i], c->copy_stream);
+            uploaded.store(i + 1, std::memory_order_release);
         }
-        if (chunks.empty()) chunks.push_back({0, 0, 0, n_entities});
-    }
-    std::vector<cudaEvent_t> evs(chunks.size(), nullptr);
-    auto free_evs = [&]() { for (auto e : evs) if (e) cudaEventDestroy(e); };
-    for (size_t i = 0; i < chunks.size(); ++i) {
-        const uint64_t b0 = off_at(chunks[i].r0), b1 = off_at(chunks[i].r1);
-        if (b1 > b0) {
-            cudaError_t e1 = cudaMemcpyAsync(c->seq.as<char>() + b0, seq + b0, b1 - b0, cudaMemcpyHostToDevice, chunks.size() > 1 ? c->copy_stream : c->stream);
-            if (e1 != cudaSuccess) { free_evs(); return fail(D2G_ECUDA, "sequence upload failed: %s", cudaGetErrorString(e1)); }
-        }
-        if (chunks.size() > 1) {
-            cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming);
-            cudaEventRecord(evs[i], c->copy_stream);
-        }
-    }
+    };
+    std::thread prod;
+    if (nch > 1) prod = std::thread(producer); else producer();
+    auto finish = [&](int rc) { if (prod.joinable()) prod.join(); cudaStreamSynchronize(c->copy_stream); free_evs(); return rc; };
+
     if (p->mode == D2G_MODE_OPMH) {
-        if (int rc = c->regs.reserve((uint64_t)n_entities * m * 8)) { free_evs(); return rc; }
+        if (int rc = c->regs.reserve((uint64_t)n_entities * m * 8)) return finish(rc);
     } else {
-        if (int rc = c->sig.reserve((uint64_t)n_entities * S * 8)) { free_evs(); return rc; }
-        if (int rc = c->card.reserve((uint64_t)n_entities * 8)) { free_evs(); return rc; }
-        if (ids_out) if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) { free_evs(); return rc; }
+        if (int rc = c->sig.reserve((uint64_t)n_entities * S * 8)) return finish(rc);
+        if (int rc = c->card.reserve((uint64_t)n_entities * 8)) return finish(rc);
+        if (ids_out) if (int rc = c->ids.reserve((uint64_t)n_entities * S * 8)) return finish(rc);
     }
-    for (size_t i = 0; i < chunks.size(); ++i) {
+    for (size_t i = 0; i < nch; ++i) {
         const Chunk &ch = chunks[i];
-        if (evs[i]) cudaStreamWaitEvent(c->stream, evs[i], 0);
+        while (uploaded.load(std::memory_order_acquire) <= i) {
+            if (prc.load()) { const int rc = prc.load(); if (prod.joinable()) prod.join(); free_evs(); return fail(rc, "%s", perr.c_str()); }
+            std::this_thread::yield();
+        }
+        cudaStreamWaitEvent(c->stream, up[i], 0);
         const uint64_t nr = ch.r1 - ch.r0; const uint32_t ne = ch.e1 - ch.e0;
         const SketchRange rg{off_at(ch.r0), off_at(ch.r1), ch.e0};
         int rc;
@@ -304,8 +412,9 @@ extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const ch
         else
             rc = launch_weighted(c, p, seq_d, off_d, ent_d, n_rec, n_entities, total_len, c->sig.as<double>(), c->card.as<double>(),
                                  ids_out ? c->ids.as<uint64_t>() : nullptr);
-        if (rc) { cudaStreamSynchronize(c->copy_stream); free_evs(); return rc; }
+        if (rc) return finish(rc);
     }
+    if (prod.joinable()) prod.join();
     free_evs();
     if (p->mode == D2G_MODE_OPMH) {
         std::vector<uint64_t> tmp;
@@ -328,4 +437,25 @@ extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const ch
     CU(cudaStreamSynchronize(c->stream));
     (void)regs_u64_out;
     return D2G_OK;
+}
+} // namespace
+
+extern "C" int d2g_sketch_batch(d2g_ctx *c, const d2g_sketch_params *p, const char *seq, const uint64_t *rec_off,
+                                const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities, uint64_t *regs_u64_out,
+                                double *sig_out, double *card_out, uint64_t *ids_out, uint64_t *n_kmers_hashed) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    if (n_rec && rec_off && rec_off[n_rec] && !seq) return fail(D2G_EINVAL, "null sequence buffer");
+    HostSeq hs; hs.ascii = seq;
+    return sketch_batch_host(c, p, hs, rec_off, rec_entity, n_rec, n_entities, regs_u64_out, sig_out, card_out, ids_out, n_kmers_hashed);
+}
+
+extern "C" int d2g_sketch_batch_packed(d2g_ctx *c, const d2g_sketch_params *p, const uint64_t *codes, const uint32_t *mask,
+                                       const uint64_t *rec_off, const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities,
+                                       uint64_t *regs_u64_out, double *sig_out, double *card_out, uint64_t *ids_out, uint64_t *n_kmers_hashed) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    if (n_rec && rec_off && rec_off[n_rec] && !codes) return fail(D2G_EINVAL, "null packed sequence");
+    HostSeq hs; hs.codes = codes; hs.mask = mask;
+    return sketch_batch_host(c, p, hs, rec_off, rec_entity, n_rec, n_entities, regs_u64_out, sig_out, card_out, ids_out, n_kmers_hashed);
 }

@@ -15,11 +15,11 @@ uint64_t pick_span(const d2g_ctx *c, uint64_t total_len, uint32_t m) {
 
 // A launch may cover only part of a batch (chunked host uploads): start positions [pos_base, pos_end) of the
 // sequence buffer, whose records are rec_off_d[0..n_rec] (absolute offsets) and whose entities start at ent_base.
-d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d,
+d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d,
                                  const uint32_t *rec_ent_d, uint64_t n_rec, uint64_t total_len, uint32_t m, const SketchRange &rg) {
     d2g::SketchArgs a;
-    a.seq = reinterpret_cast<const uint8_t *>(seq_d); a.rec_off = rec_off_d; a.rec_entity = rec_ent_d;
-    a.n_rec = n_rec; a.total_len = total_len; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
+    a.seq = seq_d; a.rec_off = rec_off_d; a.rec_entity = rec_ent_d;
+    a.n_rec = n_rec; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
     a.pos_base = rg.pos_base; a.pos_end = rg.pos_end; a.ent_base = rg.ent_base; a.ent_state = nullptr; a.want_state = 0;
     a.m = m; a.tile_stride = 1; a.score_slots = d2g::sketch_score_slots(p->k, p->w);
     a.span = pick_span(c, rg.pos_end - rg.pos_base, m);

@@ -16,7 +16,7 @@ __global__ void weighted_finalize_kernel(const uint64_t *keys, const unsigned lo
 }
 } // namespace
 
-int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                     uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d) {
     const uint32_t m = p->sketchsize;
     const uint64_t n = total_len, nreg = (uint64_t)n_ent * m;
@@ -186,7 +186,7 @@ __global__ void opmh_mincount_kernel(const uint64_t *hv, const uint32_t *ent, ui
 }
 } // namespace
 
-int launch_opmh_mincount(d2g_ctx *c, const d2g_sketch_params *p, const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
+int launch_opmh_mincount(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                          uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d) {
     const uint32_t m = d2g_opmh_m(p->sketchsize);
     const uint64_t n = total_len, nreg = (uint64_t)n_ent * m;
@@ -265,10 +265,15 @@ extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const 
     if (int rc = c->seq.reserve(n + 64)) return rc;
     if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
     if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
+    const uint64_t nw = d2g::packed_words(n);
+    if (int rc = c->pcodes.reserve(nw * 8)) return rc;
+    if (int rc = c->pmask.reserve(nw * 4)) return rc;
     cudaStream_t st = c->stream;
     CU(cudaMemcpyAsync(c->seq.p, seq, n, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = d2g_pack_dev(c, c->seq.as<char>(), n, c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>())) return rc;
+    const d2g::PackedSeq seq_d{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()};
     auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
     uint64_t off = 0;
     const uint64_t o_hvA = off; off += al(n * 8 + 8);
@@ -284,7 +289,7 @@ extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const 
     CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
     CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
     CU(cudaMemsetAsync(cnt, 0, (uint64_t)n_entities * 8, st));
-    d2g::SketchArgs a = make_sketch_args(c, p, c->seq.as<char>(), c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
     if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
     d2g::EmitConsumer::Params ep{hvA, entA, a.span};
     if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;

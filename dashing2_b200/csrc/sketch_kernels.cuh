@@ -3,8 +3,7 @@
 // One CTA owns a contiguous span of START POSITIONS of the concatenated sequence buffer and walks the
 // records that overlap it (k-mers never cross a record; windows reset per record --
 // /root/reference/bonsai/include/bonsai/encoder.h:201-206).  Per tile of SK_TILE start positions:
-//   1. coalesced 16-byte loads of ASCII bases -> 2 bits/base + 1 invalid bit/base in shared memory
-//      (alphabet: bonsai alphabet.h:128 DNA4, case-insensitive; anything else invalid);
+//   1. the packed sequence (2 bits/base + 1 invalid bit/base, pack_kernels.cuh) of the tile goes to shared memory;
 //   2. each thread rolls SK_PPT consecutive k-mers (forward and reverse-complement) out of the packed
 //      tile (encoder.h:241-272; kmerutil.h:83-90,137-140);
 //   3. windowed mode: per-position keys FRev64(canonical k-mer) go to shared memory and every thread
@@ -18,6 +17,7 @@
 // (src/setsketch.h:369-423, see fss_kernels.cuh).
 #pragma once
 #include "common.cuh"
+#include "pack_kernels.cuh"
 
 namespace d2g {
 
@@ -25,18 +25,17 @@ constexpr int SK_THREADS = 256;
 constexpr int SK_PPT = 8;                       // start positions per thread per tile
 constexpr int SK_TILE = SK_THREADS * SK_PPT;    // 2048 start positions per tile
 constexpr int SK_MAX_W = 1024;                  // largest window (bases) the tile halo supports
-constexpr int SK_NWORDS = (SK_TILE + SK_MAX_W + 16 + 31) / 32 + 2;
+constexpr int SK_NWORDS = (SK_TILE + SK_MAX_W + 128 + 31) / 32 + 4;   // a tile starts at a multiple of 128 bases (16-byte aligned in both packed arrays)
 // Window keys live in shared memory at index q + q/8: thread t owns keys 8t..8t+7 (+ window tail), so a
 // warp's simultaneous accesses are 9 u64 apart instead of 8 -- the minimum two wavefronts instead of 16.
 __host__ __device__ constexpr int sk_pad(int q) { return q + (q >> 3); }
 constexpr int SK_SCORE_SLOTS = sk_pad(SK_TILE + SK_MAX_W) + 1;
 
 struct SketchArgs {
-    const uint8_t *seq;          // concatenated record bytes (device), 16-byte aligned
+    PackedSeq seq;               // packed bases of the whole batch buffer (device), padded (pack_kernels.cuh)
     const uint64_t *rec_off;     // [n_rec + 1]
     const uint32_t *rec_entity;  // [n_rec]
     uint64_t n_rec;
-    uint64_t total_len;          // bytes of seq that may be read (bound of the 16-byte tile loads)
     uint64_t pos_base, pos_end;  // this launch covers start positions [pos_base, pos_end); rec_off values are absolute
     uint32_t ent_base;           // subtracted from rec_entity: the consumer's registers start at this entity
     const uint32_t *ent_state;   // optional [entities of this launch]: only records whose entity has ent_state == want_state are processed
@@ -49,35 +48,14 @@ struct SketchArgs {
     uint32_t score_slots;        // shared-memory window-key slots (windowed mode): sk_pad(SK_TILE + w - k + 1) + 1
 };
 
-// ---- ASCII -> packed codes ---------------------------------------------------------------------
-// 4 ASCII bytes (first base in the low byte) -> 8 bits of codes (first base in the two MSBs) and a
-// 4-bit invalid mask (first base in bit 3).  A0 C1 G2 T3.
-__device__ __forceinline__ void decode4(uint32_t v, uint32_t &codes, uint32_t &inv) {
-    uint32_t x = (v >> 1) & 0x03030303u;               // A0 C1 T2 G3
-    x ^= (x >> 1) & 0x01010101u;                        // A0 C1 G2 T3
-    codes = (x * 0x40100401u) >> 24;
-    const uint32_t u = v & 0xDFDFDFDFu;                 // fold case
-    uint32_t z, nz;
-    z = u ^ 0x41414141u; nz = (((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z);
-    z = u ^ 0x43434343u; nz &= (((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z);
-    z = u ^ 0x47474747u; nz &= (((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z);
-    z = u ^ 0x54545454u; nz &= (((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z);
-    inv = ((((nz & 0x80808080u) >> 7) * 0x08040201u) >> 24) & 0xFu;
-}
-
-// loads bytes [o, o + 16*n16) (o 16-byte aligned) of the sequence into the packed tile.
-// codes32: as uint64 words the first base of each 32 sits in the MSBs; inv16 likewise for uint32 words.
-__device__ __forceinline__ void load_tile(const SketchArgs &a, uint32_t *codes32, uint16_t *inv16, uint64_t o, int n16) {
-    const uint64_t lim16 = (a.total_len + 15) >> 4;
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.seq);
-    for (int j = threadIdx.x; j < n16; j += SK_THREADS) {
-        const uint64_t g16 = (o >> 4) + j;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (g16 < lim16) v = __ldg(src + g16);
-        uint32_t c0, c1, c2, c3, i0, i1, i2, i3;
-        decode4(v.x, c0, i0); decode4(v.y, c1, i1); decode4(v.z, c2, i2); decode4(v.w, c3, i3);
-        codes32[j ^ 1] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
-        inv16[j ^ 1] = (uint16_t)((i0 << 12) | (i1 << 8) | (i2 << 4) | i3);
+// ---- packed tile -> shared memory ----------------------------------------------------------------------
+// copies words [o/32, o/32 + nw) of the packed batch (o a multiple of 32 bases) into the tile.
+// W: as uint64 words the first base of each 32 sits in the MSBs; M likewise for uint32 words.
+__device__ __forceinline__ void load_tile(const SketchArgs &a, uint64_t *W, uint32_t *M, uint64_t o, int nw) {
+    const uint64_t w0 = o >> 5;
+    for (int j = threadIdx.x; j < 2 * nw; j += SK_THREADS) {
+        if (j < nw) W[j] = __ldg(a.seq.codes + w0 + j);
+        else M[j - nw] = __ldg(a.seq.mask + w0 + (j - nw));
     }
 }
 
@@ -245,7 +223,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
             const int nstart = (int)min((uint64_t)SK_TILE, p1 - t0);  // start positions (= windows = new keys) in this tile
             const int npre = (WINDOWED && first) ? wsz - 1 : 0;        // keys before E0 this tile has to compute itself
             const uint64_t kb = WINDOWED ? (first ? t0 : t0 + (uint64_t)(wsz - 1)) : t0;   // first key / k-mer whose bases are needed
-            const uint64_t o = kb & ~15ULL;
+            const uint64_t o = kb & ~127ULL;
             const int off = (int)(kb - o);
             const int nbases = off + npre + nstart + k - 1;
             __syncthreads();                                          // previous tile fully consumed, its minimizers staged
@@ -254,7 +232,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
             if (WINDOWED && !first)                                   // carry the last wsz-1 keys of the previous (full) tile
                 for (int i = threadIdx.x; i < wsz - 1; i += SK_THREADS)
                     score[sk_pad(OFF - (wsz - 1) + i)] = score[sk_pad(OFF + SK_TILE - (wsz - 1) + i)];
-            load_tile(a, reinterpret_cast<uint32_t *>(W), reinterpret_cast<uint16_t *>(M), o, (nbases + 15) >> 4);
+            load_tile(a, W, M, o, ((nbases + 31) >> 5) + 2);   // + two words: tile_kmer / tile_invalid read past the last base
             __syncthreads();
             if (WINDOWED && threadIdx.x == 0) *scount = 0;
             if (!WINDOWED) {

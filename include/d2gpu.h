@@ -43,7 +43,8 @@ uint64_t d2g_launch_count(const d2g_ctx *ctx);
  * kernels on the ctx stream. d2g_get_timing synchronises, returns accumulated milliseconds and launch
  * count for one kernel class and resets that class. */
 enum { D2G_T_SKETCH_MAIN = 0, D2G_T_SKETCH_BOOT = 1, D2G_T_CMP = 2 /* the pair-comparison tile kernel */,
-       D2G_T_CMP_PREP = 3 /* order-code construction: keys, per-register sort, ranks */, D2G_T_NCLASSES = 4 };
+       D2G_T_CMP_PREP = 3 /* order-code construction: keys, per-register sort, ranks */,
+       D2G_T_PACK = 4 /* ASCII -> packed sequence (d2g_pack_dev) */, D2G_T_NCLASSES = 5 };
 int d2g_set_timing(d2g_ctx *ctx, int enabled);
 int d2g_get_timing(d2g_ctx *ctx, int kernel_class, double *ms_total, uint64_t *n_launches);
 
@@ -108,11 +109,41 @@ int d2g_distinct_kmers(d2g_ctx *ctx, const d2g_sketch_params *p,
 int d2g_opmh_finalize(const uint64_t *regs_u64, uint32_t n_entities, uint32_t sketchsize, double *sig_out, double *card_out);
 
 /* Same computation with inputs and outputs resident in device memory (asynchronous on
- * d2g_stream(ctx); no host copies).  seq_d must be readable for total_len rounded up to 16 bytes. */
+ * d2g_stream(ctx); no host copies).  seq_d holds total_len ASCII bytes; it is packed on the device first
+ * (d2g_pack_dev into ctx scratch) and the sketch kernels read the packed form. */
 int d2g_sketch_batch_dev(d2g_ctx *ctx, const d2g_sketch_params *p,
                          const char *seq_d, const uint64_t *rec_off_d, const uint32_t *rec_entity_d,
                          uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
                          uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d);
+
+/* ---- packed sequence: what the sketch kernels read, and what crosses PCIe ------------------------------------------
+ * A batch of n_bases record bytes is held as
+ *   codes : uint64[d2g_packed_words(n_bases)], word i = bases [32i, 32i+32), two bits per base, first base in bits 63:62
+ *           (A0 C1 G2 T3, case-insensitive: bonsai/include/bonsai/alphabet.h:128);
+ *   mask  : uint32[d2g_packed_words(n_bases)], word i = the same bases, one bit per base, first base in bit 31,
+ *           1 = not A/C/G/T (encoder.h:254 resets the k-mer run there; in windowed mode the k-mer becomes 0, :568-571).
+ * d2g_packed_words includes the padding the kernels rely on.  This replaces the byte-per-base hand-over at
+ * Encoder::for_each (bonsai/include/bonsai/encoder.h:511-530): a quarter of the bytes per base over PCIe. */
+uint64_t d2g_packed_words(uint64_t n_bases);
+/* Host packer (AVX-512 / AVX2 / scalar, all host threads the process may use; D2G_HOST_THREADS overrides): packs the
+ * concatenation of n_pieces ASCII pieces (records with line terminators already removed).  *n_invalid_words (optional)
+ * receives the number of words holding a non-ACGT base: when 0 the mask need not be passed on. */
+int d2g_pack_sequences(const char *const *pieces, const uint64_t *piece_len, uint64_t n_pieces,
+                       uint64_t *codes, uint32_t *mask, uint64_t *n_invalid_words);
+/* Device packer: total_len ASCII bytes at seq_d -> codes_d / mask_d (d2g_packed_words(total_len) words each); asynchronous. */
+int d2g_pack_dev(d2g_ctx *ctx, const char *seq_d, uint64_t total_len, uint64_t *codes_d, uint32_t *mask_d);
+/* d2g_sketch_batch with the sequence already packed by the caller (host memory; mask may be NULL when no base is invalid).
+ * d2g_sketch_batch itself packs its ASCII input chunk by chunk on the host threads into a pinned staging ring, so both
+ * calls move the same bytes; this one saves the pass over the ASCII when the caller packs while it parses. */
+int d2g_sketch_batch_packed(d2g_ctx *ctx, const d2g_sketch_params *p,
+                            const uint64_t *codes, const uint32_t *mask, const uint64_t *rec_off, const uint32_t *rec_entity,
+                            uint64_t n_rec, uint32_t n_entities,
+                            uint64_t *regs_u64_out, double *sig_out, double *card_out, uint64_t *ids_out,
+                            uint64_t *n_kmers_hashed);
+int d2g_sketch_batch_packed_dev(d2g_ctx *ctx, const d2g_sketch_params *p,
+                                const uint64_t *codes_d, const uint32_t *mask_d, const uint64_t *rec_off_d, const uint32_t *rec_entity_d,
+                                uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
+                                uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d);
 
 /* ------------------------------------------------------------------------------------------------
  * Compare path.  Replaces compare() (src/cmp_core.cpp:349-575), densify (:577-613) and the

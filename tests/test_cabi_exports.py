@@ -79,3 +79,66 @@ def test_front_end_fails_loudly_without_device(tmp_path):
     # option errors are reported before any device work
     r = subprocess.run([exe, "sketch", "--similarity-threshold", "0.5", str(fa)], capture_output=True, text=True)
     assert r.returncode != 0 and "not supported" in r.stderr
+
+
+def _pack_reference(data: bytes):
+    """numpy restatement of the packed layout (include/d2gpu.h): codes u64 words, first base in bits 63:62; mask u32, first base in bit 31."""
+    import numpy as np
+    from dashing2_b200 import capi
+    L = capi.load()
+    n = len(data)
+    nw = int(L.d2g_packed_words(n))
+    b = np.zeros(nw * 32, dtype=np.uint8)
+    b[:n] = np.frombuffer(data, dtype=np.uint8)
+    x = (b >> 1) & 3
+    code = (x ^ (x >> 1)).astype(np.uint64)
+    u = b & 0xDF
+    inv = ~((u == ord("A")) | (u == ord("C")) | (u == ord("G")) | (u == ord("T")))
+    sh = (np.uint64(62) - np.uint64(2) * np.arange(32, dtype=np.uint64))
+    codes = (code.reshape(nw, 32) << sh).sum(axis=1, dtype=np.uint64)
+    msh = (np.uint32(31) - np.arange(32, dtype=np.uint32))
+    mask = (inv.reshape(nw, 32).astype(np.uint32) << msh).sum(axis=1, dtype=np.uint32)
+    return codes, mask
+
+
+@pytest.mark.parametrize("isa", ["0", "1", "2"])
+def test_host_packer_matches_layout(isa):
+    """d2g_pack_sequences (scalar / AVX2 / AVX-512 paths, pieces of every alignment) against the numpy restatement."""
+    import subprocess, sys, textwrap
+    from dashing2_b200 import capi
+    if not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libd2gpu.so not built")
+    flags = open("/proc/cpuinfo").read()
+    if (isa == "2" and "avx512bw" not in flags) or (isa == "1" and "avx2" not in flags):
+        pytest.skip("ISA not available on this CPU")
+    # the ISA is latched on first use: run in a child with D2G_PACK_ISA set
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path[:0] = [%r, %r]
+        from dashing2_b200 import capi
+        from test_cabi_exports import _pack_reference
+        rng = np.random.default_rng(7)
+        for trial in range(6):
+            n_pieces = int(rng.integers(1, 40))
+            pieces = []
+            for i in range(n_pieces):
+                ln = int(rng.choice([0, 1, 5, 31, 32, 33, 63, 64, 65, 127, 1000, 4097, 70000, 1 << 21]))
+                alphabet = np.frombuffer(b"ACGTacgtNnRYKM-*\\x00", dtype=np.uint8) if (trial %% 2) else np.frombuffer(b"ACGT", dtype=np.uint8)
+                pr = np.full(len(alphabet), 0.02); pr[:4] = 1.0; pr /= pr.sum()
+                pieces.append(alphabet[rng.choice(len(alphabet), size=ln, p=pr)].tobytes())
+            codes, mask, nz = capi.pack_sequences(pieces)
+            data = b"".join(pieces)
+            ec, em = _pack_reference(data)
+            nreal = (len(data) + 31) // 32
+            assert np.array_equal(codes[:nreal], ec[:nreal]), trial
+            assert np.array_equal(mask[:nreal], em[:nreal]), trial
+            assert (mask[nreal:] == 0xFFFFFFFF).all() and (codes[nreal:] == 0).all()
+            inv = np.frombuffer(data, dtype=np.uint8) & 0xDF
+            bad = ~np.isin(inv, np.frombuffer(b"ACGT", dtype=np.uint8))
+            words_bad = len(np.unique(np.nonzero(bad)[0] // 32))
+            assert nz == words_bad, (nz, words_bad)
+        print("ok")
+    """) % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, D2G_PACK_ISA=isa, D2G_HOST_THREADS="4")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

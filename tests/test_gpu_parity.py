@@ -701,3 +701,50 @@ def test_topk_matches_oracle_seeded(n, S, K, measure, cmp_kind):
     ep, ei, ev = O.topk(regs, cards, K, measure, k=31, cmp_kind=cmp_kind)
     gp, gi, gv = ctx().lsh_topk(regs, cards, K, measure, k=31, cmp_kind=cmp_kind)
     assert np.array_equal(gp, ep) and np.array_equal(gi, ei) and np.array_equal(gv.view(np.uint32), ev.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,S,K", [(1300, 64, 500), (1400, 64, 1100)])
+def test_topk_large_k_matches_oracle(n, S, K):
+    """Candidate lists longer than 1536 entries (topk >= 440) need more dynamic shared memory than the default limit in the
+    query kernel, and lists above 512 take the per-thread replay path; both against the oracle."""
+    from dashing2_b200 import synth
+    regs, cards = synth.synthetic_sketches(n, S, seed=n + K, n_families=3, p_lo=0.02, p_hi=0.5)
+    ep, ei, ev = O.topk(regs, cards, K, "similarity", k=31)
+    gp, gi, gv = ctx().lsh_topk(regs, cards, K, "similarity", k=31)
+    assert np.array_equal(gp, ep) and np.array_equal(gi, ei) and np.array_equal(gv.view(np.uint32), ev.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode,S,w", [("opmh", 1024, -1), ("fss", 512, 51), ("opmh", 256, 40)])
+def test_packed_entry_points_equal_ascii_entry_point(mode, S, w, golden_inputs):
+    """d2g_pack_sequences + d2g_sketch_batch_packed (with and without the mask) and the device packer behind
+    d2g_sketch_batch_dev give the registers of d2g_sketch_batch on the golden FASTA fixtures (N runs, lower case, short records)."""
+    import torch
+    from dashing2_b200 import capi
+    names, paths = golden_inputs
+    recs = [O.read_fastx(p) for p in paths]
+    seq, off, ent = pack_batch(recs)
+    c = ctx()
+    p = c.params(mode=mode, S=S, k=31, w=w)
+    a = c.sketch_batch(seq, off, ent, len(recs), p)
+    codes, mask, nz = capi.pack_sequences([r for rr in recs for r in rr])
+    assert nz > 0                                            # adv.fa holds N runs
+    b = c.sketch_batch_packed(codes, mask, off, ent, len(recs), p)
+    assert np.array_equal(u64(a["sig"]), u64(b["sig"])) and np.array_equal(u64(a["card"]), u64(b["card"]))
+    # a batch without invalid bases may drop the mask
+    clean = [np.frombuffer(r, dtype=np.uint8) for rr in recs[:3] for r in rr]
+    clean = [x[np.isin(x & 0xDF, np.frombuffer(b"ACGT", dtype=np.uint8))].tobytes() for x in clean]
+    seq2, off2, ent2 = pack_batch([[x] for x in clean])
+    codes2, mask2, nz2 = capi.pack_sequences(clean)
+    assert nz2 == 0
+    a2 = c.sketch_batch(seq2, off2, ent2, len(clean), p)
+    b2 = c.sketch_batch_packed(codes2, None, off2, ent2, len(clean), p)
+    assert np.array_equal(u64(a2["sig"]), u64(b2["sig"]))
+    # device packer == host packer, word for word
+    dev = torch.device("cuda", 0)
+    t_seq = torch.from_numpy(np.concatenate([seq, np.zeros(64, np.uint8)])).to(dev)
+    nw = len(codes)
+    t_codes = torch.empty(nw, dtype=torch.int64, device=dev); t_mask = torch.empty(nw, dtype=torch.int32, device=dev)
+    c.pack_dev(t_seq.data_ptr(), len(seq), t_codes.data_ptr(), t_mask.data_ptr())
+    c.sync()
+    assert np.array_equal(t_codes.cpu().numpy().view(np.uint64), codes)
+    assert np.array_equal(t_mask.cpu().numpy().view(np.uint32), mask)
