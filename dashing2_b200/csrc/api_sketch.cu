@@ -46,7 +46,7 @@ int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &se
     const bool windowed = p->w > p->k;
     d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m, rg);
     d2g::OpmhConsumer::Params cp{regs_d, d2g::make_fastmod32(m), m};
-    return launch_sketch<d2g::OpmhConsumer>(c, a, cp, windowed);
+    return windowed ? launch_sketch_windowed_set<d2g::OpmhConsumer>(c, a, cp) : launch_sketch<d2g::OpmhConsumer>(c, a, cp, false);
 }
 
 // Full SetSketch (see fss_kernels.cuh): boot -> threshold -> main -> long walks -> finalize.
@@ -84,7 +84,7 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq
         d2g::fss_guess_kernel<<<(n_ent + 255) / 256, 256, 0, c->stream>>>(npos, n_ent, m, wsz, getenv("D2G_FSS_NO_GUESS") ? 0 : 1, T, Tguess, state);
         c->launches += 2;
         a.ent_state = state; a.want_state = 0;
-        if (int rc = launch_sketch<d2g::FssMainConsumer>(c, a, mp, windowed)) return rc;
+        if (int rc = windowed ? launch_sketch_windowed_set<d2g::FssMainConsumer>(c, a, mp) : launch_sketch<d2g::FssMainConsumer>(c, a, mp, false)) return rc;
         d2g::fss_verify_kernel<<<n_ent, 256, 0, c->stream>>>(keys, m, Tguess, state, n_redo);
         c->launches++;
         unsigned int h_redo = 0;
@@ -111,7 +111,7 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq
             d2g::fss_threshold_kernel<<<n_ent, 256, 0, c->stream>>>(maxrv, m, T, state);
             c->launches++;
             a.tile_stride = 1;
-            if (int rc = launch_sketch<d2g::FssMainConsumer>(c, a, mp, windowed)) return rc;
+            if (int rc = windowed ? launch_sketch_windowed_set<d2g::FssMainConsumer>(c, a, mp) : launch_sketch<d2g::FssMainConsumer>(c, a, mp, false)) return rc;
         }
         // long walks (normally none): dense permutation state per thread slot
         uint64_t nslots = std::min<uint64_t>(4096, (256ULL << 20) / ((uint64_t)m * 8));

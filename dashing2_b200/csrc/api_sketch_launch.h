@@ -2,6 +2,7 @@
 #pragma once
 #include "api_internal.h"
 #include "sketch_kernels.cuh"
+#include "sketch_fast.cuh"
 
 namespace {
 uint64_t pick_span(const d2g_ctx *c, uint64_t total_len, uint32_t m) {
@@ -21,6 +22,8 @@ d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, c
     a.seq = seq_d; a.rec_off = rec_off_d; a.rec_entity = rec_ent_d;
     a.n_rec = n_rec; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
     a.pos_base = rg.pos_base; a.pos_end = rg.pos_end; a.ent_base = rg.ent_base; a.ent_state = nullptr; a.want_state = 0;
+    a.keymask = 0xFFFFFFFFu;
+    if (const char *ev = getenv("D2G_FAST_KEYMASK")) a.keymask = (uint32_t)strtoul(ev, nullptr, 0);   // test knob
     a.m = m; a.tile_stride = 1; a.score_slots = d2g::sketch_score_slots(p->k, p->w);
     a.span = pick_span(c, rg.pos_end - rg.pos_base, m);
     return a;
@@ -41,6 +44,53 @@ int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer:
     }
     c->launches++;
     CU(cudaGetLastError());
+    return D2G_OK;
+}
+
+// Windowed set sketches take the 32-bit-key kernel (sketch_fast.cuh) followed by the exact kernel over the tiles the fast pass put
+// on its redo list (normally none); everything else takes the exact kernel.  D2G_NO_FAST=1 forces the exact kernel (test knob).
+inline bool sketch_fast_eligible(const d2g::SketchArgs &a) {
+    const int wsz = a.w - a.k + 1;
+    return a.w > a.k && a.canon && wsz >= 2 && wsz <= d2g::SF_MAX_WSZ && a.tile_stride == 1 && !getenv("D2G_NO_FAST");
+}
+constexpr uint64_t kRedoCap = 1ULL << 16;
+
+template <class Consumer>
+int launch_sketch_windowed_set(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer::Params &cp, int tcls = D2G_T_SKETCH_MAIN) {
+    if (!sketch_fast_eligible(a)) return launch_sketch<Consumer>(c, a, cp, true, tcls);
+    if (int rc = c->redo.reserve((kRedoCap + 2) * 8)) return rc;
+    unsigned long long *redo_count = c->redo.as<unsigned long long>();
+    uint64_t *redo_list = c->redo.as<uint64_t>() + 2;
+    CU(cudaMemsetAsync(redo_count, 0, 16, c->stream));
+    const size_t cbytes = Consumer::smem_bytes(a.m, true);
+    const size_t smem = d2g::sketch_fast_smem_bytes(cbytes);
+    if (smem > 200 * 1024) return launch_sketch<Consumer>(c, a, cp, true, tcls);
+    const uint64_t grid = (a.pos_end - a.pos_base + a.span - 1) / a.span;
+    const d2g::FastAux fx{redo_count, redo_list, kRedoCap};
+    {
+        KernelTimer kt(c, tcls);
+        if (a.w - a.k + 1 == 21) {
+            CU(cudaFuncSetAttribute(d2g::sketch_fast_kernel<21, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            d2g::sketch_fast_kernel<21, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp, fx);
+        } else {
+            CU(cudaFuncSetAttribute(d2g::sketch_fast_kernel<0, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            d2g::sketch_fast_kernel<0, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp, fx);
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    // exact pass over the listed tiles; the grid is fixed (the count stays on the device) and returns at once when the list is empty
+    const size_t smem_x = d2g::sketch_smem_bytes<Consumer>(a.m, a.score_slots);
+    CU(cudaFuncSetAttribute(d2g::sketch_redo_kernel<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+    d2g::sketch_redo_kernel<Consumer><<<(unsigned)(c->sm_count * 2), d2g::SK_THREADS, smem_x, c->stream>>>(a, cp, redo_list, redo_count, kRedoCap);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (getenv("D2G_DEBUG")) {
+        unsigned long long h = 0;
+        cudaMemcpyAsync(&h, redo_count, 8, cudaMemcpyDeviceToHost, c->stream); cudaStreamSynchronize(c->stream);
+        fprintf(stderr, "[d2g] fast windowed kernel: %llu tile(s) recomputed by the exact kernel (of %llu)\n", h,
+                (unsigned long long)((a.pos_end - a.pos_base + d2g::SF_TILE - 1) / d2g::SF_TILE));
+    }
     return D2G_OK;
 }
 } // namespace

@@ -46,6 +46,7 @@ struct SketchArgs {
     uint32_t m;                  // registers per entity
     uint32_t tile_stride;        // process only tiles whose global index % tile_stride == 0 (sampling); 1 = all
     uint32_t score_slots;        // shared-memory window-key slots (windowed mode): sk_pad(SK_TILE + w - k + 1) + 1
+    uint32_t keymask;            // fast windowed kernel: bits of the 32-bit window key that take part (all; fewer only to provoke ties in tests)
 };
 
 // ---- packed tile -> shared memory ----------------------------------------------------------------------
@@ -150,27 +151,14 @@ __device__ __forceinline__ uint32_t kmers8(const uint64_t *W, const uint32_t *M,
 // ---- the kernel ---------------------------------------------------------------------------------
 constexpr int SK_SCAP = 512;   // staged window minima per tile (expected ~2/(wsz+1) of the tile); the rest take the direct path
 
+// ---- one span of start positions [span_lo, span_hi) -----------------------------------------------------
+// All threads of the CTA; the consumer is initialised by the caller and is flushed at the end of the span.
 template <bool WINDOWED, class Consumer>
-__global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
-sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons, uint64_t *W, uint32_t *M, uint64_t *score, uint64_t *stage, int *scount,
+                                            const uint64_t span_lo, const uint64_t span_hi) {
     const int k = a.k;
     const int need = WINDOWED ? a.w : a.k;           // bases a start position needs to its right
     const int wsz = WINDOWED ? (a.w - a.k + 1) : 1;  // k-mers per window
-    uint64_t *W = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *M = reinterpret_cast<uint32_t *>(W + SK_NWORDS);
-    uint64_t *score = reinterpret_cast<uint64_t *>(M + SK_NWORDS + (SK_NWORDS & 1));
-    uint64_t *stage = score + (WINDOWED ? a.score_slots : 0);
-    int *scount = reinterpret_cast<int *>(stage + (WINDOWED ? SK_SCAP : 0));
-    unsigned char *csmem = reinterpret_cast<unsigned char *>(scount + (WINDOWED ? 2 : 0));
-    Consumer cons;
-    cons.init(csmem, cp, WINDOWED);
-    if (WINDOWED && threadIdx.x == 0) *scount = 0;
-
-    const uint64_t span_lo = a.pos_base + (uint64_t)blockIdx.x * a.span;
-    const uint64_t span_hi = min(span_lo + a.span, a.pos_end);
-    if (span_lo >= span_hi) return;
-
     // first record whose end lies beyond span_lo (records are sorted by offset)
     uint64_t lo = 0, hi = a.n_rec;
     while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (a.rec_off[mid + 1] > span_lo) hi = mid; else lo = mid + 1; }
@@ -371,6 +359,59 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
         __syncthreads();
         drain_stage();
         cons.flush(cur_ent);
+    }
+}
+
+// ---- the kernels ---------------------------------------------------------------------------------
+struct SketchSmem { uint64_t *W; uint32_t *M; uint64_t *score, *stage; int *scount; unsigned char *csmem; };
+template <bool WINDOWED>
+__device__ __forceinline__ SketchSmem sketch_smem_carve(unsigned char *smem_raw, const SketchArgs &a) {
+    SketchSmem s;
+    s.W = reinterpret_cast<uint64_t *>(smem_raw);
+    s.M = reinterpret_cast<uint32_t *>(s.W + SK_NWORDS);
+    s.score = reinterpret_cast<uint64_t *>(s.M + SK_NWORDS + (SK_NWORDS & 1));
+    s.stage = s.score + (WINDOWED ? a.score_slots : 0);
+    s.scount = reinterpret_cast<int *>(s.stage + (WINDOWED ? SK_SCAP : 0));
+    s.csmem = reinterpret_cast<unsigned char *>(s.scount + (WINDOWED ? 2 : 0));
+    return s;
+}
+
+template <bool WINDOWED, class Consumer>
+__global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
+sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SketchSmem s = sketch_smem_carve<WINDOWED>(smem_raw, a);
+    Consumer cons;
+    cons.init(s.csmem, cp, WINDOWED);
+    if (WINDOWED && threadIdx.x == 0) *s.scount = 0;
+    const uint64_t span_lo = a.pos_base + (uint64_t)blockIdx.x * a.span;
+    const uint64_t span_hi = min(span_lo + a.span, a.pos_end);
+    if (span_lo >= span_hi) return;
+    sketch_span<WINDOWED>(a, cons, s.W, s.M, s.score, s.stage, s.scount, span_lo, span_hi);
+}
+
+// The exact kernel over a LIST of tiles: tile_list[i] is the first start position of a tile of SK_TILE positions that the fast
+// windowed kernel (sketch_fast.cuh) could not finish exactly (a 32-bit key tie between different k-mers, an event list overflow).
+// Set sketches are idempotent minima, so recomputing all windows of those tiles on top of what the fast kernel delivered is exact.
+// When the list overflowed (count > cap) every tile of [pos_base, pos_end) is recomputed.
+template <class Consumer>
+__global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
+sketch_redo_kernel(const SketchArgs a, const typename Consumer::Params cp, const uint64_t *tile_list, const unsigned long long *tile_count, uint64_t cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned long long cnt = *tile_count;
+    if (cnt == 0) return;
+    const SketchSmem s = sketch_smem_carve<true>(smem_raw, a);
+    Consumer cons;
+    cons.init(s.csmem, cp, true);
+    const bool all = cnt > cap;
+    const uint64_t n = all ? (a.pos_end - a.pos_base + SK_TILE - 1) / SK_TILE : (uint64_t)cnt;
+    for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint64_t lo = all ? a.pos_base + i * SK_TILE : tile_list[i];
+        const uint64_t hi = min(lo + (uint64_t)SK_TILE, a.pos_end);
+        __syncthreads();
+        if (threadIdx.x == 0) *s.scount = 0;
+        __syncthreads();
+        if (lo < hi) sketch_span<true>(a, cons, s.W, s.M, s.score, s.stage, s.scount, lo, hi);
     }
 }
 

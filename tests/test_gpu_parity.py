@@ -748,3 +748,131 @@ def test_packed_entry_points_equal_ascii_entry_point(mode, S, w, golden_inputs):
     c.sync()
     assert np.array_equal(t_codes.cpu().numpy().view(np.uint64), codes)
     assert np.array_equal(t_mask.cpu().numpy().view(np.uint32), mask)
+
+
+# ---- the 32-bit-key windowed kernel (csrc/sketch_fast.cuh) against the exact kernel and the oracle ------------------------
+def _fast_inputs(seed, n_long=3, length=260_000):
+    """Entities that exercise every path of the fast windowed kernel: multi-tile random genomes with N runs / lower case /
+    several records, homopolymer and short-period repeats (every window ties with its predecessor), a record exactly one
+    window long, records shorter than the window, an empty entity."""
+    from dashing2_b200 import synth
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    files = []
+    for g, s in synth.family_genomes(n_long, length, seed=seed):
+        b = bytearray(s.tobytes())
+        for p in rng.integers(0, len(b), 10):
+            b[p] = ord("N")
+        p = int(rng.integers(1000, len(b) - 5000)); b[p:p + 700] = b"N" * 700            # an N run longer than a window
+        for p in rng.integers(0, len(b), 100):
+            b[p] |= 0x20
+        cut = sorted(int(x) for x in rng.integers(1, len(b) - 1, 2))
+        files.append([bytes(b[:cut[0]]), bytes(b[cut[0]:cut[1]]), bytes(b[cut[1]:])])
+    files.append([b"A" * 9000 + acgt[rng.integers(0, 4, 5000)].tobytes() + b"AC" * 4000 + b"ACG" * 3000 + b"T" * 2100])
+    unit = acgt[rng.integers(0, 4, 13)].tobytes()
+    files.append([unit * 700, acgt[rng.integers(0, 4, 3000)].tobytes()])
+    files.append([acgt[rng.integers(0, 4, 51)].tobytes(), acgt[rng.integers(0, 4, 50)].tobytes(), acgt[rng.integers(0, 4, 52)].tobytes()])
+    files.append([])
+    return files
+
+
+def _oracle_regs(mode, S, k, w, recs):
+    L = O.lib()
+    hv = [O.hash_stream(x, k, w) for x in recs]
+    hv = np.concatenate(hv) if hv else np.empty(0, dtype=np.uint64)
+    if mode == "opmh":
+        m = L.d2o_opmh_m(S)
+        regs = np.empty(m, dtype=np.uint64); cnt = np.empty(m, dtype=np.float64)
+        L.d2o_opmh_reset(regs, cnt, m); L.d2o_opmh_update(regs, cnt, m, hv, len(hv))
+        return regs
+    regs = np.empty(2 * S - 1, dtype=np.float64)
+    L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), None)
+    return regs[:S]
+
+
+@pytest.mark.parametrize("mode,S,k,w", [("opmh", 1024, 31, 51), ("fss", 1024, 31, 51), ("opmh", 256, 21, 40), ("fss", 256, 31, 33),
+                                         ("opmh", 512, 31, 93), ("opmh", 128, 17, 24), ("fss", 64, 32, 70), ("opmh", 64, 31, 32)])
+def test_fast_windowed_kernel_matches_oracle_and_exact_kernel(mode, S, k, w, monkeypatch):
+    files = _fast_inputs(900 + S + w)
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    p = c.params(mode=mode, S=S, k=k, w=w)
+    fast = c.sketch_batch(seq, off, ent, len(files), p)
+    key = "regs_u64" if mode == "opmh" else "sig"
+    for e, recs in enumerate(files):
+        assert np.array_equal(u64(fast[key][e]), u64(_oracle_regs(mode, S, k, w, recs))), (mode, S, k, w, e)
+    monkeypatch.setenv("D2G_NO_FAST", "1")
+    exact = c.sketch_batch(seq, off, ent, len(files), p)
+    assert np.array_equal(u64(fast[key]), u64(exact[key])) and np.array_equal(u64(fast["card"]), u64(exact["card"]))
+
+
+@pytest.mark.parametrize("keymask", ["0xFFF00000", "0xFF000000", "0xC0000000", "0"])
+@pytest.mark.parametrize("mode,S,w", [("opmh", 512, 51), ("fss", 256, 51), ("opmh", 256, 38)])
+def test_fast_windowed_kernel_key_ties_are_resolved_exactly(mode, S, w, keymask, monkeypatch):
+    """With only a few bits of the window key taking part, equal keys of different k-mers are everywhere: the scan has to pick
+    the minimizer by the full score and the redo list has to catch minimizer changes the truncated keys cannot see; with mask 0
+    every window is an event, the lists overflow and every tile is recomputed.  Registers must not change."""
+    files = _fast_inputs(17 + S + w, n_long=2, length=120_000)
+    c = ctx()
+    seq, off, ent = pack_batch(files)
+    p = c.params(mode=mode, S=S, k=31, w=w)
+    ref = c.sketch_batch(seq, off, ent, len(files), p)
+    monkeypatch.setenv("D2G_FAST_KEYMASK", keymask)
+    got = c.sketch_batch(seq, off, ent, len(files), p)
+    key = "regs_u64" if mode == "opmh" else "sig"
+    assert np.array_equal(u64(got[key]), u64(ref[key]))
+    for e, recs in enumerate(files[:2]):
+        assert np.array_equal(u64(got[key][e]), u64(_oracle_regs(mode, S, 31, w, recs)))
+
+
+def _frev64_inv(s):
+    M = (1 << 64) - 1
+    imul = pow(0x9a98567ed20c127d | 1, -1, 1 << 64)
+    s ^= 0x691a9d706391077a
+    s = ((s >> 31) | (s << 33)) & M
+    s = (s * imul) & M
+    return s ^ 0x533f8c2151b20f97
+
+
+def _kmer_str(x, k):
+    return "".join("ACGT"[(x >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def _revcomp_int(x, k):
+    r = 0
+    for i in range(k):
+        r = (r << 2) | (3 - ((x >> (2 * i)) & 3))
+    return r
+
+
+def test_fast_windowed_kernel_real_32bit_key_tie():
+    """Two different canonical 31-mers whose scores agree in the high 32 bits (and are smaller than everything around them), planted
+    a few positions apart in random sequence in both orders: the window minimum changes from one to the other without the 32-bit
+    minimum changing.  OPMH registers against the oracle."""
+    k, w, S = 31, 51, 256
+    rng = np.random.default_rng(5)
+    found = []
+    hi = 3                                            # a tiny score: the minimizer of every window that holds it
+    lo = 1
+    while len(found) < 2:
+        x = _frev64_inv((hi << 32) | lo)
+        lo += 1
+        if x >> 62 or x > _revcomp_int(x, k):
+            continue
+        s = _kmer_str(x, k)
+        if any(s[i:] == s[:-i] for i in range(1, 8)):   # no short self-overlap: planting must not create further copies
+            continue
+        found.append(s)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs = []
+    for order in ((0, 1), (1, 0)):
+        for gap in (1, 5, 19):
+            left = acgt[rng.integers(0, 4, 3000 + 7 * gap)].tobytes().decode()
+            mid = acgt[rng.integers(0, 4, gap)].tobytes().decode()
+            right = acgt[rng.integers(0, 4, 2500)].tobytes().decode()
+            recs.append((left + found[order[0]] + mid + found[order[1]] + right).encode())
+    c = ctx()
+    seq, off, ent = pack_batch([[r] for r in recs])
+    got = c.sketch_batch(seq, off, ent, len(recs), c.params(mode="opmh", S=S, k=k, w=w))
+    for e, r in enumerate(recs):
+        assert np.array_equal(got["regs_u64"][e], _oracle_regs("opmh", S, k, w, [r])), e
