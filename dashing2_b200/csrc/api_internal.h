@@ -51,7 +51,7 @@ struct d2g_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::atomic<uint64_t> launches{0};
-    DevBuf seq, pcodes, pmask, recoff, recent, regs, sig, card, ids, aux, aux2, redo;   // sketch scratch (pcodes / pmask: the packed batch)
+    DevBuf seq, pcodes, pmask, recoff, recent, regs, sig, card, ids, aux, aux2, redo, ovfq;   // sketch scratch (pcodes / pmask: the packed batch)
     PinBuf stage[3]; cudaEvent_t stage_free[3] = {nullptr, nullptr, nullptr};        // pinned staging ring of the host packer
     DevBuf wbuf, wtmp, lbuf;                                              // counting scratch (BagMinHash / ProbMinHash)
     DevBuf cregs, ccards, cout, clut, clut80, ctmp, cktmp;         // compare scratch

@@ -49,8 +49,14 @@ int launch_opmh(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &se
     return windowed ? launch_sketch_windowed_set<d2g::OpmhConsumer>(c, a, cp) : launch_sketch<d2g::OpmhConsumer>(c, a, cp, false);
 }
 
-// Full SetSketch (see fss_kernels.cuh): boot -> threshold -> main -> long walks -> finalize.
-// sig_d [n_ent][S] / card_d [n_ent] may be null.  Synchronises the stream to check the long-walk queue.
+// Full SetSketch (see fss_kernels.cuh): guessed bound -> main -> verify; entities that fail (or are too small to guess for) take
+// boot -> threshold -> main; walks that outrun the sparse permutation state go through the long-walk queue.
+// sig_d [n_ent][S] / card_d [n_ent] may be null.  Synchronises the stream (it reads the verify / queue counters back).
+//
+// The long-walk queue holds at most one entry per k-mer position, so it is sized from the positions of the entities that can
+// reach it, and those entities are processed in groups when that is more than the queue budget (D2G_FSS_QUEUE_ELEMS, default
+// 2^27 entries = 2 GiB): read sets sketched with a large S (every element of a record with fewer than ~m ln m elements walks all m
+// registers, in the reference too: src/setsketch.h:369-423) are slow, not refused.
 int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d,
                const SketchRange *range = nullptr) {
@@ -59,44 +65,119 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq
     const uint64_t work_len = rg.pos_end > rg.pos_base ? rg.pos_end - rg.pos_base : 0;
     const uint32_t m = p->sketchsize;
     const uint64_t nreg = (uint64_t)n_ent * m;
-    const uint64_t ovf_cap = 1ULL << 20;
-    // aux layout: maxrv[nreg] | keys[nreg] | T[n_ent] | Tguess[n_ent] | npos[n_ent] | state[n_ent] (u32, padded) | ovf_count, n_redo | ovf[2*ovf_cap]
-    const size_t aux_bytes = (nreg * 2 + (uint64_t)n_ent * 4 + 4 + 2 * ovf_cap) * 8;
+    const uint64_t small_cap = 1ULL << 16;            // queue of the guessed pass: its walks are short by construction
+    // aux layout: maxrv[nreg] | keys[nreg] | T[n_ent] | Tguess[n_ent] | npos[n_ent] | state[n_ent] (u32) | gstate[n_ent] (u32) | ovf_count, n_redo | ovf[2*small_cap]
+    const uint64_t n_ent2 = ((uint64_t)n_ent + 1) / 2;   // u64 slots for n_ent u32
+    const size_t aux_bytes = (nreg * 2 + (uint64_t)n_ent * 3 + 2 * n_ent2 + 4 + 2 * small_cap) * 8;
     if (int rc = c->aux.reserve(aux_bytes)) return rc;
     uint64_t *maxrv = c->aux.as<uint64_t>(), *keys = maxrv + nreg;
     double *T = reinterpret_cast<double *>(keys + nreg), *Tguess = T + n_ent;
     unsigned long long *npos = reinterpret_cast<unsigned long long *>(Tguess + n_ent);
     uint32_t *state = reinterpret_cast<uint32_t *>(npos + n_ent);
-    unsigned long long *ovf_count = reinterpret_cast<unsigned long long *>(npos + 2 * (uint64_t)n_ent);
+    uint32_t *gstate = reinterpret_cast<uint32_t *>(npos + n_ent + n_ent2);
+    unsigned long long *ovf_count = reinterpret_cast<unsigned long long *>(npos + n_ent + 2 * n_ent2);
     unsigned int *n_redo = reinterpret_cast<unsigned int *>(ovf_count + 1);
-    uint64_t *ovf = reinterpret_cast<uint64_t *>(ovf_count + 4);
-    CU(cudaMemsetAsync(npos, 0, (uint64_t)n_ent * 8, c->stream));
-    CU(cudaMemsetAsync(ovf_count, 0, 32, c->stream));
-    fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, c->stream>>>(keys, nreg, d2g::FSS_KEY_EMPTY);
+    uint64_t *ovf_small = reinterpret_cast<uint64_t *>(ovf_count + 4);
+    cudaStream_t st = c->stream;
+    CU(cudaMemsetAsync(npos, 0, (uint64_t)n_ent * 8, st));
+    CU(cudaMemsetAsync(ovf_count, 0, 32, st));
+    fill_u64_kernel<<<(unsigned)std::min<uint64_t>((nreg + 255) / 256, 4096), 256, 0, st>>>(keys, nreg, d2g::FSS_KEY_EMPTY);
     c->launches++;
     const bool windowed = p->w > p->k;
+    const bool debug = getenv("D2G_DEBUG") != nullptr;
+    uint64_t total_long = 0;
+
+    // the queued walks: one thread per element with a dense permutation state in scratch (2 m u32 per slot)
+    auto run_longwalk = [&](const uint64_t *ovf, uint64_t cap, unsigned long long h_q, bool ids) -> int {
+        if (h_q > cap) return fail(D2G_ECUDA, "Full SetSketch: long-walk queue overflow (%llu entries, room for %llu)", h_q, (unsigned long long)cap);
+        if (!h_q) return D2G_OK;
+        total_long += h_q;
+        const uint64_t max_slots = std::max<uint64_t>(32, std::min<uint64_t>(65536, (2048ULL << 20) / ((uint64_t)m * 8)) / 32 * 32);
+        const uint64_t nslots = std::min<uint64_t>(max_slots, (h_q + 31) / 32 * 32);
+        if (int rc = c->aux2.reserve(nslots * 2ULL * m * 4)) return rc;
+        CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, st));
+        if (ids) d2g::fss_longwalk_ids_kernel<<<(unsigned)(nslots / 32), 32, 0, st>>>(ovf, ovf_count, cap, m, T, keys, ids_d, c->aux2.as<uint32_t>());
+        else d2g::fss_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, st>>>(ovf, ovf_count, cap, m, T, keys, c->aux2.as<uint32_t>());
+        c->launches++;
+        CU(cudaGetLastError());
+        return D2G_OK;
+    };
+    auto read_queue = [&](unsigned long long *h_q) -> int {
+        CU(cudaMemcpyAsync(h_q, ovf_count, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return D2G_OK;
+    };
+    // Consecutive entities selected by `take`, in groups whose positions fit the queue budget; for each group gstate = 1 exactly on its
+    // entities and body(queue, cap) runs the passes that may fill the queue.
+    uint64_t budget = 1ULL << 27;
+    if (const char *ev = getenv("D2G_FSS_QUEUE_ELEMS")) budget = std::max<uint64_t>(1024, strtoull(ev, nullptr, 10));
+    std::vector<unsigned long long> h_npos;
+    auto for_groups = [&](const std::vector<char> &take, auto &&body) -> int {
+        if (h_npos.empty()) {
+            h_npos.resize(n_ent);
+            CU(cudaMemcpyAsync(h_npos.data(), npos, (uint64_t)n_ent * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        std::vector<uint32_t> hg(n_ent);
+        uint32_t e = 0;
+        while (e < n_ent) {
+            while (e < n_ent && !take[e]) ++e;
+            if (e >= n_ent) break;
+            std::fill(hg.begin(), hg.end(), 0u);
+            uint64_t sum = 0; uint32_t cnt = 0;
+            for (; e < n_ent; ++e) {
+                if (!take[e]) continue;
+                if (cnt && sum + h_npos[e] > budget) break;
+                hg[e] = 1; sum += h_npos[e]; ++cnt;
+            }
+            // an element is queued at most once per pass over its tile (the fast windowed kernel may hand a tile to the exact kernel: twice)
+            const uint64_t cap = std::min<uint64_t>(2 * sum + 1024, 2 * budget + 1024);
+            if (int rc = c->ovfq.reserve(2 * cap * 8)) return rc;
+            CU(cudaMemcpyAsync(gstate, hg.data(), (uint64_t)n_ent * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemsetAsync(ovf_count, 0, 8, st));
+            if (int rc = body(c->ovfq.as<uint64_t>(), cap)) return rc;
+            CU(cudaStreamSynchronize(st));                // hg is reused by the next group
+        }
+        return D2G_OK;
+    };
+
     if (work_len && n_rec) {
         d2g::SketchArgs a = make_sketch_args(c, p, seq_d, rec_off_d, rec_ent_d, n_rec, total_len, m, rg);
         const int wsz = windowed ? p->w - p->k + 1 : 1;
-        d2g::FssMainConsumer::Params mp{keys, T, ovf, ovf_count, ovf_cap, m};
         // Pass A: bound guessed from the sequence length, verified afterwards (fss_kernels.cuh); only inputs with many elements per register
-        d2g::fss_entity_positions_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, c->stream>>>(rec_off_d, rec_ent_d, n_rec, rg.ent_base, windowed ? p->w : p->k, npos);
-        d2g::fss_guess_kernel<<<(n_ent + 255) / 256, 256, 0, c->stream>>>(npos, n_ent, m, wsz, getenv("D2G_FSS_NO_GUESS") ? 0 : 1, T, Tguess, state);
+        d2g::fss_entity_positions_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(rec_off_d, rec_ent_d, n_rec, rg.ent_base, windowed ? p->w : p->k, npos);
+        d2g::fss_guess_kernel<<<(n_ent + 255) / 256, 256, 0, st>>>(npos, n_ent, m, wsz, getenv("D2G_FSS_NO_GUESS") ? 0 : 1, T, Tguess, state);
         c->launches += 2;
-        a.ent_state = state; a.want_state = 0;
-        if (int rc = windowed ? launch_sketch_windowed_set<d2g::FssMainConsumer>(c, a, mp) : launch_sketch<d2g::FssMainConsumer>(c, a, mp, false)) return rc;
-        d2g::fss_verify_kernel<<<n_ent, 256, 0, c->stream>>>(keys, m, Tguess, state, n_redo);
+        {
+            d2g::FssMainConsumer::Params mp{keys, T, ovf_small, ovf_count, small_cap, m};
+            a.ent_state = state; a.want_state = 0;
+            if (int rc = windowed ? launch_sketch_windowed_set<d2g::FssMainConsumer>(c, a, mp) : launch_sketch<d2g::FssMainConsumer>(c, a, mp, false)) return rc;
+        }
+        unsigned long long h_cnt[2] = {0, 0};            // queue entries of the guessed pass, entities that failed
+        CU(cudaMemcpyAsync(&h_cnt[0], ovf_count, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (h_cnt[0] > small_cap) {
+            // more long walks than the guessed pass has room for (the length-based estimate was far off): fail every guess, the
+            // entities are redone below with a queue sized for them
+            CU(cudaMemsetAsync(Tguess, 0xFF, (uint64_t)n_ent * 8, st));
+        } else if (int rc = run_longwalk(ovf_small, small_cap, h_cnt[0], false)) return rc;
+        d2g::fss_verify_kernel<<<n_ent, 256, 0, st>>>(keys, m, Tguess, state, n_redo);
         c->launches++;
         unsigned int h_redo = 0;
-        CU(cudaMemcpyAsync(&h_redo, n_redo, 4, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        if (getenv("D2G_DEBUG")) fprintf(stderr, "[d2g] fss: %u of %u entities take the boot pass\n", h_redo, n_ent);
+        CU(cudaMemcpyAsync(&h_redo, n_redo, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (debug) fprintf(stderr, "[d2g] fss: %u of %u entities take the boot pass\n", h_redo, n_ent);
         if (h_redo) {
             // Pass B (small inputs, failed guesses): boot on every stride-th tile gives a first bound T per entity so the first
             // walks of the main pass are short; the main kernel keeps tightening it.  n_eff = elements fed to the sketch per
             // entity (with minimizer windows only ~2/(window+1) of the positions emit).  Cost model per position: 1/stride for
             // the boot pass plus the extra walkers a looser threshold admits => stride ~ sqrt(n_eff / (2 m ln m)).
-            CU(cudaMemsetAsync(maxrv, 0, nreg * 8, c->stream));
+            std::vector<uint32_t> h_state(n_ent);
+            CU(cudaMemcpyAsync(h_state.data(), state, (uint64_t)n_ent * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            std::vector<char> take(n_ent);
+            for (uint32_t e = 0; e < n_ent; ++e) take[e] = h_state[e] == 1;
+            CU(cudaMemsetAsync(maxrv, 0, nreg * 8, st));
             const double per_ent = (double)work_len / std::max(1u, n_ent);
             const double n_eff = windowed ? per_ent * 2. / (p->w - p->k + 2) : per_ent;
             const double mlnm = (double)m * std::log((double)m + 2.);
@@ -105,54 +186,48 @@ int launch_fss(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq
             // ... but every register must be hit by the sample (an unhit register leaves T infinite): >= 24 sampled elements per register
             while (stride > 1 && n_eff / stride < 24. * m) stride /= 2;
             if (const char *ev = getenv("D2G_FSS_BOOT_STRIDE")) stride = (uint32_t)std::max(1, atoi(ev));   // tuning knob
-            a.tile_stride = stride; a.want_state = 1;
-            d2g::FssBootConsumer::Params bp{maxrv, d2g::make_fastmod32(m), m};
-            if (int rc = launch_sketch<d2g::FssBootConsumer>(c, a, bp, windowed, D2G_T_SKETCH_BOOT)) return rc;
-            d2g::fss_threshold_kernel<<<n_ent, 256, 0, c->stream>>>(maxrv, m, T, state);
-            c->launches++;
-            a.tile_stride = 1;
-            if (int rc = windowed ? launch_sketch_windowed_set<d2g::FssMainConsumer>(c, a, mp) : launch_sketch<d2g::FssMainConsumer>(c, a, mp, false)) return rc;
+            if (int rc = for_groups(take, [&](uint64_t *q, uint64_t cap) -> int {
+                    a.ent_state = gstate; a.want_state = 1; a.tile_stride = stride;
+                    d2g::FssBootConsumer::Params bp{maxrv, d2g::make_fastmod32(m), m};
+                    if (int rc = launch_sketch<d2g::FssBootConsumer>(c, a, bp, windowed, D2G_T_SKETCH_BOOT)) return rc;
+                    d2g::fss_threshold_kernel<<<n_ent, 256, 0, st>>>(maxrv, m, T, gstate);
+                    c->launches++;
+                    a.tile_stride = 1;
+                    d2g::FssMainConsumer::Params mp{keys, T, q, ovf_count, cap, m};
+                    if (int rc = windowed ? launch_sketch_windowed_set<d2g::FssMainConsumer>(c, a, mp) : launch_sketch<d2g::FssMainConsumer>(c, a, mp, false)) return rc;
+                    unsigned long long h_q = 0;
+                    if (int rc = read_queue(&h_q)) return rc;
+                    return run_longwalk(q, cap, h_q, false);
+                })) return rc;
         }
-        // long walks (normally none): dense permutation state per thread slot
-        uint64_t nslots = std::min<uint64_t>(4096, (256ULL << 20) / ((uint64_t)m * 8));
-        nslots = std::max<uint64_t>(32, nslots / 32 * 32);
-        if (int rc = c->aux2.reserve(nslots * 2ULL * m * 4)) return rc;
-        CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, c->stream));
-        d2g::fss_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, c->stream>>>(ovf, ovf_count, ovf_cap, m, T, keys, c->aux2.as<uint32_t>());
-        c->launches++;
         if (ids_d) {   // --save-kmers: second pass over the final registers (FssIdsConsumer, fss_kernels.cuh)
-            unsigned long long h1 = 0;
-            CU(cudaMemcpyAsync(&h1, ovf_count, 8, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            if (h1 > ovf_cap) return fail(D2G_EUNSUPPORTED, "Full SetSketch: %llu elements needed a long register walk (queue holds %llu)", h1, (unsigned long long)ovf_cap);
             // the bound of the ids pass: the largest final register of the entity (every point at or below it is replayed)
-            d2g::fss_final_bound_kernel<<<n_ent, 256, 0, c->stream>>>(keys, m, T);
-            CU(cudaMemsetAsync(ids_d, 0, nreg * 8, c->stream));
-            CU(cudaMemsetAsync(ovf_count, 0, 8, c->stream));
-            a.ent_state = nullptr; a.tile_stride = 1;
-            d2g::FssIdsConsumer::Params ip{keys, T, ids_d, ovf, ovf_count, ovf_cap, m};
-            if (int rc = launch_sketch<d2g::FssIdsConsumer>(c, a, ip, windowed, D2G_T_SKETCH_BOOT)) return rc;
-            CU(cudaMemsetAsync(c->aux2.p, 0, nslots * 2ULL * m * 4, c->stream));
-            d2g::fss_longwalk_ids_kernel<<<(unsigned)(nslots / 32), 32, 0, c->stream>>>(ovf, ovf_count, ovf_cap, m, T, keys, ids_d, c->aux2.as<uint32_t>());
-            c->launches += 2;
+            d2g::fss_final_bound_kernel<<<n_ent, 256, 0, st>>>(keys, m, T);
+            c->launches++;
+            CU(cudaMemsetAsync(ids_d, 0, nreg * 8, st));
+            std::vector<char> take(n_ent, 1);
+            if (int rc = for_groups(take, [&](uint64_t *q, uint64_t cap) -> int {
+                    a.ent_state = gstate; a.want_state = 1; a.tile_stride = 1;
+                    d2g::FssIdsConsumer::Params ip{keys, T, ids_d, q, ovf_count, cap, m};
+                    if (int rc = launch_sketch<d2g::FssIdsConsumer>(c, a, ip, windowed, D2G_T_SKETCH_BOOT)) return rc;
+                    unsigned long long h_q = 0;
+                    if (int rc = read_queue(&h_q)) return rc;
+                    return run_longwalk(q, cap, h_q, true);
+                })) return rc;
         }
-    } else if (ids_d && nreg) CU(cudaMemsetAsync(ids_d, 0, nreg * 8, c->stream));
+    } else if (ids_d && nreg) CU(cudaMemsetAsync(ids_d, 0, nreg * 8, st));
     const uint64_t nthreads = std::max<uint64_t>(nreg, n_ent);
-    d2g::fss_finalize_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, c->stream>>>(keys, n_ent, m, sig_d, card_d);
+    d2g::fss_finalize_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(keys, n_ent, m, sig_d, card_d);
     c->launches++;
-    unsigned long long h_ovf = 0;
-    CU(cudaMemcpyAsync(&h_ovf, ovf_count, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    if (getenv("D2G_DEBUG")) {
+    if (debug) {
         std::vector<double> hT(n_ent);
         cudaMemcpy(hT.data(), T, n_ent * 8, cudaMemcpyDeviceToHost);
         uint32_t ninf = 0; double tmax = 0, tmin = 1e308;
         for (double t : hT) { if (t > 1e300) ++ninf; else { tmax = std::max(tmax, t); tmin = std::min(tmin, t); } }
-        fprintf(stderr, "[d2g] fss: n_ent=%u m=%u long-walk queue=%llu boot T: inf=%u min=%g max=%g\n", n_ent, m, h_ovf, ninf, tmin, tmax);
+        fprintf(stderr, "[d2g] fss: n_ent=%u m=%u long walks=%llu boot T: inf=%u min=%g max=%g\n", n_ent, m, (unsigned long long)total_long, ninf, tmin, tmax);
     }
-    if (h_ovf > ovf_cap) return fail(D2G_EUNSUPPORTED, "Full SetSketch: %llu elements needed a long register walk (queue holds %llu); "
-                                     "inputs this small relative to the sketch size are not supported in one batch", h_ovf, (unsigned long long)ovf_cap);
     return D2G_OK;
 }
 

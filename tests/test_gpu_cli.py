@@ -284,3 +284,28 @@ def test_unsupported_options_fail_loudly(golden_inputs):
                  ["contain", paths[0]]):
         r = subprocess.run([EXE] + argv, capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.strip()
+
+
+def test_parse_by_seq_full_setsketch_on_a_read_set(tmp_path):
+    """`sketch --parse-by-seq --full-setsketch -S4096` over 100 000 reads of 150 bp (failed with a queue overflow above
+    ~10 000 reads): every element of such a record walks all 4096 registers.  A sample of records against the oracle."""
+    import oracle_lib as O
+    rng = np.random.default_rng(2026)
+    n, L, S = 100_000, 150, 4096
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = acgt[rng.integers(0, 4, size=(n, L), dtype=np.uint8)]
+    fa = tmp_path / "reads.fa"
+    with open(fa, "wb") as f:
+        hdr = np.array([b">r%07d\n" % i for i in range(n)])
+        body = np.concatenate([reads, np.full((n, 1), 10, dtype=np.uint8)], axis=1)
+        for i in range(0, n, 10000):
+            f.write(b"".join(h + b.tobytes() for h, b in zip(hdr[i:i + 10000], body[i:i + 10000])))
+    out = str(tmp_path / "reads.stk")
+    run(["sketch", "--parse-by-seq", "--full-setsketch", "-k31", f"-S{S}", "-o", out, str(fa)])
+    n_out, s_out = (int(x) for x in np.fromfile(out, dtype=np.uint64, count=2))
+    assert (n_out, s_out) == (n, S)
+    sigs = np.memmap(out, dtype=np.float64, mode="r", offset=16 + 8 * n, shape=(n, S))
+    sample = [0, 1, 4999, 65535, 65536, 65537, n - 1] + [int(x) for x in rng.integers(0, n, 25)]
+    _, exp = O.sketch_records_byseq([reads[i].tobytes() for i in sample], "fss", S, 31, -1)
+    for j, i in enumerate(sample):
+        assert np.array_equal(np.asarray(sigs[i]).view(np.uint64), exp[j].view(np.uint64)), i

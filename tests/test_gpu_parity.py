@@ -876,3 +876,26 @@ def test_fast_windowed_kernel_real_32bit_key_tie():
     got = c.sketch_batch(seq, off, ent, len(recs), c.params(mode="opmh", S=S, k=k, w=w))
     for e, r in enumerate(recs):
         assert np.array_equal(got["regs_u64"][e], _oracle_regs("opmh", S, k, w, [r])), e
+
+
+@pytest.mark.parametrize("S,w,budget", [(512, -1, "40000"), (256, 40, "20000"), (512, -1, None)])
+def test_fss_many_small_entities_long_walk_queue_in_groups(S, w, budget, monkeypatch):
+    """Read-sized records with a Full SetSketch much larger than their element count: every element walks all registers and goes
+    through the long-walk queue.  The queue is sized from the positions of the entities that can reach it and the entities are taken
+    in groups when that exceeds the budget; registers and --save-kmers ids equal the oracle either way."""
+    rng = np.random.default_rng(31 + S)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs = [acgt[rng.integers(0, 4, size=int(rng.choice([60, 100, 150, 151, 400])))].tobytes() for _ in range(1200)]
+    if budget:
+        monkeypatch.setenv("D2G_FSS_QUEUE_ELEMS", budget)
+    c = ctx()
+    seq, off, ent = pack_batch([[r] for r in recs])
+    r = c.sketch_batch(seq, off, ent, len(recs), c.params(mode="fss", S=S, k=31, w=w), want_ids=True)
+    cards, sigs = O.sketch_records_byseq(recs, "fss", S, 31, w)
+    assert np.array_equal(u64(r["sig"]), u64(sigs))
+    L = O.lib()
+    for e in (0, 7, 500, 1199):
+        hv = O.hash_stream(recs[e], 31, w)
+        regs = np.empty(2 * S - 1); ids = np.zeros(S, dtype=np.uint64)
+        L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), ids)
+        assert np.array_equal(r["ids"][e], ids), e
