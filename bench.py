@@ -44,8 +44,10 @@ def parse_args():
     ap.add_argument("--genomes", type=int, default=10000, help="genomes per rank (config: 10000)")
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--e2e-genomes", type=int, default=1024, help="genomes per host-buffer call in the e2e leg")
-    ap.add_argument("--cpu-genomes", type=int, default=16, help="genomes in the CPU-baseline sketch sample")
-    ap.add_argument("--cpu-cmp-n", type=int, default=3000, help="sketches in the CPU-baseline cmp sample")
+    ap.add_argument("--cpu-genomes", type=int, default=64, help="genomes in the CPU-baseline sketch sample (at least 4 per host thread are used)")
+    ap.add_argument("--cpu-cmp-n", type=int, default=5200, help="sketches in the CPU-baseline cmp sample (13.5 M pairs: seconds of reference time)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one genome's registers and 1000 sampled pairs")
+    ap.add_argument("--no-cli", action="store_true", help="skip the CLI-vs-CLI leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -53,42 +55,80 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------------
 # CPU side: the reference's own OpenMP path (oracle/_ref binary) on a bounded sample of the workload
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_run(n_genomes, genome_len, cmp_n, threads, repeats=1, warm=True):
-    """Times `dashing2 sketch` and `dashing2 cmp` (unmodified reference, all host threads) on a sample of
-    the bench workload.  Returns dict(sketch_kmers_s, cmp_pairs_s, kind, cores, sample)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import refbin
-    from dashing2_b200 import synth
-    exe = refbin.ref_binary()
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
-    work = tempfile.mkdtemp(prefix="d2bench", dir=base)
+def host_cores():
     try:
-        if exe is None:
-            return cpu_port_run(n_genomes, genome_len, cmp_n)
-        paths = synth.write_fasta_set(os.path.join(work, "fa"), n_genomes, genome_len, seed=2, n_families=max(1, n_genomes // 4))
-        flist = os.path.join(work, "files.txt")
-        open(flist, "w").write("\n".join(paths) + "\n")
-        sk_cmd = ["sketch", "-k", str(K), "-w", str(W), "--full-setsketch", "-S", str(S), "-p", str(threads),
-                  "-F", flist, "-o", os.path.join(work, "out.ss")]
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class RefSample:
+    """A bounded sample of the bench workload on disk (tmpfs), timed with the unmodified reference binary: `dashing2 sketch` over
+    n_genomes FASTA files (file-parallel OpenMP loop, so at least 4 files per thread keep every thread busy) and `dashing2 cmp` over
+    cmp_n sketches (large enough to run for seconds).  Every timing returns (wall s, CPU s of the child): CPU / wall = threads busy."""
+
+    def __init__(self, n_genomes, genome_len, cmp_n, threads):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refbin
+        from dashing2_b200 import synth
+        self.refbin, self.threads = refbin, threads
+        self.exe = refbin.ref_binary()
+        self.n_genomes, self.genome_len, self.cmp_n = n_genomes, genome_len, cmp_n
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        self.work = tempfile.mkdtemp(prefix="d2bench", dir=base)
+        if self.exe is None:
+            return
+        self.paths = synth.write_fasta_set(os.path.join(self.work, "fa"), n_genomes, genome_len, seed=2, n_families=max(1, n_genomes // 4))
+        self.flist = os.path.join(self.work, "files.txt")
+        open(self.flist, "w").write("\n".join(self.paths) + "\n")
         regs, cards = synth.synthetic_sketches(cmp_n, S, seed=4, n_families=max(1, cmp_n // 64))
-        stk = os.path.join(work, "cmp.ss")
-        synth.write_stacked(stk, regs, cards, names=[f"s{i}" for i in range(cmp_n)])
-        cmp_cmd = ["cmp", "--presketched", "--binary-output", "--cmpout", os.path.join(work, "out.f32"), "-p", str(threads), stk]
-        if warm:  # discard one run each (thread spin-up, page cache)
-            refbin.run_ref(sk_cmd, threads=threads); refbin.run_ref(cmp_cmd, threads=threads)
-        ts, tc = [], []
-        for _ in range(repeats):
-            t0 = time.perf_counter(); refbin.run_ref(sk_cmd, threads=threads); ts.append(time.perf_counter() - t0)
-            t0 = time.perf_counter(); refbin.run_ref(cmp_cmd, threads=threads); tc.append(time.perf_counter() - t0)
-        kmers = n_genomes * (genome_len - K + 1)
-        pairs = cmp_n * (cmp_n - 1) // 2
-        return dict(sketch_kmers_s=kmers / float(np.median(ts)), cmp_pairs_s=pairs / float(np.median(tc)),
-                    sketch_s=float(np.median(ts)), cmp_s=float(np.median(tc)), kind="reference", cores=threads,
-                    sample=f"sketch: {n_genomes} genomes x {genome_len} bp (-k31 -w51 --full-setsketch -S4096), "
-                           f"cmp: {cmp_n} sketches S=4096 all-pairs symmetric binary; dashing2 v2.1.20 {os.path.basename(exe)} "
-                           f"-p {threads}, wall clock incl. file read/write, warm")
+        self.stk = os.path.join(self.work, "cmp.ss")
+        synth.write_stacked(self.stk, regs, cards, names=[f"s{i}" for i in range(cmp_n)])
+        self.sk_cmd = ["sketch", "-k", str(K), "-w", str(W), "--full-setsketch", "-S", str(S), "-p", str(threads),
+                       "-F", self.flist, "-o", os.path.join(self.work, "out.ss")]
+        self.cmp_cmd = ["cmp", "--presketched", "--binary-output", "--cmpout", os.path.join(self.work, "out.f32"), "-p", str(threads), self.stk]
+        self.kmers = n_genomes * (genome_len - K + 1)
+        self.pairs = cmp_n * (cmp_n - 1) // 2
+
+    def _timed(self, cmd):
+        t = os.times(); c0 = t.children_user + t.children_system
+        t0 = time.perf_counter()
+        self.refbin.run_ref(cmd, threads=self.threads)
+        wall = time.perf_counter() - t0
+        t = os.times()
+        return wall, t.children_user + t.children_system - c0
+
+    def run_sketch(self):
+        return self._timed(self.sk_cmd)
+
+    def run_cmp(self):
+        return self._timed(self.cmp_cmd)
+
+    def describe(self, busy_s, busy_c):
+        return (f"sketch: {self.n_genomes} genomes x {self.genome_len} bp (-k31 -w51 --full-setsketch -S4096; FASTA on tmpfs), "
+                f"cmp: {self.cmp_n} sketches S=4096 all-pairs symmetric binary; dashing2 v2.1.20 {os.path.basename(self.exe)} -p {self.threads}, "
+                f"wall clock of the whole process, median of the timed runs after one discarded run; threads busy (CPU s / wall s): "
+                f"sketch {busy_s:.1f}, cmp {busy_c:.1f}")
+
+    def close(self):
+        shutil.rmtree(self.work, ignore_errors=True)
+
+
+def cpu_reference_run(n_genomes, genome_len, cmp_n, threads, repeats=3):
+    """Median-of-`repeats` rates of the reference binary on the sample (one discarded warm-up run each)."""
+    rs = RefSample(n_genomes, genome_len, cmp_n, threads)
+    try:
+        if rs.exe is None:
+            return cpu_port_run(n_genomes, genome_len, cmp_n)
+        rs.run_sketch(); rs.run_cmp()
+        ts = [rs.run_sketch() for _ in range(repeats)]
+        tc = [rs.run_cmp() for _ in range(repeats)]
+        ws = float(np.median([x[0] for x in ts])); wc = float(np.median([x[0] for x in tc]))
+        busy_s = float(np.median([x[1] / x[0] for x in ts])); busy_c = float(np.median([x[1] / x[0] for x in tc]))
+        return dict(sketch_kmers_s=rs.kmers / ws, cmp_pairs_s=rs.pairs / wc, sketch_s=ws, cmp_s=wc, kind="reference", cores=threads,
+                    threads_busy={"sketch": busy_s, "cmp": busy_c}, sample=rs.describe(busy_s, busy_c))
     finally:
-        shutil.rmtree(work, ignore_errors=True)
+        rs.close()
 
 
 def cpu_port_run(n_genomes, genome_len, cmp_n):
@@ -107,14 +147,13 @@ def cpu_port_run(n_genomes, genome_len, cmp_n):
     regs, cards = synth.synthetic_sketches(cmp_n, S, seed=4)
     t0 = time.perf_counter(); O.allpairs(regs, cards); tc = time.perf_counter() - t0
     return dict(sketch_kmers_s=kmers / ts, cmp_pairs_s=cmp_n * (cmp_n - 1) / 2 / tc, sketch_s=ts, cmp_s=tc, kind="port", cores=1,
+                threads_busy={"sketch": 1.0, "cmp": 1.0},
                 sample=f"oracle port, 1 thread: {n_genomes} genomes x {genome_len} bp; {cmp_n} sketches")
 
 
-def host_cores():
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+def sample_sizes(args, cores):
+    """The reference's sketch loop is file-parallel: at least 4 genomes per host thread (and at least 64)."""
+    return max(args.cpu_genomes, 4 * cores), args.cpu_cmp_n
 
 
 def run_reference_arm(args):
@@ -122,23 +161,77 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = host_cores()
-    vals_s, vals_c, tot = [], [], []
-    res = None
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        res = cpu_reference_run(args.cpu_genomes, args.genome_len, args.cpu_cmp_n, cores, repeats=1, warm=False)
-        if i >= args.warmup:
-            vals_s.append(res["sketch_kmers_s"]); vals_c.append(res["cmp_pairs_s"]); tot.append((res["sketch_s"] + res["cmp_s"]) * 1e3)
-    v = float(np.mean(vals_s)); vc = float(np.mean(vals_c))
+    n_genomes, cmp_n = sample_sizes(args, cores)
+    rs = RefSample(n_genomes, args.genome_len, cmp_n, cores)
+    try:
+        if rs.exe is None:
+            res = cpu_port_run(n_genomes, args.genome_len, cmp_n)
+            v, vc, ms, sample, kind, busy = res["sketch_kmers_s"], res["cmp_pairs_s"], (res["sketch_s"] + res["cmp_s"]) * 1e3, res["sample"], "port", res["threads_busy"]
+            cores = 1
+        else:
+            ts, tc = [], []
+            for i in range(args.warmup + args.steps):        # one step = one run of both reference commands over the sample
+                a = rs.run_sketch(); b = rs.run_cmp()
+                if i >= args.warmup:
+                    ts.append(a); tc.append(b)
+            ws = float(np.mean([x[0] for x in ts])); wc = float(np.mean([x[0] for x in tc]))
+            busy = {"sketch": float(np.median([x[1] / x[0] for x in ts])), "cmp": float(np.median([x[1] / x[0] for x in tc]))}
+            v, vc, ms, kind = rs.kmers / ws, rs.pairs / wc, (ws + wc) * 1e3, "reference"
+            sample = rs.describe(busy["sketch"], busy["cmp"])
+    finally:
+        rs.close()
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "kmers/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": float(np.mean(tot)), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
             "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+            "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": cores, "kind": kind, "sample": sample, "threads_busy": busy},
             "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "cmp": {"value": vc, "unit": "pairs/s", "e2e": {"value": vc, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cli_vs_cli(n_genomes, genome_len, threads):
+    """Whole programs, same argv, FASTA on tmpfs: the reference binary against the drop-in front-end (dashing2-gpu), sketch + all-pairs
+    compare with binary output; reports wall clocks (median of 2 after a warm-up) and whether the output files are byte-identical."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refbin
+    from dashing2_b200 import synth
+    ref = refbin.ref_binary()
+    ours = os.path.join(ROOT, "dashing2_b200", "bin", "dashing2-gpu")
+    if ref is None or not os.path.exists(ours):
+        return {"unavailable": "reference binary or front-end missing"}
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    work = tempfile.mkdtemp(prefix="d2cli", dir=base)
+    try:
+        paths = synth.write_fasta_set(os.path.join(work, "fa"), n_genomes, genome_len, seed=2, n_families=max(1, n_genomes // 4))
+        flist = os.path.join(work, "files.txt"); open(flist, "w").write("\n".join(paths) + "\n")
+        res = {}
+        for tag, exe in (("reference", ref), ("ours", ours)):
+            argv = ["sketch", "-k", str(K), "-w", str(W), "--full-setsketch", "-S", str(S), "-p", str(threads), "-F", flist,
+                    "-o", os.path.join(work, tag + ".ss"), "--cmpout", os.path.join(work, tag + ".f32"), "--binary-output"]
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+            ts = []
+            for i in range(3):
+                t0 = time.perf_counter()
+                r = subprocess.run([exe] + argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                ts.append(time.perf_counter() - t0)
+                if r.returncode:
+                    return {"unavailable": f"{tag} failed: {r.stderr.decode(errors='replace')[-300:]}"}
+            res[tag] = float(np.median(ts[1:]))
+        same_mat = open(os.path.join(work, "ours.f32"), "rb").read() == open(os.path.join(work, "reference.f32"), "rb").read()
+        a = np.fromfile(os.path.join(work, "ours.ss"), dtype=np.uint64); b = np.fromfile(os.path.join(work, "reference.ss"), dtype=np.uint64)
+        n = n_genomes
+        same_regs = len(a) == len(b) and bool(np.array_equal(a[2 + n:], b[2 + n:]))     # registers bit for bit; cardinalities to 1e-12 (summation order)
+        kmers = n_genomes * (genome_len - K + 1)
+        return {"argv": "sketch -k31 -w51 --full-setsketch -S4096 -p %d -F files.txt -o X.ss --cmpout X.f32 --binary-output" % threads,
+                "sample": "%d genomes x %d bp, FASTA on tmpfs" % (n_genomes, genome_len),
+                "reference_s": res["reference"], "ours_s": res["ours"], "speedup": res["reference"] / res["ours"],
+                "reference_kmers_s": kmers / res["reference"], "ours_kmers_s": kmers / res["ours"],
+                "matrix_bytes_identical": same_mat, "registers_bit_identical": same_regs,
+                "note": "whole-process wall clock; ours includes CUDA context creation and teardown (about 1 s on these boxes)"}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
 
 
 def workload_config(args, n_gpus):

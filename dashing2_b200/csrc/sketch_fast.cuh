@@ -16,7 +16,8 @@
 //           probability ~ (w-k+1)^2 / 2^33 per window): the exact minimizer is chosen by the full score, and the tile (and its
 //           successor) is put on the redo list, because such a tie can later change the minimizer without changing the
 //           32-bit minimum.
-// Events are staged per tile and hashed on dense warps during the next tile.  Tiles on the redo list are recomputed by the
+// Every thread leaves the event flags of its eight windows in shared memory; during the next tile two warps compact them into the
+// two event lists (one 16-byte load per lane, a warp prefix sum) and the events are then hashed on dense warps.  Tiles on the redo list are recomputed by the
 // exact 64-bit kernel (sketch_redo_kernel): set sketches are idempotent minima, so the union of both passes is exact.  An
 // event list that overflows (pathological repeats) also sends its tile to the redo list.  Everything the fast pass emits is
 // a true minimizer; everything it might have missed lies in a listed tile.
@@ -45,7 +46,7 @@ struct FastAux {
 };
 
 inline size_t sketch_fast_smem_bytes(size_t consumer_bytes) {
-    return (size_t)3 * SF_WBYTES + 32 + (size_t)2 * SF_KEYS * 4 + (size_t)SF_LCAP * 2 * 2 + 32 + consumer_bytes;
+    return (size_t)3 * SF_WBYTES + 32 + (size_t)2 * SF_KEYS * 4 + (size_t)SK_THREADS * 2 + (size_t)SF_LCAP * 2 * 2 + 32 + consumer_bytes;
 }
 
 // canonical k-mer at base offset b of a packed tile; 0 when one of its bases is invalid (encoder.h:568-571 + kmerutil.h:137-140)
@@ -58,19 +59,19 @@ template <int WSZ_T, class Consumer>
 __global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
 sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const FastAux fx) {
     static_assert(!Consumer::kEveryWindow, "the fast windowed kernel serves set sketches only");
+    static_assert(SK_THREADS == 256 && SK_PPT == 8, "event compaction assumes 256 threads x 8 windows");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int k = a.k;
     const int wsz = WSZ_T ? WSZ_T : (a.w - a.k + 1);
     const int need = a.w;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + 3 * SF_WBYTES);
     uint32_t *KH = reinterpret_cast<uint32_t *>(smem_raw + 3 * SF_WBYTES + 32);          // two key buffers of SF_KEYS words
-    uint16_t *LA = reinterpret_cast<uint16_t *>(KH + 2 * SF_KEYS);                        // type A events: key slot
+    uint16_t *FL = reinterpret_cast<uint16_t *>(KH + 2 * SF_KEYS);                        // per thread: type A flags | type B flags << 8 of its 8 windows
+    uint16_t *LA = FL + SK_THREADS;                                                       // type A events: key slot
     uint16_t *LB = LA + SF_LCAP;                                                          // type B events: key slot of the window's last key
-    uint32_t *ctl = reinterpret_cast<uint32_t *>(LB + SF_LCAP);                                                       // [0,1] event counters (A | B << 16) by tile parity, [2,3] redo flags
+    uint32_t *ctl = reinterpret_cast<uint32_t *>(LB + SF_LCAP);                           // [0] nA, [1] nB, [2,3] redo flags by tile parity
     unsigned char *csmem = reinterpret_cast<unsigned char *>(ctl + 8);
-    auto Wc = [&](uint32_t i) { return reinterpret_cast<uint64_t *>(smem_raw + (size_t)i * SF_WBYTES); };
-    auto Wm = [&](uint32_t i) { return reinterpret_cast<uint32_t *>(smem_raw + (size_t)i * SF_WBYTES + SF_NW * 8); };
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Consumer cons;
     cons.init(csmem, cp, true);
     if (tid == 0) {
@@ -87,31 +88,54 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
     const uint64_t kmask = k < 32 ? ((1ULL << (2 * k)) - 1) : ~0ULL;
     __syncthreads();
 
-    uint32_t nt = 0;                       // tiles this CTA has issued a load for; tile n lives in buffer n % 3, barrier phase (n / 3) & 1
-    // thread 0: bulk copies of the packed words of the tile starting at start position t0
-    auto issue_tile = [&](uint32_t n, uint64_t t0, int nstart) {
+    // packed tile buffers rotate 0 -> 1 -> 2 -> 0; bit b of wphase is the mbarrier parity the next wait on buffer b expects
+    uint32_t wb = 0, wphase = 0;
+    auto next_buf = [](uint32_t b) { return b == 2 ? 0u : b + 1; };
+    // thread 0: bulk copies of the packed words of the tile starting at start position t0 into buffer b
+    auto issue_tile = [&](uint32_t b, uint64_t t0, int nstart) {
         const uint64_t o = t0 & ~127ULL;
         const int nbases = (int)(t0 - o) + nstart + wsz - 1 + k - 1;
         const uint32_t nw = (uint32_t)((((nbases + 31) >> 5) + 2 + 3) & ~3);
-        const uint32_t b = n % 3;
+        unsigned char *dst = smem_raw + b * SF_WBYTES;
         mbar_expect_tx(bar + b, nw * 12);
-        bulk_g2s(Wc(b), a.seq.codes + (o >> 5), nw * 8, bar + b);
-        bulk_g2s(Wm(b), a.seq.mask + (o >> 5), nw * 4, bar + b);
+        bulk_g2s(dst, a.seq.codes + (o >> 5), nw * 8, bar + b);
+        bulk_g2s(dst + SF_NW * 8, a.seq.mask + (o >> 5), nw * 4, bar + b);
+    };
+
+    // ---- event flags of a tile -> the two event lists (warp 7: type A, warp 6: type B) ----
+    // lane l owns threads 8l .. 8l+7 = windows 64l .. 64l+63 of the tile; one 16-byte load brings their flags
+    auto compact_events = [&](uint32_t par) {
+        if (warp < 6) return;
+        const bool isA = warp == 7;
+        const uint4 f = *reinterpret_cast<const uint4 *>(FL + 8 * lane);
+        const uint32_t sel = isA ? 0x6420u : 0x7531u;                               // low / high byte of every 16-bit entry
+        uint32_t m0 = __byte_perm(f.x, f.y, sel), m1 = __byte_perm(f.z, f.w, sel); // windows 64l .. +31, 64l+32 .. +63
+        const int cnt = __popc(m0) + __popc(m1);
+        int incl = cnt;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int at = incl - cnt;
+        uint16_t *L = isA ? LA : LB;
+        const int slot0 = SF_OFF + 64 * lane;
+        for (; m0; m0 &= m0 - 1, ++at) if (at < SF_LCAP) L[at] = (uint16_t)(slot0 + __ffs(m0) - 1);
+        for (; m1; m1 &= m1 - 1, ++at) if (at < SF_LCAP) L[at] = (uint16_t)(slot0 + 32 + __ffs(m1) - 1);
+        if (lane == 0) {
+            ctl[isA ? 0 : 1] = (uint32_t)min(total, SF_LCAP);
+            if (total > SF_LCAP) atomicOr(ctl + 2 + par, 1u);                       // a list overflowed: the exact kernel redoes this tile
+        }
     };
 
     // ---- staged events of one tile -> k-mers -> consumer (all threads; dense warps) ----
-    // keys: the tile's key buffer; boff: base offset (inside the tile's packed words) of the k-mer whose key sits in slot SF_OFF
-    auto drain_events = [&](uint32_t n, int boff) {
-        const uint64_t *W = Wc(n % 3); const uint32_t *M = Wm(n % 3);
-        const uint32_t *keys = KH + (n & 1) * SF_KEYS;
-        const uint32_t packed = ctl[n & 1];
-        const int nA = min((int)(packed & 0xFFFFu), SF_LCAP), nB = min((int)(packed >> 16), SF_LCAP);
+    // W / M / keys: the tile's packed words and key buffer; boff: base offset of the k-mer whose key sits in slot SF_OFF
+    auto drain_events = [&](const uint64_t *W, const uint32_t *M, const uint32_t *keys, int boff, uint32_t par) {
+        const int nA = (int)ctl[0], nB = (int)ctl[1];
         for (int i = tid; i < nA; i += SK_THREADS) {
             const int e = LA[i];
             const uint64_t km = tile_canonical_or_zero(W, M, boff + (e - SF_OFF), k);
             cons.consume(wang64(km ^ a.xormask));                                   // maskfn, src/enums.h:136-140
         }
-        for (int i = SK_THREADS - 1 - tid; i < nB; i += SK_THREADS) {                // from the other end of the CTA: the A events keep the first warps busy
+        for (int i = (tid - 96) & (SK_THREADS - 1); i < nB; i += SK_THREADS) {        // warps 3, 4, 5 first: warps 0-2 hash the A events, warps 6-7 compacted the flags
             const int e = LB[i];
             // the window's keys sit in slots e-(wsz-1) .. e; in the padded layout they are contiguous except for one possible 4-word pad
             const int x0 = e - (wsz - 1);
@@ -143,16 +167,16 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
                         if (s2 != best) differ = true;
                         if (s2 < best) { best = s2; km = k2; }
                     }
-                if (differ) atomicOr(ctl + 2 + (n & 1), 3u);                         // redo this tile and the next one
+                if (differ) atomicOr(ctl + 2 + par, 3u);                             // redo this tile and the next one
             }
             cons.consume(wang64(km ^ a.xormask));
         }
     };
-    // thread 0, after the barrier that ends the drain of tile n: put it on the redo list when flagged
-    auto settle_redo = [&](uint32_t n, uint64_t t0) {
-        const uint32_t f = ctl[2 + (n & 1)];
+    // thread 0, after the barrier that ends the drain of a tile: put it on the redo list when flagged
+    auto settle_redo = [&](uint32_t par, uint64_t t0) {
+        const uint32_t f = ctl[2 + par];
         if (f) {
-            ctl[2 + (n & 1)] = 0;
+            ctl[2 + par] = 0;
             const unsigned long long at = atomicAdd(fx.redo_count, (f & 2u) ? 2ULL : 1ULL);
             if (at < fx.redo_cap) fx.redo_list[at] = t0;
             if ((f & 2u) && at + 1 < fx.redo_cap) fx.redo_list[at + 1] = t0 + SF_TILE;
@@ -173,144 +197,148 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
             cur_ent = ent;
             cons.begin_entity(ent, p0 - span_lo);
         }
-        bool first = true;
-        bool pending = false; uint32_t pend_n = 0; int pend_boff = 0; uint64_t pend_t0 = 0;
-        if (tid == 0) issue_tile(nt, p0, (int)min((uint64_t)SF_TILE, p1 - p0));
-        for (uint64_t t0 = p0; t0 < p1; t0 += SF_TILE) {
-            const uint32_t n = nt++;
+        // Pipeline over the tiles of the segment.  Tile n: phase 1 computes its keys while two warps compact the event flags of tile
+        // n-1; phase 2 hashes the events of tile n-1 and computes minima + event flags of tile n.  `prev` = tile n-1, `prev2` = tile n-2.
+        bool first = true, have_prev = false, have_prev2 = false;
+        uint32_t par = 0;                                             // parity of the current tile within the segment
+        uint32_t prev_wb = 0; int prev_boff = 0; uint64_t prev_t0 = 0, prev2_t0 = 0;
+        if (tid == 0) issue_tile(wb, p0, (int)min((uint64_t)SF_TILE, p1 - p0));
+        for (uint64_t t0 = p0; t0 < p1; t0 += SF_TILE, par ^= 1u) {
             const int nstart = (int)min((uint64_t)SF_TILE, p1 - t0);
             const int boff = (int)(t0 & 127ULL) + wsz - 1;           // base offset of the first NEW key's k-mer (window of start position t0 ends there)
-            uint32_t *keys = KH + (n & 1) * SF_KEYS;
-            const uint64_t *W = Wc(n % 3); const uint32_t *M = Wm(n % 3);
-            // ---- phase 1: prefetch the next tile, hash the previous tile's events, compute this tile's keys ----
+            uint32_t *keys = KH + par * SF_KEYS;
+            const uint64_t *W = reinterpret_cast<const uint64_t *>(smem_raw + wb * SF_WBYTES);
+            const uint32_t *M = reinterpret_cast<const uint32_t *>(smem_raw + wb * SF_WBYTES + SF_NW * 8);
+            const int j0 = tid * SK_PPT;
+            const int jn = max(0, min(SK_PPT, nstart - j0));
+            // ---- phase 1 ----
             if (tid == 0) {
-                if (t0 + SF_TILE < p1) issue_tile(n + 1, t0 + SF_TILE, (int)min((uint64_t)SF_TILE, p1 - t0 - SF_TILE));
-                ctl[n & 1] = 0;                                       // this tile's event counter (last read two barriers ago)
+                if (t0 + SF_TILE < p1) issue_tile(next_buf(wb), t0 + SF_TILE, (int)min((uint64_t)SF_TILE, p1 - t0 - SF_TILE));
+                if (have_prev2) settle_redo(par, prev2_t0);           // tile n-2 has the parity of tile n
             }
-            if (pending) drain_events(pend_n, pend_boff);
-            mbar_wait(bar + n % 3, (n / 3) & 1);
-            {
-                const int j0 = tid * SK_PPT;
-                const int jn = max(0, min(SK_PPT, nstart - j0));
-                if (jn > 0) {
-                    uint64_t km[8];
-                    const uint32_t bad = kmers8(W, M, boff + j0, k, kmask, true, km);
-                    uint32_t kh[8];
-                    #pragma unroll
-                    for (int j = 0; j < SK_PPT; ++j) kh[j] = (uint32_t)(frev64(((bad >> j) & 1u) ? 0ULL : km[j]) >> 32) & a.keymask;
-                    uint32_t *dst = keys + sf_pad(SF_OFF + j0);                   // SF_OFF + j0 is a multiple of 8: two aligned groups of four
-                    if (jn == SK_PPT) {
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(kh[0], kh[1], kh[2], kh[3]);
-                        *reinterpret_cast<uint4 *>(dst + 4) = make_uint4(kh[4], kh[5], kh[6], kh[7]);
-                    } else {
-                        #pragma unroll
-                        for (int j = 0; j < SK_PPT; ++j) if (j < jn) dst[j] = kh[j];
-                    }
-                }
-                if (first) {
-                    // the wsz-1 keys before the first window's last key; the slot before them is never a window member: largest key
-                    for (int i = tid; i < wsz - 1; i += SK_THREADS)
-                        keys[sf_pad(SF_OFF - (wsz - 1) + i)] = (uint32_t)(frev64(tile_canonical_or_zero(W, M, boff - (wsz - 1) + i, k)) >> 32) & a.keymask;
-                    if (tid == 0) keys[sf_pad(SF_OFF - wsz)] = 0xFFFFFFFFu;
+            if (have_prev) compact_events(par ^ 1u);
+            mbar_wait(bar + wb, (wphase >> wb) & 1u);
+            wphase ^= 1u << wb;
+            if (jn > 0) {
+                uint64_t km[8];
+                const uint32_t bad = kmers8(W, M, boff + j0, k, kmask, true, km);
+                uint32_t kh[8];
+                #pragma unroll
+                for (int j = 0; j < SK_PPT; ++j) kh[j] = (uint32_t)(frev64(((bad >> j) & 1u) ? 0ULL : km[j]) >> 32) & a.keymask;
+                uint32_t *dst = keys + sf_pad(SF_OFF + j0);                   // SF_OFF + j0 is a multiple of 8: two aligned groups of four
+                if (jn == SK_PPT) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(kh[0], kh[1], kh[2], kh[3]);
+                    *reinterpret_cast<uint4 *>(dst + 4) = make_uint4(kh[4], kh[5], kh[6], kh[7]);
                 } else {
-                    // carry the last wsz keys of the previous (full) tile
-                    const uint32_t *pk = KH + ((n & 1) ^ 1) * SF_KEYS;
-                    for (int i = tid; i < wsz; i += SK_THREADS) keys[sf_pad(SF_OFF - wsz + i)] = pk[sf_pad(SF_OFF + SF_TILE - wsz + i)];
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j) if (j < jn) dst[j] = kh[j];
                 }
+            }
+            if (first) {
+                // the wsz-1 keys before the first window's last key; the slot before them is never a window member: largest key
+                for (int i = tid; i < wsz - 1; i += SK_THREADS)
+                    keys[sf_pad(SF_OFF - (wsz - 1) + i)] = (uint32_t)(frev64(tile_canonical_or_zero(W, M, boff - (wsz - 1) + i, k)) >> 32) & a.keymask;
+                if (tid == 0) keys[sf_pad(SF_OFF - wsz)] = 0xFFFFFFFFu;
+            } else {
+                // carry the last wsz keys of the previous (full) tile
+                const uint32_t *pk = KH + (par ^ 1u) * SF_KEYS;
+                for (int i = tid; i < wsz; i += SK_THREADS) keys[sf_pad(SF_OFF - wsz + i)] = pk[sf_pad(SF_OFF + SF_TILE - wsz + i)];
             }
             __syncthreads();
             cons.end_tile(cur_ent);
-            // ---- phase 2: sliding minima on the 32-bit keys, events ----
-            if (tid == 0 && pending) settle_redo(pend_n, pend_t0);
-            {
-                const int j0 = tid * SK_PPT;
-                const int jn = max(0, min(SK_PPT, nstart - j0));
-                if (jn > 0) {
-                    const int B0 = SF_OFF + j0;
-                    uint32_t O[8], L[7], C, extra;
-                    {
-                        const uint4 o0 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0)), o1 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0 + 4));
-                        O[0] = o0.x; O[1] = o0.y; O[2] = o0.z; O[3] = o0.w; O[4] = o1.x; O[5] = o1.y; O[6] = o1.z; O[7] = o1.w;
-                    }
-                    if (jn < SK_PPT) {
-                        #pragma unroll
-                        for (int j = 0; j < SK_PPT; ++j) if (j >= jn) O[j] = 0xFFFFFFFFu;
-                    }
-                    uint32_t mn[8], prev0;
-                    if (WSZ_T == 21) {
-                        // slots B0-20 .. B0-1 as five aligned groups of four: L0..L6 = B0-20 .. B0-14, common = B0-13 .. B0-1
-                        const uint4 v0 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0 - 20)), v1 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0 - 16)),
-                                    v2 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0 - 12)), v3 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0 - 8)),
-                                    v4 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0 - 4));
-                        extra = keys[sf_pad(B0 - 21)];
-                        L[0] = v0.x; L[1] = v0.y; L[2] = v0.z; L[3] = v0.w; L[4] = v1.x; L[5] = v1.y; L[6] = v1.z;
-                        C = min(min(v1.w, v2.x), v2.y);
-                        C = min(min(C, v2.z), v2.w); C = min(min(C, v3.x), v3.y); C = min(min(C, v3.z), v3.w);
-                        C = min(min(C, v4.x), v4.y); C = min(min(C, v4.z), v4.w);
-                    } else if (wsz >= SK_PPT) {
+            // ---- phase 2 ----
+            if (have_prev)
+                drain_events(reinterpret_cast<const uint64_t *>(smem_raw + prev_wb * SF_WBYTES),
+                             reinterpret_cast<const uint32_t *>(smem_raw + prev_wb * SF_WBYTES + SF_NW * 8), KH + (par ^ 1u) * SF_KEYS, prev_boff, par ^ 1u);
+            uint32_t flags = 0;
+            if (jn > 0) {
+                const int B0 = SF_OFF + j0;
+                uint32_t O[8], L[7], C, extra;
+                uint32_t mn[8], prev0;
+                if (WSZ_T == 21) {
+                    // slots B0-20 .. B0+7 as seven aligned groups of four; in the padded layout the groups from index gc on sit 4 words further
+                    const int u = B0 - 20;
+                    const uint32_t *pa = keys + sf_pad(u);
+                    const int gc = (32 - (u & 31)) >> 2;                                 // u & 31 is 4, 12, 20 or 28
+                    auto grp = [&](int g) { return *reinterpret_cast<const uint4 *>((g < gc ? pa : pa + 4) + 4 * g); };
+                    const uint4 v0 = grp(0), v1 = grp(1), v2 = grp(2), v3 = grp(3), v4 = grp(4), o0 = grp(5), o1 = grp(6);
+                    extra = pa[-1];
+                    O[0] = o0.x; O[1] = o0.y; O[2] = o0.z; O[3] = o0.w; O[4] = o1.x; O[5] = o1.y; O[6] = o1.z; O[7] = o1.w;
+                    L[0] = v0.x; L[1] = v0.y; L[2] = v0.z; L[3] = v0.w; L[4] = v1.x; L[5] = v1.y; L[6] = v1.z;   // L0..L6 = B0-20 .. B0-14
+                    C = min(min(v1.w, v2.x), v2.y);                                                             // common = B0-13 .. B0-1
+                    C = min(min(C, v2.z), v2.w); C = min(min(C, v3.x), v3.y); C = min(min(C, v3.z), v3.w);
+                    C = min(min(C, v4.x), v4.y); C = min(min(C, v4.z), v4.w);
+                } else {
+                    const uint4 o0 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0)), o1 = *reinterpret_cast<const uint4 *>(keys + sf_pad(B0 + 4));
+                    O[0] = o0.x; O[1] = o0.y; O[2] = o0.z; O[3] = o0.w; O[4] = o1.x; O[5] = o1.y; O[6] = o1.z; O[7] = o1.w;
+                    if (wsz >= SK_PPT) {
                         C = 0xFFFFFFFFu;
                         for (int i = 1; i <= wsz - SK_PPT; ++i) C = min(C, keys[sf_pad(B0 - i)]);      // slots B0-(wsz-8) .. B0-1 belong to all eight windows
                         #pragma unroll
                         for (int j = 0; j < 7; ++j) L[j] = keys[sf_pad(B0 + j - (wsz - 1))];
                         extra = keys[sf_pad(B0 - wsz)];
                     }
-                    if (WSZ_T == 21 || wsz >= SK_PPT) {
-                        uint32_t ls[7];                                                      // ls[j] = min(L[j..6])
-                        ls[6] = L[6];
-                        #pragma unroll
-                        for (int j = 5; j >= 0; --j) ls[j] = min(L[j], ls[j + 1]);
-                        prev0 = min(min(extra, ls[0]), C);
-                        uint32_t cr = C;
-                        #pragma unroll
-                        for (int j = 0; j < SK_PPT; ++j) { cr = min(cr, O[j]); mn[j] = j < 7 ? min(ls[j], cr) : cr; }
-                    } else {
-                        // short windows (2..7 k-mers): X[7 + j] = own key j, X[7 - d] = the d-th key before
-                        uint32_t X[15];
-                        #pragma unroll
-                        for (int d = 1; d <= 7; ++d) X[7 - d] = d <= wsz ? keys[sf_pad(B0 - d)] : 0xFFFFFFFFu;
-                        #pragma unroll
-                        for (int j = 0; j < SK_PPT; ++j) X[7 + j] = O[j];
-                        prev0 = 0xFFFFFFFFu;
-                        #pragma unroll
-                        for (int d = 1; d <= 7; ++d) if (d <= wsz) prev0 = min(prev0, X[7 - d]);
-                        #pragma unroll
-                        for (int j = 0; j < SK_PPT; ++j) {
-                            uint32_t v = X[7 + j];
-                            #pragma unroll
-                            for (int d = 1; d < 7; ++d) if (d < wsz) v = min(v, X[7 + j - d]);
-                            mn[j] = v;
-                        }
-                    }
-                    // events
-                    uint32_t fa = 0, fb = 0;                                                 // bit j: window j is a type A / type B event
+                }
+                if (jn < SK_PPT) {
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j) if (j >= jn) O[j] = 0xFFFFFFFFu;
+                }
+                if (WSZ_T == 21 || wsz >= SK_PPT) {
+                    uint32_t ls[7];                                                      // ls[j] = min(L[j..6])
+                    ls[6] = L[6];
+                    #pragma unroll
+                    for (int j = 5; j >= 0; --j) ls[j] = min(L[j], ls[j + 1]);
+                    prev0 = min(min(extra, ls[0]), C);
+                    uint32_t cr = C;
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j) { cr = min(cr, O[j]); mn[j] = j < 7 ? min(ls[j], cr) : cr; }
+                } else {
+                    // short windows (2..7 k-mers): X[7 + j] = own key j, X[7 - d] = the d-th key before
+                    uint32_t X[15];
+                    #pragma unroll
+                    for (int d = 1; d <= 7; ++d) X[7 - d] = d <= wsz ? keys[sf_pad(B0 - d)] : 0xFFFFFFFFu;
+                    #pragma unroll
+                    for (int j = 0; j < SK_PPT; ++j) X[7 + j] = O[j];
+                    prev0 = 0xFFFFFFFFu;
+                    #pragma unroll
+                    for (int d = 1; d <= 7; ++d) if (d <= wsz) prev0 = min(prev0, X[7 - d]);
                     #pragma unroll
                     for (int j = 0; j < SK_PPT; ++j) {
-                        const uint32_t pv = j ? mn[j - 1] : prev0;
-                        fa |= (uint32_t)(O[j] < pv) << j;
-                        fb |= (uint32_t)((O[j] == pv) | (mn[j] > pv)) << j;
-                    }
-                    if (first && tid == 0) { fa &= ~1u; fb |= 1u; }                          // the first window of a record segment has no predecessor
-                    if (jn < SK_PPT) { fa &= (1u << jn) - 1u; fb &= (1u << jn) - 1u; }
-                    if (fa | fb) {
-                        const uint32_t ca = __popc(fa), cb = __popc(fb);
-                        const uint32_t base = atomicAdd(ctl + (n & 1), ca | (cb << 16));
-                        uint32_t sa = base & 0xFFFFu, sb = base >> 16;
-                        if (sa + ca > (uint32_t)SF_LCAP || sb + cb > (uint32_t)SF_LCAP) atomicOr(ctl + 2 + (n & 1), 1u);   // overflow: redo this tile
-                        for (; fa; fa &= fa - 1, ++sa) if (sa < (uint32_t)SF_LCAP) LA[sa] = (uint16_t)(B0 + __ffs(fa) - 1);
-                        for (; fb; fb &= fb - 1, ++sb) if (sb < (uint32_t)SF_LCAP) LB[sb] = (uint16_t)(B0 + __ffs(fb) - 1);
+                        uint32_t v = X[7 + j];
+                        #pragma unroll
+                        for (int d = 1; d < 7; ++d) if (d < wsz) v = min(v, X[7 + j - d]);
+                        mn[j] = v;
                     }
                 }
+                // events
+                uint32_t fa = 0, fb = 0;                                                 // bit j: window j is a type A / type B event
+                #pragma unroll
+                for (int j = 0; j < SK_PPT; ++j) {
+                    const uint32_t pv = j ? mn[j - 1] : prev0;
+                    fa |= (uint32_t)(O[j] < pv) << j;
+                    fb |= (uint32_t)((O[j] == pv) | (mn[j] > pv)) << j;
+                }
+                if (first && tid == 0) { fa &= ~1u; fb |= 1u; }                          // the first window of a record segment has no predecessor
+                if (jn < SK_PPT) { fa &= (1u << jn) - 1u; fb &= (1u << jn) - 1u; }
+                flags = fa | (fb << 8);
             }
+            FL[tid] = (uint16_t)flags;
             __syncthreads();
-            pending = true; pend_n = n; pend_boff = boff; pend_t0 = t0;
+            have_prev2 = have_prev; prev2_t0 = prev_t0;
+            have_prev = true; prev_wb = wb; prev_boff = boff; prev_t0 = t0;
+            wb = next_buf(wb);
             first = false;
         }
-        // the last tile of the segment: its events, then its redo flag
-        if (pending) {
-            drain_events(pend_n, pend_boff);
+        // the last tile of the segment (it has the parity par ^ 1): compact and hash its events, settle the redo flags
+        if (have_prev) {
+            if (tid == 0 && have_prev2) settle_redo(par, prev2_t0);
+            compact_events(par ^ 1u);
+            __syncthreads();
+            drain_events(reinterpret_cast<const uint64_t *>(smem_raw + prev_wb * SF_WBYTES),
+                         reinterpret_cast<const uint32_t *>(smem_raw + prev_wb * SF_WBYTES + SF_NW * 8), KH + (par ^ 1u) * SF_KEYS, prev_boff, par ^ 1u);
             __syncthreads();
             cons.end_tile(cur_ent);
-            if (tid == 0) settle_redo(pend_n, pend_t0);
+            if (tid == 0) settle_redo(par ^ 1u, prev_t0);
             __syncthreads();
         }
     }
