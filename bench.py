@@ -378,7 +378,7 @@ def main():
     for _ in range(args.warmup):
         step(False)
     ctx.set_timing(True)
-    for c in range(4):
+    for c in range(5):
         ctx.get_timing(c)
     sampler = ClockSampler(local); sampler.start()
     l0 = ctx.launch_count()
@@ -396,6 +396,7 @@ def main():
     k_boot_ms, k_boot_n = ctx.get_timing(1)
     k_cmp_ms, k_cmp_n = ctx.get_timing(2)
     k_prep_ms, k_prep_n = ctx.get_timing(3)
+    k_pack_ms, k_pack_n = ctx.get_timing(4)
     ctx.set_timing(False)
 
     # max over ranks of the device-timed totals
@@ -449,6 +450,63 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e_sk, t_e2e_cmp = (float(x) for x in te.tolist())
 
+    # ---- e2e with the sequence packed by the caller (d2g_sketch_batch_packed): what the front-end sends once it packs while parsing
+    from dashing2_b200 import capi as _capi
+    Lc = ctx.L
+    nwp = int(Lc.d2g_packed_words(Ge * Lg))
+    h_codes = torch.empty(nwp, dtype=torch.int64).pin_memory(); h_mask = torch.empty(nwp, dtype=torch.int32).pin_memory()
+    pp = (C.c_void_p * 1)(h_seq.data_ptr()); pl = np.array([Ge * Lg], dtype=np.uint64); nzw = C.c_uint64(0)
+    t0 = time.perf_counter()
+    if Lc.d2g_pack_sequences(pp, pl.ctypes.data, 1, h_codes.data_ptr(), h_mask.data_ptr(), C.byref(nzw)):
+        raise RuntimeError(Lc.d2g_last_error().decode())
+    t_host_pack = time.perf_counter() - t0
+
+    def e2e_sketch_packed():
+        nk = C.c_uint64(0)
+        rc = Lc.d2g_sketch_batch_packed(ctx.h, C.byref(p_sk), h_codes.data_ptr(), None if nzw.value == 0 else h_mask.data_ptr(), h_off.ctypes.data,
+                                        h_ent.ctypes.data, Ge, Ge, None, h_sig.data_ptr(), h_card.data_ptr(), None, C.byref(nk))
+        if rc:
+            raise RuntimeError(Lc.d2g_last_error().decode())
+    e2e_sketch_packed()
+    barrier(); t0 = time.perf_counter()
+    for _ in range(ne):
+        e2e_sketch_packed()
+    barrier(); t_e2e_pk = (time.perf_counter() - t0) / ne
+    tp = torch.tensor([t_e2e_pk], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    t_e2e_pk = float(tp.item())
+
+    # ---- the run checks its own outputs against the oracle (test infrastructure, never the thing timed): the registers of one genome
+    # of this rank, and 1000 sampled pairs of the matrix rows this rank computed
+    verify = None
+    if not args.no_verify and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        Lo = O.lib()
+        g = G // 2
+        hv = O.hash_stream(seq[g * Lg:(g + 1) * Lg].cpu().numpy().tobytes(), K, W)
+        oregs = np.empty(2 * S - 1); Lo.d2o_css_reset(oregs, S); Lo.d2o_css_update(oregs, S, hv, len(hv), None)
+        regs_ok = bool(np.array_equal(sig[g].cpu().numpy().view(np.uint64), oregs[:S].view(np.uint64)))
+        card_ok = bool(abs(float(card[g]) - Lo.d2o_css_card(oregs, S)) <= 1e-12 * abs(float(card[g])))
+        rng = np.random.default_rng(7)
+        ii = rng.integers(r0, max(r0 + 1, r1), size=1000); jj = rng.integers(0, n_all, size=1000)
+        keep = (ii < jj) & (ii < r1)
+        ii, jj = ii[keep], jj[keep]
+        tri0 = r0 * n_all - r0 * (r0 + 1) // 2
+        idx = ii * n_all - ii * (ii + 1) // 2 + (jj - ii - 1) - tri0
+        got = out[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        ra = all_sig[torch.from_numpy(ii).to(dev)].cpu().numpy(); rb = all_sig[torch.from_numpy(jj).to(dev)].cpu().numpy()
+        ca = all_card[torch.from_numpy(ii).to(dev)].cpu().numpy(); cb2 = all_card[torch.from_numpy(jj).to(dev)].cpu().numpy()
+        Lo.d2o_finalize.restype = C.c_float
+        exp = np.array([Lo.d2o_finalize(int((ra[t] > rb[t]).sum()), int((ra[t] < rb[t]).sum()), S, float(ca[t]), float(cb2[t]), 0, K, 0)
+                        for t in range(len(ii))], dtype=np.float32)
+        pairs_ok = bool(np.array_equal(got.view(np.uint32), exp.view(np.uint32)))
+        verify = {"genome": int(g), "registers_bit_identical_to_oracle": regs_ok, "cardinality_within_1e-12": card_ok,
+                  "pairs_checked": int(len(ii)), "pairs_bit_identical_to_oracle": pairs_ok}
+        if not (regs_ok and card_ok and pairs_ok):
+            raise SystemExit("bench.py: outputs differ from the oracle: %s" % json.dumps(verify))
+
     try:
         os.sched_setaffinity(0, affinity0)
     except OSError:
@@ -491,7 +549,7 @@ def main():
         "dtype": "u64+f64", "data": "synthetic", "config": workload_config(args, world),
         "phases_ms_per_step": {"sketch": sk_ms / steps, "allgather": ag_ms / steps, "cmp": cmp_ms / steps, "wall": wall_ms / steps},
         "roofline": {"bound": "hbm", "achieved": sk_ach, "peak": hbm_peak, "unit": "GB/s", "frac": sk_ach / hbm_peak, "traffic": traffic.get("sketch_main_bytes_per_launch"),
-                     "kernel": "sketch_kernel<windowed, FssMainConsumer>", "launch_ms": k_main_ms / max(1, k_main_n),
+                     "kernel": "sketch_fast_kernel<21, FssMainConsumer> (32-bit window keys)", "launch_ms": k_main_ms / max(1, k_main_n),
                      "algorithmic_bytes_per_launch": sk_bytes, "peak_source": peak_src,
                      "note": "1 B per k-mer position; the kernel is integer-ALU bound (~hundreds of int ops per k-mer), see DESIGN.md",
                      "boot_kernel_ms": k_boot_ms / max(1, k_boot_n)},
@@ -506,15 +564,29 @@ def main():
                 "e2e": {"value": (n_e2e_cmp * (n_e2e_cmp - 1) // 2) / t_e2e_cmp, "unit": "pairs/s",
                         "h2d_bytes_per_step": n_e2e_cmp * S * 8 + n_e2e_cmp * 8, "d2h_bytes_per_step": e_pairs * 4,
                         "call": "d2g_cmp_rows (pinned host registers in, float32 rows copied into a pinned host buffer while later rows compute)", "n": n_e2e_cmp}},
-        "e2e": {"value": Ge * (Lg - K + 1) * world / t_e2e_sk, "unit": "kmers/s", "h2d_bytes_per_step": Ge * Lg + (Ge + 1) * 8 + Ge * 4,
-                "d2h_bytes_per_step": Ge * S * 8 + Ge * 8, "call": "d2g_sketch_batch (pinned host sequence buffers in, host registers out; uploads in 256 MiB chunks overlapped with the kernels)",
+        "e2e": {"value": Ge * (Lg - K + 1) * world / t_e2e_sk, "unit": "kmers/s", "h2d_bytes_per_step": Ge * Lg // 4 + (Ge + 1) * 8 + Ge * 4,
+                "d2h_bytes_per_step": Ge * S * 8 + Ge * 8, "call": "d2g_sketch_batch (pinned host ASCII buffers in, host registers out; the library packs 128 Mi-base chunks to 2 bits per base on the host threads while earlier chunks upload and sketch)",
                 "batch": "%d genomes x %d bp per call" % (Ge, Lg)},
         "gpu_launches": launches, "clocks": clocks,
     }
+    line["roofline"]["pack_kernel_ms"] = k_pack_ms / max(1, k_pack_n)
+    line["roofline"]["pack_kernel_note"] = ("ASCII -> 2 bit + invalid bit packing on the device (reads 1 B, writes 0.375 B per base) runs before the main kernel "
+                                            "inside every step; its bytes are extra, not a discount (SURVEY 8(d))")
+    line["e2e"]["packed"] = {"value": Ge * (Lg - K + 1) * world / t_e2e_pk, "unit": "kmers/s", "h2d_bytes_per_step": nwp * (8 if nzw.value == 0 else 12),
+                             "call": "d2g_sketch_batch_packed (sequence packed once by d2g_pack_sequences, outside this leg: %.3f s for the batch = %.1f G bases/s on the host threads)"
+                                     % (t_host_pack, Ge * Lg / t_host_pack / 1e9)}
+    if verify is not None:
+        line["verify"] = verify
     if not args.no_cpu_baseline:
-        cb = cpu_reference_run(args.cpu_genomes, Lg, args.cpu_cmp_n, host_cores(), repeats=1, warm=True)
-        line["cpu_baseline"] = {"value": cb["sketch_kmers_s"], "unit": "kmers/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
-        line["cmp"]["cpu_baseline"] = {"value": cb["cmp_pairs_s"], "unit": "pairs/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+        cores = host_cores()
+        ng, nc = sample_sizes(args, cores)
+        cb = cpu_reference_run(ng, Lg, nc, cores, repeats=3)
+        line["cpu_baseline"] = {"value": cb["sketch_kmers_s"], "unit": "kmers/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+                                "threads_busy": cb["threads_busy"]["sketch"]}
+        line["cmp"]["cpu_baseline"] = {"value": cb["cmp_pairs_s"], "unit": "pairs/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+                                       "threads_busy": cb["threads_busy"]["cmp"]}
+        if not args.no_cli and world == 1:
+            line["e2e_cli"] = cli_vs_cli(ng, Lg, cores)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -228,14 +228,14 @@ struct FssMainConsumer {
     static constexpr int DCAP = 192;          // walks that outran the sparse state wait here for a tighter threshold
     static constexpr uint32_t APPROX_EMPTY = 0xFFFFFFFFu, APPROX_DBLMAX = (uint32_t)(FSS_KEY_EMPTY >> 32);
     static __host__ __device__ size_t smem_bytes(uint32_t m, bool windowed) { return (size_t)((m + 1) / 2) * 8 + (size_t)(qcap(windowed) + DCAP) * 8 + 64; }
-    uint32_t *approx; uint64_t *queue, *defer, *bcast; int *qn, *dn; Params p; double T; uint64_t rvmin; int drain_at, QCAP; uint32_t cur;
+    uint32_t *approx; uint64_t *queue, *defer, *bcast; int *qn, *dn, *nx; Params p; double T; uint64_t rvmin; int drain_at, QCAP; uint32_t cur;
     __device__ __forceinline__ void init(unsigned char *smem, const Params &pp, bool windowed) {
         QCAP = qcap(windowed);
         drain_at = QCAP - (windowed ? SK_SCAP : SK_TILE); cur = 0;
         p = pp; approx = reinterpret_cast<uint32_t *>(smem); queue = reinterpret_cast<uint64_t *>(smem) + (p.m + 1) / 2; defer = queue + QCAP; bcast = defer + DCAP;
-        qn = reinterpret_cast<int *>(bcast + 4); dn = qn + 1;
+        qn = reinterpret_cast<int *>(bcast + 4); dn = qn + 1; nx = dn + 1;
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) approx[i] = APPROX_EMPTY;
-        if (threadIdx.x == 0) { *qn = 0; *dn = 0; }
+        if (threadIdx.x == 0) { *qn = 0; *dn = 0; *nx = 0; }
         T = 1.7976931348623157e308; rvmin = 0;
     }
     static __device__ __forceinline__ uint64_t rvmin_for(double t, uint32_t m) {   // every rv below this certainly has ev_0 > t
@@ -266,19 +266,66 @@ struct FssMainConsumer {
         for (int round = 0;; ++round) {
             const int n = min(*qn, QCAP);
             const ApproxSink sink{approx, p.keys + (uint64_t)ent * p.m};
-            for (int q = threadIdx.x; q < n; q += SK_THREADS) {
-                const uint64_t x = queue[q];
+            // Walks differ in length (most end after one or two steps, some take ten): every lane draws its next element from a shared
+            // counter the moment its walk ends, and the loop body holds a single log evaluation that serves the first point of a new walk
+            // and the next point of a running one alike -- the lanes of a warp stay busy instead of waiting for the longest walk.
+            // Same arithmetic, point by point, as fss_walk (setsketch.h:369-423).
+            {
+                const uint32_t m = p.m;
+                const double bv0 = -1. / m;
+                bool active = false, more = true;
+                uint64_t x = 0, hid = 0; double ev = 0., carry = 0.; uint32_t i = 0;
+                WalkRng rng; rng.seed(0);
                 SparsePerm sp;
-                if (!fss_walk(x, p.m, T, sink, sp)) {
-                    const int slot = atomicAdd(dn, 1);
-                    if (slot < DCAP) defer[slot] = x;
-                    else {
-                        const unsigned long long g = atomicAdd(p.ovf_count, 1ULL);
-                        if (g < p.ovf_cap) { p.ovf[2 * g] = x; p.ovf[2 * g + 1] = ent; }
+                while (__any_sync(0xffffffffu, active || more)) {
+                    double nv, bv; bool fresh = false;
+                    if (!active && more) {
+                        const int q = atomicAdd(nx, 1);
+                        if (q < n) {
+                            x = queue[q]; hid = x;
+                            const uint64_t rv = cehash(x ^ FSS_XOR);
+                            nv = __dmul_rn(__ull2double_rn(rv), 0x1p-64); bv = bv0;
+                            rng.seed(rv); sp.n = 0; carry = 0.; i = 0;
+                            active = true; fresh = true;
+                        } else more = false;
+                    } else if (active) {
+                        const uint64_t rv = wyhash64(hid);
+                        bv = -(1. / (double)(m - (i + 1)));                               // getbeta, setsketch.h:300-302 (i + 1 points delivered so far)
+                        nv = __dmul_rn(__ull2double_rn(rv), 0x1p-64);
+                        ++i;
+                        if (__fma_rn(__dmul_rn(bv, flog_d(nv)), .7, ev) > T) active = false;    // conservative pre-test, setsketch.h:418
+                    }
+                    if (active) {
+                        const double lg = ref_log(nv);
+                        if (fresh) ev = __dmul_rn(bv, lg);
+                        else {
+                            const double inc = __fma_rn(bv, lg, -carry);                 // kahan.h:8-13 (contracted by the reference build)
+                            const double tmp = __dadd_rn(ev, inc);
+                            carry = __dadd_rn(__dadd_rn(tmp, -ev), -inc);
+                            ev = tmp;
+                        }
+                        if (ev > T) active = false;
+                        else {
+                            const uint32_t samp = rng.next() % (m - i);
+                            uint32_t idx;
+                            if (!sp.step(i, samp, idx)) {                                // sparse state exhausted: retry after the threshold has tightened
+                                const int slot = atomicAdd(dn, 1);
+                                if (slot < DCAP) defer[slot] = x;
+                                else {
+                                    const unsigned long long g = atomicAdd(p.ovf_count, 1ULL);
+                                    if (g < p.ovf_cap) { p.ovf[2 * g] = x; p.ovf[2 * g + 1] = ent; }
+                                }
+                                active = false;
+                            } else {
+                                sink.put(idx, dkey(ev));
+                                if (i + 1 == m) active = false;
+                            }
+                        }
                     }
                 }
             }
             __syncthreads();
+            if (threadIdx.x == 0) *nx = 0;
             uint32_t mx = 0;
             for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) mx = max(mx, approx[i]);
             #pragma unroll

@@ -16,8 +16,9 @@
 //           probability ~ (w-k+1)^2 / 2^33 per window): the exact minimizer is chosen by the full score, and the tile (and its
 //           successor) is put on the redo list, because such a tie can later change the minimizer without changing the
 //           32-bit minimum.
-// Every thread leaves the event flags of its eight windows in shared memory; during the next tile two warps compact them into the
-// two event lists (one 16-byte load per lane, a warp prefix sum) and the events are then hashed on dense warps.  Tiles on the redo list are recomputed by the
+// The event flags of a warp's 256 windows are compacted into the two event lists by the warp itself (type A in its lower half,
+// type B in its upper half: same instructions, one shared-memory atomic per half-warp and tile); the events are hashed on dense
+// warps during the next tile.  Tiles on the redo list are recomputed by the
 // exact 64-bit kernel (sketch_redo_kernel): set sketches are idempotent minima, so the union of both passes is exact.  An
 // event list that overflows (pathological repeats) also sends its tile to the redo list.  Everything the fast pass emits is
 // a true minimizer; everything it might have missed lies in a listed tile.
@@ -46,7 +47,7 @@ struct FastAux {
 };
 
 inline size_t sketch_fast_smem_bytes(size_t consumer_bytes) {
-    return (size_t)3 * SF_WBYTES + 32 + (size_t)2 * SF_KEYS * 4 + (size_t)SK_THREADS * 2 + (size_t)SF_LCAP * 2 * 2 + 32 + consumer_bytes;
+    return (size_t)3 * SF_WBYTES + 32 + (size_t)2 * SF_KEYS * 4 + (size_t)SF_LCAP * 2 * 2 + 32 + consumer_bytes;
 }
 
 // canonical k-mer at base offset b of a packed tile; 0 when one of its bases is invalid (encoder.h:568-571 + kmerutil.h:137-140)
@@ -66,10 +67,9 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
     const int need = a.w;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + 3 * SF_WBYTES);
     uint32_t *KH = reinterpret_cast<uint32_t *>(smem_raw + 3 * SF_WBYTES + 32);          // two key buffers of SF_KEYS words
-    uint16_t *FL = reinterpret_cast<uint16_t *>(KH + 2 * SF_KEYS);                        // per thread: type A flags | type B flags << 8 of its 8 windows
-    uint16_t *LA = FL + SK_THREADS;                                                       // type A events: key slot
+    uint16_t *LA = reinterpret_cast<uint16_t *>(KH + 2 * SF_KEYS);                        // type A events: key slot
     uint16_t *LB = LA + SF_LCAP;                                                          // type B events: key slot of the window's last key
-    uint32_t *ctl = reinterpret_cast<uint32_t *>(LB + SF_LCAP);                           // [0] nA, [1] nB, [2,3] redo flags by tile parity
+    uint32_t *ctl = reinterpret_cast<uint32_t *>(LB + SF_LCAP);                           // [par] nA, [2 + par] nB, [4 + par] redo flags; par = tile parity
     unsigned char *csmem = reinterpret_cast<unsigned char *>(ctl + 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Consumer cons;
@@ -77,7 +77,7 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
     if (tid == 0) {
         mbar_init(bar + 0, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);
         mbar_fence_init();
-        ctl[0] = ctl[1] = ctl[2] = ctl[3] = 0;
+        for (int i = 0; i < 8; ++i) ctl[i] = 0;
     }
     const uint64_t span_lo = a.pos_base + (uint64_t)blockIdx.x * a.span;
     const uint64_t span_hi = min(span_lo + a.span, a.pos_end);
@@ -102,40 +102,39 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
         bulk_g2s(dst + SF_NW * 8, a.seq.mask + (o >> 5), nw * 4, bar + b);
     };
 
-    // ---- event flags of a tile -> the two event lists (warp 7: type A, warp 6: type B) ----
-    // lane l owns threads 8l .. 8l+7 = windows 64l .. 64l+63 of the tile; one 16-byte load brings their flags
-    auto compact_events = [&](uint32_t par) {
-        if (warp < 6) return;
-        const bool isA = warp == 7;
-        const uint4 f = *reinterpret_cast<const uint4 *>(FL + 8 * lane);
-        const uint32_t sel = isA ? 0x6420u : 0x7531u;                               // low / high byte of every 16-bit entry
-        uint32_t m0 = __byte_perm(f.x, f.y, sel), m1 = __byte_perm(f.z, f.w, sel); // windows 64l .. +31, 64l+32 .. +63
-        const int cnt = __popc(m0) + __popc(m1);
+    // ---- event flags of a warp's 256 windows -> the two event lists ----
+    // flags = type A flags | type B flags << 8 of this thread's eight windows.  Lanes 0-15 build the A list, lanes 16-31 the B list: lane
+    // l (mod 16) takes the flags of threads 2l and 2l+1 of the warp = 16 consecutive windows.  All 32 lanes of the warp call this.
+    auto compact_events = [&](uint32_t flags, uint32_t par) {
+        const int h = lane & 15;
+        const uint32_t f0 = __shfl_sync(0xffffffffu, flags, 2 * h), f1 = __shfl_sync(0xffffffffu, flags, 2 * h + 1);
+        const bool isB = lane >= 16;
+        uint32_t m = isB ? ((f0 >> 8) | (f1 & 0xFF00u)) : ((f0 & 0xFFu) | ((f1 & 0xFFu) << 8));   // bit b: window 16h + b of the warp
+        const int cnt = __popc(m);
         int incl = cnt;
         #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int at = incl - cnt;
-        uint16_t *L = isA ? LA : LB;
-        const int slot0 = SF_OFF + 64 * lane;
-        for (; m0; m0 &= m0 - 1, ++at) if (at < SF_LCAP) L[at] = (uint16_t)(slot0 + __ffs(m0) - 1);
-        for (; m1; m1 &= m1 - 1, ++at) if (at < SF_LCAP) L[at] = (uint16_t)(slot0 + 32 + __ffs(m1) - 1);
-        if (lane == 0) {
-            ctl[isA ? 0 : 1] = (uint32_t)min(total, SF_LCAP);
-            if (total > SF_LCAP) atomicOr(ctl + 2 + par, 1u);                       // a list overflowed: the exact kernel redoes this tile
-        }
+        for (int o = 1; o < 16; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o, 16); if (h >= o) incl += y; }
+        const int total = __shfl_sync(0xffffffffu, incl, 15, 16);
+        int base = 0;
+        if (h == 0 && total) base = (int)atomicAdd(ctl + (isB ? 2 : 0) + par, (uint32_t)total);
+        base = __shfl_sync(0xffffffffu, base, 0, 16);
+        int at = base + incl - cnt;
+        uint16_t *L = isB ? LB : LA;
+        const int slot0 = SF_OFF + 256 * warp + 16 * h;
+        for (; m; m &= m - 1, ++at) if (at < SF_LCAP) L[at] = (uint16_t)(slot0 + __ffs(m) - 1);
+        if (h == 0 && base + total > SF_LCAP) atomicOr(ctl + 4 + par, 1u);          // a list overflowed: the exact kernel redoes this tile
     };
 
     // ---- staged events of one tile -> k-mers -> consumer (all threads; dense warps) ----
     // W / M / keys: the tile's packed words and key buffer; boff: base offset of the k-mer whose key sits in slot SF_OFF
     auto drain_events = [&](const uint64_t *W, const uint32_t *M, const uint32_t *keys, int boff, uint32_t par) {
-        const int nA = (int)ctl[0], nB = (int)ctl[1];
+        const int nA = min((int)ctl[par], SF_LCAP), nB = min((int)ctl[2 + par], SF_LCAP);
         for (int i = tid; i < nA; i += SK_THREADS) {
             const int e = LA[i];
             const uint64_t km = tile_canonical_or_zero(W, M, boff + (e - SF_OFF), k);
             cons.consume(wang64(km ^ a.xormask));                                   // maskfn, src/enums.h:136-140
         }
-        for (int i = (tid - 96) & (SK_THREADS - 1); i < nB; i += SK_THREADS) {        // warps 3, 4, 5 first: warps 0-2 hash the A events, warps 6-7 compacted the flags
+        for (int i = (tid - 96) & (SK_THREADS - 1); i < nB; i += SK_THREADS) {        // warps 3, 4, 5 first: warps 0-2 hash the A events
             const int e = LB[i];
             // the window's keys sit in slots e-(wsz-1) .. e; in the padded layout they are contiguous except for one possible 4-word pad
             const int x0 = e - (wsz - 1);
@@ -167,16 +166,16 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
                         if (s2 != best) differ = true;
                         if (s2 < best) { best = s2; km = k2; }
                     }
-                if (differ) atomicOr(ctl + 2 + par, 3u);                             // redo this tile and the next one
+                if (differ) atomicOr(ctl + 4 + par, 3u);                             // redo this tile and the next one
             }
             cons.consume(wang64(km ^ a.xormask));
         }
     };
     // thread 0, after the barrier that ends the drain of a tile: put it on the redo list when flagged
     auto settle_redo = [&](uint32_t par, uint64_t t0) {
-        const uint32_t f = ctl[2 + par];
+        const uint32_t f = ctl[4 + par];
         if (f) {
-            ctl[2 + par] = 0;
+            ctl[4 + par] = 0;
             const unsigned long long at = atomicAdd(fx.redo_count, (f & 2u) ? 2ULL : 1ULL);
             if (at < fx.redo_cap) fx.redo_list[at] = t0;
             if ((f & 2u) && at + 1 < fx.redo_cap) fx.redo_list[at + 1] = t0 + SF_TILE;
@@ -197,11 +196,11 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
             cur_ent = ent;
             cons.begin_entity(ent, p0 - span_lo);
         }
-        // Pipeline over the tiles of the segment.  Tile n: phase 1 computes its keys while two warps compact the event flags of tile
-        // n-1; phase 2 hashes the events of tile n-1 and computes minima + event flags of tile n.  `prev` = tile n-1, `prev2` = tile n-2.
-        bool first = true, have_prev = false, have_prev2 = false;
+        // Pipeline over the tiles of the segment.  Tile n: phase 1 hashes the events of tile n-1 and computes the keys of tile n;
+        // phase 2 computes the sliding minima and the event lists of tile n.
+        bool first = true, have_prev = false;
         uint32_t par = 0;                                             // parity of the current tile within the segment
-        uint32_t prev_wb = 0; int prev_boff = 0; uint64_t prev_t0 = 0, prev2_t0 = 0;
+        uint32_t prev_wb = 0; int prev_boff = 0; uint64_t prev_t0 = 0;
         if (tid == 0) issue_tile(wb, p0, (int)min((uint64_t)SF_TILE, p1 - p0));
         for (uint64_t t0 = p0; t0 < p1; t0 += SF_TILE, par ^= 1u) {
             const int nstart = (int)min((uint64_t)SF_TILE, p1 - t0);
@@ -214,9 +213,11 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
             // ---- phase 1 ----
             if (tid == 0) {
                 if (t0 + SF_TILE < p1) issue_tile(next_buf(wb), t0 + SF_TILE, (int)min((uint64_t)SF_TILE, p1 - t0 - SF_TILE));
-                if (have_prev2) settle_redo(par, prev2_t0);           // tile n-2 has the parity of tile n
+                ctl[par] = 0; ctl[2 + par] = 0;                       // this tile's event counters (last read two barriers ago)
             }
-            if (have_prev) compact_events(par ^ 1u);
+            if (have_prev)
+                drain_events(reinterpret_cast<const uint64_t *>(smem_raw + prev_wb * SF_WBYTES),
+                             reinterpret_cast<const uint32_t *>(smem_raw + prev_wb * SF_WBYTES + SF_NW * 8), KH + (par ^ 1u) * SF_KEYS, prev_boff, par ^ 1u);
             mbar_wait(bar + wb, (wphase >> wb) & 1u);
             wphase ^= 1u << wb;
             if (jn > 0) {
@@ -247,9 +248,7 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
             __syncthreads();
             cons.end_tile(cur_ent);
             // ---- phase 2 ----
-            if (have_prev)
-                drain_events(reinterpret_cast<const uint64_t *>(smem_raw + prev_wb * SF_WBYTES),
-                             reinterpret_cast<const uint32_t *>(smem_raw + prev_wb * SF_WBYTES + SF_NW * 8), KH + (par ^ 1u) * SF_KEYS, prev_boff, par ^ 1u);
+            if (tid == 0 && have_prev) settle_redo(par ^ 1u, prev_t0);
             uint32_t flags = 0;
             if (jn > 0) {
                 const int B0 = SF_OFF + j0;
@@ -322,18 +321,14 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
                 if (jn < SK_PPT) { fa &= (1u << jn) - 1u; fb &= (1u << jn) - 1u; }
                 flags = fa | (fb << 8);
             }
-            FL[tid] = (uint16_t)flags;
+            compact_events(flags, par);
             __syncthreads();
-            have_prev2 = have_prev; prev2_t0 = prev_t0;
             have_prev = true; prev_wb = wb; prev_boff = boff; prev_t0 = t0;
             wb = next_buf(wb);
             first = false;
         }
-        // the last tile of the segment (it has the parity par ^ 1): compact and hash its events, settle the redo flags
+        // the last tile of the segment (it has the parity par ^ 1): its events, then its redo flag
         if (have_prev) {
-            if (tid == 0 && have_prev2) settle_redo(par, prev2_t0);
-            compact_events(par ^ 1u);
-            __syncthreads();
             drain_events(reinterpret_cast<const uint64_t *>(smem_raw + prev_wb * SF_WBYTES),
                          reinterpret_cast<const uint32_t *>(smem_raw + prev_wb * SF_WBYTES + SF_NW * 8), KH + (par ^ 1u) * SF_KEYS, prev_boff, par ^ 1u);
             __syncthreads();

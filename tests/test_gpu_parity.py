@@ -897,5 +897,5 @@ def test_fss_many_small_entities_long_walk_queue_in_groups(S, w, budget, monkeyp
     for e in (0, 7, 500, 1199):
         hv = O.hash_stream(recs[e], 31, w)
         regs = np.empty(2 * S - 1); ids = np.zeros(S, dtype=np.uint64)
-        L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), ids)
+        L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), ids.ctypes.data)
         assert np.array_equal(r["ids"][e], ids), e
