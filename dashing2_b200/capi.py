@@ -38,6 +38,8 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c
 EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stream", "d2g_sync", "d2g_launch_count",
            "d2g_set_timing", "d2g_get_timing",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_distinct_kmers", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
+           "d2g_init_devices", "d2g_comm_unique_id", "d2g_comm_init_rank", "d2g_comm_init_all", "d2g_comm_size", "d2g_comm_rank", "d2g_comm_destroy",
+           "d2g_cmp_rows_sharded_dev",
            "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_free"]
@@ -74,6 +76,14 @@ def load():
     L.d2g_distinct_kmers.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, vp]; L.d2g_distinct_kmers.restype = C.c_int
     L.d2g_sketch_batch_dev.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, u64, u32, u64, vp, vp, vp, vp]
     L.d2g_sketch_batch_dev.restype = C.c_int
+    L.d2g_init_devices.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]; L.d2g_init_devices.restype = C.c_int
+    L.d2g_comm_unique_id.argtypes = [vp]; L.d2g_comm_unique_id.restype = C.c_int
+    L.d2g_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]; L.d2g_comm_init_rank.restype = C.c_int
+    L.d2g_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]; L.d2g_comm_init_all.restype = C.c_int
+    L.d2g_comm_size.argtypes = [vp]; L.d2g_comm_size.restype = C.c_int
+    L.d2g_comm_rank.argtypes = [vp]; L.d2g_comm_rank.restype = C.c_int
+    L.d2g_comm_destroy.argtypes = [vp]; L.d2g_comm_destroy.restype = C.c_int
+    L.d2g_cmp_rows_sharded_dev.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, u64, u64, vp]; L.d2g_cmp_rows_sharded_dev.restype = C.c_int
     L.d2g_packed_words.argtypes = [u64]; L.d2g_packed_words.restype = u64
     L.d2g_pack_sequences.argtypes = [vp, vp, u64, vp, vp, C.POINTER(u64)]; L.d2g_pack_sequences.restype = C.c_int
     L.d2g_pack_dev.argtypes = [vp, vp, u64, vp, vp]; L.d2g_pack_dev.restype = C.c_int
@@ -297,6 +307,19 @@ class Context:
 
     def cmp_rows_dev(self, p: CmpParams, regs_d, cards_d, row_begin, row_end, out_d):
         _check(self.L.d2g_cmp_rows_dev(self.h, C.byref(p), regs_d, cards_d, row_begin, row_end, out_d))
+
+    # ---- several GPUs ----
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(self.L.d2g_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_rank(self, nranks: int, rank: int, uid: bytes):
+        _check(self.L.d2g_comm_init_rank(self.h, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    def cmp_rows_sharded_dev(self, p: CmpParams, local_regs_d, local_cards_d, local_begin, local_n, row_begin, row_end, out_d):
+        """Collective over the context's communicator (d2g_cmp_rows_sharded_dev)."""
+        _check(self.L.d2g_cmp_rows_sharded_dev(self.h, C.byref(p), local_regs_d, local_cards_d, local_begin, local_n, row_begin, row_end, out_d))
 
     def cmp_rows_size(self, p: CmpParams, row_begin, row_end) -> int:
         nv = C.c_uint64(0)

@@ -225,7 +225,7 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
         KernelTimer kt(c, D2G_T_CMP_PREP);
         cc.valid = true; cc.regs = base.regs; cc.lo1 = lo1; cc.hi1 = hi1; cc.lo2 = lo2; cc.hi2 = hi2; cc.S = S; cc.kind = p->cmp_kind; cc.mode = mode;
         CU(cudaMemsetAsync(c->c16codes.p, 0, code_bytes, st));
-        const bool use_hash = mode == 1 && U <= C16_HASH_MAX_SKETCHES && !getenv("D2G_C16_NO_HASH");
+        const bool use_hash = mode == 1 && U <= C16_HASH_MAX_SKETCHES && !getenv("D2G_C16_NO_HASH") && !c->c16_sharded;
         if (use_hash) {
             // != only: injective codes suffice -> open-addressing table per register position, no sort
             const uint32_t TS = (uint32_t)std::max<uint64_t>(64, U + U / 2);
@@ -315,6 +315,10 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     if (const char *ev = getenv("D2G_C16_MAXJOB")) M = std::max<uint64_t>(256, std::min<uint64_t>(M, strtoull(ev, nullptr, 10) / 128 * 128));  // test knob
     M = std::min<uint64_t>(M, (0x7fffffffULL / S) / 128 * 128);          // one segmented sort holds < 2^31 items
     if (S > 65535 || M < 256) path = 0;                                  // 16-bit counters / degenerate blocks
+    if (c->c16_sharded) {                                                 // the registers of the other ranks are not here: order codes only
+        if (!path && (S > 65535 || M < 256)) return fail(D2G_EUNSUPPORTED, "sharded comparison needs sketchsize <= 65535");
+        path = 1;
+    }
     if (!path) return launch_cmp_f64(c, p, a, r0, r1, cb, ce, nullptr, 0);
     auto up64 = [](uint64_t x) { return (x + 63) / 64 * 64; };
     // Decomposition into jobs of at most Mj sketches: one range when the rows lie inside the columns, two ranges
@@ -344,7 +348,8 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
     plan(M, jobs);
     const uint64_t g0 = std::min(r0, cb), g1 = std::max(r1, ce), N = g1 - g0;
     bool use_global = jobs.size() > 1 && 2 * ((N + 31) / 32) * 4 <= 200 * 1024 && N < 0xFFFFFFF0ULL && !getenv("D2G_C16_NO_GLOBAL");   // bitmap + prefix in shared memory
-    if (ne_only && !getenv("D2G_C16_NO_HASH") && M > d2g::C16_HASH_MAX_SKETCHES) {
+    if (c->c16_sharded) use_global = true;                                // ranks of all sketches were gathered: every job derives its codes from them
+    if (ne_only && !getenv("D2G_C16_NO_HASH") && M > d2g::C16_HASH_MAX_SKETCHES && !c->c16_sharded) {
         // != only: jobs of <= 16 384 sketches take their codes from a hash table (no sort).  Pick the cheaper plan with measured
         // per-element costs (B200, S=4096): segmented sort + ranks 1.2e-10 s, local codes from global ranks 0.8e-11 s, hash codes 2.8e-11 s.
         plan(d2g::C16_HASH_MAX_SKETCHES, hjobs);
@@ -355,7 +360,7 @@ int launch_cmp(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpConsts &k, con
         for (const Job &j : hjobs) cost_hashed += (double)job_sketches(j) * S * 2.8e-11 + 15e-6;
         if (cost_hashed < cost_sorted) { jobs.swap(hjobs); use_global = false; }
     }
-    if (use_global) { if (int rc = c16_build_global(c, p, regs_d, g0, N)) return rc; }
+    if (use_global && !c->c16_sharded) { if (int rc = c16_build_global(c, p, regs_d, g0, N)) return rc; }
     for (const Job &j : jobs)
         if (int rc = run_cmp16_job(c, p, a, j.lo1, j.hi1, j.lo2, j.hi2, j.r0, j.r1, j.c0, j.c1)) return rc;
     return D2G_OK;
@@ -577,3 +582,94 @@ int d2g_cmp_counts(d2g_ctx *c, uint32_t S, int32_t cmp_kind, const double *rows,
 }
 
 } // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// sharded comparison: sketches live on the rank that made them, one exchange step over NCCL
+// -------------------------------------------------------------------------------------------------
+#include "nccl_dl.h"
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(D2G_ECUDA, "%s failed: %s", #call, d2g_nccl::g_api.GetErrorString(r_)); } while (0)
+
+namespace {
+// Collective.  Rank r holds sketches [r * n_per, min(n, (r+1) * n_per)), n_per = ceil(n / nranks).  What the tile kernel needs of a
+// sketch is not its registers but, per register position, the rank of the value among all n sketches (cmp16_kernels.cuh).  So:
+//   1. all-to-all (grouped ncclSend / ncclRecv): rank r receives register positions [r * Sp, (r+1) * Sp) of every sketch, Sp = ceil(S / nranks);
+//   2. rank r sorts its Sp positions over all n sketches (1 / nranks of the single-GPU preparation) -> u32 ranks [Sp][n_pad];
+//   3. ncclAllGather of the rank slices (4 bytes per register instead of the 8 of an f64 all-gather) and of the cardinalities.
+// Afterwards ctx->c16g describes the gathered ranks and launch_cmp derives every job's 16-bit codes from them.
+int sharded_prepare(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d, uint64_t local_begin, uint64_t local_n) {
+    using namespace d2g;
+    if (!c->nccl_comm) return fail(D2G_EINVAL, "this context owns no communicator (d2g_comm_init_rank / d2g_init_devices)");
+    const uint64_t n = p->n, R = (uint64_t)c->nranks, r = (uint64_t)c->rank;
+    const uint32_t S = p->sketchsize;
+    if (S > 65535) return fail(D2G_EUNSUPPORTED, "sharded comparison needs sketchsize <= 65535");
+    if (p->cmp_kind >= D2G_CMP_SS_COMPRESSED && false) return fail(D2G_EUNSUPPORTED, "unreachable");
+    const uint64_t n_per = (n + R - 1) / R, n_pad = n_per * R;
+    const uint64_t exp_begin = std::min(n, r * n_per), exp_n = std::min(n, (r + 1) * n_per) - exp_begin;
+    if (local_begin != exp_begin || local_n != exp_n)
+        return fail(D2G_EINVAL, "rank %d of %d must hold sketches [%llu, %llu) of %llu (got [%llu, %llu))", c->rank, c->nranks, (unsigned long long)exp_begin,
+                    (unsigned long long)(exp_begin + exp_n), (unsigned long long)n, (unsigned long long)local_begin, (unsigned long long)(local_begin + local_n));
+    if (2 * ((n_pad + 31) / 32) * 4 > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sharded comparison: too many sketches (%llu) for the shared-memory rank bitmap", (unsigned long long)n);
+    const uint32_t Sp = (uint32_t)((S + R - 1) / R);
+    const uint64_t blk = n_per * Sp;                                      // doubles per (source rank, destination rank) block
+    cudaStream_t st = c->stream;
+    ncclComm_t comm = static_cast<ncclComm_t>(c->nccl_comm);
+    const auto &nc = d2g_nccl::g_api;
+    if (int rc = c->xsend.reserve(blk * R * 8)) return rc;
+    if (int rc = c->xrecv.reserve(blk * R * 8)) return rc;
+    if (int rc = c->xrank.reserve((uint64_t)Sp * n_pad * 4)) return rc;
+    if (int rc = c->c16grank.reserve((uint64_t)Sp * R * n_pad * 4)) return rc;
+    if (int rc = c->xcards.reserve(n_pad * 8 + n_per * 8)) return rc;
+    if (int rc = c->c16flag.reserve(256)) return rc;
+    KernelTimer kt(c, D2G_T_CMP_PREP);
+    double *send = c->xsend.as<double>(), *recv = c->xrecv.as<double>();
+    // 1. my registers, split by destination: block d = positions [d * Sp, (d+1) * Sp) of my sketches as an [n_per][Sp] matrix (zero padded)
+    CU(cudaMemsetAsync(send, 0, blk * R * 8, st));
+    for (uint64_t d = 0; d < R; ++d) {
+        const uint64_t c0 = d * Sp;
+        if (c0 >= S || !local_n) continue;
+        const uint64_t wcols = std::min<uint64_t>(Sp, S - c0);
+        CU(cudaMemcpy2DAsync(send + d * blk, (size_t)Sp * 8, local_regs_d + c0, (size_t)S * 8, (size_t)wcols * 8, (size_t)local_n, cudaMemcpyDeviceToDevice, st));
+    }
+    NC(nc.GroupStart());
+    for (uint64_t d = 0; d < R; ++d) {
+        NC(nc.Send(send + d * blk, blk, ncclFloat64, (int)d, comm, st));
+        NC(nc.Recv(recv + d * blk, blk, ncclFloat64, (int)d, comm, st));
+    }
+    NC(nc.GroupEnd());
+    // 2. recv is the [n_pad][Sp] matrix of my positions over all sketches: rank every position
+    CU(cudaMemsetAsync(c->c16flag.p, 0, 4, st));
+    C16Job j{};
+    j.regs = recv; j.S = Sp; j.gA0 = 0; j.nA = (uint32_t)n_pad; j.nB = 0; j.posB0 = 0; j.KP = 0;
+    if (int rc = c16_sort_rank(c, p, j, nullptr, c->xrank.as<uint32_t>(), c->c16flag.as<int>())) return rc;
+    // 3. gather the rank slices, the cardinalities and the "a register was NaN" flag
+    NC(nc.AllGather(c->xrank.p, c->c16grank.p, (size_t)Sp * n_pad, ncclUint32, comm, st));
+    double *cards_all = c->xcards.as<double>(), *cards_mine = cards_all + n_pad;
+    CU(cudaMemsetAsync(cards_mine, 0, n_per * 8, st));
+    if (local_n) CU(cudaMemcpyAsync(cards_mine, local_cards_d, local_n * 8, cudaMemcpyDeviceToDevice, st));
+    NC(nc.AllGather(cards_mine, cards_all, n_per, ncclFloat64, comm, st));
+    NC(nc.AllReduce(c->c16flag.p, c->c16flag.p, 1, ncclInt32, ncclMax, comm, st));
+    int h_flag = 0;
+    CU(cudaMemcpyAsync(&h_flag, c->c16flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_flag) return fail(D2G_EUNSUPPORTED, "sharded comparison: a register is NaN; gather the registers and use d2g_cmp_rows_dev (its f64 kernel handles NaN as the reference does)");
+    auto &g = c->c16g;
+    g.valid = true; g.regs = reinterpret_cast<const double *>(c->c16grank.p); g.g0 = 0; g.N = n_pad; g.S = S; g.kind = p->cmp_kind;
+    return D2G_OK;
+}
+} // namespace
+
+extern "C" int d2g_cmp_rows_sharded_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d,
+                                        uint64_t local_begin, uint64_t local_n, uint64_t r0, uint64_t r1, float *out_d) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    CU(cudaSetDevice(c->device));
+    c->c16cache.valid = false; c->c16g.valid = false;
+    d2g::CmpConsts k;
+    if (int rc = make_consts(c, p, &k)) return rc;
+    if (int rc = sharded_prepare(c, p, local_regs_d, local_cards_d, local_begin, local_n)) return rc;
+    c->c16_sharded = true;
+    const int rc = launch_cmp(c, p, k, c->c16g.regs, c->xcards.as<double>(), r0, r1, out_d, nullptr, nullptr);
+    c->c16_sharded = false;
+    return rc;
+}

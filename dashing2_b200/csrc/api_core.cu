@@ -46,6 +46,7 @@ void d2g_destroy(d2g_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    d2g_comm_destroy(c);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
     if (c->evd[0]) cudaEventDestroy(c->evd[0]);

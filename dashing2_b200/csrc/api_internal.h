@@ -62,6 +62,9 @@ struct d2g_ctx {
     cudaEvent_t ev[2] = {nullptr, nullptr}, evd[2] = {nullptr, nullptr};
     uint32_t lut_S = 0; int lut_k = -1;
     bool timing = false;
+    void *nccl_comm = nullptr; int nranks = 1, rank = 0;        // communicator this context owns (api_comm.cu), null = single device
+    bool c16_sharded = false;                                    // compare launcher: order codes come from gathered global ranks only (api_cmp.cu)
+    DevBuf xsend, xrecv, xrank, xcards;                          // sharded compare: register exchange, local rank slice, gathered cardinalities
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev[D2G_T_NCLASSES];
 };
 

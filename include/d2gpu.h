@@ -216,6 +216,29 @@ int d2g_cmp_counts(d2g_ctx *ctx, uint32_t sketchsize, int32_t cmp_kind,
                    uint32_t *c0_out, uint32_t *c1_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Several GPUs.  The reference shards its all-pairs phase over output rows inside one process (src/emitrect.cpp:198-326); here the
+ * rows shard over GPUs, each context owning an NCCL communicator (libnccl.so.2 is resolved at run time when one is first asked for).
+ *   d2g_init_devices      one process, several devices: contexts + their communicator (d2g_init(ctx**, devices, ndev));
+ *   d2g_comm_unique_id /  one process per GPU (torchrun, MPI): rank 0 makes an id, hands it to the others (any transport), every
+ *   d2g_comm_init_rank    rank joins with its own context.
+ * Sketching needs no communication (files are sharded).  d2g_cmp_rows_sharded_dev is the path's one exchange step: rank r holds the
+ * registers of sketches [r * n_per, min(n, (r+1) * n_per)), n_per = ceil(n / nranks), as it produced them; the ranks exchange register
+ * POSITIONS (all-to-all), each ranks its share of the positions over all sketches, and the 32-bit ranks are all-gathered -- half the
+ * bytes of an f64 all-gather and 1/nranks of the order-code preparation per GPU.  Every rank then computes rows [row_begin, row_end)
+ * of the matrix over ALL n sketches into out_d (packed from row_begin).  Collective: every rank of the communicator must call it.
+ * ---------------------------------------------------------------------------------------------- */
+#define D2G_COMM_ID_BYTES 128
+int d2g_init_devices(d2g_ctx **ctxs, const int *devices, int ndev);
+int d2g_comm_unique_id(void *id_out /* D2G_COMM_ID_BYTES */);
+int d2g_comm_init_rank(d2g_ctx *ctx, int nranks, int rank, const void *id /* D2G_COMM_ID_BYTES */);
+int d2g_comm_init_all(d2g_ctx **ctxs, int n);   /* contexts of one process on distinct devices */
+int d2g_comm_size(const d2g_ctx *ctx);
+int d2g_comm_rank(const d2g_ctx *ctx);
+int d2g_comm_destroy(d2g_ctx *ctx);
+int d2g_cmp_rows_sharded_dev(d2g_ctx *ctx, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d,
+                             uint64_t local_begin, uint64_t local_n, uint64_t row_begin, uint64_t row_end, float *out_d);
+
+/* ------------------------------------------------------------------------------------------------
  * LSH-assisted top-k neighbour graph (--topk K).  Replaces build_index (src/index_build.cpp:53-165) over
  * SetSketchIndex (src/ssi.h:290-453, default --nLSH 2), refine_results (src/refine.cpp:6-81) and the CSR
  * assembly of emit_neighbors (src/emitnn.cpp:12-52).  Output is the reference's sequential (-p1) result

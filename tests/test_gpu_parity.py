@@ -899,3 +899,37 @@ def test_fss_many_small_entities_long_walk_queue_in_groups(S, w, budget, monkeyp
         regs = np.empty(2 * S - 1); ids = np.zeros(S, dtype=np.uint64)
         L.d2o_css_reset(regs, S); L.d2o_css_update(regs, S, hv, len(hv), ids.ctypes.data)
         assert np.array_equal(r["ids"][e], ids), e
+
+
+@pytest.mark.parametrize("n,S,shape,measure,kind", [(3000, 256, "symmetric", "similarity", 0), (2500, 100, "asymmetric", "containment", 0),
+                                                     (1800, 512, "panel", "poisson_llr", 0), (2000, 128, "symmetric", "similarity", 1)])
+def test_sharded_compare_single_rank_equals_plain_compare(n, S, shape, measure, kind):
+    """d2g_cmp_rows_sharded_dev with a one-rank communicator walks the whole exchange path (register all-to-all, rank slices,
+    all-gather, codes from the gathered ranks) and must give the float32 rows of d2g_cmp_rows / the oracle."""
+    import torch
+    from dashing2_b200 import capi, synth
+    regs, cards = synth.synthetic_sketches(n, S, seed=n + S, n_families=max(2, n // 50), p_lo=0.02, p_hi=0.8)
+    cards = cards * (1 + np.arange(n) % 4)
+    if kind == 1:
+        regs = np.round(regs * 64) / 64                      # equality kind: make equal registers common
+    c = capi.Context(0)
+    c.comm_init_rank(1, 0, c.comm_unique_id())
+    nq = 700 if shape == "panel" else 0
+    p = c.cmp_params(S, n, shape, measure, k=31, cmp_kind=kind, nq=nq)
+    nrows = n - nq
+    dev = torch.device("cuda", 0)
+    t_regs = torch.from_numpy(regs).to(dev); t_cards = torch.from_numpy(cards).to(dev)
+    for r0, r1 in ((0, nrows), (nrows // 3, nrows // 2)):
+        nv = c.cmp_rows_size(p, r0, r1)
+        out = torch.empty(nv, dtype=torch.float32, device=dev)
+        c.cmp_rows_sharded_dev(p, t_regs.data_ptr(), t_cards.data_ptr(), 0, n, r0, r1, out.data_ptr())
+        c.sync()
+        exp = ctx().cmp_rows(regs, cards, p, r0, r1)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), exp.view(np.uint32)), (shape, r0, r1)
+    full = O.allpairs(regs, cards, shape, measure, k=31, cmp_kind=kind, nq=nq)
+    nv = c.cmp_rows_size(p, 0, nrows)
+    out = torch.empty(nv, dtype=torch.float32, device=dev)
+    c.cmp_rows_sharded_dev(p, t_regs.data_ptr(), t_cards.data_ptr(), 0, n, 0, nrows, out.data_ptr())
+    c.sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), full.view(np.uint32))
+    c.close()
