@@ -239,7 +239,8 @@ def workload_config(args, n_gpus):
                         "all-pairs symmetric" % (args.genomes, args.genome_len),
             "genomes_per_gpu": args.genomes, "genome_len": args.genome_len, "k": K, "w": W, "sketchsize": S,
             "sketch_mode": "--full-setsketch", "cmp": "symmetric all-pairs, similarity, f64 registers",
-            "parallelism": "files sharded over %d GPU(s), no collective; cmp rows equal-area sharded after one all-gather" % n_gpus,
+            "parallelism": "files sharded over %d GPU(s), no collective; cmp rows equal-area sharded, one exchange step inside the library over its own NCCL communicator "
+                           "(register all-to-all, each GPU ranks S/N register positions, all-gather of the 32-bit ranks)" % n_gpus,
             "l2": "inputs larger than L2 (sequence buffer %.1f GB, register matrix %.0f MB per GPU)" %
                   (args.genomes * args.genome_len / 1e9, args.genomes * S * 8 / 1e6)}
 
@@ -333,6 +334,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = capi.Context(local)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    if world > 1:
+        # the library owns its communicator; torch.distributed only carries the 128-byte id to the other ranks
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_rank(world, rank, uid[0])
 
     G, Lg = args.genomes, args.genome_len
     n_all = G * world
@@ -359,13 +365,12 @@ def main():
         ctx.sketch_batch_dev(p_sk, seq.data_ptr(), rec_off.data_ptr(), rec_ent.data_ptr(), G, G, G * Lg,
                              sig_d=sig.data_ptr(), card_d=card.data_ptr())
         evs[1].record(ext)
-        if world > 1:
-            ext.synchronize()
-            dist.all_gather_into_tensor(all_sig, sig)
-            dist.all_gather_into_tensor(all_card, card)
-            torch.cuda.current_stream().synchronize()
         evs[2].record(ext)
-        ctx.cmp_rows_dev(p_cmp, all_sig.data_ptr(), all_card.data_ptr(), r0, r1, out.data_ptr())
+        if world > 1:
+            # the path's one exchange step, inside the library: register all-to-all + 1/N of the ranking + all-gather of 32-bit ranks (NCCL)
+            ctx.cmp_rows_sharded_dev(p_cmp, sig.data_ptr(), card.data_ptr(), rank * G, G, r0, r1, out.data_ptr())
+        else:
+            ctx.cmp_rows_dev(p_cmp, all_sig.data_ptr(), all_card.data_ptr(), r0, r1, out.data_ptr())
         evs[3].record(ext)
         ext.synchronize()
         return evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])
@@ -399,6 +404,10 @@ def main():
     k_pack_ms, k_pack_n = ctx.get_timing(4)
     ctx.set_timing(False)
 
+    if world > 1:        # outside the timed region: the full register matrix for the host-buffer leg and the oracle check
+        dist.all_gather_into_tensor(all_sig, sig)
+        dist.all_gather_into_tensor(all_card, card)
+        torch.cuda.synchronize()
     # max over ranks of the device-timed totals
     tot = torch.tensor([sum(ts), sum(tg), sum(tc), sum(ts) + sum(tg) + sum(tc)], dtype=torch.float64, device=dev)
     if world > 1:

@@ -4,6 +4,7 @@
 #include "api_sketch_launch.h"
 #include "fss_kernels.cuh"
 #include "host/pack_host.h"
+#include <chrono>
 
 namespace {
 __global__ void opmh_ids_kernel(const uint64_t *regs, uint64_t *ids, uint64_t n_ent, uint32_t m, uint32_t S) {
@@ -409,7 +410,7 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
     const bool opmh_mincount = p->mode == D2G_MODE_OPMH && p->count_threshold > 1;   // counts need the whole batch sorted at once
     const bool chunked = (p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH) && !opmh_mincount;
     auto off_at = [&](uint64_t r) -> uint64_t { return n_rec ? rec_off[r] : 0; };
-    uint64_t target = 128ULL << 20;                   // bases per chunk
+    uint64_t target = 384ULL << 20;                   // bases per chunk (per-chunk launches and read-backs cost ~0.5 ms: amortised over >= 1.5 ms of kernel)
     if (const char *ev = getenv("D2G_CHUNK_BYTES")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
     if (!chunked) target = ~0ULL;
     const std::vector<Chunk> chunks = make_chunks(rec_off, rec_entity, n_rec, n_entities, target);
@@ -425,6 +426,19 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
     // Producer: runs on its own host thread so that packing and uploading chunk i+1 overlap the kernels of chunk i, whose launcher
     // may block on the stream (Full SetSketch reads a counter back per chunk).
     std::atomic<size_t> uploaded{0}; std::atomic<int> prc{0};
+    bool ascii_pinned = false, fixed_f = false;
+    double hybrid_f = 0.7;
+    if (hs.ascii && total_len) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, hs.ascii) == cudaSuccess) ascii_pinned = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+        if (const char *ev = getenv("D2G_HYBRID_F")) { hybrid_f = std::max(0., std::min(1., atof(ev))); fixed_f = true; }   // 1 = pack everything on the host
+        if (ascii_pinned) {                                // device staging of the ASCII tails: sized once for the largest chunk
+            uint64_t mw = 0;
+            for (size_t i = 0; i < nch; ++i) mw = std::max(mw, w_hi(i) - w_lo(i));
+            if (int rc = c->seq.reserve(mw * 32 + 4096)) { free_evs(); return rc; }
+        }
+    }
     std::string perr;
     auto producer = [&]() {
         cudaSetDevice(c->device);
@@ -433,18 +447,42 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
             cudaError_t e = cudaSuccess;
             if (b > a) {
                 if (hs.ascii) {
+                    // Hybrid: the tail [ws, b) of the chunk goes up as ASCII (DMA from page-locked memory costs no host cycles) and is packed by
+                    // the device; the head [a, ws) is packed by the host threads meanwhile and goes up at a quarter of the bytes.  The split
+                    // balances host packing against the link: f / P = ((1 - f) + f / 4) / B for packing rate P and link rate B (bases/s, bytes/s).
                     const int slot = (int)(i % 3);
                     if (!c->stage_free[slot]) cudaEventCreateWithFlags(&c->stage_free[slot], cudaEventDisableTiming);
                     else cudaEventSynchronize(c->stage_free[slot]);          // the copy that last used this slot has left it
-                    if (c->stage[slot].reserve((b - a) * 12) != D2G_OK) { perr = d2g_last_error(); prc = D2G_ENOMEM; break; }
+                    uint64_t ws = b;
+                    if (ascii_pinned && hybrid_f < 1.) ws = std::min(b, a + (uint64_t)((double)(b - a) * hybrid_f) / 4 * 4);
+                    if (c->stage[slot].reserve((ws - a) * 12 + 64) != D2G_OK) { perr = d2g_last_error(); prc = D2G_ENOMEM; break; }
+                    if (ws < b) {
+                        const uint64_t b0 = ws * 32, b1 = std::min(total_len, b * 32);
+                        if (b1 > b0) {
+                            e = cudaMemcpyAsync(c->seq.p, hs.ascii + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_stream);
+                        }
+                        if (e == cudaSuccess) {
+                            d2g::pack_ascii_kernel<<<(unsigned)((b - ws + 255) / 256), 256, 0, c->copy_stream>>>(c->seq.as<uint8_t>(), b1 > b0 ? b1 - b0 : 0, b - ws, codes_d + ws, mask_d + ws);
+                            c->launches++;
+                            e = cudaGetLastError();
+                        }
+                    }
                     uint64_t *sc = reinterpret_cast<uint64_t *>(c->stage[slot].p);
-                    uint32_t *sm = reinterpret_cast<uint32_t *>(sc + (b - a));
-                    const uint64_t nz = d2g_host::pack_contiguous(hs.ascii, total_len, a, b, sc, sm);
-                    e = cudaMemcpyAsync(codes_d + a, sc, (b - a) * 8, cudaMemcpyHostToDevice, c->copy_stream);
-                    // mask words only travel when the chunk holds an invalid base at all
-                    if (e == cudaSuccess) e = nz ? cudaMemcpyAsync(mask_d + a, sm, (b - a) * 4, cudaMemcpyHostToDevice, c->copy_stream)
-                                                 : cudaMemsetAsync(mask_d + a, 0, (b - a) * 4, c->copy_stream);
+                    uint32_t *sm = reinterpret_cast<uint32_t *>(sc + (ws - a));
+                    const auto t0 = std::chrono::steady_clock::now();
+                    const uint64_t nz = ws > a ? d2g_host::pack_contiguous(hs.ascii, total_len, a, ws, sc, sm) : 0;
+                    const double th = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                    if (ws > a && e == cudaSuccess) {
+                        e = cudaMemcpyAsync(codes_d + a, sc, (ws - a) * 8, cudaMemcpyHostToDevice, c->copy_stream);
+                        // mask words only travel when the chunk holds an invalid base at all
+                        if (e == cudaSuccess) e = nz ? cudaMemcpyAsync(mask_d + a, sm, (ws - a) * 4, cudaMemcpyHostToDevice, c->copy_stream)
+                                                     : cudaMemsetAsync(mask_d + a, 0, (ws - a) * 4, c->copy_stream);
+                    }
                     cudaEventRecord(c->stage_free[slot], c->copy_stream);
+                    if (ascii_pinned && !fixed_f && ws - a >= (1u << 16) && th > 0.) {   // re-balance from the packing rate just measured
+                        const double P = (double)(ws - a) * 32. / th, B = 50e9;
+                        hybrid_f = std::max(0.25, std::min(1., (1. / B) / (1. / P + 0.75 / B)));
+                    }
                 } else {
                     e = cudaMemcpyAsync(codes_d + a, hs.codes + a, (b - a) * 8, cudaMemcpyHostToDevice, c->copy_stream);
                     if (e == cudaSuccess) e = hs.mask ? cudaMemcpyAsync(mask_d + a, hs.mask + a, (b - a) * 4, cudaMemcpyHostToDevice, c->copy_stream)
