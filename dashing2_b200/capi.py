@@ -39,7 +39,7 @@ EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stre
            "d2g_set_timing", "d2g_get_timing",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_distinct_kmers", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_init_devices", "d2g_comm_unique_id", "d2g_comm_init_rank", "d2g_comm_init_all", "d2g_comm_size", "d2g_comm_rank", "d2g_comm_destroy",
-           "d2g_cmp_rows_sharded_dev",
+           "d2g_cmp_rows_sharded_dev", "d2g_cmp_stream_sharded",
            "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_free"]
@@ -84,6 +84,7 @@ def load():
     L.d2g_comm_rank.argtypes = [vp]; L.d2g_comm_rank.restype = C.c_int
     L.d2g_comm_destroy.argtypes = [vp]; L.d2g_comm_destroy.restype = C.c_int
     L.d2g_cmp_rows_sharded_dev.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, u64, u64, vp]; L.d2g_cmp_rows_sharded_dev.restype = C.c_int
+    L.d2g_cmp_stream_sharded.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, u64, u64, SINK_FN, vp]; L.d2g_cmp_stream_sharded.restype = C.c_int
     L.d2g_packed_words.argtypes = [u64]; L.d2g_packed_words.restype = u64
     L.d2g_pack_sequences.argtypes = [vp, vp, u64, vp, vp, C.POINTER(u64)]; L.d2g_pack_sequences.restype = C.c_int
     L.d2g_pack_dev.argtypes = [vp, vp, u64, vp, vp]; L.d2g_pack_dev.restype = C.c_int

@@ -481,17 +481,30 @@ int d2g_cmp_rows_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *regs_d, 
 // Rows [r0,r1) in row blocks of <= ~64M values.  Kernels run on the ctx stream, the device->host copies on the copy
 // stream (block b+1 computes while block b drains).  direct_out != nullptr: results go straight into the caller's
 // buffer (full speed when it is pinned); otherwise through two pinned staging buffers to the sink, in row order.
+// shard != nullptr: regs / cards are this rank's block of sketches only (sharded_prepare runs the exchange; collective)
+struct ShardArg { uint64_t local_begin, local_n; };
+static int sharded_prepare_fwd(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d, uint64_t local_begin, uint64_t local_n);
 static int cmp_blocks(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards,
-                      uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user, float *direct_out) {
+                      uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user, float *direct_out, const ShardArg *shard = nullptr) {
     CU(cudaSetDevice(c->device));
     c->c16cache.valid = false; c->c16g.valid = false;
     const uint32_t S = p->sketchsize;
-    if (int rc = c->cregs.reserve(p->n * S * 8)) return rc;
-    if (int rc = c->ccards.reserve(p->n * 8)) return rc;
-    CU(cudaMemcpyAsync(c->cregs.p, regs, p->n * S * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->ccards.p, cards, p->n * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t n_up = shard ? shard->local_n : p->n;
+    if (int rc = c->cregs.reserve(n_up * S * 8 + 8)) return rc;
+    if (int rc = c->ccards.reserve(n_up * 8 + 8)) return rc;
+    if (n_up) {
+        CU(cudaMemcpyAsync(c->cregs.p, regs, n_up * S * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->ccards.p, cards, n_up * 8, cudaMemcpyHostToDevice, c->stream));
+    }
     d2g::CmpConsts k;
     if (int rc = make_consts(c, p, &k)) return rc;
+    const double *regs_d = c->cregs.as<double>(), *cards_d = c->ccards.as<double>();
+    struct ShardedScope { d2g_ctx *c; ~ShardedScope() { c->c16_sharded = false; } } scope{c};
+    if (shard) {
+        if (int rc = sharded_prepare_fwd(c, p, regs_d, cards_d, shard->local_begin, shard->local_n)) return rc;
+        c->c16_sharded = true;
+        regs_d = c->c16g.regs; cards_d = c->xcards.as<double>();
+    }
     const uint64_t max_vals = 64ULL << 20;
     const uint64_t ncol = n_cols(p);
     uint64_t rows_per = std::max<uint64_t>(d2g::CMP_T, max_vals / std::max<uint64_t>(1, ncol) / d2g::CMP_T * d2g::CMP_T);
@@ -509,7 +522,7 @@ static int cmp_blocks(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, c
         const uint64_t e = std::min(r1, b + rows_per), nv = rows_size(p, b, e);
         float *out_d = c->cout.as<float>() + (uint64_t)slot * cap_vals;
         if (iblk >= 2) CU(cudaStreamWaitEvent(c->stream, c->evd[slot], 0));       // the copy of block b-2 has left this slot
-        if (int rc = launch_cmp(c, p, k, c->cregs.as<double>(), c->ccards.as<double>(), b, e, out_d, nullptr, nullptr, r0)) return rc;
+        if (int rc = launch_cmp(c, p, k, regs_d, cards_d, b, e, out_d, nullptr, nullptr, r0)) return rc;
         CU(cudaEventRecord(c->ev[slot], c->stream));
         CU(cudaStreamWaitEvent(c->copy_stream, c->ev[slot], 0));
         float *dst = direct_out ? direct_out + done_vals : (float *)c->pin[slot].p;
@@ -657,6 +670,22 @@ int sharded_prepare(d2g_ctx *c, const d2g_cmp_params *p, const double *local_reg
     return D2G_OK;
 }
 } // namespace
+
+static int sharded_prepare_fwd(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d, uint64_t local_begin, uint64_t local_n) {
+    return sharded_prepare(c, p, local_regs_d, local_cards_d, local_begin, local_n);
+}
+
+// Host in / host out variant for a front-end whose devices each hold the sketches they made: the local block is uploaded, the exchange
+// runs, and rows [row_begin, row_end) are streamed to the sink exactly as d2g_cmp_stream does.  Collective.
+extern "C" int d2g_cmp_stream_sharded(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs, const double *local_cards,
+                                      uint64_t local_begin, uint64_t local_n, uint64_t r0, uint64_t r1, d2g_sink_fn sink, void *user) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    if (!sink) return fail(D2G_EINVAL, "null sink");
+    const ShardArg sh{local_begin, local_n};
+    return cmp_blocks(c, p, local_regs, local_cards, r0, r1, sink, user, nullptr, &sh);
+}
 
 extern "C" int d2g_cmp_rows_sharded_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d,
                                         uint64_t local_begin, uint64_t local_n, uint64_t r0, uint64_t r1, float *out_d) {

@@ -481,7 +481,8 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
                     cudaEventRecord(c->stage_free[slot], c->copy_stream);
                     if (ascii_pinned && !fixed_f && ws - a >= (1u << 16) && th > 0.) {   // re-balance from the packing rate just measured
                         const double P = (double)(ws - a) * 32. / th, B = 50e9;
-                        hybrid_f = std::max(0.25, std::min(1., (1. / B) / (1. / P + 0.75 / B)));
+                        const double want = (1. / B) / (1. / P + 0.75 / B);
+                        hybrid_f = std::max(0.5, std::min(1., 0.5 * hybrid_f + 0.5 * want));   // damped: one slow chunk must not swing the split
                     }
                 } else {
                     e = cudaMemcpyAsync(codes_d + a, hs.codes + a, (b - a) * 8, cudaMemcpyHostToDevice, c->copy_stream);

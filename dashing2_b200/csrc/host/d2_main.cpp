@@ -47,7 +47,20 @@ struct PhaseTimer {
     }
 } g_timer;
 
-[[noreturn]] void die(const std::string &m) { std::fprintf(stderr, "dashing2-gpu: %s\n", m.c_str()); std::exit(1); }
+[[noreturn]] void die(const std::string &m) { std::fprintf(stderr, "dashing2-gpu: %s\n", m.c_str()); std::fflush(stderr); _exit(1); }
+// output must not be truncated silently (the reference uses checked_fwrite and throws, src/enums.h): every write, flush and close is checked
+void xwrite(const void *p, size_t size, size_t n, std::FILE *fp, const std::string &what) {
+    if (n && std::fwrite(p, size, n, fp) != n) die("short write to " + what + ": " + std::strerror(errno));
+}
+std::FILE *xopen(const std::string &path, const char *mode) {
+    std::FILE *fp = std::fopen(path.c_str(), mode);
+    if (!fp) die("Failed to open " + path + ": " + std::strerror(errno));
+    return fp;
+}
+void xclose(std::FILE *fp, const std::string &what) {
+    if (std::fflush(fp) != 0 || std::ferror(fp)) die("write error on " + what + ": " + std::strerror(errno));
+    if (std::fclose(fp) != 0) die("close failed on " + what + ": " + std::strerror(errno));
+}
 void chk(int rc) { if (rc) die(std::string("libd2gpu: ") + d2g_last_error()); }
 
 struct Opts {
@@ -316,38 +329,48 @@ void sketch_inputs(Gpus &gpus, const Opts &o, Sketches &sk) {
             for (auto &t : th) t.join();
         }
         if (G == 1) g_timer.mark("read + parse batch");
-        // one buffer for the batch: sized once, filled by the host threads in parallel
-        std::vector<uint64_t> base(idx.size() + 1, 0);
-        for (size_t j = 0; j < idx.size(); ++j) base[j + 1] = base[j] + recs[j].seq.size();
-        std::unique_ptr<char[]> seq_store(new char[base.back() + 64]);   // not zero-filled: the copy threads touch the pages first, in parallel
-        char *const seqbuf = seq_store.get();
-        memset(seqbuf + base.back(), 0, 64);
-        std::vector<uint64_t> off{0}; std::vector<uint32_t> ent;
-        for (size_t j = 0; j < idx.size(); ++j)
-            for (uint64_t e : recs[j].ends) { off.push_back(base[j] + e); ent.push_back((uint32_t)j); }
-        {
-            std::vector<std::thread> th; std::atomic<size_t> next{0};
-            const unsigned nt = (unsigned)std::min<size_t>(threads_per_worker, idx.size());
-            for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] {
-                for (size_t j; (j = next++) < idx.size();) { memcpy(seqbuf + base[j], recs[j].seq.data(), recs[j].seq.size()); recs[j] = FileRecords(); } });
-            for (auto &t : th) t.join();
-        }
-        if (G == 1) g_timer.mark("concatenate batch");
-        const uint32_t ne = (uint32_t)idx.size();
-        std::vector<double> sig((size_t)ne * S), card(ne); std::vector<uint64_t> ids(o.save_kmers ? (size_t)ne * S : 0);
-        chk(d2g_sketch_batch(gpus.get(g), &p, seqbuf, off.data(), ent.data(), ent.size(), ne, nullptr, sig.data(), card.data(),
-                             o.save_kmers ? ids.data() : nullptr, nullptr));
-        if (G == 1) g_timer.mark("d2g_sketch_batch");
-        for (size_t j = 0; j < idx.size(); ++j) {
-            std::copy(sig.begin() + j * S, sig.begin() + (j + 1) * S, sk.sig.begin() + idx[j] * S);
-            sk.card[idx[j]] = card[j];
-            if (o.save_kmers) std::copy(ids.begin() + j * S, ids.begin() + (j + 1) * S, sk.ids.begin() + idx[j] * S);
-            if (o.cache) {
-                const std::string dest = makedest(o, o.paths[idx[j]]);
-                std::FILE *fp = std::fopen(dest.c_str(), "wb");
-                if (!fp) die("Failed to open file " + dest + " for writing sketch.");
-                std::fwrite(&card[j], 8, 1, fp); std::fwrite(&sig[j * S], 8, S, fp); std::fclose(fp);
+        // Sub-batches by the bases actually read (the on-disk size says little for .gz): the counting sketches and -m sort a whole batch at
+        // once (at most 2^32 bases, ~36 bytes of scratch per base), everything else is only bounded by device memory.
+        const bool whole_batch_sort = o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH || (o.mode == D2G_MODE_OPMH && o.count_threshold > 1);
+        const uint64_t max_bases = whole_batch_sort ? 2000000000ULL : 16000000000ULL;
+        for (size_t g0 = 0; g0 < idx.size();) {
+            size_t g1 = g0; uint64_t tot = 0;
+            while (g1 < idx.size() && (g1 == g0 || tot + recs[g1].seq.size() <= max_bases)) tot += recs[g1++].seq.size();
+            const size_t nf = g1 - g0;
+            // the batch goes to the device packed (2 bits + 1 invalid bit per base), packed by the library's host threads from the per-file
+            // buffers: no concatenated ASCII copy, a quarter of the bytes over PCIe
+            std::vector<const char *> pieces(nf); std::vector<uint64_t> plen(nf);
+            std::vector<uint64_t> off{0}; std::vector<uint32_t> ent;
+            uint64_t at = 0;
+            for (size_t j = 0; j < nf; ++j) {
+                const FileRecords &fr = recs[g0 + j];
+                pieces[j] = fr.seq.data(); plen[j] = fr.seq.size();
+                for (uint64_t e : fr.ends) { off.push_back(at + e); ent.push_back((uint32_t)j); }
+                at += fr.seq.size();
             }
+            const uint64_t nw = d2g_packed_words(at);
+            std::unique_ptr<uint64_t[]> codes(new uint64_t[nw]); std::unique_ptr<uint32_t[]> mask(new uint32_t[nw]);
+            uint64_t nzw = 0;
+            chk(d2g_pack_sequences(pieces.data(), plen.data(), nf, codes.get(), mask.get(), &nzw));
+            for (size_t j = 0; j < nf; ++j) recs[g0 + j] = FileRecords();
+            if (G == 1) g_timer.mark("pack batch");
+            const uint32_t ne = (uint32_t)nf;
+            std::vector<double> sig((size_t)ne * S), card(ne); std::vector<uint64_t> ids(o.save_kmers ? (size_t)ne * S : 0);
+            chk(d2g_sketch_batch_packed(gpus.get(g), &p, codes.get(), nzw ? mask.get() : nullptr, off.data(), ent.data(), ent.size(), ne, nullptr,
+                                        sig.data(), card.data(), o.save_kmers ? ids.data() : nullptr, nullptr));
+            if (G == 1) g_timer.mark("d2g_sketch_batch_packed");
+            for (size_t jj = 0; jj < nf; ++jj) {
+                const size_t j = g0 + jj;
+                std::copy(sig.begin() + jj * S, sig.begin() + (jj + 1) * S, sk.sig.begin() + idx[j] * S);
+                sk.card[idx[j]] = card[jj];
+                if (o.save_kmers) std::copy(ids.begin() + jj * S, ids.begin() + (jj + 1) * S, sk.ids.begin() + idx[j] * S);
+                if (o.cache) {
+                    const std::string dest = makedest(o, o.paths[idx[j]]);
+                    std::FILE *fp = xopen(dest, "wb");
+                    xwrite(&card[jj], 8, 1, fp, dest); xwrite(&sig[jj * S], 8, S, fp, dest); xclose(fp, dest);
+                }
+            }
+            g0 = g1;
         }
       }
     };
@@ -417,23 +440,22 @@ void sketch_by_seq(LazyCtx &lctx, const Opts &o, Sketches &sk) {
 
 void write_stacked(const Opts &o, const Sketches &sk) {
     const uint64_t n = sk.card.size(), S = sk.S;
-    std::FILE *fp = std::fopen(o.outfile.c_str(), "wb");
-    if (!fp) die("Failed to open file " + o.outfile);
-    std::fwrite(&n, 8, 1, fp); std::fwrite(&S, 8, 1, fp);
-    std::fwrite(sk.card.data(), 8, n, fp); std::fwrite(sk.sig.data(), 8, n * S, fp); std::fclose(fp);
-    fp = std::fopen((o.outfile + ".names.txt").c_str(), "wb");
-    if (!fp) die("Failed to open outfile at " + o.outfile + ".names.txt");
+    std::FILE *fp = xopen(o.outfile, "wb");
+    xwrite(&n, 8, 1, fp, o.outfile); xwrite(&S, 8, 1, fp, o.outfile);
+    xwrite(sk.card.data(), 8, n, fp, o.outfile); xwrite(sk.sig.data(), 8, n * S, fp, o.outfile); xclose(fp, o.outfile);
+    const std::string np = o.outfile + ".names.txt";
+    fp = xopen(np, "wb");
     std::fputs("#Name\tCardinality\n", fp);
     for (size_t i = 0; i < n; ++i) std::fprintf(fp, "%s\t%0.24g\n", sk.names[i].c_str(), sk.card[i]);
-    std::fclose(fp);
+    xclose(fp, np);
     if (o.save_kmers) {
         const std::string kp = o.outfile + ".kmer64";
-        fp = std::fopen(kp.c_str(), "wb");
+        fp = xopen(kp, "wb");
         const uint32_t hdr[4] = {uint32_t(0) | (uint32_t(o.canon) << 8), (uint32_t)S, (uint32_t)o.k, (uint32_t)(o.w < 0 ? o.k : o.w)};
-        std::fwrite(hdr, 4, 4, fp); std::fwrite(&o.seed, 8, 1, fp); std::fwrite(sk.ids.data(), 8, n * S, fp); std::fclose(fp);
-        fp = std::fopen((kp + ".names.txt").c_str(), "wb");
+        xwrite(hdr, 4, 4, fp, kp); xwrite(&o.seed, 8, 1, fp, kp); xwrite(sk.ids.data(), 8, n * S, fp, kp); xclose(fp, kp);
+        fp = xopen(kp + ".names.txt", "wb");
         for (auto &nm : sk.names) { std::fputs(nm.c_str(), fp); std::fputc('\n', fp); }
-        std::fclose(fp);
+        xclose(fp, kp + ".names.txt");
     }
 }
 
@@ -569,7 +591,7 @@ void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
         const uint64_t nnz = indptr[n];
         if (o.binary) {
             const uint64_t dims[2] = {n, nnz};
-            std::fwrite(dims, 8, 2, fp); std::fwrite(indptr.data(), 8, n + 1, fp); std::fwrite(idx, 4, nnz, fp); std::fwrite(val, 4, nnz, fp);
+            xwrite(dims, 8, 2, fp, o.cmpout); xwrite(indptr.data(), 8, n + 1, fp, o.cmpout); xwrite(idx, 4, nnz, fp, o.cmpout); xwrite(val, 4, nnz, fp, o.cmpout);
         } else {
             std::fputs("#Collection\tNeighbor lists -- name:distance, separated by tabs\n", fp);
             for (uint64_t i = 0; i < n; ++i) {
@@ -579,7 +601,7 @@ void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
             }
         }
         if (G == 1) { d2g_free(idx); d2g_free(val); } else { std::free(idx); std::free(val); }
-        if (!to_stdout) std::fclose(fp); else std::fflush(fp);
+        if (!to_stdout) xclose(fp, o.cmpout); else if (std::fflush(fp) != 0) die("write error on standard output");
         return;
     }
     Writer w{o, sk, fp, (size_t)n, (size_t)o.nq, {}};
@@ -602,17 +624,36 @@ void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
         const bool positioned = o.binary && !to_stdout;      // raw float32 file: every range is written at its own offset
         std::fflush(fp);
         std::vector<std::string> mem(G);
-        std::vector<std::thread> ws;
-        for (size_t g = 0; g < G; ++g) ws.emplace_back([&, g] {
-            Writer wg{o, sk, fp, (size_t)n, (size_t)o.nq, {}};
-            if (positioned) { uint64_t before = 0; chk(d2g_cmp_rows_size(&cp, 0, b[g], &before)); wg.fd = fileno(fp); wg.file_off = before * 4; }
-            else wg.mem = &mem[g];
-            if (b[g + 1] > b[g]) chk(d2g_cmp_stream(gpus.get(g), &cp, regs, sk.card.data(), b[g], b[g + 1], Writer::sink, &wg));
-        });
-        for (auto &t : ws) t.join();
+        // Sharded: device g uploads only its block of n / G sketches; the devices exchange register positions and 32-bit ranks over the
+        // communicator the library owns (d2g_cmp_stream_sharded).  Falls back to every device holding all registers when no communicator
+        // can be had (contexts sharing a device, no NCCL) or the library refuses (NaN registers, S > 65535).
+        std::vector<d2g_ctx *> cs(G);
+        for (size_t g = 0; g < G; ++g) cs[g] = gpus.get(g);
+        bool sharded = S <= 65535 && !getenv("D2G_NO_SHARDED_CMP") && d2g_comm_init_all(cs.data(), (int)G) == D2G_OK;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            std::vector<int> rcs(G, 0); std::vector<std::string> errs(G);
+            std::vector<std::thread> ws;
+            for (size_t g = 0; g < G; ++g) ws.emplace_back([&, g] {
+                Writer wg{o, sk, fp, (size_t)n, (size_t)o.nq, {}};
+                if (positioned) { uint64_t before = 0; chk(d2g_cmp_rows_size(&cp, 0, b[g], &before)); wg.fd = fileno(fp); wg.file_off = before * 4; }
+                else { mem[g].clear(); wg.mem = &mem[g]; }
+                if (sharded) {
+                    const uint64_t n_per = (n + G - 1) / G, lb = std::min<uint64_t>(n, g * n_per), ln = std::min<uint64_t>(n, (g + 1) * n_per) - lb;
+                    rcs[g] = d2g_cmp_stream_sharded(cs[g], &cp, regs + lb * S, sk.card.data() + lb, lb, ln, b[g], b[g + 1], Writer::sink, &wg);
+                } else if (b[g + 1] > b[g]) rcs[g] = d2g_cmp_stream(cs[g], &cp, regs, sk.card.data(), b[g], b[g + 1], Writer::sink, &wg);
+                if (rcs[g]) errs[g] = d2g_last_error();
+            });
+            for (auto &t : ws) t.join();
+            bool failed = false, unsupported = true;
+            for (size_t g = 0; g < G; ++g) if (rcs[g]) { failed = true; unsupported = unsupported && rcs[g] == D2G_EUNSUPPORTED; }
+            if (!failed) break;
+            if (sharded && unsupported && attempt == 0) { sharded = false; continue; }     // nothing was emitted: the exchange refuses before any row
+            for (size_t g = 0; g < G; ++g) if (rcs[g]) die("libd2gpu: " + errs[g]);
+        }
+        if (o.verbosity > 0) std::fprintf(stderr, "[dashing2-gpu] compare on %zu devices: %s\n", G, sharded ? "sharded registers, NCCL exchange" : "replicated registers");
         if (!positioned) for (size_t g = 0; g < G; ++g) if (std::fwrite(mem[g].data(), 1, mem[g].size(), fp) != mem[g].size()) die("short write to " + o.cmpout);
     }
-    if (!to_stdout) std::fclose(fp); else std::fflush(fp);
+    if (!to_stdout) xclose(fp, o.cmpout); else if (std::fflush(fp) != 0) die("write error on standard output");
 }
 
 } // namespace
@@ -655,7 +696,7 @@ int main(int argc, char **argv) {
     // every output file is closed / flushed; tearing the CUDA context down costs another 0.2-0.5 s and frees nothing the
     // process exit does not free
     for (size_t g = 0; g < gpus.size(); ++g) gpus.get(g);
-    std::fflush(nullptr);
+    if (std::fflush(nullptr) != 0) die(std::string("flush failed: ") + std::strerror(errno));
     _exit(0);
     return 0;
 }

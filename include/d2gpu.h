@@ -237,6 +237,10 @@ int d2g_comm_rank(const d2g_ctx *ctx);
 int d2g_comm_destroy(d2g_ctx *ctx);
 int d2g_cmp_rows_sharded_dev(d2g_ctx *ctx, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d,
                              uint64_t local_begin, uint64_t local_n, uint64_t row_begin, uint64_t row_end, float *out_d);
+/* The same with host memory on both sides (the front-end's --gpus N): this rank's block of registers is uploaded, the exchange runs,
+ * and rows [row_begin, row_end) are delivered to the sink in row order like d2g_cmp_stream.  Collective. */
+int d2g_cmp_stream_sharded(d2g_ctx *ctx, const d2g_cmp_params *p, const double *local_regs, const double *local_cards,
+                           uint64_t local_begin, uint64_t local_n, uint64_t row_begin, uint64_t row_end, d2g_sink_fn sink, void *user);
 
 /* ------------------------------------------------------------------------------------------------
  * LSH-assisted top-k neighbour graph (--topk K).  Replaces build_index (src/index_build.cpp:53-165) over
