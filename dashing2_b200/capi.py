@@ -40,7 +40,7 @@ EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stre
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_distinct_kmers", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_init_devices", "d2g_comm_unique_id", "d2g_comm_init_rank", "d2g_comm_init_all", "d2g_comm_size", "d2g_comm_rank", "d2g_comm_destroy",
            "d2g_cmp_rows_sharded_dev", "d2g_cmp_stream_sharded",
-           "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
+           "d2g_kmer_counts", "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_free"]
 
@@ -85,6 +85,7 @@ def load():
     L.d2g_comm_destroy.argtypes = [vp]; L.d2g_comm_destroy.restype = C.c_int
     L.d2g_cmp_rows_sharded_dev.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, u64, u64, vp]; L.d2g_cmp_rows_sharded_dev.restype = C.c_int
     L.d2g_cmp_stream_sharded.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, u64, u64, SINK_FN, vp]; L.d2g_cmp_stream_sharded.restype = C.c_int
+    L.d2g_kmer_counts.argtypes = [vp, C.POINTER(SketchParams), vp, vp, vp, vp, u64, u32, vp, vp]; L.d2g_kmer_counts.restype = C.c_int
     L.d2g_packed_words.argtypes = [u64]; L.d2g_packed_words.restype = u64
     L.d2g_pack_sequences.argtypes = [vp, vp, u64, vp, vp, C.POINTER(u64)]; L.d2g_pack_sequences.restype = C.c_int
     L.d2g_pack_dev.argtypes = [vp, vp, u64, vp, vp]; L.d2g_pack_dev.restype = C.c_int
@@ -227,6 +228,16 @@ class Context:
         _check(self.L.d2g_sketch_batch_packed(self.h, C.byref(p), _ptr(codes), _ptr(mask), _ptr(rec_off), _ptr(rec_entity), len(rec_entity),
                                               n_entities, _ptr(regs), _ptr(sig), _ptr(card), _ptr(ids), C.byref(nk)))
         return dict(regs_u64=regs, sig=sig, card=card, ids=ids, n_kmers=int(nk.value))
+
+    def kmer_counts(self, codes, mask, rec_off, rec_entity, n_entities, p: SketchParams, ids: np.ndarray) -> np.ndarray:
+        """--save-kmercounts: multiplicity of the element behind every register (d2g_kmer_counts), float32 [n_entities][S]."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64); rec_entity = np.ascontiguousarray(rec_entity, dtype=np.uint32)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = np.empty((n_entities, p.sketchsize), dtype=np.float32)
+        _check(self.L.d2g_kmer_counts(self.h, C.byref(p), _ptr(codes), _ptr(mask), _ptr(rec_off), _ptr(rec_entity), len(rec_entity), n_entities, _ptr(ids), _ptr(out)))
+        return out
 
     def distinct_kmers(self, seq: np.ndarray, rec_off: np.ndarray, rec_entity: np.ndarray, n_entities: int, p: SketchParams) -> np.ndarray:
         """Exact distinct k-mers (minimizers) per entity, host in / host out (d2g_distinct_kmers)."""

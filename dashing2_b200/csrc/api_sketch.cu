@@ -432,6 +432,9 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, hs.ascii) == cudaSuccess) ascii_pinned = at.type == cudaMemoryTypeHost;
         else cudaGetLastError();
+        // The split is fixed (measured best on the 16-core B200 hosts: packing 75 G bases/s, link 53 GB/s); D2G_HYBRID_ADAPT=1 lets it follow
+        // the packing rate measured per chunk (noisy: host threads and the DMA engine compete for the same memory bandwidth).
+        fixed_f = !getenv("D2G_HYBRID_ADAPT");
         if (const char *ev = getenv("D2G_HYBRID_F")) { hybrid_f = std::max(0., std::min(1., atof(ev))); fixed_f = true; }   // 1 = pack everything on the host
         if (ascii_pinned) {                                // device staging of the ASCII tails: sized once for the largest chunk
             uint64_t mw = 0;

@@ -310,3 +310,92 @@ extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const 
     CU(cudaStreamSynchronize(st));
     return D2G_OK;
 }
+
+// ---- --save-kmercounts (-N): multiplicity of the element that owns each register ---------------------------------------
+// The reference keeps, beside every register, how often the element that set it was seen (one-permutation sketch: counts_ bumped when
+// an update equals the register, src/oph.h:206-209; Full SetSketch: setsketch.h:405-406; BagMinHash / ProbMinHash: the element's weight)
+// and writes them as float32 to FILE.kmercounts.f64 (src/sketch_core.cpp:162-171).  That count is a function of the register's id alone:
+// its multiplicity in the stream of hashed k-mers (one per window when w > k) that fed the entity.  Device: the emit pass of the counting
+// sketches, a sort by (entity, value), and two binary searches per (entity, register).
+namespace {
+__global__ void kmer_count_lookup_kernel(const uint64_t *hv, const uint32_t *ent, uint64_t n, const uint64_t *ids, uint64_t n_ids, uint32_t S, float *out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_ids) return;
+    const uint32_t e = (uint32_t)(i / S);
+    const uint64_t id = ids[i];
+    uint64_t lo = 0, hi = n;                                         // first index with (ent, hv) >= (e, id)
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; const uint32_t me = ent[mid]; if (me < e || (me == e && hv[mid] < id)) lo = mid + 1; else hi = mid; }
+    const uint64_t lb = lo;
+    hi = n;                                                          // first index with (ent, hv) > (e, id)
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; const uint32_t me = ent[mid]; if (me < e || (me == e && hv[mid] <= id)) lo = mid + 1; else hi = mid; }
+    out[i] = (float)(lo - lb);
+}
+}
+
+extern "C" int d2g_kmer_counts(d2g_ctx *c, const d2g_sketch_params *p, const uint64_t *codes, const uint32_t *mask, const uint64_t *rec_off,
+                               const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities, const uint64_t *ids, float *counts_out) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    if (p->countsketch_size) return fail(D2G_EUNSUPPORTED, "--save-kmercounts with a count sketch (--countsketch-size) is not implemented on the GPU");
+    if (n_entities && (!ids || !counts_out)) return fail(D2G_EINVAL, "null ids / output");
+    if (n_rec && (!rec_off || !rec_entity)) return fail(D2G_EINVAL, "null record tables");
+    CU(cudaSetDevice(c->device));
+    const uint32_t S = p->sketchsize;
+    const uint64_t n = n_rec ? rec_off[n_rec] : 0, n_ids = (uint64_t)n_entities * S;
+    for (uint64_t i = 0; i < n_ids; ++i) counts_out[i] = 0.f;
+    if (!n || !n_rec || !n_entities) return D2G_OK;
+    if (!codes) return fail(D2G_EINVAL, "null packed sequence");
+    if (rec_off[0] != 0) return fail(D2G_EINVAL, "rec_off[0] must be 0");
+    if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "k-mer counts: at most 2^32 bases per call (got %llu)", (unsigned long long)n);
+    for (uint64_t r = 0; r < n_rec; ++r) {
+        if (rec_off[r + 1] < rec_off[r]) return fail(D2G_EINVAL, "rec_off not monotone at %llu", (unsigned long long)r);
+        if (rec_entity[r] >= n_entities) return fail(D2G_EINVAL, "rec_entity[%llu]=%u >= n_entities", (unsigned long long)r, rec_entity[r]);
+        if (r && rec_entity[r] < rec_entity[r - 1]) return fail(D2G_EINVAL, "rec_entity must be non-decreasing");
+    }
+    const uint64_t nw = d2g::packed_words(n);
+    if (int rc = c->pcodes.reserve(nw * 8)) return rc;
+    if (int rc = c->pmask.reserve(nw * 4)) return rc;
+    if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
+    if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
+    if (int rc = c->ids.reserve(n_ids * 8)) return rc;
+    if (int rc = c->sig.reserve(n_ids * 4)) return rc;
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->pcodes.p, codes, nw * 8, cudaMemcpyHostToDevice, st));
+    if (mask) CU(cudaMemcpyAsync(c->pmask.p, mask, nw * 4, cudaMemcpyHostToDevice, st)); else CU(cudaMemsetAsync(c->pmask.p, 0, nw * 4, st));
+    CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->ids.p, ids, n_ids * 8, cudaMemcpyHostToDevice, st));
+    const d2g::PackedSeq seq_d{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()};
+    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
+    uint64_t off = 0;
+    const uint64_t o_hvA = off; off += al(n * 8 + 8);
+    const uint64_t o_hvB = off; off += al(n * 8 + 8);
+    const uint64_t o_entA = off; off += al(n * 4 + 4);
+    const uint64_t o_entB = off; off += al(n * 4 + 4);
+    if (int rc = c->wbuf.reserve(off)) return rc;
+    unsigned char *B = c->wbuf.as<unsigned char>();
+    uint64_t *hvA = (uint64_t *)(B + o_hvA), *hvB = (uint64_t *)(B + o_hvB);
+    uint32_t *entA = (uint32_t *)(B + o_entA), *entB = (uint32_t *)(B + o_entB);
+    CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
+    CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
+    if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
+    d2g::EmitConsumer::Params ep{hvA, entA, a.span};
+    if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    const size_t tb = std::max(t1, t2);
+    if (int rc = c->wtmp.reserve(tb + 256)) return rc;
+    size_t tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
+    tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    c->launches += 2 * 9;
+    kmer_count_lookup_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, st>>>(hvA, entA, n, c->ids.as<uint64_t>(), n_ids, S, c->sig.as<float>());
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts_out, c->sig.p, n_ids * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return D2G_OK;
+}

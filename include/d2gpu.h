@@ -103,6 +103,15 @@ int d2g_distinct_kmers(d2g_ctx *ctx, const d2g_sketch_params *p,
                        const char *seq, const uint64_t *rec_off, const uint32_t *rec_entity,
                        uint64_t n_rec, uint32_t n_entities, uint64_t *distinct_out);
 
+/* --save-kmercounts (-N): counts_out f32 [n_entities][S] = how often the element that owns each register occurs in the stream of hashed
+ * k-mers (one per window when w > k) of its entity -- what the reference keeps beside the registers (src/oph.h:206-209 counts_,
+ * src/setsketch.h:405-406, the weights of BagMinHash / ProbMinHash) and writes as float32 to FILE.kmercounts.f64
+ * (src/sketch_core.cpp:162-171).  ids [n_entities][S]: the ids_out of the sketch call over the same batch (packed sequence, host
+ * memory; mask may be NULL).  At most 2^32 bases per call; exact counting only. */
+int d2g_kmer_counts(d2g_ctx *ctx, const d2g_sketch_params *p, const uint64_t *codes, const uint32_t *mask,
+                    const uint64_t *rec_off, const uint32_t *rec_entity, uint64_t n_rec, uint32_t n_entities,
+                    const uint64_t *ids, float *counts_out);
+
 /* Host-side transform of OPMH bucket minima (host memory) into the reference's f64 signatures and
  * cardinality: sig = -1/(m-nempty) * logl(2^-64 * (2^64 - reg)), card = m*m / sum(reg * 2^-64), both in
  * x87 long double exactly as src/oph.h:240-263 does on the host. regs_u64 [n][d2g_opmh_m(S)]. */

@@ -933,3 +933,22 @@ def test_sharded_compare_single_rank_equals_plain_compare(n, S, shape, measure, 
     c.sync()
     assert np.array_equal(out.cpu().numpy().view(np.uint32), full.view(np.uint32))
     c.close()
+
+
+@pytest.mark.parametrize("mode,S,k,w", [("opmh", 64, 31, -1), ("opmh", 128, 21, 30), ("fss", 64, 31, -1), ("bmh", 32, 31, -1), ("pmh", 32, 31, -1)])
+def test_kmer_counts_match_reference_golden(mode, S, k, w):
+    """--save-kmercounts (d2g_kmer_counts): multiplicity / weight of the element behind every register, against the float32 counts the
+    unmodified reference binary wrote (tests/golden/make_golden_kmercounts.py)."""
+    from dashing2_b200 import capi
+    name = {("opmh", 64): "kmercounts_opmh_k31_S64", ("opmh", 128): "kmercounts_opmh_k21_w30_S128", ("fss", 64): "kmercounts_fss_k31_S64",
+            ("bmh", 32): "kmercounts_bmh_k31_S32", ("pmh", 32): "kmercounts_pmh_k31_S32"}[(mode, S)]
+    z = np.load(expected(name + ".npz"))
+    files = ["dup.fa.gz", "g0.fa.gz", "rep.fa.gz", "adv.fa.gz"]
+    recs = [O.read_fastx(os.path.join(GOLD, "inputs", f)) for f in files]
+    seq, off, ent = pack_batch(recs)
+    c = ctx()
+    p = c.params(mode=mode, S=S, k=k, w=w)
+    r = c.sketch_batch(seq, off, ent, len(recs), p, want_ids=True)
+    codes, mask, nz = capi.pack_sequences([x for rr in recs for x in rr])
+    counts = c.kmer_counts(codes, mask, off, ent, len(recs), p, r["ids"])
+    assert np.array_equal(counts, z["counts"]), (mode, S)
