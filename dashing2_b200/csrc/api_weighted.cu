@@ -101,7 +101,9 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
         d2g::weight_sum_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, st>>>(entA, pos, nu, n_valid, threshold, wsum, wts);
         d2g::weighted_guess_kernel<<<(n_ent + 255) / 256, 256, 0, st>>>(wsum, n_ent, m, T, state);
         c->launches += 2;
-        d2g::WeightedArgs wa{hvA, entA, pos, nu, n_valid, threshold, m, T, state, keys, ovf, ovf_count, ovf_cap, error, wts, id_shift, nullptr};
+        unsigned long long *bmh_next = n_valid + 4;                  // in the misc block
+        const unsigned bmh_grid = (unsigned)std::min<uint64_t>((nu + 127) / 128, (uint64_t)c->sm_count * 12);
+        d2g::WeightedArgs wa{hvA, entA, pos, nu, n_valid, threshold, m, T, state, keys, ovf, ovf_count, ovf_cap, error, wts, id_shift, nullptr, bmh_next};
         d2g::TexpConsts tc{};
         if (p->mode == D2G_MODE_PROBMINHASH) {   // bmh.h:490-502
             const long double lambda = log1pl(1.L / (m - 1));
@@ -122,7 +124,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
                     d2g::pmh_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, st>>>(wa, tc, c->aux2.as<uint32_t>());
                     c->launches += 2;
                 } else {
-                    d2g::bmh_kernel<<<gu, 128, 0, st>>>(wa);
+                    CU(cudaMemsetAsync(bmh_next, 0, 8, st)); d2g::bmh_kernel<<<bmh_grid, 128, 0, st>>>(wa);
                     c->launches++;
                 }
             }
@@ -147,7 +149,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
                 d2g::pmh_longwalk_kernel<<<(unsigned)(nslots / 32), 32, 0, st>>>(wa, tc, c->aux2.as<uint32_t>());
                 c->launches += 2;
             } else {
-                d2g::bmh_kernel<<<gu, 128, 0, st>>>(wa);
+                CU(cudaMemsetAsync(bmh_next, 0, 8, st)); d2g::bmh_kernel<<<bmh_grid, 128, 0, st>>>(wa);
                 c->launches++;
             }
             unsigned int h[2] = {0, 0};

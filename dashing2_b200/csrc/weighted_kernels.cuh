@@ -180,6 +180,7 @@ struct WeightedArgs {
     unsigned int *error;
     const uint32_t *wts; int id_shift;   // count sketch: weight of run u (else its length), element id = key >> id_shift (else the key)
     uint64_t *ids;                       // non-null: --save-kmers pass over final registers (every entity, no register update), ids [n_ent][m]
+    unsigned long long *next;            // bmh_kernel: element counter of its persistent grid (zeroed before every launch)
 };
 
 __global__ void pmh_kernel(const WeightedArgs a, const TexpConsts tc) {
@@ -245,50 +246,67 @@ __device__ __forceinline__ PProc bmh_split(PProc &p) {   // bmh.h:182-206
     return r;
 }
 
-__global__ void bmh_kernel(const WeightedArgs a) {
-    const uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (u >= a.nu) return;
-    const uint64_t i0 = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
-    const uint32_t e = a.ent[i0];
-    if (!a.ids && a.state[e] == 2u) return;
-    const double w = a.wts ? (double)a.wts[u] : (double)(end - i0);
-    if (!(w > a.threshold)) return;
-    const double T = a.T[e];
-    uint64_t *keys = a.keys + (uint64_t)e * a.m;
+// One lane per element, but elements differ wildly in how far their split tree has to be explored (ncu, one thread per element and
+// its whole tree: 3.8 of 32 lanes busy on average).  So the tree walk is a flat state machine -- one loop iteration is one split, one
+// step of a fully covered process, or one pop -- and a lane whose element is finished draws the next one from a global counter in the
+// same iteration.  Same operations in the same order per element as update_2 (bmh.h:269-316).  Persistent grid; a.next counts elements.
+__global__ void __launch_bounds__(128) bmh_kernel(const WeightedArgs a) {
     const FastMod32 fm{};
-    const uint64_t id = a.hv[i0] >> a.id_shift;
-    uint64_t *ids = a.ids ? a.ids + (uint64_t)e * a.m : nullptr;
+    PProc stack[BMH_STACK]; uint32_t sidx[BMH_STACK]; int sp = 0;
+    PProc p{0., 0., 0., 0., 0}; uint32_t pidx = 0;
+    bool active = false, more = true;
+    double w = 0., T = 0.; uint64_t id = 0; uint64_t *keys = nullptr, *ids = nullptr;
     auto apply = [&](uint32_t idx, double x) {
         const uint64_t kk = dkey(x);
         if (ids) { if (kk == keys[idx]) ids[idx] = id; }
         else if (kk < keys[idx]) atomicMin(reinterpret_cast<unsigned long long *>(keys + idx), (unsigned long long)kk);
     };
-    PProc stack[BMH_STACK]; uint32_t sidx[BMH_STACK]; int sp = 0;
-    PProc p{0., 0., 1.7976931348623157e308, 0., id};
-    uint32_t pidx = bmh_step(p, a.m, fm);
-    if (p.maxq <= w) apply(pidx, p.x);
-    for (;;) {
-        if (p.x < T) {                                            // bmh.h:282: only processes below the current maximum are expanded
-            while (bmh_can_split(p) && bmh_partially(p, w)) {
-                PProc q = bmh_split(p);
-                if (p.maxq <= w) apply(pidx, p.x);
-                if (bmh_partially(q, w)) {
-                    const uint32_t qidx = bmh_step(q, a.m, fm);
-                    if (q.maxq <= w) apply(qidx, q.x);
-                    if (bmh_partially(q, w) && q.x < T) {         // anything at or above T can never be expanded again
-                        if (sp == BMH_STACK) { atomicExch(a.error, 2u); return; }
-                        stack[sp] = q; sidx[sp] = qidx; ++sp;
+    while (__any_sync(0xffffffffu, active || more)) {
+        int step_who = 0;                      // 0 none, 1 = p (first step of a new element), 2 = the split-off half q, 3 = p (fully covered: next point)
+        bool pop = false;
+        PProc q{0., 0., 0., 0., 0};
+        if (!active) {
+            if (more) {
+                const unsigned long long u = atomicAdd(a.next, 1ULL);
+                if (u >= a.nu) more = false;
+                else {
+                    const uint64_t i0 = a.pos[u], end = (u + 1 < a.nu) ? a.pos[u + 1] : *a.n_valid;
+                    const uint32_t e = a.ent[i0];
+                    w = a.wts ? (double)a.wts[u] : (double)(end - i0);
+                    if ((a.ids || a.state[e] != 2u) && w > a.threshold) {
+                        T = a.T[e]; keys = a.keys + (uint64_t)e * a.m; id = a.hv[i0] >> a.id_shift;
+                        ids = a.ids ? a.ids + (uint64_t)e * a.m : nullptr;
+                        p = PProc{0., 0., 1.7976931348623157e308, 0., id};
+                        sp = 0; active = true; step_who = 1;
                     }
                 }
             }
-            if (p.maxq <= w) {
-                pidx = bmh_step(p, a.m, fm);
-                apply(pidx, p.x);
-                if (p.x < T) continue;                            // re-expand the same process (equivalent to push + pop)
+        } else if (!(p.x < T)) pop = true;                            // bmh.h:282: only processes below the current maximum are expanded
+        else if (bmh_can_split(p) && bmh_partially(p, w)) {
+            q = bmh_split(p);
+            if (p.maxq <= w) apply(pidx, p.x);
+            if (bmh_partially(q, w)) step_who = 2;
+        } else if (p.maxq <= w) step_who = 3;
+        else pop = true;
+        if (step_who) {
+            PProc t = step_who == 2 ? q : p;
+            const uint32_t idx = bmh_step(t, a.m, fm);
+            if (step_who == 2) {
+                if (t.maxq <= w) apply(idx, t.x);
+                if (bmh_partially(t, w) && t.x < T) {                 // anything at or above T can never be expanded again
+                    if (sp == BMH_STACK) { atomicExch(a.error, 2u); active = false; more = false; }
+                    else { stack[sp] = t; sidx[sp] = idx; ++sp; }
+                }
+            } else {
+                p = t; pidx = idx;
+                if (step_who == 3 || p.maxq <= w) apply(pidx, p.x);
+                if (step_who == 3 && !(p.x < T)) pop = true;          // else: re-expand the same process (equivalent to push + pop)
             }
         }
-        if (sp == 0) break;
-        --sp; p = stack[sp]; pidx = sidx[sp];
+        if (pop) {
+            if (sp == 0) active = false;
+            else { --sp; p = stack[sp]; pidx = sidx[sp]; }
+        }
     }
 }
 
