@@ -6,7 +6,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -ccbin $(CXX_HOST) --fmad=false -Xptxas -v
 CSRC := dashing2_b200/csrc
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/d2gpu.h
-UNITS := api_core api_comm api_sketch api_weighted api_cmp api_lsh
+UNITS := api_core api_comm api_sketch api_stream api_weighted api_cmp api_lsh
 OBJS := $(patsubst %,build/%.o,$(UNITS)) build/pack_host.o
 
 all: dashing2_b200/libd2gpu.so dashing2_b200/bin/dashing2-gpu

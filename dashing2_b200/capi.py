@@ -23,7 +23,7 @@ SHAPE = {"symmetric": 0, "asymmetric": 1, "panel": 2}
 class SketchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("w", C.c_int32), ("canon", C.c_int32), ("mode", C.c_int32),
                 ("xormask", C.c_uint64), ("sketchsize", C.c_uint32), ("count_threshold", C.c_uint32),
-                ("countsketch_size", C.c_uint64)]
+                ("countsketch_size", C.c_uint64), ("alphabet", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CmpParams(C.Structure):
@@ -42,7 +42,7 @@ EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stre
            "d2g_cmp_rows_sharded_dev", "d2g_cmp_stream_sharded",
            "d2g_kmer_counts", "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
-           "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_free"]
+           "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_lsh_graph", "d2g_free"]
 
 _lib = None
 
@@ -108,6 +108,8 @@ def load():
     L.d2g_lsh_topk.restype = C.c_int
     L.d2g_lsh_topk_rows.argtypes = [vp, C.POINTER(CmpParams), vp, vp, i32, u64, u64, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
     L.d2g_lsh_topk_rows.restype = C.c_int
+    L.d2g_lsh_graph.argtypes = [vp, C.POINTER(CmpParams), vp, vp, vp, i32, C.c_double, u64, u64, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
+    L.d2g_lsh_graph.restype = C.c_int
     L.d2g_free.argtypes = [vp]; L.d2g_free.restype = None
     _lib = L
     return L
@@ -190,8 +192,8 @@ class Context:
 
     # ---- sketch ----
     @staticmethod
-    def params(mode="opmh", S=1024, k=31, w=-1, canon=True, seed=0, count_threshold=0, cssize=0):
-        return SketchParams(k, w, int(canon), MODE[mode], xormask_for_seed(seed), S, int(count_threshold), int(cssize))
+    def params(mode="opmh", S=1024, k=31, w=-1, canon=True, seed=0, count_threshold=0, cssize=0, alphabet=0):
+        return SketchParams(k, w, int(canon), MODE[mode], xormask_for_seed(seed), S, int(count_threshold), int(cssize), int(alphabet), 0)
 
     def sketch_batch(self, seq: np.ndarray, rec_off: np.ndarray, rec_entity: np.ndarray, n_entities: int,
                      p: SketchParams, want_ids=False, want_regs=True):
@@ -356,6 +358,27 @@ class Context:
         indptr = np.zeros(x1 - x0 + 1, dtype=np.uint64)
         pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()
         _check(self.L.d2g_lsh_topk_rows(self.h, C.byref(p), _ptr(regs), _ptr(cards), topk, x0, x1, _ptr(indptr), C.byref(pi), C.byref(pv)))
+        nnz = int(indptr[-1])
+        idx = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
+        val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()
+        self.L.d2g_free(pi); self.L.d2g_free(pv)
+        return indptr, idx, val
+
+    def lsh_graph(self, regs: np.ndarray, cards: np.ndarray, topk: int = -1, min_similarity: float = 0., measure="similarity", k=31, cmp_kind=0,
+                  rows=None, nlsh=0, index_regs=None, regbytes=8.0, compressed_b=0.0):
+        """d2g_lsh_graph: top-k lists (topk > 0) or a similarity-threshold graph (topk <= 0); index_regs = the f64 signatures when regs
+        are compressed registers (--topk with --fastcmp).  Returns CSR (indptr, indices, data)."""
+        regs = np.ascontiguousarray(regs, dtype=np.float64); cards = np.ascontiguousarray(cards, dtype=np.float64)
+        if index_regs is not None:
+            index_regs = np.ascontiguousarray(index_regs, dtype=np.float64)
+        n, S = regs.shape
+        p = self.cmp_params(S, n, "symmetric", measure, k=k, cmp_kind=cmp_kind, regbytes=regbytes, compressed_b=compressed_b)
+        p.nlsh = nlsh
+        x0, x1 = rows if rows is not None else (0, n)
+        indptr = np.zeros(x1 - x0 + 1, dtype=np.uint64)
+        pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()
+        _check(self.L.d2g_lsh_graph(self.h, C.byref(p), _ptr(index_regs), _ptr(regs), _ptr(cards), int(topk), float(min_similarity), x0, x1,
+                                    _ptr(indptr), C.byref(pi), C.byref(pv)))
         nnz = int(indptr[-1])
         idx = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
         val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()

@@ -53,6 +53,8 @@ struct d2g_ctx {
     std::atomic<uint64_t> launches{0};
     DevBuf seq, pcodes, pmask, recoff, recent, regs, sig, card, ids, aux, aux2, redo, ovfq;   // sketch scratch (pcodes / pmask: the packed batch)
     PinBuf stage[3]; cudaEvent_t stage_free[3] = {nullptr, nullptr, nullptr};        // pinned staging ring of the host packer
+    DevBuf items, itemcnt, itemoff, segs, nseg, sflag, sexcl, svmask, slut, stmp;   // element streams (api_stream.cu)
+    DevBuf lregs;                                                        // top-k over compressed registers: what refinement compares
     DevBuf wbuf, wtmp, lbuf;                                              // counting scratch (BagMinHash / ProbMinHash)
     DevBuf cregs, ccards, cout, clut, clut80, ctmp, cktmp;         // compare scratch
     DevBuf c16buf, c16codes, c16grank, c16flag;                    // order-code compare scratch (keys, sort buffers, codes, global ranks)
@@ -93,6 +95,13 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
                     uint64_t n_rec, uint32_t n_ent, uint64_t total_len, double *sig_d, double *card_d, uint64_t *ids_d);
 int launch_opmh_mincount(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d, const uint32_t *rec_ent_d,
                          uint64_t n_rec, uint32_t n_ent, uint64_t total_len, uint64_t *regs_d);
+// Element streams (stream_kernels.cuh: k > 32, -C with a window, protein alphabets).  When p selects one, prepare_stream builds the
+// items on the ctx stream and returns the view the ordinary launchers run over: PackedSeq with items set, item-region offsets in
+// place of rec_off, (k, w) = (1, w-k+1).  ascii_d: the record bytes on the device (protein only; the packed arrays otherwise).
+struct StreamView { d2g::PackedSeq seq; const uint64_t *rec_off_d; uint64_t total_len; d2g_sketch_params p; };
+bool is_stream_mode(const d2g_sketch_params *p);
+int prepare_stream(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint8_t *ascii_d, const uint64_t *rec_off_d,
+                   uint64_t n_rec, uint64_t total_len, StreamView *out);
 static __global__ void fill_u64_kernel(uint64_t *p, uint64_t n, uint64_t v) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }

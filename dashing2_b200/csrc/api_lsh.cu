@@ -14,11 +14,20 @@ extern "C" int d2g_lsh_topk(d2g_ctx *c, const d2g_cmp_params *p, const double *r
 
 extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const double *regs, const double *cards, int32_t topk,
                                  uint64_t x0, uint64_t x1, uint64_t *indptr_out, uint32_t **idx_out, float **val_out) {
+    if (topk <= 0) return fail(D2G_EINVAL, "topk must be > 0 (similarity-threshold graphs: d2g_lsh_graph)");
+    if (p && p->cmp_kind >= D2G_CMP_SS_COMPRESSED) return fail(D2G_EINVAL, "compressed registers: the index is built over the f64 signatures, pass both to d2g_lsh_graph");
+    return d2g_lsh_graph(c, p, nullptr, regs, cards, topk, 0., x0, x1, indptr_out, idx_out, val_out);
+}
+
+extern "C" int d2g_lsh_graph(d2g_ctx *c, const d2g_cmp_params *p, const double *index_regs, const double *regs, const double *cards, int32_t topk,
+                             double min_similarity, uint64_t x0, uint64_t x1, uint64_t *indptr_out, uint32_t **idx_out, float **val_out) {
     if (!c) return fail(D2G_EINVAL, "null ctx");
     if (int rc = check_cmp_params(p)) return rc;
     if (x0 > x1 || x1 > p->n) return fail(D2G_EINVAL, "bad row range");
-    if (topk <= 0) return fail(D2G_EINVAL, "topk must be > 0 (similarity-threshold graphs are not implemented)");
-    if (p->cmp_kind >= D2G_CMP_SS_COMPRESSED) return fail(D2G_EUNSUPPORTED, "top-k over compressed registers (--fastcmp with --topk) is not implemented on the GPU");
+    const bool threshold = topk <= 0;
+    if (!index_regs) index_regs = regs;
+    if (p->cmp_kind >= D2G_CMP_SS_COMPRESSED && index_regs == regs)
+        return fail(D2G_EINVAL, "compressed registers: pass the f64 signatures as index_regs (the reference builds the index before it compresses, src/cmp_core.cpp:741-799)");
     if (!indptr_out || !idx_out || !val_out) return fail(D2G_EINVAL, "null output");
     const uint64_t n = p->n; const uint32_t S = p->sketchsize;
     if (n < 2 || x0 == x1) { for (uint64_t i = 0; i <= x1 - x0; ++i) indptr_out[i] = 0; *idx_out = (uint32_t *)malloc(4); *val_out = (float *)malloc(4); return D2G_OK; }
@@ -32,16 +41,25 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     const uint32_t n1 = p->nlsh == 1 ? 0 : S / 2;                      // two-register tables
     const uint32_t n2 = p->nlsh == 3 ? (uint32_t)((uint64_t)S * 8 / 4) : 0;   // four-register tables: 8S / 4 (cmp_core.cpp:767)
     const uint32_t ntab = S + n1 + n2;                                 // cmp_core.cpp:757-770
-    uint64_t ntoquery = (uint64_t)((float)topk * 3.5f);                // index_build.cpp:57-60
+    uint64_t ntoquery = threshold ? n - 1 : (uint64_t)((float)topk * 3.5f);   // index_build.cpp:56-60: no cap on the candidates of a threshold graph
     ntoquery = std::min<uint64_t>(ntoquery, n - 1);
     CU(cudaFuncSetAttribute(d2g::lsh_trim_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d2g::LSH_TRIM_BIG_CAP * 8));
-    if (ntoquery == 0 || ntoquery > 4096) return fail(D2G_EUNSUPPORTED, "topk %d out of the supported range", topk);
+    if (ntoquery == 0 || (!threshold && ntoquery > 4096)) return fail(D2G_EUNSUPPORTED, "topk %d out of the supported range", topk);
+    if (threshold && ntoquery * 8 > 200 * 1024)
+        return fail(D2G_EUNSUPPORTED, "similarity-threshold graphs keep one uncapped candidate list per query in shared memory: at most %d sketches per call (got %llu)",
+                    200 * 1024 / 8 + 1, (unsigned long long)n);
     const uint32_t maxcand = (uint32_t)ntoquery;
     if (int rc = c->cregs.reserve(n * S * 8)) return rc;
     if (int rc = c->ccards.reserve(n * 8)) return rc;
-    CU(cudaMemcpyAsync(c->cregs.p, regs, n * S * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->cregs.p, index_regs, n * S * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->ccards.p, cards, n * 8, cudaMemcpyHostToDevice, st));
     const double *regs_d = c->cregs.as<double>(), *cards_d = c->ccards.as<double>();
+    const double *cmp_regs_d = regs_d;                                  // what refinement compares: the compressed registers under --fastcmp
+    if (regs != index_regs) {
+        if (int rc = c->lregs.reserve(n * S * 8)) return rc;
+        CU(cudaMemcpyAsync(c->lregs.p, regs, n * S * 8, cudaMemcpyHostToDevice, st));
+        cmp_regs_d = c->lregs.as<double>();
+    }
     auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
     const uint64_t nk = (uint64_t)ntab * n, na = 2 * n * maxcand;
     if (na >= 0x7FFFFFF0ULL) return fail(D2G_EUNSUPPORTED, "n * topk too large for one call (%llu arrival slots)", (unsigned long long)na);
@@ -82,6 +100,7 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
         cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, kA, kB, iA, iB, (int)items, (int)nt, offs, offs + 1, 0, 32, st);
         if (need > tb) { tb = need; if (int rc = c->wtmp.reserve(tb + 256)) return rc; }
         size_t tbytes = tb;
+        KernelTimer kt(c, D2G_T_SORT);
         CU(cub::DeviceSegmentedRadixSort::SortPairs(c->wtmp.p, tbytes, kA + (uint64_t)t0 * n, kB + (uint64_t)t0 * n, iA + (uint64_t)t0 * n, iB + (uint64_t)t0 * n,
                                                    (int)items, (int)nt, offs, offs + 1, 0, 32, st));
         c->launches += 6;
@@ -90,6 +109,7 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     {
         int wpb = 4;                                                  // queries (warps) per CTA; fewer when the candidate lists are long
         while (wpb > 1 && (size_t)wpb * 2 * maxcand * 4 > 96 * 1024) wpb >>= 1;
+        if ((size_t)wpb * 2 * maxcand * 4 > 200 * 1024) return fail(D2G_EUNSUPPORTED, "candidate lists of %u entries do not fit shared memory", maxcand);
         const size_t smem = (size_t)wpb * 2 * maxcand * 4;
         CU(cudaFuncSetAttribute(d2g::lsh_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(c, D2G_T_CMP);
@@ -107,7 +127,7 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
         CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, alA, alB, apA, apB, (int)na, 0, 32, st));
     }
     d2g::lsh_segments_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(alB, na, n, seg);
-    {
+    if (!threshold) {
         const bool warp_ok = maxcand <= (uint32_t)d2g::LSH_REPLAY_DCAP;
         if (warp_ok) d2g::lsh_replay_warp_kernel<<<(unsigned)((n + d2g::LSH_REPLAY_WARPS - 1) / d2g::LSH_REPLAY_WARPS), d2g::LSH_REPLAY_WARPS * 32, 0, st>>>(apB, seg, n, maxcand, lst, lsz);
         else d2g::lsh_replay_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(apB, seg, n, maxcand, 0u, lst, dset, lsz);
@@ -116,6 +136,26 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     uint32_t h_total = 0;
     CU(cudaMemcpyAsync(&h_total, seg + n, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (threshold && h_total) {
+        // first arrival of every id per list, ordered by (-hits, id): two segmented sorts over the arrivals (see lsh_kernels.cuh).
+        // Buffers: apA / alA are free after the sort by list; lst / dset are not used yet.
+        uint64_t *k1 = apA, *k1s = reinterpret_cast<uint64_t *>(lst); uint32_t *cd = alA, *cds = dset;
+        const unsigned gt = (h_total + 255) / 256;
+        d2g::lsh_thr_key1_kernel<<<gt, 256, 0, st>>>(alB, apB, seg, h_total, k1, cd);
+        size_t need = 0, need2 = 0;
+        cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, k1, k1s, cd, cds, (int)h_total, (int)n, seg, seg + 1, 0, 64, st);
+        cub::DeviceSegmentedRadixSort::SortKeys(nullptr, need2, k1, k1s, (int)h_total, (int)n, seg, seg + 1, 0, 64, st);
+        need = std::max(need, need2);
+        if (need > tb) { tb = need; if (int rc = c->wtmp.reserve(tb + 256)) return rc; }
+        size_t tbytes = tb;
+        CU(cub::DeviceSegmentedRadixSort::SortPairs(c->wtmp.p, tbytes, k1, k1s, cd, cds, (int)h_total, (int)n, seg, seg + 1, 0, 64, st));
+        d2g::lsh_thr_key2_kernel<<<gt, 256, 0, st>>>(alB, k1s, cds, seg, h_total, k1);
+        tbytes = tb;
+        CU(cub::DeviceSegmentedRadixSort::SortKeys(c->wtmp.p, tbytes, k1, k1s, (int)h_total, (int)n, seg, seg + 1, 0, 64, st));
+        d2g::lsh_thr_lists_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seg, n, k1s, lsz);
+        c->launches += 9;
+        CU(cudaGetLastError());
+    } else if (threshold) CU(cudaMemsetAsync(lsz, 0, n * 4, st));
     if (getenv("D2G_DEBUG")) {
         std::vector<uint32_t> hs(n);
         cudaMemcpy(hs.data(), lsz, n * 4, cudaMemcpyDeviceToHost);
@@ -130,14 +170,21 @@ extern "C" int d2g_lsh_topk_rows(d2g_ctx *c, const d2g_cmp_params *p, const doub
     const int is_dist = !(p->measure == D2G_UNION_SIZE || p->measure == D2G_INTERSECTION || p->measure == D2G_SIMILARITY || p->measure == D2G_CONTAINMENT);
     const float mult = is_dist ? 1.f : -1.f;
     if (h_total) {
+        KernelTimer kt(c, D2G_T_LSH_REFINE);
         const uint64_t threads = (uint64_t)h_total * 32;
-        if (p->cmp_kind == D2G_CMP_GTLT) d2g::lsh_refine_kernel<0><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(regs_d, cards_d, n, seg, lsz, lst, k, mult);
-        else d2g::lsh_refine_kernel<1><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(regs_d, cards_d, n, seg, lsz, lst, k, mult);
+        if (p->cmp_kind == D2G_CMP_GTLT || p->cmp_kind == D2G_CMP_SS_COMPRESSED)
+            d2g::lsh_refine_kernel<0><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cmp_regs_d, cards_d, n, seg, lsz, lst, k, mult);
+        else d2g::lsh_refine_kernel<1><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cmp_regs_d, cards_d, n, seg, lsz, lst, k, mult);
+        c->launches++;
+    }
+    const uint32_t keep = threshold ? 0xFFFFFFFFu : (uint32_t)topk;
+    if (threshold) {       // refine.cpp:45-68: threshold + 20-consecutive-failures walk in (-hits, id) order; the trim kernels then only sort
+        d2g::lsh_thr_filter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seg, n, min_similarity, is_dist, lst, lsz);
         c->launches++;
     }
     // short lists first: a list the second kernel has trimmed (> LSH_TRIM_CAP entries before) must not be seen as short afterwards
-    d2g::lsh_trim_kernel<<<(unsigned)((n + d2g::LSH_TRIM_WARPS - 1) / d2g::LSH_TRIM_WARPS), d2g::LSH_TRIM_WARPS * 32, 0, st>>>(seg, n, (uint32_t)topk, is_dist, lst, lsz);
-    d2g::lsh_trim_big_kernel<<<(unsigned)n, d2g::LSH_TRIM_BIG_THREADS, d2g::LSH_TRIM_BIG_CAP * 8, st>>>(seg, n, (uint32_t)topk, is_dist, lst, lsz);
+    d2g::lsh_trim_kernel<<<(unsigned)((n + d2g::LSH_TRIM_WARPS - 1) / d2g::LSH_TRIM_WARPS), d2g::LSH_TRIM_WARPS * 32, 0, st>>>(seg, n, keep, is_dist, lst, lsz, threshold ? 1 : 0);
+    d2g::lsh_trim_big_kernel<<<(unsigned)n, d2g::LSH_TRIM_BIG_THREADS, d2g::LSH_TRIM_BIG_CAP * 8, st>>>(seg, n, keep, is_dist, lst, lsz, threshold ? 1 : 0);
     c->launches += 2;
     // 6. CSR: indptr = exclusive scan of list sizes
     {

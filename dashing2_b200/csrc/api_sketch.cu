@@ -17,11 +17,17 @@ __global__ void opmh_ids_kernel(const uint64_t *regs, uint64_t *ids, uint64_t n_
 
 int check_sketch_params(const d2g_sketch_params *p) {
     if (!p) return fail(D2G_EINVAL, "null params");
-    if (p->k < 1 || p->k > 32) return fail(D2G_EUNSUPPORTED, "k=%d: only 1..32 (exact 2-bit encoding) is implemented; k>32 rolling hash is out of scope", p->k);
+    const int A = p->alphabet;
+    if (A != 0 && A != 4 && A != 20 && A != 14 && A != 6 && A != 8) return fail(D2G_EINVAL, "alphabet %d: 0/4 (DNA), 20, 14, 6 or 8", A);
     if (p->sketchsize == 0) return fail(D2G_EINVAL, "sketchsize must be > 0");
+    if (A != 0 && A != 4) {
+        const int kmax = A == 20 ? 14 : A == 14 ? 16 : A == 6 ? 24 : 22;     // rhtraits.h nper64
+        if (p->k < 1 || p->k > kmax) return fail(D2G_EUNSUPPORTED, "k=%d with the %d-letter protein alphabet: 1..%d (exact encoding) is implemented; the rolling "
+                                                 "hash over protein alphabets is not", p->k, A, kmax);
+        if (p->canon) return fail(D2G_EINVAL, "protein k-mers are never canonical (src/options.h:328-331): pass canon = 0");
+    } else if (p->k < 1 || p->k > 2048) return fail(D2G_EUNSUPPORTED, "k=%d: 1..32 (exact encoding) and 33..2048 (rolling hash) are implemented", p->k);
     if (p->w > p->k) {
-        if (p->w > d2g::SK_MAX_W) return fail(D2G_EUNSUPPORTED, "window %d > %d not supported", p->w, d2g::SK_MAX_W);
-        if (!p->canon) return fail(D2G_EUNSUPPORTED, "windowed minimizers without canonicalisation (-C -w) are not implemented on the GPU");
+        if (is_stream_mode(p) ? p->w - p->k + 1 > d2g::SK_MAX_W : p->w > d2g::SK_MAX_W) return fail(D2G_EUNSUPPORTED, "window %d with k=%d not supported (at most %d)", p->w, p->k, d2g::SK_MAX_W);
     }
     if (p->mode < D2G_MODE_OPMH || p->mode > D2G_MODE_PROBMINHASH) return fail(D2G_EINVAL, "bad sketch mode %d", p->mode);
     if ((p->mode == D2G_MODE_BAGMINHASH || p->mode == D2G_MODE_PROBMINHASH) && p->sketchsize < 2) return fail(D2G_EINVAL, "weighted sketches need sketchsize >= 2");
@@ -278,7 +284,12 @@ namespace {
 // except where a launcher has to read a counter back (Full SetSketch, counting sketches).
 int sketch_packed_dev(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq &seq_d, const uint64_t *rec_off_d,
                       const uint32_t *rec_entity_d, uint64_t n_rec, uint32_t n_entities, uint64_t total_len,
-                      uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d) {
+                      uint64_t *regs_u64_out_d, double *sig_out_d, double *card_out_d, uint64_t *ids_out_d, const uint8_t *ascii_d = nullptr) {
+    if (is_stream_mode(p)) {       // k > 32, -C with a window, protein: elements first, then the same launchers over item regions
+        StreamView sv;
+        if (int rc = prepare_stream(c, p, seq_d, ascii_d, rec_off_d, n_rec, total_len, &sv)) return rc;
+        return sketch_packed_dev(c, &sv.p, sv.seq, sv.rec_off_d, rec_entity_d, n_rec, n_entities, sv.total_len, regs_u64_out_d, sig_out_d, card_out_d, ids_out_d);
+    }
     if (p->mode == D2G_MODE_OPMH) {
         if (sig_out_d || card_out_d)
             return fail(D2G_EINVAL, "OPMH signatures/cardinalities are x87 long-double transforms of the u64 minima (src/oph.h:240-263): "
@@ -340,6 +351,7 @@ extern "C" int d2g_sketch_batch_packed_dev(d2g_ctx *c, const d2g_sketch_params *
     if (!c) return fail(D2G_EINVAL, "null ctx");
     if (int rc = check_sketch_params(p)) return rc;
     if (total_len && (!codes_d || !mask_d)) return fail(D2G_EINVAL, "null packed sequence");
+    if (p->alphabet != 0 && p->alphabet != 4) return fail(D2G_EINVAL, "protein alphabets need the record bytes, not packed DNA");
     CU(cudaSetDevice(c->device));
     return sketch_packed_dev(c, p, d2g::PackedSeq{codes_d, mask_d}, rec_off_d, rec_entity_d, n_rec, n_entities, total_len,
                              regs_u64_out_d, sig_out_d, card_out_d, ids_out_d);
@@ -356,7 +368,7 @@ extern "C" int d2g_sketch_batch_dev(d2g_ctx *c, const d2g_sketch_params *p, cons
     if (int rc = c->pmask.reserve(nw * 4)) return rc;
     if (int rc = d2g_pack_dev(c, seq_d, total_len, c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>())) return rc;
     return sketch_packed_dev(c, p, d2g::PackedSeq{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()}, rec_off_d, rec_entity_d, n_rec, n_entities,
-                             total_len, regs_u64_out_d, sig_out_d, card_out_d, ids_out_d);
+                             total_len, regs_u64_out_d, sig_out_d, card_out_d, ids_out_d, reinterpret_cast<const uint8_t *>(seq_d));
 }
 
 // ---- host entry points ------------------------------------------------------------------------------------------------
@@ -408,7 +420,9 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
     const uint64_t *off_d = c->recoff.as<uint64_t>();
     const uint32_t *ent_d = c->recent.as<uint32_t>();
     const bool opmh_mincount = p->mode == D2G_MODE_OPMH && p->count_threshold > 1;   // counts need the whole batch sorted at once
-    const bool chunked = (p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH) && !opmh_mincount;
+    const bool stream_mode = is_stream_mode(p), protein = p->alphabet != 0 && p->alphabet != 4;
+    if (protein && !hs.ascii) return fail(D2G_EINVAL, "protein alphabets need the record bytes, not packed DNA");
+    const bool chunked = (p->mode == D2G_MODE_OPMH || p->mode == D2G_MODE_FULL_SETSKETCH) && !opmh_mincount && !stream_mode;
     auto off_at = [&](uint64_t r) -> uint64_t { return n_rec ? rec_off[r] : 0; };
     uint64_t target = 384ULL << 20;                   // bases per chunk (per-chunk launches and read-backs cost ~0.5 ms: amortised over >= 1.5 ms of kernel)
     if (const char *ev = getenv("D2G_CHUNK_BYTES")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));
@@ -436,7 +450,8 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
         // the packing rate measured per chunk (noisy: host threads and the DMA engine compete for the same memory bandwidth).
         fixed_f = !getenv("D2G_HYBRID_ADAPT");
         if (const char *ev = getenv("D2G_HYBRID_F")) { hybrid_f = std::max(0., std::min(1., atof(ev))); fixed_f = true; }   // 1 = pack everything on the host
-        if (ascii_pinned) {                                // device staging of the ASCII tails: sized once for the largest chunk
+        if (protein) { if (int rc = c->seq.reserve(total_len + 64)) { free_evs(); return rc; } }
+        else if (ascii_pinned) {                           // device staging of the ASCII tails: sized once for the largest chunk
             uint64_t mw = 0;
             for (size_t i = 0; i < nch; ++i) mw = std::max(mw, w_hi(i) - w_lo(i));
             if (int rc = c->seq.reserve(mw * 32 + 4096)) { free_evs(); return rc; }
@@ -449,7 +464,9 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
             const uint64_t a = w_lo(i), b = w_hi(i);
             cudaError_t e = cudaSuccess;
             if (b > a) {
-                if (hs.ascii) {
+                if (protein) {                                       // residues go up as they are (one chunk): protein_kernel reads bytes
+                    e = cudaMemcpyAsync(c->seq.p, hs.ascii, total_len, cudaMemcpyHostToDevice, c->copy_stream);
+                } else if (hs.ascii) {
                     // Hybrid: the tail [ws, b) of the chunk goes up as ASCII (DMA from page-locked memory costs no host cycles) and is packed by
                     // the device; the head [a, ws) is packed by the host threads meanwhile and goes up at a quarter of the bytes.  The split
                     // balances host packing against the link: f / P = ((1 - f) + f / 4) / B for packing rate P and link rate B (bases/s, bytes/s).
@@ -519,7 +536,11 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
         const uint64_t nr = ch.r1 - ch.r0; const uint32_t ne = ch.e1 - ch.e0;
         const SketchRange rg{off_at(ch.r0), off_at(ch.r1), ch.e0};
         int rc;
-        if (opmh_mincount)
+        if (stream_mode)                                             // one chunk: the whole batch
+            rc = sketch_packed_dev(c, p, seq_d, off_d, ent_d, n_rec, n_entities, total_len, p->mode == D2G_MODE_OPMH ? c->regs.as<uint64_t>() : nullptr,
+                                   p->mode == D2G_MODE_OPMH ? nullptr : c->sig.as<double>(), p->mode == D2G_MODE_OPMH ? nullptr : c->card.as<double>(),
+                                   (ids_out && p->mode != D2G_MODE_OPMH) ? c->ids.as<uint64_t>() : nullptr, protein ? c->seq.as<uint8_t>() : nullptr);
+        else if (opmh_mincount)
             rc = launch_opmh_mincount(c, p, seq_d, off_d, ent_d, n_rec, n_entities, total_len, c->regs.as<uint64_t>());
         else if (p->mode == D2G_MODE_OPMH)
             rc = launch_opmh(c, p, seq_d, off_d + ch.r0, ent_d + ch.r0, nr, ne, rg.pos_end, c->regs.as<uint64_t>() + (uint64_t)ch.e0 * m, &rg);

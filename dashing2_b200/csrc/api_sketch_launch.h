@@ -3,6 +3,7 @@
 #include "api_internal.h"
 #include "sketch_kernels.cuh"
 #include "sketch_fast.cuh"
+#include "stream_kernels.cuh"
 
 namespace {
 uint64_t pick_span(const d2g_ctx *c, uint64_t total_len, uint32_t m) {
@@ -29,8 +30,23 @@ d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, c
     return a;
 }
 
+// element streams (stream_kernels.cuh): the same spans and Consumer protocol over item regions instead of sequence positions
+template <class Consumer>
+int launch_stream(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer::Params &cp, int tcls) {
+    KernelTimer kt(c, tcls);
+    const size_t smem = d2g::stream_smem_bytes<Consumer>(a.m, a.w > a.k);
+    if (smem > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sketch with %u registers needs %zu bytes of shared memory per CTA (max 200 KiB)", a.m, smem);
+    const uint64_t grid = (a.pos_end - a.pos_base + a.span - 1) / a.span;
+    CU(cudaFuncSetAttribute(d2g::stream_kernel<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    d2g::stream_kernel<Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+    c->launches++;
+    CU(cudaGetLastError());
+    return D2G_OK;
+}
+
 template <class Consumer>
 int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer::Params &cp, bool windowed, int tcls = D2G_T_SKETCH_MAIN) {
+    if (a.seq.items) return launch_stream<Consumer>(c, a, cp, tcls);
     KernelTimer kt(c, tcls);
     const size_t smem = d2g::sketch_smem_bytes<Consumer>(a.m, a.score_slots);
     if (smem > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sketch with %u registers needs %zu bytes of shared memory per CTA (max 200 KiB)", a.m, smem);
@@ -57,7 +73,7 @@ constexpr uint64_t kRedoCap = 1ULL << 16;
 
 template <class Consumer>
 int launch_sketch_windowed_set(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer::Params &cp, int tcls = D2G_T_SKETCH_MAIN) {
-    if (!sketch_fast_eligible(a)) return launch_sketch<Consumer>(c, a, cp, true, tcls);
+    if (a.seq.items || !sketch_fast_eligible(a)) return launch_sketch<Consumer>(c, a, cp, true, tcls);
     if (int rc = c->redo.reserve((kRedoCap + 2) * 8)) return rc;
     unsigned long long *redo_count = c->redo.as<unsigned long long>();
     uint64_t *redo_list = c->redo.as<uint64_t>() + 2;

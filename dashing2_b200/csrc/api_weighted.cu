@@ -76,6 +76,8 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
         cub::DeviceScan::ExclusiveSum(nullptr, t3, flag, excl, n, st);
         const size_t tb = std::max(t1, std::max(t2, t3));
         if (int rc = c->wtmp.reserve(tb + 256)) return rc;
+        {
+        KernelTimer kt(c, D2G_T_SORT);
         size_t tbytes = tb;
         CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
         tbytes = tb;
@@ -87,6 +89,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
         CU(cub::DeviceScan::ExclusiveSum(c->wtmp.p, tbytes, flag, excl, n, st));
         d2g::rle_scatter_kernel<<<gb, 256, 0, st>>>(flag, excl, entA, n, pos, n_valid);
         c->launches += 3;
+        }
         uint32_t h_last[2] = {0, 0};
         CU(cudaMemcpyAsync(&h_last[0], excl + (n - 1), 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(&h_last[1], flag + (n - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -253,29 +256,37 @@ extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const 
     if (!distinct_out && n_entities) return fail(D2G_EINVAL, "null output");
     if (n_rec && (!rec_off || !rec_entity)) return fail(D2G_EINVAL, "null record tables");
     CU(cudaSetDevice(c->device));
-    const uint64_t n = n_rec ? rec_off[n_rec] : 0;
-    if (n && !seq) return fail(D2G_EINVAL, "null sequence buffer");
+    const uint64_t n_bases = n_rec ? rec_off[n_rec] : 0;
+    if (n_bases && !seq) return fail(D2G_EINVAL, "null sequence buffer");
     if (n_rec && rec_off[0] != 0) return fail(D2G_EINVAL, "rec_off[0] must be 0");
-    if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "distinct k-mers: at most 2^32 bases per call (got %llu)", (unsigned long long)n);
+    if (n_bases >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "distinct k-mers: at most 2^32 bases per call (got %llu)", (unsigned long long)n_bases);
     for (uint64_t r = 0; r < n_rec; ++r) {
         if (rec_off[r + 1] < rec_off[r]) return fail(D2G_EINVAL, "rec_off not monotone at %llu", (unsigned long long)r);
         if (rec_entity[r] >= n_entities) return fail(D2G_EINVAL, "rec_entity[%llu]=%u >= n_entities", (unsigned long long)r, rec_entity[r]);
         if (r && rec_entity[r] < rec_entity[r - 1]) return fail(D2G_EINVAL, "rec_entity must be non-decreasing");
     }
     for (uint32_t e = 0; e < n_entities; ++e) distinct_out[e] = 0;
-    if (!n || !n_rec || !n_entities) return D2G_OK;
-    if (int rc = c->seq.reserve(n + 64)) return rc;
+    if (!n_bases || !n_rec || !n_entities) return D2G_OK;
+    if (int rc = c->seq.reserve(n_bases + 64)) return rc;
     if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
     if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
-    const uint64_t nw = d2g::packed_words(n);
+    const uint64_t nw = d2g::packed_words(n_bases);
     if (int rc = c->pcodes.reserve(nw * 8)) return rc;
     if (int rc = c->pmask.reserve(nw * 4)) return rc;
     cudaStream_t st = c->stream;
-    CU(cudaMemcpyAsync(c->seq.p, seq, n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->seq.p, seq, n_bases, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, st));
-    if (int rc = d2g_pack_dev(c, c->seq.as<char>(), n, c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>())) return rc;
-    const d2g::PackedSeq seq_d{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()};
+    if (int rc = d2g_pack_dev(c, c->seq.as<char>(), n_bases, c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>())) return rc;
+    d2g::PackedSeq seq_d{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()};
+    const uint64_t *off_d = c->recoff.as<uint64_t>();
+    uint64_t n = n_bases;
+    StreamView sv;
+    if (is_stream_mode(p)) {                                        // element streams: slots are item regions (stream_kernels.cuh)
+        if (int rc = prepare_stream(c, p, seq_d, c->seq.as<uint8_t>(), off_d, n_rec, n_bases, &sv)) return rc;
+        p = &sv.p; seq_d = sv.seq; off_d = sv.rec_off_d; n = sv.total_len;
+        if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "distinct k-mers: at most 2^31 bases per call for this k-mer stream");
+    }
     auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
     uint64_t off = 0;
     const uint64_t o_hvA = off; off += al(n * 8 + 8);
@@ -291,7 +302,7 @@ extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const 
     CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
     CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
     CU(cudaMemsetAsync(cnt, 0, (uint64_t)n_entities * 8, st));
-    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, off_d, c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
     if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
     d2g::EmitConsumer::Params ep{hvA, entA, a.span};
     if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
@@ -343,18 +354,18 @@ extern "C" int d2g_kmer_counts(d2g_ctx *c, const d2g_sketch_params *p, const uin
     if (n_rec && (!rec_off || !rec_entity)) return fail(D2G_EINVAL, "null record tables");
     CU(cudaSetDevice(c->device));
     const uint32_t S = p->sketchsize;
-    const uint64_t n = n_rec ? rec_off[n_rec] : 0, n_ids = (uint64_t)n_entities * S;
+    const uint64_t n_bases = n_rec ? rec_off[n_rec] : 0, n_ids = (uint64_t)n_entities * S;
     for (uint64_t i = 0; i < n_ids; ++i) counts_out[i] = 0.f;
-    if (!n || !n_rec || !n_entities) return D2G_OK;
+    if (!n_bases || !n_rec || !n_entities) return D2G_OK;
     if (!codes) return fail(D2G_EINVAL, "null packed sequence");
     if (rec_off[0] != 0) return fail(D2G_EINVAL, "rec_off[0] must be 0");
-    if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "k-mer counts: at most 2^32 bases per call (got %llu)", (unsigned long long)n);
+    if (n_bases >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "k-mer counts: at most 2^32 bases per call (got %llu)", (unsigned long long)n_bases);
     for (uint64_t r = 0; r < n_rec; ++r) {
         if (rec_off[r + 1] < rec_off[r]) return fail(D2G_EINVAL, "rec_off not monotone at %llu", (unsigned long long)r);
         if (rec_entity[r] >= n_entities) return fail(D2G_EINVAL, "rec_entity[%llu]=%u >= n_entities", (unsigned long long)r, rec_entity[r]);
         if (r && rec_entity[r] < rec_entity[r - 1]) return fail(D2G_EINVAL, "rec_entity must be non-decreasing");
     }
-    const uint64_t nw = d2g::packed_words(n);
+    const uint64_t nw = d2g::packed_words(n_bases);
     if (int rc = c->pcodes.reserve(nw * 8)) return rc;
     if (int rc = c->pmask.reserve(nw * 4)) return rc;
     if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
@@ -367,7 +378,15 @@ extern "C" int d2g_kmer_counts(d2g_ctx *c, const d2g_sketch_params *p, const uin
     CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->recent.p, rec_entity, n_rec * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->ids.p, ids, n_ids * 8, cudaMemcpyHostToDevice, st));
-    const d2g::PackedSeq seq_d{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()};
+    d2g::PackedSeq seq_d{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()};
+    const uint64_t *off_d = c->recoff.as<uint64_t>();
+    uint64_t n = n_bases;
+    StreamView sv;
+    if (is_stream_mode(p)) {                                        // element streams: slots are item regions (stream_kernels.cuh)
+        if (int rc = prepare_stream(c, p, seq_d, nullptr, off_d, n_rec, n_bases, &sv)) return rc;
+        p = &sv.p; seq_d = sv.seq; off_d = sv.rec_off_d; n = sv.total_len;
+        if (n >= 0xFFFFFFF0ULL) return fail(D2G_EINVAL, "k-mer counts: at most 2^31 bases per call for this k-mer stream");
+    }
     auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
     uint64_t off = 0;
     const uint64_t o_hvA = off; off += al(n * 8 + 8);
@@ -380,7 +399,7 @@ extern "C" int d2g_kmer_counts(d2g_ctx *c, const d2g_sketch_params *p, const uin
     uint32_t *entA = (uint32_t *)(B + o_entA), *entB = (uint32_t *)(B + o_entB);
     CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
     CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
-    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, c->recoff.as<uint64_t>(), c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, off_d, c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
     if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
     d2g::EmitConsumer::Params ep{hvA, entA, a.span};
     if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;

@@ -68,9 +68,11 @@ struct Opts {
     uint64_t S = 1024, seed = 0;
     bool canon = true, cache = false, save_kmers = false, presketched = false, binary = false, parse_by_seq = false;
     int mode = D2G_MODE_OPMH;            // ONE_PERM default (src/sketch_main.cpp:27)
+    int alphabet = 0;                    // 0 = DNA; 20 / 14 / 6 / 8: --protein / --protein14 / --protein6 / --protein8 (src/options.h:328-331)
     int measure = D2G_SIMILARITY;
     int shape = D2G_SYMMETRIC; bool phylip = false;
     int topk = -1;
+    bool nn_threshold = false; double min_similarity = 0.;   // --similarity-threshold x / -T x (src/options.h:75,309)
     unsigned count_threshold = 0;          // -m / --count-threshold (src/options.h:83-84,352)
     int nlsh = 2;                          // --nLSH (src/options.h:162-163,380)
     uint64_t cssize = 0;                   // -c / --countsketch-size / --countmin-size (src/options.h:78-79,357)
@@ -105,7 +107,8 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else if (a == "--outprefix" || a == "--prefix") o.outprefix = arg();
         else if (a == "--seed") o.seed = std::stoull(arg());
         else if (a == "--count-threshold" || a == "--threshold" || shortarg("-m")) o.count_threshold = (unsigned)std::max(0, std::atoi(arg().c_str()));
-        else if (a == "--topk" || a == "--top-k" || shortarg("-K")) o.topk = std::stoi(arg());
+        else if (a == "--topk" || a == "--top-k" || shortarg("-K")) { o.topk = std::stoi(arg()); o.nn_threshold = false; }
+        else if (a == "--similarity-threshold" || shortarg("-T")) { o.min_similarity = std::atof(arg().c_str()); o.nn_threshold = true; o.topk = -1; }
         else if (a == "--fastcmp" || a == "--regsize") {
             o.fastcmp = std::atof(arg().c_str());
             if (o.fastcmp != 8. && o.fastcmp != 4. && o.fastcmp != 2. && o.fastcmp != 1.) die("--fastcmp must have 8, 4, 2, or 1 as the argument. These are the only register sizes supported.");
@@ -122,6 +125,10 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else if (a == "--multiset" || a == "--bagminhash" || a == "--bmh" || a == "--BMH") o.mode = D2G_MODE_BAGMINHASH;
         else if (a == "--prob" || a == "--probs" || a == "--pminhash" || a == "--pmh" || a == "--PMH" || a == "--probminhash" || a == "-P") o.mode = D2G_MODE_PROBMINHASH;
         else if (a == "--no-canon" || a == "-C") o.canon = false;
+        else if (a == "--protein" || a == "--protein20" || a == "--enable-protein") { o.alphabet = 20; o.canon = false; }
+        else if (a == "--protein14") { o.alphabet = 14; o.canon = false; }
+        else if (a == "--protein6") { o.alphabet = 6; o.canon = false; }
+        else if (a == "--protein8") { o.alphabet = 8; o.canon = false; }
         else if (a == "--cache" || a == "--cache-sketches" || a == "-W") o.cache = true;
         else if (a == "--save-kmers" || a == "-s") o.save_kmers = true;
         else if (a == "--presketched") o.presketched = true;
@@ -141,7 +148,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         } else if (!a.empty() && a[0] == '-' && a.size() > 1) die("option " + a + " is not supported by the GPU front-end (see DESIGN.md section 7)");
         else o.paths.push_back(a);
     }
-    if (o.k < 0) o.k = 32;   // nregperitem(DNA, 64-bit), src/sketch_main.cpp:70
+    if (o.k < 0) o.k = o.alphabet == 20 ? 14 : o.alphabet == 14 ? 16 : o.alphabet == 6 ? 24 : o.alphabet == 8 ? 22 : 32;   // nregperitem(rht, 64-bit), src/sketch_main.cpp:70
     if (const char *ev = getenv("D2G_GPUS")) if (o.ngpus == 1) o.ngpus = std::max(1, atoi(ev));
     auto read_list = [](const std::string &f, std::vector<std::string> &dst) {
         std::ifstream ifs(f); if (!ifs) die("No path found at " + f);
@@ -172,7 +179,9 @@ std::string makedest(const Opts &o, const std::string &path) {   // src/fastxmer
     if (counted) ret += o.cssize ? ".CountMinCounting" + std::to_string(o.cssize) : std::string(".ExactCounting");
     ret += '.';
     ret += o.mode == D2G_MODE_BAGMINHASH ? "MultisetSpace" : o.mode == D2G_MODE_PROBMINHASH ? "ProbsetSpace" : "SetSpace";
-    return ret + ".DNA" + suffix(o.mode);
+    // bns::to_string(InputType), bonsai/include/bonsai/rhtraits.h:155-169
+    const char *rht = o.alphabet == 20 ? ".PROTEIN20" : o.alphabet == 14 ? ".PROTEIN_14" : o.alphabet == 6 ? ".PROTEIN_6" : o.alphabet == 8 ? ".PROTEIN_3BIT" : ".DNA";
+    return ret + rht + suffix(o.mode);
 }
 
 // ---- FASTA/FASTQ records, kseq semantics ---------------------------------------------------------
@@ -273,6 +282,7 @@ struct Sketches { std::vector<double> sig, card; std::vector<uint64_t> ids; std:
 d2g_sketch_params sketch_params(const Opts &o) {
     d2g_sketch_params p{};
     p.k = o.k; p.w = o.w; p.canon = o.canon; p.mode = o.mode; p.sketchsize = (uint32_t)o.S; p.count_threshold = o.count_threshold;
+    p.alphabet = o.alphabet;
     if (o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH) p.countsketch_size = o.cssize;   // set sketches never count (src/fastxsketch.cpp:425-427)
     p.xormask = 0;
     if (o.seed) { // Wang(seed), src/enums.cpp:133-140
@@ -289,6 +299,7 @@ void sketch_inputs(Gpus &gpus, const Opts &o, Sketches &sk) {
     sk.sig.assign(n * S, 0.); sk.card.assign(n, 0.);
     if (o.save_kmers) sk.ids.assign(n * S, 0);
     d2g_sketch_params p = sketch_params(o);
+    if (o.alphabet) p.alphabet = 0;   // per FILE nothing is fed to the sketch for protein input (see below): the records go down empty
     std::vector<char> todo(n, 1);
     if (o.cache) {   // cache hit = load the per-file sketch (src/fastxsketch.cpp:327-373)
         for (size_t i = 0; i < n; ++i) {
@@ -328,11 +339,15 @@ void sketch_inputs(Gpus &gpus, const Opts &o, Sketches &sk) {
             for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] { for (size_t j; (j = next++) < idx.size();) read_fastx(o.paths[idx[j]], recs[j]); });
             for (auto &t : th) t.join();
         }
+        // Protein input per FILE: the reference binary feeds nothing to the sketch in this mode (empty registers; pinned by the prot*
+        // fixtures of tests/golden/make_golden_protein.py) -- only --parse-by-seq sketches residues.  Reproduced, not improved on.
+        if (o.alphabet) for (auto &fr : recs) { fr.seq.clear(); fr.ends.assign(fr.ends.size(), 0); }
         if (G == 1) g_timer.mark("read + parse batch");
         // Sub-batches by the bases actually read (the on-disk size says little for .gz): the counting sketches and -m sort a whole batch at
         // once (at most 2^32 bases, ~36 bytes of scratch per base), everything else is only bounded by device memory.
         const bool whole_batch_sort = o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH || (o.mode == D2G_MODE_OPMH && o.count_threshold > 1);
-        const uint64_t max_bases = whole_batch_sort ? 2000000000ULL : 16000000000ULL;
+        const bool element_stream = o.k > 32 || (o.w > o.k && !o.canon);   // stream_kernels.cuh: 8-16 bytes of elements per base on the device
+        const uint64_t max_bases = (whole_batch_sort || element_stream) ? 2000000000ULL : 16000000000ULL;
         for (size_t g0 = 0; g0 < idx.size();) {
             size_t g1 = g0; uint64_t tot = 0;
             while (g1 < idx.size() && (g1 == g0 || tot + recs[g1].seq.size() <= max_bases)) tot += recs[g1++].seq.size();
@@ -451,7 +466,9 @@ void write_stacked(const Opts &o, const Sketches &sk) {
     if (o.save_kmers) {
         const std::string kp = o.outfile + ".kmer64";
         fp = xopen(kp, "wb");
-        const uint32_t hdr[4] = {uint32_t(0) | (uint32_t(o.canon) << 8), (uint32_t)S, (uint32_t)o.k, (uint32_t)(o.w < 0 ? o.k : o.w)};
+        // the InputType enumerator (rhtraits.h:7-20): DNA 0, PROTEIN20 2, PROTEIN_3BIT 3, PROTEIN_14 4, PROTEIN_6 5
+        const uint32_t rht = o.alphabet == 20 ? 2u : o.alphabet == 8 ? 3u : o.alphabet == 14 ? 4u : o.alphabet == 6 ? 5u : 0u;
+        const uint32_t hdr[4] = {rht | (uint32_t(o.canon) << 8), (uint32_t)S, (uint32_t)o.k, (uint32_t)(o.w < 0 ? o.k : o.w)};
         xwrite(hdr, 4, 4, fp, kp); xwrite(&o.seed, 8, 1, fp, kp); xwrite(sk.ids.data(), 8, n * S, fp, kp); xclose(fp, kp);
         fp = xopen(kp + ".names.txt", "wb");
         for (auto &nm : sk.names) { std::fputs(nm.c_str(), fp); std::fputc('\n', fp); }
@@ -561,19 +578,23 @@ void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
     std::FILE *fp = to_stdout ? stdout : std::fopen(o.cmpout.c_str(), "wb");
     if (!fp) die("Failed to open path " + o.cmpout + " for writing");
     cp.nlsh = o.nlsh;
-    if (o.topk > 0) {   // KNN graph: build_index + refine_results + emit_neighbors (src/cmp_core.cpp:756-799, src/emitnn.cpp:12-52)
+    if (o.topk > 0 || o.nn_threshold) {   // KNN / thresholded graph: build_index + refine_results + emit_neighbors (src/cmp_core.cpp:756-799, src/emitnn.cpp:12-52)
         cp.shape = D2G_SYMMETRIC;
         std::vector<uint64_t> indptr(n + 1); uint32_t *idx = nullptr; float *val = nullptr;
         const double *r = sk.sig.data();
         if (cp.cmp_kind == D2G_CMP_EQ && sk.ids.size() == sk.sig.size()) r = reinterpret_cast<const double *>(sk.ids.data());
-        if (G == 1) chk(d2g_lsh_topk(ctx, &cp, r, sk.card.data(), o.topk, indptr.data(), &idx, &val));
+        // --fastcmp: the index is built over the f64 signatures, refinement compares the compressed registers (src/cmp_core.cpp:741-799)
+        const double *ir = creg.empty() ? nullptr : sk.sig.data();
+        if (!creg.empty()) r = creg.data();
+        const int32_t tk = o.nn_threshold ? -1 : o.topk;
+        if (G == 1) chk(d2g_lsh_graph(ctx, &cp, ir, r, sk.card.data(), tk, o.min_similarity, 0, n, indptr.data(), &idx, &val));
         else {   // every device builds the index and scans all queries, but replays / refines / trims only its own range of lists
             std::vector<std::vector<uint64_t>> ip(G); std::vector<uint32_t *> ix(G, nullptr); std::vector<float *> vl(G, nullptr);
             std::vector<std::thread> ws;
             for (size_t g = 0; g < G; ++g) ws.emplace_back([&, g] {
                 const uint64_t x0 = n * g / G, x1 = n * (g + 1) / G;
                 ip[g].assign(x1 - x0 + 1, 0);
-                chk(d2g_lsh_topk_rows(gpus.get(g), &cp, r, sk.card.data(), o.topk, x0, x1, ip[g].data(), &ix[g], &vl[g]));
+                chk(d2g_lsh_graph(gpus.get(g), &cp, ir, r, sk.card.data(), tk, o.min_similarity, x0, x1, ip[g].data(), &ix[g], &vl[g]));
             });
             for (auto &t : ws) t.join();
             uint64_t tot = 0; for (size_t g = 0; g < G; ++g) tot += ip[g].back();

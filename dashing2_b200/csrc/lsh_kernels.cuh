@@ -237,6 +237,8 @@ lsh_replay_warp_kernel(const uint64_t *apay, const uint32_t *seg, uint64_t n, ui
 }
 
 // one warp per surviving edge: exact compare() of list owner x and neighbour id
+// KIND 0: gt / lt counts (f64 registers, or log-quantised ones: cmp_kind 2); KIND 1: equal count (cmp_kind 1 and 3).  regs are the
+// registers compare() sees -- the compressed ones under --fastcmp, whatever the index was built over (cmp_core.cpp:362-449).
 template <int KIND>
 __global__ void lsh_refine_kernel(const double *regs, const double *cards, uint64_t n, const uint32_t *seg, const uint32_t *lsize,
                                   Nb *lst, const CmpConsts c, float mult) {
@@ -286,7 +288,7 @@ __device__ __forceinline__ Nb nb_unkey(uint64_t k) {
 }
 // NT threads (a warp or a CTA) sort B[0..P) ascending and trim; SYNC() separates the steps
 template <int NT, class Sync>
-__device__ __forceinline__ void trim_sorted_list(uint64_t *B, Nb *L, uint32_t nl, uint32_t topk, int is_dist, uint32_t *lsize_x, int t, uint32_t *scratch, Sync sync) {
+__device__ __forceinline__ void trim_sorted_list(uint64_t *B, Nb *L, uint32_t nl, uint32_t topk, int is_dist, uint32_t *lsize_x, int t, uint32_t *scratch, Sync sync, int keep_zeros = 0) {
     uint32_t P = 32; while (P < nl) P <<= 1;
     for (uint32_t i = t; i < P; i += NT) B[i] = i < nl ? nb_key(L[i]) : ~0ULL;
     sync();
@@ -307,9 +309,9 @@ __device__ __forceinline__ void trim_sorted_list(uint64_t *B, Nb *L, uint32_t nl
     if (t == 0) { scratch[0] = 0; scratch[1] = 0; }
     sync();
     uint32_t nz = 0;
-    if (!is_dist) { for (uint32_t i = t; i < nl; i += NT) nz += nb_unkey(B[i]).d != 0.f; if (nz) atomicAdd(scratch, nz); }
+    if (!is_dist && !keep_zeros) { for (uint32_t i = t; i < nl; i += NT) nz += nb_unkey(B[i]).d != 0.f; if (nz) atomicAdd(scratch, nz); }
     sync();
-    uint32_t keep = is_dist ? nl : scratch[0];
+    uint32_t keep = (is_dist || keep_zeros) ? nl : scratch[0];
     if (topk < keep) {                       // everything tied with the k-th entry stays (refine.cpp:39-42)
         const float bs = nb_unkey(B[topk - 1]).d;
         uint32_t le = 0;
@@ -322,7 +324,7 @@ __device__ __forceinline__ void trim_sorted_list(uint64_t *B, Nb *L, uint32_t nl
     if (t == 0) *lsize_x = keep;
 }
 __global__ void __launch_bounds__(LSH_TRIM_WARPS * 32)
-lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
+lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize, int keep_zeros = 0) {
     __shared__ uint64_t buf[LSH_TRIM_WARPS][LSH_TRIM_CAP];
     __shared__ uint32_t scr[LSH_TRIM_WARPS][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -330,20 +332,20 @@ lsh_trim_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb 
     if (x >= n) return;
     const uint32_t nl = lsize[x];
     if (nl > LSH_TRIM_CAP) return;           // lsh_trim_big_kernel
-    trim_sorted_list<32>(buf[wid], lst + seg[x], nl, topk, is_dist, lsize + x, lane, scr[wid], [] { __syncwarp(); });
+    trim_sorted_list<32>(buf[wid], lst + seg[x], nl, topk, is_dist, lsize + x, lane, scr[wid], [] { __syncwarp(); }, keep_zeros);
 }
 __global__ void __launch_bounds__(LSH_TRIM_BIG_THREADS)
-lsh_trim_big_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize) {
+lsh_trim_big_kernel(const uint32_t *seg, uint64_t n, uint32_t topk, int is_dist, Nb *lst, uint32_t *lsize, int keep_zeros = 0) {
     extern __shared__ uint64_t bigbuf[];
     __shared__ uint32_t scr[2];
     const uint64_t x = blockIdx.x;
     uint32_t nl = lsize[x];
     if (nl <= LSH_TRIM_CAP) return;
     Nb *L = lst + seg[x];
-    if (nl <= LSH_TRIM_BIG_CAP) { trim_sorted_list<LSH_TRIM_BIG_THREADS>(bigbuf, L, nl, topk, is_dist, lsize + x, (int)threadIdx.x, scr, [] { __syncthreads(); }); return; }
+    if (nl <= LSH_TRIM_BIG_CAP) { trim_sorted_list<LSH_TRIM_BIG_THREADS>(bigbuf, L, nl, topk, is_dist, lsize + x, (int)threadIdx.x, scr, [] { __syncthreads(); }, keep_zeros); return; }
     if (threadIdx.x == 0) {
         for (uint32_t i = 1; i < nl; ++i) { const Nb it = L[i]; uint32_t j = i; while (j && nb_less(it, L[j - 1])) { L[j] = L[j - 1]; --j; } L[j] = it; }
-        if (!is_dist) { uint32_t j = 0; while (j < nl && L[j].d != 0.f) ++j; nl = j; }
+        if (!is_dist && !keep_zeros) { uint32_t j = 0; while (j < nl && L[j].d != 0.f) ++j; nl = j; }
         if (topk < nl) { const float bs = L[topk - 1].d; uint32_t j = topk; while (j < nl && !(L[j].d > bs)) ++j; nl = j; }
         if (!is_dist) for (uint32_t j = 0; j < nl; ++j) L[j].d = -L[j].d;
         lsize[x] = nl;
@@ -364,6 +366,53 @@ __global__ void lsh_segments_kernel(const uint32_t *alist_sorted, uint64_t na, u
     uint64_t lo = 0, hi = na;
     while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (alist_sorted[mid] < (uint32_t)x) lo = mid + 1; else hi = mid; }
     seg[x] = (uint32_t)lo;
+}
+
+
+// ---- similarity-threshold graphs (--similarity-threshold x; src/index_build.cpp:26-31 with topk = -1, src/refine.cpp:43-68) ----------
+// Lists are not capped: every candidate of every query joins both endpoints' lists unless it is there already, and keeps the hit count
+// of its FIRST arrival.  Over the arrivals sorted by list (stable, so still in arrival order inside a list) that is: sort by
+// (id, arrival rank) inside the list, keep the head of every id run, sort the heads by (-hits, id) -- two segmented radix sorts.
+__global__ void lsh_thr_key1_kernel(const uint32_t *alist, const uint64_t *apay, const uint32_t *seg, uint32_t total, uint64_t *k1, uint32_t *cd) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= total) return;
+    const uint64_t pay = apay[a];
+    k1[a] = (pay & 0xFFFFFFFF00000000ULL) | (uint64_t)(a - seg[alist[a]]);
+    cd[a] = (uint32_t)pay;
+}
+__global__ void lsh_thr_key2_kernel(const uint32_t *alist, const uint64_t *k1s, const uint32_t *cds, const uint32_t *seg, uint32_t total, uint64_t *k2) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= total) return;
+    const uint32_t id = (uint32_t)(k1s[a] >> 32);
+    const bool head = a == seg[alist[a]] || (uint32_t)(k1s[a - 1] >> 32) != id;
+    k2[a] = head ? nb_key(Nb{__uint_as_float(cds[a]), id}) : ~0ULL;
+}
+// one thread per list: entries (heads first after the sort) from keys to Nb in place, list size
+__global__ void lsh_thr_lists_kernel(const uint32_t *seg, uint64_t n, uint64_t *k2s_and_lst, uint32_t *lsize) {
+    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const uint32_t s0 = seg[x], s1 = seg[x + 1];
+    uint32_t nl = 0;
+    Nb *L = reinterpret_cast<Nb *>(k2s_and_lst);
+    for (uint32_t a = s0; a < s1; ++a) { const uint64_t k = k2s_and_lst[a]; if (k == ~0ULL) break; L[a] = nb_unkey(k); ++nl; }
+    lsize[x] = nl;
+}
+// refine.cpp:45-68 over a list in (-hits, id) order whose d already holds mult * measure: keep what passes the threshold, give up after
+// 20 consecutive failures.  One thread per list; survivors compacted in place (the trim kernels sort them afterwards).
+__global__ void lsh_thr_filter_kernel(const uint32_t *seg, uint64_t n, double min_sim, int is_dist, Nb *lst, uint32_t *lsize) {
+    const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    Nb *L = lst + seg[x];
+    const uint32_t nl = lsize[x];
+    uint32_t o = 0, failures = 0;
+    for (uint32_t j = 0; j < nl; ++j) {
+        const Nb e = L[j];
+        const float v = is_dist ? e.d : -e.d;
+        const bool pass = is_dist ? (double)v < min_sim : (double)v >= min_sim;
+        if (pass) { L[o++] = e; failures = 0; }
+        else if (++failures == 20) break;
+    }
+    lsize[x] = o;
 }
 
 } // namespace d2g

@@ -15,7 +15,12 @@ namespace d2g {
 constexpr uint64_t PACK_PAD_WORDS = 256;   // 8192 bases: more than one tile halo
 __host__ __device__ __forceinline__ uint64_t packed_words(uint64_t n_bases) { return ((n_bases + 127) / 128) * 4 + PACK_PAD_WORDS; }
 
-struct PackedSeq { const uint64_t *codes; const uint32_t *mask; };
+struct PackedSeq {
+    const uint64_t *codes; const uint32_t *mask;
+    // set only for the element streams of stream_kernels.cuh (k > 32, -C with a window, protein): the records' elements in push order,
+    // item_cnt[r] of them from items[rec_off[r]] on (rec_off then counts item slots), STREAM_* flags
+    const uint64_t *items = nullptr; const uint32_t *item_cnt = nullptr; uint32_t item_flags = 0;
+};
 
 // 4 ASCII bytes (first base in the low byte) -> 8 bits of codes (first base in the two MSBs) and a
 // 4-bit invalid mask (first base in bit 3).

@@ -42,9 +42,11 @@ uint64_t d2g_launch_count(const d2g_ctx *ctx);
 /* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket the dominant
  * kernels on the ctx stream. d2g_get_timing synchronises, returns accumulated milliseconds and launch
  * count for one kernel class and resets that class. */
-enum { D2G_T_SKETCH_MAIN = 0, D2G_T_SKETCH_BOOT = 1, D2G_T_CMP = 2 /* the pair-comparison tile kernel */,
+enum { D2G_T_SKETCH_MAIN = 0, D2G_T_SKETCH_BOOT = 1 /* Full SetSketch boot / ids passes; the BagMinHash / ProbMinHash element kernels */, D2G_T_CMP = 2 /* the pair-comparison tile kernel */,
        D2G_T_CMP_PREP = 3 /* order-code construction: keys, per-register sort, ranks */,
-       D2G_T_PACK = 4 /* ASCII -> packed sequence (d2g_pack_dev) */, D2G_T_NCLASSES = 5 };
+       D2G_T_PACK = 4 /* ASCII -> packed sequence (d2g_pack_dev) */,
+       D2G_T_SORT = 5 /* counting sketches: radix sorts by (entity, value) + run-length encode; LSH: per-table key sort */,
+       D2G_T_LSH_REFINE = 6 /* exact compare of the surviving neighbour-list entries */, D2G_T_NCLASSES = 7 };
 int d2g_set_timing(d2g_ctx *ctx, int enabled);
 int d2g_get_timing(d2g_ctx *ctx, int kernel_class, double *ms_total, uint64_t *n_launches);
 
@@ -57,7 +59,8 @@ int d2g_get_timing(d2g_ctx *ctx, int kernel_class, double *ms_total, uint64_t *n
 enum { D2G_MODE_OPMH = 0, D2G_MODE_FULL_SETSKETCH = 1, D2G_MODE_BAGMINHASH = 2, D2G_MODE_PROBMINHASH = 3 };
 
 typedef struct {
-    int32_t k;                 /* 1..32 (2-bit exact encoding; k > 32 rolling hash is out of scope) */
+    int32_t k;                 /* 1..32: exact 2-bit encoding (bonsai encoder.h:241-272); 33..: 64-bit cyclic rolling hash
+                                  (RollingHasher, encoder.h:644-865; dispatch src/fastxsketch.cpp:399-421) */
     int32_t w;                 /* window; w <= k means unwindowed */
     int32_t canon;             /* reference default 1 (src/sketch_main.cpp:28) */
     int32_t mode;              /* D2G_MODE_* */
@@ -67,6 +70,9 @@ typedef struct {
                                   sketches: elements with count <= c are skipped (counter.h:123); Full SetSketch: D2G_EUNSUPPORTED */
     uint64_t countsketch_size; /* -c / --countsketch-size n, counting sketches only; 0 = exact counting.  n > 0: signed count sketch of n buckets,
                                   elements (bucket index, |count|) for |count| >= count_threshold (counter.h:68-77,131-137) */
+    int32_t alphabet;          /* 0 (or 4) = DNA; 20 / 14 / 6 / 8 = --protein(20) / --protein14 / --protein6 / --protein8 (src/options.h:328-331;
+                                  bonsai alphabet.h:107-120, rhtraits.h:52-62), never canonical, k up to 14 / 16 / 24 / 22, ASCII input only */
+    int32_t reserved;
 } d2g_sketch_params;
 
 /* Number of registers per entity the OPMH sketch keeps (S rounded up to even, src/oph.h:145). */
@@ -267,6 +273,17 @@ int d2g_lsh_topk(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, cons
  * queries and replay / refine / trim only their own range of lists; concatenated in rank order the pieces are the graph. */
 int d2g_lsh_topk_rows(d2g_ctx *ctx, const d2g_cmp_params *p, const double *regs, const double *cards,
                       int32_t topk, uint64_t row_begin, uint64_t row_end, uint64_t *indptr_out, uint32_t **idx_out, float **val_out);
+
+/* General form.  index_regs: the registers the LSH index is built over (NULL = regs); regs: the registers refinement compares -- with
+ * cmp_kind D2G_CMP_SS_COMPRESSED / D2G_CMP_BBIT the output of d2g_make_compressed, while index_regs are the f64 signatures (--topk with
+ * --fastcmp: the reference builds the index before it compresses, src/cmp_core.cpp:741-799, and refine_results goes through the compressed
+ * branch of compare(), :362-449).  topk > 0: top-k lists as above.  topk <= 0: similarity-threshold graph (--similarity-threshold x,
+ * NN_GRAPH_THRESHOLD; src/options.h:309, src/index_build.cpp:26-31,56-60, src/refine.cpp:43-68): candidate lists without a cap, first
+ * arrival keeps its hit count, lists walked in (-hits, id) order keeping measure >= min_similarity (distances: < min_similarity) until
+ * 20 consecutive failures, sorted best first.  Threshold graphs hold one uncapped list per query in shared memory: n <= 25601. */
+int d2g_lsh_graph(d2g_ctx *ctx, const d2g_cmp_params *p, const double *index_regs, const double *regs, const double *cards,
+                  int32_t topk, double min_similarity, uint64_t row_begin, uint64_t row_end,
+                  uint64_t *indptr_out, uint32_t **idx_out, float **val_out);
 
 void d2g_free(void *p);
 

@@ -280,7 +280,7 @@ def test_cmp_topk_csr_file(tmp_path):
 
 def test_unsupported_options_fail_loudly(golden_inputs):
     names, paths = golden_inputs
-    for argv in (["sketch", "-k31", "--full-setsketch", "-m", "2", paths[0]], ["sketch", "-k40", paths[0]], ["sketch", "--parse-by-seq", paths[0], paths[1]],
+    for argv in (["sketch", "-k31", "--full-setsketch", "-m", "2", paths[0]], ["sketch", "-k4000", paths[0]], ["sketch", "--protein", "-k15", "--parse-by-seq", paths[0]], ["sketch", "--parse-by-seq", paths[0], paths[1]],
                  ["contain", paths[0]]):
         r = subprocess.run([EXE] + argv, capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.strip()
@@ -309,3 +309,64 @@ def test_parse_by_seq_full_setsketch_on_a_read_set(tmp_path):
     _, exp = O.sketch_records_byseq([reads[i].tobytes() for i in sample], "fss", S, 31, -1)
     for j, i in enumerate(sample):
         assert np.array_equal(np.asarray(sigs[i]).view(np.uint64), exp[j].view(np.uint64)), i
+
+
+@pytest.mark.parametrize("case,argv", [("roll_opmh_k40_S128", ["-k40", "-S128"]), ("roll_opmh_k33_w50_S64_nocanon", ["-k33", "-w50", "-S64", "-C"]),
+                                       ("roll_fss_k45_S64_seed3", ["-k45", "-S64", "--seed", "3", "--full-setsketch"]),
+                                       ("opmh_k21_w30_S256_nocanon", ["-k21", "-w30", "-S256", "-C"])])
+def test_element_stream_modes_stacked_file(case, argv, golden_inputs, tmp_path):
+    """k > 32 (rolling hash) and -C with a window through the front-end: registers as the reference binary wrote them."""
+    if case.startswith("roll"):
+        files = ["g0.fa.gz", "g1.fa.gz", "dup.fa.gz", "adv.fa.gz", "reads.fq.gz"]
+        paths = [os.path.join(GOLD, "inputs", f) for f in files]
+    else:
+        paths = golden_inputs[1]
+    flist = tmp_path / "files.txt"; flist.write_text("\n".join(paths) + "\n")
+    out = str(tmp_path / "out.stk")
+    run(["sketch", "-p4", "-F", str(flist), "-o", out] + argv)
+    cards, sigs = read_stacked(out)
+    z = np.load(expected(case + ".npz"))
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64))
+    if "fss" in case:
+        np.testing.assert_allclose(cards, z["cards"], rtol=1e-12)
+    else:
+        assert np.array_equal(cards, z["cards"])
+
+
+@pytest.mark.parametrize("case,argv", [("prot20_opmh_k7_S64", ["--protein", "-k7", "-S64"]), ("prot8_opmh_k12_S64", ["--protein8", "-k12", "-S64"]),
+                                       ("prot14_opmh_k10_S64", ["--protein14", "-k10", "-S64"]), ("prot6_opmh_k20_S64", ["--protein6", "-k20", "-S64"]),
+                                       ("prot20_opmh_k5_w12_S32", ["--protein", "-k5", "-w12", "-S32"]), ("prot20_fss_k7_S64", ["--protein", "-k7", "-S64", "--full-setsketch"])])
+def test_protein_alphabets_stacked_files(case, argv, tmp_path):
+    """--protein* through the front-end: --parse-by-seq sketches per record; per FILE the reference binary leaves the registers empty
+    (reproduced).  Both stacked files as the reference binary wrote them."""
+    import gzip
+    fa = str(tmp_path / "prot.fa")
+    open(fa, "wb").write(gzip.open(os.path.join(GOLD, "inputs", "prot.fa.gz"), "rb").read())
+    z = np.load(expected(case + ".npz"))
+    out = str(tmp_path / "byseq.stk")
+    run(["sketch", "--parse-by-seq", "-p2", "-o", out] + argv + [fa])
+    cards, sigs = read_stacked(out)
+    assert np.array_equal(sigs.view(np.uint64), z["byseq_sigs"].view(np.uint64))
+    if "fss" in case:
+        np.testing.assert_allclose(cards, z["byseq_cards"], rtol=1e-12)
+    else:
+        assert np.array_equal(cards, z["byseq_cards"])
+    out = str(tmp_path / "file.stk")
+    run(["sketch", "-p2", "-o", out] + argv + [fa])
+    cards, sigs = read_stacked(out)
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64)) and np.array_equal(cards, z["cards"])
+
+
+def test_cmp_threshold_graph_and_topk_fastcmp_csr_files(tmp_path):
+    """`cmp --similarity-threshold x` and `cmp --topk 8 --fastcmp N [--bbit-sigs]`: the CSR files of the reference binary, byte for byte."""
+    from dashing2_b200 import synth
+    z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
+    stk = str(tmp_path / "sk600.ss")
+    synth.write_stacked(stk, z["regs"], z["cards"], names=[f"s{i}" for i in range(600)])
+    out = str(tmp_path / "g.csr")
+    for tag, argv in (("t0.5", ["--similarity-threshold", "0.5"]), ("t0.8", ["-T", "0.8"]), ("t0.3_containment", ["--similarity-threshold", "0.3", "--containment"])):
+        run(["cmp", "--presketched", "--binary-output", "--cmpout", out, stk] + argv)
+        assert open(out, "rb").read() == open(expected(f"nnthr_{tag}_sk600.csr"), "rb").read(), tag
+    for tag, argv in (("fd1", ["--fastcmp", "1"]), ("fd2_bbit", ["--fastcmp", "2", "--bbit-sigs"])):
+        run(["cmp", "--presketched", "--binary-output", "--topk", "8", "--cmpout", out, stk] + argv)
+        assert open(out, "rb").read() == open(expected(f"topk8_{tag}_sk600.csr"), "rb").read(), tag

@@ -53,9 +53,9 @@ def test_unsupported_modes_fail_loudly(golden_inputs):
     c = ctx()
     seq, off, ent = pack_files(paths[:1])
     with pytest.raises(D2GError):
-        c.sketch_batch(seq, off, ent, 1, c.params(mode="opmh", S=64, k=21, w=30, canon=False))
+        c.sketch_batch(seq, off, ent, 1, c.params(mode="fss", S=64, k=21, count_threshold=2))
     with pytest.raises(D2GError):
-        c.sketch_batch(seq, off, ent, 1, c.params(mode="opmh", S=64, k=40))
+        c.sketch_batch(seq, off, ent, 1, c.params(mode="opmh", S=64, k=4000))
 
 
 def test_save_kmers_ids(golden_inputs):
