@@ -41,15 +41,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genomes", type=int, default=10000, help="genomes per rank (config: 10000)")
-    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE config to run, 1-based: 2 = configs[1], the headline (default); 1, 3, 4, 5 = the other configs' own lines (bench_configs.py, one GPU)")
+    ap.add_argument("--genomes", type=int, default=None, help="genomes per rank (config 2: 10000; config 1: 64; config 3: 2000)")
+    ap.add_argument("--genome-len", type=int, default=None, help="bases per genome (config 2: 5 000 000; config 1: 1 000 000; config 3: 20 000 000)")
+    ap.add_argument("--n", type=int, default=None, help="config 4: reference sketches (queries = 2n; default 50 000); config 5: sketches (default 1 000 000)")
+    ap.add_argument("--batch-genomes", type=int, default=64, help="config 3: genomes per library call (a batch of the counting sketches is sorted at once)")
     ap.add_argument("--e2e-genomes", type=int, default=1024, help="genomes per host-buffer call in the e2e leg")
     ap.add_argument("--cpu-genomes", type=int, default=64, help="genomes in the CPU-baseline sketch sample (at least 4 per host thread are used)")
     ap.add_argument("--cpu-cmp-n", type=int, default=5200, help="sketches in the CPU-baseline cmp sample (13.5 M pairs: seconds of reference time)")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one genome's registers and 1000 sampled pairs")
     ap.add_argument("--no-cli", action="store_true", help="skip the CLI-vs-CLI leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config == 2:
+        args.genomes = args.genomes or 10000
+        args.genome_len = args.genome_len or 5_000_000
+    return args
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -310,6 +318,9 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.config != 2:
+        import bench_configs
+        return bench_configs.run(args, sys.modules[__name__])
     import torch
     import torch.distributed as dist
     from dashing2_b200 import capi

@@ -36,15 +36,18 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c
 
 # every symbol include/d2gpu.h declares
 EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stream", "d2g_sync", "d2g_launch_count",
-           "d2g_set_timing", "d2g_get_timing",
+           "d2g_set_timing", "d2g_get_timing", "d2g_stat",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_distinct_kmers", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_init_devices", "d2g_comm_unique_id", "d2g_comm_init_rank", "d2g_comm_init_all", "d2g_comm_size", "d2g_comm_rank", "d2g_comm_destroy",
            "d2g_cmp_rows_sharded_dev", "d2g_cmp_stream_sharded",
-           "d2g_kmer_counts", "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
+           "d2g_set_filterset", "d2g_set_filterset_values", "d2g_clear_filterset", "d2g_kmer_counts", "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_lsh_graph", "d2g_free"]
 
 _lib = None
+
+
+u64_t = C.c_uint64
 
 
 class D2GError(RuntimeError):
@@ -110,6 +113,10 @@ def load():
     L.d2g_lsh_topk_rows.restype = C.c_int
     L.d2g_lsh_graph.argtypes = [vp, C.POINTER(CmpParams), vp, vp, vp, i32, C.c_double, u64, u64, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
     L.d2g_lsh_graph.restype = C.c_int
+    L.d2g_stat.argtypes = [vp, C.c_int]; L.d2g_stat.restype = u64
+    L.d2g_set_filterset.argtypes = [vp, C.POINTER(SketchParams), vp, vp, u64, C.POINTER(u64)]; L.d2g_set_filterset.restype = C.c_int
+    L.d2g_set_filterset_values.argtypes = [vp, vp, u64]; L.d2g_set_filterset_values.restype = C.c_int
+    L.d2g_clear_filterset.argtypes = [vp]; L.d2g_clear_filterset.restype = C.c_int
     L.d2g_free.argtypes = [vp]; L.d2g_free.restype = None
     _lib = L
     return L
@@ -180,6 +187,9 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.L.d2g_launch_count(self.h))
+
+    def stat(self, which: int = 0) -> int:
+        return int(self.L.d2g_stat(self.h, which))
 
     def set_timing(self, on: bool):
         _check(self.L.d2g_set_timing(self.h, int(on)))
@@ -384,3 +394,17 @@ class Context:
         val = np.ctypeslib.as_array(pv, shape=(max(nnz, 1),))[:nnz].copy()
         self.L.d2g_free(pi); self.L.d2g_free(pv)
         return indptr, idx, val
+
+    def set_filterset(self, seq: np.ndarray, rec_off: np.ndarray, p: SketchParams) -> int:
+        """--filterset from the records of a FASTX file (d2g_set_filterset); returns the number of hashed values kept."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8); rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        n = u64_t(0)
+        _check(self.L.d2g_set_filterset(self.h, C.byref(p), _ptr(seq), _ptr(rec_off), len(rec_off) - 1, C.byref(n)))
+        return int(n.value)
+
+    def set_filterset_values(self, values: np.ndarray):
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        _check(self.L.d2g_set_filterset_values(self.h, _ptr(values), len(values)))
+
+    def clear_filterset(self):
+        _check(self.L.d2g_clear_filterset(self.h))

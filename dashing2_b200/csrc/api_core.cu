@@ -60,6 +60,7 @@ void d2g_destroy(d2g_ctx *c) {
 void *d2g_stream(d2g_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int d2g_sync(d2g_ctx *c) { if (!c) return fail(D2G_EINVAL, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return D2G_OK; }
 uint64_t d2g_launch_count(const d2g_ctx *c) { return c ? c->launches.load() : 0; }
+uint64_t d2g_stat(const d2g_ctx *c, int which) { return (c && which >= 0 && which < D2G_STAT_NSTATS) ? c->stats[which] : 0; }
 int d2g_set_timing(d2g_ctx *c, int on) { if (!c) return fail(D2G_EINVAL, "null ctx"); c->timing = on != 0; return D2G_OK; }
 int d2g_get_timing(d2g_ctx *c, int cls, double *ms_total, uint64_t *n) {
     if (!c || cls < 0 || cls >= D2G_T_NCLASSES) return fail(D2G_EINVAL, "bad timing class");

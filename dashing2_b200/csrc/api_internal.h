@@ -54,6 +54,7 @@ struct d2g_ctx {
     DevBuf seq, pcodes, pmask, recoff, recent, regs, sig, card, ids, aux, aux2, redo, ovfq;   // sketch scratch (pcodes / pmask: the packed batch)
     PinBuf stage[3]; cudaEvent_t stage_free[3] = {nullptr, nullptr, nullptr};        // pinned staging ring of the host packer
     DevBuf items, itemcnt, itemoff, segs, nseg, sflag, sexcl, svmask, slut, stmp;   // element streams (api_stream.cu)
+    DevBuf filter; uint64_t filter_n = 0;                                // --filterset: sorted hashed k-mers (d2g_set_filterset*)
     DevBuf lregs;                                                        // top-k over compressed registers: what refinement compares
     DevBuf wbuf, wtmp, lbuf;                                              // counting scratch (BagMinHash / ProbMinHash)
     DevBuf cregs, ccards, cout, clut, clut80, ctmp, cktmp;         // compare scratch
@@ -64,6 +65,7 @@ struct d2g_ctx {
     cudaEvent_t ev[2] = {nullptr, nullptr}, evd[2] = {nullptr, nullptr};
     uint32_t lut_S = 0; int lut_k = -1;
     bool timing = false;
+    uint64_t stats[D2G_STAT_NSTATS] = {0};
     void *nccl_comm = nullptr; int nranks = 1, rank = 0;        // communicator this context owns (api_comm.cu), null = single device
     bool c16_sharded = false;                                    // compare launcher: order codes come from gathered global ranks only (api_cmp.cu)
     DevBuf xsend, xrecv, xrank, xcards;                          // sharded compare: register exchange, local rank slice, gathered cardinalities

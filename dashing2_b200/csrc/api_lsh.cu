@@ -169,11 +169,19 @@ extern "C" int d2g_lsh_graph(d2g_ctx *c, const d2g_cmp_params *p, const double *
     if (int rc = make_consts(c, p, &k)) return rc;
     const int is_dist = !(p->measure == D2G_UNION_SIZE || p->measure == D2G_INTERSECTION || p->measure == D2G_SIMILARITY || p->measure == D2G_CONTAINMENT);
     const float mult = is_dist ? 1.f : -1.f;
+    c->stats[D2G_STAT_REFINED] = 0;
     if (h_total) {
+        {   // entries the replay kept = what refinement compares
+            std::vector<uint32_t> hs(n);
+            CU(cudaMemcpyAsync(hs.data(), lsz, n * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            uint64_t sum = 0; for (uint32_t v : hs) sum += v;
+            c->stats[D2G_STAT_REFINED] = sum;
+        }
         KernelTimer kt(c, D2G_T_LSH_REFINE);
         const uint64_t threads = (uint64_t)h_total * 32;
-        if (p->cmp_kind == D2G_CMP_GTLT || p->cmp_kind == D2G_CMP_SS_COMPRESSED)
-            d2g::lsh_refine_kernel<0><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cmp_regs_d, cards_d, n, seg, lsz, lst, k, mult);
+        const bool gtlt = p->cmp_kind == D2G_CMP_GTLT || p->cmp_kind == D2G_CMP_SS_COMPRESSED;
+        if (gtlt) d2g::lsh_refine_kernel<0><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cmp_regs_d, cards_d, n, seg, lsz, lst, k, mult);
         else d2g::lsh_refine_kernel<1><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cmp_regs_d, cards_d, n, seg, lsz, lst, k, mult);
         c->launches++;
     }

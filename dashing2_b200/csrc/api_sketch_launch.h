@@ -24,6 +24,7 @@ d2g::SketchArgs make_sketch_args(const d2g_ctx *c, const d2g_sketch_params *p, c
     a.n_rec = n_rec; a.k = p->k; a.w = p->w; a.canon = p->canon; a.xormask = p->xormask;
     a.pos_base = rg.pos_base; a.pos_end = rg.pos_end; a.ent_base = rg.ent_base; a.ent_state = nullptr; a.want_state = 0;
     a.keymask = 0xFFFFFFFFu;
+    a.filter = c->filter_n ? c->filter.p ? reinterpret_cast<const uint64_t *>(c->filter.p) : nullptr : nullptr; a.filter_n = c->filter_n;
     if (const char *ev = getenv("D2G_FAST_KEYMASK")) a.keymask = (uint32_t)strtoul(ev, nullptr, 0);   // test knob
     a.m = m; a.tile_stride = 1; a.score_slots = d2g::sketch_score_slots(p->k, p->w);
     a.span = pick_span(c, rg.pos_end - rg.pos_base, m);
@@ -37,8 +38,13 @@ int launch_stream(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer:
     const size_t smem = d2g::stream_smem_bytes<Consumer>(a.m, a.w > a.k);
     if (smem > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sketch with %u registers needs %zu bytes of shared memory per CTA (max 200 KiB)", a.m, smem);
     const uint64_t grid = (a.pos_end - a.pos_base + a.span - 1) / a.span;
-    CU(cudaFuncSetAttribute(d2g::stream_kernel<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    d2g::stream_kernel<Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+    if (a.filter_n) {
+        CU(cudaFuncSetAttribute(d2g::stream_kernel<Consumer, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        d2g::stream_kernel<Consumer, true><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+    } else {
+        CU(cudaFuncSetAttribute(d2g::stream_kernel<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        d2g::stream_kernel<Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+    }
     c->launches++;
     CU(cudaGetLastError());
     return D2G_OK;
@@ -51,7 +57,15 @@ int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer:
     const size_t smem = d2g::sketch_smem_bytes<Consumer>(a.m, a.score_slots);
     if (smem > 200 * 1024) return fail(D2G_EUNSUPPORTED, "sketch with %u registers needs %zu bytes of shared memory per CTA (max 200 KiB)", a.m, smem);
     const uint64_t grid = (a.pos_end - a.pos_base + a.span - 1) / a.span;
-    if (windowed) {
+    if (a.filter_n) {            // --filterset: the same kernels with the membership test in front of the consumer
+        if (windowed) {
+            CU(cudaFuncSetAttribute(d2g::sketch_kernel<true, Consumer, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            d2g::sketch_kernel<true, Consumer, true><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+        } else {
+            CU(cudaFuncSetAttribute(d2g::sketch_kernel<false, Consumer, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            d2g::sketch_kernel<false, Consumer, true><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
+        }
+    } else if (windowed) {
         CU(cudaFuncSetAttribute(d2g::sketch_kernel<true, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         d2g::sketch_kernel<true, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
     } else {
@@ -67,7 +81,7 @@ int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer:
 // on its redo list (normally none); everything else takes the exact kernel.  D2G_NO_FAST=1 forces the exact kernel (test knob).
 inline bool sketch_fast_eligible(const d2g::SketchArgs &a) {
     const int wsz = a.w - a.k + 1;
-    return a.w > a.k && a.canon && wsz >= 2 && wsz <= d2g::SF_MAX_WSZ && a.tile_stride == 1 && !getenv("D2G_NO_FAST");
+    return a.w > a.k && a.canon && wsz >= 2 && wsz <= d2g::SF_MAX_WSZ && a.tile_stride == 1 && !a.filter_n && !getenv("D2G_NO_FAST");
 }
 constexpr uint64_t kRedoCap = 1ULL << 16;
 

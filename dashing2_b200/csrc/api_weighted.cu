@@ -324,6 +324,112 @@ extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const 
     return D2G_OK;
 }
 
+// ---- --filterset (src/d2.cpp:45-98, src/filterset.h): the sorted set of hashed k-mers that later sketch calls skip -----------------
+namespace {
+__global__ void count_valid_kernel(const uint32_t *ent_sorted, uint64_t n, unsigned long long *n_valid) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (ent_sorted[i] != 0xFFFFFFFFu && (i + 1 == n || ent_sorted[i + 1] == 0xFFFFFFFFu)) *n_valid = i + 1;
+}
+}
+
+extern "C" int d2g_clear_filterset(d2g_ctx *c) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    c->filter_n = 0;
+    return D2G_OK;
+}
+
+extern "C" int d2g_set_filterset_values(d2g_ctx *c, const uint64_t *values, uint64_t n) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (n && !values) return fail(D2G_EINVAL, "null values");
+    CU(cudaSetDevice(c->device));
+    c->filter_n = 0;
+    if (!n) return D2G_OK;
+    std::vector<uint64_t> v(values, values + n);
+    std::sort(v.begin(), v.end());
+    if (int rc = c->filter.reserve(n * 8)) return rc;
+    CU(cudaMemcpyAsync(c->filter.p, v.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->filter_n = n;
+    return D2G_OK;
+}
+
+extern "C" int d2g_set_filterset(d2g_ctx *c, const d2g_sketch_params *p, const char *seq, const uint64_t *rec_off, uint64_t n_rec, uint64_t *n_out) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_sketch_params(p)) return rc;
+    if (n_rec && !rec_off) return fail(D2G_EINVAL, "null record table");
+    CU(cudaSetDevice(c->device));
+    c->filter_n = 0;                                                 // the set is built from unfiltered k-mers
+    if (n_out) *n_out = 0;
+    const uint64_t n_bases = n_rec ? rec_off[n_rec] : 0;
+    if (!n_bases) return D2G_OK;
+    if (!seq) return fail(D2G_EINVAL, "null sequence buffer");
+    if (rec_off[0] != 0) return fail(D2G_EINVAL, "rec_off[0] must be 0");
+    if (n_bases >= 0x7FFFFFF0ULL) return fail(D2G_EINVAL, "filter set: at most 2^31 bases per call (got %llu)", (unsigned long long)n_bases);
+    for (uint64_t r = 0; r < n_rec; ++r) if (rec_off[r + 1] < rec_off[r]) return fail(D2G_EINVAL, "rec_off not monotone at %llu", (unsigned long long)r);
+    std::vector<uint32_t> ent(n_rec, 0u);
+    if (int rc = c->seq.reserve(n_bases + 64)) return rc;
+    if (int rc = c->recoff.reserve((n_rec + 1) * 8)) return rc;
+    if (int rc = c->recent.reserve((n_rec + 1) * 4)) return rc;
+    const uint64_t nw = d2g::packed_words(n_bases);
+    if (int rc = c->pcodes.reserve(nw * 8)) return rc;
+    if (int rc = c->pmask.reserve(nw * 4)) return rc;
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->seq.p, seq, n_bases, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->recoff.p, rec_off, (n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->recent.p, ent.data(), n_rec * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = d2g_pack_dev(c, c->seq.as<char>(), n_bases, c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>())) return rc;
+    d2g::PackedSeq seq_d{c->pcodes.as<uint64_t>(), c->pmask.as<uint32_t>()};
+    const uint64_t *off_d = c->recoff.as<uint64_t>();
+    uint64_t n = n_bases;
+    StreamView sv;
+    if (is_stream_mode(p)) {
+        if (int rc = prepare_stream(c, p, seq_d, c->seq.as<uint8_t>(), off_d, n_rec, n_bases, &sv)) return rc;
+        p = &sv.p; seq_d = sv.seq; off_d = sv.rec_off_d; n = sv.total_len;
+    }
+    auto al = [](uint64_t b) { return (b + 255) / 256 * 256; };
+    uint64_t off = 0;
+    const uint64_t o_hvA = off; off += al(n * 8 + 8);
+    const uint64_t o_hvB = off; off += al(n * 8 + 8);
+    const uint64_t o_entA = off; off += al(n * 4 + 4);
+    const uint64_t o_entB = off; off += al(n * 4 + 4);
+    const uint64_t o_cnt = off; off += 256;
+    if (int rc = c->wbuf.reserve(off)) return rc;
+    unsigned char *B = c->wbuf.as<unsigned char>();
+    uint64_t *hvA = (uint64_t *)(B + o_hvA), *hvB = (uint64_t *)(B + o_hvB);
+    uint32_t *entA = (uint32_t *)(B + o_entA), *entB = (uint32_t *)(B + o_entB);
+    unsigned long long *cnt = (unsigned long long *)(B + o_cnt);
+    CU(cudaMemsetAsync(hvA, 0xFF, n * 8 + 8, st));
+    CU(cudaMemsetAsync(entA, 0xFF, n * 4 + 4, st));
+    CU(cudaMemsetAsync(cnt, 0, 8, st));
+    d2g::SketchArgs a = make_sketch_args(c, p, seq_d, off_d, c->recent.as<uint32_t>(), n_rec, n, 0, SketchRange{0, n, 0});
+    if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
+    d2g::EmitConsumer::Params ep{hvA, entA, a.span};
+    if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    const size_t tb = std::max(t1, t2);
+    if (int rc = c->wtmp.reserve(tb + 256)) return rc;
+    size_t tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
+    tbytes = tb;
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    count_valid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(entA, n, cnt);
+    c->launches += 2 * 9 + 1;
+    unsigned long long h_n = 0;
+    CU(cudaMemcpyAsync(&h_n, cnt, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_n) {
+        if (int rc = c->filter.reserve(h_n * 8)) return rc;
+        CU(cudaMemcpyAsync(c->filter.p, hvA, h_n * 8, cudaMemcpyDeviceToDevice, st));   // sorted by value; duplicates do not disturb the search
+        CU(cudaStreamSynchronize(st));
+    }
+    c->filter_n = h_n;
+    if (n_out) *n_out = h_n;
+    return D2G_OK;
+}
+
 // ---- --save-kmercounts (-N): multiplicity of the element that owns each register ---------------------------------------
 // The reference keeps, beside every register, how often the element that set it was seen (one-permutation sketch: counts_ bumped when
 // an update equals the register, src/oph.h:206-209; Full SetSketch: setsketch.h:405-406; BagMinHash / ProbMinHash: the element's weight)

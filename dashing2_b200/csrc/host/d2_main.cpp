@@ -79,6 +79,7 @@ struct Opts {
     int ngpus = 1;                         // --gpus N (not a reference option; also D2G_GPUS): files / output rows sharded over N devices
     double fastcmp = 8.; bool bbit = false;   // --fastcmp/--regsize N, --bbit-sigs (src/options.h:76,101)
     std::string ffile, qfile, outfile, cmpout, outprefix;
+    std::string filterset;                 // --filterset PATH[:x] (src/options.h:157,377; src/d2.cpp:45-98)
     std::vector<std::string> paths;
     size_t nq = 0;
     int verbosity = 0;
@@ -106,6 +107,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else if (a == "--cmpout" || a == "--distout" || a == "--cmp-outfile") o.cmpout = arg();
         else if (a == "--outprefix" || a == "--prefix") o.outprefix = arg();
         else if (a == "--seed") o.seed = std::stoull(arg());
+        else if (a == "--filterset") o.filterset = arg();
         else if (a == "--count-threshold" || a == "--threshold" || shortarg("-m")) o.count_threshold = (unsigned)std::max(0, std::atoi(arg().c_str()));
         else if (a == "--topk" || a == "--top-k" || shortarg("-K")) { o.topk = std::stoi(arg()); o.nn_threshold = false; }
         else if (a == "--similarity-threshold" || shortarg("-T")) { o.min_similarity = std::atof(arg().c_str()); o.nn_threshold = true; o.topk = -1; }
@@ -290,6 +292,28 @@ d2g_sketch_params sketch_params(const Opts &o) {
         key = (key + (key << 2)) + (key << 4); key ^= key >> 28; key += key << 31; p.xormask = key;
     }
     return p;
+}
+
+// ---- --filterset PATH[:x] (src/d2.cpp:45-98): hashed k-mers of PATH never reach a sketch ------------------------------------------
+// PATH alone (or PATH:K): a FASTX file hashed with the options of the run.  A colon followed by anything else selects the reference's raw
+// file of 64-bit hashed values -- which the reference binary cannot open (it passes the empty decompression command to fopen, d2.cpp:60-62,
+// and aborts); reproduced as an error here, with the reference's message.
+uint64_t g_filterset_n = 0;   // hashed values in the filter set, duplicates included (the reference's data_.size())
+void load_filterset(Gpus &gpus, const Opts &o) {
+    const size_t colon = o.filterset.find_last_of(':');
+    const std::string path = o.filterset.substr(0, colon);
+    if (colon != std::string::npos && colon + 1 < o.filterset.size() && (o.filterset[colon + 1] & 0xdf) != 'K')
+        die("Failed to open file " + path + " for reading");
+    if (o.mode == D2G_MODE_BAGMINHASH || o.mode == D2G_MODE_PROBMINHASH)
+        die("--filterset with --multiset / --prob: the reference binary crashes on this combination (v2.1.20); refusing instead");
+    FileRecords fr;
+    read_fastx(path, fr);
+    std::vector<uint64_t> off{0};
+    for (uint64_t e : fr.ends) off.push_back(e);
+    fr.seq.append(64, '\0');
+    d2g_sketch_params p = sketch_params(o);
+    for (size_t g = 0; g < gpus.size(); ++g) chk(d2g_set_filterset(gpus.get(g), &p, fr.seq.data(), off.data(), off.size() - 1, &g_filterset_n));
+    g_timer.mark("filter set");
 }
 
 // ---- sketch all inputs through libd2gpu in batches -----------------------------------------------
@@ -501,6 +525,7 @@ std::string options_string(const Opts &o, int mode) {   // Dashing2Options::to_s
     if (!o.outprefix.empty()) r += ";outprefix:" + o.outprefix;
     if (o.cssize) r += ";counting=countsketch" + std::to_string(o.cssize) + "\n";   // the newline is the reference's (src/d2.cpp:34)
     if (o.canon) r += ";canon";
+    if (!o.filterset.empty()) r += ";FilterSetSortedHashSet-size=" + std::to_string(g_filterset_n);   // FilterSet::to_string, src/filterset.h:78-83
     return r;
 }
 
@@ -701,6 +726,7 @@ int main(int argc, char **argv) {
         load_stacked(o.paths[0], sk);
         o.S = sk.S;
     } else {
+        if (!o.filterset.empty()) load_filterset(gpus, o);
         if (o.parse_by_seq) sketch_by_seq(gpus.lazy(0), o, sk); else sketch_inputs(gpus, o, sk);
         if (!o.outfile.empty()) {
             // the reference densifies signatures_ in place before the stacked file is closed when --cmpout is given

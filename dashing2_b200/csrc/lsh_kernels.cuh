@@ -236,7 +236,10 @@ lsh_replay_warp_kernel(const uint64_t *apay, const uint32_t *seg, uint64_t n, ui
     if (lane == 0) lsize[x] = nl;
 }
 
-// one warp per surviving edge: exact compare() of list owner x and neighbour id
+// one warp per surviving edge: exact compare() of list owner x and neighbour id.  Consecutive warps work on the same list, so the owner's
+// row comes out of L1 / L2 and HBM only streams the neighbours' rows: 210.8 M entries x 8 KiB in 309 ms at n = 10^6, S = 1024 = 5.6 TB/s,
+// 86 % of the measured HBM peak (profiles/r2k_lsh_refine_per_entry_n100000_S1024.ncu.txt).  A one-warp-per-list variant that kept the owner's
+// row in registers was measured and dropped: the same HBM bytes with fewer warps in flight, 348 ms.
 // KIND 0: gt / lt counts (f64 registers, or log-quantised ones: cmp_kind 2); KIND 1: equal count (cmp_kind 1 and 3).  regs are the
 // registers compare() sees -- the compressed ones under --fastcmp, whatever the index was built over (cmp_core.cpp:362-449).
 template <int KIND>

@@ -47,7 +47,16 @@ struct SketchArgs {
     uint32_t tile_stride;        // process only tiles whose global index % tile_stride == 0 (sampling); 1 = all
     uint32_t score_slots;        // shared-memory window-key slots (windowed mode): sk_pad(SK_TILE + w - k + 1) + 1
     uint32_t keymask;            // fast windowed kernel: bits of the 32-bit window key that take part (all; fewer only to provoke ties in tests)
+    const uint64_t *filter;      // --filterset (src/fastxsketch.cpp:385-388, src/filterset.h): sorted hashed k-mers that never reach the sketch
+    uint64_t filter_n;           // 0 = no filter set; kernels are instantiated with FILTER = true only when it is set
 };
+
+// FilterSet::in_set, the sorted-hash-set flavour (src/filterset.h:207-213)
+__device__ __forceinline__ bool sk_filtered(const SketchArgs &a, uint64_t hv) {
+    uint64_t lo = 0, hi = a.filter_n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (__ldg(a.filter + mid) < hv) lo = mid + 1; else hi = mid; }
+    return lo < a.filter_n && __ldg(a.filter + lo) == hv;
+}
 
 // ---- packed tile -> shared memory ----------------------------------------------------------------------
 // copies words [o/32, o/32 + nw) of the packed batch (o a multiple of 32 bases) into the tile.
@@ -153,7 +162,7 @@ constexpr int SK_SCAP = 512;   // staged window minima per tile (expected ~2/(ws
 
 // ---- one span of start positions [span_lo, span_hi) -----------------------------------------------------
 // All threads of the CTA; the consumer is initialised by the caller and is flushed at the end of the span.
-template <bool WINDOWED, class Consumer>
+template <bool WINDOWED, class Consumer, bool FILTER = false>
 __device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons, uint64_t *W, uint32_t *M, uint64_t *score, uint64_t *stage, int *scount,
                                             const uint64_t span_lo, const uint64_t span_hi) {
     const int k = a.k;
@@ -166,6 +175,7 @@ __device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons,
     const uint64_t kmask = k < 32 ? ((1ULL << (2 * k)) - 1) : ~0ULL;
     const bool canon = a.canon != 0;
     const int lane = threadIdx.x & 31;
+    auto feed = [&](uint64_t hv) { if (FILTER && sk_filtered(a, hv)) return; cons.consume(hv); };
     __syncthreads();
 
     // Windowed mode stages the minimizers of a tile (as window keys) and hashes them densely at the start of the
@@ -176,7 +186,7 @@ __device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons,
         const int n = min(*scount, SK_SCAP);
         for (int i = threadIdx.x; i < n; i += SK_THREADS) {
             const uint64_t km = frev64_inv(stage[i]);
-            if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask));
+            if (km != ~0ULL) feed(wang64(km ^ a.xormask));
         }
     };
 
@@ -232,7 +242,7 @@ __device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons,
                     #pragma unroll
                     for (int j = 0; j < SK_PPT; ++j)
                         if (j < jn && !((bad >> j) & 1u))             // encoder.h:254 -- k-mers holding a non-ACGT base are skipped
-                            cons.consume(wang64(km[j] ^ a.xormask));  // maskfn, src/enums.h:136-140
+                            feed(wang64(km[j] ^ a.xormask));  // maskfn, src/enums.h:136-140
                 }
             } else {
                 // canonical windowed path: a k-mer holding an invalid base enters the window as k-mer 0
@@ -318,7 +328,7 @@ __device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons,
                 if (Consumer::kEveryWindow) {
                     #pragma unroll
                     for (int j = 0; j < SK_PPT; ++j)
-                        if (j < jn) { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
+                        if (j < jn) { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) feed(wang64(km ^ a.xormask)); }
                 } else {
                     uint32_t emask = 0;
                     #pragma unroll
@@ -346,7 +356,7 @@ __device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons,
                             for (int j = 0; j < SK_PPT; ++j)
                                 if ((emask >> j) & 1u) {
                                     if (slot < SK_SCAP) stage[slot] = mn[j];
-                                    else { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) cons.consume(wang64(km ^ a.xormask)); }
+                                    else { const uint64_t km = frev64_inv(mn[j]); if (km != ~0ULL) feed(wang64(km ^ a.xormask)); }
                                     ++slot;
                                 }
                         }
@@ -376,7 +386,7 @@ __device__ __forceinline__ SketchSmem sketch_smem_carve(unsigned char *smem_raw,
     return s;
 }
 
-template <bool WINDOWED, class Consumer>
+template <bool WINDOWED, class Consumer, bool FILTER = false>
 __global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
 sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -387,7 +397,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     const uint64_t span_lo = a.pos_base + (uint64_t)blockIdx.x * a.span;
     const uint64_t span_hi = min(span_lo + a.span, a.pos_end);
     if (span_lo >= span_hi) return;
-    sketch_span<WINDOWED>(a, cons, s.W, s.M, s.score, s.stage, s.scount, span_lo, span_hi);
+    sketch_span<WINDOWED, Consumer, FILTER>(a, cons, s.W, s.M, s.score, s.stage, s.scount, span_lo, span_hi);
 }
 
 // The exact kernel over a LIST of tiles: tile_list[i] is the first start position of a tile of SK_TILE positions that the fast

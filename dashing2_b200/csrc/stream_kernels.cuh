@@ -24,7 +24,7 @@ constexpr uint32_t STREAM_NOFLUSH_BIT = 0x80000000u;   // item_cnt[r]: the recor
 // ---- consume ----------------------------------------------------------------------------------------------------------------
 constexpr int ST_SCORE_SLOTS = SK_TILE + SK_MAX_W + 8;
 
-template <class Consumer>
+template <class Consumer, bool FILTER = false>
 __global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
 stream_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -40,6 +40,7 @@ stream_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (a.rec_off[mid + 1] > span_lo) hi = mid; else lo = mid + 1; }
     uint32_t cur_ent = 0xFFFFFFFFu;
     const uint64_t *items = a.seq.items;
+    auto feed = [&](uint64_t hv) { if (FILTER && sk_filtered(a, hv)) return; cons.consume(hv); };
     __syncthreads();
     for (uint64_t r = lo; r < a.n_rec; ++r) {
         const uint64_t rs = a.rec_off[r];
@@ -65,7 +66,7 @@ stream_kernel(const SketchArgs a, const typename Consumer::Params cp) {
             __syncthreads();
             cons.end_tile(cur_ent);
             if (!windowed) {
-                for (int j = threadIdx.x; j < nstart; j += SK_THREADS) cons.consume(wang64(items[t0 + j] ^ a.xormask));
+                for (int j = threadIdx.x; j < nstart; j += SK_THREADS) feed(wang64(items[t0 + j] ^ a.xormask));
                 continue;
             }
             const int wl = tail ? (int)cnt : wsz;
@@ -76,7 +77,7 @@ stream_kernel(const SketchArgs a, const typename Consumer::Params cp) {
                 uint64_t mn = score[j];
                 for (int q = 1; q < wl; ++q) mn = min(mn, score[j + q]);
                 const uint64_t el = frev64_inv(mn);
-                if (tail || !(a.seq.item_flags & STREAM_SKIP_ONES) || el != ~0ULL) cons.consume(wang64(el ^ a.xormask));
+                if (tail || !(a.seq.item_flags & STREAM_SKIP_ONES) || el != ~0ULL) feed(wang64(el ^ a.xormask));
             }
         }
     }

@@ -39,6 +39,10 @@ void *d2g_stream(d2g_ctx *ctx);
 int d2g_sync(d2g_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t d2g_launch_count(const d2g_ctx *ctx);
+/* Counters of the last call, for the roofline report.  which: D2G_STAT_REFINED = neighbour-list entries the last d2g_lsh_* call compared
+ * exactly (before trimming; each reads one neighbour row of S registers, plus the owner's row once per list). */
+enum { D2G_STAT_REFINED = 0, D2G_STAT_NSTATS = 1 };
+uint64_t d2g_stat(const d2g_ctx *ctx, int which);
 /* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket the dominant
  * kernels on the ctx stream. d2g_get_timing synchronises, returns accumulated milliseconds and launch
  * count for one kernel class and resets that class. */
@@ -108,6 +112,17 @@ int d2g_sketch_batch(d2g_ctx *ctx, const d2g_sketch_params *p,
 int d2g_distinct_kmers(d2g_ctx *ctx, const d2g_sketch_params *p,
                        const char *seq, const uint64_t *rec_off, const uint32_t *rec_entity,
                        uint64_t n_rec, uint32_t n_entities, uint64_t *distinct_out);
+
+/* --filterset PATH (src/d2.cpp:45-98, src/filterset.h FilterSet as a sorted hash set; the test in front of every sketch update,
+ * src/fastxsketch.cpp:385-388): hashed k-mers (minimizers when w > k) found in the set never reach the sketches of later d2g_sketch_* /
+ * d2g_distinct_kmers / d2g_kmer_counts calls on this ctx.  d2g_set_filterset builds the set on the device from the records of the filter
+ * file (host ASCII, same record table as d2g_sketch_batch with rec_off[0] == 0; k, w, canon, xormask, alphabet of p as for the sketch
+ * itself -- the reference hashes the filter file with the options of the run); *n_out (optional) = hashed values kept, duplicates
+ * included.  d2g_set_filterset_values takes hashed values directly (the reference's "PATH:x" raw 64-bit file).  The kernels with the
+ * membership test are separate instantiations: nothing changes for a ctx without a filter set. */
+int d2g_set_filterset(d2g_ctx *ctx, const d2g_sketch_params *p, const char *seq, const uint64_t *rec_off, uint64_t n_rec, uint64_t *n_out);
+int d2g_set_filterset_values(d2g_ctx *ctx, const uint64_t *values, uint64_t n);
+int d2g_clear_filterset(d2g_ctx *ctx);
 
 /* --save-kmercounts (-N): counts_out f32 [n_entities][S] = how often the element that owns each register occurs in the stream of hashed
  * k-mers (one per window when w > k) of its entity -- what the reference keeps beside the registers (src/oph.h:206-209 counts_,

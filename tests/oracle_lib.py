@@ -135,13 +135,15 @@ def hash_stream(seq: bytes, k: int, w: int = -1, canon: bool = True, seed: int =
 
 
 def sketch_file(path: str, mode: str, S: int, k: int, w: int = -1, canon: bool = True, seed: int = 0,
-                count_threshold: float = 0.0, cssize: int = 0, alphabet: int = 4):
+                count_threshold: float = 0.0, cssize: int = 0, alphabet: int = 4, filterset=None):
     """Oracle equivalent of one iteration of the per-file loop (src/fastxsketch.cpp:303-624).
 
     Returns dict(card=..., sig=f64[S], regs_u64=..., ids=...)."""
     L = lib()
     streams = [hash_stream(r, k, w, canon, seed, alphabet) for r in read_fastx(path)]
     hv = np.concatenate(streams) if streams else np.empty(0, dtype=np.uint64)
+    if filterset is not None:       # --filterset: `if(!fs_->in_set(x)) func(x)`, src/fastxsketch.cpp:385-388 (sorted hash set, src/filterset.h:207-213)
+        hv = hv[~np.isin(hv, filterset)]
     if mode == "opmh":
         m = L.d2o_opmh_m(S)
         regs = np.empty(m, dtype=np.uint64); counts = np.empty(m, dtype=np.float64)
@@ -307,3 +309,10 @@ def read_csr(path):
     ix = np.frombuffer(raw, np.uint32, nnz, 16 + 8 * (n + 1))
     dv = np.frombuffer(raw, np.float32, nnz, 16 + 8 * (n + 1) + 4 * nnz)
     return ip, ix, dv
+
+
+def filterset_from_fastx(path: str, k: int, w: int = -1, canon: bool = True, seed: int = 0) -> np.ndarray:
+    """Dashing2Options::filterset for a FASTX path (src/d2.cpp:78-96): every maskfn'd k-mer / minimizer of the file, hashed with the options
+    of the run; FilterSet::finalize sorts (src/filterset.cpp).  Duplicates stay (data_.size() counts them)."""
+    hv = [hash_stream(r, k, w, canon, seed) for r in read_fastx(path)]
+    return np.sort(np.concatenate(hv)) if hv else np.empty(0, dtype=np.uint64)

@@ -77,7 +77,7 @@ def test_front_end_fails_loudly_without_device(tmp_path):
     assert r.returncode != 0 and ("no CUDA device" in r.stderr or "CPU fallback" in r.stderr), r.stderr
     assert not out.exists()
     # option errors are reported before any device work
-    r = subprocess.run([exe, "sketch", "--similarity-threshold", "0.5", str(fa)], capture_output=True, text=True)
+    r = subprocess.run([exe, "sketch", "--entmin", str(fa)], capture_output=True, text=True)
     assert r.returncode != 0 and "not supported" in r.stderr
 
 

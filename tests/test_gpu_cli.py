@@ -370,3 +370,28 @@ def test_cmp_threshold_graph_and_topk_fastcmp_csr_files(tmp_path):
     for tag, argv in (("fd1", ["--fastcmp", "1"]), ("fd2_bbit", ["--fastcmp", "2", "--bbit-sigs"])):
         run(["cmp", "--presketched", "--binary-output", "--topk", "8", "--cmpout", out, stk] + argv)
         assert open(out, "rb").read() == open(expected(f"topk8_{tag}_sk600.csr"), "rb").read(), tag
+
+
+@pytest.mark.parametrize("case,argv", [("fs_opmh_k31_S128", ["-k31", "-S128"]), ("fs_opmh_k21_w30_S64", ["-k21", "-w30", "-S64"]),
+                                       ("fs_fss_k31_S64", ["-k31", "-S64", "--full-setsketch"]), ("fs_opmh_k40_S64", ["-k40", "-S64"])])
+def test_filterset_option(case, argv, tmp_path):
+    """`sketch --filterset dup.fa`: registers as the reference binary wrote them; the combinations the reference binary itself cannot run
+    (raw k-mer file, --multiset) are refused."""
+    import gzip
+    paths = []
+    for f in ["g0.fa", "g1.fa", "dup.fa", "adv.fa"]:
+        dst = str(tmp_path / f); open(dst, "wb").write(gzip.open(os.path.join(GOLD, "inputs", f + ".gz"), "rb").read()); paths.append(dst)
+    flist = tmp_path / "files.txt"; flist.write_text("\n".join(paths) + "\n")
+    out = str(tmp_path / "out.stk")
+    run(["sketch", "-p4", "-F", str(flist), "-o", out, "--filterset", paths[2]] + argv)
+    cards, sigs = read_stacked(out)
+    z = np.load(expected(case + ".npz"))
+    assert np.array_equal(sigs.view(np.uint64), z["sigs"].view(np.uint64))
+    if "fss" in case:
+        np.testing.assert_allclose(cards, z["cards"], rtol=1e-12)
+    else:
+        assert np.array_equal(cards, z["cards"])
+    if case == "fs_opmh_k31_S128":
+        for bad in (["--filterset", paths[2] + ":B"], ["--filterset", paths[2], "--multiset"]):
+            r = subprocess.run([EXE, "sketch", "-F", str(flist), "-o", out, "-k31"] + bad, capture_output=True, text=True)
+            assert r.returncode != 0 and r.stderr.strip()

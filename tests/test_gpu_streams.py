@@ -193,3 +193,42 @@ def test_stream_limits_fail_loudly():
         c.sketch_batch(seq, off, ent, 1, c.params(mode="opmh", S=64, k=7, alphabet=20, canon=True))        # protein is never canonical
     with pytest.raises(D2GError):
         c.sketch_batch(seq, off, ent, 1, c.params(mode="opmh", S=64, k=40, w=40 + 2000))                     # window beyond the tile halo
+
+
+FILTERSET = {
+    "fs_opmh_k31_S128": dict(mode="opmh", S=128, k=31),
+    "fs_opmh_k21_w30_S64": dict(mode="opmh", S=64, k=21, w=30),
+    "fs_fss_k31_S64": dict(mode="fss", S=64, k=31),
+    "fs_opmh_k40_S64": dict(mode="opmh", S=64, k=40),
+}
+
+
+@pytest.mark.parametrize("case", sorted(FILTERSET))
+def test_filterset_matches_reference_golden(case):
+    """--filterset dup.fa: the set is built on the device from the filter file's records, the sketch kernels (exact and element-stream
+    flavours; the 32-bit-key fast kernel steps aside) test membership in front of the consumer.  Registers of the reference binary."""
+    kw = FILTERSET[case]
+    z = np.load(expected(case + ".npz"))
+    c = ctx()
+    p = c.params(**kw)
+    fseq, foff, _ = pack_files([os.path.join(GOLD, "inputs", "dup.fa.gz")])
+    try:
+        nfs = c.set_filterset(fseq, foff, p)
+        assert nfs == len(O.filterset_from_fastx(os.path.join(GOLD, "inputs", "dup.fa.gz"), kw["k"], kw.get("w", -1)))
+        paths = [os.path.join(GOLD, "inputs", f) for f in ["g0.fa.gz", "g1.fa.gz", "dup.fa.gz", "adv.fa.gz"]]
+        seq, off, ent = pack_files(paths)
+        r = c.sketch_batch(seq, off, ent, len(paths), p)
+        assert np.array_equal(u64(r["sig"]), u64(z["sigs"]))
+        if kw["mode"] == "opmh":
+            assert np.array_equal(r["card"], z["cards"])
+        else:
+            np.testing.assert_allclose(r["card"], z["cards"], rtol=1e-12)
+        # raw hashed values instead of a FASTX source: the same set, the same registers
+        c.set_filterset_values(O.filterset_from_fastx(os.path.join(GOLD, "inputs", "dup.fa.gz"), kw["k"], kw.get("w", -1))[::-1].copy())
+        r2 = c.sketch_batch(seq, off, ent, len(paths), p)
+        assert np.array_equal(u64(r2["sig"]), u64(z["sigs"]))
+    finally:
+        c.clear_filterset()
+    # and without the filter the registers differ (the filter did something)
+    r3 = c.sketch_batch(seq, off, ent, len(paths), p)
+    assert not np.array_equal(u64(r3["sig"]), u64(z["sigs"]))

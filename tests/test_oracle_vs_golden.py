@@ -372,3 +372,28 @@ def test_topk_with_fastcmp_matches_reference(tag, fd, bbit):
     ip, ix, dv = O.read_csr(expected(f"topk8_{tag}_sk600.csr"))
     gp, gi, gv = O.topk_compressed(z["regs"], creg, z["cards"], 8, fd, bbit, b, "similarity", k=32)
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
+
+
+FILTERSET = {
+    "fs_opmh_k31_S128": dict(mode="opmh", S=128, k=31),
+    "fs_opmh_k21_w30_S64": dict(mode="opmh", S=64, k=21, w=30),
+    "fs_fss_k31_S64": dict(mode="fss", S=64, k=31),
+    "fs_opmh_k40_S64": dict(mode="opmh", S=64, k=40),
+}
+
+
+@pytest.mark.parametrize("case", sorted(FILTERSET))
+def test_filterset_matches_reference(case):
+    """--filterset dup.fa (src/d2.cpp:45-98, src/fastxsketch.cpp:385-388): k-mers of the filter file never reach the sketch.  The reference
+    binary crashes with --multiset and cannot open its raw k-mer file flavour (tests/golden/make_golden_filterset.py), so set sketches with
+    a FASTX filter are what is pinned."""
+    kw = FILTERSET[case]
+    z = np.load(expected(case + ".npz"))
+    fs = O.filterset_from_fastx(os.path.join(GOLD, "inputs", "dup.fa.gz"), kw["k"], kw.get("w", -1))
+    for i, f in enumerate(["g0.fa.gz", "g1.fa.gz", "dup.fa.gz", "adv.fa.gz"]):
+        o = O.sketch_file(os.path.join(GOLD, "inputs", f), filterset=fs, **kw)
+        assert np.array_equal(o["sig"].view(np.uint64), z["sigs"][i].view(np.uint64)), (case, f)
+        if kw["mode"] == "opmh":
+            assert o["card"] == z["cards"][i], (case, f)
+        else:
+            np.testing.assert_allclose(o["card"], z["cards"][i], rtol=1e-12)
