@@ -35,12 +35,19 @@ extern "C" int d2g_lsh_graph(d2g_ctx *c, const d2g_cmp_params *p, const double *
     if (S < 2) return fail(D2G_EINVAL, "sketchsize must be >= 2 for the default two LSH table types");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    if (p->nlsh < 0 || p->nlsh > 3)
-        return fail(D2G_EUNSUPPORTED, "--nLSH %d: 1, 2 (the default) and 3 are implemented; 4 and up add six-register tables keyed by XXH3 (src/ssi.h:345-352)", p->nlsh);
-    if (p->nlsh == 3 && S < 4) return fail(D2G_EINVAL, "--nLSH 3 needs at least four registers");
-    const uint32_t n1 = p->nlsh == 1 ? 0 : S / 2;                      // two-register tables
-    const uint32_t n2 = p->nlsh == 3 ? (uint32_t)((uint64_t)S * 8 / 4) : 0;   // four-register tables: 8S / 4 (cmp_core.cpp:767)
-    const uint32_t ntab = S + n1 + n2;                                 // cmp_core.cpp:757-770
+    const int nlsh = p->nlsh ? p->nlsh : 2;
+    if (nlsh < 1 || nlsh > d2g::LSH_MAX_TYPES)
+        return fail(D2G_EUNSUPPORTED, "--nLSH %d: 1 .. %d are implemented (keys of more than 16 registers leave XXH3's 128-byte branch, src/ssi.h:345-352)", p->nlsh, d2g::LSH_MAX_TYPES);
+    d2g::LshGeom geom{};
+    geom.ntypes = (uint32_t)nlsh;
+    for (int ty = 0; ty < nlsh; ++ty) {                                // cmp_core.cpp:757-770
+        const uint32_t nper = d2g::lsh_nper((uint32_t)ty);
+        geom.cnt[ty] = nper <= 2 ? S / nper : (uint32_t)((uint64_t)S * 8 / nper);
+        geom.start[ty] = ty ? geom.start[ty - 1] + geom.cnt[ty - 1] : 0;
+        if (nper > S) return fail(D2G_EINVAL, "--nLSH %d needs at least %u registers", nlsh, nper);
+    }
+    for (int ty = nlsh - 1, acc = 0; ty >= 0; --ty) { geom.scan0[ty] = (uint32_t)acc; acc += (int)geom.cnt[ty]; }
+    const uint32_t ntab = geom.ntab = geom.start[nlsh - 1] + geom.cnt[nlsh - 1];
     uint64_t ntoquery = threshold ? n - 1 : (uint64_t)((float)topk * 3.5f);   // index_build.cpp:56-60: no cap on the candidates of a threshold graph
     ntoquery = std::min<uint64_t>(ntoquery, n - 1);
     CU(cudaFuncSetAttribute(d2g::lsh_trim_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d2g::LSH_TRIM_BIG_CAP * 8));
@@ -95,7 +102,7 @@ extern "C" int d2g_lsh_graph(d2g_ctx *c, const d2g_cmp_params *p, const double *
         CU(cudaMemcpyAsync(offs, ho.data(), (nt + 1) * 8, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
         const uint64_t items = (uint64_t)nt * n;
-        d2g::lsh_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(regs_d, n, S, t0, nt, kA + (uint64_t)t0 * n, iA + (uint64_t)t0 * n, n1);
+        d2g::lsh_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(regs_d, n, S, t0, nt, kA + (uint64_t)t0 * n, iA + (uint64_t)t0 * n, geom);
         size_t need = 0;
         cub::DeviceSegmentedRadixSort::SortPairs(nullptr, need, kA, kB, iA, iB, (int)items, (int)nt, offs, offs + 1, 0, 32, st);
         if (need > tb) { tb = need; if (int rc = c->wtmp.reserve(tb + 256)) return rc; }
@@ -113,7 +120,7 @@ extern "C" int d2g_lsh_graph(d2g_ctx *c, const d2g_cmp_params *p, const double *
         const size_t smem = (size_t)wpb * 2 * maxcand * 4;
         CU(cudaFuncSetAttribute(d2g::lsh_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(c, D2G_T_CMP);
-        d2g::lsh_query_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(regs_d, n, S, kB, iB, maxcand, cand, cnt, ncand, n1, n2);
+        d2g::lsh_query_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(regs_d, n, S, kB, iB, maxcand, cand, cnt, ncand, geom);
         c->launches++;
         CU(cudaGetLastError());
     }

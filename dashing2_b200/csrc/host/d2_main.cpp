@@ -704,11 +704,133 @@ void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
 
 } // namespace
 
+// ---- `contain` (src/contain_main.cpp:133-301) --------------------------------------------------------------------------------------
+// dashing2 contain [-b] [-p N] [-o OUT] [-F list] DB.kmer64 query...: for every query file, which of each reference's sampled k-mers
+// (the FILE.kmer64 of `sketch --save-kmers`) occur in the query's k-mer stream, and how often.  Coverage = sampled k-mers seen / S, mean depth =
+// sum of their multiplicities / sampled k-mers seen (uint32 division).  The stream side is d2g_kmer_counts: emit -> sort -> two binary searches
+// per sampled k-mer, with the whole database as the ids of one entity.
+int contain_main(int argc, char **argv) {
+    bool binary = false; std::string outpath; int nthreads = 1;
+    for (int i = 0; i < argc; ++i) {
+        std::string a = argv[i];
+        auto need = [&]() -> std::string { if (i + 1 >= argc) die("option " + a + " needs an argument"); return argv[++i]; };
+        if (a == "-b") binary = true;
+        else if (a == "-h" || a == "-?") { std::printf("dashing2-gpu contain <flags> database.kmer64 <input.fq> <input2.fq>...\n-b: binary output  -o: output path  -F: list of query files  -p: threads\n"); std::exit(0); }
+        else if (a.rfind("-p", 0) == 0) nthreads = std::max(1, std::atoi(a.size() > 2 ? a.c_str() + 2 : need().c_str()));
+        else if (a.rfind("-o", 0) == 0) outpath = a.size() > 2 ? a.substr(2) : need();
+        else if (a.rfind("-F", 0) == 0) { if (a.size() == 2) need(); }
+        else if (!a.empty() && a[0] == '-' && a.size() > 1) die("option " + a + " is not a `contain` option (-b -h -p -o -F)");
+    }
+    (void)nthreads;   // the stream side runs on the device
+    std::vector<std::string> pos;
+    {   // re-scan: the database is the first non-option argument, -F entries precede the remaining positionals (src/contain_main.cpp:151-153)
+        std::vector<std::string> listed, positional;
+        for (int i = 0; i < argc; ++i) {
+            std::string a = argv[i];
+            if (a == "-b") continue;
+            if (a == "-p" || a == "-o") { ++i; continue; }
+            if (a.rfind("-p", 0) == 0 || a.rfind("-o", 0) == 0) continue;
+            if (a == "-F") { std::ifstream ifs(argv[++i]); for (std::string l; std::getline(ifs, l);) listed.push_back(l); continue; }
+            if (a.rfind("-F", 0) == 0) { std::ifstream ifs(a.substr(2)); for (std::string l; std::getline(ifs, l);) listed.push_back(l); continue; }
+            positional.push_back(a);
+        }
+        if (positional.empty()) die("usage: dashing2-gpu contain <flags> database.kmer64 <input.fq> ...");
+        pos.push_back(positional[0]);
+        pos.insert(pos.end(), listed.begin(), listed.end());
+        pos.insert(pos.end(), positional.begin() + 1, positional.end());
+    }
+    const std::string dbpath = pos[0];
+    std::vector<std::string> queries(pos.begin() + 1, pos.end());
+    if (queries.empty()) die("contain: no query files (reading standard input is not supported by the GPU front-end)");
+    // database: u32 alphabet | canon << 8, u32 S, u32 k, u32 w, u64 seed, u64 ids[n][S]
+    std::FILE *fp = std::fopen(dbpath.c_str(), "rb");
+    if (!fp) die("Failed to open " + dbpath);
+    uint32_t hdr[4]; uint64_t seed = 0;
+    if (std::fread(hdr, 4, 4, fp) != 4 || std::fread(&seed, 8, 1, fp) != 1) die("short database file " + dbpath);
+    std::fseek(fp, 0, SEEK_END); const size_t fsz = (size_t)std::ftell(fp); std::fseek(fp, 24, SEEK_SET);
+    const uint32_t S = hdr[1];
+    if (!S || (fsz - 24) % S) die("Database corrupted (not a multiple of uint64_t size). Regenerate?");
+    std::vector<uint64_t> ids((fsz - 24) / 8);
+    if (std::fread(ids.data(), 8, ids.size(), fp) != ids.size()) die("truncated database file " + dbpath);
+    std::fclose(fp);
+    std::vector<std::string> names;
+    {
+        std::ifstream ifs(dbpath + ".names.txt");
+        if (ifs) for (std::string l; std::getline(ifs, l);) names.push_back(l);
+        else { const size_t v = (fsz - 24) / S; while (names.size() < v) names.push_back(std::to_string(v)); }   // the reference's fallback, as it is
+    }
+    const size_t nitems = names.size();
+    if (nitems != ids.size() / S) die("Database corrupted; wrong number of names.");
+    if ((hdr[0] & 0xFF) != 0) die("contain: only DNA databases are supported by the GPU front-end");
+    if ((uint64_t)nitems * S > 0xFFFFFFFFull) die("contain: database too large for one lookup (n * S must fit 32 bits)");
+    Opts o; o.k = (int)hdr[2]; o.w = (int)hdr[3]; o.canon = (hdr[0] & 0x100) != 0; o.seed = seed; o.S = (uint64_t)nitems * S; o.mode = D2G_MODE_OPMH;
+    d2g_sketch_params p = sketch_params(o);
+    setenv("CUDA_VISIBLE_DEVICES", "0", 0);
+    Gpus gpus; gpus.start(1);
+    const size_t nq = queries.size();
+    std::vector<float> cov(nitems * nq * 2, 0.f);
+    float *stats = cov.data() + nitems * nq;
+    std::vector<float> counts(ids.size());
+    std::vector<uint64_t> total(ids.size());
+    for (size_t q = 0; q < nq; ++q) {
+        FileRecords fr; read_fastx(queries[q], fr);
+        std::fill(total.begin(), total.end(), 0);
+        // batches of whole records below the per-call limit; multiplicities add up
+        const uint64_t max_bases = 2000000000ULL;
+        size_t r0 = 0; const size_t nr = fr.ends.size();
+        while (r0 < nr) {
+            const uint64_t b0 = r0 ? fr.ends[r0 - 1] : 0;
+            size_t r1 = r0 + 1;
+            while (r1 < nr && fr.ends[r1] - b0 <= max_bases) ++r1;
+            const uint64_t nb = fr.ends[r1 - 1] - b0;
+            std::vector<uint64_t> off{0}; std::vector<uint32_t> ent(r1 - r0, 0u);
+            for (size_t r = r0; r < r1; ++r) off.push_back(fr.ends[r] - b0);
+            const char *piece = fr.seq.data() + b0; const uint64_t plen = nb;
+            const uint64_t nw = d2g_packed_words(nb);
+            std::unique_ptr<uint64_t[]> codes(new uint64_t[nw]); std::unique_ptr<uint32_t[]> mask(new uint32_t[nw]);
+            uint64_t nzw = 0;
+            chk(d2g_pack_sequences(&piece, &plen, 1, codes.get(), mask.get(), &nzw));
+            chk(d2g_kmer_counts(gpus.get(0), &p, codes.get(), nzw ? mask.get() : nullptr, off.data(), ent.data(), ent.size(), 1, ids.data(), counts.data()));
+            for (size_t i = 0; i < ids.size(); ++i) total[i] += (uint64_t)counts[i];
+            r0 = r1;
+        }
+        const double ssiv = 1. / S;
+        for (size_t j = 0; j < nitems; ++j) {
+            uint32_t matches = 0, sums = 0;
+            for (uint32_t t = 0; t < S; ++t) { const uint64_t c = total[j * S + t]; if (c) { ++matches; sums += (uint32_t)c; } }
+            if (matches) { cov[nitems * q + j] = (float)(ssiv * matches); stats[nitems * q + j] = (float)(sums / matches); }
+        }
+    }
+    std::FILE *ofp = outpath.empty() ? stdout : xopen(outpath, "w");
+    if (binary) {
+        const uint64_t dims[2] = {nitems, nq};
+        xwrite(dims, 8, 2, ofp, outpath); xwrite(cov.data(), 4, cov.size(), ofp, outpath);
+    } else {
+        // the reference formats blocks of 16 (AVX-512) / 8 (AVX2) references with fmt::print WITHOUT the file argument, i.e. to standard output
+        // whatever -o says (src/contain_main.cpp:262-291); here every entry goes where -o points
+        std::fputs("#Dashing2 contain - a list of coverage %%s for the set of references, + mean coverage levels.\n"
+                   "#Each matrix entry consists of <coverage%%:mean depth of coverage>\n##References:", ofp);
+        for (size_t i = 0; i < nitems; ++i) std::fprintf(ofp, "\t%s", names[i].c_str());
+        std::fputc('\n', ofp);
+        for (size_t q = 0; q < nq; ++q) {
+            std::fputs(queries[q].c_str(), ofp);
+            for (size_t j = 0; j < nitems; ++j) std::fprintf(ofp, "\t%.6g%%:%.0f", (double)(100.f * cov[nitems * q + j]), (double)stats[nitems * q + j]);
+            std::fputc('\n', ofp);
+        }
+    }
+    if (ofp != stdout) xclose(ofp, outpath);
+    gpus.get(0);
+    if (std::fflush(nullptr) != 0) die(std::string("flush failed: ") + std::strerror(errno));
+    _exit(0);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) die("subcommands: sketch, cmp (alias dist). See `dashing2-gpu sketch -h`");
     const std::string sub = argv[1];
     const bool is_cmp = sub == "cmp" || sub == "dist";
-    if (!is_cmp && sub != "sketch") die("subcommand '" + sub + "' is outside the GPU hot paths (only sketch and cmp are provided)");
+    if (sub == "contain") return contain_main(argc - 2, argv + 2);
+    if (!is_cmp && sub != "sketch") die("subcommand '" + sub + "' is outside the GPU hot paths (sketch, cmp and contain are provided)");
     Opts o = parse(argc - 2, argv + 2, is_cmp);
     g_timer.verbosity = o.verbosity;
     // this front-end drives one GPU: hiding the others from the CUDA driver cuts its start-up (context creation touches

@@ -30,8 +30,52 @@ __device__ __forceinline__ uint64_t xxh64_4words(uint64_t w0, uint64_t w1, uint6
     h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
     return h;
 }
-// key of table (type, j), hash_index ssi.h:355-392: type 0 one register (hashmem64), type 1 two (hashmem128), type 2 four: hashmem256
-// while 4(j+1) <= S, else XXH64 seeded with (type << 32) | j over four registers picked by wyhash64(seed) -- 32 bits of it -- mod S
+// XXH64 over nw 64-bit words (nw >= 4)
+__device__ __forceinline__ uint64_t xxh64_words(const uint64_t *w, int nw, uint64_t seed) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL;
+    uint64_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+    int i = 0;
+    for (; i + 4 <= nw; i += 4) { v1 = xxh_round(v1, w[i]); v2 = xxh_round(v2, w[i + 1]); v3 = xxh_round(v3, w[i + 2]); v4 = xxh_round(v4, w[i + 3]); }
+    uint64_t h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
+    h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    h += (uint64_t)nw * 8;
+    for (; i < nw; ++i) { h ^= xxh_round(0, w[i]); h = ((h << 27) | (h >> 37)) * P1 + P4; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+// XXH3_64bits of W = 6 .. 16 whole words (48 .. 128 bytes), seed 0, default secret: XXH3_len_17to128_64b of xxHash 0.8.0 (the published
+// algorithm; the reference reaches it through hashmem's default branch, ssi.h:352).  Secret = first 128 bytes of XXH3_kSecret, little endian.
+__device__ __forceinline__ uint64_t xxh3_secret(int i) {
+    constexpr uint64_t sec[16] = {
+        0xbe4ba423396cfeb8ULL, 0x1cad21f72c81017cULL, 0xdb979083e96dd4deULL, 0x1f67b3b7a4a44072ULL, 0x78e5c0cc4ee679cbULL, 0x2172ffcc7dd05a82ULL,
+        0x8e2443f7744608b8ULL, 0x4c263a81e69035e0ULL, 0xcb00c391bb52283cULL, 0xa32e531b8b65d088ULL, 0x4ef90da297486471ULL, 0xd8acdea946ef1938ULL,
+        0x3f349ce33f76faa8ULL, 0x1d4f0bc7c7bbdcf9ULL, 0x3159b4cd4be0518aULL, 0x647378d9c97e9fc8ULL};
+    return sec[i];
+}
+__device__ __forceinline__ uint64_t xxh3_mix16(const uint64_t *in, int s) { return wymum(in[0] ^ xxh3_secret(s), in[1] ^ xxh3_secret(s + 1)); }
+__device__ __forceinline__ uint64_t xxh3_64_words(const uint64_t *in, int W) {
+    const uint64_t len = (uint64_t)W * 8;
+    uint64_t acc = len * 0x9E3779B185EBCA87ULL;
+    if (len > 32) {
+        if (len > 64) {
+            if (len > 96) { acc += xxh3_mix16(in + 6, 12); acc += xxh3_mix16(in + W - 8, 14); }
+            acc += xxh3_mix16(in + 4, 8); acc += xxh3_mix16(in + W - 6, 10);
+        }
+        acc += xxh3_mix16(in + 2, 4); acc += xxh3_mix16(in + W - 4, 6);
+    }
+    acc += xxh3_mix16(in, 0); acc += xxh3_mix16(in + W - 2, 2);
+    acc ^= acc >> 37; acc *= 0x165667919E3779F9ULL; acc ^= acc >> 32;
+    return acc;
+}
+// Table geometry of --nLSH L (src/cmp_core.cpp:757-770): type ty hashes 1, 2, 4, 6, 8, ... registers per key (2 * ty from type 3 on) and has
+// S / nper (types 0, 1) or 8S / nper tables; tables of type ty are [start[ty], start[ty] + cnt[ty]) in the sorted-table arrays; the query
+// scans the most specific type first (ssi.h:425).
+constexpr int LSH_MAX_TYPES = 9;      // XXH3's 17..128-byte branch covers up to 16 registers per key
+struct LshGeom { uint32_t ntypes, ntab; uint32_t cnt[LSH_MAX_TYPES], start[LSH_MAX_TYPES], scan0[LSH_MAX_TYPES]; };   // scan0[ty] = tables of more specific types
+__host__ __device__ __forceinline__ uint32_t lsh_nper(uint32_t ty) { return ty < 3 ? (1u << ty) : 2u * ty; }
+// key of table (type, j), hash_index ssi.h:355-392: one register hashmem64, two hashmem128, four hashmem256, more XXH3_64bits while
+// nper (j + 1) <= S; else XXH64 seeded with (type << 32) | j over registers picked by wyhash64(seed) -- 32 bits of it -- mod S, eight per whole
+// eight of nper and then nper more
 __device__ __forceinline__ uint32_t lsh_key(const double *sig, uint32_t S, uint32_t type, uint64_t j) {
     if (type == 0) return (uint32_t)wang64((uint64_t)__double_as_longlong(sig[j]));
     if (type == 1) {
@@ -39,35 +83,55 @@ __device__ __forceinline__ uint32_t lsh_key(const double *sig, uint32_t S, uint3
         const uint64_t v1 = wang64((uint64_t)__double_as_longlong(sig[2 * j + 1]) ^ v0);
         return (uint32_t)(v0 ^ v1);
     }
-    uint64_t v[4];
-    if ((j + 1) * 4 <= S) {
+    if (type == 2) {
+        uint64_t v[4];
+        if ((j + 1) * 4 <= S) {
+            #pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = (uint64_t)__double_as_longlong(sig[4 * j + r]);
+            return (uint32_t)wang64(cehash(v[0]) ^ (cehash(v[1]) * cehash(v[2]) - v[3]));
+        }
+        uint64_t seed = ((uint64_t)type << 32) | j;
+        const uint64_t seed0 = seed;
         #pragma unroll
-        for (int r = 0; r < 4; ++r) v[r] = (uint64_t)__double_as_longlong(sig[4 * j + r]);
-        return (uint32_t)wang64(cehash(v[0]) ^ (cehash(v[1]) * cehash(v[2]) - v[3]));
+        for (int r = 0; r < 4; ++r) { const uint32_t pick = (uint32_t)wyhash64(seed) % S; v[r] = (uint64_t)__double_as_longlong(sig[pick]); }
+        return (uint32_t)xxh64_4words(v[0], v[1], v[2], v[3], seed0);
+    }
+    const int nper = (int)lsh_nper(type);
+    uint64_t v[32];
+    if ((j + 1) * (uint64_t)nper <= S) {
+        for (int r = 0; r < nper; ++r) v[r] = (uint64_t)__double_as_longlong(sig[(uint64_t)nper * j + r]);
+        return (uint32_t)xxh3_64_words(v, nper);
     }
     uint64_t seed = ((uint64_t)type << 32) | j;
     const uint64_t seed0 = seed;
-    #pragma unroll
-    for (int r = 0; r < 4; ++r) { const uint32_t pick = (uint32_t)wyhash64(seed) % S; v[r] = (uint64_t)__double_as_longlong(sig[pick]); }
-    return (uint32_t)xxh64_4words(v[0], v[1], v[2], v[3], seed0);
+    const int nw = nper + 8 * (nper / 8);
+    for (int r = 0; r < nw; ++r) { const uint32_t pick = (uint32_t)wyhash64(seed) % S; v[r] = (uint64_t)__double_as_longlong(sig[pick]); }
+    return (uint32_t)xxh64_words(v, nw, seed0);
 }
-// table geometry: global table index t in [0, S) is type 0, [S, S + n1) type 1 (n1 = S/2 or 0), [S + n1, S + n1 + n2) type 2 (n2 = 2S or 0)
-__device__ __forceinline__ uint32_t lsh_key_of_table(const double *sig, uint32_t S, uint32_t n1, uint32_t t) {
-    return t < S ? lsh_key(sig, S, 0, t) : t < S + n1 ? lsh_key(sig, S, 1, t - S) : lsh_key(sig, S, 2, t - S - n1);
+__device__ __forceinline__ uint32_t lsh_key_of_table(const double *sig, uint32_t S, const LshGeom &g, uint32_t t) {
+    uint32_t ty = 0;
+    while (ty + 1 < g.ntypes && t >= g.start[ty + 1]) ++ty;
+    return lsh_key(sig, S, ty, t - g.start[ty]);
+}
+// position o of the scan order -> table index
+__device__ __forceinline__ uint32_t lsh_scan_table(const LshGeom &g, uint32_t o) {
+    int ty = (int)g.ntypes - 1;
+    while (ty > 0 && o >= g.scan0[ty] + g.cnt[ty]) --ty;
+    return g.start[ty] + (o - g.scan0[ty]);
 }
 
 // keys[t][i], ids[t][i] = i ; table t < S: type 0 register t ; t >= S: type 1 registers 2(t-S), 2(t-S)+1
-__global__ void lsh_keys_kernel(const double *regs, uint64_t n, uint32_t S, uint32_t t0, uint32_t nt, uint32_t *keys, uint32_t *ids, uint32_t n1) {
+__global__ void lsh_keys_kernel(const double *regs, uint64_t n, uint32_t S, uint32_t t0, uint32_t nt, uint32_t *keys, uint32_t *ids, const LshGeom g) {
     const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (e >= (uint64_t)nt * n) return;
     const uint32_t t = t0 + (uint32_t)(e / n); const uint64_t i = e % n;
-    keys[e] = lsh_key_of_table(regs + i * S, S, n1, t);
+    keys[e] = lsh_key_of_table(regs + i * S, S, g, t);
     ids[e] = (uint32_t)i;
 }
 
 // One warp per query.  skeys/sids: [ntab][n] sorted per table.  Outputs cand[q][maxcand], cnt[q][maxcand], ncand[q].
 __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, const uint32_t *skeys, const uint32_t *sids,
-                                 uint32_t maxcand, uint32_t *cand, uint32_t *cnt, uint32_t *ncand, uint32_t n1, uint32_t n2) {
+                                 uint32_t maxcand, uint32_t *cand, uint32_t *cnt, uint32_t *ncand, const LshGeom g) {
     extern __shared__ uint32_t sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const uint64_t q = (uint64_t)blockIdx.x * wpb + wib;
@@ -75,14 +139,14 @@ __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, con
     uint32_t *set_id = sm + (size_t)wib * 2 * maxcand, *set_ct = set_id + maxcand;
     const double *sig = regs + q * S;
     uint32_t nset = 0;
-    const uint32_t ntab = S + n1 + n2;    // n1 two-register tables (S / 2, or 0 under --nLSH 1), n2 four-register tables (2S under --nLSH 3)
-    // scan order, most specific first (ssi.h:425): type 2 tables j = 0..n2-1, type 1 tables j = 0..n1-1, then type 0 tables j = 0..S-1
+    const uint32_t ntab = g.ntab;
+    // scan order, most specific first (ssi.h:425): the tables of the last type, ..., type 1 tables j = 0..S/2-1, then type 0 tables j = 0..S-1
     for (uint32_t base = 0; base < ntab && nset < maxcand; base += 32) {
         const uint32_t o = base + lane;                  // position in scan order
         uint32_t lo = 0, hi = 0;
         if (o < ntab) {
-            const uint32_t t = o < n2 ? S + n1 + o : o < n2 + n1 ? S + (o - n2) : o - n2 - n1;
-            const uint32_t key = lsh_key_of_table(sig, S, n1, t);
+            const uint32_t t = lsh_scan_table(g, o);
+            const uint32_t key = lsh_key_of_table(sig, S, g, t);
             const uint32_t *K = skeys + (uint64_t)t * n;
             uint32_t a = 0, b = (uint32_t)n;
             while (a < b) { const uint32_t mid = (a + b) >> 1; if (K[mid] < key) a = mid + 1; else b = mid; }
@@ -94,7 +158,7 @@ __global__ void lsh_query_kernel(const double *regs, uint64_t n, uint32_t S, con
             const uint32_t blo = __shfl_sync(0xffffffffu, lo, l), bhi = __shfl_sync(0xffffffffu, hi, l);
             const uint32_t oo = base + l;
             if (oo >= ntab) break;
-            const uint32_t t = oo < n2 ? S + n1 + oo : oo < n2 + n1 ? S + (oo - n2) : oo - n2 - n1;
+            const uint32_t t = lsh_scan_table(g, oo);
             const uint32_t *I = sids + (uint64_t)t * n;
             for (uint32_t p = blo; p < bhi && nset < maxcand; p += 32) {
                 const bool have = p + lane < bhi;

@@ -977,9 +977,9 @@ static int cmp_kid(const void *a, const void *b) {
 }
 typedef struct { kid_t *tab; uint64_t n, S, ntab; int nlsh; } lshidx_t; /* table t occupies tab[t*n, (t+1)*n), sorted by (key,id) */
 /* --nLSH: table types 0 .. nlsh-1 with 1, 2, 4 registers per key and S, S/2, 8S/4 tables (src/cmp_core.cpp:757-770); 1 to 3 are
- * restated (type 3 keys of 6 registers go through XXH3, not restated) */
+ * restated directly; types 3 .. 8 hash 6, 8, ... 16 registers (nperhashes = 2 * type, 8S / nperhashes tables) through XXH3_64bits (below) */
 static int g_nlsh = 2;
-void d2o_set_nlsh(int nlsh) { g_nlsh = nlsh < 1 ? 2 : nlsh > 3 ? 3 : nlsh; }
+void d2o_set_nlsh(int nlsh) { g_nlsh = nlsh < 1 ? 2 : nlsh > 9 ? 9 : nlsh; }
 /* XXH64 (the published algorithm; the reference vendors xxHash) over len bytes, len a multiple of 8 */
 static inline uint64_t xxh_round(uint64_t acc, uint64_t in) { acc += in * 0xC2B2AE3D27D4EB4FULL; acc = (acc << 31) | (acc >> 33); return acc * 0x9E3779B185EBCA87ULL; }
 static inline uint64_t xxh_merge(uint64_t h, uint64_t v) { h ^= xxh_round(0, v); return h * 0x9E3779B185EBCA87ULL + 0x85EBCA77C2B2AE63ULL; }
@@ -999,25 +999,53 @@ static uint64_t xxh64_words(const uint64_t *w, uint64_t nwords, uint64_t seed) {
 }
 /* key of table (type, j): hash_index, ssi.h:355-392.  type 2 = four registers: hashmem256 (:313-318) while 4(j+1) <= S, else XXH64
  * seeded with ((type << 32) ^ (type >> 32)) | j over four registers picked by wyhash64(seed) -- truncated to 32 bits -- mod S. */
+/* XXH3_64bits of 17 .. 128 bytes, seed 0, default secret (xxHash 0.8.0, the published algorithm: XXH3_len_17to128_64b).  Inputs here are
+ * whole 64-bit words, an even number of them, so every 16-byte lane is two aligned words.  Secret: the first 128 bytes of XXH3_kSecret as
+ * little-endian words. */
+static const uint64_t XXH3_SECRET64[16] = {
+    0xbe4ba423396cfeb8ULL, 0x1cad21f72c81017cULL, 0xdb979083e96dd4deULL, 0x1f67b3b7a4a44072ULL, 0x78e5c0cc4ee679cbULL, 0x2172ffcc7dd05a82ULL,
+    0x8e2443f7744608b8ULL, 0x4c263a81e69035e0ULL, 0xcb00c391bb52283cULL, 0xa32e531b8b65d088ULL, 0x4ef90da297486471ULL, 0xd8acdea946ef1938ULL,
+    0x3f349ce33f76faa8ULL, 0x1d4f0bc7c7bbdcf9ULL, 0x3159b4cd4be0518aULL, 0x647378d9c97e9fc8ULL};
+static inline uint64_t xxh3_mix16(const uint64_t *in, const uint64_t *sec) { return wymum(in[0] ^ sec[0], in[1] ^ sec[1]); }   /* mul128_fold64 */
+static uint64_t xxh3_64_words(const uint64_t *in, uint64_t W) {       /* W = 4 .. 16 words (32 .. 128 bytes; 32 bytes never gets here) */
+    const uint64_t len = W * 8, *sec = XXH3_SECRET64;
+    uint64_t acc = len * 0x9E3779B185EBCA87ULL;
+    if (len > 32) {
+        if (len > 64) {
+            if (len > 96) { acc += xxh3_mix16(in + 6, sec + 12); acc += xxh3_mix16(in + W - 8, sec + 14); }
+            acc += xxh3_mix16(in + 4, sec + 8); acc += xxh3_mix16(in + W - 6, sec + 10);
+        }
+        acc += xxh3_mix16(in + 2, sec + 4); acc += xxh3_mix16(in + W - 4, sec + 6);
+    }
+    acc += xxh3_mix16(in, sec); acc += xxh3_mix16(in + W - 2, sec + 2);
+    acc ^= acc >> 37; acc *= 0x165667919E3779F9ULL; acc ^= acc >> 32;
+    return acc;
+}
+static uint64_t lsh_nper(int type) { return type < 3 ? (1ULL << type) : 2ULL * (uint64_t)type; }    /* registers per key, cmp_core.cpp:757-760 */
 static uint32_t lsh_key_any(const double *sig, uint64_t S, uint32_t type, uint64_t j) {
     if (type < 2) return d2o_lsh_key(sig, type, j);
-    uint64_t v[4];
-    if ((j + 1) * 4 <= S) {
-        memcpy(v, sig + 4 * j, 32);
-        return (uint32_t)d2o_wang64(d2o_cehash(v[0]) ^ (d2o_cehash(v[1]) * d2o_cehash(v[2]) - v[3]));
+    const uint64_t nreg = lsh_nper((int)type);
+    uint64_t v[32];
+    if ((j + 1) * nreg <= S) {
+        memcpy(v, sig + nreg * j, nreg * 8);
+        if (nreg == 4) return (uint32_t)d2o_wang64(d2o_cehash(v[0]) ^ (d2o_cehash(v[1]) * d2o_cehash(v[2]) - v[3]));   /* hashmem256 */
+        return (uint32_t)xxh3_64_words(v, nreg);                                                                    /* hashmem default: XXH3_64bits, ssi.h:352 */
     }
+    /* ssi.h:375-391: XXH64 seeded with ((type << 32) ^ (type >> 32)) | j over registers picked by wyhash64(seed) -- truncated to 32 bits -- mod S:
+     * eight picks per whole eight of nreg, then nreg more */
     uint64_t seed = (((uint64_t)type << 32) ^ ((uint64_t)type >> 32)) | j;
-    const uint64_t seed0 = seed;
-    for (int r = 0; r < 4; ++r) { const uint32_t pick = (uint32_t)d2o_wyhash64(&seed) % (uint32_t)S; memcpy(&v[r], sig + pick, 8); }
-    return (uint32_t)xxh64_words(v, 4, seed0);
+    const uint64_t seed0 = seed, nw = nreg + 8 * (nreg / 8);
+    for (uint64_t r = 0; r < nw; ++r) { const uint32_t pick = (uint32_t)d2o_wyhash64(&seed) % (uint32_t)S; memcpy(&v[r], sig + pick, 8); }
+    return (uint32_t)xxh64_words(v, nw, seed0);
 }
-static uint64_t lsh_nsubs(uint64_t S, int type) { return type == 0 ? S : type == 1 ? S / 2 : S * 8 / 4; }
+static uint64_t lsh_nsubs(uint64_t S, int type) { const uint64_t nh = lsh_nper(type); return nh <= 2 ? S / nh : S * 8 / nh; }
 static uint64_t lsh_tab0(uint64_t S, int type) { uint64_t t = 0; for (int q = 0; q < type; ++q) t += lsh_nsubs(S, q); return t; }
 static lshidx_t lsh_build(const double *regs, uint64_t n, uint64_t S) {
     lshidx_t ix; ix.n = n; ix.S = S; ix.nlsh = g_nlsh; ix.ntab = lsh_tab0(S, ix.nlsh);
     ix.tab = (kid_t *)malloc(sizeof(kid_t) * ix.ntab * n);
     for (uint64_t t = 0; t < ix.ntab; ++t) {
-        const uint32_t type = t < S ? 0 : t < S + S / 2 ? 1 : 2; const uint64_t j = t - lsh_tab0(S, (int)type);
+        uint32_t type = 0; while (t >= lsh_tab0(S, (int)type + 1)) ++type;
+        const uint64_t j = t - lsh_tab0(S, (int)type);
         kid_t *T = ix.tab + t * n;
         for (uint64_t i = 0; i < n; ++i) { T[i].key = lsh_key_any(regs + i * S, S, type, j); T[i].id = (uint32_t)i; }
         qsort(T, n, sizeof(kid_t), cmp_kid); /* bucket order = insertion order = ascending id under -p1 */

@@ -16,7 +16,7 @@ def main():
     z = np.load(os.path.join(INP, "sk600x64.npz"))
     stk = os.path.join(work, "sk600.ss")
     synth.write_stacked(stk, z["regs"], z["cards"], names=[f"s{i}" for i in range(600)])
-    for nlsh in (1, 3):
+    for nlsh in (1, 3, 4, 5):
         for K in (5, 32):
             mat = os.path.join(work, f"top{K}.csr")
             refbin.run_ref(["cmp", "--presketched", "-p1", "--binary-output", "--nLSH", str(nlsh), "--topk", str(K), "--cmpout", mat, stk], threads=1)

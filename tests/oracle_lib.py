@@ -316,3 +316,23 @@ def filterset_from_fastx(path: str, k: int, w: int = -1, canon: bool = True, see
     of the run; FilterSet::finalize sorts (src/filterset.cpp).  Duplicates stay (data_.size() counts them)."""
     hv = [hash_stream(r, k, w, canon, seed) for r in read_fastx(path)]
     return np.sort(np.concatenate(hv)) if hv else np.empty(0, dtype=np.uint64)
+
+
+def contain(db_ids: np.ndarray, query_records, k: int, w: int = -1, canon: bool = True, seed: int = 0):
+    """`dashing2 contain` for one query file (src/contain_main.cpp:33-58,218-243): every hashed k-mer of the query that is one of the
+    database's sampled k-mers is counted; per reference, coverage = (sampled k-mers seen) / S and mean depth = (sum of their multiplicities)
+    / (sampled k-mers seen) in uint32 integer division.  A k-mer a reference holds in two registers counts twice (kmer2ids keeps both)."""
+    db_ids = np.ascontiguousarray(db_ids, dtype=np.uint64)
+    nref, S = db_ids.shape
+    hv = [hash_stream(r, k, w, canon, seed) for r in query_records]
+    hv = np.concatenate(hv) if hv else np.empty(0, dtype=np.uint64)
+    u, c = np.unique(hv, return_counts=True)
+    pos = np.searchsorted(u, db_ids.reshape(-1))
+    pos_c = np.minimum(pos, max(len(u) - 1, 0))
+    hit = (u[pos_c] == db_ids.reshape(-1)) if len(u) else np.zeros(db_ids.size, dtype=bool)
+    mult = np.where(hit, c[pos_c] if len(u) else 0, 0).reshape(nref, S).astype(np.uint64)
+    matches = (mult > 0).sum(1).astype(np.uint32)
+    sums = (mult.sum(1) & 0xFFFFFFFF).astype(np.uint32)
+    cov = np.where(matches > 0, (1. / S) * matches, 0.).astype(np.float32)
+    depth = np.where(matches > 0, sums // np.maximum(matches, 1), 0).astype(np.float32)
+    return cov, depth

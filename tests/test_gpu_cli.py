@@ -273,7 +273,7 @@ def test_cmp_topk_csr_file(tmp_path):
         out = str(tmp_path / f"top{K}.csr")
         run(["cmp", "--presketched", "--binary-output", "--topk", str(K), "--cmpout", out, stk])
         assert open(out, "rb").read() == open(expected(f"topk{K}_sk600.csr"), "rb").read()
-        for nlsh in ("1", "3"):
+        for nlsh in ("1", "3", "4", "5"):
             run(["cmp", "--presketched", "--binary-output", "--nLSH", nlsh, "--topk", str(K), "--cmpout", out, stk])
             assert open(out, "rb").read() == open(expected(f"topk{K}_nlsh{nlsh}_sk600.csr"), "rb").read()
 
@@ -281,7 +281,7 @@ def test_cmp_topk_csr_file(tmp_path):
 def test_unsupported_options_fail_loudly(golden_inputs):
     names, paths = golden_inputs
     for argv in (["sketch", "-k31", "--full-setsketch", "-m", "2", paths[0]], ["sketch", "-k4000", paths[0]], ["sketch", "--protein", "-k15", "--parse-by-seq", paths[0]], ["sketch", "--parse-by-seq", paths[0], paths[1]],
-                 ["contain", paths[0]]):
+                 ["wsketch", paths[0]]):
         r = subprocess.run([EXE] + argv, capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.strip()
 
@@ -395,3 +395,31 @@ def test_filterset_option(case, argv, tmp_path):
         for bad in (["--filterset", paths[2] + ":B"], ["--filterset", paths[2], "--multiset"]):
             r = subprocess.run([EXE, "sketch", "-F", str(flist), "-o", out, "-k31"] + bad, capture_output=True, text=True)
             assert r.returncode != 0 and r.stderr.strip()
+
+
+@pytest.mark.parametrize("case,argv", [("contain_opmh_k31_S64", ["-k31", "-S64"]), ("contain_opmh_k21_w30_S32_seed5", ["-k21", "-w30", "-S32", "--seed", "5"]),
+                                       ("contain_fss_k31_S64", ["-k31", "-S64", "--full-setsketch"])])
+def test_contain_subcommand(case, argv, tmp_path):
+    """`sketch --save-kmers` then `contain`: the database file and the coverage / mean-depth matrices as the reference binary wrote them
+    (binary form; the text form for the case whose golden holds it)."""
+    import gzip
+    def fetch(f):
+        dst = str(tmp_path / f); open(dst, "wb").write(gzip.open(os.path.join(GOLD, "inputs", f + ".gz"), "rb").read()); return dst
+    refs = [fetch(f) for f in ["g0.fa", "g1.fa", "dup.fa", "adv.fa"]]
+    queries = [fetch(f) for f in ["g0.fa", "rep.fa", "reads.fq", "adv.fa", "dup.fa"]]
+    z = np.load(expected(case + ".npz"))
+    db = str(tmp_path / "db.stk")
+    run(["sketch", "-p1", "--save-kmers", "-o", db] + argv + refs)
+    assert np.array_equal(np.fromfile(db + ".kmer64", dtype=np.uint32, count=4), z["hdr"])
+    assert np.array_equal(np.fromfile(db + ".kmer64", dtype=np.uint64, offset=24).reshape(4, -1), z["ids"])
+    out = str(tmp_path / "c.bin")
+    qlist = tmp_path / "q.txt"; qlist.write_text("\n".join(queries[:2]) + "\n")
+    run(["contain", "-b", "-o", out, "-F", str(qlist), db + ".kmer64"] + queries[2:])
+    raw = open(out, "rb").read()
+    assert tuple(np.frombuffer(raw, np.uint64, 2)) == (4, 5)
+    mat = np.frombuffer(raw, np.float32, 40, 16).reshape(2, 5, 4)
+    assert np.array_equal(mat[0].view(np.uint32), z["coverage"].view(np.uint32)) and np.array_equal(mat[1], z["depth"])
+    if os.path.exists(expected(case + ".txt")):
+        outt = str(tmp_path / "c.txt")
+        run(["contain", "-o", outt, db + ".kmer64"] + queries)
+        assert open(outt).read().replace(str(tmp_path) + "/", "") == open(expected(case + ".txt")).read()

@@ -654,11 +654,12 @@ def test_topk_matches_reference_golden(K):
     assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32))
 
 
-@pytest.mark.parametrize("nlsh", [1, 3])
+@pytest.mark.parametrize("nlsh", [1, 3, 4, 5])
 @pytest.mark.parametrize("K", [5, 32])
 def test_topk_nlsh1_matches_reference_golden(K, nlsh):
     """--nLSH 1: the index holds only the S one-register tables; --nLSH 3: 2S four-register tables on top (hashmem256 / XXH64 keys),
-    scanned first (src/cmp_core.cpp:757-770, src/ssi.h:355-392)."""
+    scanned first; --nLSH 4 / 5: 8S/6 six-register and S eight-register tables keyed by XXH3_64bits, or XXH64 over 6 / 16 wyhash-picked
+    registers beyond the last whole group (src/cmp_core.cpp:757-770, src/ssi.h:345-392)."""
     z = np.load(os.path.join(GOLD, "inputs", "sk600x64.npz"))
     ip, ix, dv = O.read_csr(expected(f"topk{K}_nlsh{nlsh}_sk600.csr"))
     gp, gi, gv = ctx().lsh_topk(z["regs"], z["cards"], K, "similarity", k=32, nlsh=nlsh)
@@ -669,12 +670,12 @@ def test_topk_nlsh1_matches_oracle_seeded_and_nlsh3_fails():
     from dashing2_b200 import synth
     from dashing2_b200.capi import D2GError
     regs, cards = synth.synthetic_sketches(2500, 128, seed=77, n_families=40)
-    for nlsh in (1, 3):
+    for nlsh in (1, 3, 4, 6, 9):
         ip, ix, dv = O.topk(regs, cards, 10, "similarity", k=31, nlsh=nlsh)
         gp, gi, gv = ctx().lsh_topk(regs, cards, 10, "similarity", k=31, nlsh=nlsh)
         assert np.array_equal(gp, ip) and np.array_equal(gi, ix) and np.array_equal(gv.view(np.uint32), dv.view(np.uint32)), nlsh
     with pytest.raises(D2GError):
-        ctx().lsh_topk(regs[:100], cards[:100], 5, nlsh=4)
+        ctx().lsh_topk(regs[:100], cards[:100], 5, nlsh=10)
 
 
 def test_topk_row_ranges_concatenate_to_the_graph():

@@ -267,7 +267,7 @@ def test_fss_save_kmers_ids_match_reference(case):
         assert np.array_equal(o["ids"], z["ids"][i]), (case, f)
 
 
-@pytest.mark.parametrize("nlsh", [1, 3])
+@pytest.mark.parametrize("nlsh", [1, 3, 4, 5])
 @pytest.mark.parametrize("K", [5, 32])
 def test_topk_nlsh1_matches_reference(K, nlsh):
     """--nLSH 1: only the S one-register tables are built and scanned; --nLSH 3: 2S four-register tables on top, scanned first, three
@@ -397,3 +397,21 @@ def test_filterset_matches_reference(case):
             assert o["card"] == z["cards"][i], (case, f)
         else:
             np.testing.assert_allclose(o["card"], z["cards"][i], rtol=1e-12)
+
+
+CONTAIN = {
+    "contain_opmh_k31_S64": dict(k=31),
+    "contain_opmh_k21_w30_S32_seed5": dict(k=21, w=30, seed=5),
+    "contain_fss_k31_S64": dict(k=31),
+}
+CONTAIN_QUERIES = ["g0.fa.gz", "rep.fa.gz", "reads.fq.gz", "adv.fa.gz", "dup.fa.gz"]
+
+
+@pytest.mark.parametrize("case", sorted(CONTAIN))
+def test_contain_matches_reference(case):
+    """`dashing2 contain` (src/contain_main.cpp:133-301): coverage and mean depth of a .kmer64 database's sampled k-mers in query streams."""
+    z = np.load(expected(case + ".npz"))
+    for qi, f in enumerate(CONTAIN_QUERIES):
+        cov, depth = O.contain(z["ids"], O.read_fastx(os.path.join(GOLD, "inputs", f)), **CONTAIN[case])
+        assert np.array_equal(cov.view(np.uint32), z["coverage"][qi].view(np.uint32)), (case, f)
+        assert np.array_equal(depth, z["depth"][qi]), (case, f)
