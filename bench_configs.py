@@ -196,7 +196,7 @@ def run(args, bench):
                 cmd = ["sketch", "-k", "31", "-S", "8192", "--multiset", "-p", str(threads), "-F", fl, "-o", os.path.join(work, "o.ss"), "--cache", "--outprefix", cdir]
                 w, busy = _ref_timed(refbin, cmd, threads, repeats=2, before=wipe)
                 cpu = {"value": ng * (Lg - K + 1) / w, "unit": "kmers/s", "cores": threads, "kind": "reference", "threads_busy": busy,
-                       "sample": f"dashing2 {' '.join(cmd[:7])} --cache ... over {ng} genomes x {Lg} bp (FASTA on tmpfs), whole process wall clock {w:.2f} s, median after one discarded run"}
+                       "sample": f"dashing2 sketch -k 31 -S 8192 --multiset -p {threads} --cache ... over {ng} genomes x {Lg} bp (FASTA on tmpfs), whole process wall clock {w:.2f} s, median after one discarded run"}
             elif refbin.ref_binary() is not None:
                 w, busy = _ref_timed(refbin, cmd, threads, repeats=3 if cfg == 1 else 2)
                 cpu = {"value": ng * (Lg - K + 1) / w, "unit": "kmers/s", "cores": threads, "kind": "reference", "threads_busy": busy,
