@@ -53,16 +53,6 @@ D2G_HD uint64_t frev64_inv(uint64_t s) {
     s ^= CE_XOR2; s = (s >> 31) | (s << 33); s *= imul;
     return s ^ CE_XOR1;
 }
-// High 32 bits of frev64(x) -- the window key of the fast windowed kernel.  The rotation by 31 moves bits 32..1 of the product into the high
-// word, and bit 32 of a product depends on the operands' low 33 bits only: with p = xlo * Mlo (one IMAD.WIDE), bit 32 of x * M is the parity
-// of hi(p), xlo * Mhi and xhi * Mlo; Mhi is even and Mlo odd, so it is (hi(p) ^ xhi) & 1.  Five instructions instead of a 64-bit multiply.
-__device__ __forceinline__ uint32_t frev64_hi(uint64_t x) {
-    static_assert(((CE_MUL >> 32) & 1ULL) == 0 && (CE_MUL & 1ULL) == 1, "parity shortcut needs an even high and an odd low multiplier word");
-    const uint32_t xlo = (uint32_t)x ^ (uint32_t)CE_XOR1, xhi = (uint32_t)(x >> 32) ^ (uint32_t)(CE_XOR1 >> 32);
-    const uint64_t p = (uint64_t)xlo * (uint32_t)CE_MUL;
-    const uint32_t t = (uint32_t)(p >> 32) ^ xhi;                    // bit 0 = bit 32 of the full product
-    return __funnelshift_r((uint32_t)p, t, 1) ^ (uint32_t)(CE_XOR2 >> 32);
-}
 // CEHasher -- hash.h:858
 D2G_HD uint64_t cehash(uint64_t x) { x ^= CE_XOR1; x *= CE_MUL; return x ^ CE_XOR2; }
 

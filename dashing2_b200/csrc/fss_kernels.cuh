@@ -54,7 +54,7 @@ struct FssBootConsumer {
         const uint32_t idx = fastmod32((uint32_t)wyhash64(st), p.fm);   // first draw of the permutation, fy.h:36-37
         if (rv > s[idx]) atomicMax(reinterpret_cast<unsigned long long *>(s + idx), (unsigned long long)rv);
     }
-    __device__ __forceinline__ void end_tile(uint32_t, bool = false) {}
+    __device__ __forceinline__ void end_tile(uint32_t) {}
     __device__ __forceinline__ void flush(uint32_t ent) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < p.m; i += SK_THREADS) {
@@ -375,9 +375,8 @@ struct FssMainConsumer {
             return;
         }
     }
-    // synced: the caller has just passed a barrier behind the last consume() and nothing has touched the queue since
-    __device__ __forceinline__ void end_tile(uint32_t ent, bool synced = false) {
-        if (!synced) __syncthreads();
+    __device__ __forceinline__ void end_tile(uint32_t ent) {
+        __syncthreads();
         if (*qn > drain_at) drain(ent, false);           // uniform: every thread reads the same counter after the barrier
     }
     __device__ __forceinline__ void flush(uint32_t ent) {
@@ -424,7 +423,7 @@ struct FssIdsConsumer {
             if (g < p.ovf_cap) { p.ovf[2 * g] = hv; p.ovf[2 * g + 1] = cur; }
         }
     }
-    __device__ __forceinline__ void end_tile(uint32_t, bool = false) {}
+    __device__ __forceinline__ void end_tile(uint32_t) {}
     __device__ __forceinline__ void flush(uint32_t) {}
 };
 static __global__ void fss_longwalk_ids_kernel(const uint64_t *ovf, const unsigned long long *ovf_count, uint64_t ovf_cap, uint32_t m,

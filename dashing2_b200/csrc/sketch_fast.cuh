@@ -225,7 +225,7 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
                 const uint32_t bad = kmers8(W, M, boff + j0, k, kmask, true, km);
                 uint32_t kh[8];
                 #pragma unroll
-                for (int j = 0; j < SK_PPT; ++j) kh[j] = frev64_hi(((bad >> j) & 1u) ? 0ULL : km[j]) & a.keymask;
+                for (int j = 0; j < SK_PPT; ++j) kh[j] = (uint32_t)(frev64(((bad >> j) & 1u) ? 0ULL : km[j]) >> 32) & a.keymask;
                 uint32_t *dst = keys + sf_pad(SF_OFF + j0);                   // SF_OFF + j0 is a multiple of 8: two aligned groups of four
                 if (jn == SK_PPT) {
                     *reinterpret_cast<uint4 *>(dst) = make_uint4(kh[0], kh[1], kh[2], kh[3]);
@@ -238,7 +238,7 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
             if (first) {
                 // the wsz-1 keys before the first window's last key; the slot before them is never a window member: largest key
                 for (int i = tid; i < wsz - 1; i += SK_THREADS)
-                    keys[sf_pad(SF_OFF - (wsz - 1) + i)] = frev64_hi(tile_canonical_or_zero(W, M, boff - (wsz - 1) + i, k)) & a.keymask;
+                    keys[sf_pad(SF_OFF - (wsz - 1) + i)] = (uint32_t)(frev64(tile_canonical_or_zero(W, M, boff - (wsz - 1) + i, k)) >> 32) & a.keymask;
                 if (tid == 0) keys[sf_pad(SF_OFF - wsz)] = 0xFFFFFFFFu;
             } else {
                 // carry the last wsz keys of the previous (full) tile
@@ -246,7 +246,7 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
                 for (int i = tid; i < wsz; i += SK_THREADS) keys[sf_pad(SF_OFF - wsz + i)] = pk[sf_pad(SF_OFF + SF_TILE - wsz + i)];
             }
             __syncthreads();
-            cons.end_tile(cur_ent, true);
+            cons.end_tile(cur_ent);
             // ---- phase 2 ----
             if (tid == 0 && have_prev) settle_redo(par ^ 1u, prev_t0);
             uint32_t flags = 0;
@@ -332,7 +332,7 @@ sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const
             drain_events(reinterpret_cast<const uint64_t *>(smem_raw + prev_wb * SF_WBYTES),
                          reinterpret_cast<const uint32_t *>(smem_raw + prev_wb * SF_WBYTES + SF_NW * 8), KH + (par ^ 1u) * SF_KEYS, prev_boff, par ^ 1u);
             __syncthreads();
-            cons.end_tile(cur_ent, true);
+            cons.end_tile(cur_ent);
             if (tid == 0) settle_redo(par ^ 1u, prev_t0);
             __syncthreads();
         }

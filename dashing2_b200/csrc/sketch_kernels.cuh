@@ -101,7 +101,7 @@ struct OpmhConsumer {
         const uint32_t idx = fastmod32((uint32_t)id, p.fm);  // oph.h:184 (32-bit truncation, div.h:256-262)
         if (id < sreg[idx]) atomicMin(reinterpret_cast<unsigned long long *>(sreg + idx), (unsigned long long)id);
     }
-    __device__ __forceinline__ void end_tile(uint32_t, bool = false) {}
+    __device__ __forceinline__ void end_tile(uint32_t) {}
     // all threads; flushes the CTA-local registers of entity `ent` to HBM and clears them
     __device__ __forceinline__ void flush(uint32_t ent) {
         __syncthreads();

@@ -41,7 +41,7 @@ struct EmitConsumer {
         const unsigned int slot = atomicAdd(cur, 1u);
         p.out_hv[base + slot] = hv; p.out_ent[base + slot] = ent;
     }
-    __device__ __forceinline__ void end_tile(uint32_t, bool = false) {}
+    __device__ __forceinline__ void end_tile(uint32_t) {}
     __device__ __forceinline__ void flush(uint32_t) {}
 };
 
