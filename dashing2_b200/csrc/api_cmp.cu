@@ -230,7 +230,9 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
             // != only: injective codes suffice -> open-addressing table per register position, no sort
             const uint32_t TS = (uint32_t)std::max<uint64_t>(64, U + U / 2);
             const size_t smem = (size_t)TS * 8;
-            CU(cudaMemsetAsync(flag, 0, 4, st));
+            // the flag also carries "a register of the global ranking was NaN" for the jobs that derive their codes from it: while those
+            // ranks are live it is only ever raised, never cleared (a set flag costs a redundant f64 pass, a lost one wrong counts)
+            if (!gl.valid) CU(cudaMemsetAsync(flag, 0, 4, st));
             if (counts_gtlt(p->cmp_kind)) {
                 CU(cudaFuncSetAttribute(c16_hash_codes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 c16_hash_codes_kernel<0><<<(S + 3) / 4, 512, smem, st>>>(j, TS, c->c16codes.as<uint16_t>(), flag);
@@ -250,7 +252,7 @@ int run_cmp16_job(d2g_ctx *c, const d2g_cmp_params *p, const d2g::CmpArgs &base,
             c->launches++;
             CU(cudaGetLastError());
         } else if (!use_hash) {
-            CU(cudaMemsetAsync(flag, 0, 4, st));
+            if (!gl.valid) CU(cudaMemsetAsync(flag, 0, 4, st));
             if (int rc = c16_sort_rank(c, p, j, c->c16codes.as<uint16_t>(), nullptr, flag)) return rc;
         }
     }

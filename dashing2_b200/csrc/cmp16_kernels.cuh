@@ -234,7 +234,7 @@ c16_keys_kernel(const C16Job j, uint64_t *keysT, uint32_t *idxT, int *nan_flag) 
         if (u < U && s < j.s_count) {
             const double d = __ldg(j.regs + job_sketch(j, u) * j.S + j.s_begin + s);
             if (KIND == 0) { nan |= d != d; key = dkey(d == 0. ? 0. : d); }
-            else key = (uint64_t)__double_as_longlong(d);
+            else { nan |= d != d; key = (uint64_t)__double_as_longlong(d == 0. ? 0. : d); }   // IEEE ==: -0 folds onto +0, NaN never matches (f64 kernel)
         }
         t[ly + 8 * r][lx] = key;
     }
@@ -308,7 +308,7 @@ c16_hash_codes_kernel(const C16Job j, uint32_t TS, uint16_t *codes16, int *nan_f
             const double d = __ldg(j.regs + job_sketch(j, u) * j.S + s);
             uint64_t key;
             if (KIND == 0) { nan |= d != d; key = dkey(d == 0. ? 0. : d); }
-            else key = (uint64_t)__double_as_longlong(d);
+            else { nan |= d != d; key = (uint64_t)__double_as_longlong(d == 0. ? 0. : d); }   // IEEE ==: -0 folds onto +0, NaN never matches (f64 kernel)
             uint32_t slot;
             if (key == C16_HASH_EMPTY) slot = TS;                        // cannot live in the table: its own code
             else {

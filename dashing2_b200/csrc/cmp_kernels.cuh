@@ -182,7 +182,7 @@ cmp_tile_kernel(const CmpArgs a) {
                 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     if (KIND == 0) { gt[u][v] += av[u] > bv[v]; lt[u][v] += av[u] < bv[v]; }
-                    else gt[u][v] += __double_as_longlong(av[u]) != __double_as_longlong(bv[v]);
+                    else gt[u][v] += !(av[u] == bv[v]);   // count_eq<double> is the IEEE `==` (count_eq.h:40-45), also over k-mer ids viewed as doubles: NaN patterns never match, -0 == +0
                 }
         }
     }

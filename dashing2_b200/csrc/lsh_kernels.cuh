@@ -324,7 +324,7 @@ __global__ void lsh_refine_kernel(const double *regs, const double *cards, uint6
     #pragma unroll 8
     for (uint32_t r = lane; r < c.S; r += 32) {            // 8 independent 256-byte row segments in flight per warp
         const double a = __ldg(A + r), b = __ldg(B + r);
-        if (KIND == 0) { g += a > b; l += a < b; } else g += __double_as_longlong(a) != __double_as_longlong(b);
+        if (KIND == 0) { g += a > b; l += a < b; } else g += !(a == b);
     }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); l += __shfl_xor_sync(0xffffffffu, l, o); }

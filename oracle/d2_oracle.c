@@ -567,9 +567,12 @@ void d2o_count_gtlt(const double *a, const double *b, uint64_t n, uint64_t *gt, 
     *gt = g; *lt = l;
 }
 
+/* sketch::eq::count_eq<double> (count_eq.h:40-45): the IEEE `==` on RegT = double, also when the k-mer ids are viewed as doubles
+ * (cmp_core.cpp:501-506) -- NaN bit patterns never match, -0 equals +0 */
 uint64_t d2o_count_eq(const uint64_t *a, const uint64_t *b, uint64_t n) {
+    const double *x = (const double *)a, *y = (const double *)b;
     uint64_t e = 0;
-    for (uint64_t i = 0; i < n; ++i) e += a[i] == b[i];
+    for (uint64_t i = 0; i < n; ++i) e += x[i] == y[i];
     return e;
 }
 

@@ -953,3 +953,30 @@ def test_kmer_counts_match_reference_golden(mode, S, k, w):
     codes, mask, nz = capi.pack_sequences([x for rr in recs for x in rr])
     counts = c.kmer_counts(codes, mask, off, ent, len(recs), p, r["ids"])
     assert np.array_equal(counts, z["counts"]), (mode, S)
+
+
+@pytest.mark.parametrize("path", ["f64", "codes"])
+def test_equality_compare_is_ieee_on_id_registers(path, monkeypatch):
+    """The equality branch compares RegT = double with `==` even when the registers are k-mer ids viewed as doubles (cmp_core.cpp:501-506,
+    count_eq.h:40-45): ids whose bits are a NaN never match -- not even themselves -- and +0 / -0 match each other.  Both compare kernels
+    (and the top-k refinement) against the oracle on ids with such patterns planted in matching positions."""
+    monkeypatch.setenv("D2G_CMP_PATH", path)
+    rng = np.random.default_rng(9)
+    n, S = 300, 64
+    base = rng.integers(0, 2**63, size=(6, S), dtype=np.uint64)
+    ids = base[rng.integers(0, 6, n)].copy()
+    mut = rng.random((n, S)) < 0.3
+    ids[mut] = rng.integers(0, 2**63, size=int(mut.sum()), dtype=np.uint64)
+    ids[:, 3] = np.uint64(0x7FF8000000000001)                      # a NaN pattern everywhere in one column: never equal
+    ids[::2, 5] = np.uint64(0x8000000000000000); ids[1::2, 5] = 0   # -0 and +0: equal
+    ids[::3, 7] = np.uint64(0xFFF0000000000123)                     # NaN in a third of the rows
+    regs = ids.view(np.float64)
+    cards = rng.uniform(1e3, 1e4, n)
+    c = ctx()
+    for measure in ("similarity", "containment", "poisson_llr"):
+        exp = O.allpairs(regs, cards, "symmetric", measure, k=31, cmp_kind=1)
+        got = c.cmp_matrix(regs, cards, c.cmp_params(S, n, "symmetric", measure, k=31, cmp_kind=1))
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), measure
+    ep = O.topk(regs, cards, 7, "similarity", k=31, cmp_kind=1)
+    gp = c.lsh_topk(regs, cards, 7, "similarity", k=31, cmp_kind=1)
+    assert np.array_equal(gp[0], ep[0]) and np.array_equal(gp[1], ep[1]) and np.array_equal(gp[2].view(np.uint32), ep[2].view(np.uint32))
