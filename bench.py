@@ -343,6 +343,14 @@ def main():
         pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # one process per GPU: the ranks of a node share its cores, so each rank's host packer takes its share (the library sizes its
+    # host / device packing split from that; a single process keeps every core)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if local_world > 1 and "D2G_HOST_THREADS" not in os.environ:
+        os.environ["D2G_HOST_THREADS"] = str(max(1, len(affinity0) // local_world))
+    # the library's split between host packing and device packing of an ASCII chunk (api_sketch.cu: same formula, same inputs)
+    host_thr = int(os.environ.get("D2G_HOST_THREADS", "0")) or min(64, len(os.sched_getaffinity(0)))
+    hyb_f = float(os.environ["D2G_HYBRID_F"]) if "D2G_HYBRID_F" in os.environ else max(0.1, min(0.9, (1. / 50e9) / (1. / (5e9 * host_thr) + 0.75 / 50e9)))
     ctx = capi.Context(local)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     if world > 1:
@@ -584,8 +592,12 @@ def main():
                 "e2e": {"value": (n_e2e_cmp * (n_e2e_cmp - 1) // 2) / t_e2e_cmp, "unit": "pairs/s",
                         "h2d_bytes_per_step": n_e2e_cmp * S * 8 + n_e2e_cmp * 8, "d2h_bytes_per_step": e_pairs * 4,
                         "call": "d2g_cmp_rows (pinned host registers in, float32 rows copied into a pinned host buffer while later rows compute)", "n": n_e2e_cmp}},
-        "e2e": {"value": Ge * (Lg - K + 1) * world / t_e2e_sk, "unit": "kmers/s", "h2d_bytes_per_step": Ge * Lg // 4 + (Ge + 1) * 8 + Ge * 4,
-                "d2h_bytes_per_step": Ge * S * 8 + Ge * 8, "call": "d2g_sketch_batch (pinned host ASCII buffers in, host registers out; the library packs 128 Mi-base chunks to 2 bits per base on the host threads while earlier chunks upload and sketch)",
+        "e2e": {"value": Ge * (Lg - K + 1) * world / t_e2e_sk, "unit": "kmers/s",
+                "h2d_bytes_per_step": int(Ge * Lg * (hyb_f * 0.25 + (1. - hyb_f))) + (Ge + 1) * 8 + Ge * 4,
+                "d2h_bytes_per_step": Ge * S * 8 + Ge * 8,
+                "call": "d2g_sketch_batch (pinned host ASCII buffers in, host registers out; of every 384 Mi-base chunk the library packs the first %.0f %% to 2 bits "
+                        "per base on its %d host threads and sends the rest as ASCII by DMA to be packed on the device, while earlier chunks sketch)" % (100 * hyb_f, host_thr),
+                "host_threads": host_thr, "host_packed_fraction": hyb_f,
                 "batch": "%d genomes x %d bp per call" % (Ge, Lg)},
         "gpu_launches": launches, "clocks": clocks,
     }

@@ -441,12 +441,15 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
     // may block on the stream (Full SetSketch reads a counter back per chunk).
     std::atomic<size_t> uploaded{0}; std::atomic<int> prc{0};
     bool ascii_pinned = false, fixed_f = false;
-    double hybrid_f = 0.7;
+    // Share of a chunk the host threads pack; the rest goes up as ASCII by DMA and is packed on the device.  Balance of f / P (host) against
+    // ((1 - f) + f / 4) / B (link) for P = 5 G bases/s per packing thread (80.7 G bases/s measured on 16 threads) and B = 50 GB/s: 0.73 with
+    // 16 threads, 0.5 with 8, 0.31 with 4 -- processes that share a host (one per GPU) set D2G_HOST_THREADS to their share of the cores.
+    double hybrid_f = [] { const double P = 5e9 * d2g_host::host_threads(), B = 50e9; return std::max(0.1, std::min(0.9, (1. / B) / (1. / P + 0.75 / B))); }();
     if (hs.ascii && total_len) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, hs.ascii) == cudaSuccess) ascii_pinned = at.type == cudaMemoryTypeHost;
         else cudaGetLastError();
-        // The split is fixed (measured best on the 16-core B200 hosts: packing 75 G bases/s, link 53 GB/s); D2G_HYBRID_ADAPT=1 lets it follow
+        // The split is fixed per call (from the packing threads available, above); D2G_HYBRID_ADAPT=1 lets it follow
         // the packing rate measured per chunk (noisy: host threads and the DMA engine compete for the same memory bandwidth).
         fixed_f = !getenv("D2G_HYBRID_ADAPT");
         if (const char *ev = getenv("D2G_HYBRID_F")) { hybrid_f = std::max(0., std::min(1., atof(ev))); fixed_f = true; }   // 1 = pack everything on the host
