@@ -350,7 +350,7 @@ def main():
         os.environ["D2G_HOST_THREADS"] = str(max(1, len(affinity0) // local_world))
     # the library's split between host packing and device packing of an ASCII chunk (api_sketch.cu: same formula, same inputs)
     host_thr = int(os.environ.get("D2G_HOST_THREADS", "0")) or min(64, len(os.sched_getaffinity(0)))
-    hyb_f = float(os.environ["D2G_HYBRID_F"]) if "D2G_HYBRID_F" in os.environ else max(0.1, min(0.9, (1. / 50e9) / (1. / (5e9 * host_thr) + 0.75 / 50e9)))
+    hyb_f = float(os.environ["D2G_HYBRID_F"]) if "D2G_HYBRID_F" in os.environ else max(0.1, min(0.9, (1. / 50e9) / (1. / (4.6e9 * host_thr) + 0.75 / 50e9)))
     ctx = capi.Context(local)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     if world > 1:

@@ -442,9 +442,9 @@ int sketch_batch_host(d2g_ctx *c, const d2g_sketch_params *p, const HostSeq &hs,
     std::atomic<size_t> uploaded{0}; std::atomic<int> prc{0};
     bool ascii_pinned = false, fixed_f = false;
     // Share of a chunk the host threads pack; the rest goes up as ASCII by DMA and is packed on the device.  Balance of f / P (host) against
-    // ((1 - f) + f / 4) / B (link) for P = 5 G bases/s per packing thread (80.7 G bases/s measured on 16 threads) and B = 50 GB/s: 0.73 with
+    // ((1 - f) + f / 4) / B (link) for P = 4.6 G bases/s per packing thread (the measured best split on 16 threads is 0.7) and B = 50 GB/s: 0.70 with
     // 16 threads, 0.5 with 8, 0.31 with 4 -- processes that share a host (one per GPU) set D2G_HOST_THREADS to their share of the cores.
-    double hybrid_f = [] { const double P = 5e9 * d2g_host::host_threads(), B = 50e9; return std::max(0.1, std::min(0.9, (1. / B) / (1. / P + 0.75 / B))); }();
+    double hybrid_f = [] { const double P = 4.6e9 * d2g_host::host_threads(), B = 50e9; return std::max(0.1, std::min(0.9, (1. / B) / (1. / P + 0.75 / B))); }();
     if (hs.ascii && total_len) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, hs.ascii) == cudaSuccess) ascii_pinned = at.type == cudaMemoryTypeHost;

@@ -232,3 +232,27 @@ def test_filterset_matches_reference_golden(case):
     # and without the filter the registers differ (the filter did something)
     r3 = c.sketch_batch(seq, off, ent, len(paths), p)
     assert not np.array_equal(u64(r3["sig"]), u64(z["sigs"]))
+
+
+@pytest.mark.parametrize("kw", [dict(k=40), dict(k=40, w=48), dict(k=21, w=30, canon=False)], ids=lambda d: "_".join(f"{a}{b}" for a, b in d.items()))
+def test_stream_save_kmers_ids_and_counts(kw):
+    """--save-kmers ids and -N counts over an element stream: the ids are hashed values of the stream and each count is the multiplicity
+    of its id in it (one occurrence per window when w > k)."""
+    from dashing2_b200 import capi
+    rng = np.random.default_rng(21)
+    base = _adversarial_records(rng, kw["k"])
+    ents = [base + base[:2], base[2:8] + base[2:4]]
+    seq, off, ent = pack_batch(ents)
+    c = ctx()
+    p = c.params(mode="opmh", S=64, **kw)
+    r = c.sketch_batch(seq, off, ent, len(ents), p, want_ids=True)
+    codes, mask, nz = capi.pack_sequences([x for rr in ents for x in rr])
+    counts = c.kmer_counts(codes, mask, off, ent, len(ents), p, r["ids"])
+    for e, recs in enumerate(ents):
+        hv = np.concatenate([O.hash_stream(x, kw["k"], kw.get("w", -1), kw.get("canon", True)) for x in recs])
+        u, cnt = np.unique(hv, return_counts=True)
+        mult = dict(zip(u.tolist(), cnt.tolist()))
+        filled = r["regs_u64"][e][:64] != np.uint64(0xFFFFFFFFFFFFFFFF)
+        assert all(int(x) in mult for x in r["ids"][e][filled])
+        exp = np.array([mult.get(int(x), 0) for x in r["ids"][e]], dtype=np.float32)
+        assert np.array_equal(counts[e][filled], exp[filled]), (kw, e)
