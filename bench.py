@@ -348,6 +348,10 @@ def main():
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if local_world > 1 and "D2G_HOST_THREADS" not in os.environ:
         os.environ["D2G_HOST_THREADS"] = str(max(1, len(affinity0) // local_world))
+    # From three ranks up the host's DRAM, not the PCIe links, bounds the upload (r1: 183 G k-mers/s at N = 8 with plain DMA of ASCII; r2r: 155 with
+    # 29 % of every chunk packed by four threads per rank -- packing adds 0.75 B of host memory traffic per base): send ASCII, pack on the device
+    if local_world >= 3:
+        os.environ.setdefault("D2G_HYBRID_F", "0")
     # the library's split between host packing and device packing of an ASCII chunk (api_sketch.cu: same formula, same inputs)
     host_thr = int(os.environ.get("D2G_HOST_THREADS", "0")) or min(64, len(os.sched_getaffinity(0)))
     hyb_f = float(os.environ["D2G_HYBRID_F"]) if "D2G_HYBRID_F" in os.environ else max(0.1, min(0.9, (1. / 50e9) / (1. / (4.6e9 * host_thr) + 0.75 / 50e9)))

@@ -7,6 +7,9 @@
 #include <cub/device/device_scan.cuh>
 
 namespace {
+// bits of the entity key a stable LSD pass has to sort: entities are 0 .. n_ent-1 and empty slots carry 0xFFFFFFFF, whose low b bits (all ones)
+// exceed every entity as soon as 2^b > n_ent -- one 8-bit pass for up to 255 entities instead of four
+inline int ent_sort_bits(uint32_t n_ent) { int b = 1; while (b < 32 && (1ull << b) <= (uint64_t)n_ent) ++b; return b; }
 // BagMinHash / ProbMinHash (see weighted_kernels.cuh): emit -> sort -> run-length encode -> sketch -> verify loop.
 // sig_d [n_ent][S], card_d [n_ent].  Synchronises (needs the number of distinct elements and the redo count).
 __global__ void weighted_finalize_kernel(const uint64_t *keys, const unsigned long long *wsum, uint32_t n_ent, uint32_t m, double *sig, double *card) {
@@ -70,9 +73,10 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
         if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, windowed, D2G_T_SKETCH_MAIN)) return rc;
         if (cssize) { d2g::cs_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvA, entA, n, cssize); c->launches++; }
         // sort by (entity, value): LSD radix -- value first, then a stable pass over the entity
+        const int ebits = ent_sort_bits(n_ent);   // the entity pass sorts only the bits entities use (the 0xFFFFFFFF sentinel still sorts last)
         size_t t1 = 0, t2 = 0, t3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
-        cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, ebits, st);
         cub::DeviceScan::ExclusiveSum(nullptr, t3, flag, excl, n, st);
         const size_t tb = std::max(t1, std::max(t2, t3));
         if (int rc = c->wtmp.reserve(tb + 256)) return rc;
@@ -81,7 +85,7 @@ int launch_weighted(d2g_ctx *c, const d2g_sketch_params *p, const d2g::PackedSeq
         size_t tbytes = tb;
         CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
         tbytes = tb;
-        CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+        CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, ebits, st));
         c->launches += 2 * 9;
         const unsigned gb = (unsigned)((n + 255) / 256);
         d2g::rle_flag_kernel<<<gb, 256, 0, st>>>(hvA, entA, n, flag, id_shift);
@@ -215,15 +219,16 @@ int launch_opmh_mincount(d2g_ctx *c, const d2g_sketch_params *p, const d2g::Pack
     if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
     d2g::EmitConsumer::Params ep{hvA, entA, a.span};
     if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    const int ebits = ent_sort_bits(n_ent);   // the entity pass sorts only the bits entities use (the 0xFFFFFFFF sentinel still sorts last)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, ebits, st);
     const size_t tb = std::max(t1, t2);
     if (int rc = c->wtmp.reserve(tb + 256)) return rc;
     size_t tbytes = tb;
     CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
     tbytes = tb;
-    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, ebits, st));
     c->launches += 2 * 9;
     opmh_mincount_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvA, entA, n, p->count_threshold, regs_d, d2g::make_fastmod32(m), m);
     c->launches++;
@@ -306,15 +311,16 @@ extern "C" int d2g_distinct_kmers(d2g_ctx *c, const d2g_sketch_params *p, const 
     if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
     d2g::EmitConsumer::Params ep{hvA, entA, a.span};
     if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    const int ebits = ent_sort_bits(n_entities);   // the entity pass sorts only the bits entities use (the 0xFFFFFFFF sentinel still sorts last)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, ebits, st);
     const size_t tb = std::max(t1, t2);
     if (int rc = c->wtmp.reserve(tb + 256)) return rc;
     size_t tbytes = tb;
     CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
     tbytes = tb;
-    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, ebits, st));
     c->launches += 2 * 9;
     distinct_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hvA, entA, n, cnt);
     c->launches++;
@@ -406,15 +412,16 @@ extern "C" int d2g_set_filterset(d2g_ctx *c, const d2g_sketch_params *p, const c
     if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
     d2g::EmitConsumer::Params ep{hvA, entA, a.span};
     if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    const int ebits = ent_sort_bits(1u);   // the entity pass sorts only the bits entities use (the 0xFFFFFFFF sentinel still sorts last)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, ebits, st);
     const size_t tb = std::max(t1, t2);
     if (int rc = c->wtmp.reserve(tb + 256)) return rc;
     size_t tbytes = tb;
     CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
     tbytes = tb;
-    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, ebits, st));
     count_valid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(entA, n, cnt);
     c->launches += 2 * 9 + 1;
     unsigned long long h_n = 0;
@@ -509,15 +516,16 @@ extern "C" int d2g_kmer_counts(d2g_ctx *c, const d2g_sketch_params *p, const uin
     if (a.span >= 0xFFFFFFFFULL) return fail(D2G_EINVAL, "span too large");
     d2g::EmitConsumer::Params ep{hvA, entA, a.span};
     if (int rc = launch_sketch<d2g::EmitConsumer>(c, a, ep, p->w > p->k, D2G_T_SKETCH_MAIN)) return rc;
+    const int ebits = ent_sort_bits(n_entities);   // the entity pass sorts only the bits entities use (the 0xFFFFFFFF sentinel still sorts last)
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, hvA, hvB, entA, entB, n, 0, 64, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, entB, entA, hvB, hvA, n, 0, ebits, st);
     const size_t tb = std::max(t1, t2);
     if (int rc = c->wtmp.reserve(tb + 256)) return rc;
     size_t tbytes = tb;
     CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, hvA, hvB, entA, entB, n, 0, 64, st));
     tbytes = tb;
-    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, 32, st));
+    CU(cub::DeviceRadixSort::SortPairs(c->wtmp.p, tbytes, entB, entA, hvB, hvA, n, 0, ebits, st));
     c->launches += 2 * 9;
     kmer_count_lookup_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, st>>>(hvA, entA, n, c->ids.as<uint64_t>(), n_ids, S, c->sig.as<float>());
     c->launches++;
