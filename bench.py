@@ -464,8 +464,16 @@ def main():
     h_out = torch.empty(e_pairs, dtype=torch.float32).pin_memory()
     out_np = h_out.numpy()
 
+    # N > 1: every rank hands over only the registers of the sketches it made (its block of the host matrix); the exchange step runs inside
+    # the library (d2g_cmp_rows_sharded).  N = 1: the plain host entry point.
+    h_regs_np, h_cards_np = h_regs.numpy(), h_cards.numpy()
+    loc0, loc1 = rank * G, (rank + 1) * G
+
     def e2e_cmp():
-        ctx.cmp_rows(h_regs.numpy(), h_cards.numpy(), p_e2e_cmp, eb[rank], eb[rank + 1], out=out_np)
+        if world > 1:
+            ctx.cmp_rows_sharded(p_e2e_cmp, h_regs_np[loc0:loc1], h_cards_np[loc0:loc1], loc0, eb[rank], eb[rank + 1], out_np)
+        else:
+            ctx.cmp_rows(h_regs_np, h_cards_np, p_e2e_cmp, eb[rank], eb[rank + 1], out=out_np)
 
     e2e_sketch(); e2e_cmp()   # warm (allocations)
     barrier(); t0 = time.perf_counter()
@@ -594,8 +602,9 @@ def main():
                              "note": "code_prep = keys + per-register segmented radix sort + rank kernels that turn f64 registers into order codes; "
                                      "included in cmp.ms_per_step and cmp.value, not in launch_ms"},
                 "e2e": {"value": (n_e2e_cmp * (n_e2e_cmp - 1) // 2) / t_e2e_cmp, "unit": "pairs/s",
-                        "h2d_bytes_per_step": n_e2e_cmp * S * 8 + n_e2e_cmp * 8, "d2h_bytes_per_step": e_pairs * 4,
-                        "call": "d2g_cmp_rows (pinned host registers in, float32 rows copied into a pinned host buffer while later rows compute)", "n": n_e2e_cmp}},
+                        "h2d_bytes_per_step": (G if world > 1 else n_e2e_cmp) * (S * 8 + 8), "d2h_bytes_per_step": e_pairs * 4,
+                        "call": ("d2g_cmp_rows_sharded (this rank's block of pinned host registers in, exchange inside the library, its rows of the matrix copied into a pinned host buffer while later rows compute)"
+                                 if world > 1 else "d2g_cmp_rows (pinned host registers in, float32 rows copied into a pinned host buffer while later rows compute)"), "n": n_e2e_cmp}},
         "e2e": {"value": Ge * (Lg - K + 1) * world / t_e2e_sk, "unit": "kmers/s",
                 "h2d_bytes_per_step": int(Ge * Lg * (hyb_f * 0.25 + (1. - hyb_f))) + (Ge + 1) * 8 + Ge * 4,
                 "d2h_bytes_per_step": Ge * S * 8 + Ge * 8,

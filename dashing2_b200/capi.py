@@ -39,7 +39,7 @@ EXPORTS = ["d2g_init", "d2g_destroy", "d2g_last_error", "d2g_version", "d2g_stre
            "d2g_set_timing", "d2g_get_timing", "d2g_stat",
            "d2g_opmh_m", "d2g_count_kmers", "d2g_sketch_batch", "d2g_distinct_kmers", "d2g_opmh_finalize", "d2g_sketch_batch_dev",
            "d2g_init_devices", "d2g_comm_unique_id", "d2g_comm_init_rank", "d2g_comm_init_all", "d2g_comm_size", "d2g_comm_rank", "d2g_comm_destroy",
-           "d2g_cmp_rows_sharded_dev", "d2g_cmp_stream_sharded",
+           "d2g_cmp_rows_sharded_dev", "d2g_cmp_stream_sharded", "d2g_cmp_rows_sharded",
            "d2g_set_filterset", "d2g_set_filterset_values", "d2g_clear_filterset", "d2g_kmer_counts", "d2g_packed_words", "d2g_pack_sequences", "d2g_pack_dev", "d2g_sketch_batch_packed", "d2g_sketch_batch_packed_dev",
            "d2g_densify", "d2g_densify_dev", "d2g_make_compressed", "d2g_cmp_output_size", "d2g_cmp_rows_size", "d2g_cmp_matrix",
            "d2g_cmp_stream", "d2g_cmp_rows", "d2g_cmp_rows_dev", "d2g_cmp_counts", "d2g_lsh_topk", "d2g_lsh_topk_rows", "d2g_lsh_graph", "d2g_free"]
@@ -113,6 +113,7 @@ def load():
     L.d2g_lsh_topk_rows.restype = C.c_int
     L.d2g_lsh_graph.argtypes = [vp, C.POINTER(CmpParams), vp, vp, vp, i32, C.c_double, u64, u64, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_float))]
     L.d2g_lsh_graph.restype = C.c_int
+    L.d2g_cmp_rows_sharded.argtypes = [vp, C.POINTER(CmpParams), vp, vp, u64, u64, u64, u64, vp]; L.d2g_cmp_rows_sharded.restype = C.c_int
     L.d2g_stat.argtypes = [vp, C.c_int]; L.d2g_stat.restype = u64
     L.d2g_set_filterset.argtypes = [vp, C.POINTER(SketchParams), vp, vp, u64, C.POINTER(u64)]; L.d2g_set_filterset.restype = C.c_int
     L.d2g_set_filterset_values.argtypes = [vp, vp, u64]; L.d2g_set_filterset_values.restype = C.c_int
@@ -408,3 +409,8 @@ class Context:
 
     def clear_filterset(self):
         _check(self.L.d2g_clear_filterset(self.h))
+
+    def cmp_rows_sharded(self, p: CmpParams, local_regs: np.ndarray, local_cards: np.ndarray, local_begin: int, row_begin: int, row_end: int, out: np.ndarray):
+        """Collective: this rank's block of host registers in, rows [row_begin, row_end) of the whole matrix out (d2g_cmp_rows_sharded)."""
+        _check(self.L.d2g_cmp_rows_sharded(self.h, C.byref(p), _ptr(local_regs), _ptr(local_cards), local_begin, len(local_cards), row_begin, row_end, _ptr(out)))
+        return out

@@ -689,6 +689,17 @@ extern "C" int d2g_cmp_stream_sharded(d2g_ctx *c, const d2g_cmp_params *p, const
     return cmp_blocks(c, p, local_regs, local_cards, r0, r1, sink, user, nullptr, &sh);
 }
 
+// The same into a caller buffer (page-locked memory moves at full PCIe speed): rows [row_begin, row_end) packed from row_begin.  Collective.
+extern "C" int d2g_cmp_rows_sharded(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs, const double *local_cards,
+                                    uint64_t local_begin, uint64_t local_n, uint64_t r0, uint64_t r1, float *out) {
+    if (!c) return fail(D2G_EINVAL, "null ctx");
+    if (int rc = check_cmp_params(p)) return rc;
+    if (r0 > r1 || r1 > n_rows(p)) return fail(D2G_EINVAL, "bad row range");
+    if (r1 > r0 && !out) return fail(D2G_EINVAL, "null output");
+    const ShardArg sh{local_begin, local_n};
+    return cmp_blocks(c, p, local_regs, local_cards, r0, r1, nullptr, nullptr, out, &sh);
+}
+
 extern "C" int d2g_cmp_rows_sharded_dev(d2g_ctx *c, const d2g_cmp_params *p, const double *local_regs_d, const double *local_cards_d,
                                         uint64_t local_begin, uint64_t local_n, uint64_t r0, uint64_t r1, float *out_d) {
     if (!c) return fail(D2G_EINVAL, "null ctx");

@@ -39,8 +39,10 @@ namespace {
 // phase timing on stderr with -v
 struct PhaseTimer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0; int verbosity = 0;
+    std::vector<std::pair<std::string, double>> phases;      // for --gpu-stats
     void mark(const char *what) {
         const auto now = std::chrono::steady_clock::now();
+        phases.emplace_back(what, std::chrono::duration<double, std::milli>(now - last).count());
         if (verbosity > 0) std::fprintf(stderr, "[dashing2-gpu] %-28s %8.1f ms (total %8.1f ms)\n", what,
                                         std::chrono::duration<double, std::milli>(now - last).count(), std::chrono::duration<double, std::milli>(now - t0).count());
         last = now;
@@ -79,6 +81,7 @@ struct Opts {
     int ngpus = 1;                         // --gpus N (not a reference option; also D2G_GPUS): files / output rows sharded over N devices
     double fastcmp = 8.; bool bbit = false;   // --fastcmp/--regsize N, --bbit-sigs (src/options.h:76,101)
     std::string ffile, qfile, outfile, cmpout, outprefix;
+    std::string gpu_stats;                 // --gpu-stats FILE (not a reference option): host phases + per-class device kernel times as JSON
     std::string filterset;                 // --filterset PATH[:x] (src/options.h:157,377; src/d2.cpp:45-98)
     std::vector<std::string> paths;
     size_t nq = 0;
@@ -108,6 +111,7 @@ Opts parse(int argc, char **argv, bool is_cmp) {
         else if (a == "--outprefix" || a == "--prefix") o.outprefix = arg();
         else if (a == "--seed") o.seed = std::stoull(arg());
         else if (a == "--filterset") o.filterset = arg();
+        else if (a == "--gpu-stats") o.gpu_stats = arg();
         else if (a == "--count-threshold" || a == "--threshold" || shortarg("-m")) o.count_threshold = (unsigned)std::max(0, std::atoi(arg().c_str()));
         else if (a == "--topk" || a == "--top-k" || shortarg("-K")) { o.topk = std::stoi(arg()); o.nn_threshold = false; }
         else if (a == "--similarity-threshold" || shortarg("-T")) { o.min_similarity = std::atof(arg().c_str()); o.nn_threshold = true; o.topk = -1; }
@@ -704,6 +708,29 @@ void compare_and_emit(Gpus &gpus, const Opts &o, Sketches &sk) {
 
 } // namespace
 
+// ---- --gpu-stats FILE: what the device did, for the operator (the reference only has -v timers on stderr) ----------------
+void write_gpu_stats(Gpus &gpus, const Opts &o) {
+    static const char *cls[D2G_T_NCLASSES] = {"sketch_main", "sketch_boot_or_weighted_elements", "compare_tile_or_candidate_scan", "compare_code_preparation",
+                                               "pack_ascii", "radix_sorts", "neighbour_refine"};
+    std::FILE *fp = xopen(o.gpu_stats, "w");
+    std::fprintf(fp, "{\"library\": \"%s\", \"devices\": [", d2g_version());
+    for (size_t g = 0; g < gpus.size(); ++g) {
+        d2g_ctx *c = gpus.get(g);
+        std::fprintf(fp, "%s{\"device\": %zu, \"kernel_launches\": %llu, \"kernel_ms\": {", g ? ", " : "", g, (unsigned long long)d2g_launch_count(c));
+        for (int k = 0; k < D2G_T_NCLASSES; ++k) {
+            double ms = 0; uint64_t n = 0;
+            chk(d2g_get_timing(c, k, &ms, &n));
+            std::fprintf(fp, "%s\"%s\": {\"ms\": %.3f, \"timed_regions\": %llu}", k ? ", " : "", cls[k], ms, (unsigned long long)n);
+        }
+        std::fprintf(fp, "}}");
+    }
+    std::fprintf(fp, "], \"host_phases_ms\": [");
+    for (size_t i = 0; i < g_timer.phases.size(); ++i)
+        std::fprintf(fp, "%s{\"phase\": \"%s\", \"ms\": %.3f}", i ? ", " : "", g_timer.phases[i].first.c_str(), g_timer.phases[i].second);
+    std::fprintf(fp, "]}\n");
+    xclose(fp, o.gpu_stats);
+}
+
 // ---- `contain` (src/contain_main.cpp:133-301) --------------------------------------------------------------------------------------
 // dashing2 contain [-b] [-p N] [-o OUT] [-F list] DB.kmer64 query...: for every query file, which of each reference's sampled k-mers
 // (the FILE.kmer64 of `sketch --save-kmers`) occur in the query's k-mer stream, and how often.  Coverage = sampled k-mers seen / S, mean depth =
@@ -842,6 +869,7 @@ int main(int argc, char **argv) {
     }
     Gpus gpus;
     gpus.start(o.ngpus);
+    if (!o.gpu_stats.empty()) for (size_t g = 0; g < gpus.size(); ++g) chk(d2g_set_timing(gpus.get(g), 1));
     Sketches sk;
     if (is_cmp && o.presketched) {
         if (o.paths.size() != 1) die("--presketched: pass one stacked sketch file (the reference's multi-file branch is degenerate for panels, SURVEY 8a b9)");
@@ -857,11 +885,13 @@ int main(int argc, char **argv) {
         }
     }
     g_timer.mark("sketches ready / written");
+    (void)0;
     if (is_cmp || !o.cmpout.empty()) {
         if (is_cmp && o.cmpout.empty()) o.cmpout = "-";
         compare_and_emit(gpus, o, sk);
         g_timer.mark("compare + emit");
     }
+    if (!o.gpu_stats.empty()) write_gpu_stats(gpus, o);
     // every output file is closed / flushed; tearing the CUDA context down costs another 0.2-0.5 s and frees nothing the
     // process exit does not free
     for (size_t g = 0; g < gpus.size(); ++g) gpus.get(g);

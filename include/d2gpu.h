@@ -271,6 +271,9 @@ int d2g_cmp_rows_sharded_dev(d2g_ctx *ctx, const d2g_cmp_params *p, const double
  * and rows [row_begin, row_end) are delivered to the sink in row order like d2g_cmp_stream.  Collective. */
 int d2g_cmp_stream_sharded(d2g_ctx *ctx, const d2g_cmp_params *p, const double *local_regs, const double *local_cards,
                            uint64_t local_begin, uint64_t local_n, uint64_t row_begin, uint64_t row_end, d2g_sink_fn sink, void *user);
+/* ... and into a caller buffer holding d2g_cmp_rows_size values (device->host copies overlap the kernels, as in d2g_cmp_rows).  Collective. */
+int d2g_cmp_rows_sharded(d2g_ctx *ctx, const d2g_cmp_params *p, const double *local_regs, const double *local_cards,
+                         uint64_t local_begin, uint64_t local_n, uint64_t row_begin, uint64_t row_end, float *out);
 
 /* ------------------------------------------------------------------------------------------------
  * LSH-assisted top-k neighbour graph (--topk K).  Replaces build_index (src/index_build.cpp:53-165) over

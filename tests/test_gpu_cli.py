@@ -423,3 +423,16 @@ def test_contain_subcommand(case, argv, tmp_path):
         outt = str(tmp_path / "c.txt")
         run(["contain", "-o", outt, db + ".kmer64"] + queries)
         assert open(outt).read().replace(str(tmp_path) + "/", "") == open(expected(case + ".txt")).read()
+
+
+def test_gpu_stats_json(golden_inputs, tmp_path):
+    """--gpu-stats FILE: kernel launches, per-class device times and host phases of the run as JSON (an operator hook, not a reference option)."""
+    import json
+    names, paths = golden_inputs
+    flist = tmp_path / "files.txt"; flist.write_text("\n".join(paths) + "\n")
+    st = str(tmp_path / "stats.json")
+    run(["sketch", "-F", str(flist), "-k31", "-w51", "-S512", "--full-setsketch", "-o", str(tmp_path / "o.stk"), "--cmpout", str(tmp_path / "o.f32"), "--binary-output", "--gpu-stats", st])
+    d = json.load(open(st))
+    dev = d["devices"][0]
+    assert dev["kernel_launches"] > 5 and dev["kernel_ms"]["sketch_main"]["ms"] > 0 and dev["kernel_ms"]["sketch_main"]["timed_regions"] >= 1
+    assert any(p["phase"].startswith("compare") for p in d["host_phases_ms"])
