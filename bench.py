@@ -542,8 +542,13 @@ def main():
         exp = np.array([Lo.d2o_finalize(int((ra[t] > rb[t]).sum()), int((ra[t] < rb[t]).sum()), S, float(ca[t]), float(cb2[t]), 0, K, 0)
                         for t in range(len(ii))], dtype=np.float32)
         pairs_ok = bool(np.array_equal(got.view(np.uint32), exp.view(np.uint32)))
+        # the host-buffer legs produced the same bytes as the resident ones (registers of the first Ge genomes; this rank's rows of the matrix)
+        e2e_regs_ok = bool(torch.equal(h_sig.view(torch.int64), sig[:Ge].cpu().view(torch.int64)))
+        e2e_rows_ok = bool(torch.equal(h_out.view(torch.int32), out.cpu().view(torch.int32)))
         verify = {"genome": int(g), "registers_bit_identical_to_oracle": regs_ok, "cardinality_within_1e-12": card_ok,
-                  "pairs_checked": int(len(ii)), "pairs_bit_identical_to_oracle": pairs_ok}
+                  "pairs_checked": int(len(ii)), "pairs_bit_identical_to_oracle": pairs_ok,
+                  "e2e_registers_equal_resident": e2e_regs_ok, "e2e_rows_equal_resident": e2e_rows_ok}
+        regs_ok = regs_ok and e2e_regs_ok; pairs_ok = pairs_ok and e2e_rows_ok
         if not (regs_ok and card_ok and pairs_ok):
             raise SystemExit("bench.py: outputs differ from the oracle: %s" % json.dumps(verify))
 
