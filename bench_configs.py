@@ -266,9 +266,16 @@ def run(args, bench):
             del regs; torch.cuda.empty_cache()
             nnz = [0]; refined = [0]
 
-            def step():
-                ip, ix, dv = ctx.lsh_topk(h_regs, h_cards, topk)
-                nnz[0] = int(ip[-1]); refined[0] = ctx.stat(0)
+            p5 = ctx.cmp_params(S, n, "symmetric", "similarity", k=K)
+            indptr = np.zeros(n + 1, dtype=np.uint64)
+
+            def step():      # the C entry point itself: host registers in, malloc'ed CSR out (released with d2g_free, not copied again)
+                pi = C.POINTER(C.c_uint32)(); pv = C.POINTER(C.c_float)()
+                rc = ctx.L.d2g_lsh_topk(ctx.h, C.byref(p5), h_regs.ctypes.data, h_cards.ctypes.data, topk, indptr.ctypes.data, C.byref(pi), C.byref(pv))
+                if rc:
+                    raise RuntimeError(ctx.L.d2g_last_error().decode())
+                nnz[0] = int(indptr[-1]); refined[0] = ctx.stat(0)
+                ctx.L.d2g_free(pi); ctx.L.d2g_free(pv)
             # the call is synchronous and host-in / host-out: wall clock == device timeline + copies; events on the stream bracket it too
             ms, launches, clocks, kt = timed_steps(step, flush=False)
             ntab = S + S // 2
