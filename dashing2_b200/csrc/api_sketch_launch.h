@@ -99,7 +99,10 @@ int launch_sketch_windowed_set(d2g_ctx *c, const d2g::SketchArgs &a, const typen
     const d2g::FastAux fx{redo_count, redo_list, kRedoCap};
     {
         KernelTimer kt(c, tcls);
-        if (a.w - a.k + 1 == 21) {
+        if (a.w - a.k + 1 == 21 && a.k == 31 && !getenv("D2G_FAST_NO_K31")) {
+            CU(cudaFuncSetAttribute(d2g::sketch_fast_kernel<21, Consumer, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            d2g::sketch_fast_kernel<21, Consumer, 31><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp, fx);
+        } else if (a.w - a.k + 1 == 21) {
             CU(cudaFuncSetAttribute(d2g::sketch_fast_kernel<21, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             d2g::sketch_fast_kernel<21, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp, fx);
         } else {

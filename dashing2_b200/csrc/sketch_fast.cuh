@@ -56,13 +56,14 @@ __device__ __forceinline__ uint64_t tile_canonical_or_zero(const uint64_t *W, co
     return canonical(tile_kmer(W, b, k), k);
 }
 
-template <int WSZ_T, class Consumer>
+// WSZ_T / K_T: window size (k-mers) and k as compile-time constants (0 = run time); the BASELINE shape k = 31, w = 51 gets both.
+template <int WSZ_T, class Consumer, int K_T = 0>
 __global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
 sketch_fast_kernel(const SketchArgs a, const typename Consumer::Params cp, const FastAux fx) {
     static_assert(!Consumer::kEveryWindow, "the fast windowed kernel serves set sketches only");
     static_assert(SK_THREADS == 256 && SK_PPT == 8, "event compaction assumes 256 threads x 8 windows");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int k = a.k;
+    const int k = K_T ? K_T : a.k;
     const int wsz = WSZ_T ? WSZ_T : (a.w - a.k + 1);
     const int need = a.w;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + 3 * SF_WBYTES);
