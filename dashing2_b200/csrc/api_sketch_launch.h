@@ -65,6 +65,9 @@ int launch_sketch(d2g_ctx *c, const d2g::SketchArgs &a, const typename Consumer:
             CU(cudaFuncSetAttribute(d2g::sketch_kernel<false, Consumer, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             d2g::sketch_kernel<false, Consumer, true><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
         }
+    } else if (!windowed && a.k == 31 && !getenv("D2G_FAST_NO_K31")) {   // the unwindowed BASELINE shape (configs[0]): k = 31 folded into the kernel
+        CU(cudaFuncSetAttribute(d2g::sketch_kernel<false, Consumer, false, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        d2g::sketch_kernel<false, Consumer, false, 31><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);
     } else if (windowed) {
         CU(cudaFuncSetAttribute(d2g::sketch_kernel<true, Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         d2g::sketch_kernel<true, Consumer><<<(unsigned)grid, d2g::SK_THREADS, smem, c->stream>>>(a, cp);

@@ -162,11 +162,11 @@ constexpr int SK_SCAP = 512;   // staged window minima per tile (expected ~2/(ws
 
 // ---- one span of start positions [span_lo, span_hi) -----------------------------------------------------
 // All threads of the CTA; the consumer is initialised by the caller and is flushed at the end of the span.
-template <bool WINDOWED, class Consumer, bool FILTER = false>
+template <bool WINDOWED, class Consumer, bool FILTER = false, int K_T = 0>
 __device__ __forceinline__ void sketch_span(const SketchArgs &a, Consumer &cons, uint64_t *W, uint32_t *M, uint64_t *score, uint64_t *stage, int *scount,
                                             const uint64_t span_lo, const uint64_t span_hi) {
-    const int k = a.k;
-    const int need = WINDOWED ? a.w : a.k;           // bases a start position needs to its right
+    const int k = K_T ? K_T : a.k;                   // K_T: k as a compile-time constant (masks and shift counts fold)
+    const int need = WINDOWED ? a.w : k;           // bases a start position needs to its right
     const int wsz = WINDOWED ? (a.w - a.k + 1) : 1;  // k-mers per window
     // first record whose end lies beyond span_lo (records are sorted by offset)
     uint64_t lo = 0, hi = a.n_rec;
@@ -386,7 +386,7 @@ __device__ __forceinline__ SketchSmem sketch_smem_carve(unsigned char *smem_raw,
     return s;
 }
 
-template <bool WINDOWED, class Consumer, bool FILTER = false>
+template <bool WINDOWED, class Consumer, bool FILTER = false, int K_T = 0>
 __global__ void __launch_bounds__(SK_THREADS, Consumer::kMinBlocks)
 sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -397,7 +397,7 @@ sketch_kernel(const SketchArgs a, const typename Consumer::Params cp) {
     const uint64_t span_lo = a.pos_base + (uint64_t)blockIdx.x * a.span;
     const uint64_t span_hi = min(span_lo + a.span, a.pos_end);
     if (span_lo >= span_hi) return;
-    sketch_span<WINDOWED, Consumer, FILTER>(a, cons, s.W, s.M, s.score, s.stage, s.scount, span_lo, span_hi);
+    sketch_span<WINDOWED, Consumer, FILTER, K_T>(a, cons, s.W, s.M, s.score, s.stage, s.scount, span_lo, span_hi);
 }
 
 // The exact kernel over a LIST of tiles: tile_list[i] is the first start position of a tile of SK_TILE positions that the fast
