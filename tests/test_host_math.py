@@ -43,3 +43,16 @@ def test_make_compressed_host_matches_oracle():
     assert L.d2g_make_compressed(flat.ctypes.data, None, 3, 8, 1.0, 0, C.byref(a), C.byref(b), out.ctypes.data, C.byref(used)) == 0
     oreg, trunc, oa, ob = O.make_compressed(flat, 1, False)
     assert used.value == trunc and np.array_equal(out, oreg)
+
+
+def test_bench_entry_points_parse():
+    """bench.py and its per-config module import and parse their arguments without a GPU (the driver calls them by contract)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--config" in r.stdout and "--impl" in r.stdout
+    sys.path.insert(0, root)
+    import bench_configs
+    assert callable(bench_configs.run)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--config", "4"], capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA device" in (r.stderr + r.stdout)      # fails loudly without a GPU, no CPU fallback
